@@ -1,0 +1,87 @@
+// common.cuh -- shared device helpers for the sm_100a codec kernels.
+// The same sources also compile with g++ under tests/emu/simt_emu.h (MSC_EMU) for the CPU test-suite.
+#pragma once
+#ifndef MSC_EMU
+#include <cuda_runtime.h>
+#include <stdint.h>
+#endif
+
+namespace msc {
+
+// Status codes shared with the C ABI (include/mscomp/general.h).
+enum : int { ST_OK = 0, ST_ARG = -2, ST_DATA = -3, ST_MEM = -4, ST_BUF = -5 };
+
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ int lane_id() { return (int)(threadIdx.x & 31); }
+
+// 16-byte streaming load (read-once data: do not allocate in L1).
+__device__ __forceinline__ uint4 ld_stream16(const void* p)
+{
+#ifndef MSC_EMU
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+#else
+    return *reinterpret_cast<const uint4*>(p);
+#endif
+}
+__device__ __forceinline__ void st_stream16(void* p, const uint4& v)
+{
+#ifndef MSC_EMU
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+#else
+    *reinterpret_cast<uint4*>(p) = v;
+#endif
+}
+
+// Inclusive warp prefix sum.
+__device__ __forceinline__ int warp_incl_scan(int v)
+{
+    const int lane = lane_id();
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(FULL, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+
+// Warp-cooperative copy of `n` bytes global/shared -> global, arbitrary alignment of both sides.
+// Uses 16-byte stores on the destination-aligned body and builds each vector from byte loads only at the
+// ragged ends; the body loads are 4-byte aligned-down words recombined with a funnel shift.
+__device__ __forceinline__ void warp_copy_bytes(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n)
+{
+    const int lane = lane_id();
+    // head: bring dst to 16-byte alignment
+    uint32_t head = (uint32_t)((16u - ((uintptr_t)dst & 15u)) & 15u);
+    if (head > n) head = n;
+    if ((uint32_t)lane < head) dst[lane] = src[lane];
+    dst += head; src += head; n -= head;
+    const uint32_t nvec = n >> 4;
+    const uint32_t sh = (uint32_t)((uintptr_t)src & 3u);
+    const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src - sh);
+    for (uint32_t v = lane; v < nvec; v += 32) {
+        const uint32_t* p = s32 + 4 * v;
+        uint32_t w0 = p[0], w1 = p[1], w2 = p[2], w3 = p[3];
+        uint4 o;
+        if (sh == 0) { o = make_uint4(w0, w1, w2, w3); }
+        else {
+            uint32_t w4 = p[4];
+            o.x = __funnelshift_r(w0, w1, 8 * sh); o.y = __funnelshift_r(w1, w2, 8 * sh);
+            o.z = __funnelshift_r(w2, w3, 8 * sh); o.w = __funnelshift_r(w3, w4, 8 * sh);
+        }
+        *reinterpret_cast<uint4*>(dst + 16 * v) = o;
+    }
+    const uint32_t done = nvec << 4;
+    if (done + lane < n) dst[done + lane] = src[done + lane];
+}
+
+} // namespace msc
+
+// Dynamic shared memory declaration usable by both builds.
+#ifndef MSC_EMU
+#define MSC_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#else
+#define MSC_DYN_SMEM(name) unsigned char* name = emu::dyn_smem()
+#endif

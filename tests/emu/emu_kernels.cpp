@@ -1,0 +1,17 @@
+// emu_kernels.cpp -- TEST INFRASTRUCTURE: compiles the CUDA kernel sources for the CPU through simt_emu.h and
+// exposes one C entry point per kernel so that pytest can drive them with host buffers (see tests/test_emu_*.py).
+#include "simt_emu.h"
+#include "../../ms-compress_b200/csrc/kernels/lznt1_decode.cuh"
+
+using emu::dim3e;
+
+extern "C" {
+
+void emu_lznt1_decode(const uint8_t* in, uint64_t in_len, const uint64_t* chunk_off, uint32_t nchunks,
+                      uint8_t* out, uint32_t* out_size, int32_t* status, uint32_t grid)
+{
+    emu::launch(msc::lznt1_decode_kernel, dim3e(grid), dim3e(msc::LZNT1_WARPS_PER_BLOCK * 32),
+                in, in_len, chunk_off, nchunks, out, out_size, status);
+}
+
+}
