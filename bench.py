@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark (see BASELINE.json): MB/s of encode+decode, HBM-roofline fraction, CPU reference beside it.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU; torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU implementation on the host cores
+
+Workload at N=1 = BASELINE.json configs[1]: LZNT1 encode+decode of a 1 GiB synthetic text stream cut into 4 KiB chunks
+(1024 x 1 MiB blocks of generator `text`, seeds 42+i).  One "step" = one encode of the whole stream plus one
+decode of the result, device-resident (inputs already in HBM when the timed region starts).  With N > 1 every rank holds its
+own 1 GiB shard (weak scaling; units are independent) and the only exchange is one all-gather of the per-rank
+output sizes per step.  `e2e` is the same round trip through the C ABI (lznt1_compress / lznt1_decompress) with pinned HOST
+buffers, host<->device copies inside the timed region.  Extra keys report the other formats once their kernels are linked.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MB = 1e6
+BLOCK = 1 << 20
+METRIC = "LZNT1 encode+decode throughput (uncompressed MB/s, 1 GiB synthetic text stream as 4 KiB chunks per GPU)"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own implementation (oracle/_ref, compiled from the unmodified sources) or, if that file is
+# absent, the oracle port -- timed on the host cores, one process per core (threads do not scale).
+# ------------------------------------------------------------------------------------------------------------------
+def _cpu_lib():
+    ref = os.path.join(ROOT, "oracle", "_ref", "libMSCompression.so")
+    if os.path.exists(ref):
+        return ref, "", "reference"
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+    return os.path.join(ROOT, "oracle", "liboracle.so"), "orc_", "port"
+
+
+def _cpu_worker(args):
+    path, prefix, fmt, seed0, nblocks, reps = args
+    import mscompress_b200 as ms
+    lib = ctypes.CDLL(path)
+    comp_f, dec_f = getattr(lib, prefix + fmt + "_compress"), getattr(lib, prefix + fmt + "_decompress")
+    blocks = [ms.generate("text", BLOCK, seed0 + i) for i in range(nblocks)]
+    cap = BLOCK + BLOCK // 8 + 4096
+    cbuf, dbuf = ctypes.create_string_buffer(cap), ctypes.create_string_buffer(BLOCK)
+    t_c = t_d = 0.0
+    csize = 0
+    for _ in range(reps):
+        for b in blocks:
+            n = ctypes.c_size_t(cap)
+            t0 = time.perf_counter()
+            rc = comp_f(b, ctypes.c_size_t(BLOCK), cbuf, ctypes.byref(n))
+            t1 = time.perf_counter()
+            m = ctypes.c_size_t(BLOCK)
+            rc2 = dec_f(cbuf, n, dbuf, ctypes.byref(m))
+            t2 = time.perf_counter()
+            assert rc == 0 and rc2 == 0 and m.value == BLOCK
+            t_c += t1 - t0
+            t_d += t2 - t1
+            csize += n.value
+    return nblocks * reps * BLOCK, t_c, t_d, csize
+
+
+def cpu_measure(fmt="lznt1", blocks_per_proc=8, reps=1, procs=None):
+    """Aggregate MB/s of compress+decompress of 1 MiB text blocks over `procs` worker processes."""
+    import multiprocessing as mp
+    path, prefix, kind = _cpu_lib()
+    procs = procs or (os.cpu_count() or 1)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(procs) as pool:
+        pool.map(_cpu_worker, [(path, prefix, fmt, 7, 1, 1)] * procs)                 # warm the workers
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_worker, [(path, prefix, fmt, 42 + p * blocks_per_proc, blocks_per_proc, reps) for p in range(procs)])
+        wall = time.perf_counter() - t0
+    total = sum(r[0] for r in res)
+    tc, td = sum(r[1] for r in res), sum(r[2] for r in res)
+    return {
+        "value": total / MB / wall, "unit": "MB/s", "cores": procs, "kind": kind,
+        "sample": "%d processes x %d x 1 MiB text blocks, %s compress+decompress via %s" % (procs, blocks_per_proc * reps, fmt, os.path.basename(path)),
+        "compress_MBps_per_core": total / MB / tc * 1.0, "decompress_MBps_per_core": total / MB / td * 1.0,
+        "ratio": sum(r[3] for r in res) / total, "wall_s": wall,
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    vals = []
+    meas = None
+    for i in range(args.warmup + args.steps):
+        meas = cpu_measure("lznt1", blocks_per_proc=16, reps=1)
+        if i >= args.warmup:
+            vals.append(meas["value"])
+    v = statistics.mean(vals)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "MB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * meas["wall_s"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "LZNT1 encode+decode, 1 GiB synthetic text stream as 4 KiB chunks (BASELINE.json configs[1]); CPU arm: bounded sample per step"},
+        "cpu_baseline": {"value": v, "unit": "MB/s", "cores": meas["cores"], "kind": meas["kind"], "sample": meas["sample"]},
+        "e2e": {"value": v, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# clocks sampler
+# ------------------------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.samples, self.stop = index, [], False
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop:
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.samples.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = [int(s[0]) for s in self.samples if s[0].isdigit()]
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import numpy as np
+    import torch
+    import mscompress_b200 as ms
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this framework has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    nblocks = args.mib
+    U = nblocks * BLOCK
+    host = torch.empty(U, dtype=torch.uint8).pin_memory()
+    ms.generate_batch_into(host.numpy(), BLOCK, nblocks, 42 + rank * nblocks, "text")
+    d_in = host.to(dev, non_blocking=True)
+    ctx = ms.GpuContext(local)
+    nchunks = U // 4096
+    d_comp = torch.empty(U + 2 * nchunks + 64, dtype=torch.uint8, device=dev)
+    d_off = torch.empty(nchunks + 1, dtype=torch.int64, device=dev)
+    d_out = torch.empty(U, dtype=torch.uint8, device=dev)
+    d_res_c = torch.zeros(ms.RESULT_BYTES, dtype=torch.uint8, device=dev)
+    d_res_d = torch.zeros(ms.RESULT_BYTES, dtype=torch.uint8, device=dev)
+    sizes_all = torch.zeros(world, dtype=torch.int64, device=dev)
+
+    def step(events=None):
+        if events:
+            events[0].record()
+        ctx.lznt1_compress(d_in, d_comp, d_off, d_res_c)
+        if events:
+            events[1].record()
+        # the compressed stream stays resident; its length lives in d_off[nchunks] / d_res_c (the decoder takes the buffer bound)
+        ctx.lznt1_decompress(d_comp, d_off, nchunks, d_out, d_res_d)
+        if events:
+            events[2].record()
+        if dist is not None:   # the single collective -- all-gather of the per-rank compressed sizes
+            dist.all_gather_into_tensor(sizes_all, d_off[nchunks:nchunks + 1])
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    C = ms.parse_result(d_res_c)["bytes"]
+    rd = ms.parse_result(d_res_d)
+    assert rd["status"] == 0 and rd["bytes"] == U and torch.equal(d_out, d_in), "round trip mismatch"
+
+    launches0 = ctx.launches()
+    ctx.profile(True)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    with Clocks(local) as clk:
+        start.record()
+        for k in range(args.steps):
+            step(ev[k])
+        end.record()
+        torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    total_ms = start.elapsed_time(end)
+    prof = ctx.profile_report()
+    ctx.profile(False)
+    launches = ctx.launches() - launches0
+    enc_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in ev)
+    dec_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in ev)
+    t = torch.tensor([total_ms, enc_ms, dec_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, enc_ms, dec_ms = t.tolist()
+    ms_per_step = total_ms / args.steps
+    value = world * U / MB / (ms_per_step / 1e3)
+
+    # ---- e2e through the C ABI with pinned host buffers ----
+    h_comp = torch.empty(U + 2 * nchunks + 64, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(U, dtype=torch.uint8).pin_memory()
+    L = ms.lib()
+    e2e_steps = max(1, min(args.steps, 3))
+    e2e_t = []
+    csz = 0
+    for k in range(1 + e2e_steps):
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        n = ctypes.c_size_t(h_comp.numel())
+        st = L.lznt1_compress(host.data_ptr(), U, h_comp.data_ptr(), ctypes.byref(n))
+        m = ctypes.c_size_t(U)
+        st2 = L.lznt1_decompress(h_comp.data_ptr(), n.value, h_out.data_ptr(), ctypes.byref(m))
+        dt = time.perf_counter() - t0
+        assert st == 0 and st2 == 0 and m.value == U, (st, st2)
+        csz = n.value
+        if k > 0:
+            e2e_t.append(dt)
+    assert torch.equal(h_out, host) and csz == C
+    te = torch.tensor([statistics.mean(e2e_t)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = peaks()
+    steps = args.steps
+    kern = {}
+    alg = {"lznt1_encode_kernel": U + C, "lznt1_decode_kernel": C + U, "gather_slots_kernel": 2 * C}
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp))
+    for name, (calls, ms_tot) in prof.items():
+        per = ms_tot / max(calls, 1)
+        e = {"calls_per_step": calls / steps, "ms_per_launch": per}
+        if name in alg and per > 0:
+            e["achieved_GBps"] = alg[name] / 1e9 / (per / 1e3)
+            e["frac"] = e["achieved_GBps"] / peak
+        kern[name] = e
+    dom = max((k for k in kern if k in alg), key=lambda k: kern[k]["ms_per_launch"] * kern[k]["calls_per_step"])
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["achieved_GBps"], "peak": peak, "unit": "GB/s", "frac": kern[dom]["frac"],
+                "traffic": traffic.get(dom), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg[dom], "note": "achieved = (uncompressed + compressed bytes) / CUDA-event kernel time (SURVEY.md 8d)"}
+    cpu = cpu_measure("lznt1", blocks_per_proc=8, reps=1) if world == 1 else None
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "MB/s", "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "LZNT1 encode+decode, %d MiB synthetic text stream as 4 KiB chunks per GPU (BASELINE.json configs[1])" % nblocks,
+                   "chunks_per_gpu": nchunks, "compressed_ratio": C / U, "l2": "inputs larger than L2 (1 GiB in, %.2f GiB compressed, 126 MB L2); no flush needed" % (C / 2**30),
+                   "collective": "all_gather of per-rank compressed size (8 B/rank) per step" if world > 1 else "none (N=1)"},
+        "gpu_launches": launches,
+        "encode_MBps": world * U / MB / (enc_ms / 1e3), "decode_MBps": world * U / MB / (dec_ms / 1e3),
+        "encode_ms": enc_ms, "decode_ms": dec_ms,
+        "roofline": roofline, "kernels": kern,
+        "decode_roofline": {"bound": "hbm", "achieved": kern.get("lznt1_decode_kernel", {}).get("achieved_GBps"), "peak": peak, "unit": "GB/s",
+                            "frac": kern.get("lznt1_decode_kernel", {}).get("frac"), "target_frac": 0.40},
+        "e2e": {"value": world * U / MB / e2e_s, "unit": "MB/s", "h2d_bytes_per_step": U + C, "d2h_bytes_per_step": C + U,
+                "api": "lznt1_compress + lznt1_decompress (C ABI, pinned host buffers)", "ms_per_step": 1e3 * e2e_s},
+        "clocks": clk.summary(),
+    }
+    if cpu:
+        line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line["cpu_baseline_detail"] = {k: cpu[k] for k in ("compress_MBps_per_core", "decompress_MBps_per_core", "ratio")}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mib", type=int, default=1024, help="MiB of uncompressed data per GPU (default: the 1 GiB of BASELINE.json configs[1])")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,27 @@
+/*
+ * mscomp.h -- format-dispatching one-shot API of the B200-native libMSCompression.
+ *
+ * Replaces the reference's include/mscomp.h one-shot entry points
+ *   ms_compress            (reference include/mscomp.h:59,  src/mscomp.cpp:113-117)
+ *   ms_decompress          (reference include/mscomp.h:88,  src/mscomp.cpp:128-132)
+ *   ms_max_compressed_size (reference include/mscomp.h:99,  src/mscomp.cpp:96-102)
+ * Same names, argument order and status conventions: *out_len is the capacity of `out` on entry and the number
+ * of bytes produced on success; it is unspecified on failure.  Buffers are HOST memory owned by the caller;
+ * the call stages them through the GPU (see mscomp_gpu.h for the device-resident batch interface).
+ * Every call is re-entrant; each calling thread gets its own CUDA stream and scratch.
+ * There is no CPU implementation behind these functions: without a usable CUDA device they return
+ * MSCOMP_MEM_ERROR after printing one diagnostic line to stderr.
+ */
+#ifndef MSCOMPRESSION_H
+#define MSCOMPRESSION_H
+#include "mscomp/general.h"
+
+EXTERN_C_START
+
+MSCOMPAPI MSCompStatus ms_compress(MSCompFormat format, const_bytes in, size_t in_len, bytes out, size_t* out_len);
+MSCOMPAPI MSCompStatus ms_decompress(MSCompFormat format, const_bytes in, size_t in_len, bytes out, size_t* out_len);
+/* Upper bound of ms_compress output for in_len input bytes; (size_t)-1 for an invalid format. */
+MSCOMPAPI size_t ms_max_compressed_size(MSCompFormat format, size_t in_len);
+
+EXTERN_C_END
+#endif

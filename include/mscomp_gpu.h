@@ -1,0 +1,88 @@
+/*
+ * mscomp_gpu.h -- device-resident batch interface of the B200-native libMSCompression (not in the reference).
+ *
+ * The reference is host-memory-in / host-memory-out (include/mscomp.h:59,:88); the six one-shot functions of this
+ * library (lznt1.h, xpress.h, xpress_huff.h) are thin wrappers that stage host buffers through the functions
+ * below.  Callers that already hold their data in HBM use these directly: all `d_` pointers are DEVICE pointers,
+ * every call is asynchronous on the context's CUDA stream, results (sizes / statuses) are written to device
+ * memory and are valid after mscomp_gpu_synchronize() or any later work on the same stream.
+ *
+ * Data-parallel units: LZNT1 -- the 4 KiB chunk; Xpress-Huffman and plain Xpress -- the
+ * independent buffer (its own stream, as WIM stores them).  Nothing here falls back to the CPU.
+ *
+ * Alignment: kernels read 16-byte granules that contain at least one valid byte, so buffers may start and end at
+ * any address; best throughput with 16-byte aligned bases.
+ */
+#ifndef MSCOMP_GPU_H
+#define MSCOMP_GPU_H
+#include "mscomp/general.h"
+
+EXTERN_C_START
+
+typedef struct mscomp_gpu_ctx mscomp_gpu_ctx;
+
+/* Summary written by the stream-level calls. */
+typedef struct mscomp_gpu_result {
+    uint64_t bytes;        /* total bytes produced */
+    int32_t  status;       /* MSCOMP_OK or the status of the first failing unit */
+    uint32_t first_bad;    /* index of the first failing unit (valid when status < 0) */
+    uint32_t short_units;  /* LZNT1 decode: number of non-final chunks that produced fewer than 4096 bytes */
+    uint32_t reserved;
+} mscomp_gpu_result;
+
+/* Per-buffer descriptors of a batch (device arrays of length count). */
+typedef struct mscomp_gpu_batch {
+    uint32_t        count;
+    const uint64_t* d_in_off;    /* byte offset of buffer i inside d_in */
+    const uint32_t* d_in_len;    /* its length */
+    const uint64_t* d_out_off;   /* where its output starts inside d_out */
+    const uint32_t* d_out_cap;   /* output capacity */
+    uint32_t*       d_out_len;   /* OUT: bytes produced */
+    int32_t*        d_status;    /* OUT: MSCompStatus per buffer */
+} mscomp_gpu_batch;
+
+/* cuda_stream: a cudaStream_t passed as void* (NULL = the context creates and owns a non-blocking stream).
+ * Returns NULL when the device cannot be used. */
+MSCOMPAPI mscomp_gpu_ctx* mscomp_gpu_create(int device, void* cuda_stream);
+MSCOMPAPI void            mscomp_gpu_destroy(mscomp_gpu_ctx* ctx);
+MSCOMPAPI MSCompStatus    mscomp_gpu_synchronize(mscomp_gpu_ctx* ctx);
+/* Kernels launched through this context so far (the benchmark reports it as gpu_launches). */
+MSCOMPAPI uint64_t        mscomp_gpu_kernel_launches(const mscomp_gpu_ctx* ctx);
+/* Optional per-kernel timing: CUDA events on the context's stream around every launch (at most 2048 launches between
+ * reports).  mscomp_gpu_profile_report synchronises and writes one "kernel_name calls total_ms" line per kernel. */
+MSCOMPAPI void            mscomp_gpu_profile_enable(mscomp_gpu_ctx* ctx, int on);
+MSCOMPAPI size_t          mscomp_gpu_profile_report(mscomp_gpu_ctx* ctx, char* buf, size_t cap);
+
+/* ---- LZNT1: one logical stream of 4 KiB chunks ------------------------------------------------------------ */
+/* Device path behind lznt1_compress (reference src/lznt1_compress.cpp:233-273).  out_cap must be at least
+ * lznt1_max_compressed_size(in_len).  d_chunk_off (may be NULL) receives ceil(in_len/4096)+1 offsets: the byte
+ * offset of every chunk header in d_out, then the total.  d_result->bytes = total compressed bytes. */
+MSCOMPAPI MSCompStatus mscomp_gpu_lznt1_compress(mscomp_gpu_ctx* ctx, const uint8_t* d_in, size_t in_len,
+                                                 uint8_t* d_out, size_t out_cap, uint64_t* d_chunk_off,
+                                                 mscomp_gpu_result* d_result);
+/* Device path behind lznt1_decompress (reference src/lznt1_decompress.cpp:122-209, :37-121).  d_chunk_off[i] is
+ * the offset of chunk i's 2-byte header in d_in (the format stores no index: take it from
+ * mscomp_gpu_lznt1_compress, or from a walk over the headers as the one-shot wrapper does).  Chunk i is written to
+ * d_out + 4096*i, so d_out needs 4096*nchunks bytes; the stream is contiguous when d_result->short_units == 0
+ * (always true for streams made by the one-shot compressors).  d_chunk_size / d_chunk_status (may be NULL)
+ * receive the per-chunk byte counts and statuses. */
+MSCOMPAPI MSCompStatus mscomp_gpu_lznt1_decompress(mscomp_gpu_ctx* ctx, const uint8_t* d_in, size_t in_len,
+                                                   const uint64_t* d_chunk_off, uint32_t nchunks, uint8_t* d_out,
+                                                   uint32_t* d_chunk_size, int32_t* d_chunk_status,
+                                                   mscomp_gpu_result* d_result);
+
+/* ---- Xpress-Huffman and plain Xpress: batches of independent buffers ----------------------------------------- */
+/* Device paths behind xpress_huff_compress / _decompress (reference src/xpress_huff_compress.cpp:247-331,
+ * src/xpress_huff_decompress.cpp:136-162) and xpress_compress / _decompress (src/xpress_compress.cpp:240-347,
+ * src/xpress_decompress.cpp:405-462).  Each buffer is a complete stream of the format. */
+MSCOMPAPI MSCompStatus mscomp_gpu_xpress_huff_compress_batch(mscomp_gpu_ctx* ctx, const uint8_t* d_in, uint8_t* d_out,
+                                                             const mscomp_gpu_batch* batch);
+MSCOMPAPI MSCompStatus mscomp_gpu_xpress_huff_decompress_batch(mscomp_gpu_ctx* ctx, const uint8_t* d_in, uint8_t* d_out,
+                                                               const mscomp_gpu_batch* batch);
+MSCOMPAPI MSCompStatus mscomp_gpu_xpress_compress_batch(mscomp_gpu_ctx* ctx, const uint8_t* d_in, uint8_t* d_out,
+                                                        const mscomp_gpu_batch* batch);
+MSCOMPAPI MSCompStatus mscomp_gpu_xpress_decompress_batch(mscomp_gpu_ctx* ctx, const uint8_t* d_in, uint8_t* d_out,
+                                                          const mscomp_gpu_batch* batch);
+
+EXTERN_C_END
+#endif

@@ -1,0 +1,324 @@
+"""mscompress_b200 -- Python binding of the B200-native libMSCompression (test / benchmark convenience).
+
+The product is the C-ABI shared library `lib/libMSCompression.so` (CUDA kernels for sm_100a + the reference's
+`ms_compress` / `ms_decompress` / per-format one-shot functions, see include/*.h).  This module only binds it:
+
+* `OpenSrc`            -- the same class the reference's Python harness exposes (test/compressors.py:214-314):
+                          `OpenSrc(format).Compress(data)`, `.Decompress(data)`, `.MaxCompressedSize(n)`, host bytes in / out.
+* `GpuContext`         -- the device-resident batch interface (include/mscomp_gpu.h) over torch CUDA tensors; torch
+                          supplies device memory and the stream, nothing else.
+* `generate(...)`      -- the synthetic byte streams of SURVEY.md section 8(d).
+
+There is no CPU fallback: if the library has not been built, loading raises.
+"""
+import ctypes
+import os
+import struct
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_DIR = os.path.join(_HERE, "lib")
+LIB_PATH = os.path.join(LIB_DIR, "libMSCompression.so")
+GEN_PATH = os.path.join(LIB_DIR, "libmsdatagen.so")
+
+MSCOMP_OK, MSCOMP_ARG_ERROR, MSCOMP_DATA_ERROR, MSCOMP_MEM_ERROR, MSCOMP_BUF_ERROR = 0, -2, -3, -4, -5
+
+
+class CompressionFormat:
+    """MSCompFormat (include/mscomp/general.h); names follow the reference's test/compressors.py."""
+    NoCompression = 0
+    LZNT1 = 2
+    Xpress = 3
+    XpressHuffman = 4
+
+
+FORMAT_NAMES = {CompressionFormat.LZNT1: "lznt1", CompressionFormat.Xpress: "xpress", CompressionFormat.XpressHuffman: "xpress_huff"}
+
+_lib = None
+_gen = None
+
+
+class MSCompError(Exception):
+    def __init__(self, func, status):
+        super().__init__("%s failed: %d" % (func, status))
+        self.status = status
+
+
+def build(force=False, verbose=False):
+    """Compile the native libraries in-tree (nvcc, sm_100a)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_mscomp_build", os.path.join(_HERE, "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.build(force=force, verbose=verbose)
+
+
+def lib():
+    """The loaded libMSCompression.so (ctypes).  Raises if it has not been built -- there is no other code path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("mscompress_b200: %s is missing -- run `python __graft_entry__.py build` (nvcc); "
+                              "this package has no CPU or PyTorch fallback" % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        vp, sz, i32, u32, u64 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint64
+        psz = ctypes.POINTER(ctypes.c_size_t)
+        for name in ("lznt1", "xpress", "xpress_huff"):
+            if not hasattr(L, name + "_compress"):
+                continue
+            for op in ("compress", "decompress"):
+                f = getattr(L, "%s_%s" % (name, op))
+                f.restype, f.argtypes = i32, [vp, sz, vp, psz]
+            f = getattr(L, name + "_max_compressed_size")
+            f.restype, f.argtypes = sz, [sz]
+        L.ms_compress.restype, L.ms_compress.argtypes = i32, [i32, vp, sz, vp, psz]
+        L.ms_decompress.restype, L.ms_decompress.argtypes = i32, [i32, vp, sz, vp, psz]
+        L.ms_max_compressed_size.restype, L.ms_max_compressed_size.argtypes = sz, [i32, sz]
+        L.mscomp_gpu_create.restype, L.mscomp_gpu_create.argtypes = vp, [i32, vp]
+        L.mscomp_gpu_destroy.restype, L.mscomp_gpu_destroy.argtypes = None, [vp]
+        L.mscomp_gpu_synchronize.restype, L.mscomp_gpu_synchronize.argtypes = i32, [vp]
+        L.mscomp_gpu_kernel_launches.restype, L.mscomp_gpu_kernel_launches.argtypes = u64, [vp]
+        L.mscomp_gpu_profile_enable.restype, L.mscomp_gpu_profile_enable.argtypes = None, [vp, i32]
+        L.mscomp_gpu_profile_report.restype, L.mscomp_gpu_profile_report.argtypes = sz, [vp, vp, sz]
+        L.mscomp_gpu_lznt1_compress.restype, L.mscomp_gpu_lznt1_compress.argtypes = i32, [vp, vp, sz, vp, sz, vp, vp]
+        L.mscomp_gpu_lznt1_decompress.restype, L.mscomp_gpu_lznt1_decompress.argtypes = i32, [vp, vp, sz, vp, u32, vp, vp, vp, vp]
+        for fmt in ("xpress_huff", "xpress"):
+            for op in ("compress", "decompress"):
+                if not hasattr(L, "mscomp_gpu_%s_%s_batch" % (fmt, op)):
+                    continue
+                f = getattr(L, "mscomp_gpu_%s_%s_batch" % (fmt, op))
+                f.restype, f.argtypes = i32, [vp, vp, vp, vp]
+        _lib = L
+    return _lib
+
+
+# ---- host-pointer API, mirroring the reference's ctypes harness -------------------------------------------------
+
+def _as_cbuf(data):
+    """(address, length, keepalive) of a bytes-like object or a numpy / torch CPU uint8 array, without copying."""
+    if hasattr(data, "data_ptr"):                       # torch tensor (host, possibly pinned)
+        return data.data_ptr(), data.numel() * data.element_size(), data
+    if hasattr(data, "ctypes") and hasattr(data, "nbytes"):   # numpy
+        return data.ctypes.data, data.nbytes, data
+    if isinstance(data, (bytes, bytearray)):
+        buf = (ctypes.c_char * len(data)).from_buffer_copy(data) if isinstance(data, bytes) else (ctypes.c_char * len(data)).from_buffer(data)
+        return ctypes.addressof(buf), len(data), buf
+    mv = memoryview(data)
+    buf = (ctypes.c_char * mv.nbytes).from_buffer_copy(mv.tobytes())
+    return ctypes.addressof(buf), mv.nbytes, buf
+
+
+class OpenSrc:
+    """One-shot codec object: same shape as the reference harness' `OpenSrc` (test/compressors.py:214-314)."""
+
+    def __init__(self, format):
+        self.format = int(format)
+
+    def MaxCompressedSize(self, input_len):
+        val = lib().ms_max_compressed_size(self.format, input_len)
+        if val == 0xFFFFFFFFFFFFFFFF:
+            raise ValueError("invalid format")
+        return val
+
+    def Compress(self, input, output_buf=None):
+        addr, n, keep = _as_cbuf(input)
+        cap = self.MaxCompressedSize(n) + 16 if output_buf is None else len(output_buf)
+        out = ctypes.create_string_buffer(max(cap, 1)) if output_buf is None else (ctypes.c_char * cap).from_buffer(output_buf)
+        olen = ctypes.c_size_t(cap)
+        st = lib().ms_compress(self.format, addr, n, ctypes.addressof(out), ctypes.byref(olen))
+        if st < 0:
+            raise MSCompError("ms_compress", st)
+        return bytes(out[:olen.value])
+
+    def Decompress(self, input, output_buf=None, out_size=None):
+        addr, n, keep = _as_cbuf(input)
+        if output_buf is None:
+            cap = n * 4 if out_size is None else out_size
+            out = ctypes.create_string_buffer(max(cap, 1))
+        else:
+            cap = len(output_buf)
+            out = (ctypes.c_char * cap).from_buffer(output_buf)
+        olen = ctypes.c_size_t(cap)
+        st = lib().ms_decompress(self.format, addr, n, ctypes.addressof(out), ctypes.byref(olen))
+        if st < 0:
+            raise MSCompError("ms_decompress", st)
+        return bytes(out[:olen.value])
+
+
+OpenSrc.NoCompression = OpenSrc(CompressionFormat.NoCompression)
+OpenSrc.LZNT1 = OpenSrc(CompressionFormat.LZNT1)
+OpenSrc.Xpress = OpenSrc(CompressionFormat.Xpress)
+OpenSrc.XpressHuffman = OpenSrc(CompressionFormat.XpressHuffman)
+
+
+def raw_call(func_name, data, cap):
+    """Call `<func_name>(in, in_len, out, &out_len)` of the library with an explicit capacity; returns (status, bytes|None)."""
+    addr, n, keep = _as_cbuf(data)
+    out = ctypes.create_string_buffer(max(cap, 1))
+    olen = ctypes.c_size_t(cap)
+    st = getattr(lib(), func_name)(addr, n, ctypes.addressof(out), ctypes.byref(olen))
+    return st, (bytes(out[:olen.value]) if st == 0 else None)
+
+
+# ---- device-resident API over torch tensors ------------------------------------------------------------------------
+
+RESULT_BYTES = 24
+
+
+def parse_result(t):
+    """mscomp_gpu_result (include/mscomp_gpu.h) from a 24-byte uint8 tensor; synchronises through .cpu()."""
+    b = bytes(t.cpu().numpy().tobytes())
+    nbytes, status, first_bad, short_units, _ = struct.unpack("<QiIII", b[:RESULT_BYTES])
+    return {"bytes": nbytes, "status": status, "first_bad": first_bad, "short_units": short_units}
+
+
+class Batch(ctypes.Structure):
+    """mscomp_gpu_batch (include/mscomp_gpu.h)."""
+    _fields_ = [("count", ctypes.c_uint32), ("d_in_off", ctypes.c_void_p), ("d_in_len", ctypes.c_void_p),
+                ("d_out_off", ctypes.c_void_p), ("d_out_cap", ctypes.c_void_p), ("d_out_len", ctypes.c_void_p),
+                ("d_status", ctypes.c_void_p)]
+
+
+class GpuContext:
+    """mscomp_gpu_ctx bound to a torch device and to torch's CURRENT stream (so torch.cuda.Event timing sees the kernels)."""
+
+    def __init__(self, device=None):
+        import torch
+        self.torch = torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("mscompress_b200.GpuContext needs a CUDA device (there is no CPU fallback)")
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        with torch.cuda.device(self.device):
+            self.stream = torch.cuda.current_stream()
+            self.handle = lib().mscomp_gpu_create(self.device.index, ctypes.c_void_p(self.stream.cuda_stream))
+        if not self.handle:
+            raise RuntimeError("mscomp_gpu_create failed")
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib().mscomp_gpu_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def launches(self):
+        return int(lib().mscomp_gpu_kernel_launches(self.handle))
+
+    def profile(self, on=True):
+        lib().mscomp_gpu_profile_enable(self.handle, 1 if on else 0)
+
+    def profile_report(self):
+        """{kernel_name: (calls, total_ms)} since profiling was enabled / last reported (synchronises)."""
+        buf = ctypes.create_string_buffer(1 << 16)
+        lib().mscomp_gpu_profile_report(self.handle, ctypes.addressof(buf), len(buf))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, calls, ms = line.split()
+            out[name] = (int(calls), float(ms))
+        return out
+
+    def synchronize(self):
+        st = lib().mscomp_gpu_synchronize(self.handle)
+        if st < 0:
+            raise MSCompError("mscomp_gpu_synchronize", st)
+
+    def _u8(self, n):
+        return self.torch.empty(n, dtype=self.torch.uint8, device=self.device)
+
+    # -- LZNT1 stream --
+    def lznt1_compress(self, d_in, d_out=None, d_chunk_off=None, d_result=None):
+        t = self.torch
+        n = d_in.numel()
+        nchunks = (n + 4095) // 4096
+        if d_out is None:
+            d_out = self._u8(n + 2 * nchunks + 16)
+        if d_chunk_off is None:
+            d_chunk_off = t.empty(nchunks + 1, dtype=t.int64, device=self.device)
+        if d_result is None:
+            d_result = self._u8(RESULT_BYTES)
+        st = lib().mscomp_gpu_lznt1_compress(self.handle, d_in.data_ptr(), n, d_out.data_ptr(), d_out.numel(),
+                                             d_chunk_off.data_ptr(), d_result.data_ptr())
+        if st < 0:
+            raise MSCompError("mscomp_gpu_lznt1_compress", st)
+        return d_out, d_chunk_off, d_result
+
+    def lznt1_decompress(self, d_in, d_chunk_off, nchunks, d_out=None, d_result=None, d_sizes=None, d_status=None, in_len=None):
+        if d_out is None:
+            d_out = self._u8(nchunks * 4096)
+        if d_result is None:
+            d_result = self._u8(RESULT_BYTES)
+        st = lib().mscomp_gpu_lznt1_decompress(self.handle, d_in.data_ptr(), d_in.numel() if in_len is None else in_len,
+                                               d_chunk_off.data_ptr(), nchunks, d_out.data_ptr(),
+                                               d_sizes.data_ptr() if d_sizes is not None else None,
+                                               d_status.data_ptr() if d_status is not None else None, d_result.data_ptr())
+        if st < 0:
+            raise MSCompError("mscomp_gpu_lznt1_decompress", st)
+        return d_out, d_result
+
+    # -- batches of independent buffers (Xpress-Huffman, Xpress) --
+    def make_batch(self, in_off, in_len, out_off, out_cap):
+        """Device descriptor arrays from host sequences; returns (Batch, out_len tensor, status tensor, keepalive)."""
+        t = self.torch
+        dev = self.device
+        a = t.as_tensor(in_off, dtype=t.int64).to(dev)
+        b = t.as_tensor(in_len, dtype=t.int32).to(dev)
+        c = t.as_tensor(out_off, dtype=t.int64).to(dev)
+        d = t.as_tensor(out_cap, dtype=t.int32).to(dev)
+        olen = t.zeros(len(in_len), dtype=t.int32, device=dev)
+        stat = t.zeros(len(in_len), dtype=t.int32, device=dev)
+        batch = Batch(len(in_len), a.data_ptr(), b.data_ptr(), c.data_ptr(), d.data_ptr(), olen.data_ptr(), stat.data_ptr())
+        return batch, olen, stat, (a, b, c, d)
+
+    def run_batch(self, fmt, op, d_in, d_out, batch):
+        """fmt in {'xpress_huff','xpress'}, op in {'compress','decompress'}."""
+        f = getattr(lib(), "mscomp_gpu_%s_%s_batch" % (fmt, op))
+        st = f(self.handle, d_in.data_ptr(), d_out.data_ptr(), ctypes.byref(batch))
+        if st < 0:
+            raise MSCompError(f.__name__, st)
+
+
+# ---- synthetic data ---------------------------------------------------------------------------------
+
+def _genlib():
+    global _gen
+    if _gen is None:
+        if not os.path.exists(GEN_PATH):
+            raise ImportError("mscompress_b200: %s is missing -- run the build" % GEN_PATH)
+        g = ctypes.CDLL(GEN_PATH)
+        for name in ("msgen_text", "msgen_random", "msgen_runs"):
+            getattr(g, name).restype = None
+            getattr(g, name).argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint64]
+        g.msgen_batch.restype = None
+        g.msgen_batch.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_int]
+        _gen = g
+    return _gen
+
+
+KINDS = {"text": 0, "random": 1, "runs": 2}
+
+
+def generate(kind, n, seed=42):
+    """n bytes of generator `kind` ('text' | 'random' | 'runs') as a bytes object."""
+    buf = ctypes.create_string_buffer(max(n, 1))
+    getattr(_genlib(), "msgen_" + kind)(ctypes.addressof(buf), n, seed)
+    return buf.raw[:n]
+
+
+def generate_batch_into(array, each, count, seed0=42, kind="text", threads=None):
+    """Fill a writable contiguous uint8 numpy array with `count` buffers of `each` bytes (buffer i: seed0+i); threaded."""
+    import concurrent.futures as cf
+    g = _genlib()
+    base = array.ctypes.data
+    threads = threads or min(32, os.cpu_count() or 1)
+    per = (count + threads - 1) // threads
+    jobs = [(i, min(per, count - i)) for i in range(0, count, per)]
+
+    def run(job):
+        i, c = job
+        g.msgen_batch(base + i * each, each, c, seed0 + i, KINDS[kind])
+    with cf.ThreadPoolExecutor(threads) as ex:
+        list(ex.map(run, jobs))
+    return array

@@ -1,0 +1,79 @@
+// ctx.cuh -- the GPU context behind mscomp_gpu_ctx: one CUDA stream + grow-only device/pinned scratch.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/mscomp_gpu.h"
+
+enum ScratchId { SC_SLOTS = 0, SC_SIZES, SC_STATUS, SC_OFFS, SC_RESULT, SC_IN, SC_OUT, SC_AUX0, SC_AUX1, SC_AUX2, SC_AUX3, SC_COUNT };
+
+struct mscomp_gpu_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    uint64_t launches = 0;
+    void* scratch[SC_COUNT] = {};
+    size_t scratch_cap[SC_COUNT] = {};
+    void* pinned = nullptr;          // small pinned mailbox for results
+    size_t pinned_cap = 0;
+
+    // ---- optional per-kernel profiling ----
+    static constexpr int kProfMax = 2048;
+    bool prof_on = false;
+    int prof_n = 0;
+    cudaEvent_t* prof_ev = nullptr;          // 2 * kProfMax events, created on first use
+    const char* prof_name[kProfMax];
+    int prof_begin(const char* name)
+    {
+        if (!prof_on || prof_n >= kProfMax) return -1;
+        if (!prof_ev) {
+            prof_ev = new cudaEvent_t[2 * kProfMax];
+            for (int i = 0; i < 2 * kProfMax; ++i) cudaEventCreate(&prof_ev[i]);
+        }
+        const int s = prof_n++;
+        prof_name[s] = name;
+        cudaEventRecord(prof_ev[2 * s], stream);
+        return s;
+    }
+    void prof_end(int s) { if (s >= 0) cudaEventRecord(prof_ev[2 * s + 1], stream); }
+
+    // grow-only device scratch; returns nullptr on allocation failure
+    void* get(ScratchId id, size_t bytes)
+    {
+        if (bytes <= scratch_cap[id]) return scratch[id];
+        cudaStreamSynchronize(stream);              // the old block may still be in use
+        if (scratch[id]) cudaFree(scratch[id]);
+        scratch[id] = nullptr; scratch_cap[id] = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        if (cudaMalloc(&scratch[id], want) != cudaSuccess) { cudaGetLastError(); scratch[id] = nullptr; return nullptr; }
+        scratch_cap[id] = want;
+        return scratch[id];
+    }
+    void* get_pinned(size_t bytes)
+    {
+        if (bytes <= pinned_cap) return pinned;
+        if (pinned) cudaFreeHost(pinned);
+        pinned = nullptr; pinned_cap = 0;
+        if (cudaMallocHost(&pinned, bytes + 256) != cudaSuccess) { cudaGetLastError(); pinned = nullptr; return nullptr; }
+        pinned_cap = bytes + 256;
+        return pinned;
+    }
+};
+
+// Optional per-kernel timing (mscomp_gpu_profile_*): CUDA events recorded on the context's stream around every
+// launch; the benchmark uses it to report each kernel's device time for the roofline figures.
+#define MSC_LAUNCH(ctx, kernel, grid, block, ...)                                                   \
+    do {                                                                                            \
+        const int prof_slot_ = (ctx)->prof_begin(#kernel);                                          \
+        kernel<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__);                                 \
+        ++(ctx)->launches;                                                                          \
+        (ctx)->prof_end(prof_slot_);                                                                \
+    } while (0)
+
+static inline MSCompStatus msc_cuda_status(cudaError_t e, const char* what)
+{
+    if (e == cudaSuccess) return MSCOMP_OK;
+    fprintf(stderr, "libMSCompression(B200): CUDA failure in %s: %s\n", what, cudaGetErrorString(e));
+    return e == cudaErrorMemoryAllocation ? MSCOMP_MEM_ERROR : MSCOMP_ERRNO;
+}

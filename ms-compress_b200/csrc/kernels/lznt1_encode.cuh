@@ -1,0 +1,230 @@
+// lznt1_encode.cuh -- LZNT1 chunk encoder, one 256-thread block per 4 KiB chunk.
+//
+// Replaces the reference's lznt1_compress_chunk (src/lznt1_compress.cpp:49-94), its matcher
+// LZNT1Dictionary::Fill/Find (include/mscomp/LZNT1Dictionary.h:93-106, :114-143) and the per-chunk part of
+// lznt1_compress (:233-273: header, stored-chunk fallback).  Output is byte-identical to the reference:
+// exhaustive longest match among all earlier positions with the same first three bytes, earliest position
+// wins ties, stop at max_len; greedy parse; groups of 8 items behind a flag byte.
+//
+// Key fact: Find(p) is a pure function of (chunk, p), so it is evaluated for ALL positions in
+// parallel; only the greedy walk p += max(1, len[p]) is serial, and it touches one word per match.
+//
+// Stages (all in shared memory):
+//   A  stage the chunk, zero padded
+//   B  counting sort of positions by a 12-bit hash of their first 3 bytes (ascending inside a bucket)
+//   C  all-position match search -> lenoff[p] = len | dist << 16, match bitmap M
+//   D  greedy parse: one thread walks M with find-first-set and records the visited bitmap V
+//   E  every visited position computes its item index k and the number of matches before it from prefix
+//      popcounts of V and V&M:  byte offset = k + (k >> 3) + 1 + matches_before;  flag bits by atomicOr
+//   F  header + payload to the chunk's slot (compaction to a contiguous stream is a separate kernel)
+#pragma once
+#include "common.cuh"
+#include "lznt1_decode.cuh"   // lznt1_shift_limit, LZNT1_CHUNK
+
+namespace msc {
+
+constexpr int LZE_THREADS = 256;
+constexpr int LZE_BUCKETS = 4096;
+constexpr int LZNT1_SLOT = 4112;                 // 2-byte header + <= 4096 payload, rounded up to 16
+
+struct Lznt1EncSmem {
+    __align__(16) uint8_t in[LZNT1_CHUNK + 16];  // zero padded
+    union {
+        uint32_t cnt[LZE_BUCKETS];               // B,C: bucket counts -> end offsets
+        uint8_t out[LZNT1_SLOT];                 // E,F: assembled chunk (aliases cnt, which is dead by then)
+    };
+    uint16_t sorted[LZNT1_CHUNK];                // positions grouped by hash, ascending inside a group
+    uint32_t lenoff[LZNT1_CHUNK];                // len | dist << 16 (0 = no match)
+    uint32_t M[128], V[128], F[128];             // match bitmap, visited bitmap (by position), flag bits (by item)
+    uint16_t prefV[128], prefVM[128];
+    uint16_t goff[LZNT1_CHUNK / 8 + 8];          // byte offset of each group's flag byte
+    uint32_t items, matches, scan_tmp[8];
+};
+
+__device__ __forceinline__ uint32_t lz_load4(const uint8_t* s, int idx)
+{   // unaligned 4-byte read from a 4-byte aligned shared array
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(s) + (idx >> 2);
+    return __funnelshift_r(w[0], w[1], 8 * (idx & 3));
+}
+__device__ __forceinline__ uint32_t lz_hash3(uint32_t x) { return ((x & 0xFFFFFFu) * 0x9E3779B1u) >> 20; }
+
+__global__ void __launch_bounds__(LZE_THREADS)
+lznt1_encode_kernel(const uint8_t* __restrict__ in, uint64_t in_len, uint32_t nchunks,
+                    uint8_t* __restrict__ slots, uint32_t* __restrict__ slot_size)
+{
+    __shared__ Lznt1EncSmem sm;
+    const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (uint32_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        const uint64_t base = (uint64_t)c * LZNT1_CHUNK;
+        const int n = (int)((in_len - base < (uint64_t)LZNT1_CHUNK) ? (in_len - base) : LZNT1_CHUNK);
+        const uint8_t* src = in + base;
+        uint8_t* slot = slots + (uint64_t)c * LZNT1_SLOT;
+
+        // ---- A: stage ------------------------------------------------------------------------------------
+        if ((((uintptr_t)src) & 15u) == 0 && n == LZNT1_CHUNK) {
+            reinterpret_cast<uint4*>(sm.in)[tid] = ld_stream16(src + 16 * tid);
+        } else {
+            for (int i = tid; i < LZNT1_CHUNK; i += LZE_THREADS) sm.in[i] = (i < n) ? src[i] : 0;
+        }
+        if (tid < 16) sm.in[LZNT1_CHUNK + tid] = 0;
+        for (int i = tid; i < LZE_BUCKETS; i += LZE_THREADS) sm.cnt[i] = 0;
+        if (tid < 128) { sm.V[tid] = 0; sm.F[tid] = 0; }
+        __syncthreads();
+
+        // ---- B: counting sort by hash ------------------------------------------------------------------
+        const int npos = n - 2;                      // positions 0..n-3 are indexed (Fill :99)
+        for (int p = tid; p < npos; p += LZE_THREADS) atomicAdd(&sm.cnt[lz_hash3(lz_load4(sm.in, p))], 1u);
+        __syncthreads();
+        {   // exclusive scan of 4096 counts: 16 per thread, then a block scan of the 256 partial sums
+            uint32_t loc[16], sum = 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { loc[i] = sm.cnt[tid * 16 + i]; sum += loc[i]; }
+            int incl = warp_incl_scan((int)sum);
+            if (lane == 31) sm.scan_tmp[warp] = (uint32_t)incl;
+            __syncthreads();
+            uint32_t woff = 0;
+            for (int w = 0; w < warp; ++w) woff += sm.scan_tmp[w];
+            uint32_t run = woff + (uint32_t)incl - sum;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { sm.cnt[tid * 16 + i] = run; run += loc[i]; }
+        }
+        __syncthreads();
+        if (warp == 0) {   // ordered scatter: one warp walks the positions in order, ranks by lane inside a group
+            for (int g = 0; g < npos; g += 32) {
+                const int p = g + lane;
+                const bool on = p < npos;
+                const uint32_t h = on ? lz_hash3(lz_load4(sm.in, p)) : (0x10000u + (uint32_t)lane);
+                const unsigned peers = __match_any_sync(FULL, h);
+                const int rank = __popc(peers & ((1u << lane) - 1));
+                uint32_t b = 0;
+                if (on) { b = sm.cnt[h]; sm.sorted[b + rank] = (uint16_t)p; }
+                __syncwarp();
+                if (on && rank == 0) sm.cnt[h] = b + (uint32_t)__popc(peers);
+                __syncwarp();
+            }
+        }
+        __syncthreads();   // cnt[h] now = end offset of bucket h; begin = cnt[h-1] (0 for h == 0)
+
+        // ---- C: match search for every position ------------------------------------------------------
+        for (int p = tid; p < LZNT1_CHUNK; p += LZE_THREADS) {
+            uint32_t res = 0;
+            if (p > 0 && p < npos) {
+                int S, lim;
+                lznt1_shift_limit(p, S, lim);
+                const int max_len = min(n - p, (1 << S) + 2);       // mask3 (src/lznt1_compress.cpp:51,:66)
+                const uint32_t key = lz_load4(sm.in, p);
+                const uint32_t h = lz_hash3(key);
+                int k = (h == 0) ? 0 : (int)sm.cnt[h - 1];
+                const int e = (int)sm.cnt[h];
+                int best = 0, bj = 0;
+                for (; k < e; ++k) {
+                    const int j = sm.sorted[k];
+                    if (j >= p) break;
+                    if ((lz_load4(sm.in, j) ^ key) & 0xFFFFFFu) continue;
+                    int i = 0;
+                    while (i < max_len) {
+                        const uint32_t d = lz_load4(sm.in, p + i) ^ lz_load4(sm.in, j + i);
+                        if (d) { i += (__ffs((int)d) - 1) >> 3; break; }
+                        i += 4;
+                    }
+                    if (i > max_len) i = max_len;
+                    if (i > best) { best = i; bj = j; if (best == max_len) break; }
+                }
+                if (best >= 3) res = (uint32_t)best | ((uint32_t)(p - bj) << 16);
+            }
+            sm.lenoff[p] = res;
+            const unsigned mm = __ballot_sync(FULL, res != 0);
+            if (lane == 0) sm.M[p >> 5] = mm;
+        }
+        __syncthreads();
+
+        // ---- D: greedy parse (serial over matches) ----------------------------------------------------------
+        if (tid == 0) {
+            int p = 0;
+            uint32_t items = 0, matches = 0;
+            while (p < n) {
+                // next match position >= p
+                int w = p >> 5;
+                uint32_t bits = sm.M[w] & (0xffffffffu << (p & 31));
+                while (!bits && ++w < 128) bits = sm.M[w];
+                int q = bits ? (w * 32 + __ffs((int)bits) - 1) : n;
+                if (q > n) q = n;
+                // literals [p, q) and the match at q are visited
+                const int hi = (q < n) ? q + 1 : q;                 // visited range [p, hi)
+                for (int ww = p >> 5; ww <= ((hi - 1) >> 5) && hi > p; ++ww) {
+                    const int lo_b = max(p, ww * 32) - ww * 32, hi_b = min(hi, ww * 32 + 32) - ww * 32;   // [lo_b, hi_b)
+                    const uint32_t m = (hi_b == 32 ? 0xffffffffu : ((1u << hi_b) - 1)) & (0xffffffffu << lo_b);
+                    sm.V[ww] |= m;
+                }
+                items += (uint32_t)(hi - p);
+                if (q < n) { ++matches; p = q + (int)(sm.lenoff[q] & 0xFFFF); }
+                else p = n;
+            }
+            sm.items = items; sm.matches = matches;
+        }
+        __syncthreads();
+
+        // ---- E: offsets and emission ------------------------------------------------------------------
+        if (warp == 0) {   // exclusive prefix popcounts over the 128 bitmap words (4 per lane)
+            uint32_t a[4], b[4], sa = 0, sb = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t v = sm.V[lane * 4 + i];
+                a[i] = (uint32_t)__popc(v); b[i] = (uint32_t)__popc(v & sm.M[lane * 4 + i]);
+                sa += a[i]; sb += b[i];
+            }
+            uint32_t ra = (uint32_t)warp_incl_scan((int)sa) - sa, rb = (uint32_t)warp_incl_scan((int)sb) - sb;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                sm.prefV[lane * 4 + i] = (uint16_t)ra; sm.prefVM[lane * 4 + i] = (uint16_t)rb;
+                ra += a[i]; rb += b[i];
+            }
+        }
+        __syncthreads();
+        const uint32_t items = sm.items, matches = sm.matches;
+        const uint32_t ngroups = (items + 7) >> 3;
+        const uint32_t total = items + ngroups + matches;
+        const bool compressed = total < (uint32_t)n;                 // src/lznt1_compress.cpp:86, :245
+        if (compressed) {
+            uint8_t* o = sm.out + 2;
+            for (int p = tid; p < LZNT1_CHUNK; p += LZE_THREADS) {
+                const uint32_t v = sm.V[p >> 5], below = (1u << (p & 31)) - 1;
+                if ((v >> (p & 31)) & 1) {
+                    const uint32_t vm = v & sm.M[p >> 5];
+                    const uint32_t k = sm.prefV[p >> 5] + (uint32_t)__popc(v & below);
+                    const uint32_t m = sm.prefVM[p >> 5] + (uint32_t)__popc(vm & below);
+                    const uint32_t off = k + (k >> 3) + 1 + m;
+                    if ((k & 7) == 0) sm.goff[k >> 3] = (uint16_t)(off - 1);
+                    if ((vm >> (p & 31)) & 1) {
+                        int S, lim;
+                        lznt1_shift_limit(p, S, lim);
+                        const uint32_t lo = sm.lenoff[p];
+                        const uint32_t tok = (((lo >> 16) - 1) << S) | ((lo & 0xFFFF) - 3);
+                        o[off] = (uint8_t)tok; o[off + 1] = (uint8_t)(tok >> 8);
+                        atomicOr(&sm.F[k >> 5], 1u << (k & 31));
+                    } else {
+                        o[off] = sm.in[p];
+                    }
+                }
+            }
+            __syncthreads();
+            for (uint32_t g = tid; g < ngroups; g += LZE_THREADS)
+                o[sm.goff[g]] = (uint8_t)(sm.F[g >> 2] >> (8 * (g & 3)));
+            if (tid == 0) { const uint32_t hdr = 0xB000u | (total - 1); sm.out[0] = (uint8_t)hdr; sm.out[1] = (uint8_t)(hdr >> 8); }
+        } else {
+            for (int i = tid; i < n; i += LZE_THREADS) sm.out[2 + i] = sm.in[i];
+            if (tid == 0) { const uint32_t hdr = 0x3000u | (uint32_t)(n - 1); sm.out[0] = (uint8_t)hdr; sm.out[1] = (uint8_t)(hdr >> 8); }
+        }
+        __syncthreads();
+
+        // ---- F: slot write ---------------------------------------------------------------------------------
+        const uint32_t bytes = 2 + (compressed ? total : (uint32_t)n);
+        for (uint32_t v = tid; v * 16 < bytes; v += LZE_THREADS)
+            st_stream16(slot + 16 * v, *reinterpret_cast<const uint4*>(sm.out + 16 * v));
+        if (tid == 0) slot_size[c] = bytes;
+        __syncthreads();
+    }
+}
+
+} // namespace msc

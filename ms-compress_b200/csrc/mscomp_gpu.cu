@@ -1,0 +1,140 @@
+// mscomp_gpu.cu -- device-resident batch API (include/mscomp_gpu.h): context management and kernel launches.
+#include "ctx.cuh"
+#include "shim_common.h"
+#include "kernels/lznt1_decode.cuh"
+#include "kernels/lznt1_encode.cuh"
+#include "kernels/compact.cuh"
+#include "kernels/summary.cuh"
+#include <new>
+
+using namespace msc;
+
+static_assert(sizeof(GpuResult) == sizeof(mscomp_gpu_result), "result layout");
+
+MSCompStatus msc_compact_slots(mscomp_gpu_ctx* ctx, const uint8_t* d_slots, uint64_t stride, const uint32_t* d_sizes,
+                               uint32_t n, uint64_t* d_offs, uint8_t* d_dst)
+{
+    MSC_LAUNCH(ctx, scan_sizes_kernel, 1, SCAN_THREADS, d_sizes, n, (uint64_t)0, d_offs);
+    if (n) {
+        const uint32_t gw = (n + 7) / 8;
+        const uint32_t grid = gw < (uint32_t)ctx->sm_count * 8 ? gw : (uint32_t)ctx->sm_count * 8;
+        MSC_LAUNCH(ctx, gather_slots_kernel, grid, 256, d_slots, stride, d_sizes, d_offs, n, d_dst);
+    }
+    return msc_cuda_status(cudaGetLastError(), "compact_slots");
+}
+
+extern "C" {
+
+mscomp_gpu_ctx* mscomp_gpu_create(int device, void* cuda_stream)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { cudaGetLastError(); return nullptr; }
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    mscomp_gpu_ctx* ctx = new (std::nothrow) mscomp_gpu_ctx();
+    if (!ctx) return nullptr;
+    ctx->device = device;
+    if (cuda_stream) { ctx->stream = (cudaStream_t)cuda_stream; ctx->own_stream = false; }
+    else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); delete ctx; return nullptr; }
+        ctx->own_stream = true;
+    }
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (ctx->sm_count <= 0) ctx->sm_count = 148;
+    return ctx;
+}
+
+void mscomp_gpu_destroy(mscomp_gpu_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < SC_COUNT; ++i) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+MSCompStatus mscomp_gpu_synchronize(mscomp_gpu_ctx* ctx)
+{
+    if (!ctx) return MSCOMP_ARG_ERROR;
+    return msc_cuda_status(cudaStreamSynchronize(ctx->stream), "synchronize");
+}
+
+uint64_t mscomp_gpu_kernel_launches(const mscomp_gpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+void mscomp_gpu_profile_enable(mscomp_gpu_ctx* ctx, int on)
+{
+    if (!ctx) return;
+    ctx->prof_on = on != 0;
+    ctx->prof_n = 0;
+}
+
+// Synchronises, then writes "kernel_name calls total_ms" lines (one per distinct kernel) into buf; returns bytes written.
+size_t mscomp_gpu_profile_report(mscomp_gpu_ctx* ctx, char* buf, size_t cap)
+{
+    if (!ctx || !buf || !cap) return 0;
+    cudaStreamSynchronize(ctx->stream);
+    size_t w = 0;
+    buf[0] = 0;
+    for (int i = 0; i < ctx->prof_n; ++i) {
+        bool seen = false;
+        for (int j = 0; j < i; ++j) if (ctx->prof_name[j] == ctx->prof_name[i]) { seen = true; break; }
+        if (seen) continue;
+        double ms = 0; int calls = 0;
+        for (int j = i; j < ctx->prof_n; ++j) if (ctx->prof_name[j] == ctx->prof_name[i]) {
+            float t = 0; cudaEventElapsedTime(&t, ctx->prof_ev[2 * j], ctx->prof_ev[2 * j + 1]); ms += t; ++calls;
+        }
+        int k = snprintf(buf + w, cap - w, "%s %d %.6f\n", ctx->prof_name[i], calls, ms);
+        if (k < 0 || (size_t)k >= cap - w) break;
+        w += (size_t)k;
+    }
+    ctx->prof_n = 0;
+    return w;
+}
+
+// ---- LZNT1 ------------------------------------------------------------------------------------------------------
+
+MSCompStatus mscomp_gpu_lznt1_compress(mscomp_gpu_ctx* ctx, const uint8_t* d_in, size_t in_len, uint8_t* d_out, size_t out_cap,
+                                       uint64_t* d_chunk_off, mscomp_gpu_result* d_result)
+{
+    if (!ctx || (!d_in && in_len) || !d_out || !d_result) return MSCOMP_ARG_ERROR;
+    const uint64_t nchunks64 = (in_len + LZNT1_CHUNK - 1) / LZNT1_CHUNK;
+    if (nchunks64 > 0x7fffffffu) return MSCOMP_ARG_ERROR;
+    const uint32_t nchunks = (uint32_t)nchunks64;
+    if (out_cap < in_len + 2 * nchunks64) return MSCOMP_BUF_ERROR;            // worst case: every chunk stored raw
+    cudaSetDevice(ctx->device);
+    uint8_t* slots = (uint8_t*)ctx->get(SC_SLOTS, (size_t)nchunks * LZNT1_SLOT + 16);
+    uint32_t* sizes = (uint32_t*)ctx->get(SC_SIZES, ((size_t)nchunks + 1) * sizeof(uint32_t));
+    uint64_t* offs = d_chunk_off ? d_chunk_off : (uint64_t*)ctx->get(SC_OFFS, ((size_t)nchunks + 1) * sizeof(uint64_t));
+    if (!slots || !sizes || !offs) return MSCOMP_MEM_ERROR;
+    if (nchunks) {
+        const uint32_t grid = nchunks < (uint32_t)ctx->sm_count * 8 ? nchunks : (uint32_t)ctx->sm_count * 8;
+        MSC_LAUNCH(ctx, lznt1_encode_kernel, grid, LZE_THREADS, d_in, (uint64_t)in_len, nchunks, slots, sizes);
+    }
+    msc_compact_slots(ctx, slots, LZNT1_SLOT, sizes, nchunks, offs, d_out);
+    // result: bytes = offs[nchunks]
+    cudaMemsetAsync(d_result, 0, sizeof(mscomp_gpu_result), ctx->stream);
+    cudaMemcpyAsync(&d_result->bytes, offs + nchunks, sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream);
+    return msc_cuda_status(cudaGetLastError(), "lznt1_compress");
+}
+
+MSCompStatus mscomp_gpu_lznt1_decompress(mscomp_gpu_ctx* ctx, const uint8_t* d_in, size_t in_len, const uint64_t* d_chunk_off,
+                                         uint32_t nchunks, uint8_t* d_out, uint32_t* d_chunk_size, int32_t* d_chunk_status,
+                                         mscomp_gpu_result* d_result)
+{
+    if (!ctx || !d_result || (nchunks && (!d_in || !d_chunk_off || !d_out))) return MSCOMP_ARG_ERROR;
+    cudaSetDevice(ctx->device);
+    uint32_t* sizes = d_chunk_size ? d_chunk_size : (uint32_t*)ctx->get(SC_SIZES, ((size_t)nchunks + 1) * sizeof(uint32_t));
+    int32_t* status = d_chunk_status ? d_chunk_status : (int32_t*)ctx->get(SC_STATUS, ((size_t)nchunks + 1) * sizeof(int32_t));
+    if (!sizes || !status) return MSCOMP_MEM_ERROR;
+    if (nchunks) {
+        const uint32_t blocks = (nchunks + LZNT1_WARPS_PER_BLOCK - 1) / LZNT1_WARPS_PER_BLOCK;
+        const uint32_t cap = (uint32_t)ctx->sm_count * 6 * 4;                 // 6 resident blocks per SM, a few waves
+        MSC_LAUNCH(ctx, lznt1_decode_kernel, blocks < cap ? blocks : cap, LZNT1_WARPS_PER_BLOCK * 32,
+                   d_in, (uint64_t)in_len, d_chunk_off, nchunks, d_out, sizes, status);
+    }
+    MSC_LAUNCH(ctx, summarize_kernel, 1, SUM_THREADS, sizes, status, nchunks, (uint32_t)LZNT1_CHUNK, (GpuResult*)d_result);
+    return msc_cuda_status(cudaGetLastError(), "lznt1_decompress");
+}
+
+} // extern "C"

@@ -1,0 +1,213 @@
+// mscomp_shim.cu -- the reference's host-pointer C ABI on top of the device batch API.
+//
+// Entry points and the reference code each one replaces:
+//   lznt1_compress / lznt1_decompress / lznt1_max_compressed_size ....... src/lznt1_compress.cpp:27,:233-273,
+//                                                                        src/lznt1_decompress.cpp:337 (+ :122-273 driver)
+//   xpress_* ............................................................ src/xpress_compress.cpp:30,:240-347, src/xpress_decompress.cpp:405-462
+//   xpress_huff_* ....................................................... src/xpress_huff_compress.cpp:46,:247-331, src/xpress_huff_decompress.cpp:136-162
+//   ms_compress / ms_decompress / ms_max_compressed_size ................ src/mscomp.cpp:96-132 (+ the MSCOMP_NONE copy engine :26-32)
+//
+// Each call: host -> device copy of the input, kernels on the calling thread's stream, device -> host copy of the
+// result.  Host-side work is limited to what the format forces to be serial on an unindexed stream (the LZNT1
+// header walk) and to reproducing the reference's status codes.  No codec work happens on the CPU.
+#include "ctx.cuh"
+#include "shim_common.h"
+#include <string.h>
+#include <vector>
+
+// ---- per-thread default context -------------------------------------------------------------------------------
+mscomp_gpu_ctx* msc_thread_ctx()
+{
+    // Deliberately leaked at thread/process exit: CUDA may already be shut down when TLS destructors run.
+    static thread_local mscomp_gpu_ctx* ctx = nullptr;
+    static thread_local bool failed = false;
+    if (ctx || failed) return ctx;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+    ctx = mscomp_gpu_create(dev, nullptr);
+    if (!ctx) {
+        failed = true;
+        fprintf(stderr, "libMSCompression(B200): no usable CUDA device -- this library has no CPU implementation\n");
+    }
+    return ctx;
+}
+
+static inline unsigned rd16(const uint8_t* p) { return (unsigned)p[0] | ((unsigned)p[1] << 8); }
+
+// =================================================================================================================
+// LZNT1
+// =================================================================================================================
+extern "C" size_t lznt1_max_compressed_size(size_t in_len) { return in_len + 3 + 2 * ((in_len + 4095) / 4096); }
+
+extern "C" MSCompStatus lznt1_compress(const_bytes in, size_t in_len, bytes out, size_t* out_len)
+{
+    if (!out_len || (!in && in_len) || !out) return MSCOMP_ARG_ERROR;
+    const size_t cap = *out_len;
+    if (cap == 0) return MSCOMP_BUF_ERROR;                 // undefined upstream (src/lznt1_compress.cpp:239), rejected here
+    mscomp_gpu_ctx* ctx = msc_thread_ctx();
+    if (!ctx) return MSCOMP_MEM_ERROR;
+    const size_t nchunks = (in_len + 4095) / 4096;
+    const size_t dcap = in_len + 2 * nchunks + 16;
+    uint8_t* d_in = (uint8_t*)ctx->get(SC_IN, in_len + 64);
+    uint8_t* d_out = (uint8_t*)ctx->get(SC_OUT, dcap + 64);
+    mscomp_gpu_result* d_res = (mscomp_gpu_result*)ctx->get(SC_RESULT, 256);
+    mscomp_gpu_result* h_res = (mscomp_gpu_result*)ctx->get_pinned(256);
+    if (!d_in || !d_out || !d_res || !h_res) return MSCOMP_MEM_ERROR;
+    if (in_len) cudaMemcpyAsync(d_in, in, in_len, cudaMemcpyHostToDevice, ctx->stream);
+    MSCompStatus st = mscomp_gpu_lznt1_compress(ctx, d_in, in_len, d_out, dcap, nullptr, d_res);
+    if (st != MSCOMP_OK) return st;
+    cudaMemcpyAsync(h_res, d_res, sizeof(*h_res), cudaMemcpyDeviceToHost, ctx->stream);
+    if ((st = msc_cuda_status(cudaStreamSynchronize(ctx->stream), "lznt1_compress")) != MSCOMP_OK) return st;
+    const size_t total = (size_t)h_res->bytes;
+    if (total > cap) return MSCOMP_BUF_ERROR;              // same outcome as the chunk-by-chunk checks upstream (:239-259)
+    if (total) cudaMemcpyAsync(out, d_out, total, cudaMemcpyDeviceToHost, ctx->stream);
+    if ((st = msc_cuda_status(cudaStreamSynchronize(ctx->stream), "lznt1_compress")) != MSCOMP_OK) return st;
+    if (cap - total >= 2) out[total] = out[total + 1] = 0; // end-of-buffer terminator, not counted (:268-271)
+    *out_len = total;
+    return MSCOMP_OK;
+}
+
+namespace {
+enum Lznt1Tail { T_CLEAN, T_ZERO, T_GARBAGE, T_TERM_OK, T_TERM_BAD, T_TRUNC, T_BADSIG };
+
+// Replays the reference's sequential driver (src/lznt1_decompress.cpp:254-273 + internal.h:616-630) over the
+// per-chunk results to obtain its status code.  size_of / status_of give chunk c's decoded size and status.
+template <class FS, class FT>
+MSCompStatus lznt1_replay(size_t nchunks, size_t cap, Lznt1Tail tail, FS size_of, FT status_of, size_t* total)
+{
+    size_t op = 0;
+    for (size_t c = 0; c < nchunks; ++c) {
+        if (cap - op == 0) return MSCOMP_BUF_ERROR;        // output full while input remains
+        if (status_of(c) < 0) return MSCOMP_DATA_ERROR;
+        const size_t sz = size_of(c);
+        if (sz > cap - op) return MSCOMP_BUF_ERROR;        // decoded bytes left over in the bounce buffer
+        op += sz;
+    }
+    *total = op;
+    switch (tail) {
+    case T_CLEAN: case T_ZERO: return MSCOMP_OK;
+    case T_GARBAGE: return MSCOMP_BUF_ERROR;
+    default: break;
+    }
+    if (cap - op == 0) return MSCOMP_BUF_ERROR;            // the loop never looks at the next header (:254)
+    switch (tail) {
+    case T_TERM_OK: return MSCOMP_OK;
+    case T_TRUNC: return MSCOMP_BUF_ERROR;
+    default: return MSCOMP_DATA_ERROR;                     // T_TERM_BAD, T_BADSIG
+    }
+}
+} // namespace
+
+extern "C" MSCompStatus lznt1_decompress(const_bytes in, size_t in_len, bytes out, size_t* out_len)
+{
+    if (!out_len || (!in && in_len) || (!out && *out_len)) return MSCOMP_ARG_ERROR;
+    const size_t cap = *out_len;
+
+    // Header walk: the format stores no chunk index and each header gives only the distance to the next one
+    // (src/lznt1_decompress.cpp:127-135), so an unindexed stream is a linked list; it is walked here, on the host,
+    // where the stream already is.
+    std::vector<uint64_t> offs;
+    offs.reserve(in_len / 2048 + 4);
+    Lznt1Tail tail = T_CLEAN;
+    size_t ip = 0;
+    bool stopped = false;
+    while (in_len - ip >= 2) {
+        const unsigned h = rd16(in + ip);
+        if (h == 0) { tail = (in_len - ip == 2) ? T_TERM_OK : T_TERM_BAD; stopped = true; break; }
+        const size_t sz = (h & 0x0FFF) + 3;
+        if (sz > in_len - ip) { tail = T_TRUNC; stopped = true; break; }
+        if ((h & 0x7000) != 0x3000) { tail = T_BADSIG; stopped = true; break; }
+        offs.push_back(ip);
+        ip += sz;
+    }
+    if (!stopped) tail = (in_len - ip == 0) ? T_CLEAN : (in[ip] == 0 ? T_ZERO : T_GARBAGE);
+    const size_t nchunks = offs.size();
+    if (nchunks > 0x7fffffffu) return MSCOMP_ARG_ERROR;
+
+    size_t total = 0;
+    if (nchunks == 0) {
+        MSCompStatus st = lznt1_replay(0, cap, tail, [](size_t) { return (size_t)0; }, [](size_t) { return 0; }, &total);
+        if (st == MSCOMP_OK) *out_len = 0;
+        return st;
+    }
+
+    mscomp_gpu_ctx* ctx = msc_thread_ctx();
+    if (!ctx) return MSCOMP_MEM_ERROR;
+    uint8_t* d_in = (uint8_t*)ctx->get(SC_IN, in_len + 64);
+    uint8_t* d_out = (uint8_t*)ctx->get(SC_OUT, nchunks * 4096 + 64);
+    uint64_t* d_offs = (uint64_t*)ctx->get(SC_OFFS, (nchunks + 1) * sizeof(uint64_t));
+    uint32_t* d_sizes = (uint32_t*)ctx->get(SC_SIZES, (nchunks + 1) * sizeof(uint32_t));
+    int32_t* d_status = (int32_t*)ctx->get(SC_STATUS, (nchunks + 1) * sizeof(int32_t));
+    mscomp_gpu_result* d_res = (mscomp_gpu_result*)ctx->get(SC_RESULT, 256);
+    mscomp_gpu_result* h_res = (mscomp_gpu_result*)ctx->get_pinned(256);
+    if (!d_in || !d_out || !d_offs || !d_sizes || !d_status || !d_res || !h_res) return MSCOMP_MEM_ERROR;
+    cudaMemcpyAsync(d_in, in, ip, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(d_offs, offs.data(), nchunks * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
+    MSCompStatus st = mscomp_gpu_lznt1_decompress(ctx, d_in, ip, d_offs, (uint32_t)nchunks, d_out, d_sizes, d_status, d_res);
+    if (st != MSCOMP_OK) return st;
+    cudaMemcpyAsync(h_res, d_res, sizeof(*h_res), cudaMemcpyDeviceToHost, ctx->stream);
+    if ((st = msc_cuda_status(cudaStreamSynchronize(ctx->stream), "lznt1_decompress")) != MSCOMP_OK) return st;
+
+    const mscomp_gpu_result r = *h_res;
+    const uint8_t* d_final = d_out;
+    if (r.status == 0 && r.short_units == 0) {
+        // every chunk but the last produced 4096 bytes: sizes are implied, output is already contiguous
+        const size_t last = (size_t)r.bytes - (nchunks - 1) * 4096;
+        st = lznt1_replay(nchunks, cap, tail, [&](size_t c) { return c + 1 < nchunks ? (size_t)4096 : last; }, [](size_t) { return 0; }, &total);
+    } else {
+        // rare: a failing chunk, or short chunks in mid-stream (streams cut by a flushing compressor)
+        std::vector<uint32_t> sizes(nchunks);
+        std::vector<int32_t> status(nchunks);
+        cudaMemcpyAsync(sizes.data(), d_sizes, nchunks * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaMemcpyAsync(status.data(), d_status, nchunks * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+        if ((st = msc_cuda_status(cudaStreamSynchronize(ctx->stream), "lznt1_decompress")) != MSCOMP_OK) return st;
+        st = lznt1_replay(nchunks, cap, tail, [&](size_t c) { return (size_t)sizes[c]; }, [&](size_t c) { return status[c]; }, &total);
+        if (st == MSCOMP_OK && r.short_units) {
+            uint8_t* d_packed = (uint8_t*)ctx->get(SC_AUX0, (size_t)r.bytes + 64);
+            uint64_t* d_dst = (uint64_t*)ctx->get(SC_AUX1, (nchunks + 1) * sizeof(uint64_t));
+            if (!d_packed || !d_dst) return MSCOMP_MEM_ERROR;
+            msc_compact_slots(ctx, d_out, 4096, d_sizes, (uint32_t)nchunks, d_dst, d_packed);
+            d_final = d_packed;
+        }
+    }
+    if (st != MSCOMP_OK) return st;
+    if (total) cudaMemcpyAsync(out, d_final, total, cudaMemcpyDeviceToHost, ctx->stream);
+    if ((st = msc_cuda_status(cudaStreamSynchronize(ctx->stream), "lznt1_decompress")) != MSCOMP_OK) return st;
+    *out_len = total;
+    return MSCOMP_OK;
+}
+
+// =================================================================================================================
+// format dispatch (src/mscomp.cpp:87-132)
+// =================================================================================================================
+static MSCompStatus copy_engine(const_bytes in, size_t in_len, bytes out, size_t* out_len)
+{   // MSCOMP_NONE: src/mscomp.cpp:26-32
+    if (!out_len) return MSCOMP_ARG_ERROR;
+    if (in_len > *out_len) return MSCOMP_BUF_ERROR;
+    if (in_len) memcpy(out, in, in_len);
+    *out_len = in_len;
+    return MSCOMP_OK;
+}
+static size_t copy_max_size(size_t in_len) { return in_len; }
+
+typedef MSCompStatus (*codec_fn)(const_bytes, size_t, bytes, size_t*);
+typedef size_t (*size_fn)(size_t);
+static const codec_fn kCompress[5]   = { copy_engine, nullptr, lznt1_compress,   MSC_XPRESS_COMPRESS,   MSC_XPRESS_HUFF_COMPRESS };
+static const codec_fn kDecompress[5] = { copy_engine, nullptr, lznt1_decompress, MSC_XPRESS_DECOMPRESS, MSC_XPRESS_HUFF_DECOMPRESS };
+static const size_fn  kMaxSize[5]    = { copy_max_size, nullptr, lznt1_max_compressed_size, MSC_XPRESS_MAX, MSC_XPRESS_HUFF_MAX };
+
+extern "C" MSCompStatus ms_compress(MSCompFormat format, const_bytes in, size_t in_len, bytes out, size_t* out_len)
+{
+    if ((unsigned)format >= 5 || !kCompress[format]) return MSCOMP_ARG_ERROR;
+    return kCompress[format](in, in_len, out, out_len);
+}
+extern "C" MSCompStatus ms_decompress(MSCompFormat format, const_bytes in, size_t in_len, bytes out, size_t* out_len)
+{
+    if ((unsigned)format >= 5 || !kDecompress[format]) return MSCOMP_ARG_ERROR;
+    return kDecompress[format](in, in_len, out, out_len);
+}
+extern "C" size_t ms_max_compressed_size(MSCompFormat format, size_t in_len)
+{
+    if ((unsigned)format >= 5 || !kMaxSize[format]) return (size_t)-1;
+    return kMaxSize[format](in_len);
+}

@@ -2,6 +2,8 @@
 // exposes one C entry point per kernel so that pytest can drive them with host buffers (see tests/test_emu_*.py).
 #include "simt_emu.h"
 #include "../../ms-compress_b200/csrc/kernels/lznt1_decode.cuh"
+#include "../../ms-compress_b200/csrc/kernels/lznt1_encode.cuh"
+#include "../../ms-compress_b200/csrc/kernels/compact.cuh"
 
 using emu::dim3e;
 
@@ -12,6 +14,16 @@ void emu_lznt1_decode(const uint8_t* in, uint64_t in_len, const uint64_t* chunk_
 {
     emu::launch(msc::lznt1_decode_kernel, dim3e(grid), dim3e(msc::LZNT1_WARPS_PER_BLOCK * 32),
                 in, in_len, chunk_off, nchunks, out, out_size, status);
+}
+
+// whole-stream LZNT1 compress: encode kernel -> size scan -> gather.  `slots` = nchunks*4112 scratch.
+void emu_lznt1_encode(const uint8_t* in, uint64_t in_len, uint32_t nchunks, uint8_t* slots, uint32_t* slot_size,
+                      uint64_t* offs, uint8_t* out, uint32_t grid)
+{
+    emu::launch(msc::lznt1_encode_kernel, dim3e(grid), dim3e(msc::LZE_THREADS), in, in_len, nchunks, slots, slot_size);
+    emu::launch(msc::scan_sizes_kernel, dim3e(1), dim3e(msc::SCAN_THREADS), (const uint32_t*)slot_size, nchunks, (uint64_t)0, offs);
+    emu::launch(msc::gather_slots_kernel, dim3e(grid), dim3e(256), (const uint8_t*)slots, (uint64_t)msc::LZNT1_SLOT,
+                (const uint32_t*)slot_size, (const uint64_t*)offs, nchunks, out);
 }
 
 }

@@ -1,0 +1,51 @@
+"""The C-ABI library loads and exports every symbol the public headers declare (no compute calls -- no GPU here)."""
+import ctypes
+import glob
+import os
+import re
+
+from conftest import ROOT
+
+
+def declared_symbols():
+    names = set()
+    for h in glob.glob(os.path.join(ROOT, "include", "*.h")):
+        text = re.sub(r"/\*.*?\*/", "", open(h).read(), flags=re.S)
+        for m in re.finditer(r"MSCOMPAPI\s+[\w\s\*]+?\b(\w+)\s*\(", text):
+            names.add(m.group(1))
+    return names
+
+
+def test_library_exports_declared_symbols(ms):
+    lib = ctypes.CDLL(ms.LIB_PATH)
+    names = declared_symbols()
+    assert {"ms_compress", "ms_decompress", "ms_max_compressed_size", "lznt1_compress", "lznt1_decompress"} <= names
+    missing = [n for n in sorted(names) if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_max_compressed_size_matches_reference_formulas(ms):
+    L = ms.lib()
+    # reference values: SURVEY.md 8(b) table, src/lznt1_compress.cpp:27, src/xpress_compress.cpp:30, src/xpress_huff_compress.cpp:46
+    assert L.ms_max_compressed_size(2, 65536) == 65571
+    assert L.ms_max_compressed_size(3, 65536) == 73732
+    assert L.ms_max_compressed_size(4, 65536) == 66086
+    assert L.ms_max_compressed_size(0, 65536) == 65536
+    assert L.ms_max_compressed_size(1, 65536) == 2 ** 64 - 1
+    assert L.ms_max_compressed_size(5, 65536) == 2 ** 64 - 1
+
+
+def test_bad_format_is_arg_error(ms):
+    out = ctypes.create_string_buffer(16)
+    n = ctypes.c_size_t(16)
+    for fmt in (1, 5, 99):
+        assert ms.lib().ms_compress(fmt, b"abc", 3, out, ctypes.byref(n)) == ms.MSCOMP_ARG_ERROR
+        assert ms.lib().ms_decompress(fmt, b"abc", 3, out, ctypes.byref(n)) == ms.MSCOMP_ARG_ERROR
+
+
+def test_none_format_copies(ms):
+    out = ctypes.create_string_buffer(16)
+    n = ctypes.c_size_t(16)
+    assert ms.lib().ms_compress(0, b"hello", 5, out, ctypes.byref(n)) == 0 and out.raw[:n.value] == b"hello"
+    n = ctypes.c_size_t(2)
+    assert ms.lib().ms_decompress(0, b"hello", 5, out, ctypes.byref(n)) == ms.MSCOMP_BUF_ERROR
