@@ -41,9 +41,12 @@ typedef struct mscomp_gpu_batch {
     int32_t*        d_status;    /* OUT: MSCompStatus per buffer */
 } mscomp_gpu_batch;
 
-/* cuda_stream: a cudaStream_t passed as void* (NULL = the context creates and owns a non-blocking stream).
- * Returns NULL when the device cannot be used. */
-MSCOMPAPI mscomp_gpu_ctx* mscomp_gpu_create(int device, void* cuda_stream);
+/* mscomp_gpu_create: the context creates and owns a non-blocking stream.
+ * mscomp_gpu_create_on_stream: all work is issued on the caller's stream (a cudaStream_t passed as void*; NULL is
+ * the legacy default stream), so it orders with the caller's other work on that stream.
+ * Both return NULL when the device cannot be used. */
+MSCOMPAPI mscomp_gpu_ctx* mscomp_gpu_create(int device);
+MSCOMPAPI mscomp_gpu_ctx* mscomp_gpu_create_on_stream(int device, void* cuda_stream);
 MSCOMPAPI void            mscomp_gpu_destroy(mscomp_gpu_ctx* ctx);
 MSCOMPAPI MSCompStatus    mscomp_gpu_synchronize(mscomp_gpu_ctx* ctx);
 /* Kernels launched through this context so far (the benchmark reports it as gpu_launches). */

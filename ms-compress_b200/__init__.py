@@ -73,7 +73,8 @@ def lib():
         L.ms_compress.restype, L.ms_compress.argtypes = i32, [i32, vp, sz, vp, psz]
         L.ms_decompress.restype, L.ms_decompress.argtypes = i32, [i32, vp, sz, vp, psz]
         L.ms_max_compressed_size.restype, L.ms_max_compressed_size.argtypes = sz, [i32, sz]
-        L.mscomp_gpu_create.restype, L.mscomp_gpu_create.argtypes = vp, [i32, vp]
+        L.mscomp_gpu_create.restype, L.mscomp_gpu_create.argtypes = vp, [i32]
+        L.mscomp_gpu_create_on_stream.restype, L.mscomp_gpu_create_on_stream.argtypes = vp, [i32, vp]
         L.mscomp_gpu_destroy.restype, L.mscomp_gpu_destroy.argtypes = None, [vp]
         L.mscomp_gpu_synchronize.restype, L.mscomp_gpu_synchronize.argtypes = i32, [vp]
         L.mscomp_gpu_kernel_launches.restype, L.mscomp_gpu_kernel_launches.argtypes = u64, [vp]
@@ -189,7 +190,7 @@ class GpuContext:
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         with torch.cuda.device(self.device):
             self.stream = torch.cuda.current_stream()
-            self.handle = lib().mscomp_gpu_create(self.device.index, ctypes.c_void_p(self.stream.cuda_stream))
+            self.handle = lib().mscomp_gpu_create_on_stream(self.device.index, ctypes.c_void_p(self.stream.cuda_stream))
         if not self.handle:
             raise RuntimeError("mscomp_gpu_create failed")
 

@@ -1,0 +1,247 @@
+// xhuff_decode.cuh -- Xpress-Huffman decoder, one lane per independent buffer (32 buffers per warp).
+//
+// Replaces the reference's xpress_huff_decompress (src/xpress_huff_decompress.cpp:136-162), its chunk loop
+// xpress_huff_decompress_chunk (:39-135), the bit reader InputBitstream (include/mscomp/Bitstream.h:34-107) and
+// the canonical decoder HuffmanDecoder::SetCodeLengths / DecodeSymbol (include/mscomp/HuffmanDecoder.h:42-103).
+//
+// Per buffer the format is strictly serial: codes are variable length, raw length bytes are interleaved at the
+// reader's BYTE cursor (Bitstream.h:104-106) and a chunk's length is stored nowhere -- so a lane
+// keeps the reference's exact reader state (32-bit window, valid-bit count, byte cursor) and walks its buffer
+// chunk after chunk; parallelism comes from the batch.  Symbols become tokens in a shared-memory queue and are
+// executed by the whole warp (lz_exec.cuh).  A multi-chunk stream produced by the reference (cross-chunk matches,
+// implicit chunk boundaries) decodes on the same path.
+//
+// Canonical decoding without a big lookup table: the per-length limits of the left-aligned 15-bit code space
+// (`lims`, HuffmanDecoder.h:58-76) live in 8 registers as packed 16-bit pairs; the code length is
+// 1 + #{k : x >= lims[k]}, counted with 16-bit SIMD compares; the symbol is syms[base[n] + (x >> (15-n))].
+// Shared memory per lane: 512 x u16 symbols (interleaved across lanes) + 16 x i16 bases.
+#pragma once
+#include "common.cuh"
+#include "lz_exec.cuh"
+
+namespace msc {
+
+constexpr int XH_SYMS = 512;
+constexpr int XH_EOS = 256;
+constexpr uint32_t XH_CHUNK = 65536;
+constexpr int XH_MIN_DATA = 260;
+
+struct XhWarpSmem {
+    uint16_t syms[XH_SYMS * 32];         // syms[i * 32 + lane]
+    int16_t base[16 * 32];               // base[n * 32 + lane]; doubles as the per-length counters while building
+    uint16_t fill[16 * 32];              // table build only: next free slot per length
+    uint32_t q[32 * LZQ_STRIDE];
+};
+constexpr int XHD_WARPS_PER_BLOCK = 1;
+constexpr size_t XHD_SMEM_BYTES = sizeof(XhWarpSmem) * XHD_WARPS_PER_BLOCK;
+
+#ifndef MSC_EMU
+__device__ __forceinline__ uint32_t vcmpgeu2(uint32_t a, uint32_t b) { return __vcmpgeu2(a, b); }
+#else
+inline uint32_t vcmpgeu2(uint32_t a, uint32_t b)
+{ return (((a & 0xFFFFu) >= (b & 0xFFFFu)) ? 0xFFFFu : 0u) | (((a >> 16) >= (b >> 16)) ? 0xFFFF0000u : 0u); }
+#endif
+
+struct XhLane {
+    // stream
+    const uint8_t* in; uint32_t in_len; uint32_t cap;
+    // reader state (Bitstream.h:34-44): window, valid bits, byte cursor
+    uint32_t mask; int bits; uint32_t ip;
+    ByteWindow win;
+    // decode tables
+    uint32_t lims2[8];                   // lims[1..15] packed: lims2[k] = lims[2k+1] | lims[2k+2] << 16 (lims[16] = 0xFFFF filler)
+    // progress
+    uint32_t opos, chunk_end;
+    uint32_t pend_len, pend_off;         // rest of a match longer than LZQ_MAXLEN
+    int status;                          // 0 running, 1 finished OK, <0 error
+    bool need_table;
+};
+
+__device__ __forceinline__ uint32_t xh_rd16(XhLane& L, uint32_t at) { L.win.seek(L.in + at); return L.win.get32(L.in + at) & 0xFFFFu; }
+__device__ __forceinline__ uint32_t xh_rd32(XhLane& L, uint32_t at) { L.win.seek(L.in + at); return L.win.get32(L.in + at); }
+
+__device__ __forceinline__ bool xh_mask_is_zero(const XhLane& L) { return L.bits == 0 || (L.mask >> (32 - L.bits)) == 0; }
+__device__ __forceinline__ uint32_t xh_peek(const XhLane& L, int n) { return (L.mask >> 16) >> (16 - n); }
+__device__ __forceinline__ void xh_skip(XhLane& L, int n)
+{   // InputBitstream::Skip (Bitstream.h:59-70)
+    L.mask <<= n; L.bits -= n;
+    if (L.bits < 16 && L.ip + 2 <= L.in_len) {
+        L.mask |= xh_rd16(L, L.ip) << (16 - L.bits);
+        L.bits += 16;
+        L.ip += 2;
+    }
+}
+
+// HuffmanDecoder::SetCodeLengths (HuffmanDecoder.h:42-91) from the 256 packed nibbles at in[at..at+256).
+__device__ __forceinline__ bool xh_build_table(XhLane& L, XhWarpSmem& sm, int lane, uint32_t at)
+{
+    for (int l = 0; l < 16; ++l) sm.base[l * 32 + lane] = 0;
+    for (int i = 0; i < 256; i += 4) {
+        const uint32_t w = xh_rd32(L, at + i);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sm.base[((w >> (4 * k)) & 15) * 32 + lane] += 1;
+    }
+    uint32_t last = 0, pos = 0, cnt_prev = 0;                   // lims[len-1], poss[len], cnts[len-1] (cnts[0] counts as 0)
+    uint32_t lim[17];
+    bool ok = true;
+#pragma unroll
+    for (int len = 1; len <= 15; ++len) {
+        const uint32_t cnt = (uint32_t)(uint16_t)sm.base[len * 32 + lane];
+        pos += cnt_prev;                                        // poss[len] = poss[len-1] + cnts[len-1]   (:79-80)
+        cnt_prev = cnt;
+        sm.fill[len * 32 + lane] = (uint16_t)pos;
+        sm.base[len * 32 + lane] = (int16_t)((int)pos - (int)(last >> (15 - len)));     // idx = base[n] + (x >> (15-n))
+        if (len < 15) {
+            const uint32_t inc = cnt << (15 - len);
+            if (last + inc > 32768u) ok = false;                // :65, :73 over-subscribed
+            last += inc;
+            lim[len] = last;
+        } else {
+            if (last + cnt > 32768u) ok = false;                // :76
+            lim[len] = 32768u;                                  // :61
+        }
+    }
+    lim[16] = 0xFFFFu;                                          // filler, never reached (x < 32768)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) L.lims2[k] = lim[2 * k + 1] | (lim[2 * k + 2] << 16);
+    if (!ok) return false;
+    for (int i = 0; i < XH_SYMS; ++i) sm.syms[i * 32 + lane] = 0xFFFFu;        // :44
+    for (int i = 0; i < 256; i += 4) {                          // symbols in (length, symbol) order (:83-88)
+        const uint32_t w = xh_rd32(L, at + i);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t l = (w >> (4 * k)) & 15;
+            if (l) {
+                const uint32_t f = sm.fill[l * 32 + lane];
+                sm.fill[l * 32 + lane] = (uint16_t)(f + 1);
+                sm.syms[f * 32 + lane] = (uint16_t)(2 * i + k);
+            }
+        }
+    }
+    return true;
+}
+
+// DecodeSymbol (HuffmanDecoder.h:93-103): returns the symbol or 0xFFFF
+__device__ __forceinline__ uint32_t xh_decode_symbol(XhLane& L, const XhWarpSmem& sm, int lane)
+{
+    const int r = L.bits;
+    const uint32_t x = (r < 15) ? (r == 0 ? 0u : ((L.mask >> (32 - r)) << (15 - r))) : (L.mask >> 17);
+    const uint32_t xx = x | (x << 16);
+    int n = 1;                                                   // first length whose limit exceeds x
+#pragma unroll
+    for (int k = 0; k < 8; ++k) n += __popc(vcmpgeu2(xx, L.lims2[k])) >> 4;
+    if (n > r) return 0xFFFFu;
+    const int idx = (int)sm.base[n * 32 + lane] + (int)(x >> (15 - n));
+    xh_skip(L, n);
+    if ((unsigned)idx >= (unsigned)XH_SYMS) return 0xFFFFu;
+    return sm.syms[idx * 32 + lane];
+}
+
+// Parse up to LZQ_TOKENS tokens of this lane's stream into its queue; returns the number queued.
+__device__ __forceinline__ int xh_parse_round(XhLane& L, XhWarpSmem& sm, int lane)
+{
+    uint32_t* q = sm.q + lane * LZQ_STRIDE;
+    int nt = 0;
+    while (nt < LZQ_TOKENS && L.status == 0) {
+        if (L.pend_len) {                                           // continue a long match
+            const uint32_t l = L.pend_len > LZQ_MAXLEN ? LZQ_MAXLEN : L.pend_len;
+            q[nt++] = lzq_match(L.pend_off, l);
+            L.pend_len -= l; L.opos += l;
+            continue;
+        }
+        if (L.need_table) {                                         // start of a chunk (xpress_huff_decompress :143-157)
+            if (L.in_len - L.ip < (uint32_t)XH_MIN_DATA) { L.status = (L.ip == L.in_len) ? 1 : ST_DATA; break; }
+            if (!xh_build_table(L, sm, lane, L.ip)) { L.status = ST_DATA; break; }
+            L.mask = (xh_rd16(L, L.ip + 256) << 16) | xh_rd16(L, L.ip + 258);
+            L.bits = 32;
+            L.ip += 260;
+            L.chunk_end = L.opos + XH_CHUNK;
+            L.need_table = false;
+        }
+        if (!(L.opos < L.chunk_end || !xh_mask_is_zero(L))) {       // end of chunk (:79, :127-133)
+            XhLane T = L;                                            // trial decode of an end-of-stream symbol
+            const uint32_t s2 = xh_decode_symbol(T, sm, lane);
+            if (s2 == (uint32_t)XH_EOS && T.in_len - T.ip == 0 && xh_mask_is_zero(T)) { L.status = 1; break; }
+            L.need_table = true;
+            continue;
+        }
+        const uint32_t sym = xh_decode_symbol(L, sm, lane);
+#ifdef XHDBG
+        if (lane==0) printf("sym=%x bits=%d mask=%08x ip=%u opos=%u\n", sym, L.bits, L.mask, L.ip, L.opos);
+#endif
+        if (sym == 0xFFFFu) { L.status = ST_DATA; break; }
+        if (sym == (uint32_t)XH_EOS && L.in_len - L.ip == 0 && xh_mask_is_zero(L)) { L.status = 1; break; }   // :83
+        if (sym < 256) {
+            if (L.opos == L.cap) { L.status = ST_BUF; break; }
+            q[nt++] = lzq_lit(sym);
+            L.opos += 1;
+        } else {
+            uint32_t len = sym & 15;
+            if (len == 15) {
+                if (L.in_len - L.ip < 1) { L.status = ST_DATA; break; }
+                len = xh_rd16(L, L.ip) & 0xFF; L.ip += 1;
+                if (len == 0xFF) {
+                    if (L.in_len - L.ip < 2) { L.status = ST_DATA; break; }
+                    len = xh_rd16(L, L.ip); L.ip += 2;
+                    if (len == 0) {
+                        if (L.in_len - L.ip < 4) { L.status = ST_DATA; break; }
+                        len = xh_rd32(L, L.ip); L.ip += 4;
+                    }
+                    if (len < 15) { L.status = ST_DATA; break; }
+                    len -= 15;
+                }
+                len += 15;
+            }
+            len += 3;
+            const int off_bits = (int)((sym >> 4) & 15);
+            if (off_bits > L.bits) { L.status = ST_DATA; break; }
+            const uint32_t off = xh_peek(L, off_bits) + (1u << off_bits);
+            xh_skip(L, off_bits);
+            if (L.opos < off) { L.status = ST_DATA; break; }             // :113
+            if (L.cap - L.opos < len) { L.status = ST_BUF; break; }      // :114
+            const uint32_t l = len > LZQ_MAXLEN ? LZQ_MAXLEN : len;
+            q[nt++] = lzq_match(off, l);
+            L.opos += l;
+            L.pend_len = len - l; L.pend_off = off;
+        }
+    }
+    return nt;
+}
+
+// Batch decode: buffer i = in[in_off[i] .. +in_len[i]) -> out[out_off[i] .. +out_cap[i]); out_len / status per buffer.
+__global__ void __launch_bounds__(32 * XHD_WARPS_PER_BLOCK)
+xhuff_decode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint32_t count,
+                    const uint64_t* __restrict__ in_off, const uint32_t* __restrict__ in_len,
+                    const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ out_cap,
+                    uint32_t* __restrict__ out_len, int32_t* __restrict__ status)
+{
+    MSC_DYN_SMEM(smem_raw);
+    XhWarpSmem& sm = reinterpret_cast<XhWarpSmem*>(smem_raw)[threadIdx.x >> 5];
+    const int lane = lane_id();
+    const uint32_t warps_total = gridDim.x * XHD_WARPS_PER_BLOCK;
+    for (uint32_t g = blockIdx.x * XHD_WARPS_PER_BLOCK + (threadIdx.x >> 5); g * 32 < count; g += warps_total) {
+        const uint32_t i = g * 32 + lane;
+        XhLane L;
+        L.status = 1; L.opos = 0; L.pend_len = 0; L.pend_off = 0; L.in = in; L.in_len = 0; L.cap = 0; L.ip = 0;
+        L.mask = 0; L.bits = 0; L.chunk_end = 0; L.need_table = true;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) L.lims2[k] = 0xFFFFFFFFu;
+        uint8_t* o = out;
+        if (i < count) {
+            L.in = in + in_off[i]; L.in_len = in_len[i]; L.cap = out_cap[i];
+            o = out + out_off[i];
+            L.status = 0;
+        }
+        L.win.init(L.in, L.in + L.in_len);
+        uint32_t done_pos = 0;                      // bytes already executed
+        for (;;) {
+            const int nt = xh_parse_round(L, sm, lane);
+            __syncwarp();
+            if (!__any_sync(FULL, nt > 0)) break;
+            lzq_execute(sm.q, nt, o, done_pos);
+        }
+        if (i < count) { out_len[i] = L.opos; status[i] = L.status == 1 ? ST_OK : L.status; }
+    }
+}
+
+} // namespace msc

@@ -1,0 +1,139 @@
+// xpress_decode.cuh -- plain Xpress (LZ77) decoder, one lane per independent buffer (32 buffers per warp).
+//
+// Replaces the reference's xpress_decompress (src/xpress_decompress.cpp:405-462: checked loop :425-460; the
+// unchecked fast path INFLATE_FAST :119-198 computes the same thing) and its symbol reader (:62-113).
+//
+// The stream is one unbroken sequence of 32-item flag words interleaved with item bytes, plus a shared length
+// nibble whose partner can be arbitrarily far away: it has to be parsed serially, so a lane
+// parses its buffer into a token queue and the warp executes the copies (lz_exec.cuh).
+#pragma once
+#include "common.cuh"
+#include "lz_exec.cuh"
+
+namespace msc {
+
+constexpr int XPD_WARPS_PER_BLOCK = 4;
+
+struct XpLane {
+    const uint8_t* in; uint32_t in_len; uint32_t cap;
+    ByteWindow win;
+    uint32_t ip, opos;
+    uint32_t flags; bool flagged, have_flags;
+    uint32_t half_val; bool has_half;        // value of the byte whose high nibble is still unused (:88-92)
+    uint32_t pend_len, pend_off;
+    int status;                              // 0 running, 1 finished OK, < 0 error
+};
+
+__device__ __forceinline__ uint32_t xp_rd32(XpLane& L, uint32_t at) { L.win.seek(L.in + at); return L.win.get32(L.in + at); }
+
+// all 1 bits above all 0 bits (src/xpress_decompress.cpp:41)
+__device__ __forceinline__ bool xp_set_bits_are_highest(uint32_t x) { x = ~x; return ((x + 1) & x) == 0; }
+
+__device__ __forceinline__ int xp_parse_round(XpLane& L, uint32_t* q)
+{
+    int nt = 0;
+    while (nt < LZQ_TOKENS && L.status == 0) {
+        if (L.pend_len) {
+            const uint32_t l = L.pend_len > LZQ_MAXLEN ? LZQ_MAXLEN : L.pend_len;
+            q[nt++] = lzq_match(L.pend_off, l);
+            L.pend_len -= l; L.opos += l;
+            continue;
+        }
+        if (!L.have_flags) {                                            // start a fragment (:425-430)
+            if (L.ip + 4 > L.in_len) { L.status = ST_DATA; break; }     // :461
+            const uint32_t f = xp_rd32(L, L.ip);
+            L.flagged = (f & 0x80000000u) != 0;
+            L.flags = (f << 1) | 1;
+            L.ip += 4;
+            L.have_flags = true;
+        }
+        if (L.ip == L.in_len) {                                         // :433-438 end of stream
+            L.status = (L.flagged && xp_set_bits_are_highest(L.flags)) ? 1 : ST_DATA;
+            break;
+        }
+        if (L.flagged) {                                                // _READ_SYMBOL :85-112
+            if (L.ip + 2 > L.in_len) { L.status = ST_DATA; break; }
+            const uint32_t sym = xp_rd32(L, L.ip) & 0xFFFFu;
+            L.ip += 2;
+            const uint32_t off = (sym >> 3) + 1;
+            uint32_t len = sym & 7;
+            if (len == 7) {
+                if (L.has_half) { len = L.half_val >> 4; L.has_half = false; }
+                else if (L.ip == L.in_len) { L.status = ST_DATA; break; }
+                else { L.half_val = xp_rd32(L, L.ip) & 0xFF; L.has_half = true; len = L.half_val & 0xF; L.ip += 1; }
+                if (len == 0xF) {
+                    if (L.ip == L.in_len) { L.status = ST_DATA; break; }
+                    len = xp_rd32(L, L.ip) & 0xFF; L.ip += 1;
+                    if (len == 0xFF) {
+                        if (L.ip + 2 > L.in_len) { L.status = ST_DATA; break; }
+                        len = xp_rd32(L, L.ip) & 0xFFFF; L.ip += 2;
+                        if (len == 0) {
+                            if (L.ip + 4 > L.in_len) { L.status = ST_DATA; break; }
+                            len = xp_rd32(L, L.ip); L.ip += 4;
+                        }
+                        if (len < 0xF + 0x7) { L.status = ST_DATA; break; }
+                        len -= 0xF + 0x7;
+                    }
+                    len += 0xF;
+                }
+                len += 0x7;
+            }
+            len += 0x3;
+            if (off > L.opos) { L.status = ST_DATA; break; }            // :442
+            if ((uint64_t)L.opos + len > L.cap) { L.status = ST_BUF; break; }     // :443
+            const uint32_t l = len > LZQ_MAXLEN ? LZQ_MAXLEN : len;
+            q[nt++] = lzq_match(off, l);
+            L.opos += l;
+            L.pend_len = len - l; L.pend_off = off;
+        } else {
+            if (L.opos == L.cap) { L.status = ST_BUF; break; }          // :455
+            q[nt++] = lzq_lit(xp_rd32(L, L.ip));
+            L.ip += 1; L.opos += 1;
+        }
+        L.flagged = (L.flags & 0x80000000u) != 0;
+        L.flags <<= 1;
+        if (L.flags == 0) L.have_flags = false;
+    }
+    return nt;
+}
+
+__global__ void __launch_bounds__(32 * XPD_WARPS_PER_BLOCK)
+xpress_decode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint32_t count,
+                     const uint64_t* __restrict__ in_off, const uint32_t* __restrict__ in_len,
+                     const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ out_cap,
+                     uint32_t* __restrict__ out_len, int32_t* __restrict__ status)
+{
+    __shared__ uint32_t s_q[XPD_WARPS_PER_BLOCK][32 * LZQ_STRIDE];
+    const int lane = lane_id();
+    const int wib = (int)(threadIdx.x >> 5);
+    uint32_t* q = s_q[wib];
+    const uint32_t warps_total = gridDim.x * XPD_WARPS_PER_BLOCK;
+    for (uint32_t g = blockIdx.x * XPD_WARPS_PER_BLOCK + wib; g * 32 < count; g += warps_total) {
+        const uint32_t i = g * 32 + lane;
+        XpLane L;
+        L.in = in; L.in_len = 0; L.cap = 0; L.ip = 0; L.opos = 0; L.flags = 0; L.flagged = false; L.have_flags = false;
+        L.half_val = 0; L.has_half = false; L.pend_len = 0; L.pend_off = 0; L.status = 1;
+        uint8_t* o = out;
+        if (i < count) {
+            L.in = in + in_off[i]; L.in_len = in_len[i]; L.cap = out_cap[i];
+            o = out + out_off[i];
+            L.status = 0;
+            if (L.in_len < 5) {                                         // :414-418 (sic)
+                uint32_t w = 0;
+                if (L.in_len == 4) w = (uint32_t)L.in[0] | ((uint32_t)L.in[1] << 8) | ((uint32_t)L.in[2] << 16) | ((uint32_t)L.in[3] << 24);
+                L.status = (L.in_len == 0 || (L.in_len == 4 && w != 0xFFFFFFFFu)) ? 1 : ST_DATA;
+            }
+        }
+        L.win.init(L.in, L.in + L.in_len);
+        uint32_t done_pos = 0;
+        for (;;) {
+            const int nt = xp_parse_round(L, q + lane * LZQ_STRIDE);
+            __syncwarp();
+            if (!__any_sync(FULL, nt > 0)) break;
+            lzq_execute(q, nt, o, done_pos);
+        }
+        if (i < count) { out_len[i] = L.opos; status[i] = L.status == 1 ? ST_OK : L.status; }
+    }
+}
+
+} // namespace msc

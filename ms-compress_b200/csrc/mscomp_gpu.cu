@@ -25,7 +25,7 @@ MSCompStatus msc_compact_slots(mscomp_gpu_ctx* ctx, const uint8_t* d_slots, uint
 
 extern "C" {
 
-mscomp_gpu_ctx* mscomp_gpu_create(int device, void* cuda_stream)
+static mscomp_gpu_ctx* create_ctx(int device, void* cuda_stream, bool use_given)
 {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { cudaGetLastError(); return nullptr; }
@@ -33,7 +33,7 @@ mscomp_gpu_ctx* mscomp_gpu_create(int device, void* cuda_stream)
     mscomp_gpu_ctx* ctx = new (std::nothrow) mscomp_gpu_ctx();
     if (!ctx) return nullptr;
     ctx->device = device;
-    if (cuda_stream) { ctx->stream = (cudaStream_t)cuda_stream; ctx->own_stream = false; }
+    if (use_given) { ctx->stream = (cudaStream_t)cuda_stream; ctx->own_stream = false; }
     else {
         if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); delete ctx; return nullptr; }
         ctx->own_stream = true;
@@ -42,6 +42,9 @@ mscomp_gpu_ctx* mscomp_gpu_create(int device, void* cuda_stream)
     if (ctx->sm_count <= 0) ctx->sm_count = 148;
     return ctx;
 }
+
+mscomp_gpu_ctx* mscomp_gpu_create(int device) { return create_ctx(device, nullptr, false); }
+mscomp_gpu_ctx* mscomp_gpu_create_on_stream(int device, void* cuda_stream) { return create_ctx(device, cuda_stream, true); }
 
 void mscomp_gpu_destroy(mscomp_gpu_ctx* ctx)
 {

@@ -24,7 +24,7 @@ mscomp_gpu_ctx* msc_thread_ctx()
     if (ctx || failed) return ctx;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
-    ctx = mscomp_gpu_create(dev, nullptr);
+    ctx = mscomp_gpu_create(dev);
     if (!ctx) {
         failed = true;
         fprintf(stderr, "libMSCompression(B200): no usable CUDA device -- this library has no CPU implementation\n");

@@ -4,6 +4,8 @@
 #include "../../ms-compress_b200/csrc/kernels/lznt1_decode.cuh"
 #include "../../ms-compress_b200/csrc/kernels/lznt1_encode.cuh"
 #include "../../ms-compress_b200/csrc/kernels/compact.cuh"
+#include "../../ms-compress_b200/csrc/kernels/xhuff_decode.cuh"
+#include "../../ms-compress_b200/csrc/kernels/xpress_decode.cuh"
 
 using emu::dim3e;
 
@@ -24,6 +26,20 @@ void emu_lznt1_encode(const uint8_t* in, uint64_t in_len, uint32_t nchunks, uint
     emu::launch(msc::scan_sizes_kernel, dim3e(1), dim3e(msc::SCAN_THREADS), (const uint32_t*)slot_size, nchunks, (uint64_t)0, offs);
     emu::launch(msc::gather_slots_kernel, dim3e(grid), dim3e(256), (const uint8_t*)slots, (uint64_t)msc::LZNT1_SLOT,
                 (const uint32_t*)slot_size, (const uint64_t*)offs, nchunks, out);
+}
+
+
+void emu_xhuff_decode(const uint8_t* in, uint8_t* out, uint32_t count, const uint64_t* in_off, const uint32_t* in_len,
+                      const uint64_t* out_off, const uint32_t* out_cap, uint32_t* out_len, int32_t* status, uint32_t grid)
+{
+    emu::launch(msc::xhuff_decode_kernel, dim3e(grid), dim3e(32 * msc::XHD_WARPS_PER_BLOCK), in, out, count, in_off, in_len, out_off, out_cap, out_len, status);
+}
+
+
+void emu_xpress_decode(const uint8_t* in, uint8_t* out, uint32_t count, const uint64_t* in_off, const uint32_t* in_len,
+                       const uint64_t* out_off, const uint32_t* out_cap, uint32_t* out_len, int32_t* status, uint32_t grid)
+{
+    emu::launch(msc::xpress_decode_kernel, dim3e(grid), dim3e(32 * msc::XPD_WARPS_PER_BLOCK), in, out, count, in_off, in_len, out_off, out_cap, out_len, status);
 }
 
 }

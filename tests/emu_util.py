@@ -54,3 +54,31 @@ def emu_lznt1_encode(emu, data, grid=3):
     emu.emu_lznt1_encode(ctypes.c_void_p(addr), ctypes.c_uint64(n), ctypes.c_uint32(nch), P(slots), P(ss), P(offs),
                          ctypes.c_void_p(out.ctypes.data + 16), ctypes.c_uint32(grid))
     return out[16:16 + int(offs[nch])].tobytes(), offs
+
+
+def emu_batch(emu, fn_name, bufs, caps, grid=2):
+    """Run a batch kernel (decode or encode) over independent buffers; returns (status, out_len, [outputs])."""
+    count = len(bufs)
+    in_off, pos = [], 0
+    for b in bufs:
+        in_off.append(pos)
+        pos += (len(b) + 7) // 8 * 8 + 8
+    blob = bytearray(pos + 8)
+    for b, o in zip(bufs, in_off):
+        blob[o:o + len(b)] = b
+    a, addr = padded(bytes(blob))
+    out_off, opos = [], 0
+    for c in caps:
+        out_off.append(opos)
+        opos += (c + 15) // 16 * 16 + 16
+    out = np.zeros(opos + 2 * PAD, dtype=np.uint8)
+    io = np.array(in_off, dtype=np.uint64)
+    il = np.array([len(b) for b in bufs], dtype=np.uint32)
+    oo = np.array(out_off, dtype=np.uint64)
+    oc = np.array(caps, dtype=np.uint32)
+    ol = np.zeros(count, dtype=np.uint32)
+    st = np.zeros(count, dtype=np.int32)
+    getattr(emu, fn_name)(ctypes.c_void_p(addr), ctypes.c_void_p(out.ctypes.data + PAD), ctypes.c_uint32(count), P(io), P(il), P(oo), P(oc),
+                          P(ol), P(st), ctypes.c_uint32(grid))
+    outs = [out[PAD + out_off[i]:PAD + out_off[i] + ol[i]].tobytes() for i in range(count)]
+    return st, ol, outs
