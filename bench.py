@@ -160,6 +160,70 @@ class Clocks:
 # ------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------------------
+
+def measure_batch_format(ms, ctx, torch, fmt, each, count, steps, dev, peak, rank):
+    """Encode+decode of `count` independent buffers of `each` bytes (generator text, seeds 42+rank*count+i) through the
+    device batch API; returns a dict with MB/s, kernel times and roofline fractions."""
+    import numpy as np
+    U = each * count
+    host = np.empty(U, dtype=np.uint8)
+    ms.generate_batch_into(host, each, count, 42 + rank * count, "text")
+    d_in = torch.empty(U, dtype=torch.uint8, device=dev)
+    step_b = 1 << 28
+    for o in range(0, U, step_b):
+        d_in[o:o + step_b].copy_(torch.from_numpy(host[o:o + step_b]))
+    capf = {"xpress_huff": lambda n: n + 34 + 258 + 258 * (n // 65536), "xpress": lambda n: n + 4 + 4 * (n // 32)}[fmt]
+    slot = (capf(each) + 15) // 16 * 16
+    d_comp = torch.empty(slot * count, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(U, dtype=torch.uint8, device=dev)
+    ar = torch.arange(count, dtype=torch.int64, device=dev)
+    in_off, c_off = ar * each, ar * slot
+    in_len = torch.full((count,), each, dtype=torch.int32, device=dev)
+    c_cap = torch.full((count,), slot, dtype=torch.int32, device=dev)
+    c_len = torch.zeros(count, dtype=torch.int32, device=dev)
+    st1 = torch.zeros(count, dtype=torch.int32, device=dev)
+    o_len = torch.zeros(count, dtype=torch.int32, device=dev)
+    st2 = torch.zeros(count, dtype=torch.int32, device=dev)
+    enc = ms.Batch(count, in_off.data_ptr(), in_len.data_ptr(), c_off.data_ptr(), c_cap.data_ptr(), c_len.data_ptr(), st1.data_ptr())
+    dec = ms.Batch(count, c_off.data_ptr(), c_len.data_ptr(), in_off.data_ptr(), in_len.data_ptr(), o_len.data_ptr(), st2.data_ptr())
+
+    def step(ev=None):
+        if ev:
+            ev[0].record()
+        ctx.run_batch(fmt, "compress", d_in, d_comp, enc)
+        if ev:
+            ev[1].record()
+        ctx.run_batch(fmt, "decompress", d_comp, d_out, dec)
+        if ev:
+            ev[2].record()
+
+    step()
+    torch.cuda.synchronize()
+    assert int(st1.abs().sum().item()) == 0 and int(st2.abs().sum().item()) == 0, "%s: kernel reported an error" % fmt
+    assert torch.equal(d_out, d_in), "%s round trip mismatch" % fmt
+    C = int(c_len.to(torch.int64).sum().item())
+    l0 = ctx.launches()
+    ctx.profile(True)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    torch.cuda.synchronize()
+    for k in range(steps):
+        step(evs[k])
+    torch.cuda.synchronize()
+    prof = ctx.profile_report()
+    ctx.profile(False)
+    enc_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in evs)
+    dec_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in evs)
+    kern = {}
+    for name, (calls, ms_tot) in prof.items():
+        per = ms_tot / max(calls, 1)
+        kern[name] = {"ms_per_launch": per, "achieved_GBps": (U + C) / 1e9 / (per / 1e3), "frac": (U + C) / 1e9 / (per / 1e3) / peak}
+    del d_in, d_comp, d_out
+    torch.cuda.empty_cache()
+    return {"workload": "%d independent buffers x %d bytes (text), device batch API" % (count, each), "uncompressed_bytes": U, "compressed_ratio": C / U,
+            "encode_ms": enc_ms, "decode_ms": dec_ms, "encode_MBps": U / MB / (enc_ms / 1e3), "decode_MBps": U / MB / (dec_ms / 1e3),
+            "encode_decode_MBps": U / MB / ((enc_ms + dec_ms) / 1e3), "gpu_launches": ctx.launches() - l0, "kernels": kern}
+
+
 def run_gpu(args):
     import numpy as np
     import torch
@@ -266,12 +330,23 @@ def run_gpu(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te.item())
 
+    peak, peak_src = peaks()
+    formats = {}
+    if args.formats != "none" and world == 1:
+        del d_comp, d_out, h_comp, h_out
+        torch.cuda.empty_cache()
+        if hasattr(ms.lib(), "mscomp_gpu_xpress_huff_compress_batch"):
+            gib = args.xhuff_gib
+            formats["xpress_huff"] = measure_batch_format(ms, ctx, torch, "xpress_huff", 65536, gib * 16384, 2, dev, peak, rank)
+            formats["xpress_huff"]["config"] = "BASELINE.json configs[3]: %d GiB synthetic text as independent 64 KiB buffers" % gib
+            formats["xpress"] = measure_batch_format(ms, ctx, torch, "xpress", BLOCK, args.mib, 2, dev, peak, rank)
+            formats["xpress"]["config"] = "BASELINE.json configs[2]: %d MiB synthetic text as %d independent 1 MiB buffers (one stream each)" % (args.mib, args.mib)
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return 0
 
-    peak, peak_src = peaks()
     steps = args.steps
     kern = {}
     alg = {"lznt1_encode_kernel": U + C, "lznt1_decode_kernel": C + U, "gather_slots_kernel": 2 * C}
@@ -307,6 +382,7 @@ def run_gpu(args):
         "e2e": {"value": world * U / MB / e2e_s, "unit": "MB/s", "h2d_bytes_per_step": U + C, "d2h_bytes_per_step": C + U,
                 "api": "lznt1_compress + lznt1_decompress (C ABI, pinned host buffers)", "ms_per_step": 1e3 * e2e_s},
         "clocks": clk.summary(),
+        "formats": formats,
     }
     if cpu:
         line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -323,6 +399,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--formats", default="all", choices=["all", "none"], help="also measure Xpress-Huffman (configs[3]) and Xpress (configs[2]) at N=1")
+    ap.add_argument("--xhuff-gib", type=int, default=4, help="GiB of uncompressed data for the Xpress-Huffman measurement")
     ap.add_argument("--mib", type=int, default=1024, help="MiB of uncompressed data per GPU (default: the 1 GiB of BASELINE.json configs[1])")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -17,7 +17,6 @@ LIB = os.path.join(HERE, "lib")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared",
-    "-DMSC_NO_XPRESS",   # bring-up: Xpress / Xpress-Huffman entry points not linked yet
 ]
 CU_SOURCES = ["mscomp_gpu.cu", "mscomp_shim.cu"]
 

@@ -1,0 +1,307 @@
+// xhuff_encode.cuh -- Xpress-Huffman encoder, one 256-thread block per buffer (64 KiB chunk after chunk).
+//
+// Replaces the reference's xpress_huff_compress (src/xpress_huff_compress.cpp:247-331): LZ77 + symbol histogram
+// (xh_compress_lz77 :52-153), code construction (HuffmanEncoder::CreateCodes, include/mscomp/HuffmanEncoder.h:58-127),
+// the expansion guard with its literal-only fallback (:274-280, :310-316, xh_compress_no_matching :155-180) and the
+// bit packer (xh_compress_encode :195-245 over OutputBitstream, include/mscomp/Bitstream.h:111-148).
+//
+// Differences from the reference that keep the stream valid for its decoder: the match
+// window is reset at every 64 KiB chunk, unused symbols get code length 0, code lengths come from a plain
+// Huffman tree clamped to 15 bits by a Kraft-sum repair instead of the reference's rescale-and-retry.
+//
+// Stages per chunk:  tiles of 2048 positions -> tokens (lz_front.cuh) + 512-bin histogram (shared atomics)
+//   -> code lengths / canonical codes -> exact size (expansion guard) -> 256-byte table
+//   -> pass A over tokens: running bit / raw-byte prefix sums give every code its bit address, every raw length
+//      byte and every 16-bit word its final byte address (placement model of SURVEY.md A.3, which mirrors
+//      OutputBitstream: two words are always reserved ahead, raw bytes go to the write cursor)
+//   -> pass B: the assembled 16-bit words are scattered to their addresses.
+#pragma once
+#include "common.cuh"
+#include "lz_front.cuh"
+
+namespace msc {
+
+constexpr int XHE_THREADS = LZF_THREADS;
+constexpr uint32_t XHE_CHUNK = 65536;
+constexpr int XHE_SYMS = 512;
+constexpr uint32_t XHE_TOK_CAP = XHE_CHUNK + 64;                 // tokens per chunk (+EOS)
+constexpr uint32_t XHE_WORD_CAP = 36864;                         // 16-bit words per chunk: <= 1 + ceil(bits/16)
+// per-block global scratch layout (bytes)
+constexpr size_t XHE_SCR_TOK = 0;
+constexpr size_t XHE_SCR_BITS = XHE_SCR_TOK + (size_t)XHE_TOK_CAP * 4;
+constexpr size_t XHE_SCR_WPOS = XHE_SCR_BITS + (size_t)XHE_WORD_CAP * 2;
+constexpr size_t XHE_SCRATCH_BYTES = XHE_SCR_WPOS + (size_t)XHE_WORD_CAP * 4;
+
+struct XhEncSmem {
+    LzFrontSmem lz;
+    uint32_t hist[XHE_SYMS];
+    uint32_t key[XHE_SYMS];            // (count << 9 | symbol), sorted ascending; unused symbols sort first
+    uint32_t w[2 * XHE_SYMS];          // Huffman node weights (leaves then internal nodes)
+    uint16_t parent[2 * XHE_SYMS];
+    uint16_t code[XHE_SYMS];
+    uint8_t len[XHE_SYMS];
+    uint32_t blc[16];                  // codes per length
+    uint32_t nused, raw_total, bits_total, scan_tmp[8];
+    unsigned long long bit_carry;      // running (bits << 32 | raw bytes) between token tiles
+};
+
+__device__ __forceinline__ uint32_t xhe_sym_of(uint32_t tok)
+{
+    if (!(tok >> 31)) return (tok & LZF_TOK_EOS) ? 256u : (tok & 0xFFu);
+    const uint32_t off = tok & 0xFFFFu, lm3 = ((tok >> 16) & 0x7FFFu) + 1 - 3;
+    const uint32_t ob = 31u - (uint32_t)__clz((int)off);
+    return 256u + ((ob << 4) | min(lm3, 15u));
+}
+__device__ __forceinline__ uint32_t xhe_raw_of(uint32_t tok)
+{   // raw length bytes after the code: 0, 1 or 3 (lengths are capped at 32768, the u32 form never occurs)
+    if (!(tok >> 31)) return 0;
+    const uint32_t lm3 = ((tok >> 16) & 0x7FFFu) + 1 - 3;
+    return lm3 < 15 ? 0u : (lm3 < 15 + 255 ? 1u : 3u);
+}
+
+// Code lengths (<= 15) and canonical codes from sm.hist.  All threads.
+__device__ __forceinline__ void xhe_build_codes(XhEncSmem& sm)
+{
+    const int tid = (int)threadIdx.x;
+    for (int i = tid; i < XHE_SYMS; i += XHE_THREADS) { sm.key[i] = (sm.hist[i] << 9) | (uint32_t)i; sm.len[i] = 0; sm.code[i] = 0; }
+    if (tid < 16) sm.blc[tid] = 0;
+    __syncthreads();
+    // bitonic sort of 512 keys, ascending
+    for (int k = 2; k <= XHE_SYMS; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < XHE_SYMS; i += XHE_THREADS) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const uint32_t a = sm.key[i], b = sm.key[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) { sm.key[i] = b; sm.key[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (tid == 0) {
+        int first = 0;
+        while (first < XHE_SYMS && (sm.key[first] >> 9) == 0) ++first;
+        const int m = XHE_SYMS - first;                            // used symbols, ascending by (count, symbol)
+        sm.nused = (uint32_t)m;
+        if (m == 1) { sm.parent[0] = 0; }
+        else if (m > 1) {                                          // two-queue Huffman: leaves 0..m-1, internal m..2m-2
+            for (int i = 0; i < m; ++i) sm.w[i] = sm.key[first + i] >> 9;
+            int i = 0, j = m, k = m;
+            while (k < 2 * m - 1) {
+                int a, b;
+                if (i < m && (j >= k || sm.w[i] <= sm.w[j])) a = i++; else a = j++;
+                if (i < m && (j >= k || sm.w[i] <= sm.w[j])) b = i++; else b = j++;
+                sm.w[k] = sm.w[a] + sm.w[b];
+                sm.parent[a] = (uint16_t)k; sm.parent[b] = (uint16_t)k;
+                ++k;
+            }
+        }
+    }
+    __syncthreads();
+    const int m = (int)sm.nused, first = XHE_SYMS - m;
+    // depth of every leaf, clamped to 15; codes per length
+    for (int i = tid; i < m; i += XHE_THREADS) {
+        int d = 0;
+        if (m == 1) d = 1;
+        else for (int x = i; x != 2 * m - 2; x = sm.parent[x]) ++d;
+        if (d > 15) d = 15;
+        atomicAdd(&sm.blc[d], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        // Kraft repair: while over-subscribed, lengthen one code of the longest length below 15
+        uint32_t K = 0;
+        for (int l = 1; l <= 15; ++l) K += sm.blc[l] << (15 - l);
+        while (K > 32768u) {
+            int l = 14;
+            while (sm.blc[l] == 0) --l;
+            sm.blc[l]--; sm.blc[l + 1]++;
+            K -= 1u << (14 - l);
+        }
+        // lengths by rank: the least frequent symbols take the longest codes
+        int idx = 0;
+        for (int l = 15; l >= 1; --l)
+            for (uint32_t c = 0; c < sm.blc[l]; ++c) sm.len[sm.key[first + idx++] & 511] = (uint8_t)l;
+        // canonical codes, ascending (length, symbol)  (HuffmanEncoder.h:115-123)
+        uint32_t next[16], code = 0;
+        for (int l = 1; l <= 15; ++l) { next[l] = code; code = (code + sm.blc[l]) << 1; }
+        for (int s = 0; s < XHE_SYMS; ++s) { const int l = sm.len[s]; if (l) sm.code[s] = (uint16_t)next[l]++; }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void xhe_or16(uint32_t* bits32, uint32_t j, uint32_t v)
+{   // OR a 16-bit value into word j of the little-endian 16-bit word array
+    atomicOr(&bits32[j >> 1], (v & 0xFFFFu) << (16 * (j & 1)));
+}
+// write the n-bit value v at bit address b of the MSB-first bit string
+__device__ __forceinline__ void xhe_put_bits(uint32_t* bits32, uint32_t b, uint32_t v, uint32_t n)
+{
+    if (!n) return;
+    const uint32_t j = b >> 4, avail = 16 - (b & 15);
+    if (n <= avail) xhe_or16(bits32, j, v << (avail - n));
+    else { xhe_or16(bits32, j, v >> (n - avail)); xhe_or16(bits32, j + 1, v << (16 - (n - avail))); }
+}
+__device__ __forceinline__ uint32_t xhe_reserved(uint32_t B) { return B ? 1 + ((B + 15) >> 4) : 2; }   // words reserved at B bits
+
+// One block per buffer.  eos_mode 0: every buffer is its own stream (ends with the end-of-stream symbol);
+// eos_mode 1: the buffers are consecutive chunks of ONE stream -- only the last buffer of the batch carries it.
+__global__ void __launch_bounds__(XHE_THREADS)
+xhuff_encode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint32_t count,
+                    const uint64_t* __restrict__ in_off, const uint32_t* __restrict__ in_len,
+                    const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ out_cap,
+                    uint32_t* __restrict__ out_len, int32_t* __restrict__ status, uint8_t* __restrict__ scratch, int eos_mode)
+{
+    MSC_DYN_SMEM(smem_raw);
+    XhEncSmem& sm = *reinterpret_cast<XhEncSmem*>(smem_raw);
+    const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint8_t* scr = scratch + (size_t)blockIdx.x * XHE_SCRATCH_BYTES;
+    uint32_t* tok = reinterpret_cast<uint32_t*>(scr + XHE_SCR_TOK);
+    uint32_t* bits32 = reinterpret_cast<uint32_t*>(scr + XHE_SCR_BITS);
+    uint16_t* bits16 = reinterpret_cast<uint16_t*>(scr + XHE_SCR_BITS);
+    uint32_t* wpos = reinterpret_cast<uint32_t*>(scr + XHE_SCR_WPOS);
+
+    for (uint32_t u = blockIdx.x; u < count; u += gridDim.x) {
+        const uint8_t* ubase = in + in_off[u];
+        const uint32_t ulen = in_len[u], cap = out_cap[u];
+        uint8_t* obase = out + out_off[u];
+        uint32_t opos = 0;
+        int st = ST_OK;
+        const bool stream_end_here = (eos_mode == 0) || (u + 1 == count);
+
+        for (uint32_t c0 = 0; c0 < ulen && st == ST_OK; c0 += XHE_CHUNK) {
+            const uint8_t* src = ubase + c0;
+            const uint32_t n = min(ulen - c0, XHE_CHUNK);
+            const bool last = (c0 + n == ulen) && stream_end_here;
+
+            // ---- LZ77 -> tokens + histogram ----
+            for (int i = tid; i < (1 << LZF_HBITS); i += XHE_THREADS) sm.lz.H[i] = 0;
+            for (int i = tid; i < XHE_SYMS; i += XHE_THREADS) sm.hist[i] = 0;
+            if (tid == 0) { sm.lz.next_p = 0; sm.lz.ntok = 0; }
+            __syncthreads();
+            bool literal_only = false;
+            for (int attempt = 0; attempt < 2; ++attempt) {
+                if (!literal_only) {
+                    for (uint32_t t0 = 0; t0 < n; t0 += LZF_TILE) {
+                        const uint32_t cnt = lzf_tile(sm.lz, src, n, t0, 65535u, 4096u);
+                        const uint32_t tb = sm.lz.ntok;
+                        for (int r = tid; r < LZF_TILE; r += XHE_THREADS) {
+                            const uint32_t v = sm.lz.V[r >> 5];
+                            if ((v >> (r & 31)) & 1) {
+                                const uint32_t k = tb + sm.lz.prefV[r >> 5] + (uint32_t)__popc(v & ((1u << (r & 31)) - 1));
+                                const uint32_t lo = sm.lz.lenoff[r];
+                                const uint32_t t = lo ? (0x80000000u | lo) : (uint32_t)src[t0 + r];
+                                tok[k] = t;
+                                atomicAdd(&sm.hist[xhe_sym_of(t)], 1u);
+                            }
+                        }
+                        __syncthreads();
+                        if (tid == 0) sm.lz.ntok = tb + cnt;
+                        __syncthreads();
+                    }
+                } else {    // literal-only fallback (xh_compress_no_matching :155-180)
+                    for (int i = tid; i < XHE_SYMS; i += XHE_THREADS) sm.hist[i] = 0;
+                    __syncthreads();
+                    for (uint32_t i = tid; i < n; i += XHE_THREADS) { const uint32_t b = src[i]; tok[i] = b; atomicAdd(&sm.hist[b], 1u); }
+                    if (tid == 0) sm.lz.ntok = n;
+                    __syncthreads();
+                }
+                if (tid == 0 && last) { tok[sm.lz.ntok] = LZF_TOK_EOS; sm.lz.ntok += 1; sm.hist[256] += 1; }
+                __syncthreads();
+
+                // ---- codes + exact size (xh_calc_compressed_len :181-188) ----
+                xhe_build_codes(sm);
+                {
+                    unsigned long long local = 0;      // bits << 32 | raw bytes
+                    for (int s = tid; s < XHE_SYMS; s += XHE_THREADS) {
+                        const uint32_t h = sm.hist[s];
+                        if (h) {
+                            const uint32_t ob = s >= 256 ? (uint32_t)((s >> 4) & 15) : 0u;
+                            local += ((unsigned long long)(h * (sm.len[s] + ob))) << 32;
+                        }
+                    }
+                    for (int d = 16; d; d >>= 1) local += __shfl_xor_sync(FULL, local, d);
+                    if (lane == 0) reinterpret_cast<unsigned long long*>(sm.w)[warp] = local;
+                    __syncthreads();
+                    if (tid == 0) { unsigned long long t = 0; for (int i = 0; i < XHE_THREADS / 32; ++i) t += reinterpret_cast<unsigned long long*>(sm.w)[i]; sm.bits_total = (uint32_t)(t >> 32); }
+                    __syncthreads();
+                }
+                // raw bytes: counted from the tokens (only length symbols with nibble 15 carry them)
+                {
+                    uint32_t r = 0;
+                    const uint32_t nt = sm.lz.ntok;
+                    if (!literal_only) for (uint32_t k = tid; k < nt; k += XHE_THREADS) r += xhe_raw_of(tok[k]);
+                    for (int d = 16; d; d >>= 1) r += __shfl_xor_sync(FULL, r, d);
+                    if (lane == 0) sm.scan_tmp[warp] = r;
+                    __syncthreads();
+                    if (tid == 0) { uint32_t t = 0; for (int i = 0; i < XHE_THREADS / 32; ++i) t += sm.scan_tmp[i]; sm.raw_total = t; }
+                    __syncthreads();
+                }
+                const uint32_t Btot = sm.bits_total;
+                const uint32_t comp_len = 2 * (((Btot + 15) >> 4) + 1) + sm.raw_total;
+                if (!literal_only && comp_len > n + (last ? 36u : 2u)) { literal_only = true; continue; }   // :274, :310
+                break;
+            }
+
+            const uint32_t ntok = sm.lz.ntok;
+            const uint32_t Btot = sm.bits_total;
+            const uint32_t nwords = xhe_reserved(Btot);
+            const uint32_t comp_len = 2 * nwords + sm.raw_total;
+            if ((uint64_t)opos + 256 + comp_len > cap || nwords + 2 > XHE_WORD_CAP) { st = ST_BUF; break; }
+            uint8_t* o = obase + opos + 256;
+            // 256-byte table: symbol 2i in the low nibble of byte i (:284, :320)
+            for (int i = tid; i < 256; i += XHE_THREADS) obase[opos + i] = (uint8_t)(sm.len[2 * i] | (sm.len[2 * i + 1] << 4));
+            // ---- pass A: bit addresses, raw bytes, word addresses ----
+            for (uint32_t i = tid; i < (nwords + 1) / 2 + 1; i += XHE_THREADS) bits32[i] = 0;
+            if (tid == 0) { sm.bit_carry = 0; wpos[0] = 0; wpos[1] = 2; }
+            __syncthreads();
+            for (uint32_t k0 = 0; k0 < ntok; k0 += XHE_THREADS) {
+                const uint32_t k = k0 + tid;
+                uint32_t t = 0, sym = 0, cl = 0, ob = 0, raw = 0;
+                if (k < ntok) {
+                    t = tok[k]; sym = xhe_sym_of(t); cl = sm.len[sym];
+                    if (t >> 31) { ob = (sym >> 4) & 15; raw = xhe_raw_of(t); }
+                }
+                unsigned long long v = ((unsigned long long)(cl + ob) << 32) | raw, incl = v;
+                for (int d = 1; d < 32; d <<= 1) { const unsigned long long x = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += x; }
+                if (lane == 31) reinterpret_cast<unsigned long long*>(sm.w)[warp] = incl;
+                __syncthreads();
+                unsigned long long base = sm.bit_carry;
+                for (int w2 = 0; w2 < warp; ++w2) base += reinterpret_cast<unsigned long long*>(sm.w)[w2];
+                const unsigned long long excl = base + incl - v;
+                if (k < ntok) {
+                    const uint32_t B0 = (uint32_t)(excl >> 32), R0 = (uint32_t)excl;
+                    const uint32_t B1 = B0 + cl, B2 = B1 + ob;
+                    xhe_put_bits(bits32, B0, sm.code[sym], cl);
+                    if (xhe_reserved(B1) > xhe_reserved(B0)) { const uint32_t j = xhe_reserved(B0); wpos[j] = 4 + 2 * (j - 2) + R0; }
+                    if (t >> 31) {
+                        const uint32_t off = t & 0xFFFFu, lm3 = ((t >> 16) & 0x7FFFu) + 1 - 3;
+                        if (raw) {
+                            uint8_t* rp = o + 4 + 2 * (B1 ? ((B1 + 15) >> 4) - 1 : 0) + R0;
+                            if (raw == 1) rp[0] = (uint8_t)(lm3 - 15);
+                            else { rp[0] = 0xFF; rp[1] = (uint8_t)lm3; rp[2] = (uint8_t)(lm3 >> 8); }
+                        }
+                        xhe_put_bits(bits32, B1, off - (1u << ob), ob);
+                        if (xhe_reserved(B2) > xhe_reserved(B1)) { const uint32_t j = xhe_reserved(B1); wpos[j] = 4 + 2 * (j - 2) + R0 + raw; }
+                    }
+                }
+                __syncthreads();
+                if (tid == XHE_THREADS - 1) sm.bit_carry = excl + v;
+                __syncthreads();
+            }
+            // ---- pass B: words to their addresses ----
+            for (uint32_t j = tid; j < nwords; j += XHE_THREADS) {
+                const uint32_t wv = bits16[j], p = wpos[j];
+                o[p] = (uint8_t)wv; o[p + 1] = (uint8_t)(wv >> 8);
+            }
+            __syncthreads();
+            opos += 256 + comp_len;
+        }
+        if (tid == 0) { out_len[u] = (st == ST_OK) ? opos : 0; status[u] = st; }
+        __syncthreads();
+    }
+}
+
+} // namespace msc

@@ -1,0 +1,206 @@
+// xpress_encode.cuh -- plain Xpress (LZ77) encoder, one 256-thread block per buffer.
+//
+// Replaces the reference's xpress_compress (src/xpress_compress.cpp:240-347) and its use of
+// XpressDictionary<0x2000> (:28).  Matching / greedy parse: lz_front.cuh (window 8192).  Emission is done tile by
+// tile with three running prefix sums instead of the reference's serial output cursor:
+//   item bytes   -- literal 1; match 2 (+1 when it opens a new shared length nibble byte, +1 extension byte,
+//                   +2 for a 16-bit length), src/xpress_compress.cpp:274-315
+//   item count   -- a 4-byte flag word (MSB first, 1 = match) precedes every 32 items (:317-324), so item k sits at
+//                   4 * (k / 32 + 1) + (bytes of the items before it)
+//   nibble users -- the q-th match with length >= 10 writes the low (q even) or high (q odd) nibble of a byte
+//                   that the even one allocates right after its own 2-byte symbol (:281-290)
+// The stream ends inside a flag word whose unused bits are 1, which costs an extra FFFFFFFF word when the item
+// count is a multiple of 32 (:343); empty input encodes as FF FF FF FF (:253-259).
+#pragma once
+#include "common.cuh"
+#include "lz_front.cuh"
+
+namespace msc {
+
+constexpr int XPE_THREADS = LZF_THREADS;
+constexpr int XPE_PER_THREAD = LZF_TILE / XPE_THREADS;     // 8 consecutive positions per thread
+
+struct XpEncSmem {
+    LzFrontSmem lz;
+    uint32_t flagw[LZF_TILE / 32 + 2];       // flag words touched by this tile (first one may be carried in)
+    uint32_t flagpos[LZF_TILE / 32 + 2];     // their byte positions in the output
+    uint32_t nibpos[LZF_TILE];               // half-byte position of the even-ranked nibble users of this tile
+    unsigned long long wsum[XPE_THREADS / 32];
+    // carried across tiles
+    uint32_t items, bytes, nibs;             // totals so far (bytes = item bytes only, flag words not included)
+    uint32_t pend_half;                      // position of the half byte waiting for its high nibble (nibs odd)
+    uint32_t cur_flags, cur_flagpos;         // the partially filled flag word
+    int status;
+};
+
+// bytes of a match item, given whether it has to allocate the shared half byte
+__device__ __forceinline__ uint32_t xpe_match_bytes(uint32_t lm3, bool new_half)
+{
+    uint32_t b = 2;
+    if (lm3 >= 7) { b += new_half ? 1u : 0u; if (lm3 - 7 >= 15) { b += 1; if (lm3 - 22 >= 255) b += 2; } }
+    return b;
+}
+
+__global__ void __launch_bounds__(XPE_THREADS)
+xpress_encode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint32_t count,
+                     const uint64_t* __restrict__ in_off, const uint32_t* __restrict__ in_len,
+                     const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ out_cap,
+                     uint32_t* __restrict__ out_len, int32_t* __restrict__ status)
+{
+    MSC_DYN_SMEM(smem_raw);
+    XpEncSmem& sm = *reinterpret_cast<XpEncSmem*>(smem_raw);
+    const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (uint32_t u = blockIdx.x; u < count; u += gridDim.x) {
+        const uint8_t* src = in + in_off[u];
+        const uint32_t n = in_len[u], cap = out_cap[u];
+        uint8_t* o = out + out_off[u];
+        for (int i = tid; i < (1 << LZF_HBITS); i += XPE_THREADS) sm.lz.H[i] = 0;
+        if (tid == 0) {
+            sm.lz.next_p = 0; sm.lz.ntok = 0;
+            sm.items = 0; sm.bytes = 0; sm.nibs = 0; sm.pend_half = 0; sm.cur_flags = 0; sm.cur_flagpos = 0;
+            sm.status = (cap < 4) ? ST_BUF : ST_OK;
+        }
+        __syncthreads();
+
+        for (uint32_t t0 = 0; t0 < n && sm.status == ST_OK; t0 += LZF_TILE) {
+            lzf_tile(sm.lz, src, n, t0, 8192u, 8192u);
+            // ---- per-thread item statistics over 8 consecutive positions ----
+            const uint32_t items0 = sm.items, bytes0 = sm.bytes, nibs0 = sm.nibs;
+            uint32_t my_items = 0, my_bytes = 0, my_nibs = 0;
+#pragma unroll
+            for (int i = 0; i < XPE_PER_THREAD; ++i) {
+                const int r = tid * XPE_PER_THREAD + i;
+                if ((sm.lz.V[r >> 5] >> (r & 31)) & 1) {
+                    const uint32_t lo = sm.lz.lenoff[r];
+                    ++my_items;
+                    if (lo && (lo >> 16) + 1 - 3 >= 7) ++my_nibs;
+                }
+            }
+            // The half-byte allocation depends on the GLOBAL parity of the nibble-user rank: scan the nibble users first,
+            // then size the items with the right parity, then scan bytes and items.
+            uint32_t nincl = (uint32_t)warp_incl_scan((int)my_nibs);
+            if (lane == 31) sm.wsum[warp] = nincl;
+            __syncthreads();
+            uint32_t nbase = nibs0;
+            for (int w2 = 0; w2 < warp; ++w2) nbase += (uint32_t)sm.wsum[w2];
+            const uint32_t nib_excl = nbase + nincl - my_nibs;
+            __syncthreads();
+            {
+                uint32_t q = nib_excl;
+#pragma unroll
+                for (int i = 0; i < XPE_PER_THREAD; ++i) {
+                    const int r = tid * XPE_PER_THREAD + i;
+                    if ((sm.lz.V[r >> 5] >> (r & 31)) & 1) {
+                        const uint32_t lo = sm.lz.lenoff[r];
+                        if (lo) {
+                            const uint32_t lm3 = (lo >> 16) + 1 - 3;
+                            const bool nib = lm3 >= 7;
+                            my_bytes += xpe_match_bytes(lm3, nib && ((q & 1) == 0));
+                            if (nib) ++q;
+                        } else my_bytes += 1;
+                    }
+                }
+            }
+            unsigned long long v = ((unsigned long long)my_bytes << 32) | my_items, incl = v;
+            for (int d = 1; d < 32; d <<= 1) { const unsigned long long x = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += x; }
+            if (lane == 31) sm.wsum[warp] = incl;
+            __syncthreads();
+            unsigned long long base = 0, total = 0;
+            for (int w2 = 0; w2 < XPE_THREADS / 32; ++w2) { if (w2 < warp) base += sm.wsum[w2]; total += sm.wsum[w2]; }
+            const unsigned long long excl = base + incl - v;
+            const uint32_t tile_items = (uint32_t)total, tile_bytes = (uint32_t)(total >> 32);
+            // capacity: everything this tile can touch, including the flag word it may open at its end
+            const uint32_t need = bytes0 + tile_bytes + 4 * ((items0 + tile_items) / 32 + 1);
+            if (need > cap) { if (tid == 0) sm.status = ST_BUF; __syncthreads(); break; }
+
+            // ---- flag words of this tile ----
+            const uint32_t w_first = items0 >> 5;
+            for (int i = tid; i < LZF_TILE / 32 + 2; i += XPE_THREADS) { sm.flagw[i] = (i == 0) ? sm.cur_flags : 0; sm.flagpos[i] = (i == 0) ? sm.cur_flagpos : 0; }
+            __syncthreads();
+            // ---- emit ----
+            {
+                uint32_t k = items0 + (uint32_t)excl, b = bytes0 + (uint32_t)(excl >> 32), q = nib_excl;
+#pragma unroll
+                for (int i = 0; i < XPE_PER_THREAD; ++i) {
+                    const int r = tid * XPE_PER_THREAD + i;
+                    if ((sm.lz.V[r >> 5] >> (r & 31)) & 1) {
+                        const uint32_t lo = sm.lz.lenoff[r];
+                        uint32_t pos = b + 4 * ((k >> 5) + 1);
+                        if ((k & 31) == 0) sm.flagpos[(k >> 5) - w_first] = pos - 4;
+                        if (lo) {
+                            const uint32_t lm3 = (lo >> 16) + 1 - 3, off = lo & 0xFFFFu;
+                            const uint32_t sym = ((off - 1) << 3) | min(lm3, 7u);
+                            atomicOr(&sm.flagw[(k >> 5) - w_first], 0x80000000u >> (k & 31));
+                            o[pos] = (uint8_t)sym; o[pos + 1] = (uint8_t)(sym >> 8);
+                            uint32_t e = pos + 2, sz = 2;
+                            if (lm3 >= 7) {
+                                const uint32_t nv = min(lm3 - 7, 15u);
+                                if ((q & 1) == 0) { o[e] = (uint8_t)nv; sm.nibpos[q - nibs0] = e; ++e; ++sz; }
+                                else sm.nibpos[q - nibs0] = 0x80000000u | nv;          // to be OR-ed into the previous user's byte
+                                ++q;
+                                if (lm3 - 7 >= 15) {
+                                    o[e++] = (uint8_t)min(lm3 - 22, 255u); ++sz;
+                                    if (lm3 - 22 >= 255) { o[e] = (uint8_t)lm3; o[e + 1] = (uint8_t)(lm3 >> 8); sz += 2; }
+                                }
+                            }
+                            b += sz;
+                        } else { o[pos] = src[t0 + r]; b += 1; }
+                        ++k;
+                    }
+                }
+            }
+            __syncthreads();
+            // nibble users of the tile (= last thread's inclusive count); the odd-ranked ones complete the previous byte
+            if (tid == XPE_THREADS - 1) sm.wsum[0] = (unsigned long long)(nib_excl + my_nibs - nibs0);
+            __syncthreads();
+            const uint32_t tile_nibs = (uint32_t)sm.wsum[0];
+            for (uint32_t j = tid; j < tile_nibs; j += XPE_THREADS) {
+                const uint32_t e = sm.nibpos[j];
+                if (e & 0x80000000u) {                                     // odd-ranked user
+                    const uint32_t where = (j == 0) ? sm.pend_half : sm.nibpos[j - 1];
+                    o[where] = (uint8_t)(o[where] | ((e & 15u) << 4));
+                }
+            }
+            // complete flag words go out; the last (possibly partial) one is carried
+            const uint32_t w_last = (items0 + tile_items) >> 5;            // word that receives the next item
+            for (uint32_t w = w_first + tid; w < w_last; w += XPE_THREADS) {
+                const uint32_t fv = sm.flagw[w - w_first], fp = sm.flagpos[w - w_first];
+                o[fp] = (uint8_t)fv; o[fp + 1] = (uint8_t)(fv >> 8); o[fp + 2] = (uint8_t)(fv >> 16); o[fp + 3] = (uint8_t)(fv >> 24);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                if (tile_nibs) {
+                    const uint32_t lastq = tile_nibs - 1;
+                    if (!(sm.nibpos[lastq] & 0x80000000u)) sm.pend_half = sm.nibpos[lastq];
+                }
+                sm.items = items0 + tile_items; sm.bytes = bytes0 + tile_bytes; sm.nibs = nibs0 + tile_nibs;
+                if (((items0 + tile_items) & 31) == 0) {
+                    // the word for the next 32 items is reserved right after the last item (:317-324)
+                    sm.cur_flags = 0; sm.cur_flagpos = bytes0 + tile_bytes + 4 * (w_last);
+                } else { sm.cur_flags = sm.flagw[w_last - w_first]; sm.cur_flagpos = sm.flagpos[w_last - w_first]; }
+            }
+            __syncthreads();
+        }
+        if (tid == 0) {
+            uint32_t total = 0;
+            if (sm.status == ST_OK) {
+                const uint32_t cnt = sm.items & 31;
+                uint32_t fv, fp;
+                if (n == 0) { fv = 0xFFFFFFFFu; fp = 0; total = 4; }
+                else {
+                    fp = sm.cur_flagpos;
+                    fv = cnt ? (sm.cur_flags | (0xFFFFFFFFu >> cnt)) : 0xFFFFFFFFu;     // :343
+                    total = sm.bytes + 4 * ((sm.items >> 5) + 1);
+                }
+                if (total > cap) sm.status = ST_BUF;
+                else { o[fp] = (uint8_t)fv; o[fp + 1] = (uint8_t)(fv >> 8); o[fp + 2] = (uint8_t)(fv >> 16); o[fp + 3] = (uint8_t)(fv >> 24); }
+            }
+            out_len[u] = sm.status == ST_OK ? total : 0;
+            status[u] = sm.status;
+        }
+        __syncthreads();
+    }
+}
+
+} // namespace msc

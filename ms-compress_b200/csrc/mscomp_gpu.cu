@@ -5,6 +5,10 @@
 #include "kernels/lznt1_encode.cuh"
 #include "kernels/compact.cuh"
 #include "kernels/summary.cuh"
+#include "kernels/xhuff_decode.cuh"
+#include "kernels/xpress_decode.cuh"
+#include "kernels/xhuff_encode.cuh"
+#include "kernels/xpress_encode.cuh"
 #include <new>
 
 using namespace msc;
@@ -21,6 +25,12 @@ MSCompStatus msc_compact_slots(mscomp_gpu_ctx* ctx, const uint8_t* d_slots, uint
         MSC_LAUNCH(ctx, gather_slots_kernel, grid, 256, d_slots, stride, d_sizes, d_offs, n, d_dst);
     }
     return msc_cuda_status(cudaGetLastError(), "compact_slots");
+}
+
+MSCompStatus msc_summarize(mscomp_gpu_ctx* ctx, const uint32_t* d_sizes, const int32_t* d_status, uint32_t n, mscomp_gpu_result* d_res)
+{
+    MSC_LAUNCH(ctx, summarize_kernel, 1, SUM_THREADS, d_sizes, d_status, n, 0u, (GpuResult*)d_res);
+    return msc_cuda_status(cudaGetLastError(), "summarize");
 }
 
 extern "C" {
@@ -138,6 +148,79 @@ MSCompStatus mscomp_gpu_lznt1_decompress(mscomp_gpu_ctx* ctx, const uint8_t* d_i
     }
     MSC_LAUNCH(ctx, summarize_kernel, 1, SUM_THREADS, sizes, status, nchunks, (uint32_t)LZNT1_CHUNK, (GpuResult*)d_result);
     return msc_cuda_status(cudaGetLastError(), "lznt1_decompress");
+}
+
+
+// ---- Xpress-Huffman / Xpress batches ---------------------------------------------------------------------------------
+
+static bool batch_ok(const mscomp_gpu_ctx* ctx, const uint8_t* d_in, const uint8_t* d_out, const mscomp_gpu_batch* b)
+{
+    return ctx && b && (b->count == 0 || (d_in && d_out && b->d_in_off && b->d_in_len && b->d_out_off && b->d_out_cap && b->d_out_len && b->d_status));
+}
+
+MSCompStatus msc_xpress_huff_compress_units(mscomp_gpu_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, const mscomp_gpu_batch* b, int eos_mode)
+{
+    if (!batch_ok(ctx, d_in, d_out, b)) return MSCOMP_ARG_ERROR;
+    if (!b->count) return MSCOMP_OK;
+    cudaSetDevice(ctx->device);
+    static bool attr_done = false;
+    if (!attr_done) { cudaFuncSetAttribute(xhuff_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(XhEncSmem)); attr_done = true; }
+    const uint32_t cap = (uint32_t)ctx->sm_count * 4;
+    const uint32_t grid = b->count < cap ? b->count : cap;
+    uint8_t* scratch = (uint8_t*)ctx->get(SC_AUX2, (size_t)grid * XHE_SCRATCH_BYTES + 64);
+    if (!scratch) return MSCOMP_MEM_ERROR;
+    const int prof_slot_ = ctx->prof_begin("xhuff_encode_kernel");
+    xhuff_encode_kernel<<<grid, XHE_THREADS, sizeof(XhEncSmem), ctx->stream>>>(d_in, d_out, b->count, b->d_in_off, b->d_in_len, b->d_out_off,
+                                                                                 b->d_out_cap, b->d_out_len, b->d_status, scratch, eos_mode);
+    ++ctx->launches;
+    ctx->prof_end(prof_slot_);
+    return msc_cuda_status(cudaGetLastError(), "xpress_huff_compress");
+}
+
+MSCompStatus mscomp_gpu_xpress_huff_compress_batch(mscomp_gpu_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, const mscomp_gpu_batch* b)
+{
+    return msc_xpress_huff_compress_units(ctx, d_in, d_out, b, 0);
+}
+
+MSCompStatus mscomp_gpu_xpress_huff_decompress_batch(mscomp_gpu_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, const mscomp_gpu_batch* b)
+{
+    if (!batch_ok(ctx, d_in, d_out, b)) return MSCOMP_ARG_ERROR;
+    if (!b->count) return MSCOMP_OK;
+    cudaSetDevice(ctx->device);
+    const uint32_t groups = (b->count + 31) / 32, cap = (uint32_t)ctx->sm_count * 5;
+    const int prof_slot_ = ctx->prof_begin("xhuff_decode_kernel");
+    xhuff_decode_kernel<<<groups < cap ? groups : cap, 32 * XHD_WARPS_PER_BLOCK, XHD_SMEM_BYTES, ctx->stream>>>(
+        d_in, d_out, b->count, b->d_in_off, b->d_in_len, b->d_out_off, b->d_out_cap, b->d_out_len, b->d_status);
+    ++ctx->launches;
+    ctx->prof_end(prof_slot_);
+    return msc_cuda_status(cudaGetLastError(), "xpress_huff_decompress");
+}
+
+MSCompStatus mscomp_gpu_xpress_compress_batch(mscomp_gpu_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, const mscomp_gpu_batch* b)
+{
+    if (!batch_ok(ctx, d_in, d_out, b)) return MSCOMP_ARG_ERROR;
+    if (!b->count) return MSCOMP_OK;
+    cudaSetDevice(ctx->device);
+    static bool attr_done = false;
+    if (!attr_done) { cudaFuncSetAttribute(xpress_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(XpEncSmem)); attr_done = true; }
+    const uint32_t cap = (uint32_t)ctx->sm_count * 4;
+    const int prof_slot_ = ctx->prof_begin("xpress_encode_kernel");
+    xpress_encode_kernel<<<b->count < cap ? b->count : cap, XPE_THREADS, sizeof(XpEncSmem), ctx->stream>>>(
+        d_in, d_out, b->count, b->d_in_off, b->d_in_len, b->d_out_off, b->d_out_cap, b->d_out_len, b->d_status);
+    ++ctx->launches;
+    ctx->prof_end(prof_slot_);
+    return msc_cuda_status(cudaGetLastError(), "xpress_compress");
+}
+
+MSCompStatus mscomp_gpu_xpress_decompress_batch(mscomp_gpu_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, const mscomp_gpu_batch* b)
+{
+    if (!batch_ok(ctx, d_in, d_out, b)) return MSCOMP_ARG_ERROR;
+    if (!b->count) return MSCOMP_OK;
+    cudaSetDevice(ctx->device);
+    const uint32_t groups = (b->count + 32 * XPD_WARPS_PER_BLOCK - 1) / (32 * XPD_WARPS_PER_BLOCK), cap = (uint32_t)ctx->sm_count * 8;
+    MSC_LAUNCH(ctx, xpress_decode_kernel, groups < cap ? groups : cap, 32 * XPD_WARPS_PER_BLOCK,
+               d_in, d_out, b->count, b->d_in_off, b->d_in_len, b->d_out_off, b->d_out_cap, b->d_out_len, b->d_status);
+    return msc_cuda_status(cudaGetLastError(), "xpress_decompress");
 }
 
 } // extern "C"

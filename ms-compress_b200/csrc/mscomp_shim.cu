@@ -178,6 +178,138 @@ extern "C" MSCompStatus lznt1_decompress(const_bytes in, size_t in_len, bytes ou
 }
 
 // =================================================================================================================
+// Xpress-Huffman and plain Xpress: the unit is the buffer
+// =================================================================================================================
+namespace {
+
+struct UnitBatch {
+    mscomp_gpu_batch b;
+    uint32_t* d_out_len;
+    int32_t* d_status;
+};
+
+// Uploads `count` unit descriptors into the context's scratch and fills a device-side batch.
+bool upload_units(mscomp_gpu_ctx* ctx, const std::vector<uint64_t>& in_off, const std::vector<uint32_t>& in_len,
+                  const std::vector<uint64_t>& out_off, const std::vector<uint32_t>& out_cap, UnitBatch* ub)
+{
+    const size_t n = in_off.size();
+    const size_t bytes = n * (8 + 8 + 4 + 4 + 4 + 4);
+    uint8_t* d = (uint8_t*)ctx->get(SC_AUX3, bytes + 64);
+    uint8_t* h = (uint8_t*)ctx->get_pinned(bytes + 512);
+    if (!d || !h) return false;
+    h += 256;                                         // the first 256 bytes of the mailbox are used for results
+    memcpy(h, in_off.data(), n * 8);
+    memcpy(h + n * 8, out_off.data(), n * 8);
+    memcpy(h + n * 16, in_len.data(), n * 4);
+    memcpy(h + n * 20, out_cap.data(), n * 4);
+    memset(h + n * 24, 0, n * 8);
+    cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    ub->b.count = (uint32_t)n;
+    ub->b.d_in_off = (const uint64_t*)d;
+    ub->b.d_out_off = (const uint64_t*)(d + n * 8);
+    ub->b.d_in_len = (const uint32_t*)(d + n * 16);
+    ub->b.d_out_cap = (const uint32_t*)(d + n * 20);
+    ub->b.d_out_len = ub->d_out_len = (uint32_t*)(d + n * 24);
+    ub->b.d_status = ub->d_status = (int32_t*)(d + n * 28);
+    return true;
+}
+
+typedef MSCompStatus (*batch_fn)(mscomp_gpu_ctx*, const uint8_t*, uint8_t*, const mscomp_gpu_batch*);
+
+// One buffer through a batch entry point: host in -> device -> host out.  dev_cap = capacity given to the kernel.
+MSCompStatus one_buffer(batch_fn fn, const char* what, const_bytes in, size_t in_len, bytes out, size_t* out_len, size_t dev_cap)
+{
+    if (!out_len || (!in && in_len) || (!out && *out_len)) return MSCOMP_ARG_ERROR;
+    if (in_len > 0xFFFFFFFFull) return MSCOMP_ARG_ERROR;          // the device batch interface uses 32-bit lengths
+    const size_t cap = *out_len;
+    if (dev_cap > 0xFFFFFFFFull) dev_cap = 0xFFFFFFFFull;
+    mscomp_gpu_ctx* ctx = msc_thread_ctx();
+    if (!ctx) return MSCOMP_MEM_ERROR;
+    uint8_t* d_in = (uint8_t*)ctx->get(SC_IN, in_len + 64);
+    uint8_t* d_out = (uint8_t*)ctx->get(SC_OUT, dev_cap + 64);
+    struct { uint32_t len; int32_t status; }* h_res = (decltype(h_res))ctx->get_pinned(256);
+    if (!d_in || !d_out || !h_res) return MSCOMP_MEM_ERROR;
+    UnitBatch ub;
+    if (!upload_units(ctx, {0}, {(uint32_t)in_len}, {0}, {(uint32_t)dev_cap}, &ub)) return MSCOMP_MEM_ERROR;
+    h_res = (decltype(h_res))ctx->get_pinned(256);                // (the mailbox may have been reallocated)
+    if (in_len) cudaMemcpyAsync(d_in, in, in_len, cudaMemcpyHostToDevice, ctx->stream);
+    MSCompStatus st = fn(ctx, d_in, d_out, &ub.b);
+    if (st != MSCOMP_OK) return st;
+    cudaMemcpyAsync(&h_res->len, ub.d_out_len, 4, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(&h_res->status, ub.d_status, 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if ((st = msc_cuda_status(cudaStreamSynchronize(ctx->stream), what)) != MSCOMP_OK) return st;
+    if (h_res->status < 0) return (MSCompStatus)h_res->status;
+    const size_t total = h_res->len;
+    if (total > cap) return MSCOMP_BUF_ERROR;
+    if (total) cudaMemcpyAsync(out, d_out, total, cudaMemcpyDeviceToHost, ctx->stream);
+    if ((st = msc_cuda_status(cudaStreamSynchronize(ctx->stream), what)) != MSCOMP_OK) return st;
+    *out_len = total;
+    return MSCOMP_OK;
+}
+} // namespace
+
+extern "C" size_t xpress_max_compressed_size(size_t in_len) { return in_len + 4 + 4 * (in_len / 32); }
+extern "C" size_t xpress_huff_max_compressed_size(size_t in_len) { return in_len + 34 + 258 + 258 * (in_len / 65536); }
+
+extern "C" MSCompStatus xpress_compress(const_bytes in, size_t in_len, bytes out, size_t* out_len)
+{   // one buffer = one stream = one thread block (the format has no independent sub-units)
+    return one_buffer(mscomp_gpu_xpress_compress_batch, "xpress_compress", in, in_len, out, out_len, xpress_max_compressed_size(in_len));
+}
+extern "C" MSCompStatus xpress_decompress(const_bytes in, size_t in_len, bytes out, size_t* out_len)
+{
+    return one_buffer(mscomp_gpu_xpress_decompress_batch, "xpress_decompress", in, in_len, out, out_len, out_len ? *out_len : 0);
+}
+extern "C" MSCompStatus xpress_huff_decompress(const_bytes in, size_t in_len, bytes out, size_t* out_len)
+{   // a multi-chunk stream is a serial chain (chunk lengths are implicit, matches cross chunks): one lane walks it
+    return one_buffer(mscomp_gpu_xpress_huff_decompress_batch, "xpress_huff_decompress", in, in_len, out, out_len, out_len ? *out_len : 0);
+}
+
+extern "C" MSCompStatus xpress_huff_compress(const_bytes in, size_t in_len, bytes out, size_t* out_len)
+{
+    if (!out_len || (!in && in_len) || (!out && *out_len)) return MSCOMP_ARG_ERROR;
+    if (in_len == 0) { *out_len = 0; return MSCOMP_OK; }                     // src/xpress_huff_compress.cpp:249
+    if (in_len > 0xFFFFFFFF0000ull) return MSCOMP_ARG_ERROR;
+    const size_t cap = *out_len;
+    mscomp_gpu_ctx* ctx = msc_thread_ctx();
+    if (!ctx) return MSCOMP_MEM_ERROR;
+    // Every 64 KiB chunk is compressed on its own (window reset per chunk, valid for the reference's decoder:
+    // SURVEY.md 0.2) by its own thread block into a slot; the slots are then packed into one stream.
+    const size_t nunits = (in_len + 65535) / 65536;
+    const size_t stride = 65536 + 256 + 64;
+    uint8_t* d_in = (uint8_t*)ctx->get(SC_IN, in_len + 64);
+    uint8_t* d_slots = (uint8_t*)ctx->get(SC_SLOTS, nunits * stride + 64);
+    uint8_t* d_out = (uint8_t*)ctx->get(SC_OUT, nunits * stride + 64);
+    uint64_t* d_offs = (uint64_t*)ctx->get(SC_OFFS, (nunits + 1) * sizeof(uint64_t));
+    if (!d_in || !d_slots || !d_out || !d_offs) return MSCOMP_MEM_ERROR;
+    std::vector<uint64_t> in_off(nunits), out_off(nunits);
+    std::vector<uint32_t> in_len_u(nunits), out_cap(nunits, (uint32_t)stride);
+    for (size_t u = 0; u < nunits; ++u) {
+        in_off[u] = u * 65536; out_off[u] = u * stride;
+        in_len_u[u] = (uint32_t)(in_len - u * 65536 < 65536 ? in_len - u * 65536 : 65536);
+    }
+    UnitBatch ub;
+    if (!upload_units(ctx, in_off, in_len_u, out_off, out_cap, &ub)) return MSCOMP_MEM_ERROR;
+    struct Res { uint64_t total; int32_t status; uint32_t pad; };
+    mscomp_gpu_result* d_res = (mscomp_gpu_result*)ctx->get(SC_RESULT, 256);
+    mscomp_gpu_result* h_res = (mscomp_gpu_result*)ctx->get_pinned(256);
+    if (!d_res || !h_res) return MSCOMP_MEM_ERROR;
+    cudaMemcpyAsync(d_in, in, in_len, cudaMemcpyHostToDevice, ctx->stream);
+    MSCompStatus st = msc_xpress_huff_compress_units(ctx, d_in, d_slots, &ub.b, 1);
+    if (st != MSCOMP_OK) return st;
+    if ((st = msc_summarize(ctx, ub.d_out_len, ub.d_status, (uint32_t)nunits, d_res)) != MSCOMP_OK) return st;
+    if ((st = msc_compact_slots(ctx, d_slots, stride, ub.d_out_len, (uint32_t)nunits, d_offs, d_out)) != MSCOMP_OK) return st;
+    cudaMemcpyAsync(h_res, d_res, sizeof(*h_res), cudaMemcpyDeviceToHost, ctx->stream);
+    if ((st = msc_cuda_status(cudaStreamSynchronize(ctx->stream), "xpress_huff_compress")) != MSCOMP_OK) return st;
+    if (h_res->status < 0) return (MSCompStatus)h_res->status;
+    const size_t total = (size_t)h_res->bytes;
+    if (total > cap) return MSCOMP_BUF_ERROR;
+    cudaMemcpyAsync(out, d_out, total, cudaMemcpyDeviceToHost, ctx->stream);
+    if ((st = msc_cuda_status(cudaStreamSynchronize(ctx->stream), "xpress_huff_compress")) != MSCOMP_OK) return st;
+    *out_len = total;
+    return MSCOMP_OK;
+}
+
+// =================================================================================================================
 // format dispatch (src/mscomp.cpp:87-132)
 // =================================================================================================================
 static MSCompStatus copy_engine(const_bytes in, size_t in_len, bytes out, size_t* out_len)

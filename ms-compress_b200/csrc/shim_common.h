@@ -13,6 +13,12 @@ mscomp_gpu_ctx* msc_thread_ctx();
 MSCompStatus msc_compact_slots(mscomp_gpu_ctx* ctx, const uint8_t* d_slots, uint64_t stride, const uint32_t* d_sizes,
                                uint32_t n, uint64_t* d_offs, uint8_t* d_dst);
 
+// reduce per-unit sizes / statuses into one mscomp_gpu_result (device)
+MSCompStatus msc_summarize(mscomp_gpu_ctx* ctx, const uint32_t* d_sizes, const int32_t* d_status, uint32_t n, mscomp_gpu_result* d_res);
+
+// Xpress-Huffman encoder over explicit units; eos_mode 1 = the units are consecutive chunks of one stream.
+extern "C" MSCompStatus msc_xpress_huff_compress_units(mscomp_gpu_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, const mscomp_gpu_batch* b, int eos_mode);
+
 #ifdef MSC_NO_XPRESS   // bring-up only
 #define MSC_XPRESS_COMPRESS nullptr
 #define MSC_XPRESS_DECOMPRESS nullptr

@@ -6,6 +6,9 @@
 #include "../../ms-compress_b200/csrc/kernels/compact.cuh"
 #include "../../ms-compress_b200/csrc/kernels/xhuff_decode.cuh"
 #include "../../ms-compress_b200/csrc/kernels/xpress_decode.cuh"
+#include "../../ms-compress_b200/csrc/kernels/xhuff_encode.cuh"
+#include "../../ms-compress_b200/csrc/kernels/xpress_encode.cuh"
+#include <vector>
 
 using emu::dim3e;
 
@@ -40,6 +43,22 @@ void emu_xpress_decode(const uint8_t* in, uint8_t* out, uint32_t count, const ui
                        const uint64_t* out_off, const uint32_t* out_cap, uint32_t* out_len, int32_t* status, uint32_t grid)
 {
     emu::launch(msc::xpress_decode_kernel, dim3e(grid), dim3e(32 * msc::XPD_WARPS_PER_BLOCK), in, out, count, in_off, in_len, out_off, out_cap, out_len, status);
+}
+
+
+void emu_xhuff_encode(const uint8_t* in, uint8_t* out, uint32_t count, const uint64_t* in_off, const uint32_t* in_len,
+                      const uint64_t* out_off, const uint32_t* out_cap, uint32_t* out_len, int32_t* status, uint32_t grid)
+{
+    std::vector<uint8_t> scratch((size_t)grid * msc::XHE_SCRATCH_BYTES + 64);
+    emu::launch(msc::xhuff_encode_kernel, dim3e(grid), dim3e(msc::XHE_THREADS), in, out, count, in_off, in_len, out_off, out_cap, out_len, status,
+                scratch.data(), 0);
+}
+
+
+void emu_xpress_encode(const uint8_t* in, uint8_t* out, uint32_t count, const uint64_t* in_off, const uint32_t* in_len,
+                       const uint64_t* out_off, const uint32_t* out_cap, uint32_t* out_len, int32_t* status, uint32_t grid)
+{
+    emu::launch(msc::xpress_encode_kernel, dim3e(grid), dim3e(msc::XPE_THREADS), in, out, count, in_off, in_len, out_off, out_cap, out_len, status);
 }
 
 }
