@@ -120,27 +120,43 @@ __device__ __forceinline__ int lznt1_decode_payload(const uint8_t* __restrict__ 
         // ---- 3. emit the valid groups -----------------------------------------------------------------
         {
             const bool mine = lane < G;
-            int j = 0, o = my + 1, pos = gs;
-            int m_len = 0, m_off = 0;
-            bool pending = false, bad = false;
-            // advance: write literals until the next token (or the end of the group)
-#define LZNT1_ADVANCE()                                                                                   \
-            pending = false;                                                                              \
-            while (mine && j < 8 && o < n) {                                                              \
-                if ((myf >> j) & 1) {                                                                     \
-                    const int t = s_in[o] | (s_in[o + 1] << 8);                                           \
-                    m_len = (t & mask) + 3; m_off = (t >> S) + 1;                                         \
-                    if (m_off > pos) bad = true; else pending = true;                                     \
-                    break;                                                                                \
-                }                                                                                         \
-                s_out[pos++] = s_in[o++]; ++j;                                                            \
+            // 3a. literals: every lane walks its (at most 8) items once; positions follow from the group start
+            unsigned mb = 0;                                   // my match items still to execute
+            if (mine) {
+                int o = my + 1, run = gs;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (o < n) {
+                        if ((myf >> j) & 1) {
+                            const int t = s_in[o] | (s_in[o + 1] << 8);
+                            run += (t & mask) + 3;
+                            o += 2;
+                            mb |= 1u << j;
+                        } else { s_out[run++] = s_in[o++]; }
+                    }
+                }
             }
-            LZNT1_ADVANCE();
+            // 3b. matches, in position order per lane, under the watermark rule.  The next match of a lane is found
+            //     with find-first-set; its input / output offsets follow from popcounts (tokens are 2 bytes, literals 1).
+            int acc = 0;                                       // output bytes of my matches executed so far
+            bool bad = false;
             for (;;) {
+                int pos = 0, m_len = 0, m_off = 0;
+                const bool pending = mb != 0;
+                if (pending) {
+                    const int j = __ffs((int)mb) - 1;
+                    const int tb = __popc(myf & ((1u << j) - 1));          // tokens before item j
+                    const int o = my + 1 + j + tb;
+                    pos = gs + (j - tb) + acc;
+                    const int t = s_in[o] | (s_in[o + 1] << 8);
+                    m_len = (t & mask) + 3; m_off = (t >> S) + 1;
+                    if (m_off > pos) { bad = true; mb = 0; }
+                }
                 __syncwarp();
-                const unsigned W = __reduce_min_sync(FULL, pending ? (unsigned)pos : 0xffffffffu);
+                const bool live = pending && !bad;
+                const unsigned W = __reduce_min_sync(FULL, live ? (unsigned)pos : 0xffffffffu);
                 if (W == 0xffffffffu) break;
-                const bool can = pending && ((unsigned)pos == W || (unsigned)(pos - m_off + m_len) <= W);
+                const bool can = live && ((unsigned)pos == W || (unsigned)(pos - m_off + m_len) <= W);
                 unsigned coop = __ballot_sync(FULL, can && m_len >= LZNT1_COOP_LEN);
                 if (can && m_len < LZNT1_COOP_LEN) {
                     for (int i = 0; i < m_len; ++i) s_out[pos + i] = s_out[pos - m_off + i];
@@ -151,9 +167,8 @@ __device__ __forceinline__ int lznt1_decode_payload(const uint8_t* __restrict__ 
                     const int d = __shfl_sync(FULL, pos, src), l = __shfl_sync(FULL, m_len, src), f = __shfl_sync(FULL, m_off, src);
                     lznt1_warp_match_copy(s_out, d, f, l);
                 }
-                if (can) { pos += m_len; o += 2; ++j; LZNT1_ADVANCE(); }
+                if (can) { acc += m_len; mb &= mb - 1; }
             }
-#undef LZNT1_ADVANCE
             if (__ballot_sync(FULL, bad)) { err = ST_DATA; break; }
         }
         P = Pend;

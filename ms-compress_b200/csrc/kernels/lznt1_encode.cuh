@@ -107,20 +107,23 @@ lznt1_encode_kernel(const uint8_t* __restrict__ in, uint64_t in_len, uint32_t nc
         __syncthreads();   // cnt[h] now = end offset of bucket h; begin = cnt[h-1] (0 for h == 0)
 
         // ---- C: match search for every position ------------------------------------------------------
-        for (int p = tid; p < LZNT1_CHUNK; p += LZE_THREADS) {
+        // Threads take the positions in SORTED order: neighbouring lanes then sit in the same bucket with nearly the
+        // same number of candidates (the k-th entry of a bucket has k of them), which keeps the warp converged, and
+        // they read the same candidates (shared-memory broadcast).
+        for (int p = (npos > 0 ? npos : 0) + tid; p < LZNT1_CHUNK; p += LZE_THREADS) sm.lenoff[p] = 0;   // not indexed: no match
+        for (int idx = tid; idx < npos; idx += LZE_THREADS) {
+            const int p = sm.sorted[idx];
             uint32_t res = 0;
-            if (p > 0 && p < npos) {
+            if (p > 0) {
                 int S, lim;
                 lznt1_shift_limit(p, S, lim);
                 const int max_len = min(n - p, (1 << S) + 2);       // mask3 (src/lznt1_compress.cpp:51,:66)
                 const uint32_t key = lz_load4(sm.in, p);
                 const uint32_t h = lz_hash3(key);
                 int k = (h == 0) ? 0 : (int)sm.cnt[h - 1];
-                const int e = (int)sm.cnt[h];
                 int best = 0, bj = 0;
-                for (; k < e; ++k) {
+                for (; k < idx; ++k) {                              // earlier entries of my bucket = earlier positions
                     const int j = sm.sorted[k];
-                    if (j >= p) break;
                     if ((lz_load4(sm.in, j) ^ key) & 0xFFFFFFu) continue;
                     int i = 0;
                     while (i < max_len) {
@@ -134,34 +137,63 @@ lznt1_encode_kernel(const uint8_t* __restrict__ in, uint64_t in_len, uint32_t nc
                 if (best >= 3) res = (uint32_t)best | ((uint32_t)(p - bj) << 16);
             }
             sm.lenoff[p] = res;
-            const unsigned mm = __ballot_sync(FULL, res != 0);
+        }
+        __syncthreads();
+        for (int p = tid; p < LZNT1_CHUNK; p += LZE_THREADS) {
+            const unsigned mm = __ballot_sync(FULL, sm.lenoff[p] != 0);
             if (lane == 0) sm.M[p >> 5] = mm;
         }
         __syncthreads();
 
-        // ---- D: greedy parse (serial over matches) ----------------------------------------------------------
-        if (tid == 0) {
-            int p = 0;
-            uint32_t items = 0, matches = 0;
-            while (p < n) {
-                // next match position >= p
-                int w = p >> 5;
-                uint32_t bits = sm.M[w] & (0xffffffffu << (p & 31));
+        // ---- D: greedy parse p += max(1, len[p]) without a serial walk ------------------------------------------
+        // For a match position q the parse continues at nxt(q) = first match position >= q + len[q] (everything in
+        // between is literals).  The visited matches are the positions reachable from the first match by nxt; they are
+        // marked by pointer jumping (nxt <- nxt o nxt, 12 rounds cover any chain in a 4 KiB chunk).
+        {
+            uint16_t* cur = sm.sorted;                                                        // dead after stage C
+            uint16_t* oth = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(sm.cnt) + 8192);   // dead too
+            auto first_match_from = [&](int e) -> int {
+                if (e >= LZNT1_CHUNK) return LZNT1_CHUNK;
+                int w = e >> 5;
+                uint32_t bits = sm.M[w] & (0xffffffffu << (e & 31));
                 while (!bits && ++w < 128) bits = sm.M[w];
-                int q = bits ? (w * 32 + __ffs((int)bits) - 1) : n;
-                if (q > n) q = n;
-                // literals [p, q) and the match at q are visited
-                const int hi = (q < n) ? q + 1 : q;                 // visited range [p, hi)
-                for (int ww = p >> 5; ww <= ((hi - 1) >> 5) && hi > p; ++ww) {
-                    const int lo_b = max(p, ww * 32) - ww * 32, hi_b = min(hi, ww * 32 + 32) - ww * 32;   // [lo_b, hi_b)
-                    const uint32_t m = (hi_b == 32 ? 0xffffffffu : ((1u << hi_b) - 1)) & (0xffffffffu << lo_b);
-                    sm.V[ww] |= m;
+                return bits ? (w * 32 + __ffs((int)bits) - 1) : LZNT1_CHUNK;
+            };
+            auto or_range = [&](int lo, int hi) {                                             // V |= [lo, hi)
+                for (int w = lo >> 5; lo < hi && w <= ((hi - 1) >> 5); ++w) {
+                    const int lo_b = max(lo, w * 32) - w * 32, hi_b = min(hi, w * 32 + 32) - w * 32;
+                    atomicOr(&sm.V[w], (hi_b == 32 ? 0xffffffffu : ((1u << hi_b) - 1)) & (0xffffffffu << lo_b));
                 }
-                items += (uint32_t)(hi - p);
-                if (q < n) { ++matches; p = q + (int)(sm.lenoff[q] & 0xFFFF); }
-                else p = n;
+            };
+            for (int p = tid; p < LZNT1_CHUNK; p += LZE_THREADS)
+                cur[p] = (uint16_t)(((sm.M[p >> 5] >> (p & 31)) & 1) ? first_match_from(p + (int)(sm.lenoff[p] & 0xFFFF)) : LZNT1_CHUNK);
+            if (tid == 0) {
+                const int s0 = first_match_from(0);
+                if (s0 < LZNT1_CHUNK) sm.F[s0 >> 5] = 1u << (s0 & 31);                        // F doubles as the mark bitmap
+                or_range(0, min(s0, n));                                                      // leading literals
             }
-            sm.items = items; sm.matches = matches;
+            __syncthreads();
+            for (int round = 0; round < 12; ++round) {
+                for (int p = tid; p < LZNT1_CHUNK; p += LZE_THREADS) {
+                    if ((sm.M[p >> 5] >> (p & 31)) & 1) {
+                        const int t = cur[p];
+                        if (t < LZNT1_CHUNK && ((sm.F[p >> 5] >> (p & 31)) & 1)) atomicOr(&sm.F[t >> 5], 1u << (t & 31));
+                        oth[p] = (uint16_t)(t < LZNT1_CHUNK ? cur[t] : LZNT1_CHUNK);
+                    }
+                }
+                __syncthreads();
+                uint16_t* t2 = cur; cur = oth; oth = t2;
+            }
+            // visited bitmap: every visited match plus the literals up to the next visited match
+            for (int p = tid; p < LZNT1_CHUNK; p += LZE_THREADS) {
+                if ((sm.F[p >> 5] >> (p & 31)) & 1) {
+                    const int e = p + (int)(sm.lenoff[p] & 0xFFFF);
+                    or_range(p, p + 1);
+                    or_range(e, min(first_match_from(e), n));
+                }
+            }
+            __syncthreads();
+            if (tid < 128) sm.F[tid] = 0;
         }
         __syncthreads();
 
@@ -182,7 +214,8 @@ lznt1_encode_kernel(const uint8_t* __restrict__ in, uint64_t in_len, uint32_t nc
             }
         }
         __syncthreads();
-        const uint32_t items = sm.items, matches = sm.matches;
+        const uint32_t items = sm.prefV[127] + (uint32_t)__popc(sm.V[127]);
+        const uint32_t matches = sm.prefVM[127] + (uint32_t)__popc(sm.V[127] & sm.M[127]);
         const uint32_t ngroups = (items + 7) >> 3;
         const uint32_t total = items + ngroups + matches;
         const bool compressed = total < (uint32_t)n;                 // src/lznt1_compress.cpp:86, :245
