@@ -10,8 +10,8 @@
 //               (shared-memory table), candidate B = nearest earlier lane of the same warp with the same hash
 //               (__match_any_sync); both are verified / extended against the input itself
 //     insert  : atomicMax of (position+1) into the table          (deterministic: max = most recent)
-//   every 2048 positions: one thread does the greedy parse p += max(1, len[p]) over the match bitmap (it touches
-//   one word per match), leaving a "visited" bitmap; ranks inside it give every token its index.
+//   every 2048 positions: the greedy parse p += max(1, len[p]) is resolved by pointer jumping over the match bitmap,
+//   leaving a "visited" bitmap; ranks inside it give every token its index.
 //
 // Output bytes differ from the reference's (different candidate set); any greedy LZ77 parse with valid
 // (offset, length) pairs is a valid stream for the reference's decoders.
@@ -32,6 +32,9 @@ struct LzFrontSmem {
     uint32_t M[LZF_TILE / 32];         // match bitmap of the tile
     uint32_t V[LZF_TILE / 32];         // visited (= token start) bitmap of the tile
     uint32_t prefV[LZF_TILE / 32];     // exclusive prefix popcount of V
+    uint32_t K[LZF_TILE / 32];         // visited matches (marks of the pointer-jumping parse)
+    uint16_t nxt[2][LZF_TILE];         // nxt(q) = first match position >= q + len[q] (relative; LZF_TILE = leaves the tile)
+    uint32_t next_out;                 // furthest match end seen in this tile (relative)
     uint32_t next_p;                   // position (relative to the unit) where parsing resumes
     uint32_t ntok;                     // tokens emitted so far in the unit
 };
@@ -106,26 +109,61 @@ __device__ __forceinline__ uint32_t lzf_tile(LzFrontSmem& sm, const uint8_t* __r
         if (on) atomicMax(&sm.H[h], p + 1);
         __syncthreads();
     }
-    // greedy parse of the tile (serial over matches)
-    if (tid == 0) {
-        const uint32_t tend = min(t0 + LZF_TILE, n);
-        uint32_t p = sm.next_p;
-        for (int w = 0; w < LZF_TILE / 32; ++w) sm.V[w] = 0;
-        while (p < tend) {
-            const uint32_t r = p - t0;
-            int w = (int)(r >> 5);
-            uint32_t bits = sm.M[w] & (0xffffffffu << (r & 31));
+    // Greedy parse of the tile, p += max(1, len[p]), without a serial walk: for a match position q the parse continues
+    // at nxt(q) = first match position >= q + len[q]; the visited matches are those reachable from the first match at
+    // or after the carried-in position; they are marked by pointer jumping (nxt <- nxt o nxt).  A tile holds at most
+    // 2048 / 3 chained matches, so 10 rounds suffice.
+    {
+        const uint32_t tend_r = min(t0 + LZF_TILE, n) - t0;                 // tile length (relative)
+        const uint32_t start_r = sm.next_p > t0 ? sm.next_p - t0 : 0;       // >= tend_r when a long match skips the tile
+        auto first_match_from = [&](uint32_t e) -> uint32_t {               // relative position or LZF_TILE
+            if (e >= (uint32_t)LZF_TILE) return LZF_TILE;
+            uint32_t w = e >> 5;
+            uint32_t bits = sm.M[w] & (0xffffffffu << (e & 31));
             while (!bits && ++w < LZF_TILE / 32) bits = sm.M[w];
-            uint32_t q = bits ? (t0 + (uint32_t)w * 32 + (uint32_t)__ffs((int)bits) - 1) : tend;
-            if (q > tend) q = tend;
-            const uint32_t hi = (q < tend) ? q + 1 : q;             // visited: literals [p, q) and the match at q
-            for (uint32_t ww = (p - t0) >> 5; hi > p && ww <= ((hi - 1 - t0) >> 5); ++ww) {
-                const uint32_t lo_b = max(p - t0, ww * 32) - ww * 32, hi_b = min(hi - t0, ww * 32 + 32) - ww * 32;
-                sm.V[ww] |= (hi_b == 32 ? 0xffffffffu : ((1u << hi_b) - 1)) & (0xffffffffu << lo_b);
+            return bits ? (w * 32 + (uint32_t)__ffs((int)bits) - 1) : (uint32_t)LZF_TILE;
+        };
+        auto or_range = [&](uint32_t lo, uint32_t hi) {                     // V |= [lo, hi)
+            for (uint32_t w = lo >> 5; lo < hi && w <= ((hi - 1) >> 5); ++w) {
+                const uint32_t lo_b = max(lo, w * 32) - w * 32, hi_b = min(hi, w * 32 + 32) - w * 32;
+                atomicOr(&sm.V[w], (hi_b == 32 ? 0xffffffffu : ((1u << hi_b) - 1)) & (0xffffffffu << lo_b));
             }
-            p = (q < tend) ? q + (sm.lenoff[q - t0] >> 16) + 1 : tend;
+        };
+        uint16_t* cur = sm.nxt[0];
+        uint16_t* oth = sm.nxt[1];
+        for (int r = tid; r < LZF_TILE; r += LZF_THREADS)
+            cur[r] = (uint16_t)(((sm.M[r >> 5] >> (r & 31)) & 1) ? first_match_from((uint32_t)r + (sm.lenoff[r] >> 16) + 1) : (uint32_t)LZF_TILE);
+        if (tid < LZF_TILE / 32) { sm.V[tid] = 0; sm.K[tid] = 0; }
+        if (tid == 0) sm.next_out = 0;
+        __syncthreads();
+        if (tid == 0 && start_r < tend_r) {
+            const uint32_t s0 = first_match_from(start_r);
+            if (s0 < tend_r) sm.K[s0 >> 5] = 1u << (s0 & 31);
+            or_range(start_r, min(s0, tend_r));                             // leading literals
         }
-        sm.next_p = p;
+        __syncthreads();
+        for (int round = 0; round < 10; ++round) {
+            for (int r = tid; r < LZF_TILE; r += LZF_THREADS) {
+                if ((sm.M[r >> 5] >> (r & 31)) & 1) {
+                    const uint32_t t = cur[r];
+                    if (t < (uint32_t)LZF_TILE && ((sm.K[r >> 5] >> (r & 31)) & 1)) atomicOr(&sm.K[t >> 5], 1u << (t & 31));
+                    oth[r] = (uint16_t)(t < (uint32_t)LZF_TILE ? cur[t] : (uint32_t)LZF_TILE);
+                }
+            }
+            __syncthreads();
+            uint16_t* t2 = cur; cur = oth; oth = t2;
+        }
+        // visited = marked matches + the literals up to the next marked match; carry-out = furthest match end
+        for (int r = tid; r < LZF_TILE; r += LZF_THREADS) {
+            if ((sm.K[r >> 5] >> (r & 31)) & 1) {
+                const uint32_t e = (uint32_t)r + (sm.lenoff[r] >> 16) + 1;
+                or_range((uint32_t)r, (uint32_t)r + 1);
+                or_range(e, min(first_match_from(e), tend_r));
+                atomicMax(&sm.next_out, e);
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && start_r < tend_r) sm.next_p = t0 + max(sm.next_out, tend_r);
     }
     __syncthreads();
     if (tid < 32) {     // exclusive prefix popcount of V (64 words, 2 per lane)

@@ -7,9 +7,9 @@
 // Per buffer the format is strictly serial: codes are variable length, raw length bytes are interleaved at the
 // reader's BYTE cursor (Bitstream.h:104-106) and a chunk's length is stored nowhere -- so a lane
 // keeps the reference's exact reader state (32-bit window, valid-bit count, byte cursor) and walks its buffer
-// chunk after chunk; parallelism comes from the batch.  Symbols become tokens in a shared-memory queue and are
-// executed by the whole warp (lz_exec.cuh).  A multi-chunk stream produced by the reference (cross-chunk matches,
-// implicit chunk boundaries) decodes on the same path.
+// chunk after chunk; parallelism comes from the batch.  Literals and match copies go through a per-lane output
+// cursor that stores whole 8-byte words (lane_out.cuh).  A multi-chunk stream produced by the reference
+// (cross-chunk matches, implicit chunk boundaries) decodes on the same path.
 //
 // Canonical decoding without a big lookup table: the per-length limits of the left-aligned 15-bit code space
 // (`lims`, HuffmanDecoder.h:58-76) live in 8 registers as packed 16-bit pairs; the code length is
@@ -18,6 +18,7 @@
 #pragma once
 #include "common.cuh"
 #include "lz_exec.cuh"
+#include "lane_out.cuh"
 
 namespace msc {
 
@@ -30,7 +31,6 @@ struct XhWarpSmem {
     uint16_t syms[XH_SYMS * 32];         // syms[i * 32 + lane]
     int16_t base[16 * 32];               // base[n * 32 + lane]; doubles as the per-length counters while building
     uint16_t fill[16 * 32];              // table build only: next free slot per length
-    uint32_t q[32 * LZQ_STRIDE];
 };
 constexpr int XHD_WARPS_PER_BLOCK = 1;
 constexpr size_t XHD_SMEM_BYTES = sizeof(XhWarpSmem) * XHD_WARPS_PER_BLOCK;
@@ -51,8 +51,7 @@ struct XhLane {
     // decode tables
     uint32_t lims2[8];                   // lims[1..15] packed: lims2[k] = lims[2k+1] | lims[2k+2] << 16 (lims[16] = 0xFFFF filler)
     // progress
-    uint32_t opos, chunk_end;
-    uint32_t pend_len, pend_off;         // rest of a match longer than LZQ_MAXLEN
+    uint32_t chunk_end;
     int status;                          // 0 running, 1 finished OK, <0 error
     bool need_table;
 };
@@ -137,28 +136,20 @@ __device__ __forceinline__ uint32_t xh_decode_symbol(XhLane& L, const XhWarpSmem
     return sm.syms[idx * 32 + lane];
 }
 
-// Parse up to LZQ_TOKENS tokens of this lane's stream into its queue; returns the number queued.
-__device__ __forceinline__ int xh_parse_round(XhLane& L, XhWarpSmem& sm, int lane)
+// Decode this lane's whole stream (xpress_huff_decompress :143-159 around xpress_huff_decompress_chunk :39-135).
+__device__ __forceinline__ void xh_run(XhLane& L, XhWarpSmem& sm, int lane, LaneOut& O)
 {
-    uint32_t* q = sm.q + lane * LZQ_STRIDE;
-    int nt = 0;
-    while (nt < LZQ_TOKENS && L.status == 0) {
-        if (L.pend_len) {                                           // continue a long match
-            const uint32_t l = L.pend_len > LZQ_MAXLEN ? LZQ_MAXLEN : L.pend_len;
-            q[nt++] = lzq_match(L.pend_off, l);
-            L.pend_len -= l; L.opos += l;
-            continue;
-        }
-        if (L.need_table) {                                         // start of a chunk (xpress_huff_decompress :143-157)
+    while (L.status == 0) {
+        if (L.need_table) {                                         // start of a chunk (:143-157)
             if (L.in_len - L.ip < (uint32_t)XH_MIN_DATA) { L.status = (L.ip == L.in_len) ? 1 : ST_DATA; break; }
             if (!xh_build_table(L, sm, lane, L.ip)) { L.status = ST_DATA; break; }
             L.mask = (xh_rd16(L, L.ip + 256) << 16) | xh_rd16(L, L.ip + 258);
             L.bits = 32;
             L.ip += 260;
-            L.chunk_end = L.opos + XH_CHUNK;
+            L.chunk_end = O.opos + XH_CHUNK;
             L.need_table = false;
         }
-        if (!(L.opos < L.chunk_end || !xh_mask_is_zero(L))) {       // end of chunk (:79, :127-133)
+        if (!(O.opos < L.chunk_end || !xh_mask_is_zero(L))) {       // end of chunk (:79, :127-133)
             XhLane T = L;                                            // trial decode of an end-of-stream symbol
             const uint32_t s2 = xh_decode_symbol(T, sm, lane);
             if (s2 == (uint32_t)XH_EOS && T.in_len - T.ip == 0 && xh_mask_is_zero(T)) { L.status = 1; break; }
@@ -166,15 +157,11 @@ __device__ __forceinline__ int xh_parse_round(XhLane& L, XhWarpSmem& sm, int lan
             continue;
         }
         const uint32_t sym = xh_decode_symbol(L, sm, lane);
-#ifdef XHDBG
-        if (lane==0) printf("sym=%x bits=%d mask=%08x ip=%u opos=%u\n", sym, L.bits, L.mask, L.ip, L.opos);
-#endif
         if (sym == 0xFFFFu) { L.status = ST_DATA; break; }
         if (sym == (uint32_t)XH_EOS && L.in_len - L.ip == 0 && xh_mask_is_zero(L)) { L.status = 1; break; }   // :83
         if (sym < 256) {
-            if (L.opos == L.cap) { L.status = ST_BUF; break; }
-            q[nt++] = lzq_lit(sym);
-            L.opos += 1;
+            if (O.opos == L.cap) { L.status = ST_BUF; break; }
+            O.put_byte(sym);
         } else {
             uint32_t len = sym & 15;
             if (len == 15) {
@@ -197,15 +184,11 @@ __device__ __forceinline__ int xh_parse_round(XhLane& L, XhWarpSmem& sm, int lan
             if (off_bits > L.bits) { L.status = ST_DATA; break; }
             const uint32_t off = xh_peek(L, off_bits) + (1u << off_bits);
             xh_skip(L, off_bits);
-            if (L.opos < off) { L.status = ST_DATA; break; }             // :113
-            if (L.cap - L.opos < len) { L.status = ST_BUF; break; }      // :114
-            const uint32_t l = len > LZQ_MAXLEN ? LZQ_MAXLEN : len;
-            q[nt++] = lzq_match(off, l);
-            L.opos += l;
-            L.pend_len = len - l; L.pend_off = off;
+            if (O.opos < off) { L.status = ST_DATA; break; }             // :113
+            if (L.cap - O.opos < len) { L.status = ST_BUF; break; }      // :114
+            O.copy_match(off, len);
         }
     }
-    return nt;
 }
 
 // Batch decode: buffer i = in[in_off[i] .. +in_len[i]) -> out[out_off[i] .. +out_cap[i]); out_len / status per buffer.
@@ -222,25 +205,22 @@ xhuff_decode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, u
     for (uint32_t g = blockIdx.x * XHD_WARPS_PER_BLOCK + (threadIdx.x >> 5); g * 32 < count; g += warps_total) {
         const uint32_t i = g * 32 + lane;
         XhLane L;
-        L.status = 1; L.opos = 0; L.pend_len = 0; L.pend_off = 0; L.in = in; L.in_len = 0; L.cap = 0; L.ip = 0;
+        L.status = 1; L.in = in; L.in_len = 0; L.cap = 0; L.ip = 0;
         L.mask = 0; L.bits = 0; L.chunk_end = 0; L.need_table = true;
 #pragma unroll
         for (int k = 0; k < 8; ++k) L.lims2[k] = 0xFFFFFFFFu;
-        uint8_t* o = out;
+        LaneOut O;
+        O.init(out);
         if (i < count) {
             L.in = in + in_off[i]; L.in_len = in_len[i]; L.cap = out_cap[i];
-            o = out + out_off[i];
+            O.init(out + out_off[i]);
             L.status = 0;
         }
         L.win.init(L.in, L.in + L.in_len);
-        uint32_t done_pos = 0;                      // bytes already executed
-        for (;;) {
-            const int nt = xh_parse_round(L, sm, lane);
-            __syncwarp();
-            if (!__any_sync(FULL, nt > 0)) break;
-            lzq_execute(sm.q, nt, o, done_pos);
-        }
-        if (i < count) { out_len[i] = L.opos; status[i] = L.status == 1 ? ST_OK : L.status; }
+        xh_run(L, sm, lane, O);
+        O.finish();
+        __syncwarp();
+        if (i < count) { out_len[i] = O.opos; status[i] = L.status == 1 ? ST_OK : L.status; }
     }
 }
 

@@ -5,10 +5,11 @@
 //
 // The stream is one unbroken sequence of 32-item flag words interleaved with item bytes, plus a shared length
 // nibble whose partner can be arbitrarily far away: it has to be parsed serially, so a lane
-// parses its buffer into a token queue and the warp executes the copies (lz_exec.cuh).
+// walks its own buffer; its output goes through a cursor that stores whole 8-byte words (lane_out.cuh).
 #pragma once
 #include "common.cuh"
 #include "lz_exec.cuh"
+#include "lane_out.cuh"
 
 namespace msc {
 
@@ -17,10 +18,9 @@ constexpr int XPD_WARPS_PER_BLOCK = 4;
 struct XpLane {
     const uint8_t* in; uint32_t in_len; uint32_t cap;
     ByteWindow win;
-    uint32_t ip, opos;
+    uint32_t ip;
     uint32_t flags; bool flagged, have_flags;
     uint32_t half_val; bool has_half;        // value of the byte whose high nibble is still unused (:88-92)
-    uint32_t pend_len, pend_off;
     int status;                              // 0 running, 1 finished OK, < 0 error
 };
 
@@ -29,16 +29,9 @@ __device__ __forceinline__ uint32_t xp_rd32(XpLane& L, uint32_t at) { L.win.seek
 // all 1 bits above all 0 bits (src/xpress_decompress.cpp:41)
 __device__ __forceinline__ bool xp_set_bits_are_highest(uint32_t x) { x = ~x; return ((x + 1) & x) == 0; }
 
-__device__ __forceinline__ int xp_parse_round(XpLane& L, uint32_t* q)
+__device__ __forceinline__ void xp_run(XpLane& L, LaneOut& O)
 {
-    int nt = 0;
-    while (nt < LZQ_TOKENS && L.status == 0) {
-        if (L.pend_len) {
-            const uint32_t l = L.pend_len > LZQ_MAXLEN ? LZQ_MAXLEN : L.pend_len;
-            q[nt++] = lzq_match(L.pend_off, l);
-            L.pend_len -= l; L.opos += l;
-            continue;
-        }
+    while (L.status == 0) {
         if (!L.have_flags) {                                            // start a fragment (:425-430)
             if (L.ip + 4 > L.in_len) { L.status = ST_DATA; break; }     // :461
             const uint32_t f = xp_rd32(L, L.ip);
@@ -79,22 +72,18 @@ __device__ __forceinline__ int xp_parse_round(XpLane& L, uint32_t* q)
                 len += 0x7;
             }
             len += 0x3;
-            if (off > L.opos) { L.status = ST_DATA; break; }            // :442
-            if ((uint64_t)L.opos + len > L.cap) { L.status = ST_BUF; break; }     // :443
-            const uint32_t l = len > LZQ_MAXLEN ? LZQ_MAXLEN : len;
-            q[nt++] = lzq_match(off, l);
-            L.opos += l;
-            L.pend_len = len - l; L.pend_off = off;
+            if (off > O.opos) { L.status = ST_DATA; break; }            // :442
+            if ((uint64_t)O.opos + len > L.cap) { L.status = ST_BUF; break; }     // :443
+            O.copy_match(off, len);
         } else {
-            if (L.opos == L.cap) { L.status = ST_BUF; break; }          // :455
-            q[nt++] = lzq_lit(xp_rd32(L, L.ip));
-            L.ip += 1; L.opos += 1;
+            if (O.opos == L.cap) { L.status = ST_BUF; break; }          // :455
+            O.put_byte(xp_rd32(L, L.ip));
+            L.ip += 1;
         }
         L.flagged = (L.flags & 0x80000000u) != 0;
         L.flags <<= 1;
         if (L.flags == 0) L.have_flags = false;
     }
-    return nt;
 }
 
 __global__ void __launch_bounds__(32 * XPD_WARPS_PER_BLOCK)
@@ -103,20 +92,19 @@ xpress_decode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, 
                      const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ out_cap,
                      uint32_t* __restrict__ out_len, int32_t* __restrict__ status)
 {
-    __shared__ uint32_t s_q[XPD_WARPS_PER_BLOCK][32 * LZQ_STRIDE];
     const int lane = lane_id();
     const int wib = (int)(threadIdx.x >> 5);
-    uint32_t* q = s_q[wib];
     const uint32_t warps_total = gridDim.x * XPD_WARPS_PER_BLOCK;
     for (uint32_t g = blockIdx.x * XPD_WARPS_PER_BLOCK + wib; g * 32 < count; g += warps_total) {
         const uint32_t i = g * 32 + lane;
         XpLane L;
-        L.in = in; L.in_len = 0; L.cap = 0; L.ip = 0; L.opos = 0; L.flags = 0; L.flagged = false; L.have_flags = false;
-        L.half_val = 0; L.has_half = false; L.pend_len = 0; L.pend_off = 0; L.status = 1;
-        uint8_t* o = out;
+        L.in = in; L.in_len = 0; L.cap = 0; L.ip = 0; L.flags = 0; L.flagged = false; L.have_flags = false;
+        L.half_val = 0; L.has_half = false; L.status = 1;
+        LaneOut O;
+        O.init(out);
         if (i < count) {
             L.in = in + in_off[i]; L.in_len = in_len[i]; L.cap = out_cap[i];
-            o = out + out_off[i];
+            O.init(out + out_off[i]);
             L.status = 0;
             if (L.in_len < 5) {                                         // :414-418 (sic)
                 uint32_t w = 0;
@@ -125,14 +113,10 @@ xpress_decode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, 
             }
         }
         L.win.init(L.in, L.in + L.in_len);
-        uint32_t done_pos = 0;
-        for (;;) {
-            const int nt = xp_parse_round(L, q + lane * LZQ_STRIDE);
-            __syncwarp();
-            if (!__any_sync(FULL, nt > 0)) break;
-            lzq_execute(q, nt, o, done_pos);
-        }
-        if (i < count) { out_len[i] = L.opos; status[i] = L.status == 1 ? ST_OK : L.status; }
+        xp_run(L, O);
+        O.finish();
+        __syncwarp();
+        if (i < count) { out_len[i] = O.opos; status[i] = L.status == 1 ? ST_OK : L.status; }
     }
 }
 
