@@ -1,0 +1,93 @@
+// lznt1_decode_lanes.cuh -- LZNT1 chunk decoder, one LANE per 4 KiB chunk (32 chunks per warp).
+//
+// Same contract as lznt1_decode_kernel (lznt1_decode.cuh) -- replaces src/lznt1_decompress.cpp:37-121 and the per-chunk
+// part of :122-209 -- but with the opposite mapping: a lane walks its own chunk exactly like the reference's checked
+// loop (:77-116), so there is no chase / scan / watermark machinery and almost every instruction does useful work for
+// 32 chunks at once.  Input bytes come through a 16-byte register window (8-byte loads), output through LaneOut
+// (8-byte word stores, far matches read 8 bytes at a time from the chunk's own output in L2).  Runs of literal items
+// (consecutive 0 flags) are moved as one unit.  Used for large batches, where chunks outnumber the lanes of the GPU;
+// the warp-per-chunk kernel serves small batches.
+#pragma once
+#include "common.cuh"
+#include "lz_exec.cuh"
+#include "lane_out.cuh"
+#include "lznt1_decode.cuh"
+
+namespace msc {
+
+constexpr int LZL_WARPS_PER_BLOCK = 4;
+
+__global__ void __launch_bounds__(32 * LZL_WARPS_PER_BLOCK)
+lznt1_decode_lanes_kernel(const uint8_t* __restrict__ in, uint64_t in_len, const uint64_t* __restrict__ chunk_off, uint32_t nchunks,
+                          uint8_t* __restrict__ out, uint32_t* __restrict__ out_size, int32_t* __restrict__ status)
+{
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < nchunks; c += stride) {
+        const uint64_t start = chunk_off[c];
+        int st = ST_OK;
+        LaneOut O;
+        O.init(out + (uint64_t)c * LZNT1_CHUNK);
+        if (start + 2 > in_len) st = ST_BUF;
+        else {
+            const uint32_t hdr = (uint32_t)in[start] | ((uint32_t)in[start + 1] << 8);
+            const uint32_t n = (hdr & 0x0FFF) + 1;                       // payload bytes
+            if (hdr == 0) st = ST_DATA;
+            else if (start + 2 + n > in_len) st = ST_BUF;                // truncated chunk (reference: internal.h:627)
+            else if ((hdr & 0x7000) != 0x3000) st = ST_DATA;             // src/lznt1_decompress.cpp:152
+            else {
+                const uint8_t* src = in + start + 2;
+                ByteWindow win;
+                win.init(src, src + n);
+                uint32_t ip = 0;
+                if (!(hdr & 0x8000)) {                                   // stored chunk :188-206
+                    while (ip < n) {
+                        const uint32_t k = min(n - ip, 8u);
+                        win.seek(src + ip);
+                        uint64_t v = win.get32(src + ip);
+                        if (k > 4) { win.seek(src + ip + 4); v |= (uint64_t)win.get32(src + ip + 4) << 32; }
+                        if (O.opos < O.head) { for (uint32_t i = 0; i < k; ++i) O.put_byte((uint32_t)(v >> (8 * i))); }
+                        else O.put_bytes(v, k);
+                        ip += k;
+                    }
+                } else {
+                    while (ip < n && st == ST_OK) {
+                        win.seek(src + ip);
+                        uint32_t f = (win.get32(src + ip) & 0xFFu) | 0x100u;     // flag bits, LSB first, with a sentinel
+                        ++ip;
+                        while (f != 1u && st == ST_OK) {
+                            if (ip == n) { f = 1u; break; }                       // :86 input ends inside the group
+                            if (f & 1u) {                                         // token
+                                if (ip + 2 > n) { st = ST_DATA; break; }          // :90
+                                win.seek(src + ip);
+                                const uint32_t t = win.get32(src + ip) & 0xFFFFu;
+                                ip += 2;
+                                int S, lim;
+                                lznt1_shift_limit((int)O.opos, S, lim);           // :91
+                                const uint32_t len = (t & ((1u << S) - 1)) + 3, off = (t >> S) + 1;
+                                if (off > O.opos || O.opos + len > (uint32_t)LZNT1_CHUNK) { st = ST_DATA; break; }   // :98-99
+                                O.copy_match(off, len);
+                                f >>= 1;
+                            } else {                                              // run of literal items
+                                uint32_t k = (uint32_t)__ffs((int)f) - 1;         // consecutive 0 flags (<= 8: the sentinel stops it)
+                                k = min(k, n - ip);
+                                if (O.opos + k > (uint32_t)LZNT1_CHUNK) { st = ST_DATA; break; }
+                                win.seek(src + ip);
+                                uint64_t v = win.get32(src + ip);
+                                if (k > 4) { win.seek(src + ip + 4); v |= (uint64_t)win.get32(src + ip + 4) << 32; }
+                                if (O.opos < O.head) { for (uint32_t i = 0; i < k; ++i) O.put_byte((uint32_t)(v >> (8 * i))); }
+                                else O.put_bytes(v, k);
+                                ip += k;
+                                f >>= k;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        O.finish();
+        out_size[c] = st == ST_OK ? O.opos : 0;
+        status[c] = st;
+    }
+}
+
+} // namespace msc

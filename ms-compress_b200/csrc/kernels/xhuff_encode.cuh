@@ -43,6 +43,7 @@ struct XhEncSmem {
     uint32_t blc[16];                  // codes per length
     uint32_t nused, raw_total, bits_total, scan_tmp[8];
     unsigned long long bit_carry;      // running (bits << 32 | raw bytes) between token tiles
+    unsigned long long wsum[XHE_THREADS / 32];   // per-warp partial sums of the block scans
 };
 
 __device__ __forceinline__ uint32_t xhe_sym_of(uint32_t tok)
@@ -223,9 +224,9 @@ xhuff_encode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, u
                         }
                     }
                     for (int d = 16; d; d >>= 1) local += __shfl_xor_sync(FULL, local, d);
-                    if (lane == 0) reinterpret_cast<unsigned long long*>(sm.w)[warp] = local;
+                    if (lane == 0) sm.wsum[warp] = local;
                     __syncthreads();
-                    if (tid == 0) { unsigned long long t = 0; for (int i = 0; i < XHE_THREADS / 32; ++i) t += reinterpret_cast<unsigned long long*>(sm.w)[i]; sm.bits_total = (uint32_t)(t >> 32); }
+                    if (tid == 0) { unsigned long long t = 0; for (int i = 0; i < XHE_THREADS / 32; ++i) t += sm.wsum[i]; sm.bits_total = (uint32_t)(t >> 32); }
                     __syncthreads();
                 }
                 // raw bytes: counted from the tokens (only length symbols with nibble 15 carry them)
@@ -266,10 +267,10 @@ xhuff_encode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, u
                 }
                 unsigned long long v = ((unsigned long long)(cl + ob) << 32) | raw, incl = v;
                 for (int d = 1; d < 32; d <<= 1) { const unsigned long long x = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += x; }
-                if (lane == 31) reinterpret_cast<unsigned long long*>(sm.w)[warp] = incl;
+                if (lane == 31) sm.wsum[warp] = incl;
                 __syncthreads();
                 unsigned long long base = sm.bit_carry;
-                for (int w2 = 0; w2 < warp; ++w2) base += reinterpret_cast<unsigned long long*>(sm.w)[w2];
+                for (int w2 = 0; w2 < warp; ++w2) base += sm.wsum[w2];
                 const unsigned long long excl = base + incl - v;
                 if (k < ntok) {
                     const uint32_t B0 = (uint32_t)(excl >> 32), R0 = (uint32_t)excl;

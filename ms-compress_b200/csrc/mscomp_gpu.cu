@@ -3,6 +3,9 @@
 #include "shim_common.h"
 #include "kernels/lznt1_decode.cuh"
 #include "kernels/lznt1_encode.cuh"
+#include "kernels/lznt1_decode_lanes.cuh"
+#include <stdlib.h>
+#include <string.h>
 #include "kernels/compact.cuh"
 #include "kernels/summary.cuh"
 #include "kernels/xhuff_decode.cuh"
@@ -141,10 +144,21 @@ MSCompStatus mscomp_gpu_lznt1_decompress(mscomp_gpu_ctx* ctx, const uint8_t* d_i
     int32_t* status = d_chunk_status ? d_chunk_status : (int32_t*)ctx->get(SC_STATUS, ((size_t)nchunks + 1) * sizeof(int32_t));
     if (!sizes || !status) return MSCOMP_MEM_ERROR;
     if (nchunks) {
-        const uint32_t blocks = (nchunks + LZNT1_WARPS_PER_BLOCK - 1) / LZNT1_WARPS_PER_BLOCK;
-        const uint32_t cap = (uint32_t)ctx->sm_count * 6 * 4;                 // 6 resident blocks per SM, a few waves
-        MSC_LAUNCH(ctx, lznt1_decode_kernel, blocks < cap ? blocks : cap, LZNT1_WARPS_PER_BLOCK * 32,
-                   d_in, (uint64_t)in_len, d_chunk_off, nchunks, d_out, sizes, status);
+        // Two mappings of the same decoder: a lane per chunk when the batch has enough chunks to fill the GPU's lanes
+        // (far fewer instructions per chunk), a warp per chunk otherwise.  MSCOMP_LZNT1_DECODE=warp|lanes overrides.
+        static const char* mode = getenv("MSCOMP_LZNT1_DECODE");
+        const bool lanes = mode ? (strcmp(mode, "lanes") == 0) : (nchunks >= (uint32_t)ctx->sm_count * 256);
+        if (lanes) {
+            const uint32_t tpb = 32 * LZL_WARPS_PER_BLOCK;
+            const uint32_t blocks = (nchunks + tpb - 1) / tpb, cap = (uint32_t)ctx->sm_count * 16;
+            MSC_LAUNCH(ctx, lznt1_decode_lanes_kernel, blocks < cap ? blocks : cap, tpb,
+                       d_in, (uint64_t)in_len, d_chunk_off, nchunks, d_out, sizes, status);
+        } else {
+            const uint32_t blocks = (nchunks + LZNT1_WARPS_PER_BLOCK - 1) / LZNT1_WARPS_PER_BLOCK;
+            const uint32_t cap = (uint32_t)ctx->sm_count * 6 * 4;             // 6 resident blocks per SM, a few waves
+            MSC_LAUNCH(ctx, lznt1_decode_kernel, blocks < cap ? blocks : cap, LZNT1_WARPS_PER_BLOCK * 32,
+                       d_in, (uint64_t)in_len, d_chunk_off, nchunks, d_out, sizes, status);
+        }
     }
     MSC_LAUNCH(ctx, summarize_kernel, 1, SUM_THREADS, sizes, status, nchunks, (uint32_t)LZNT1_CHUNK, (GpuResult*)d_result);
     return msc_cuda_status(cudaGetLastError(), "lznt1_decompress");

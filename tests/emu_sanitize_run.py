@@ -1,0 +1,28 @@
+"""Driven by tests/test_emu_sanitized.py in a subprocess with libasan/libubsan preloaded: every kernel, every format,
+on tests/emu/libemu_san.so (the kernels compiled with -fsanitize=address,undefined)."""
+import os
+import sys, ctypes
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'tests')); sys.path.insert(0, ROOT)
+import mscompress_b200 as ms, emu_util
+emu=ctypes.CDLL(os.path.join(ROOT, 'tests', 'emu', 'libemu_san.so'))
+orc=ctypes.CDLL(os.path.join(ROOT, 'oracle', 'liboracle.so'))
+def ocall(name,data,cap):
+    out=ctypes.create_string_buffer(max(cap,1)); n=ctypes.c_size_t(cap)
+    rc=getattr(orc,'orc_'+name)(data,ctypes.c_size_t(len(data)),out,ctypes.byref(n)); return rc,out.raw[:n.value]
+MAX={"xpress": lambda n: n + 4 + 4 * (n // 32), "xpress_huff": lambda n: n + 34 + 258 + 258 * (n // 65536)}
+plains=[ms.generate(k,n,5) for k in ('text','runs','random') for n in (1,100,5000,70000,140000)]
+for fmt,(dk,ek) in {"xpress_huff":("emu_xhuff_decode","emu_xhuff_encode"),"xpress":("emu_xpress_decode","emu_xpress_encode")}.items():
+    st,ol,outs=emu_util.emu_batch(emu,ek,plains,[MAX[fmt](len(p)) for p in plains])
+    assert not st.any()
+    for p,c in zip(plains,outs): assert ocall(fmt+'_decompress',c,len(p))==(0,p)
+    st,ol,outs2=emu_util.emu_batch(emu,dk,outs,[len(p) for p in plains])
+    assert not st.any() and outs2==plains
+    print(fmt,'ok')
+for kern in ("emu_lznt1_decode","emu_lznt1_decode_lanes"):
+    for p in plains:
+        rc,c=ocall('lznt1_compress',p,len(p)+100)
+        st,sz,ch=emu_util.emu_lznt1_decode(emu,c,kernel=kern); assert not st.any() and b''.join(ch)==p
+        e,_=emu_util.emu_lznt1_encode(emu,p); assert e==c
+    print(kern,'ok')
+print('sanitized run ok')

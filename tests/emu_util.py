@@ -29,7 +29,7 @@ def lznt1_walk(c):
     return offs
 
 
-def emu_lznt1_decode(emu, comp, offs=None, grid=3):
+def emu_lznt1_decode(emu, comp, offs=None, grid=3, kernel="emu_lznt1_decode"):
     offs = lznt1_walk(comp) if offs is None else offs
     nch = len(offs)
     a, addr = padded(comp)
@@ -37,7 +37,7 @@ def emu_lznt1_decode(emu, comp, offs=None, grid=3):
     out = np.zeros(nch * 4096 + PAD, dtype=np.uint8)
     sz = np.zeros(max(nch, 1), dtype=np.uint32)
     st = np.zeros(max(nch, 1), dtype=np.int32)
-    emu.emu_lznt1_decode(ctypes.c_void_p(addr), ctypes.c_uint64(len(comp)), P(off), ctypes.c_uint32(nch), P(out), P(sz), P(st),
+    getattr(emu, kernel)(ctypes.c_void_p(addr), ctypes.c_uint64(len(comp)), P(off), ctypes.c_uint32(nch), P(out), P(sz), P(st),
                          ctypes.c_uint32(grid))
     chunks = [out[i * 4096:i * 4096 + sz[i]].tobytes() for i in range(nch)]
     return st[:nch], sz[:nch], chunks

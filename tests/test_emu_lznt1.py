@@ -9,12 +9,16 @@ from emu_util import emu_lznt1_decode, emu_lznt1_encode, lznt1_walk
 SIZES = [1, 2, 3, 4, 7, 8, 9, 16, 17, 31, 32, 33, 100, 4095, 4096, 4097, 8193, 65536, 150000]
 
 
+KERNELS = ["emu_lznt1_decode", "emu_lznt1_decode_lanes"]      # warp per chunk, lane per chunk
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("kind", ["text", "runs", "random"])
-def test_decode_matches_oracle(emu, oracle, ms, kind):
+def test_decode_matches_oracle(emu, oracle, ms, kind, kernel):
     for n in SIZES:
         plain = ms.generate(kind, n, 42 + n)
         comp = oracle.compress("lznt1", plain)
-        st, sz, chunks = emu_lznt1_decode(emu, comp)
+        st, sz, chunks = emu_lznt1_decode(emu, comp, kernel=kernel)
         assert not st.any() and b"".join(chunks) == plain, (kind, n)
 
 
@@ -32,7 +36,8 @@ def test_encode_degenerate_inputs(emu, oracle):
         assert got == oracle.compress("lznt1", plain)
 
 
-def test_decode_status_on_corrupted_chunks(emu, oracle, ms):
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_decode_status_on_corrupted_chunks(emu, oracle, ms, kernel):
     """Bit flips: per-chunk status and output equal the oracle's chunk decoder (src/lznt1_decompress.cpp:37-121)."""
     rnd = random.Random(3)
     f = oracle.lib.orc_lznt1_decompress_chunk
@@ -46,7 +51,7 @@ def test_decode_status_on_corrupted_chunks(emu, oracle, ms):
             for _ in range(rnd.randint(1, 4)):
                 b[rnd.randrange(len(b))] ^= 1 << rnd.randrange(8)
             b = bytes(b)
-            st, sz, chunks = emu_lznt1_decode(emu, b, offs)
+            st, sz, chunks = emu_lznt1_decode(emu, b, offs, kernel=kernel)
             for ci, p in enumerate(offs):
                 h = b[p] | (b[p + 1] << 8)
                 n = (h & 0xFFF) + 1
