@@ -63,12 +63,20 @@ struct mscomp_gpu_ctx {
 
 // Optional per-kernel timing (mscomp_gpu_profile_*): CUDA events recorded on the context's stream around every
 // launch; the benchmark uses it to report each kernel's device time for the roofline figures.
-#define MSC_LAUNCH(ctx, kernel, grid, block, ...)                                                   \
+#define MSC_LAUNCH_SMEM(ctx, kernel, grid, block, smem, ...)                                        \
     do {                                                                                            \
         const int prof_slot_ = (ctx)->prof_begin(#kernel);                                          \
-        kernel<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__);                                 \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                            \
         ++(ctx)->launches;                                                                          \
         (ctx)->prof_end(prof_slot_);                                                                \
+    } while (0)
+#define MSC_LAUNCH(ctx, kernel, grid, block, ...) MSC_LAUNCH_SMEM(ctx, kernel, grid, block, 0, __VA_ARGS__)
+
+// Kernels that need more than 48 KB of dynamic shared memory opt in once per process.
+#define MSC_OPT_IN_SMEM(kernel, bytes)                                                              \
+    do {                                                                                            \
+        static bool done_ = false;                                                                  \
+        if (!done_) { cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); done_ = true; } \
     } while (0)
 
 static inline MSCompStatus msc_cuda_status(cudaError_t e, const char* what)

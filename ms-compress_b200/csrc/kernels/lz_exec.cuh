@@ -30,12 +30,17 @@ struct ByteWindow {
     // make [p, p+4) readable from the window; cheap when p moves forward by a few bytes
     __device__ __forceinline__ void seek(const uint8_t* p)
     {
-        if (p < base) { init(p, lim); return; }                 // rewind (second pass over a code-length table)
-        while (p >= base + 8) {
-            if (p >= base + 16) { init(p, lim); return; }       // long jump (new chunk table etc.)
+        if (p >= base && p < base + 8) return;
+        if (p >= base + 8 && p < base + 16) {                      // the usual case: slide by one word
             base += 8; w0 = w1;
             w1 = (base + 8 < lim) ? *reinterpret_cast<const uint64_t*>(base + 8) : 0;
+#ifndef MSC_EMU
+            // entering a new 128-byte line: ask for the one after the next so that the loads above hit L1 / L2
+            if ((((uintptr_t)base) & 127u) == 0 && base + 256 < lim) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + 256));
+#endif
+            return;
         }
+        init(p, lim);                                               // rewind / long jump (code-length table, new chunk)
     }
     __device__ __forceinline__ uint32_t get32(const uint8_t* p)
     {   // 4 bytes at p (little endian), p in [base, base+8)

@@ -10,8 +10,8 @@
 //               (shared-memory table), candidate B = nearest earlier lane of the same warp with the same hash
 //               (__match_any_sync); both are verified / extended against the input itself
 //     insert  : atomicMax of (position+1) into the table          (deterministic: max = most recent)
-//   every 2048 positions: the greedy parse p += max(1, len[p]) is resolved by pointer jumping over the match bitmap,
-//   leaving a "visited" bitmap; ranks inside it give every token its index.
+//   every 2048 positions: the greedy parse p += max(1, len[p]) -- successor links nxt(q) for all match positions in
+//   parallel, then one thread follows the chain -- leaves a "visited" bitmap; ranks inside it give token indices.
 //
 // Output bytes differ from the reference's (different candidate set); any greedy LZ77 parse with valid
 // (offset, length) pairs is a valid stream for the reference's decoders.
@@ -33,7 +33,7 @@ struct LzFrontSmem {
     uint32_t V[LZF_TILE / 32];         // visited (= token start) bitmap of the tile
     uint32_t prefV[LZF_TILE / 32];     // exclusive prefix popcount of V
     uint32_t K[LZF_TILE / 32];         // visited matches (marks of the pointer-jumping parse)
-    uint16_t nxt[2][LZF_TILE];         // nxt(q) = first match position >= q + len[q] (relative; LZF_TILE = leaves the tile)
+    uint16_t nxt[LZF_TILE];            // nxt(q) = first match position >= q + len[q] (relative; LZF_TILE = leaves the tile)
     uint32_t next_out;                 // furthest match end seen in this tile (relative)
     uint32_t next_p;                   // position (relative to the unit) where parsing resumes
     uint32_t ntok;                     // tokens emitted so far in the unit
@@ -109,10 +109,9 @@ __device__ __forceinline__ uint32_t lzf_tile(LzFrontSmem& sm, const uint8_t* __r
         if (on) atomicMax(&sm.H[h], p + 1);
         __syncthreads();
     }
-    // Greedy parse of the tile, p += max(1, len[p]), without a serial walk: for a match position q the parse continues
-    // at nxt(q) = first match position >= q + len[q]; the visited matches are those reachable from the first match at
-    // or after the carried-in position; they are marked by pointer jumping (nxt <- nxt o nxt).  A tile holds at most
-    // 2048 / 3 chained matches, so 10 rounds suffice.
+    // Greedy parse of the tile, p += max(1, len[p]): for a match position q the parse continues at
+    // nxt(q) = first match position >= q + len[q] (computed for all match positions in parallel); the visited matches
+    // are the chain from the first match at or after the carried-in position -- one shared-memory load per link.
     {
         const uint32_t tend_r = min(t0 + LZF_TILE, n) - t0;                 // tile length (relative)
         const uint32_t start_r = sm.next_p > t0 ? sm.next_p - t0 : 0;       // >= tend_r when a long match skips the tile
@@ -129,30 +128,18 @@ __device__ __forceinline__ uint32_t lzf_tile(LzFrontSmem& sm, const uint8_t* __r
                 atomicOr(&sm.V[w], (hi_b == 32 ? 0xffffffffu : ((1u << hi_b) - 1)) & (0xffffffffu << lo_b));
             }
         };
-        uint16_t* cur = sm.nxt[0];
-        uint16_t* oth = sm.nxt[1];
+        uint16_t* cur = sm.nxt;
         for (int r = tid; r < LZF_TILE; r += LZF_THREADS)
             cur[r] = (uint16_t)(((sm.M[r >> 5] >> (r & 31)) & 1) ? first_match_from((uint32_t)r + (sm.lenoff[r] >> 16) + 1) : (uint32_t)LZF_TILE);
         if (tid < LZF_TILE / 32) { sm.V[tid] = 0; sm.K[tid] = 0; }
         if (tid == 0) sm.next_out = 0;
         __syncthreads();
-        if (tid == 0 && start_r < tend_r) {
-            const uint32_t s0 = first_match_from(start_r);
-            if (s0 < tend_r) sm.K[s0 >> 5] = 1u << (s0 & 31);
-            or_range(start_r, min(s0, tend_r));                             // leading literals
+        if (tid == 32 && start_r < tend_r) or_range(start_r, min(first_match_from(start_r), tend_r));   // leading literals
+        if (tid == 0 && start_r < tend_r) {        // the chain itself: one shared-memory load per visited match
+            uint32_t q = first_match_from(start_r);
+            while (q < tend_r) { sm.K[q >> 5] |= 1u << (q & 31); q = cur[q]; }
         }
         __syncthreads();
-        for (int round = 0; round < 10; ++round) {
-            for (int r = tid; r < LZF_TILE; r += LZF_THREADS) {
-                if ((sm.M[r >> 5] >> (r & 31)) & 1) {
-                    const uint32_t t = cur[r];
-                    if (t < (uint32_t)LZF_TILE && ((sm.K[r >> 5] >> (r & 31)) & 1)) atomicOr(&sm.K[t >> 5], 1u << (t & 31));
-                    oth[r] = (uint16_t)(t < (uint32_t)LZF_TILE ? cur[t] : (uint32_t)LZF_TILE);
-                }
-            }
-            __syncthreads();
-            uint16_t* t2 = cur; cur = oth; oth = t2;
-        }
         // visited = marked matches + the literals up to the next marked match; carry-out = furthest match end
         for (int r = tid; r < LZF_TILE; r += LZF_THREADS) {
             if ((sm.K[r >> 5] >> (r & 31)) & 1) {

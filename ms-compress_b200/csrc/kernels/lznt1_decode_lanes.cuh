@@ -22,71 +22,77 @@ lznt1_decode_lanes_kernel(const uint8_t* __restrict__ in, uint64_t in_len, const
                           uint8_t* __restrict__ out, uint32_t* __restrict__ out_size, int32_t* __restrict__ status)
 {
     const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < nchunks; c += stride) {
-        const uint64_t start = chunk_off[c];
+    const uint32_t first = blockIdx.x * blockDim.x + threadIdx.x;
+    // all lanes of a warp run the same number of rounds (c - lane is warp-uniform), the tail lanes just idle
+    for (uint32_t c = first; c - (threadIdx.x & 31) < nchunks; c += stride) {
         int st = ST_OK;
         LaneOut O;
-        O.init(out + (uint64_t)c * LZNT1_CHUNK);
-        if (start + 2 > in_len) st = ST_BUF;
-        else {
-            const uint32_t hdr = (uint32_t)in[start] | ((uint32_t)in[start + 1] << 8);
-            const uint32_t n = (hdr & 0x0FFF) + 1;                       // payload bytes
-            if (hdr == 0) st = ST_DATA;
-            else if (start + 2 + n > in_len) st = ST_BUF;                // truncated chunk (reference: internal.h:627)
-            else if ((hdr & 0x7000) != 0x3000) st = ST_DATA;             // src/lznt1_decompress.cpp:152
+        O.init(out + (uint64_t)(c < nchunks ? c : 0) * LZNT1_CHUNK);
+        ByteWindow win;
+        const uint8_t* src = in;
+        uint32_t n = 0, ip = 0, f = 1u;
+        bool active = false, raw = false;
+        if (c < nchunks) {
+            const uint64_t start = chunk_off[c];
+            if (start + 2 > in_len) st = ST_BUF;
             else {
-                const uint8_t* src = in + start + 2;
-                ByteWindow win;
-                win.init(src, src + n);
-                uint32_t ip = 0;
-                if (!(hdr & 0x8000)) {                                   // stored chunk :188-206
-                    while (ip < n) {
-                        const uint32_t k = min(n - ip, 8u);
-                        win.seek(src + ip);
-                        uint64_t v = win.get32(src + ip);
-                        if (k > 4) { win.seek(src + ip + 4); v |= (uint64_t)win.get32(src + ip + 4) << 32; }
-                        if (O.opos < O.head) { for (uint32_t i = 0; i < k; ++i) O.put_byte((uint32_t)(v >> (8 * i))); }
-                        else O.put_bytes(v, k);
-                        ip += k;
-                    }
-                } else {
-                    while (ip < n && st == ST_OK) {
-                        win.seek(src + ip);
-                        uint32_t f = (win.get32(src + ip) & 0xFFu) | 0x100u;     // flag bits, LSB first, with a sentinel
-                        ++ip;
-                        while (f != 1u && st == ST_OK) {
-                            if (ip == n) { f = 1u; break; }                       // :86 input ends inside the group
-                            if (f & 1u) {                                         // token
-                                if (ip + 2 > n) { st = ST_DATA; break; }          // :90
-                                win.seek(src + ip);
-                                const uint32_t t = win.get32(src + ip) & 0xFFFFu;
-                                ip += 2;
-                                int S, lim;
-                                lznt1_shift_limit((int)O.opos, S, lim);           // :91
-                                const uint32_t len = (t & ((1u << S) - 1)) + 3, off = (t >> S) + 1;
-                                if (off > O.opos || O.opos + len > (uint32_t)LZNT1_CHUNK) { st = ST_DATA; break; }   // :98-99
-                                O.copy_match(off, len);
-                                f >>= 1;
-                            } else {                                              // run of literal items
-                                uint32_t k = (uint32_t)__ffs((int)f) - 1;         // consecutive 0 flags (<= 8: the sentinel stops it)
-                                k = min(k, n - ip);
-                                if (O.opos + k > (uint32_t)LZNT1_CHUNK) { st = ST_DATA; break; }
-                                win.seek(src + ip);
-                                uint64_t v = win.get32(src + ip);
-                                if (k > 4) { win.seek(src + ip + 4); v |= (uint64_t)win.get32(src + ip + 4) << 32; }
-                                if (O.opos < O.head) { for (uint32_t i = 0; i < k; ++i) O.put_byte((uint32_t)(v >> (8 * i))); }
-                                else O.put_bytes(v, k);
-                                ip += k;
-                                f >>= k;
-                            }
-                        }
-                    }
-                }
+                const uint32_t hdr = (uint32_t)in[start] | ((uint32_t)in[start + 1] << 8);
+                n = (hdr & 0x0FFF) + 1;                                  // payload bytes
+                if (hdr == 0) st = ST_DATA;
+                else if (start + 2 + n > in_len) st = ST_BUF;            // truncated chunk (reference: internal.h:627)
+                else if ((hdr & 0x7000) != 0x3000) st = ST_DATA;         // src/lznt1_decompress.cpp:152
+                else { src = in + start + 2; active = true; raw = !(hdr & 0x8000); }
+            }
+        }
+        win.init(src, src + (active ? n : 0));
+        // One step per iteration and lane: a flag byte fetch plus one item (token or run of literals), or 8 stored bytes.
+        // The loop condition is a warp vote, so the lanes re-converge after every step.
+        while (__any_sync(FULL, active)) {
+            if (!active) continue;
+            if (raw) {                                                   // stored chunk :188-206
+                const uint32_t k = min(n - ip, 8u);
+                win.seek(src + ip);
+                uint64_t v = win.get32(src + ip);
+                if (k > 4) { win.seek(src + ip + 4); v |= (uint64_t)win.get32(src + ip + 4) << 32; }
+                if (O.opos < O.head) { for (uint32_t i = 0; i < k; ++i) O.put_byte((uint32_t)(v >> (8 * i))); }
+                else O.put_bytes(v, k);
+                ip += k;
+                if (ip >= n) active = false;
+                continue;
+            }
+            if (f == 1u) {                                               // next flag byte (:80-82)
+                if (ip >= n) { active = false; continue; }
+                win.seek(src + ip);
+                f = (win.get32(src + ip) & 0xFFu) | 0x100u;              // flag bits, LSB first, with a sentinel
+                ++ip;
+            }
+            if (ip == n) { active = false; continue; }                   // :86 input ends inside the group
+            if (f & 1u) {                                                // token
+                if (ip + 2 > n) { st = ST_DATA; active = false; continue; }          // :90
+                win.seek(src + ip);
+                const uint32_t t = win.get32(src + ip) & 0xFFFFu;
+                ip += 2;
+                int S, lim;
+                lznt1_shift_limit((int)O.opos, S, lim);                  // :91
+                const uint32_t len = (t & ((1u << S) - 1)) + 3, off = (t >> S) + 1;
+                if (off > O.opos || O.opos + len > (uint32_t)LZNT1_CHUNK) { st = ST_DATA; active = false; continue; }   // :98-99
+                O.copy_match(off, len);
+                f >>= 1;
+            } else {                                                     // run of literal items
+                uint32_t k = (uint32_t)__ffs((int)f) - 1;                // consecutive 0 flags (<= 8: the sentinel stops it)
+                k = min(k, n - ip);
+                if (O.opos + k > (uint32_t)LZNT1_CHUNK) { st = ST_DATA; active = false; continue; }
+                win.seek(src + ip);
+                uint64_t v = win.get32(src + ip);
+                if (k > 4) { win.seek(src + ip + 4); v |= (uint64_t)win.get32(src + ip + 4) << 32; }
+                if (O.opos < O.head) { for (uint32_t i = 0; i < k; ++i) O.put_byte((uint32_t)(v >> (8 * i))); }
+                else O.put_bytes(v, k);
+                ip += k;
+                f >>= k;
             }
         }
         O.finish();
-        out_size[c] = st == ST_OK ? O.opos : 0;
-        status[c] = st;
+        if (c < nchunks) { out_size[c] = st == ST_OK ? O.opos : 0; status[c] = st; }
     }
 }
 

@@ -34,6 +34,8 @@ struct Lznt1EncSmem {
         uint8_t out[LZNT1_SLOT];                 // E,F: assembled chunk (aliases cnt, which is dead by then)
     };
     uint16_t sorted[LZNT1_CHUNK];                // positions grouped by hash, ascending inside a group
+    uint16_t ord[LZNT1_CHUNK];                   // indices into sorted[], grouped by rank inside their bucket
+    uint32_t rankcnt[256];                       // entries per rank (ranks >= 255 share the last bin)
     uint32_t lenoff[LZNT1_CHUNK];                // len | dist << 16 (0 = no match)
     uint32_t M[128], V[128], F[128];             // match bitmap, visited bitmap (by position), flag bits (by item)
     uint16_t prefV[128], prefVM[128];
@@ -52,7 +54,8 @@ __global__ void __launch_bounds__(LZE_THREADS)
 lznt1_encode_kernel(const uint8_t* __restrict__ in, uint64_t in_len, uint32_t nchunks,
                     uint8_t* __restrict__ slots, uint32_t* __restrict__ slot_size)
 {
-    __shared__ Lznt1EncSmem sm;
+    MSC_DYN_SMEM(smem_raw);
+    Lznt1EncSmem& sm = *reinterpret_cast<Lznt1EncSmem*>(smem_raw);
     const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     for (uint32_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
@@ -107,11 +110,35 @@ lznt1_encode_kernel(const uint8_t* __restrict__ in, uint64_t in_len, uint32_t nc
         __syncthreads();   // cnt[h] now = end offset of bucket h; begin = cnt[h-1] (0 for h == 0)
 
         // ---- C: match search for every position ------------------------------------------------------
-        // Threads take the positions in SORTED order: neighbouring lanes then sit in the same bucket with nearly the
-        // same number of candidates (the k-th entry of a bucket has k of them), which keeps the warp converged, and
-        // they read the same candidates (shared-memory broadcast).
+        // The k-th entry of a bucket has k candidates (the earlier entries).  Threads take the entries grouped by that
+        // rank, so the lanes of a warp run the candidate loop the same number of times.
         for (int p = (npos > 0 ? npos : 0) + tid; p < LZNT1_CHUNK; p += LZE_THREADS) sm.lenoff[p] = 0;   // not indexed: no match
+        sm.rankcnt[tid] = 0;
+        __syncthreads();
         for (int idx = tid; idx < npos; idx += LZE_THREADS) {
+            const uint32_t h = lz_hash3(lz_load4(sm.in, sm.sorted[idx]));
+            const int r = idx - (int)(h ? sm.cnt[h - 1] : 0);
+            atomicAdd(&sm.rankcnt[r < 255 ? r : 255], 1u);
+        }
+        __syncthreads();
+        {   // exclusive scan of the 256 rank counts (one per thread)
+            const uint32_t v = sm.rankcnt[tid];
+            const int incl = warp_incl_scan((int)v);
+            if (lane == 31) sm.scan_tmp[warp] = (uint32_t)incl;
+            __syncthreads();
+            uint32_t woff = 0;
+            for (int w = 0; w < warp; ++w) woff += sm.scan_tmp[w];
+            sm.rankcnt[tid] = woff + (uint32_t)incl - v;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < npos; idx += LZE_THREADS) {
+            const uint32_t h = lz_hash3(lz_load4(sm.in, sm.sorted[idx]));
+            const int r = idx - (int)(h ? sm.cnt[h - 1] : 0);
+            sm.ord[atomicAdd(&sm.rankcnt[r < 255 ? r : 255], 1u)] = (uint16_t)idx;
+        }
+        __syncthreads();
+        for (int i = tid; i < npos; i += LZE_THREADS) {
+            const int idx = sm.ord[i];
             const int p = sm.sorted[idx];
             uint32_t res = 0;
             if (p > 0) {
@@ -145,13 +172,12 @@ lznt1_encode_kernel(const uint8_t* __restrict__ in, uint64_t in_len, uint32_t nc
         }
         __syncthreads();
 
-        // ---- D: greedy parse p += max(1, len[p]) without a serial walk ------------------------------------------
+        // ---- D: greedy parse p += max(1, len[p]) ------------------------------------------
         // For a match position q the parse continues at nxt(q) = first match position >= q + len[q] (everything in
-        // between is literals).  The visited matches are the positions reachable from the first match by nxt; they are
-        // marked by pointer jumping (nxt <- nxt o nxt, 12 rounds cover any chain in a 4 KiB chunk).
+        // between is literals); nxt is computed for all match positions in parallel, the visited ones are then the
+        // chain from the first match -- one shared-memory load per visited match.
         {
             uint16_t* cur = sm.sorted;                                                        // dead after stage C
-            uint16_t* oth = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(sm.cnt) + 8192);   // dead too
             auto first_match_from = [&](int e) -> int {
                 if (e >= LZNT1_CHUNK) return LZNT1_CHUNK;
                 int w = e >> 5;
@@ -167,23 +193,13 @@ lznt1_encode_kernel(const uint8_t* __restrict__ in, uint64_t in_len, uint32_t nc
             };
             for (int p = tid; p < LZNT1_CHUNK; p += LZE_THREADS)
                 cur[p] = (uint16_t)(((sm.M[p >> 5] >> (p & 31)) & 1) ? first_match_from(p + (int)(sm.lenoff[p] & 0xFFFF)) : LZNT1_CHUNK);
-            if (tid == 0) {
-                const int s0 = first_match_from(0);
-                if (s0 < LZNT1_CHUNK) sm.F[s0 >> 5] = 1u << (s0 & 31);                        // F doubles as the mark bitmap
-                or_range(0, min(s0, n));                                                      // leading literals
+            __syncthreads();                                                                  // F doubles as the mark bitmap
+            if (tid == 32) or_range(0, min(first_match_from(0), n));                          // leading literals
+            if (tid == 0) {     // the chain itself is a pointer chase over nxt: one shared-memory load per visited match
+                int q = first_match_from(0);
+                while (q < LZNT1_CHUNK) { sm.F[q >> 5] |= 1u << (q & 31); q = cur[q]; }
             }
             __syncthreads();
-            for (int round = 0; round < 12; ++round) {
-                for (int p = tid; p < LZNT1_CHUNK; p += LZE_THREADS) {
-                    if ((sm.M[p >> 5] >> (p & 31)) & 1) {
-                        const int t = cur[p];
-                        if (t < LZNT1_CHUNK && ((sm.F[p >> 5] >> (p & 31)) & 1)) atomicOr(&sm.F[t >> 5], 1u << (t & 31));
-                        oth[p] = (uint16_t)(t < LZNT1_CHUNK ? cur[t] : LZNT1_CHUNK);
-                    }
-                }
-                __syncthreads();
-                uint16_t* t2 = cur; cur = oth; oth = t2;
-            }
             // visited bitmap: every visited match plus the literals up to the next visited match
             for (int p = tid; p < LZNT1_CHUNK; p += LZE_THREADS) {
                 if ((sm.F[p >> 5] >> (p & 31)) & 1) {

@@ -9,12 +9,14 @@
 // keeps the reference's exact reader state (32-bit window, valid-bit count, byte cursor) and walks its buffer
 // chunk after chunk; parallelism comes from the batch.  Literals and match copies go through a per-lane output
 // cursor that stores whole 8-byte words (lane_out.cuh).  A multi-chunk stream produced by the reference
-// (cross-chunk matches, implicit chunk boundaries) decodes on the same path.
+// (cross-chunk matches, implicit chunk boundaries) decodes on the same path.  The warp re-converges after every
+// symbol (the loop condition is a warp vote), so the lanes stay in lock step apart from the literal / match split.
 //
 // Canonical decoding without a big lookup table: the per-length limits of the left-aligned 15-bit code space
-// (`lims`, HuffmanDecoder.h:58-76) live in 8 registers as packed 16-bit pairs; the code length is
-// 1 + #{k : x >= lims[k]}, counted with 16-bit SIMD compares; the symbol is syms[base[n] + (x >> (15-n))].
-// Shared memory per lane: 512 x u16 symbols (interleaved across lanes) + 16 x i16 bases.
+// (`lims`, HuffmanDecoder.h:58-76) live in 14 registers; the code length is 1 + #{k : x >= lims[k]}; the symbol is
+// syms[base[n] + (x >> (15-n))].  Canonical order puts the literals of a length before its match symbols, so the
+// table stores 8 bits per symbol and a per-length boundary (`litend`) supplies the ninth.
+// Shared memory per lane: 512 B symbols + 3 x 16 x 2 B, interleaved across lanes (19 KB per warp, 11 warps per SM).
 #pragma once
 #include "common.cuh"
 #include "lz_exec.cuh"
@@ -28,19 +30,13 @@ constexpr uint32_t XH_CHUNK = 65536;
 constexpr int XH_MIN_DATA = 260;
 
 struct XhWarpSmem {
-    uint16_t syms[XH_SYMS * 32];         // syms[i * 32 + lane]
+    uint8_t syms[XH_SYMS * 32];          // low 8 bits of the symbol at rank i: syms[i * 32 + lane]
     int16_t base[16 * 32];               // base[n * 32 + lane]; doubles as the per-length counters while building
     uint16_t fill[16 * 32];              // table build only: next free slot per length
+    uint16_t litend[16 * 32];            // rank of the first match symbol (>= 256) of each length
 };
 constexpr int XHD_WARPS_PER_BLOCK = 1;
 constexpr size_t XHD_SMEM_BYTES = sizeof(XhWarpSmem) * XHD_WARPS_PER_BLOCK;
-
-#ifndef MSC_EMU
-__device__ __forceinline__ uint32_t vcmpgeu2(uint32_t a, uint32_t b) { return __vcmpgeu2(a, b); }
-#else
-inline uint32_t vcmpgeu2(uint32_t a, uint32_t b)
-{ return (((a & 0xFFFFu) >= (b & 0xFFFFu)) ? 0xFFFFu : 0u) | (((a >> 16) >= (b >> 16)) ? 0xFFFF0000u : 0u); }
-#endif
 
 struct XhLane {
     // stream
@@ -49,7 +45,8 @@ struct XhLane {
     uint32_t mask; int bits; uint32_t ip;
     ByteWindow win;
     // decode tables
-    uint32_t lims2[8];                   // lims[1..15] packed: lims2[k] = lims[2k+1] | lims[2k+2] << 16 (lims[16] = 0xFFFF filler)
+    uint32_t lims[15];                   // lims[k] = limit of length k (k = 1..14), left aligned in 15 bits
+    uint32_t nused;                      // symbols with a code (ranks >= nused are invalid)
     // progress
     uint32_t chunk_end;
     int status;                          // 0 running, 1 finished OK, <0 error
@@ -81,7 +78,6 @@ __device__ __forceinline__ bool xh_build_table(XhLane& L, XhWarpSmem& sm, int la
         for (int k = 0; k < 8; ++k) sm.base[((w >> (4 * k)) & 15) * 32 + lane] += 1;
     }
     uint32_t last = 0, pos = 0, cnt_prev = 0;                   // lims[len-1], poss[len], cnts[len-1] (cnts[0] counts as 0)
-    uint32_t lim[17];
     bool ok = true;
 #pragma unroll
     for (int len = 1; len <= 15; ++len) {
@@ -89,23 +85,24 @@ __device__ __forceinline__ bool xh_build_table(XhLane& L, XhWarpSmem& sm, int la
         pos += cnt_prev;                                        // poss[len] = poss[len-1] + cnts[len-1]   (:79-80)
         cnt_prev = cnt;
         sm.fill[len * 32 + lane] = (uint16_t)pos;
-        sm.base[len * 32 + lane] = (int16_t)((int)pos - (int)(last >> (15 - len)));     // idx = base[n] + (x >> (15-n))
+        sm.litend[len * 32 + lane] = (uint16_t)pos;             // corrected below if the length has literals
+        sm.base[len * 32 + lane] = (int16_t)((int)pos - (int)(last >> (15 - len)));     // rank = base[n] + (x >> (15-n))
         if (len < 15) {
             const uint32_t inc = cnt << (15 - len);
             if (last + inc > 32768u) ok = false;                // :65, :73 over-subscribed
             last += inc;
-            lim[len] = last;
+            L.lims[len] = last;
         } else {
-            if (last + cnt > 32768u) ok = false;                // :76
-            lim[len] = 32768u;                                  // :61
+            if (last + cnt > 32768u) ok = false;                // :76  (lims[15] itself is the whole code space, :61)
+            L.nused = pos + cnt;
         }
     }
-    lim[16] = 0xFFFFu;                                          // filler, never reached (x < 32768)
-#pragma unroll
-    for (int k = 0; k < 8; ++k) L.lims2[k] = lim[2 * k + 1] | (lim[2 * k + 2] << 16);
     if (!ok) return false;
-    for (int i = 0; i < XH_SYMS; ++i) sm.syms[i * 32 + lane] = 0xFFFFu;        // :44
     for (int i = 0; i < 256; i += 4) {                          // symbols in (length, symbol) order (:83-88)
+        if (i == 128) {                                         // all literals are placed: the match symbols start here
+#pragma unroll
+            for (int len = 1; len <= 15; ++len) sm.litend[len * 32 + lane] = sm.fill[len * 32 + lane];
+        }
         const uint32_t w = xh_rd32(L, at + i);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -113,7 +110,7 @@ __device__ __forceinline__ bool xh_build_table(XhLane& L, XhWarpSmem& sm, int la
             if (l) {
                 const uint32_t f = sm.fill[l * 32 + lane];
                 sm.fill[l * 32 + lane] = (uint16_t)(f + 1);
-                sm.syms[f * 32 + lane] = (uint16_t)(2 * i + k);
+                sm.syms[f * 32 + lane] = (uint8_t)(2 * i + k);
             }
         }
     }
@@ -125,69 +122,66 @@ __device__ __forceinline__ uint32_t xh_decode_symbol(XhLane& L, const XhWarpSmem
 {
     const int r = L.bits;
     const uint32_t x = (r < 15) ? (r == 0 ? 0u : ((L.mask >> (32 - r)) << (15 - r))) : (L.mask >> 17);
-    const uint32_t xx = x | (x << 16);
     int n = 1;                                                   // first length whose limit exceeds x
 #pragma unroll
-    for (int k = 0; k < 8; ++k) n += __popc(vcmpgeu2(xx, L.lims2[k])) >> 4;
+    for (int k = 1; k <= 14; ++k) n += (x >= L.lims[k]) ? 1 : 0;
     if (n > r) return 0xFFFFu;
-    const int idx = (int)sm.base[n * 32 + lane] + (int)(x >> (15 - n));
+    const uint32_t rank = (uint32_t)((int)sm.base[n * 32 + lane] + (int)(x >> (15 - n)));
     xh_skip(L, n);
-    if ((unsigned)idx >= (unsigned)XH_SYMS) return 0xFFFFu;
-    return sm.syms[idx * 32 + lane];
+    if (rank >= L.nused) return 0xFFFFu;                         // unassigned part of an incomplete code (:44, :102)
+    return (uint32_t)sm.syms[rank * 32 + lane] | (rank >= (uint32_t)sm.litend[n * 32 + lane] ? 256u : 0u);
 }
 
-// Decode this lane's whole stream (xpress_huff_decompress :143-159 around xpress_huff_decompress_chunk :39-135).
-__device__ __forceinline__ void xh_run(XhLane& L, XhWarpSmem& sm, int lane, LaneOut& O)
+// One symbol of this lane's stream (xpress_huff_decompress :143-159 around xpress_huff_decompress_chunk :39-135).
+__device__ __forceinline__ void xh_step(XhLane& L, XhWarpSmem& sm, int lane, LaneOut& O)
 {
-    while (L.status == 0) {
-        if (L.need_table) {                                         // start of a chunk (:143-157)
-            if (L.in_len - L.ip < (uint32_t)XH_MIN_DATA) { L.status = (L.ip == L.in_len) ? 1 : ST_DATA; break; }
-            if (!xh_build_table(L, sm, lane, L.ip)) { L.status = ST_DATA; break; }
-            L.mask = (xh_rd16(L, L.ip + 256) << 16) | xh_rd16(L, L.ip + 258);
-            L.bits = 32;
-            L.ip += 260;
-            L.chunk_end = O.opos + XH_CHUNK;
-            L.need_table = false;
-        }
-        if (!(O.opos < L.chunk_end || !xh_mask_is_zero(L))) {       // end of chunk (:79, :127-133)
-            XhLane T = L;                                            // trial decode of an end-of-stream symbol
-            const uint32_t s2 = xh_decode_symbol(T, sm, lane);
-            if (s2 == (uint32_t)XH_EOS && T.in_len - T.ip == 0 && xh_mask_is_zero(T)) { L.status = 1; break; }
-            L.need_table = true;
-            continue;
-        }
-        const uint32_t sym = xh_decode_symbol(L, sm, lane);
-        if (sym == 0xFFFFu) { L.status = ST_DATA; break; }
-        if (sym == (uint32_t)XH_EOS && L.in_len - L.ip == 0 && xh_mask_is_zero(L)) { L.status = 1; break; }   // :83
-        if (sym < 256) {
-            if (O.opos == L.cap) { L.status = ST_BUF; break; }
-            O.put_byte(sym);
-        } else {
-            uint32_t len = sym & 15;
-            if (len == 15) {
-                if (L.in_len - L.ip < 1) { L.status = ST_DATA; break; }
-                len = xh_rd16(L, L.ip) & 0xFF; L.ip += 1;
-                if (len == 0xFF) {
-                    if (L.in_len - L.ip < 2) { L.status = ST_DATA; break; }
-                    len = xh_rd16(L, L.ip); L.ip += 2;
-                    if (len == 0) {
-                        if (L.in_len - L.ip < 4) { L.status = ST_DATA; break; }
-                        len = xh_rd32(L, L.ip); L.ip += 4;
-                    }
-                    if (len < 15) { L.status = ST_DATA; break; }
-                    len -= 15;
+    if (L.need_table) {                                         // start of a chunk (:143-157)
+        if (L.in_len - L.ip < (uint32_t)XH_MIN_DATA) { L.status = (L.ip == L.in_len) ? 1 : ST_DATA; return; }
+        if (!xh_build_table(L, sm, lane, L.ip)) { L.status = ST_DATA; return; }
+        L.mask = (xh_rd16(L, L.ip + 256) << 16) | xh_rd16(L, L.ip + 258);
+        L.bits = 32;
+        L.ip += 260;
+        L.chunk_end = O.opos + XH_CHUNK;
+        L.need_table = false;
+    }
+    if (!(O.opos < L.chunk_end || !xh_mask_is_zero(L))) {       // end of chunk (:79, :127-133)
+        XhLane T = L;                                            // trial decode of an end-of-stream symbol
+        const uint32_t s2 = xh_decode_symbol(T, sm, lane);
+        if (s2 == (uint32_t)XH_EOS && T.in_len - T.ip == 0 && xh_mask_is_zero(T)) { L.status = 1; return; }
+        L.need_table = true;
+        return;
+    }
+    const uint32_t sym = xh_decode_symbol(L, sm, lane);
+    if (sym == 0xFFFFu) { L.status = ST_DATA; return; }
+    if (sym == (uint32_t)XH_EOS && L.in_len - L.ip == 0 && xh_mask_is_zero(L)) { L.status = 1; return; }   // :83
+    if (sym < 256) {
+        if (O.opos == L.cap) { L.status = ST_BUF; return; }
+        O.put_byte(sym);
+    } else {
+        uint32_t len = sym & 15;
+        if (len == 15) {
+            if (L.in_len - L.ip < 1) { L.status = ST_DATA; return; }
+            len = xh_rd16(L, L.ip) & 0xFF; L.ip += 1;
+            if (len == 0xFF) {
+                if (L.in_len - L.ip < 2) { L.status = ST_DATA; return; }
+                len = xh_rd16(L, L.ip); L.ip += 2;
+                if (len == 0) {
+                    if (L.in_len - L.ip < 4) { L.status = ST_DATA; return; }
+                    len = xh_rd32(L, L.ip); L.ip += 4;
                 }
-                len += 15;
+                if (len < 15) { L.status = ST_DATA; return; }
+                len -= 15;
             }
-            len += 3;
-            const int off_bits = (int)((sym >> 4) & 15);
-            if (off_bits > L.bits) { L.status = ST_DATA; break; }
-            const uint32_t off = xh_peek(L, off_bits) + (1u << off_bits);
-            xh_skip(L, off_bits);
-            if (O.opos < off) { L.status = ST_DATA; break; }             // :113
-            if (L.cap - O.opos < len) { L.status = ST_BUF; break; }      // :114
-            O.copy_match(off, len);
+            len += 15;
         }
+        len += 3;
+        const int off_bits = (int)((sym >> 4) & 15);
+        if (off_bits > L.bits) { L.status = ST_DATA; return; }
+        const uint32_t off = xh_peek(L, off_bits) + (1u << off_bits);
+        xh_skip(L, off_bits);
+        if (O.opos < off) { L.status = ST_DATA; return; }            // :113
+        if (L.cap - O.opos < len) { L.status = ST_BUF; return; }     // :114
+        O.copy_match(off, len);
     }
 }
 
@@ -205,10 +199,10 @@ xhuff_decode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, u
     for (uint32_t g = blockIdx.x * XHD_WARPS_PER_BLOCK + (threadIdx.x >> 5); g * 32 < count; g += warps_total) {
         const uint32_t i = g * 32 + lane;
         XhLane L;
-        L.status = 1; L.in = in; L.in_len = 0; L.cap = 0; L.ip = 0;
+        L.status = 1; L.in = in; L.in_len = 0; L.cap = 0; L.ip = 0; L.nused = 0;
         L.mask = 0; L.bits = 0; L.chunk_end = 0; L.need_table = true;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) L.lims2[k] = 0xFFFFFFFFu;
+        for (int k = 0; k < 15; ++k) L.lims[k] = 0x8000u;
         LaneOut O;
         O.init(out);
         if (i < count) {
@@ -217,9 +211,10 @@ xhuff_decode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, u
             L.status = 0;
         }
         L.win.init(L.in, L.in + L.in_len);
-        xh_run(L, sm, lane, O);
+        while (__any_sync(FULL, L.status == 0)) {
+            if (L.status == 0) xh_step(L, sm, lane, O);
+        }
         O.finish();
-        __syncwarp();
         if (i < count) { out_len[i] = O.opos; status[i] = L.status == 1 ? ST_OK : L.status; }
     }
 }

@@ -29,9 +29,10 @@ __device__ __forceinline__ uint32_t xp_rd32(XpLane& L, uint32_t at) { L.win.seek
 // all 1 bits above all 0 bits (src/xpress_decompress.cpp:41)
 __device__ __forceinline__ bool xp_set_bits_are_highest(uint32_t x) { x = ~x; return ((x + 1) & x) == 0; }
 
-__device__ __forceinline__ void xp_run(XpLane& L, LaneOut& O)
+// One item of this lane's stream.
+__device__ __forceinline__ void xp_step(XpLane& L, LaneOut& O)
 {
-    while (L.status == 0) {
+    do {
         if (!L.have_flags) {                                            // start a fragment (:425-430)
             if (L.ip + 4 > L.in_len) { L.status = ST_DATA; break; }     // :461
             const uint32_t f = xp_rd32(L, L.ip);
@@ -83,7 +84,7 @@ __device__ __forceinline__ void xp_run(XpLane& L, LaneOut& O)
         L.flagged = (L.flags & 0x80000000u) != 0;
         L.flags <<= 1;
         if (L.flags == 0) L.have_flags = false;
-    }
+    } while (false);
 }
 
 __global__ void __launch_bounds__(32 * XPD_WARPS_PER_BLOCK)
@@ -113,9 +114,10 @@ xpress_decode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, 
             }
         }
         L.win.init(L.in, L.in + L.in_len);
-        xp_run(L, O);
+        while (__any_sync(FULL, L.status == 0)) {      // warp vote: the lanes re-converge after every item
+            if (L.status == 0) xp_step(L, O);
+        }
         O.finish();
-        __syncwarp();
         if (i < count) { out_len[i] = O.opos; status[i] = L.status == 1 ? ST_OK : L.status; }
     }
 }

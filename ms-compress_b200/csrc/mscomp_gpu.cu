@@ -125,7 +125,8 @@ MSCompStatus mscomp_gpu_lznt1_compress(mscomp_gpu_ctx* ctx, const uint8_t* d_in,
     if (!slots || !sizes || !offs) return MSCOMP_MEM_ERROR;
     if (nchunks) {
         const uint32_t grid = nchunks < (uint32_t)ctx->sm_count * 8 ? nchunks : (uint32_t)ctx->sm_count * 8;
-        MSC_LAUNCH(ctx, lznt1_encode_kernel, grid, LZE_THREADS, d_in, (uint64_t)in_len, nchunks, slots, sizes);
+        MSC_OPT_IN_SMEM(lznt1_encode_kernel, sizeof(Lznt1EncSmem));
+        MSC_LAUNCH_SMEM(ctx, lznt1_encode_kernel, grid, LZE_THREADS, sizeof(Lznt1EncSmem), d_in, (uint64_t)in_len, nchunks, slots, sizes);
     }
     msc_compact_slots(ctx, slots, LZNT1_SLOT, sizes, nchunks, offs, d_out);
     // result: bytes = offs[nchunks]
@@ -177,17 +178,13 @@ MSCompStatus msc_xpress_huff_compress_units(mscomp_gpu_ctx* ctx, const uint8_t* 
     if (!batch_ok(ctx, d_in, d_out, b)) return MSCOMP_ARG_ERROR;
     if (!b->count) return MSCOMP_OK;
     cudaSetDevice(ctx->device);
-    static bool attr_done = false;
-    if (!attr_done) { cudaFuncSetAttribute(xhuff_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(XhEncSmem)); attr_done = true; }
+    MSC_OPT_IN_SMEM(xhuff_encode_kernel, sizeof(XhEncSmem));
     const uint32_t cap = (uint32_t)ctx->sm_count * 4;
     const uint32_t grid = b->count < cap ? b->count : cap;
     uint8_t* scratch = (uint8_t*)ctx->get(SC_AUX2, (size_t)grid * XHE_SCRATCH_BYTES + 64);
     if (!scratch) return MSCOMP_MEM_ERROR;
-    const int prof_slot_ = ctx->prof_begin("xhuff_encode_kernel");
-    xhuff_encode_kernel<<<grid, XHE_THREADS, sizeof(XhEncSmem), ctx->stream>>>(d_in, d_out, b->count, b->d_in_off, b->d_in_len, b->d_out_off,
-                                                                                 b->d_out_cap, b->d_out_len, b->d_status, scratch, eos_mode);
-    ++ctx->launches;
-    ctx->prof_end(prof_slot_);
+    MSC_LAUNCH_SMEM(ctx, xhuff_encode_kernel, grid, XHE_THREADS, sizeof(XhEncSmem), d_in, d_out, b->count, b->d_in_off, b->d_in_len, b->d_out_off,
+                    b->d_out_cap, b->d_out_len, b->d_status, scratch, eos_mode);
     return msc_cuda_status(cudaGetLastError(), "xpress_huff_compress");
 }
 
@@ -202,11 +199,8 @@ MSCompStatus mscomp_gpu_xpress_huff_decompress_batch(mscomp_gpu_ctx* ctx, const 
     if (!b->count) return MSCOMP_OK;
     cudaSetDevice(ctx->device);
     const uint32_t groups = (b->count + 31) / 32, cap = (uint32_t)ctx->sm_count * 5;
-    const int prof_slot_ = ctx->prof_begin("xhuff_decode_kernel");
-    xhuff_decode_kernel<<<groups < cap ? groups : cap, 32 * XHD_WARPS_PER_BLOCK, XHD_SMEM_BYTES, ctx->stream>>>(
-        d_in, d_out, b->count, b->d_in_off, b->d_in_len, b->d_out_off, b->d_out_cap, b->d_out_len, b->d_status);
-    ++ctx->launches;
-    ctx->prof_end(prof_slot_);
+    MSC_LAUNCH_SMEM(ctx, xhuff_decode_kernel, groups < cap ? groups : cap, 32 * XHD_WARPS_PER_BLOCK, XHD_SMEM_BYTES,
+                    d_in, d_out, b->count, b->d_in_off, b->d_in_len, b->d_out_off, b->d_out_cap, b->d_out_len, b->d_status);
     return msc_cuda_status(cudaGetLastError(), "xpress_huff_decompress");
 }
 
@@ -215,14 +209,10 @@ MSCompStatus mscomp_gpu_xpress_compress_batch(mscomp_gpu_ctx* ctx, const uint8_t
     if (!batch_ok(ctx, d_in, d_out, b)) return MSCOMP_ARG_ERROR;
     if (!b->count) return MSCOMP_OK;
     cudaSetDevice(ctx->device);
-    static bool attr_done = false;
-    if (!attr_done) { cudaFuncSetAttribute(xpress_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(XpEncSmem)); attr_done = true; }
+    MSC_OPT_IN_SMEM(xpress_encode_kernel, sizeof(XpEncSmem));
     const uint32_t cap = (uint32_t)ctx->sm_count * 4;
-    const int prof_slot_ = ctx->prof_begin("xpress_encode_kernel");
-    xpress_encode_kernel<<<b->count < cap ? b->count : cap, XPE_THREADS, sizeof(XpEncSmem), ctx->stream>>>(
-        d_in, d_out, b->count, b->d_in_off, b->d_in_len, b->d_out_off, b->d_out_cap, b->d_out_len, b->d_status);
-    ++ctx->launches;
-    ctx->prof_end(prof_slot_);
+    MSC_LAUNCH_SMEM(ctx, xpress_encode_kernel, b->count < cap ? b->count : cap, XPE_THREADS, sizeof(XpEncSmem),
+                    d_in, d_out, b->count, b->d_in_off, b->d_in_len, b->d_out_off, b->d_out_cap, b->d_out_len, b->d_status);
     return msc_cuda_status(cudaGetLastError(), "xpress_compress");
 }
 
