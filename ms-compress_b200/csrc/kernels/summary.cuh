@@ -39,4 +39,19 @@ summarize_kernel(const uint32_t* __restrict__ sizes, const int32_t* __restrict__
     }
 }
 
+// max over units of (off[i] + cap[i]): the extent of the output region a batch can touch (single block)
+__global__ void __launch_bounds__(SUM_THREADS)
+batch_extent_kernel(const uint64_t* __restrict__ off, const uint32_t* __restrict__ cap, uint32_t n, uint64_t* __restrict__ extent)
+{
+    __shared__ uint64_t s_max[32];
+    const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint64_t m = 0;
+    for (uint32_t i = tid; i < n; i += SUM_THREADS) { const uint64_t e = off[i] + cap[i]; if (e > m) m = e; }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) { const uint64_t o = __shfl_xor_sync(FULL, m, d); if (o > m) m = o; }
+    if (lane == 0) s_max[warp] = m;
+    __syncthreads();
+    if (tid == 0) { for (int w = 1; w < SUM_THREADS / 32; ++w) if (s_max[w] > m) m = s_max[w]; *extent = m; }
+}
+
 } // namespace msc

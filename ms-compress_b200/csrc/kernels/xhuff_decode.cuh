@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "lz_exec.cuh"
 #include "lane_out.cuh"
+#include "lz_apply.cuh"
 
 namespace msc {
 
@@ -133,7 +134,8 @@ __device__ __forceinline__ uint32_t xh_decode_symbol(XhLane& L, const XhWarpSmem
 }
 
 // One symbol of this lane's stream (xpress_huff_decompress :143-159 around xpress_huff_decompress_chunk :39-135).
-__device__ __forceinline__ void xh_step(XhLane& L, XhWarpSmem& sm, int lane, LaneOut& O)
+template <class Sink>
+__device__ __forceinline__ void xh_step(XhLane& L, XhWarpSmem& sm, int lane, Sink& O)
 {
     if (L.need_table) {                                         // start of a chunk (:143-157)
         if (L.in_len - L.ip < (uint32_t)XH_MIN_DATA) { L.status = (L.ip == L.in_len) ? 1 : ST_DATA; return; }
@@ -186,11 +188,14 @@ __device__ __forceinline__ void xh_step(XhLane& L, XhWarpSmem& sm, int lane, Lan
 }
 
 // Batch decode: buffer i = in[in_off[i] .. +in_len[i]) -> out[out_off[i] .. +out_cap[i]); out_len / status per buffer.
-__global__ void __launch_bounds__(32 * XHD_WARPS_PER_BLOCK)
-xhuff_decode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint32_t count,
-                    const uint64_t* __restrict__ in_off, const uint32_t* __restrict__ in_len,
-                    const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ out_cap,
-                    uint32_t* __restrict__ out_len, int32_t* __restrict__ status)
+// Sink = LaneOut : single-kernel decoder, the lane writes its own output (no scratch; small batches, huge buffers).
+// Sink = LaneTok : stage one of the two-kernel decoder, the lane only appends tokens at tok + 4 * out_off[i];
+//                  lz_apply_kernel (lz_apply.cuh) turns them into bytes with one warp per buffer.
+template <class Sink>
+__device__ __forceinline__ void xhuff_decode_body(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint32_t* __restrict__ tok, uint32_t count,
+                                                  const uint64_t* __restrict__ in_off, const uint32_t* __restrict__ in_len,
+                                                  const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ out_cap,
+                                                  uint32_t* __restrict__ out_len, int32_t* __restrict__ status, uint32_t* __restrict__ ntok)
 {
     MSC_DYN_SMEM(smem_raw);
     XhWarpSmem& sm = reinterpret_cast<XhWarpSmem*>(smem_raw)[threadIdx.x >> 5];
@@ -203,20 +208,37 @@ xhuff_decode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, u
         L.mask = 0; L.bits = 0; L.chunk_end = 0; L.need_table = true;
 #pragma unroll
         for (int k = 0; k < 15; ++k) L.lims[k] = 0x8000u;
-        LaneOut O;
-        O.init(out);
+        Sink O;
         if (i < count) {
             L.in = in + in_off[i]; L.in_len = in_len[i]; L.cap = out_cap[i];
-            O.init(out + out_off[i]);
+            sink_init(O, out, tok, out_off[i]);
             L.status = 0;
-        }
+        } else sink_init(O, out, tok, 0);
         L.win.init(L.in, L.in + L.in_len);
         while (__any_sync(FULL, L.status == 0)) {
             if (L.status == 0) xh_step(L, sm, lane, O);
         }
         O.finish();
-        if (i < count) { out_len[i] = O.opos; status[i] = L.status == 1 ? ST_OK : L.status; }
+        if (i < count) { out_len[i] = O.opos; status[i] = L.status == 1 ? ST_OK : L.status; sink_count(O, ntok, i); }
     }
+}
+
+__global__ void __launch_bounds__(32 * XHD_WARPS_PER_BLOCK)
+xhuff_decode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint32_t count,
+                    const uint64_t* __restrict__ in_off, const uint32_t* __restrict__ in_len,
+                    const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ out_cap,
+                    uint32_t* __restrict__ out_len, int32_t* __restrict__ status)
+{
+    xhuff_decode_body<LaneOut>(in, out, nullptr, count, in_off, in_len, out_off, out_cap, out_len, status, nullptr);
+}
+
+__global__ void __launch_bounds__(32 * XHD_WARPS_PER_BLOCK)
+xhuff_parse_kernel(const uint8_t* __restrict__ in, uint32_t* __restrict__ tok, uint32_t count,
+                   const uint64_t* __restrict__ in_off, const uint32_t* __restrict__ in_len,
+                   const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ out_cap,
+                   uint32_t* __restrict__ out_len, int32_t* __restrict__ status, uint32_t* __restrict__ ntok)
+{
+    xhuff_decode_body<LaneTok>(in, nullptr, tok, count, in_off, in_len, out_off, out_cap, out_len, status, ntok);
 }
 
 } // namespace msc

@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "lz_exec.cuh"
 #include "lane_out.cuh"
+#include "lz_apply.cuh"
 
 namespace msc {
 
@@ -30,7 +31,8 @@ __device__ __forceinline__ uint32_t xp_rd32(XpLane& L, uint32_t at) { L.win.seek
 __device__ __forceinline__ bool xp_set_bits_are_highest(uint32_t x) { x = ~x; return ((x + 1) & x) == 0; }
 
 // One item of this lane's stream.
-__device__ __forceinline__ void xp_step(XpLane& L, LaneOut& O)
+template <class Sink>
+__device__ __forceinline__ void xp_step(XpLane& L, Sink& O)
 {
     do {
         if (!L.have_flags) {                                            // start a fragment (:425-430)
@@ -87,11 +89,12 @@ __device__ __forceinline__ void xp_step(XpLane& L, LaneOut& O)
     } while (false);
 }
 
-__global__ void __launch_bounds__(32 * XPD_WARPS_PER_BLOCK)
-xpress_decode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint32_t count,
-                     const uint64_t* __restrict__ in_off, const uint32_t* __restrict__ in_len,
-                     const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ out_cap,
-                     uint32_t* __restrict__ out_len, int32_t* __restrict__ status)
+// Sink = LaneOut: single-kernel decoder; Sink = LaneTok: stage one of the two-kernel decoder (see xhuff_decode.cuh).
+template <class Sink>
+__device__ __forceinline__ void xpress_decode_body(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint32_t* __restrict__ tok, uint32_t count,
+                                                   const uint64_t* __restrict__ in_off, const uint32_t* __restrict__ in_len,
+                                                   const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ out_cap,
+                                                   uint32_t* __restrict__ out_len, int32_t* __restrict__ status, uint32_t* __restrict__ ntok)
 {
     const int lane = lane_id();
     const int wib = (int)(threadIdx.x >> 5);
@@ -101,25 +104,42 @@ xpress_decode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, 
         XpLane L;
         L.in = in; L.in_len = 0; L.cap = 0; L.ip = 0; L.flags = 0; L.flagged = false; L.have_flags = false;
         L.half_val = 0; L.has_half = false; L.status = 1;
-        LaneOut O;
-        O.init(out);
+        Sink O;
         if (i < count) {
             L.in = in + in_off[i]; L.in_len = in_len[i]; L.cap = out_cap[i];
-            O.init(out + out_off[i]);
+            sink_init(O, out, tok, out_off[i]);
             L.status = 0;
             if (L.in_len < 5) {                                         // :414-418 (sic)
                 uint32_t w = 0;
                 if (L.in_len == 4) w = (uint32_t)L.in[0] | ((uint32_t)L.in[1] << 8) | ((uint32_t)L.in[2] << 16) | ((uint32_t)L.in[3] << 24);
                 L.status = (L.in_len == 0 || (L.in_len == 4 && w != 0xFFFFFFFFu)) ? 1 : ST_DATA;
             }
-        }
+        } else sink_init(O, out, tok, 0);
         L.win.init(L.in, L.in + L.in_len);
         while (__any_sync(FULL, L.status == 0)) {      // warp vote: the lanes re-converge after every item
             if (L.status == 0) xp_step(L, O);
         }
         O.finish();
-        if (i < count) { out_len[i] = O.opos; status[i] = L.status == 1 ? ST_OK : L.status; }
+        if (i < count) { out_len[i] = O.opos; status[i] = L.status == 1 ? ST_OK : L.status; sink_count(O, ntok, i); }
     }
+}
+
+__global__ void __launch_bounds__(32 * XPD_WARPS_PER_BLOCK)
+xpress_decode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint32_t count,
+                     const uint64_t* __restrict__ in_off, const uint32_t* __restrict__ in_len,
+                     const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ out_cap,
+                     uint32_t* __restrict__ out_len, int32_t* __restrict__ status)
+{
+    xpress_decode_body<LaneOut>(in, out, nullptr, count, in_off, in_len, out_off, out_cap, out_len, status, nullptr);
+}
+
+__global__ void __launch_bounds__(32 * XPD_WARPS_PER_BLOCK)
+xpress_parse_kernel(const uint8_t* __restrict__ in, uint32_t* __restrict__ tok, uint32_t count,
+                    const uint64_t* __restrict__ in_off, const uint32_t* __restrict__ in_len,
+                    const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ out_cap,
+                    uint32_t* __restrict__ out_len, int32_t* __restrict__ status, uint32_t* __restrict__ ntok)
+{
+    xpress_decode_body<LaneTok>(in, nullptr, tok, count, in_off, in_len, out_off, out_cap, out_len, status, ntok);
 }
 
 } // namespace msc

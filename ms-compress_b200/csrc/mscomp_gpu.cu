@@ -168,6 +168,27 @@ MSCompStatus mscomp_gpu_lznt1_decompress(mscomp_gpu_ctx* ctx, const uint8_t* d_i
 
 // ---- Xpress-Huffman / Xpress batches ---------------------------------------------------------------------------------
 
+// Token scratch for the two-kernel decoders: 4 bytes per output byte of the region the batch can touch.  Returns the
+// scratch pointer, or nullptr when the region is unknown / too large (the single-kernel decoder is used then).
+static uint32_t* token_scratch(mscomp_gpu_ctx* ctx, const mscomp_gpu_batch* b)
+{
+    static const char* mode = getenv("MSCOMP_LZ_DECODE");            // "fused" forces the single-kernel decoders
+    if (mode && strcmp(mode, "fused") == 0) return nullptr;
+    uint64_t* d_ext = (uint64_t*)ctx->get(SC_RESULT, 256);
+    uint64_t* h_ext = (uint64_t*)ctx->get_pinned(256);
+    if (!d_ext || !h_ext) return nullptr;
+    MSC_LAUNCH(ctx, batch_extent_kernel, 1, SUM_THREADS, b->d_out_off, b->d_out_cap, b->count, d_ext + 8);
+    cudaMemcpyAsync(h_ext + 8, d_ext + 8, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return nullptr;
+    const uint64_t extent = h_ext[8];
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    const uint64_t have = ctx->scratch_cap[SC_AUX2];
+    if (extent == 0 || extent > (1ull << 36)) return nullptr;
+    if (4 * extent + 64 > have && 4 * extent + 64 > (uint64_t)free_b / 2 + have) return nullptr;   // would not fit comfortably
+    return (uint32_t*)ctx->get(SC_AUX2, 4 * extent + 64);
+}
+
 static bool batch_ok(const mscomp_gpu_ctx* ctx, const uint8_t* d_in, const uint8_t* d_out, const mscomp_gpu_batch* b)
 {
     return ctx && b && (b->count == 0 || (d_in && d_out && b->d_in_off && b->d_in_len && b->d_out_off && b->d_out_cap && b->d_out_len && b->d_status));
@@ -198,9 +219,19 @@ MSCompStatus mscomp_gpu_xpress_huff_decompress_batch(mscomp_gpu_ctx* ctx, const 
     if (!batch_ok(ctx, d_in, d_out, b)) return MSCOMP_ARG_ERROR;
     if (!b->count) return MSCOMP_OK;
     cudaSetDevice(ctx->device);
-    const uint32_t groups = (b->count + 31) / 32, cap = (uint32_t)ctx->sm_count * 5;
-    MSC_LAUNCH_SMEM(ctx, xhuff_decode_kernel, groups < cap ? groups : cap, 32 * XHD_WARPS_PER_BLOCK, XHD_SMEM_BYTES,
-                    d_in, d_out, b->count, b->d_in_off, b->d_in_len, b->d_out_off, b->d_out_cap, b->d_out_len, b->d_status);
+    const uint32_t groups = (b->count + 31) / 32, cap = (uint32_t)ctx->sm_count * 11;     // 11 resident warps per SM (19 KB each)
+    uint32_t* tok = b->count >= 64 ? token_scratch(ctx, b) : nullptr;
+    uint32_t* ntok = tok ? (uint32_t*)ctx->get(SC_AUX1, ((size_t)b->count + 1) * sizeof(uint32_t)) : nullptr;
+    if (tok && ntok) {
+        // two kernels: bit parsing by one lane per buffer (tokens only), LZ77 execution by one warp per buffer
+        MSC_LAUNCH_SMEM(ctx, xhuff_parse_kernel, groups < cap ? groups : cap, 32 * XHD_WARPS_PER_BLOCK, XHD_SMEM_BYTES,
+                        d_in, tok, b->count, b->d_in_off, b->d_in_len, b->d_out_off, b->d_out_cap, b->d_out_len, b->d_status, ntok);
+        const uint32_t ab = (b->count + LZA_WARPS_PER_BLOCK - 1) / LZA_WARPS_PER_BLOCK, acap = (uint32_t)ctx->sm_count * 16;
+        MSC_LAUNCH(ctx, lz_apply_kernel, ab < acap ? ab : acap, 32 * LZA_WARPS_PER_BLOCK, tok, ntok, b->d_out_off, b->d_status, b->count, d_out);
+    } else {
+        MSC_LAUNCH_SMEM(ctx, xhuff_decode_kernel, groups < cap ? groups : cap, 32 * XHD_WARPS_PER_BLOCK, XHD_SMEM_BYTES,
+                        d_in, d_out, b->count, b->d_in_off, b->d_in_len, b->d_out_off, b->d_out_cap, b->d_out_len, b->d_status);
+    }
     return msc_cuda_status(cudaGetLastError(), "xpress_huff_decompress");
 }
 
@@ -222,8 +253,17 @@ MSCompStatus mscomp_gpu_xpress_decompress_batch(mscomp_gpu_ctx* ctx, const uint8
     if (!b->count) return MSCOMP_OK;
     cudaSetDevice(ctx->device);
     const uint32_t groups = (b->count + 32 * XPD_WARPS_PER_BLOCK - 1) / (32 * XPD_WARPS_PER_BLOCK), cap = (uint32_t)ctx->sm_count * 8;
-    MSC_LAUNCH(ctx, xpress_decode_kernel, groups < cap ? groups : cap, 32 * XPD_WARPS_PER_BLOCK,
-               d_in, d_out, b->count, b->d_in_off, b->d_in_len, b->d_out_off, b->d_out_cap, b->d_out_len, b->d_status);
+    uint32_t* tok = b->count >= 64 ? token_scratch(ctx, b) : nullptr;
+    uint32_t* ntok = tok ? (uint32_t*)ctx->get(SC_AUX1, ((size_t)b->count + 1) * sizeof(uint32_t)) : nullptr;
+    if (tok && ntok) {
+        MSC_LAUNCH(ctx, xpress_parse_kernel, groups < cap ? groups : cap, 32 * XPD_WARPS_PER_BLOCK,
+                   d_in, tok, b->count, b->d_in_off, b->d_in_len, b->d_out_off, b->d_out_cap, b->d_out_len, b->d_status, ntok);
+        const uint32_t ab = (b->count + LZA_WARPS_PER_BLOCK - 1) / LZA_WARPS_PER_BLOCK, acap = (uint32_t)ctx->sm_count * 16;
+        MSC_LAUNCH(ctx, lz_apply_kernel, ab < acap ? ab : acap, 32 * LZA_WARPS_PER_BLOCK, tok, ntok, b->d_out_off, b->d_status, b->count, d_out);
+    } else {
+        MSC_LAUNCH(ctx, xpress_decode_kernel, groups < cap ? groups : cap, 32 * XPD_WARPS_PER_BLOCK,
+                   d_in, d_out, b->count, b->d_in_off, b->d_in_len, b->d_out_off, b->d_out_cap, b->d_out_len, b->d_status);
+    }
     return msc_cuda_status(cudaGetLastError(), "xpress_decompress");
 }
 

@@ -69,4 +69,24 @@ void emu_xpress_encode(const uint8_t* in, uint8_t* out, uint32_t count, const ui
     emu::launch(msc::xpress_encode_kernel, dim3e(grid), dim3e(msc::XPE_THREADS), in, out, count, in_off, in_len, out_off, out_cap, out_len, status);
 }
 
+
+// two-kernel decoders: parse (one lane per buffer, tokens) + apply (one warp per buffer)
+static uint64_t emu_extent(uint32_t count, const uint64_t* out_off, const uint32_t* out_cap)
+{ uint64_t e = 0; for (uint32_t i = 0; i < count; ++i) e = std::max<uint64_t>(e, out_off[i] + out_cap[i]); return e; }
+
+void emu_xhuff_decode2(const uint8_t* in, uint8_t* out, uint32_t count, const uint64_t* in_off, const uint32_t* in_len,
+                       const uint64_t* out_off, const uint32_t* out_cap, uint32_t* out_len, int32_t* status, uint32_t grid)
+{
+    std::vector<uint32_t> tok(emu_extent(count, out_off, out_cap) + 16), ntok(count + 1);
+    emu::launch(msc::xhuff_parse_kernel, dim3e(grid), dim3e(32 * msc::XHD_WARPS_PER_BLOCK), in, tok.data(), count, in_off, in_len, out_off, out_cap, out_len, status, ntok.data());
+    emu::launch(msc::lz_apply_kernel, dim3e(grid), dim3e(32 * msc::LZA_WARPS_PER_BLOCK), (const uint32_t*)tok.data(), (const uint32_t*)ntok.data(), out_off, (const int32_t*)status, count, out);
+}
+void emu_xpress_decode2(const uint8_t* in, uint8_t* out, uint32_t count, const uint64_t* in_off, const uint32_t* in_len,
+                        const uint64_t* out_off, const uint32_t* out_cap, uint32_t* out_len, int32_t* status, uint32_t grid)
+{
+    std::vector<uint32_t> tok(emu_extent(count, out_off, out_cap) + 16), ntok(count + 1);
+    emu::launch(msc::xpress_parse_kernel, dim3e(grid), dim3e(32 * msc::XPD_WARPS_PER_BLOCK), in, tok.data(), count, in_off, in_len, out_off, out_cap, out_len, status, ntok.data());
+    emu::launch(msc::lz_apply_kernel, dim3e(grid), dim3e(32 * msc::LZA_WARPS_PER_BLOCK), (const uint32_t*)tok.data(), (const uint32_t*)ntok.data(), out_off, (const int32_t*)status, count, out);
+}
+
 }

@@ -19,11 +19,15 @@ def corpus(ms):
     return out
 
 
+DECODERS = {"xpress_huff": ["emu_xhuff_decode", "emu_xhuff_decode2"], "xpress": ["emu_xpress_decode", "emu_xpress_decode2"]}   # fused, parse+apply
+
+
+@pytest.mark.parametrize("variant", [0, 1])
 @pytest.mark.parametrize("fmt", ["xpress_huff", "xpress"])
-def test_decode_matches_oracle(emu, oracle, ms, fmt):
+def test_decode_matches_oracle(emu, oracle, ms, fmt, variant):
     plains = corpus(ms)
     comps = [oracle.compress(fmt, p) for p in plains]
-    st, ol, outs = emu_batch(emu, KERNELS[fmt][0], comps + [b""], [len(p) for p in plains] + [0])
+    st, ol, outs = emu_batch(emu, DECODERS[fmt][variant], comps + [b""], [len(p) for p in plains] + [0])
     assert not st.any()
     assert outs[:-1] == plains and outs[-1] == b""
 
@@ -46,8 +50,9 @@ def test_encode_roundtrips_through_oracle(emu, oracle, ms, fmt):
     assert len(ours) <= 1.15 * len(oracle.compress(fmt, p))
 
 
+@pytest.mark.parametrize("variant", [0, 1])
 @pytest.mark.parametrize("fmt", ["xpress_huff", "xpress"])
-def test_decode_status_equals_oracle_on_bad_input(emu, oracle, ms, fmt):
+def test_decode_status_equals_oracle_on_bad_input(emu, oracle, ms, fmt, variant):
     rnd = random.Random(5)
     cases = []
     for kind in ("text", "runs"):
@@ -62,7 +67,7 @@ def test_decode_status_equals_oracle_on_bad_input(emu, oracle, ms, fmt):
             for _ in range(rnd.randint(1, 3)):
                 b[rnd.randrange(len(b))] ^= 1 << rnd.randrange(8)
             cases.append((bytes(b), n + rnd.choice((0, 64))))
-    st, ol, outs = emu_batch(emu, KERNELS[fmt][0], [c for c, _ in cases], [cap for _, cap in cases])
+    st, ol, outs = emu_batch(emu, DECODERS[fmt][variant], [c for c, _ in cases], [cap for _, cap in cases])
     for i, (src, cap) in enumerate(cases):
         rc, exp = oracle.decompress(fmt, src, cap)
         assert st[i] == rc, (i, st[i], rc)
