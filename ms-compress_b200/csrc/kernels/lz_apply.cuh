@@ -75,33 +75,27 @@ lz_apply_kernel(const uint32_t* __restrict__ tok_base, const uint32_t* __restric
                 const unsigned W = __reduce_min_sync(FULL, pending ? pos : 0xffffffffu);
                 if (W == 0xffffffffu) break;
                 const bool can = pending && (pos == W || pos - off + len <= W);
-                unsigned coop = __ballot_sync(FULL, can && len >= 64);
-                if (can && len < 64) {
-                    if (off >= len) {
-                        // no overlap: batch the loads ahead of the stores (8 at a time) for memory-level parallelism
-                        for (uint32_t i = 0; i < len; i += 8) {
-                            uint8_t b[8];
+                // The runnable matches are copied BYTE-transposed: their bytes are numbered consecutively, lane j takes
+                // byte j, j+32, ... -- neighbouring lanes write neighbouring addresses and read neighbouring sources.
+                const uint32_t cl = can ? len : 0u;
+                const uint32_t cincl = (uint32_t)warp_incl_scan((int)cl);
+                const uint32_t total = __shfl_sync(FULL, cincl, 31);
+                for (uint32_t b0 = 0; b0 < total; b0 += 32) {
+                    const uint32_t bidx = b0 + lane;
+                    // owner token: first lane whose inclusive count exceeds bidx (binary search over the lanes)
+                    int t = 0;
 #pragma unroll
-                            for (int k = 0; k < 8; ++k) b[k] = (i + k < len) ? o[pos - off + i + k] : (uint8_t)0;
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) if (i + k < len) o[pos + i + k] = b[k];
-                        }
-                    } else {
-                        for (uint32_t i = 0; i < len; ++i) o[pos + i] = o[pos - off + i];
+                    for (int step = 16; step; step >>= 1) {
+                        const uint32_t c = __shfl_sync(FULL, cincl, t + step - 1);
+                        if (c <= bidx) t += step;
                     }
-                }
-                while (coop) {                                  // long matches: the whole warp copies
-                    const int src = __ffs((int)coop) - 1;
-                    coop &= coop - 1;
-                    const uint32_t d = __shfl_sync(FULL, pos, src), l = __shfl_sync(FULL, len, src), f = __shfl_sync(FULL, off, src);
-                    if (f >= 32) {
-                        for (uint32_t i = 0; i < l; i += 32) {
-                            if (i + lane < l) o[d + i + lane] = o[d - f + i + lane];
-                            __syncwarp();
-                        }
-                    } else {
-                        for (uint32_t i = lane; i < l; i += 32) o[d + i] = o[d - f + (i % f)];
-                        __syncwarp();
+                    const uint32_t t_incl = __shfl_sync(FULL, cincl, t), t_len = __shfl_sync(FULL, cl, t);
+                    const uint32_t t_pos = __shfl_sync(FULL, pos, t), t_off = __shfl_sync(FULL, off, t);
+                    if (bidx < total) {
+                        const uint32_t k = bidx - (t_incl - t_len);                      // byte index inside the match
+                        // overlapped match (off < len): byte k equals byte k mod off of the period just before it
+                        const uint32_t sk = (t_off < t_len) ? (k % t_off) : k;
+                        o[t_pos + k] = o[t_pos - t_off + sk];
                     }
                 }
                 if (can) pending = false;

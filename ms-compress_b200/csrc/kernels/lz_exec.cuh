@@ -14,37 +14,45 @@ constexpr uint32_t LZQ_MAXLEN = 32768;         // longest single match token the
 __device__ __forceinline__ uint32_t lzq_lit(uint32_t b) { return b & 0xFFu; }
 __device__ __forceinline__ uint32_t lzq_match(uint32_t off, uint32_t len) { return 0x80000000u | ((len - 1) << 16) | off; }
 
-// Byte-sequential reader over global memory with a 16-byte window held in registers (two aligned 8-byte words).
-// Reads of <= 4 bytes at the cursor never touch memory except when the cursor crosses an 8-byte boundary.
+// Byte-sequential reader over one stream in global memory: a 16-byte window held in registers (two aligned 8-byte
+// words).  Positions are 32-bit offsets from the start of the stream, so the bookkeeping is single 32-bit
+// instructions; reads of <= 4 bytes at the cursor touch memory only when the cursor crosses an 8-byte boundary.
 struct ByteWindow {
-    const uint8_t* base;     // aligned-down address of w0
+    const uint8_t* origin;   // 8-byte aligned address at or just below the stream start
+    uint32_t skew;           // stream start - origin (0..7)
+    uint32_t wb;             // offset (from origin, multiple of 8) of w0
+    uint32_t lim;            // first multiple of 8 (from origin) at or beyond the end of the stream
     uint64_t w0, w1;
-    const uint8_t* lim;      // first 8-byte aligned address at or beyond the end of the buffer
+    __device__ __forceinline__ void load(uint32_t at8)
+    {
+        wb = at8;
+        w0 = (wb < lim) ? *reinterpret_cast<const uint64_t*>(origin + wb) : 0;
+        w1 = (wb + 8 < lim) ? *reinterpret_cast<const uint64_t*>(origin + wb + 8) : 0;
+    }
     __device__ __forceinline__ void init(const uint8_t* p, const uint8_t* end)
     {
-        base = p - ((uintptr_t)p & 7u);
-        lim = end + ((8u - ((uintptr_t)end & 7u)) & 7u);
-        w0 = (base < lim) ? *reinterpret_cast<const uint64_t*>(base) : 0;
-        w1 = (base + 8 < lim) ? *reinterpret_cast<const uint64_t*>(base + 8) : 0;
+        skew = (uint32_t)((uintptr_t)p & 7u);
+        origin = p - skew;
+        lim = ((uint32_t)(end - p) + skew + 7u) & ~7u;
+        load(0);
     }
-    // make [p, p+4) readable from the window; cheap when p moves forward by a few bytes
-    __device__ __forceinline__ void seek(const uint8_t* p)
+    // 4 bytes (little endian) at stream offset `at`; bytes beyond the end of the stream read as 0
+    __device__ __forceinline__ uint32_t get32(uint32_t at)
     {
-        if (p >= base && p < base + 8) return;
-        if (p >= base + 8 && p < base + 16) {                      // the usual case: slide by one word
-            base += 8; w0 = w1;
-            w1 = (base + 8 < lim) ? *reinterpret_cast<const uint64_t*>(base + 8) : 0;
+        const uint32_t a = at + skew;
+        uint32_t d = a - wb;
+        if (d >= 8u) {
+            if (d < 16u) {                                       // the usual case: slide by one word
+                wb += 8; w0 = w1;
+                w1 = (wb + 8 < lim) ? *reinterpret_cast<const uint64_t*>(origin + wb + 8) : 0;
 #ifndef MSC_EMU
-            // entering a new 128-byte line: ask for the one after the next so that the loads above hit L1 / L2
-            if ((((uintptr_t)base) & 127u) == 0 && base + 256 < lim) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + 256));
+                // entering a new 128-byte line: ask for the one after the next so that the loads above hit L1 / L2
+                if ((wb & 127u) == 0 && wb + 256 < lim) asm volatile("prefetch.global.L2 [%0];" ::"l"(origin + wb + 256));
 #endif
-            return;
+            } else load(a & ~7u);                                // rewind / long jump (code-length table, new chunk)
+            d = a - wb;
         }
-        init(p, lim);                                               // rewind / long jump (code-length table, new chunk)
-    }
-    __device__ __forceinline__ uint32_t get32(const uint8_t* p)
-    {   // 4 bytes at p (little endian), p in [base, base+8)
-        const uint32_t sh = (uint32_t)(p - base) * 8;            // 0..56
+        const uint32_t sh = d * 8;                               // 0..56
         uint64_t v = w0 >> sh;
         if (sh > 32) v |= w1 << (64 - sh);
         return (uint32_t)v;

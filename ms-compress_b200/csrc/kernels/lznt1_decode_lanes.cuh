@@ -51,9 +51,8 @@ lznt1_decode_lanes_kernel(const uint8_t* __restrict__ in, uint64_t in_len, const
             if (!active) continue;
             if (raw) {                                                   // stored chunk :188-206
                 const uint32_t k = min(n - ip, 8u);
-                win.seek(src + ip);
-                uint64_t v = win.get32(src + ip);
-                if (k > 4) { win.seek(src + ip + 4); v |= (uint64_t)win.get32(src + ip + 4) << 32; }
+                uint64_t v = win.get32(ip);
+                if (k > 4) v |= (uint64_t)win.get32(ip + 4) << 32;
                 if (O.opos < O.head) { for (uint32_t i = 0; i < k; ++i) O.put_byte((uint32_t)(v >> (8 * i))); }
                 else O.put_bytes(v, k);
                 ip += k;
@@ -62,15 +61,13 @@ lznt1_decode_lanes_kernel(const uint8_t* __restrict__ in, uint64_t in_len, const
             }
             if (f == 1u) {                                               // next flag byte (:80-82)
                 if (ip >= n) { active = false; continue; }
-                win.seek(src + ip);
-                f = (win.get32(src + ip) & 0xFFu) | 0x100u;              // flag bits, LSB first, with a sentinel
+                f = (win.get32(ip) & 0xFFu) | 0x100u;              // flag bits, LSB first, with a sentinel
                 ++ip;
             }
             if (ip == n) { active = false; continue; }                   // :86 input ends inside the group
             if (f & 1u) {                                                // token
                 if (ip + 2 > n) { st = ST_DATA; active = false; continue; }          // :90
-                win.seek(src + ip);
-                const uint32_t t = win.get32(src + ip) & 0xFFFFu;
+                const uint32_t t = win.get32(ip) & 0xFFFFu;
                 ip += 2;
                 int S, lim;
                 lznt1_shift_limit((int)O.opos, S, lim);                  // :91
@@ -82,9 +79,8 @@ lznt1_decode_lanes_kernel(const uint8_t* __restrict__ in, uint64_t in_len, const
                 uint32_t k = (uint32_t)__ffs((int)f) - 1;                // consecutive 0 flags (<= 8: the sentinel stops it)
                 k = min(k, n - ip);
                 if (O.opos + k > (uint32_t)LZNT1_CHUNK) { st = ST_DATA; active = false; continue; }
-                win.seek(src + ip);
-                uint64_t v = win.get32(src + ip);
-                if (k > 4) { win.seek(src + ip + 4); v |= (uint64_t)win.get32(src + ip + 4) << 32; }
+                uint64_t v = win.get32(ip);
+                if (k > 4) v |= (uint64_t)win.get32(ip + 4) << 32;
                 if (O.opos < O.head) { for (uint32_t i = 0; i < k; ++i) O.put_byte((uint32_t)(v >> (8 * i))); }
                 else O.put_bytes(v, k);
                 ip += k;

@@ -11,7 +11,7 @@
 //
 // Stages (all in shared memory):
 //   A  stage the chunk, zero padded
-//   B  counting sort of positions by a 12-bit hash of their first 3 bytes (ascending inside a bucket)
+//   B  stable radix sort of positions by a 12-bit hash of their first 3 bytes (ascending inside a bucket)
 //   C  all-position match search -> lenoff[p] = len | dist << 16, match bitmap M
 //   D  greedy parse: one thread walks M with find-first-set and records the visited bitmap V
 //   E  every visited position computes its item index k and the number of matches before it from prefix
@@ -40,7 +40,8 @@ struct Lznt1EncSmem {
     uint32_t M[128], V[128], F[128];             // match bitmap, visited bitmap (by position), flag bits (by item)
     uint16_t prefV[128], prefVM[128];
     uint16_t goff[LZNT1_CHUNK / 8 + 8];          // byte offset of each group's flag byte
-    uint32_t items, matches, scan_tmp[8];
+    uint16_t chain[LZNT1_CHUNK / 12 + 8];        // every 4th visited match of the greedy parse
+    uint32_t nchain, scan_tmp[8];
 };
 
 __device__ __forceinline__ uint32_t lz_load4(const uint8_t* s, int idx)
@@ -79,7 +80,7 @@ lznt1_encode_kernel(const uint8_t* __restrict__ in, uint64_t in_len, uint32_t nc
         const int npos = n - 2;                      // positions 0..n-3 are indexed (Fill :99)
         for (int p = tid; p < npos; p += LZE_THREADS) atomicAdd(&sm.cnt[lz_hash3(lz_load4(sm.in, p))], 1u);
         __syncthreads();
-        {   // exclusive scan of 4096 counts: 16 per thread, then a block scan of the 256 partial sums
+        {   // inclusive scan of 4096 counts (16 per thread + block scan of the 256 partial sums): cnt[h] = END of bucket h
             uint32_t loc[16], sum = 0;
 #pragma unroll
             for (int i = 0; i < 16; ++i) { loc[i] = sm.cnt[tid * 16 + i]; sum += loc[i]; }
@@ -90,24 +91,56 @@ lznt1_encode_kernel(const uint8_t* __restrict__ in, uint64_t in_len, uint32_t nc
             for (int w = 0; w < warp; ++w) woff += sm.scan_tmp[w];
             uint32_t run = woff + (uint32_t)incl - sum;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) { sm.cnt[tid * 16 + i] = run; run += loc[i]; }
+            for (int i = 0; i < 16; ++i) { run += loc[i]; sm.cnt[tid * 16 + i] = run; }
         }
-        __syncthreads();
-        if (warp == 0) {   // ordered scatter: one warp walks the positions in order, ranks by lane inside a group
-            for (int g = 0; g < npos; g += 32) {
-                const int p = g + lane;
-                const bool on = p < npos;
-                const uint32_t h = on ? lz_hash3(lz_load4(sm.in, p)) : (0x10000u + (uint32_t)lane);
-                const unsigned peers = __match_any_sync(FULL, h);
-                const int rank = __popc(peers & ((1u << lane) - 1));
-                uint32_t b = 0;
-                if (on) { b = sm.cnt[h]; sm.sorted[b + rank] = (uint16_t)p; }
-                __syncwarp();
-                if (on && rank == 0) sm.cnt[h] = b + (uint32_t)__popc(peers);
-                __syncwarp();
+        // Stable LSD radix sort of the positions by their 12-bit hash (3 passes of 4 bits): every thread owns 16
+        // consecutive elements and a private column of 16 digit counters, so ranks need no atomics and equal keys
+        // keep their order -- positions stay ascending inside a bucket, which the early exit of the search relies on.
+        {
+            uint16_t* cntT = reinterpret_cast<uint16_t*>(sm.lenoff);          // [16 digits][256 threads], lenoff is not live yet
+            const uint16_t* srcA = sm.ord;                                    // pass 0 reads the identity instead
+            uint16_t* dstA = sm.sorted;
+            for (int pass = 0; pass < 3; ++pass) {
+                const int sh = 4 * pass;
+#pragma unroll
+                for (int d = 0; d < 16; ++d) cntT[d * LZE_THREADS + tid] = 0;
+                for (int i = 0; i < 16; ++i) {
+                    const int e = tid * 16 + i;
+                    if (e < npos) {
+                        const int p = pass ? (int)srcA[e] : e;
+                        cntT[((lz_hash3(lz_load4(sm.in, p)) >> sh) & 15) * LZE_THREADS + tid] += 1;
+                    }
+                }
+                __syncthreads();
+                {   // exclusive scan of the 4096 counters in (digit, thread) order
+                    uint32_t loc[16], sum = 0;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) { loc[i] = cntT[tid * 16 + i]; sum += loc[i]; }
+                    const int incl = warp_incl_scan((int)sum);
+                    if (lane == 31) sm.scan_tmp[warp] = (uint32_t)incl;
+                    __syncthreads();
+                    uint32_t woff = 0;
+                    for (int w = 0; w < warp; ++w) woff += sm.scan_tmp[w];
+                    uint32_t run = woff + (uint32_t)incl - sum;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) { cntT[tid * 16 + i] = (uint16_t)run; run += loc[i]; }
+                }
+                __syncthreads();
+                for (int i = 0; i < 16; ++i) {
+                    const int e = tid * 16 + i;
+                    if (e < npos) {
+                        const int p = pass ? (int)srcA[e] : e;
+                        const int c = ((lz_hash3(lz_load4(sm.in, p)) >> sh) & 15) * LZE_THREADS + tid;
+                        const uint32_t slot = cntT[c];
+                        cntT[c] = (uint16_t)(slot + 1);
+                        dstA[slot] = (uint16_t)p;
+                    }
+                }
+                __syncthreads();
+                const uint16_t* t2 = dstA; dstA = const_cast<uint16_t*>(srcA); srcA = t2;     // sorted -> ord -> sorted
             }
         }
-        __syncthreads();   // cnt[h] now = end offset of bucket h; begin = cnt[h-1] (0 for h == 0)
+        // cnt[h] = end offset of bucket h; begin = cnt[h-1] (0 for h == 0); sorted[] holds the result of pass 2
 
         // ---- C: match search for every position ------------------------------------------------------
         // The k-th entry of a bucket has k candidates (the earlier entries).  Threads take the entries grouped by that
@@ -191,13 +224,30 @@ lznt1_encode_kernel(const uint8_t* __restrict__ in, uint64_t in_len, uint32_t nc
                     atomicOr(&sm.V[w], (hi_b == 32 ? 0xffffffffu : ((1u << hi_b) - 1)) & (0xffffffffu << lo_b));
                 }
             };
+            uint16_t* nxt2 = sm.ord;                                                          // dead after stage C as well
+            uint16_t* nxt4 = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(sm.cnt) + 8192);   // upper half of cnt: dead, clear of `out`
             for (int p = tid; p < LZNT1_CHUNK; p += LZE_THREADS)
                 cur[p] = (uint16_t)(((sm.M[p >> 5] >> (p & 31)) & 1) ? first_match_from(p + (int)(sm.lenoff[p] & 0xFFFF)) : LZNT1_CHUNK);
             __syncthreads();                                                                  // F doubles as the mark bitmap
             if (tid == 32) or_range(0, min(first_match_from(0), n));                          // leading literals
-            if (tid == 0) {     // the chain itself is a pointer chase over nxt: one shared-memory load per visited match
-                int q = first_match_from(0);
-                while (q < LZNT1_CHUNK) { sm.F[q >> 5] |= 1u << (q & 31); q = cur[q]; }
+            // two rounds of pointer doubling shorten the serial part of the chase by 4: nxt2 = nxt o nxt, nxt4 = nxt2 o nxt2
+            for (int p = tid; p < LZNT1_CHUNK; p += LZE_THREADS) { const int t = cur[p]; nxt2[p] = (uint16_t)(t < LZNT1_CHUNK ? cur[t] : LZNT1_CHUNK); }
+            __syncthreads();
+            for (int p = tid; p < LZNT1_CHUNK; p += LZE_THREADS) { const int t = nxt2[p]; nxt4[p] = (uint16_t)(t < LZNT1_CHUNK ? nxt2[t] : LZNT1_CHUNK); }
+            __syncthreads();
+            if (tid == 0) {     // every 4th visited match: one shared-memory load per link
+                int q = first_match_from(0), k = 0;
+                while (q < LZNT1_CHUNK) { sm.chain[k++] = (uint16_t)q; q = nxt4[q]; }
+                sm.nchain = (uint32_t)k;
+            }
+            __syncthreads();
+            for (uint32_t k = tid; k < sm.nchain; k += LZE_THREADS) {                         // the three in between, in parallel
+                int q = sm.chain[k];
+                atomicOr(&sm.F[q >> 5], 1u << (q & 31));
+                const int q2 = nxt2[q];
+                q = cur[q];
+                if (q < LZNT1_CHUNK) atomicOr(&sm.F[q >> 5], 1u << (q & 31));
+                if (q2 < LZNT1_CHUNK) { atomicOr(&sm.F[q2 >> 5], 1u << (q2 & 31)); const int q3 = cur[q2]; if (q3 < LZNT1_CHUNK) atomicOr(&sm.F[q3 >> 5], 1u << (q3 & 31)); }
             }
             __syncthreads();
             // visited bitmap: every visited match plus the literals up to the next visited match

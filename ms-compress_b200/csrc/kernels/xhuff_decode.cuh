@@ -54,8 +54,8 @@ struct XhLane {
     bool need_table;
 };
 
-__device__ __forceinline__ uint32_t xh_rd16(XhLane& L, uint32_t at) { L.win.seek(L.in + at); return L.win.get32(L.in + at) & 0xFFFFu; }
-__device__ __forceinline__ uint32_t xh_rd32(XhLane& L, uint32_t at) { L.win.seek(L.in + at); return L.win.get32(L.in + at); }
+__device__ __forceinline__ uint32_t xh_rd16(XhLane& L, uint32_t at) { return L.win.get32(at) & 0xFFFFu; }
+__device__ __forceinline__ uint32_t xh_rd32(XhLane& L, uint32_t at) { return L.win.get32(at); }
 
 __device__ __forceinline__ bool xh_mask_is_zero(const XhLane& L) { return L.bits == 0 || (L.mask >> (32 - L.bits)) == 0; }
 __device__ __forceinline__ uint32_t xh_peek(const XhLane& L, int n) { return (L.mask >> 16) >> (16 - n); }
@@ -123,9 +123,14 @@ __device__ __forceinline__ uint32_t xh_decode_symbol(XhLane& L, const XhWarpSmem
 {
     const int r = L.bits;
     const uint32_t x = (r < 15) ? (r == 0 ? 0u : ((L.mask >> (32 - r)) << (15 - r))) : (L.mask >> 17);
-    int n = 1;                                                   // first length whose limit exceeds x
-#pragma unroll
-    for (int k = 1; k <= 14; ++k) n += (x >= L.lims[k]) ? 1 : 0;
+    // n = 1 + #{k : x >= lims[k]}: the limits are non-decreasing, so a 4-level binary search over registers finds it
+    // with 4 compares and 11 selects (lims[15] is the whole code space: never reached)
+    const bool c8 = x >= L.lims[8];
+    const bool c4 = x >= (c8 ? L.lims[12] : L.lims[4]);
+    const bool c2 = x >= (c8 ? (c4 ? L.lims[14] : L.lims[10]) : (c4 ? L.lims[6] : L.lims[2]));
+    const uint32_t l1 = c8 ? (c4 ? (c2 ? 0x8000u : L.lims[13]) : (c2 ? L.lims[11] : L.lims[9]))
+                           : (c4 ? (c2 ? L.lims[7] : L.lims[5]) : (c2 ? L.lims[3] : L.lims[1]));
+    const int n = 1 + (c8 ? 8 : 0) + (c4 ? 4 : 0) + (c2 ? 2 : 0) + (x >= l1 ? 1 : 0);
     if (n > r) return 0xFFFFu;
     const uint32_t rank = (uint32_t)((int)sm.base[n * 32 + lane] + (int)(x >> (15 - n)));
     xh_skip(L, n);

@@ -25,7 +25,7 @@ struct XpLane {
     int status;                              // 0 running, 1 finished OK, < 0 error
 };
 
-__device__ __forceinline__ uint32_t xp_rd32(XpLane& L, uint32_t at) { L.win.seek(L.in + at); return L.win.get32(L.in + at); }
+__device__ __forceinline__ uint32_t xp_rd32(XpLane& L, uint32_t at) { return L.win.get32(at); }
 
 // all 1 bits above all 0 bits (src/xpress_decompress.cpp:41)
 __device__ __forceinline__ bool xp_set_bits_are_highest(uint32_t x) { x = ~x; return ((x + 1) & x) == 0; }
