@@ -14,21 +14,18 @@ constexpr uint32_t LZQ_MAXLEN = 32768;         // longest single match token the
 __device__ __forceinline__ uint32_t lzq_lit(uint32_t b) { return b & 0xFFu; }
 __device__ __forceinline__ uint32_t lzq_match(uint32_t off, uint32_t len) { return 0x80000000u | ((len - 1) << 16) | off; }
 
-// Byte-sequential reader over one stream in global memory: a 16-byte window held in registers (two aligned 8-byte
-// words).  Positions are 32-bit offsets from the start of the stream, so the bookkeeping is single 32-bit
-// instructions; reads of <= 4 bytes at the cursor touch memory only when the cursor crosses an 8-byte boundary.
+// Byte-sequential reader over one stream in global memory: a 24-byte window held in registers (three aligned 8-byte
+// words: two to read from, one already requested for the next slide, so no read ever waits for the load it issues).
+// Positions are 32-bit offsets from the start of the stream, so the bookkeeping is single 32-bit instructions;
+// reads of <= 4 bytes at the cursor touch memory only when the cursor crosses an 8-byte boundary.
 struct ByteWindow {
     const uint8_t* origin;   // 8-byte aligned address at or just below the stream start
     uint32_t skew;           // stream start - origin (0..7)
     uint32_t wb;             // offset (from origin, multiple of 8) of w0
     uint32_t lim;            // first multiple of 8 (from origin) at or beyond the end of the stream
-    uint64_t w0, w1;
-    __device__ __forceinline__ void load(uint32_t at8)
-    {
-        wb = at8;
-        w0 = (wb < lim) ? *reinterpret_cast<const uint64_t*>(origin + wb) : 0;
-        w1 = (wb + 8 < lim) ? *reinterpret_cast<const uint64_t*>(origin + wb + 8) : 0;
-    }
+    uint64_t w0, w1, w2;
+    __device__ __forceinline__ uint64_t word(uint32_t at8) const { return (at8 < lim) ? *reinterpret_cast<const uint64_t*>(origin + at8) : 0; }
+    __device__ __forceinline__ void load(uint32_t at8) { wb = at8; w0 = word(wb); w1 = word(wb + 8); w2 = word(wb + 16); }
     __device__ __forceinline__ void init(const uint8_t* p, const uint8_t* end)
     {
         skew = (uint32_t)((uintptr_t)p & 7u);
@@ -43,8 +40,8 @@ struct ByteWindow {
         uint32_t d = a - wb;
         if (d >= 8u) {
             if (d < 16u) {                                       // the usual case: slide by one word
-                wb += 8; w0 = w1;
-                w1 = (wb + 8 < lim) ? *reinterpret_cast<const uint64_t*>(origin + wb + 8) : 0;
+                wb += 8; w0 = w1; w1 = w2;
+                w2 = word(wb + 16);
 #ifndef MSC_EMU
                 // entering a new 128-byte line: ask for the one after the next so that the loads above hit L1 / L2
                 if ((wb & 127u) == 0 && wb + 256 < lim) asm volatile("prefetch.global.L2 [%0];" ::"l"(origin + wb + 256));

@@ -34,6 +34,9 @@ struct LzFrontSmem {
     uint32_t prefV[LZF_TILE / 32];     // exclusive prefix popcount of V
     uint32_t K[LZF_TILE / 32];         // visited matches (marks of the pointer-jumping parse)
     uint16_t nxt[LZF_TILE];            // nxt(q) = first match position >= q + len[q] (relative; LZF_TILE = leaves the tile)
+    uint16_t nxt2[LZF_TILE], nxt4[LZF_TILE];   // nxt o nxt and its square
+    uint16_t chain[LZF_TILE / 12 + 8]; // every 4th visited match of the tile
+    uint32_t nchain;
     uint32_t next_out;                 // furthest match end seen in this tile (relative)
     uint32_t next_p;                   // position (relative to the unit) where parsing resumes
     uint32_t ntok;                     // tokens emitted so far in the unit
@@ -135,9 +138,31 @@ __device__ __forceinline__ uint32_t lzf_tile(LzFrontSmem& sm, const uint8_t* __r
         if (tid == 0) sm.next_out = 0;
         __syncthreads();
         if (tid == 32 && start_r < tend_r) or_range(start_r, min(first_match_from(start_r), tend_r));   // leading literals
-        if (tid == 0 && start_r < tend_r) {        // the chain itself: one shared-memory load per visited match
-            uint32_t q = first_match_from(start_r);
-            while (q < tend_r) { sm.K[q >> 5] |= 1u << (q & 31); q = cur[q]; }
+        // two rounds of pointer doubling (nxt2 = nxt o nxt, nxt4 = nxt2 o nxt2) cut the serial part of the chase by four
+        for (int r = tid; r < LZF_TILE; r += LZF_THREADS) { const uint32_t t = cur[r]; sm.nxt2[r] = (uint16_t)(t < (uint32_t)LZF_TILE ? cur[t] : (uint32_t)LZF_TILE); }
+        __syncthreads();
+        for (int r = tid; r < LZF_TILE; r += LZF_THREADS) { const uint32_t t = sm.nxt2[r]; sm.nxt4[r] = (uint16_t)(t < (uint32_t)LZF_TILE ? sm.nxt2[t] : (uint32_t)LZF_TILE); }
+        __syncthreads();
+        if (tid == 0) {                             // every 4th visited match: one shared-memory load per link
+            uint32_t k = 0;
+            if (start_r < tend_r) {
+                uint32_t q = first_match_from(start_r);
+                while (q < tend_r) { sm.chain[k++] = (uint16_t)q; q = sm.nxt4[q]; }
+            }
+            sm.nchain = k;
+        }
+        __syncthreads();
+        for (uint32_t k = tid; k < sm.nchain; k += LZF_THREADS) {                      // the three in between, in parallel
+            uint32_t q = sm.chain[k];
+            atomicOr(&sm.K[q >> 5], 1u << (q & 31));
+            const uint32_t q2 = sm.nxt2[q];
+            q = cur[q];
+            if (q < tend_r) atomicOr(&sm.K[q >> 5], 1u << (q & 31));
+            if (q2 < tend_r) {
+                atomicOr(&sm.K[q2 >> 5], 1u << (q2 & 31));
+                const uint32_t q3 = cur[q2];
+                if (q3 < tend_r) atomicOr(&sm.K[q3 >> 5], 1u << (q3 & 31));
+            }
         }
         __syncthreads();
         // visited = marked matches + the literals up to the next marked match; carry-out = furthest match end
