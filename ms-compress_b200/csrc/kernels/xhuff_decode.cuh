@@ -16,7 +16,8 @@
 // (`lims`, HuffmanDecoder.h:58-76) live in 14 registers; the code length is 1 + #{k : x >= lims[k]}; the symbol is
 // syms[base[n] + (x >> (15-n))].  Canonical order puts the literals of a length before its match symbols, so the
 // table stores 8 bits per symbol and a per-length boundary (`litend`) supplies the ninth.
-// Shared memory per lane: 512 B symbols + 3 x 16 x 2 B, interleaved across lanes (19 KB per warp, 11 warps per SM).
+// The per-length `base` and `litend` values sit in packed registers and are selected with the predicates of the
+// length search, so shared memory holds only the symbols: 512 B per lane, interleaved across lanes (16 KB per warp).
 #pragma once
 #include "common.cuh"
 #include "lz_exec.cuh"
@@ -32,11 +33,11 @@ constexpr int XH_MIN_DATA = 260;
 
 struct XhWarpSmem {
     uint8_t syms[XH_SYMS * 32];          // low 8 bits of the symbol at rank i: syms[i * 32 + lane]
-    int16_t base[16 * 32];               // base[n * 32 + lane]; doubles as the per-length counters while building
-    uint16_t fill[16 * 32];              // table build only: next free slot per length
-    uint16_t litend[16 * 32];            // rank of the first match symbol (>= 256) of each length
+                                         // (the first 32 slots of a lane's column hold its counters while it builds a table)
 };
-constexpr int XHD_WARPS_PER_BLOCK = 1;
+// 7 warps x 16 KB per block, 2 blocks per SM: 14 resident warps = 448 buffers per SM, which holds the whole
+// 65,536-buffer batch of BASELINE.json configs[3] in ONE wave on 148 SMs (a lane is latency-bound, so waves cost).
+constexpr int XHD_WARPS_PER_BLOCK = 7;
 constexpr size_t XHD_SMEM_BYTES = sizeof(XhWarpSmem) * XHD_WARPS_PER_BLOCK;
 
 struct XhLane {
@@ -45,8 +46,10 @@ struct XhLane {
     // reader state (Bitstream.h:34-44): window, valid bits, byte cursor
     uint32_t mask; int bits; uint32_t ip;
     ByteWindow win;
-    // decode tables
+    // decode tables, all in registers except the symbols
     uint32_t lims[15];                   // lims[k] = limit of length k (k = 1..14), left aligned in 15 bits
+    uint32_t baseP[8];                   // base[n] (16-bit signed) for n-1 = 2k (low half) and 2k+1 (high half)
+    uint32_t litendP[8];                 // rank of the first match symbol (>= 256) of each length, packed the same way
     uint32_t nused;                      // symbols with a code (ranks >= nused are invalid)
     // progress
     uint32_t chunk_end;
@@ -72,47 +75,63 @@ __device__ __forceinline__ void xh_skip(XhLane& L, int n)
 // HuffmanDecoder::SetCodeLengths (HuffmanDecoder.h:42-91) from the 256 packed nibbles at in[at..at+256).
 __device__ __forceinline__ bool xh_build_table(XhLane& L, XhWarpSmem& sm, int lane, uint32_t at)
 {
-    for (int l = 0; l < 16; ++l) sm.base[l * 32 + lane] = 0;
+    // Per-length counters: 16 x 16 bits kept in the first 32 slots of this lane's OWN symbol column (slot 2l = low
+    // byte, 2l+1 = high byte), so a lane that rebuilds its table never touches the live tables of the other lanes.
+    uint8_t* col = sm.syms + lane;
+    for (int f = 0; f < 32; ++f) col[f * 32] = 0;
+    uint32_t lit[16];                                           // literal symbols (< 256) per length
     for (int i = 0; i < 256; i += 4) {
-        const uint32_t w = xh_rd32(L, at + i);
+        if (i == 128) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) sm.base[((w >> (4 * k)) & 15) * 32 + lane] += 1;
-    }
-    uint32_t last = 0, pos = 0, cnt_prev = 0;                   // lims[len-1], poss[len], cnts[len-1] (cnts[0] counts as 0)
-    bool ok = true;
-#pragma unroll
-    for (int len = 1; len <= 15; ++len) {
-        const uint32_t cnt = (uint32_t)(uint16_t)sm.base[len * 32 + lane];
-        pos += cnt_prev;                                        // poss[len] = poss[len-1] + cnts[len-1]   (:79-80)
-        cnt_prev = cnt;
-        sm.fill[len * 32 + lane] = (uint16_t)pos;
-        sm.litend[len * 32 + lane] = (uint16_t)pos;             // corrected below if the length has literals
-        sm.base[len * 32 + lane] = (int16_t)((int)pos - (int)(last >> (15 - len)));     // rank = base[n] + (x >> (15-n))
-        if (len < 15) {
-            const uint32_t inc = cnt << (15 - len);
-            if (last + inc > 32768u) ok = false;                // :65, :73 over-subscribed
-            last += inc;
-            L.lims[len] = last;
-        } else {
-            if (last + cnt > 32768u) ok = false;                // :76  (lims[15] itself is the whole code space, :61)
-            L.nused = pos + cnt;
-        }
-    }
-    if (!ok) return false;
-    for (int i = 0; i < 256; i += 4) {                          // symbols in (length, symbol) order (:83-88)
-        if (i == 128) {                                         // all literals are placed: the match symbols start here
-#pragma unroll
-            for (int len = 1; len <= 15; ++len) sm.litend[len * 32 + lane] = sm.fill[len * 32 + lane];
+            for (int l = 1; l <= 15; ++l) lit[l] = (uint32_t)col[(2 * l) * 32] | ((uint32_t)col[(2 * l + 1) * 32] << 8);
         }
         const uint32_t w = xh_rd32(L, at + i);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const uint32_t l = (w >> (4 * k)) & 15;
-            if (l) {
-                const uint32_t f = sm.fill[l * 32 + lane];
-                sm.fill[l * 32 + lane] = (uint16_t)(f + 1);
-                sm.syms[f * 32 + lane] = (uint8_t)(2 * i + k);
-            }
+            const uint32_t c = ((uint32_t)col[(2 * l) * 32] | ((uint32_t)col[(2 * l + 1) * 32] << 8)) + 1;
+            col[(2 * l) * 32] = (uint8_t)c; col[(2 * l + 1) * 32] = (uint8_t)(c >> 8);
+        }
+    }
+    uint32_t last = 0, pos = 0, cnt_prev = 0;                   // lims[len-1], poss[len], cnts[len-1] (cnts[0] counts as 0)
+    uint32_t used_lens = 0;
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { L.baseP[k] = 0; L.litendP[k] = 0; }
+#pragma unroll
+    for (int len = 1; len <= 15; ++len) {
+        const uint32_t c = (uint32_t)col[(2 * len) * 32] | ((uint32_t)col[(2 * len + 1) * 32] << 8);
+        pos += cnt_prev;                                        // poss[len] = poss[len-1] + cnts[len-1]   (:79-80)
+        cnt_prev = c;
+        if (c) used_lens |= 1u << len;
+        const uint32_t b16 = (uint32_t)((int)pos - (int)(last >> (15 - len))) & 0xFFFFu;    // rank = base[n] + (x >> (15-n))
+        const uint32_t e16 = (pos + lit[len]) & 0xFFFFu;
+        const int m = len - 1;
+        L.baseP[m >> 1] |= b16 << (16 * (m & 1));
+        L.litendP[m >> 1] |= e16 << (16 * (m & 1));
+        if (len < 15) {
+            const uint32_t inc = c << (15 - len);
+            if (last + inc > 32768u) ok = false;                // :65, :73 over-subscribed
+            last += inc;
+            L.lims[len] = last;
+        } else {
+            if (last + c > 32768u) ok = false;                  // :76  (lims[15] itself is the whole code space, :61)
+            L.nused = pos + c;
+        }
+    }
+    if (!ok) return false;
+    // symbols in (length, symbol) order (:83-88): one sweep over the table per code length in use
+    uint32_t fill = 0;
+    for (int n = 1; n <= 15; ++n) {
+        if (!((used_lens >> n) & 1)) continue;
+        for (int i = 0; i < 256; i += 4) {
+            const uint32_t w = xh_rd32(L, at + i);
+            // lanes whose nibble equals n: compare all 8 nibbles at once
+            uint32_t eq = w ^ (0x11111111u * (uint32_t)n);      // nibble == 0  <=>  length n
+            if (((eq - 0x11111111u) & ~eq & 0x88888888u) == 0) continue;          // no zero nibble in this word
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (((eq >> (4 * k)) & 15) == 0) { sm.syms[fill * 32 + lane] = (uint8_t)(2 * i + k); ++fill; }
         }
     }
     return true;
@@ -124,18 +143,26 @@ __device__ __forceinline__ uint32_t xh_decode_symbol(XhLane& L, const XhWarpSmem
     const int r = L.bits;
     const uint32_t x = (r < 15) ? (r == 0 ? 0u : ((L.mask >> (32 - r)) << (15 - r))) : (L.mask >> 17);
     // n = 1 + #{k : x >= lims[k]}: the limits are non-decreasing, so a 4-level binary search over registers finds it
-    // with 4 compares and 11 selects (lims[15] is the whole code space: never reached)
+    // with 4 compares and a few selects (lims[15] is the whole code space: never reached)
     const bool c8 = x >= L.lims[8];
     const bool c4 = x >= (c8 ? L.lims[12] : L.lims[4]);
     const bool c2 = x >= (c8 ? (c4 ? L.lims[14] : L.lims[10]) : (c4 ? L.lims[6] : L.lims[2]));
     const uint32_t l1 = c8 ? (c4 ? (c2 ? 0x8000u : L.lims[13]) : (c2 ? L.lims[11] : L.lims[9]))
                            : (c4 ? (c2 ? L.lims[7] : L.lims[5]) : (c2 ? L.lims[3] : L.lims[1]));
-    const int n = 1 + (c8 ? 8 : 0) + (c4 ? 4 : 0) + (c2 ? 2 : 0) + (x >= l1 ? 1 : 0);
+    const bool c1 = x >= l1;
+    const int n = 1 + (c8 ? 8 : 0) + (c4 ? 4 : 0) + (c2 ? 2 : 0) + (c1 ? 1 : 0);
     if (n > r) return 0xFFFFu;
-    const uint32_t rank = (uint32_t)((int)sm.base[n * 32 + lane] + (int)(x >> (15 - n)));
+    // the same predicates select base[n] and litend[n] out of their packed registers
+    const uint32_t bp = c8 ? (c4 ? (c2 ? L.baseP[7] : L.baseP[6]) : (c2 ? L.baseP[5] : L.baseP[4]))
+                           : (c4 ? (c2 ? L.baseP[3] : L.baseP[2]) : (c2 ? L.baseP[1] : L.baseP[0]));
+    const uint32_t ep = c8 ? (c4 ? (c2 ? L.litendP[7] : L.litendP[6]) : (c2 ? L.litendP[5] : L.litendP[4]))
+                           : (c4 ? (c2 ? L.litendP[3] : L.litendP[2]) : (c2 ? L.litendP[1] : L.litendP[0]));
+    const int base = (int)(int16_t)(uint16_t)(c1 ? (bp >> 16) : bp);
+    const uint32_t litend = c1 ? (ep >> 16) : (ep & 0xFFFFu);
+    const uint32_t rank = (uint32_t)(base + (int)(x >> (15 - n)));
     xh_skip(L, n);
     if (rank >= L.nused) return 0xFFFFu;                         // unassigned part of an incomplete code (:44, :102)
-    return (uint32_t)sm.syms[rank * 32 + lane] | (rank >= (uint32_t)sm.litend[n * 32 + lane] ? 256u : 0u);
+    return (uint32_t)sm.syms[rank * 32 + lane] | (rank >= litend ? 256u : 0u);
 }
 
 // One symbol of this lane's stream (xpress_huff_decompress :143-159 around xpress_huff_decompress_chunk :39-135).
@@ -213,6 +240,8 @@ __device__ __forceinline__ void xhuff_decode_body(const uint8_t* __restrict__ in
         L.mask = 0; L.bits = 0; L.chunk_end = 0; L.need_table = true;
 #pragma unroll
         for (int k = 0; k < 15; ++k) L.lims[k] = 0x8000u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { L.baseP[k] = 0; L.litendP[k] = 0; }
         Sink O;
         if (i < count) {
             L.in = in + in_off[i]; L.in_len = in_len[i]; L.cap = out_cap[i];

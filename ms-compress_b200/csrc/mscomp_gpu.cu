@@ -219,7 +219,10 @@ MSCompStatus mscomp_gpu_xpress_huff_decompress_batch(mscomp_gpu_ctx* ctx, const 
     if (!batch_ok(ctx, d_in, d_out, b)) return MSCOMP_ARG_ERROR;
     if (!b->count) return MSCOMP_OK;
     cudaSetDevice(ctx->device);
-    const uint32_t groups = (b->count + 31) / 32, cap = (uint32_t)ctx->sm_count * 11;     // 11 resident warps per SM (19 KB each)
+    MSC_OPT_IN_SMEM(xhuff_parse_kernel, XHD_SMEM_BYTES);
+    MSC_OPT_IN_SMEM(xhuff_decode_kernel, XHD_SMEM_BYTES);
+    // 7 warps x 16 KB per block, two blocks per SM
+    const uint32_t groups = (b->count + 32 * XHD_WARPS_PER_BLOCK - 1) / (32 * XHD_WARPS_PER_BLOCK), cap = (uint32_t)ctx->sm_count * 2;
     uint32_t* tok = b->count >= 64 ? token_scratch(ctx, b) : nullptr;
     uint32_t* ntok = tok ? (uint32_t*)ctx->get(SC_AUX1, ((size_t)b->count + 1) * sizeof(uint32_t)) : nullptr;
     if (tok && ntok) {
