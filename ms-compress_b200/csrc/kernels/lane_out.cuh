@@ -100,6 +100,10 @@ struct LaneOut {
             for (; len; --len, ++src) put_byte(get_byte(src));
         }
     }
+    __device__ __forceinline__ void emit(bool is_match, uint32_t lit, uint32_t off, uint32_t len)
+    {
+        if (is_match) copy_match(off, len); else put_byte(lit);
+    }
     // write out the pending piece and the bytes of the unfinished word
     __device__ __forceinline__ void finish()
     {

@@ -37,6 +37,13 @@ struct LaneTok {
             len -= l;
         }
     }
+    // one item, branch-free in the common case (a match of at most LZQ_MAXLEN bytes, or a literal)
+    __device__ __forceinline__ void emit(bool is_match, uint32_t lit, uint32_t off, uint32_t len)
+    {
+        if (is_match && len > LZQ_MAXLEN) { copy_match(off, len); return; }
+        tok[ntok++] = is_match ? lzt_match(off, len) : lzt_lit(lit);
+        opos += len;
+    }
     __device__ __forceinline__ void finish() {}
 };
 

@@ -188,35 +188,33 @@ __device__ __forceinline__ void xh_step(XhLane& L, XhWarpSmem& sm, int lane, Sin
     const uint32_t sym = xh_decode_symbol(L, sm, lane);
     if (sym == 0xFFFFu) { L.status = ST_DATA; return; }
     if (sym == (uint32_t)XH_EOS && L.in_len - L.ip == 0 && xh_mask_is_zero(L)) { L.status = 1; return; }   // :83
-    if (sym < 256) {
-        if (O.opos == L.cap) { L.status = ST_BUF; return; }
-        O.put_byte(sym);
-    } else {
-        uint32_t len = sym & 15;
-        if (len == 15) {
-            if (L.in_len - L.ip < 1) { L.status = ST_DATA; return; }
-            len = xh_rd16(L, L.ip) & 0xFF; L.ip += 1;
-            if (len == 0xFF) {
-                if (L.in_len - L.ip < 2) { L.status = ST_DATA; return; }
-                len = xh_rd16(L, L.ip); L.ip += 2;
-                if (len == 0) {
-                    if (L.in_len - L.ip < 4) { L.status = ST_DATA; return; }
-                    len = xh_rd32(L, L.ip); L.ip += 4;
-                }
-                if (len < 15) { L.status = ST_DATA; return; }
-                len -= 15;
+    // Literals and matches share one instruction stream (a literal is handled as a "match" with 0 offset bits whose
+    // length/offset are ignored), so the lanes of the warp only part ways for the rare long-length escape codes.
+    const bool is_match = sym >= 256;
+    uint32_t len = sym & 15;
+    if (is_match && len == 15) {                                // :57-66 length escapes: byte, then u16, then u32
+        if (L.in_len - L.ip < 1) { L.status = ST_DATA; return; }
+        len = xh_rd16(L, L.ip) & 0xFF; L.ip += 1;
+        if (len == 0xFF) {
+            if (L.in_len - L.ip < 2) { L.status = ST_DATA; return; }
+            len = xh_rd16(L, L.ip); L.ip += 2;
+            if (len == 0) {
+                if (L.in_len - L.ip < 4) { L.status = ST_DATA; return; }
+                len = xh_rd32(L, L.ip); L.ip += 4;
             }
-            len += 15;
+            if (len < 15) { L.status = ST_DATA; return; }
+            len -= 15;
         }
-        len += 3;
-        const int off_bits = (int)((sym >> 4) & 15);
-        if (off_bits > L.bits) { L.status = ST_DATA; return; }
-        const uint32_t off = xh_peek(L, off_bits) + (1u << off_bits);
-        xh_skip(L, off_bits);
-        if (O.opos < off) { L.status = ST_DATA; return; }            // :113
-        if (L.cap - O.opos < len) { L.status = ST_BUF; return; }     // :114
-        O.copy_match(off, len);
+        len += 15;
     }
+    len = is_match ? len + 3 : 1u;
+    const int off_bits = is_match ? (int)((sym >> 4) & 15) : 0;
+    if (off_bits > L.bits) { L.status = ST_DATA; return; }
+    const uint32_t off = xh_peek(L, off_bits) + (1u << off_bits);
+    if (off_bits) xh_skip(L, off_bits);
+    if (is_match && O.opos < off) { L.status = ST_DATA; return; }        // :113
+    if (L.cap - O.opos < len) { L.status = ST_BUF; return; }             // :114 (and :87 for a literal)
+    O.emit(is_match, sym, off, len);
 }
 
 // Batch decode: buffer i = in[in_off[i] .. +in_len[i]) -> out[out_off[i] .. +out_cap[i]); out_len / status per buffer.
