@@ -15,8 +15,19 @@ struct mscomp_gpu_ctx {
     uint64_t launches = 0;
     void* scratch[SC_COUNT] = {};
     size_t scratch_cap[SC_COUNT] = {};
+    cudaStream_t copy_stream = nullptr;   // second stream of the host-pointer wrappers: uploads overlap with kernels
+    cudaEvent_t copy_ev[16] = {};
     void* pinned = nullptr;          // small pinned mailbox for results
     size_t pinned_cap = 0;
+
+    // lazily created upload stream + a ring of events
+    bool copy_ready()
+    {
+        if (copy_stream) return true;
+        if (cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); copy_stream = nullptr; return false; }
+        for (int i = 0; i < 16; ++i) cudaEventCreateWithFlags(&copy_ev[i], cudaEventDisableTiming);
+        return true;
+    }
 
     // ---- optional per-kernel profiling ----
     static constexpr int kProfMax = 2048;

@@ -52,14 +52,15 @@ __device__ __forceinline__ uint32_t lz_load4(const uint8_t* s, int idx)
 __device__ __forceinline__ uint32_t lz_hash3(uint32_t x) { return ((x & 0xFFFFFFu) * 0x9E3779B1u) >> 20; }
 
 __global__ void __launch_bounds__(LZE_THREADS)
-lznt1_encode_kernel(const uint8_t* __restrict__ in, uint64_t in_len, uint32_t nchunks,
+lznt1_encode_kernel(const uint8_t* __restrict__ in, uint64_t in_len, uint32_t first, uint32_t nchunks,
                     uint8_t* __restrict__ slots, uint32_t* __restrict__ slot_size)
 {
     MSC_DYN_SMEM(smem_raw);
     Lznt1EncSmem& sm = *reinterpret_cast<Lznt1EncSmem*>(smem_raw);
     const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    for (uint32_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    // chunks [first, first + nchunks) of the stream `in` (a slice, so that uploads can overlap with encoding)
+    for (uint32_t c = first + blockIdx.x; c < first + nchunks; c += gridDim.x) {
         const uint64_t base = (uint64_t)c * LZNT1_CHUNK;
         const int n = (int)((in_len - base < (uint64_t)LZNT1_CHUNK) ? (in_len - base) : LZNT1_CHUNK);
         const uint8_t* src = in + base;

@@ -30,6 +30,16 @@ MSCompStatus msc_compact_slots(mscomp_gpu_ctx* ctx, const uint8_t* d_slots, uint
     return msc_cuda_status(cudaGetLastError(), "compact_slots");
 }
 
+// Encode chunks [first, first+count) of the stream d_in[0..in_len) into their slots (one 256-thread block per chunk).
+MSCompStatus msc_lznt1_encode_chunks(mscomp_gpu_ctx* ctx, const uint8_t* d_in, size_t in_len, uint32_t first, uint32_t count,
+                                     uint8_t* d_slots, uint32_t* d_sizes)
+{
+    const uint32_t grid = count < (uint32_t)ctx->sm_count * 8 ? count : (uint32_t)ctx->sm_count * 8;
+    MSC_OPT_IN_SMEM(lznt1_encode_kernel, sizeof(Lznt1EncSmem));
+    MSC_LAUNCH_SMEM(ctx, lznt1_encode_kernel, grid, LZE_THREADS, sizeof(Lznt1EncSmem), d_in, (uint64_t)in_len, first, count, d_slots, d_sizes);
+    return msc_cuda_status(cudaGetLastError(), "lznt1_encode");
+}
+
 MSCompStatus msc_summarize(mscomp_gpu_ctx* ctx, const uint32_t* d_sizes, const int32_t* d_status, uint32_t n, mscomp_gpu_result* d_res)
 {
     MSC_LAUNCH(ctx, summarize_kernel, 1, SUM_THREADS, d_sizes, d_status, n, 0u, (GpuResult*)d_res);
@@ -66,6 +76,7 @@ void mscomp_gpu_destroy(mscomp_gpu_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < SC_COUNT; ++i) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->copy_stream) { for (int i = 0; i < 16; ++i) cudaEventDestroy(ctx->copy_ev[i]); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -123,11 +134,7 @@ MSCompStatus mscomp_gpu_lznt1_compress(mscomp_gpu_ctx* ctx, const uint8_t* d_in,
     uint32_t* sizes = (uint32_t*)ctx->get(SC_SIZES, ((size_t)nchunks + 1) * sizeof(uint32_t));
     uint64_t* offs = d_chunk_off ? d_chunk_off : (uint64_t*)ctx->get(SC_OFFS, ((size_t)nchunks + 1) * sizeof(uint64_t));
     if (!slots || !sizes || !offs) return MSCOMP_MEM_ERROR;
-    if (nchunks) {
-        const uint32_t grid = nchunks < (uint32_t)ctx->sm_count * 8 ? nchunks : (uint32_t)ctx->sm_count * 8;
-        MSC_OPT_IN_SMEM(lznt1_encode_kernel, sizeof(Lznt1EncSmem));
-        MSC_LAUNCH_SMEM(ctx, lznt1_encode_kernel, grid, LZE_THREADS, sizeof(Lznt1EncSmem), d_in, (uint64_t)in_len, nchunks, slots, sizes);
-    }
+    if (nchunks) msc_lznt1_encode_chunks(ctx, d_in, in_len, 0, nchunks, slots, sizes);
     msc_compact_slots(ctx, slots, LZNT1_SLOT, sizes, nchunks, offs, d_out);
     // result: bytes = offs[nchunks]
     cudaMemsetAsync(d_result, 0, sizeof(mscomp_gpu_result), ctx->stream);
@@ -181,11 +188,13 @@ static uint32_t* token_scratch(mscomp_gpu_ctx* ctx, const mscomp_gpu_batch* b)
     cudaMemcpyAsync(h_ext + 8, d_ext + 8, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return nullptr;
     const uint64_t extent = h_ext[8];
-    size_t free_b = 0, total_b = 0;
-    cudaMemGetInfo(&free_b, &total_b);
     const uint64_t have = ctx->scratch_cap[SC_AUX2];
     if (extent == 0 || extent > (1ull << 36)) return nullptr;
-    if (4 * extent + 64 > have && 4 * extent + 64 > (uint64_t)free_b / 2 + have) return nullptr;   // would not fit comfortably
+    if (4 * extent + 64 > have) {                                     // growing: only if it fits comfortably
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        if (4 * extent + 64 > (uint64_t)free_b / 2 + have) return nullptr;
+    }
     return (uint32_t*)ctx->get(SC_AUX2, 4 * extent + 64);
 }
 

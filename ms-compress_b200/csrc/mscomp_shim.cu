@@ -53,9 +53,33 @@ extern "C" MSCompStatus lznt1_compress(const_bytes in, size_t in_len, bytes out,
     mscomp_gpu_result* d_res = (mscomp_gpu_result*)ctx->get(SC_RESULT, 256);
     mscomp_gpu_result* h_res = (mscomp_gpu_result*)ctx->get_pinned(256);
     if (!d_in || !d_out || !d_res || !h_res) return MSCOMP_MEM_ERROR;
-    if (in_len) cudaMemcpyAsync(d_in, in, in_len, cudaMemcpyHostToDevice, ctx->stream);
-    MSCompStatus st = mscomp_gpu_lznt1_compress(ctx, d_in, in_len, d_out, dcap, nullptr, d_res);
-    if (st != MSCOMP_OK) return st;
+    MSCompStatus st;
+    const size_t kSlice = (size_t)64 << 20;                 // upload / encode granularity (a multiple of the chunk size)
+    if (in_len > kSlice && ctx->copy_ready()) {
+        // chunks are independent: upload slice i+1 on the copy stream while slice i is being encoded
+        uint8_t* d_slots = (uint8_t*)ctx->get(SC_SLOTS, nchunks * MSC_LZNT1_SLOT_BYTES + 16);
+        uint32_t* d_sizes = (uint32_t*)ctx->get(SC_SIZES, (nchunks + 1) * sizeof(uint32_t));
+        uint64_t* d_offs = (uint64_t*)ctx->get(SC_OFFS, (nchunks + 1) * sizeof(uint64_t));
+        if (!d_slots || !d_sizes || !d_offs) return MSCOMP_MEM_ERROR;
+        cudaEventRecord(ctx->copy_ev[15], ctx->stream);                      // earlier work on the scratch buffers
+        cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[15], 0);
+        int k = 0;
+        for (size_t off = 0; off < in_len; off += kSlice, ++k) {
+            const size_t len = in_len - off < kSlice ? in_len - off : kSlice;
+            cudaEvent_t ev = ctx->copy_ev[k % 15];
+            if (k >= 15) cudaEventSynchronize(ev);                            // (ring reuse: that slice was consumed long ago)
+            cudaMemcpyAsync(d_in + off, in + off, len, cudaMemcpyHostToDevice, ctx->copy_stream);
+            cudaEventRecord(ev, ctx->copy_stream);
+            cudaStreamWaitEvent(ctx->stream, ev, 0);
+            if ((st = msc_lznt1_encode_chunks(ctx, d_in, in_len, (uint32_t)(off / 4096), (uint32_t)((len + 4095) / 4096), d_slots, d_sizes)) != MSCOMP_OK) return st;
+        }
+        if ((st = msc_compact_slots(ctx, d_slots, MSC_LZNT1_SLOT_BYTES, d_sizes, (uint32_t)nchunks, d_offs, d_out)) != MSCOMP_OK) return st;
+        cudaMemsetAsync(d_res, 0, sizeof(*d_res), ctx->stream);
+        cudaMemcpyAsync(&d_res->bytes, d_offs + nchunks, sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream);
+    } else {
+        if (in_len) cudaMemcpyAsync(d_in, in, in_len, cudaMemcpyHostToDevice, ctx->stream);
+        if ((st = mscomp_gpu_lznt1_compress(ctx, d_in, in_len, d_out, dcap, nullptr, d_res)) != MSCOMP_OK) return st;
+    }
     cudaMemcpyAsync(h_res, d_res, sizeof(*h_res), cudaMemcpyDeviceToHost, ctx->stream);
     if ((st = msc_cuda_status(cudaStreamSynchronize(ctx->stream), "lznt1_compress")) != MSCOMP_OK) return st;
     const size_t total = (size_t)h_res->bytes;
@@ -103,6 +127,24 @@ extern "C" MSCompStatus lznt1_decompress(const_bytes in, size_t in_len, bytes ou
     if (!out_len || (!in && in_len) || (!out && *out_len)) return MSCOMP_ARG_ERROR;
     const size_t cap = *out_len;
 
+    // The upload of the stream starts first, on the copy stream, so that it overlaps with the header walk below.
+    mscomp_gpu_ctx* ctx = in_len >= 2 ? msc_thread_ctx() : nullptr;
+    if (in_len >= 2 && !ctx) return MSCOMP_MEM_ERROR;
+    uint8_t* d_in = ctx ? (uint8_t*)ctx->get(SC_IN, in_len + 64) : nullptr;
+    if (ctx && !d_in) return MSCOMP_MEM_ERROR;
+    struct CopyGuard {          // the user's buffer must not be in use by a DMA once we return
+        cudaStream_t s = nullptr;
+        ~CopyGuard() { if (s) cudaStreamSynchronize(s); }
+    } guard;
+    const bool early = ctx && in_len > ((size_t)1 << 20) && ctx->copy_ready();
+    if (early) {
+        cudaEventRecord(ctx->copy_ev[15], ctx->stream);                      // earlier work on the scratch buffer
+        cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[15], 0);
+        cudaMemcpyAsync(d_in, in, in_len, cudaMemcpyHostToDevice, ctx->copy_stream);
+        cudaEventRecord(ctx->copy_ev[0], ctx->copy_stream);
+        guard.s = ctx->copy_stream;
+    }
+
     // Header walk: the format stores no chunk index and each header gives only the distance to the next one
     // (src/lznt1_decompress.cpp:127-135), so an unindexed stream is a linked list; it is walked here, on the host,
     // where the stream already is.
@@ -131,17 +173,15 @@ extern "C" MSCompStatus lznt1_decompress(const_bytes in, size_t in_len, bytes ou
         return st;
     }
 
-    mscomp_gpu_ctx* ctx = msc_thread_ctx();
-    if (!ctx) return MSCOMP_MEM_ERROR;
-    uint8_t* d_in = (uint8_t*)ctx->get(SC_IN, in_len + 64);
     uint8_t* d_out = (uint8_t*)ctx->get(SC_OUT, nchunks * 4096 + 64);
     uint64_t* d_offs = (uint64_t*)ctx->get(SC_OFFS, (nchunks + 1) * sizeof(uint64_t));
     uint32_t* d_sizes = (uint32_t*)ctx->get(SC_SIZES, (nchunks + 1) * sizeof(uint32_t));
     int32_t* d_status = (int32_t*)ctx->get(SC_STATUS, (nchunks + 1) * sizeof(int32_t));
     mscomp_gpu_result* d_res = (mscomp_gpu_result*)ctx->get(SC_RESULT, 256);
     mscomp_gpu_result* h_res = (mscomp_gpu_result*)ctx->get_pinned(256);
-    if (!d_in || !d_out || !d_offs || !d_sizes || !d_status || !d_res || !h_res) return MSCOMP_MEM_ERROR;
-    cudaMemcpyAsync(d_in, in, ip, cudaMemcpyHostToDevice, ctx->stream);
+    if (!d_out || !d_offs || !d_sizes || !d_status || !d_res || !h_res) return MSCOMP_MEM_ERROR;
+    if (early) cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[0], 0);
+    else cudaMemcpyAsync(d_in, in, ip, cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(d_offs, offs.data(), nchunks * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
     MSCompStatus st = mscomp_gpu_lznt1_decompress(ctx, d_in, ip, d_offs, (uint32_t)nchunks, d_out, d_sizes, d_status, d_res);
     if (st != MSCOMP_OK) return st;

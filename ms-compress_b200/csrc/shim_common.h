@@ -13,6 +13,11 @@ mscomp_gpu_ctx* msc_thread_ctx();
 MSCompStatus msc_compact_slots(mscomp_gpu_ctx* ctx, const uint8_t* d_slots, uint64_t stride, const uint32_t* d_sizes,
                                uint32_t n, uint64_t* d_offs, uint8_t* d_dst);
 
+// LZNT1 encoder over a slice of chunks (lets the host wrapper overlap uploads with encoding)
+MSCompStatus msc_lznt1_encode_chunks(mscomp_gpu_ctx* ctx, const uint8_t* d_in, size_t in_len, uint32_t first, uint32_t count,
+                                     uint8_t* d_slots, uint32_t* d_sizes);
+constexpr size_t MSC_LZNT1_SLOT_BYTES = 4112;
+
 // reduce per-unit sizes / statuses into one mscomp_gpu_result (device)
 MSCompStatus msc_summarize(mscomp_gpu_ctx* ctx, const uint32_t* d_sizes, const int32_t* d_status, uint32_t n, mscomp_gpu_result* d_res);
 
