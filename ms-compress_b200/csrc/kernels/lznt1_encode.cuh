@@ -35,6 +35,7 @@ struct Lznt1EncSmem {
     };
     uint16_t sorted[LZNT1_CHUNK];                // positions grouped by hash, ascending inside a group
     uint16_t ord[LZNT1_CHUNK];                   // indices into sorted[], grouped by rank inside their bucket
+    uint16_t hashv[LZNT1_CHUNK];                 // 12-bit hash of the 3 bytes at every indexed position
     uint32_t rankcnt[256];                       // entries per rank (ranks >= 255 share the last bin)
     uint32_t lenoff[LZNT1_CHUNK];                // len | dist << 16 (0 = no match)
     uint32_t M[128], V[128], F[128];             // match bitmap, visited bitmap (by position), flag bits (by item)
@@ -79,7 +80,11 @@ lznt1_encode_kernel(const uint8_t* __restrict__ in, uint64_t in_len, uint32_t fi
 
         // ---- B: counting sort by hash ------------------------------------------------------------------
         const int npos = n - 2;                      // positions 0..n-3 are indexed (Fill :99)
-        for (int p = tid; p < npos; p += LZE_THREADS) atomicAdd(&sm.cnt[lz_hash3(lz_load4(sm.in, p))], 1u);
+        for (int p = tid; p < npos; p += LZE_THREADS) {
+            const uint32_t h = lz_hash3(lz_load4(sm.in, p));
+            sm.hashv[p] = (uint16_t)h;
+            atomicAdd(&sm.cnt[h], 1u);
+        }
         __syncthreads();
         {   // inclusive scan of 4096 counts (16 per thread + block scan of the 256 partial sums): cnt[h] = END of bucket h
             uint32_t loc[16], sum = 0;
@@ -109,7 +114,7 @@ lznt1_encode_kernel(const uint8_t* __restrict__ in, uint64_t in_len, uint32_t fi
                     const int e = tid * 16 + i;
                     if (e < npos) {
                         const int p = pass ? (int)srcA[e] : e;
-                        cntT[((lz_hash3(lz_load4(sm.in, p)) >> sh) & 15) * LZE_THREADS + tid] += 1;
+                        cntT[(((uint32_t)sm.hashv[p] >> sh) & 15) * LZE_THREADS + tid] += 1;
                     }
                 }
                 __syncthreads();
@@ -131,7 +136,7 @@ lznt1_encode_kernel(const uint8_t* __restrict__ in, uint64_t in_len, uint32_t fi
                     const int e = tid * 16 + i;
                     if (e < npos) {
                         const int p = pass ? (int)srcA[e] : e;
-                        const int c = ((lz_hash3(lz_load4(sm.in, p)) >> sh) & 15) * LZE_THREADS + tid;
+                        const int c = (((uint32_t)sm.hashv[p] >> sh) & 15) * LZE_THREADS + tid;
                         const uint32_t slot = cntT[c];
                         cntT[c] = (uint16_t)(slot + 1);
                         dstA[slot] = (uint16_t)p;
@@ -150,7 +155,7 @@ lznt1_encode_kernel(const uint8_t* __restrict__ in, uint64_t in_len, uint32_t fi
         sm.rankcnt[tid] = 0;
         __syncthreads();
         for (int idx = tid; idx < npos; idx += LZE_THREADS) {
-            const uint32_t h = lz_hash3(lz_load4(sm.in, sm.sorted[idx]));
+            const uint32_t h = sm.hashv[sm.sorted[idx]];
             const int r = idx - (int)(h ? sm.cnt[h - 1] : 0);
             atomicAdd(&sm.rankcnt[r < 255 ? r : 255], 1u);
         }
@@ -166,7 +171,7 @@ lznt1_encode_kernel(const uint8_t* __restrict__ in, uint64_t in_len, uint32_t fi
         }
         __syncthreads();
         for (int idx = tid; idx < npos; idx += LZE_THREADS) {
-            const uint32_t h = lz_hash3(lz_load4(sm.in, sm.sorted[idx]));
+            const uint32_t h = sm.hashv[sm.sorted[idx]];
             const int r = idx - (int)(h ? sm.cnt[h - 1] : 0);
             sm.ord[atomicAdd(&sm.rankcnt[r < 255 ? r : 255], 1u)] = (uint16_t)idx;
         }
@@ -180,7 +185,7 @@ lznt1_encode_kernel(const uint8_t* __restrict__ in, uint64_t in_len, uint32_t fi
                 lznt1_shift_limit(p, S, lim);
                 const int max_len = min(n - p, (1 << S) + 2);       // mask3 (src/lznt1_compress.cpp:51,:66)
                 const uint32_t key = lz_load4(sm.in, p);
-                const uint32_t h = lz_hash3(key);
+                const uint32_t h = sm.hashv[p];
                 int k = (h == 0) ? 0 : (int)sm.cnt[h - 1];
                 int best = 0, bj = 0;
                 for (; k < idx; ++k) {                              // earlier entries of my bucket = earlier positions
