@@ -239,6 +239,7 @@ def run_gpu(args):
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = os.environ.get("MSCOMP_NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
