@@ -190,13 +190,15 @@ lznt1_encode_kernel(const uint8_t* __restrict__ in, uint64_t in_len, uint32_t fi
                 int best = 0, bj = 0;
                 for (; k < idx; ++k) {                              // earlier entries of my bucket = earlier positions
                     const int j = sm.sorted[k];
-                    if ((lz_load4(sm.in, j) ^ key) & 0xFFFFFFu) continue;
+                    // common prefix of p and j, 4 bytes at a time; a hash collision simply ends with i < 3
                     int i = 0;
-                    while (i < max_len) {
-                        const uint32_t d = lz_load4(sm.in, p + i) ^ lz_load4(sm.in, j + i);
-                        if (d) { i += (__ffs((int)d) - 1) >> 3; break; }
+                    uint32_t d = lz_load4(sm.in, j) ^ key;
+                    while (!d) {
                         i += 4;
+                        if (i >= max_len) break;
+                        d = lz_load4(sm.in, p + i) ^ lz_load4(sm.in, j + i);
                     }
+                    if (d) i += (__ffs((int)d) - 1) >> 3;
                     if (i > max_len) i = max_len;
                     if (i > best) { best = i; bj = j; if (best == max_len) break; }
                 }

@@ -15,7 +15,7 @@ rows = list(csv.reader(out.splitlines()))
 lines = []
 fname, hdr = "?", None
 for r in rows:
-    if len(r) >= 2 and r[0] == "File Name":
+    if len(r) >= 2 and r[0] in ("File Name", "File Path"):
         fname = os.path.basename(r[1])
         continue
     if r and r[0] == "Line No":
