@@ -152,10 +152,12 @@ MSCompStatus mscomp_gpu_lznt1_decompress(mscomp_gpu_ctx* ctx, const uint8_t* d_i
     int32_t* status = d_chunk_status ? d_chunk_status : (int32_t*)ctx->get(SC_STATUS, ((size_t)nchunks + 1) * sizeof(int32_t));
     if (!sizes || !status) return MSCOMP_MEM_ERROR;
     if (nchunks) {
-        // Two mappings of the same decoder: a lane per chunk when the batch has enough chunks to fill the GPU's lanes
-        // (far fewer instructions per chunk), a warp per chunk otherwise.  MSCOMP_LZNT1_DECODE=warp|lanes overrides.
+        // Two mappings of the same decoder.  Default: a warp per chunk with the chunk staged in shared memory -- its DRAM
+        // traffic equals the algorithmic bytes (profiles/traffic.json).  MSCOMP_LZNT1_DECODE=lanes selects the
+        // lane-per-chunk variant: same speed on B200 but every lane's 4 KiB window lives in L2/HBM, and with ~300k
+        // chunks in flight the match reads miss L2 (20x read amplification measured), so it is not the default.
         static const char* mode = getenv("MSCOMP_LZNT1_DECODE");
-        const bool lanes = mode ? (strcmp(mode, "lanes") == 0) : (nchunks >= (uint32_t)ctx->sm_count * 256);
+        const bool lanes = mode && strcmp(mode, "lanes") == 0;
         if (lanes) {
             const uint32_t tpb = 32 * LZL_WARPS_PER_BLOCK;
             const uint32_t blocks = (nchunks + tpb - 1) / tpb, cap = (uint32_t)ctx->sm_count * 16;
