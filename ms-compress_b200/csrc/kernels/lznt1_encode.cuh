@@ -9,11 +9,15 @@
 // Key fact: Find(p) is a pure function of (chunk, p), so it is evaluated for ALL positions in
 // parallel; only the greedy walk p += max(1, len[p]) is serial, and it touches one word per match.
 //
-// Stages (all in shared memory):
+// Stages (all in shared memory, 50 KB per block -> 4 blocks per SM):
 //   A  stage the chunk, zero padded
-//   B  stable radix sort of positions by a 12-bit hash of their first 3 bytes (ascending inside a bucket)
-//   C  all-position match search -> lenoff[p] = len | dist << 16, match bitmap M
-//   D  greedy parse: one thread walks M with find-first-set and records the visited bitmap V
+//   B  12-bit hash of the 3 bytes at every position; histogram -> bucket begin offsets; ONE warp then places the
+//      positions in position order, 32 per round (__match_any_sync gives the rank among equal hashes of the round), so
+//      buckets come out ascending by position -- a stable counting sort without per-thread counter columns
+//   C  all-position match search -> lenoff[p] = len | dist << 16, match bitmap M; entries are handed to threads
+//      grouped by their rank inside the bucket (= number of candidates), rank-0 entries are skipped
+//   D  greedy parse: successor links between match positions, doubled twice, one thread chases every 4th visited
+//      match, the rest is filled in parallel; visited bitmap V by ballot
 //   E  every visited position computes its item index k and the number of matches before it from prefix
 //      popcounts of V and V&M:  byte offset = k + (k >> 3) + 1 + matches_before;  flag bits by atomicOr
 //   F  header + payload to the chunk's slot (compaction to a contiguous stream is a separate kernel)
@@ -26,23 +30,30 @@ namespace msc {
 constexpr int LZE_THREADS = 256;
 constexpr int LZE_BUCKETS = 4096;
 constexpr int LZNT1_SLOT = 4112;                 // 2-byte header + <= 4096 payload, rounded up to 16
+// A chunk whose all-position search would cost more than LZE_HEAVY_WORK candidate evaluations (long runs, tiny alphabets:
+// huge buckets) is "heavy": entries of rank >= LZE_LAZY_RANK are then searched only if the greedy parse visits them
+// (as the reference does for every position, src/lznt1_compress.cpp:62-70), by a whole warp per visited position.
+constexpr uint32_t LZE_HEAVY_WORK = 32768;
+constexpr int LZE_LAZY_RANK = 16;
 
 struct Lznt1EncSmem {
     __align__(16) uint8_t in[LZNT1_CHUNK + 16];  // zero padded
     union {
-        uint32_t cnt[LZE_BUCKETS];               // B,C: bucket counts -> end offsets
-        uint8_t out[LZNT1_SLOT];                 // E,F: assembled chunk (aliases cnt, which is dead by then)
+        __align__(16) uint16_t cnt[LZE_BUCKETS]; // B,C: bucket cursors: begin offsets -> (after placement) end offsets
+        uint16_t nxt4[LZNT1_CHUNK];              // D: successor link doubled twice
+        uint8_t out[LZNT1_SLOT];                 // E,F: assembled chunk
     };
-    uint16_t sorted[LZNT1_CHUNK];                // positions grouped by hash, ascending inside a group
-    uint16_t ord[LZNT1_CHUNK];                   // indices into sorted[], grouped by rank inside their bucket
-    uint16_t hashv[LZNT1_CHUNK];                 // 12-bit hash of the 3 bytes at every indexed position
+    __align__(16) uint16_t sorted[LZNT1_CHUNK];  // B,C: positions grouped by hash, ascending inside a group; D: nxt
+    __align__(16) uint16_t ord[LZNT1_CHUNK];     // C: indices into sorted[], grouped by rank inside their bucket; D: nxt2
+    __align__(16) uint32_t lenoff[LZNT1_CHUNK];  // C..E: len | dist << 16 (0 = no match); B: its first half holds the hashes
     uint32_t rankcnt[256];                       // entries per rank (ranks >= 255 share the last bin)
-    uint32_t lenoff[LZNT1_CHUNK];                // len | dist << 16 (0 = no match)
-    uint32_t M[128], V[128], F[128];             // match bitmap, visited bitmap (by position), flag bits (by item)
+    uint32_t M[132], V[128], F[128], K[128];     // match bitmap (+ zero sentinel), visited bitmap, flag bits (by item), visited matches
+    uint32_t U[128];                             // heavy chunks: positions whose search is deferred to the parse
+    uint16_t nmw[132], pmw[128];                 // next non-zero word of M at or after w; previous non-zero word of K before w
     uint16_t prefV[128], prefVM[128];
     uint16_t goff[LZNT1_CHUNK / 8 + 8];          // byte offset of each group's flag byte
     uint16_t chain[LZNT1_CHUNK / 12 + 8];        // every 4th visited match of the greedy parse
-    uint32_t nchain, scan_tmp[8];
+    uint32_t nchain, scan_tmp[8], work_tmp[8];
 };
 
 __device__ __forceinline__ uint32_t lz_load4(const uint8_t* s, int idx)
@@ -52,13 +63,14 @@ __device__ __forceinline__ uint32_t lz_load4(const uint8_t* s, int idx)
 }
 __device__ __forceinline__ uint32_t lz_hash3(uint32_t x) { return ((x & 0xFFFFFFu) * 0x9E3779B1u) >> 20; }
 
-__global__ void __launch_bounds__(LZE_THREADS)
+__global__ void __launch_bounds__(LZE_THREADS, 4)
 lznt1_encode_kernel(const uint8_t* __restrict__ in, uint64_t in_len, uint32_t first, uint32_t nchunks,
-                    uint8_t* __restrict__ slots, uint32_t* __restrict__ slot_size)
+                    uint8_t* __restrict__ slots, uint32_t* __restrict__ slot_size, uint32_t heavy_work)
 {
     MSC_DYN_SMEM(smem_raw);
     Lznt1EncSmem& sm = *reinterpret_cast<Lznt1EncSmem*>(smem_raw);
     const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint16_t* hashv = reinterpret_cast<uint16_t*>(sm.lenoff);           // live in B and in the rank pass of C only
 
     // chunks [first, first + nchunks) of the stream `in` (a slice, so that uploads can overlap with encoding)
     for (uint32_t c = first + blockIdx.x; c < first + nchunks; c += gridDim.x) {
@@ -74,143 +86,166 @@ lznt1_encode_kernel(const uint8_t* __restrict__ in, uint64_t in_len, uint32_t fi
             for (int i = tid; i < LZNT1_CHUNK; i += LZE_THREADS) sm.in[i] = (i < n) ? src[i] : 0;
         }
         if (tid < 16) sm.in[LZNT1_CHUNK + tid] = 0;
-        for (int i = tid; i < LZE_BUCKETS; i += LZE_THREADS) sm.cnt[i] = 0;
-        if (tid < 128) { sm.V[tid] = 0; sm.F[tid] = 0; }
+        reinterpret_cast<uint4*>(sm.cnt)[tid] = make_uint4(0, 0, 0, 0);
+        reinterpret_cast<uint4*>(sm.cnt)[tid + LZE_THREADS] = make_uint4(0, 0, 0, 0);
+        if (tid < 128) { sm.F[tid] = 0; sm.K[tid] = 0; sm.U[tid] = 0; }
+        sm.rankcnt[tid] = 0;
         __syncthreads();
 
         // ---- B: counting sort by hash ------------------------------------------------------------------
         const int npos = n - 2;                      // positions 0..n-3 are indexed (Fill :99)
-        for (int p = tid; p < npos; p += LZE_THREADS) {
-            const uint32_t h = lz_hash3(lz_load4(sm.in, p));
-            sm.hashv[p] = (uint16_t)h;
-            atomicAdd(&sm.cnt[h], 1u);
-        }
-        __syncthreads();
-        {   // inclusive scan of 4096 counts (16 per thread + block scan of the 256 partial sums): cnt[h] = END of bucket h
-            uint32_t loc[16], sum = 0;
+        {
+            uint32_t* cntw = reinterpret_cast<uint32_t*>(sm.cnt);     // two 16-bit counters per word (counts <= 4094)
+            for (int p = tid; p < npos; p += LZE_THREADS) {
+                const uint32_t h = lz_hash3(lz_load4(sm.in, p));
+                hashv[p] = (uint16_t)h;
+                atomicAdd(&cntw[h >> 1], 1u << (16 * (h & 1)));
+            }
+            __syncthreads();
+            // exclusive scan of the 4096 counts (16 per thread + block scan of the 256 partial sums): cnt[h] = BEGIN of bucket h
+            uint4 q0 = reinterpret_cast<const uint4*>(sm.cnt)[2 * tid], q1 = reinterpret_cast<const uint4*>(sm.cnt)[2 * tid + 1];
+            uint32_t wv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+            uint32_t sum = 0;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) { loc[i] = sm.cnt[tid * 16 + i]; sum += loc[i]; }
-            int incl = warp_incl_scan((int)sum);
+            for (int i = 0; i < 8; ++i) sum += (wv[i] & 0xFFFFu) + (wv[i] >> 16);
+            const int incl = warp_incl_scan((int)sum);
             if (lane == 31) sm.scan_tmp[warp] = (uint32_t)incl;
             __syncthreads();
             uint32_t woff = 0;
             for (int w = 0; w < warp; ++w) woff += sm.scan_tmp[w];
             uint32_t run = woff + (uint32_t)incl - sum;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) { run += loc[i]; sm.cnt[tid * 16 + i] = run; }
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t lo = run; run += wv[i] & 0xFFFFu;
+                const uint32_t hi = run; run += wv[i] >> 16;
+                wv[i] = lo | (hi << 16);
+            }
+            reinterpret_cast<uint4*>(sm.cnt)[2 * tid] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+            reinterpret_cast<uint4*>(sm.cnt)[2 * tid + 1] = make_uint4(wv[4], wv[5], wv[6], wv[7]);
         }
-        // Stable LSD radix sort of the positions by their 12-bit hash (3 passes of 4 bits): every thread owns 16
-        // consecutive elements and a private column of 16 digit counters, so ranks need no atomics and equal keys
-        // keep their order -- positions stay ascending inside a bucket, which the early exit of the search relies on.
-        {
-            uint16_t* cntT = reinterpret_cast<uint16_t*>(sm.lenoff);          // [16 digits][256 threads], lenoff is not live yet
-            const uint16_t* srcA = sm.ord;                                    // pass 0 reads the identity instead
-            uint16_t* dstA = sm.sorted;
-            for (int pass = 0; pass < 3; ++pass) {
-                const int sh = 4 * pass;
+        __syncthreads();
+        // Placement in position order by one warp: a round takes 32 consecutive positions; lanes with equal hashes find
+        // each other with __match_any_sync, the first of them advances the bucket cursor by the size of the group with
+        // one shared-memory atomic and hands the old value to the others.  Rounds are ordered (__syncwarp between their
+        // cursor updates), lanes are ordered inside a round, so buckets come out ascending by
+        // position -- which the early exit and the tie rule of the search rely on.  Four rounds are in flight at a time
+        // (nothing but the cursors links them).  The other warps wait at the barrier; other blocks of the SM fill the
+        // issue slots meanwhile.
+        if (warp == 0) {
+            uint32_t* cntw = reinterpret_cast<uint32_t*>(sm.cnt);
+            const int rounds = (npos + 31) >> 5;
+            for (int k = 0; k < rounds; k += 4) {
+                uint32_t h[4], got[4];
+                unsigned peers[4];
 #pragma unroll
-                for (int d = 0; d < 16; ++d) cntT[d * LZE_THREADS + tid] = 0;
-                for (int i = 0; i < 16; ++i) {
-                    const int e = tid * 16 + i;
-                    if (e < npos) {
-                        const int p = pass ? (int)srcA[e] : e;
-                        cntT[(((uint32_t)sm.hashv[p] >> sh) & 15) * LZE_THREADS + tid] += 1;
-                    }
-                }
-                __syncthreads();
-                {   // exclusive scan of the 4096 counters in (digit, thread) order
-                    uint32_t loc[16], sum = 0;
+                for (int u = 0; u < 4; ++u) { const int p = 32 * (k + u) + lane; h[u] = p < npos ? (uint32_t)hashv[p] : 0xFFFFu; }
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) { loc[i] = cntT[tid * 16 + i]; sum += loc[i]; }
-                    const int incl = warp_incl_scan((int)sum);
-                    if (lane == 31) sm.scan_tmp[warp] = (uint32_t)incl;
-                    __syncthreads();
-                    uint32_t woff = 0;
-                    for (int w = 0; w < warp; ++w) woff += sm.scan_tmp[w];
-                    uint32_t run = woff + (uint32_t)incl - sum;
+                for (int u = 0; u < 4; ++u) peers[u] = __match_any_sync(FULL, h[u]);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) { cntT[tid * 16 + i] = (uint16_t)run; run += loc[i]; }
+                for (int u = 0; u < 4; ++u) {
+                    got[u] = 0;
+                    if (h[u] != 0xFFFFu && (peers[u] & ((1u << lane) - 1)) == 0)
+                        got[u] = atomicAdd(&cntw[h[u] >> 1], (uint32_t)__popc(peers[u]) << (16 * (h[u] & 1)));
+                    __syncwarp();                                    // cursor updates of round u before those of round u+1
                 }
-                __syncthreads();
-                for (int i = 0; i < 16; ++i) {
-                    const int e = tid * 16 + i;
-                    if (e < npos) {
-                        const int p = pass ? (int)srcA[e] : e;
-                        const int c = (((uint32_t)sm.hashv[p] >> sh) & 15) * LZE_THREADS + tid;
-                        const uint32_t slot = cntT[c];
-                        cntT[c] = (uint16_t)(slot + 1);
-                        dstA[slot] = (uint16_t)p;
-                    }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t base = (__shfl_sync(FULL, got[u], __ffs((int)peers[u]) - 1) >> (16 * (h[u] & 1))) & 0xFFFFu;
+                    if (h[u] != 0xFFFFu) sm.sorted[base + (uint32_t)__popc(peers[u] & ((1u << lane) - 1))] = (uint16_t)(32 * (k + u) + lane);
                 }
-                __syncthreads();
-                const uint16_t* t2 = dstA; dstA = const_cast<uint16_t*>(srcA); srcA = t2;     // sorted -> ord -> sorted
             }
         }
-        // cnt[h] = end offset of bucket h; begin = cnt[h-1] (0 for h == 0); sorted[] holds the result of pass 2
+        __syncthreads();
+        // cnt[h] = end offset of bucket h; begin = cnt[h-1] (0 for h == 0)
 
         // ---- C: match search for every position ------------------------------------------------------
         // The k-th entry of a bucket has k candidates (the earlier entries).  Threads take the entries grouped by that
         // rank, so the lanes of a warp run the candidate loop the same number of times.
-        for (int p = (npos > 0 ? npos : 0) + tid; p < LZNT1_CHUNK; p += LZE_THREADS) sm.lenoff[p] = 0;   // not indexed: no match
-        sm.rankcnt[tid] = 0;
-        __syncthreads();
-        for (int idx = tid; idx < npos; idx += LZE_THREADS) {
-            const uint32_t h = sm.hashv[sm.sorted[idx]];
-            const int r = idx - (int)(h ? sm.cnt[h - 1] : 0);
-            atomicAdd(&sm.rankcnt[r < 255 ? r : 255], 1u);
-        }
-        __syncthreads();
-        {   // exclusive scan of the 256 rank counts (one per thread)
-            const uint32_t v = sm.rankcnt[tid];
-            const int incl = warp_incl_scan((int)v);
-            if (lane == 31) sm.scan_tmp[warp] = (uint32_t)incl;
+        bool heavy;                                                  // block-uniform
+        {
+            uint32_t rr[4] = {0, 0, 0, 0};                           // ranks of my 16 entries, one byte each
+            heavy = false;
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                const int idx = tid + LZE_THREADS * m;
+                if (idx < npos) {
+                    const uint32_t h = hashv[sm.sorted[idx]];
+                    int r = idx - (int)(h ? sm.cnt[h - 1] : 0);
+                    r = r < 255 ? r : 255;
+                    rr[m >> 2] |= (uint32_t)r << (8 * (m & 3));
+                    atomicAdd(&sm.rankcnt[r], 1u);
+                }
+            }
             __syncthreads();
-            uint32_t woff = 0;
-            for (int w = 0; w < warp; ++w) woff += sm.scan_tmp[w];
-            sm.rankcnt[tid] = woff + (uint32_t)incl - v;
+            {   // exclusive scan of the 256 rank counts (one per thread); sum of rank * count = candidate evaluations
+                const uint32_t v = sm.rankcnt[tid];
+                const int incl = warp_incl_scan((int)v);
+                const uint32_t wk = __reduce_add_sync(FULL, v * (uint32_t)tid);
+                if (lane == 31) { sm.scan_tmp[warp] = (uint32_t)incl; sm.work_tmp[warp] = wk; }
+                __syncthreads();
+                uint32_t woff = 0, work = 0;
+                for (int w = 0; w < warp; ++w) woff += sm.scan_tmp[w];
+                for (int w = 0; w < LZE_THREADS / 32; ++w) work += sm.work_tmp[w];
+                heavy = work > heavy_work;
+                sm.rankcnt[tid] = woff + (uint32_t)incl - v;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                const int idx = tid + LZE_THREADS * m;
+                if (idx < npos) sm.ord[atomicAdd(&sm.rankcnt[(rr[m >> 2] >> (8 * (m & 3))) & 0xFFu], 1u)] = (uint16_t)idx;
+            }
         }
+        __syncthreads();                                             // hashes are dead from here: lenoff takes their place
+#pragma unroll
+        for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(sm.lenoff)[tid + LZE_THREADS * i] = make_uint4(0, 0, 0, 0);
+        const int rank0_end = (int)sm.rankcnt[0];                    // entries of rank 0 have no candidate: no match
+        const int defer_start = heavy ? (int)sm.rankcnt[LZE_LAZY_RANK - 1] : npos;   // rankcnt[r] = end of rank r by now
         __syncthreads();
-        for (int idx = tid; idx < npos; idx += LZE_THREADS) {
-            const uint32_t h = sm.hashv[sm.sorted[idx]];
-            const int r = idx - (int)(h ? sm.cnt[h - 1] : 0);
-            sm.ord[atomicAdd(&sm.rankcnt[r < 255 ? r : 255], 1u)] = (uint16_t)idx;
-        }
-        __syncthreads();
-        for (int i = tid; i < npos; i += LZE_THREADS) {
+        for (int i = defer_start + tid; i < npos; i += LZE_THREADS) { const int p = sm.sorted[sm.ord[i]]; atomicOr(&sm.U[p >> 5], 1u << (p & 31)); }
+        for (int i = rank0_end + tid; i < defer_start; i += LZE_THREADS) {
             const int idx = sm.ord[i];
             const int p = sm.sorted[idx];
-            uint32_t res = 0;
-            if (p > 0) {
-                int S, lim;
-                lznt1_shift_limit(p, S, lim);
-                const int max_len = min(n - p, (1 << S) + 2);       // mask3 (src/lznt1_compress.cpp:51,:66)
-                const uint32_t key = lz_load4(sm.in, p);
-                const uint32_t h = sm.hashv[p];
-                int k = (h == 0) ? 0 : (int)sm.cnt[h - 1];
-                int best = 0, bj = 0;
-                for (; k < idx; ++k) {                              // earlier entries of my bucket = earlier positions
-                    const int j = sm.sorted[k];
-                    // common prefix of p and j, 4 bytes at a time; a hash collision simply ends with i < 3
-                    int i = 0;
-                    uint32_t d = lz_load4(sm.in, j) ^ key;
+            int S, lim;
+            lznt1_shift_limit(p, S, lim);
+            const int max_len = min(n - p, (1 << S) + 2);           // mask3 (src/lznt1_compress.cpp:51,:66)
+            const uint32_t key = lz_load4(sm.in, p), key2 = lz_load4(sm.in, p + 4);
+            const uint32_t h = lz_hash3(key);
+            int k = (h == 0) ? 0 : (int)sm.cnt[h - 1];
+            int best = 0, bj = 0;
+            int j = sm.sorted[k];
+            uint32_t dj = lz_load4(sm.in, j);
+            for (;;) {                                              // earlier entries of my bucket = earlier positions
+                const int kn = k + 1;
+                int jn = 0;
+                uint32_t djn = 0;
+                if (kn < idx) { jn = sm.sorted[kn]; djn = lz_load4(sm.in, jn); }   // next candidate: loads in flight during the compare
+                // common prefix of p and j, 4 bytes at a time; a hash collision simply ends with i < 3
+                int i2 = 0;
+                uint32_t d = dj ^ key;
+                if (!d) {
+                    i2 = 4;
+                    d = lz_load4(sm.in, j + 4) ^ key2;
                     while (!d) {
-                        i += 4;
-                        if (i >= max_len) break;
-                        d = lz_load4(sm.in, p + i) ^ lz_load4(sm.in, j + i);
+                        i2 += 4;
+                        if (i2 >= max_len) break;
+                        d = lz_load4(sm.in, p + i2) ^ lz_load4(sm.in, j + i2);
                     }
-                    if (d) i += (__ffs((int)d) - 1) >> 3;
-                    if (i > max_len) i = max_len;
-                    if (i > best) { best = i; bj = j; if (best == max_len) break; }
                 }
-                if (best >= 3) res = (uint32_t)best | ((uint32_t)(p - bj) << 16);
+                if (d) i2 += (__ffs((int)d) - 1) >> 3;
+                if (i2 > max_len) i2 = max_len;
+                if (i2 > best) { best = i2; bj = j; if (best == max_len) break; }
+                if (kn >= idx) break;
+                k = kn; j = jn; dj = djn;
             }
-            sm.lenoff[p] = res;
+            if (best >= 3) sm.lenoff[p] = (uint32_t)best | ((uint32_t)(p - bj) << 16);
         }
         __syncthreads();
         for (int p = tid; p < LZNT1_CHUNK; p += LZE_THREADS) {
             const unsigned mm = __ballot_sync(FULL, sm.lenoff[p] != 0);
             if (lane == 0) sm.M[p >> 5] = mm;
         }
+        if (tid == 0) sm.M[128] = 0;
         __syncthreads();
 
         // ---- D: greedy parse p += max(1, len[p]) ------------------------------------------
@@ -218,56 +253,141 @@ lznt1_encode_kernel(const uint8_t* __restrict__ in, uint64_t in_len, uint32_t fi
         // between is literals); nxt is computed for all match positions in parallel, the visited ones are then the
         // chain from the first match -- one shared-memory load per visited match.
         {
-            uint16_t* cur = sm.sorted;                                                        // dead after stage C
-            auto first_match_from = [&](int e) -> int {
-                if (e >= LZNT1_CHUNK) return LZNT1_CHUNK;
-                int w = e >> 5;
-                uint32_t bits = sm.M[w] & (0xffffffffu << (e & 31));
-                while (!bits && ++w < 128) bits = sm.M[w];
-                return bits ? (w * 32 + __ffs((int)bits) - 1) : LZNT1_CHUNK;
-            };
-            auto or_range = [&](int lo, int hi) {                                             // V |= [lo, hi)
-                for (int w = lo >> 5; lo < hi && w <= ((hi - 1) >> 5); ++w) {
-                    const int lo_b = max(lo, w * 32) - w * 32, hi_b = min(hi, w * 32 + 32) - w * 32;
-                    atomicOr(&sm.V[w], (hi_b == 32 ? 0xffffffffu : ((1u << hi_b) - 1)) & (0xffffffffu << lo_b));
+            if (!heavy) {
+                if (warp == 0) {   // nmw[w] = first word >= w of M that is not zero (128 = none)
+                    int nz[4], carry = 128;
+#pragma unroll
+                    for (int i = 3; i >= 0; --i) { const int w = lane * 4 + i; carry = sm.M[w] ? w : carry; nz[i] = carry; }
+                    int v = nz[0];
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_down_sync(FULL, v, d); if (lane + d < 32) v = min(v, t); }
+                    int after = __shfl_down_sync(FULL, v, 1);
+                    if (lane == 31) after = 128;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) sm.nmw[lane * 4 + i] = (uint16_t)(nz[i] == 128 ? after : nz[i]);
+                    if (lane == 0) sm.nmw[128] = 128;
                 }
-            };
-            uint16_t* nxt2 = sm.ord;                                                          // dead after stage C as well
-            uint16_t* nxt4 = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(sm.cnt) + 8192);   // upper half of cnt: dead, clear of `out`
-            for (int p = tid; p < LZNT1_CHUNK; p += LZE_THREADS)
-                cur[p] = (uint16_t)(((sm.M[p >> 5] >> (p & 31)) & 1) ? first_match_from(p + (int)(sm.lenoff[p] & 0xFFFF)) : LZNT1_CHUNK);
-            __syncthreads();                                                                  // F doubles as the mark bitmap
-            if (tid == 32) or_range(0, min(first_match_from(0), n));                          // leading literals
-            // two rounds of pointer doubling shorten the serial part of the chase by 4: nxt2 = nxt o nxt, nxt4 = nxt2 o nxt2
-            for (int p = tid; p < LZNT1_CHUNK; p += LZE_THREADS) { const int t = cur[p]; nxt2[p] = (uint16_t)(t < LZNT1_CHUNK ? cur[t] : LZNT1_CHUNK); }
-            __syncthreads();
-            for (int p = tid; p < LZNT1_CHUNK; p += LZE_THREADS) { const int t = nxt2[p]; nxt4[p] = (uint16_t)(t < LZNT1_CHUNK ? nxt2[t] : LZNT1_CHUNK); }
-            __syncthreads();
-            if (tid == 0) {     // every 4th visited match: one shared-memory load per link
-                int q = first_match_from(0), k = 0;
-                while (q < LZNT1_CHUNK) { sm.chain[k++] = (uint16_t)q; q = nxt4[q]; }
-                sm.nchain = (uint32_t)k;
+                __syncthreads();
+                uint16_t* cur = sm.sorted;                                                        // dead after stage C
+                uint16_t* nxt2 = sm.ord;                                                          // dead after stage C as well
+                auto first_match_from = [&](int e) -> int {
+                    if (e >= LZNT1_CHUNK) return LZNT1_CHUNK;
+                    int w = e >> 5;
+                    uint32_t bits = sm.M[w] & (0xffffffffu << (e & 31));
+                    if (!bits) { w = sm.nmw[w + 1]; bits = sm.M[w]; }                              // M[128] == 0
+                    return bits ? (w * 32 + __ffs((int)bits) - 1) : LZNT1_CHUNK;
+                };
+                for (int p = tid; p < LZNT1_CHUNK; p += LZE_THREADS)
+                    cur[p] = (uint16_t)(((sm.M[p >> 5] >> (p & 31)) & 1) ? first_match_from(p + (int)(sm.lenoff[p] & 0xFFFF)) : LZNT1_CHUNK);
+                __syncthreads();
+                // two rounds of pointer doubling shorten the serial part of the chase by 4: nxt2 = nxt o nxt, nxt4 = nxt2 o nxt2
+                for (int p = tid; p < LZNT1_CHUNK; p += LZE_THREADS) { const int t = cur[p]; nxt2[p] = (uint16_t)(t < LZNT1_CHUNK ? cur[t] : LZNT1_CHUNK); }
+                __syncthreads();
+                for (int p = tid; p < LZNT1_CHUNK; p += LZE_THREADS) { const int t = nxt2[p]; sm.nxt4[p] = (uint16_t)(t < LZNT1_CHUNK ? nxt2[t] : LZNT1_CHUNK); }
+                __syncthreads();
+                if (tid == 0) {     // every 4th visited match: one shared-memory load per link
+                    int q = first_match_from(0), k = 0;
+                    while (q < LZNT1_CHUNK) { sm.chain[k++] = (uint16_t)q; q = sm.nxt4[q]; }
+                    sm.nchain = (uint32_t)k;
+                }
+                __syncthreads();
+                for (uint32_t k = tid; k < sm.nchain; k += LZE_THREADS) {                         // the three in between, in parallel
+                    int q = sm.chain[k];
+                    atomicOr(&sm.K[q >> 5], 1u << (q & 31));
+                    const int q2 = nxt2[q];
+                    q = cur[q];
+                    if (q < LZNT1_CHUNK) atomicOr(&sm.K[q >> 5], 1u << (q & 31));
+                    if (q2 < LZNT1_CHUNK) { atomicOr(&sm.K[q2 >> 5], 1u << (q2 & 31)); const int q3 = cur[q2]; if (q3 < LZNT1_CHUNK) atomicOr(&sm.K[q3 >> 5], 1u << (q3 & 31)); }
+                }
+            } else if (warp == 0) {
+                // Heavy chunk: one warp walks the parse; a deferred position is searched when (and only if) it is reached.
+                int p = 0;
+                while (p < n) {
+                    // first position >= p that has a match or a deferred search (everything before it is a literal)
+                    int q = LZNT1_CHUNK;
+                    for (int w0 = p >> 5; w0 < 128; w0 += 32) {
+                        const int w = w0 + lane;
+                        uint32_t bits = (w < 128) ? (sm.M[w] | sm.U[w]) : 0u;
+                        if (w == (p >> 5)) bits &= 0xffffffffu << (p & 31);
+                        const unsigned nz = __ballot_sync(FULL, bits != 0);
+                        if (nz) {
+                            const int f = __ffs((int)nz) - 1;
+                            q = (w0 + f) * 32 + __ffs((int)__shfl_sync(FULL, bits, f)) - 1;
+                            break;
+                        }
+                    }
+                    if (q >= LZNT1_CHUNK) break;
+                    uint32_t lo = sm.lenoff[q];
+                    if ((sm.U[q >> 5] >> (q & 31)) & 1) {
+                        // Find(q) by the warp: candidates = entries of q's bucket before q, 32 per round, ascending
+                        int S, lim;
+                        lznt1_shift_limit(q, S, lim);
+                        const int max_len = min(n - q, (1 << S) + 2);
+                        const uint32_t key = lz_load4(sm.in, q);
+                        const uint32_t h = lz_hash3(key);
+                        const int kend = (int)sm.cnt[h];
+                        uint32_t bestkey = 0;                               // len << 12 | (4095 - j): longest, then earliest
+                        for (int kb = (h == 0) ? 0 : (int)sm.cnt[h - 1]; kb < kend; kb += 32) {
+                            const int k = kb + lane;
+                            const int j = (k < kend) ? (int)sm.sorted[k] : LZNT1_CHUNK;
+                            const bool valid = j < q;
+                            int i2 = 0;
+                            if (valid) {
+                                uint32_t d = lz_load4(sm.in, j) ^ key;
+                                while (!d) {
+                                    i2 += 4;
+                                    if (i2 >= max_len) break;
+                                    d = lz_load4(sm.in, q + i2) ^ lz_load4(sm.in, j + i2);
+                                }
+                                if (d) i2 += (__ffs((int)d) - 1) >> 3;
+                                if (i2 > max_len) i2 = max_len;
+                                if (i2 >= 3) bestkey = max(bestkey, ((uint32_t)i2 << 12) | (uint32_t)(4095 - j));
+                            }
+                            // ascending candidates: the first round that reaches max_len holds the earliest such candidate
+                            if (__any_sync(FULL, !valid || i2 == max_len)) break;
+                        }
+                        bestkey = __reduce_max_sync(FULL, bestkey);
+                        lo = bestkey ? ((bestkey >> 12) | ((uint32_t)(q - (4095 - (int)(bestkey & 4095u))) << 16)) : 0u;
+                        __syncwarp();
+                        if (lane == 0) {
+                            sm.lenoff[q] = lo;
+                            sm.U[q >> 5] &= ~(1u << (q & 31));
+                            if (lo) sm.M[q >> 5] |= 1u << (q & 31);
+                        }
+                        __syncwarp();
+                    }
+                    if (lo) { if (lane == 0) sm.K[q >> 5] |= 1u << (q & 31); p = q + (int)(lo & 0xFFFF); }
+                    else p = q + 1;
+                }
             }
             __syncthreads();
-            for (uint32_t k = tid; k < sm.nchain; k += LZE_THREADS) {                         // the three in between, in parallel
-                int q = sm.chain[k];
-                atomicOr(&sm.F[q >> 5], 1u << (q & 31));
-                const int q2 = nxt2[q];
-                q = cur[q];
-                if (q < LZNT1_CHUNK) atomicOr(&sm.F[q >> 5], 1u << (q & 31));
-                if (q2 < LZNT1_CHUNK) { atomicOr(&sm.F[q2 >> 5], 1u << (q2 & 31)); const int q3 = cur[q2]; if (q3 < LZNT1_CHUNK) atomicOr(&sm.F[q3 >> 5], 1u << (q3 & 31)); }
+            if (warp == 0) {   // pmw[w] = last word < w of K that is not zero (0xFFFF = none)
+                int pz[4], carry = -1;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { const int w = lane * 4 + i; pz[i] = carry; carry = sm.K[w] ? w : carry; }
+                int v = carry;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULL, v, d); if (lane >= d) v = max(v, t); }
+                int before = __shfl_up_sync(FULL, v, 1);
+                if (lane == 0) before = -1;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) sm.pmw[lane * 4 + i] = (uint16_t)max(pz[i], before);
             }
             __syncthreads();
-            // visited bitmap: every visited match plus the literals up to the next visited match
+            // visited bitmap: a position is visited iff it is a visited match, or it is not covered by the last visited
+            // match at or before it (then it is a literal: there is no match between the end of a visited match and the
+            // next visited match).  A warp handles one bitmap word per iteration, so V needs no atomics.
             for (int p = tid; p < LZNT1_CHUNK; p += LZE_THREADS) {
-                if ((sm.F[p >> 5] >> (p & 31)) & 1) {
-                    const int e = p + (int)(sm.lenoff[p] & 0xFFFF);
-                    or_range(p, p + 1);
-                    or_range(e, min(first_match_from(e), n));
-                }
+                const int w = p >> 5;
+                const uint32_t below = sm.K[w] & (0xffffffffu >> (31 - lane));
+                int q = -1;
+                if (below) q = w * 32 + 31 - __clz((int)below);
+                else { const int w2 = (int)(int16_t)sm.pmw[w]; if (w2 >= 0) q = w2 * 32 + 31 - __clz((int)sm.K[w2]); }
+                bool vis = p < n;
+                if (q >= 0) vis = vis && (p == q || p >= q + (int)(sm.lenoff[q] & 0xFFFF));
+                const unsigned vv = __ballot_sync(FULL, vis);
+                if (lane == 0) sm.V[w] = vv;
             }
-            __syncthreads();
-            if (tid < 128) sm.F[tid] = 0;
         }
         __syncthreads();
 

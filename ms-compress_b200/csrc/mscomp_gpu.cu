@@ -34,9 +34,13 @@ MSCompStatus msc_compact_slots(mscomp_gpu_ctx* ctx, const uint8_t* d_slots, uint
 MSCompStatus msc_lznt1_encode_chunks(mscomp_gpu_ctx* ctx, const uint8_t* d_in, size_t in_len, uint32_t first, uint32_t count,
                                      uint8_t* d_slots, uint32_t* d_sizes)
 {
-    const uint32_t grid = count < (uint32_t)ctx->sm_count * 8 ? count : (uint32_t)ctx->sm_count * 8;
+    // one block per chunk: the hardware block scheduler balances the chunks (their cost varies with the data) better than a
+    // static grid-stride assignment; a block lives ~50 us, so its launch cost does not matter
+    const uint32_t grid = count;
     MSC_OPT_IN_SMEM(lznt1_encode_kernel, sizeof(Lznt1EncSmem));
-    MSC_LAUNCH_SMEM(ctx, lznt1_encode_kernel, grid, LZE_THREADS, sizeof(Lznt1EncSmem), d_in, (uint64_t)in_len, first, count, d_slots, d_sizes);
+    static const char* hw_env = getenv("MSCOMP_LZNT1_HEAVY_WORK");         // tuning / test hook: candidate evaluations above which a chunk is "heavy"
+    const uint32_t heavy_work = hw_env ? (uint32_t)strtoul(hw_env, nullptr, 10) : LZE_HEAVY_WORK;
+    MSC_LAUNCH_SMEM(ctx, lznt1_encode_kernel, grid, LZE_THREADS, sizeof(Lznt1EncSmem), d_in, (uint64_t)in_len, first, count, d_slots, d_sizes, heavy_work);
     return msc_cuda_status(cudaGetLastError(), "lznt1_encode");
 }
 

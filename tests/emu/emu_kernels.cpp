@@ -31,9 +31,9 @@ void emu_lznt1_decode_lanes(const uint8_t* in, uint64_t in_len, const uint64_t* 
 
 // whole-stream LZNT1 compress: encode kernel -> size scan -> gather.  `slots` = nchunks*4112 scratch.
 void emu_lznt1_encode(const uint8_t* in, uint64_t in_len, uint32_t nchunks, uint8_t* slots, uint32_t* slot_size,
-                      uint64_t* offs, uint8_t* out, uint32_t grid)
+                      uint64_t* offs, uint8_t* out, uint32_t grid, uint32_t heavy_work)
 {
-    emu::launch(msc::lznt1_encode_kernel, dim3e(grid), dim3e(msc::LZE_THREADS), in, in_len, 0u, nchunks, slots, slot_size);
+    emu::launch(msc::lznt1_encode_kernel, dim3e(grid), dim3e(msc::LZE_THREADS), in, in_len, 0u, nchunks, slots, slot_size, heavy_work);
     emu::launch(msc::scan_sizes_kernel, dim3e(1), dim3e(msc::SCAN_THREADS), (const uint32_t*)slot_size, nchunks, (uint64_t)0, offs);
     emu::launch(msc::gather_slots_kernel, dim3e(grid), dim3e(256), (const uint8_t*)slots, (uint64_t)msc::LZNT1_SLOT,
                 (const uint32_t*)slot_size, (const uint64_t*)offs, nchunks, out);

@@ -43,7 +43,7 @@ def emu_lznt1_decode(emu, comp, offs=None, grid=3, kernel="emu_lznt1_decode"):
     return st[:nch], sz[:nch], chunks
 
 
-def emu_lznt1_encode(emu, data, grid=3):
+def emu_lznt1_encode(emu, data, grid=3, heavy_work=32768):
     n = len(data)
     nch = (n + 4095) // 4096
     a, addr = padded(data)
@@ -52,7 +52,7 @@ def emu_lznt1_encode(emu, data, grid=3):
     offs = np.zeros(nch + 1, dtype=np.uint64)
     out = np.zeros(n + 2 * nch + 2 * PAD, dtype=np.uint8)
     emu.emu_lznt1_encode(ctypes.c_void_p(addr), ctypes.c_uint64(n), ctypes.c_uint32(nch), P(slots), P(ss), P(offs),
-                         ctypes.c_void_p(out.ctypes.data + 16), ctypes.c_uint32(grid))
+                         ctypes.c_void_p(out.ctypes.data + 16), ctypes.c_uint32(grid), ctypes.c_uint32(heavy_work))
     return out[16:16 + int(offs[nch])].tobytes(), offs
 
 

@@ -22,12 +22,26 @@ def test_decode_matches_oracle(emu, oracle, ms, kind, kernel):
         assert not st.any() and b"".join(chunks) == plain, (kind, n)
 
 
+@pytest.mark.parametrize("heavy_work", [32768, 0], ids=["default", "all-chunks-lazy"])
 @pytest.mark.parametrize("kind", ["text", "runs", "random"])
-def test_encode_is_byte_identical_to_oracle(emu, oracle, ms, kind):
+def test_encode_is_byte_identical_to_oracle(emu, oracle, ms, kind, heavy_work):
+    """heavy_work=0 sends every chunk through the lazy (search-on-visit) parse that heavy chunks take."""
     for n in SIZES:
         plain = ms.generate(kind, n, 42 + n)
-        got, _ = emu_lznt1_encode(emu, plain)
+        got, _ = emu_lznt1_encode(emu, plain, heavy_work=heavy_work)
         assert got == oracle.compress("lznt1", plain), (kind, n)
+
+
+def test_encode_heavy_chunks(emu, oracle):
+    """Tiny alphabets and interleaved runs: huge hash buckets, the default threshold routes them to the lazy parse."""
+    rnd = random.Random(11)
+    cases = [bytes(rnd.choice(b"ACGT") for _ in range(3 * 4096 + 100)),
+             b"".join(bytes([rnd.choice(b"\x00\x00\x00\xff\x01")]) * rnd.randint(1, 40) for _ in range(700)),
+             b"".join((b"\x00" * rnd.randint(3, 300)) + bytes([rnd.randint(1, 255)]) for _ in range(120))]
+    for plain in cases:
+        for hw in (32768, 0, 1 << 30):
+            got, _ = emu_lznt1_encode(emu, plain, heavy_work=hw)
+            assert got == oracle.compress("lznt1", plain)
 
 
 def test_encode_degenerate_inputs(emu, oracle):

@@ -61,6 +61,19 @@ def test_degenerate_inputs(ms, oracle):
         assert ms.raw_call("lznt1_decompress", comp, len(plain)) == (0, plain)
 
 
+def test_heavy_chunks_are_byte_identical(ms, oracle):
+    """Tiny alphabets / interleaved runs: huge hash buckets -> the encoder's lazy (search-on-visit) parse."""
+    rnd = random.Random(11)
+    cases = [bytes(rnd.choice(b"ACGT") for _ in range(64 * 4096 + 100)),
+             b"".join(bytes([rnd.choice(b"\x00\x00\x00\xff\x01")]) * rnd.randint(1, 40) for _ in range(20000)),
+             b"".join((b"\x00" * rnd.randint(3, 300)) + bytes([rnd.randint(1, 255)]) for _ in range(3000)),
+             ms.generate("runs", 1 << 20, 5) + ms.generate("text", 1 << 18, 6)]
+    for plain in cases:
+        comp = oracle.compress("lznt1", plain)
+        assert ms.raw_call("lznt1_compress", plain, MAXSZ["lznt1"](len(plain))) == (0, comp)
+        assert ms.raw_call("lznt1_decompress", comp, len(plain)) == (0, plain)
+
+
 def test_status_codes_match_oracle(ms, oracle):
     """SURVEY.md 8(b) table and bit flips: same status (and bytes on success) as the oracle."""
     rnd = random.Random(11)
