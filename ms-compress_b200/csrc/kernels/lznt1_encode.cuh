@@ -96,10 +96,19 @@ lznt1_encode_kernel(const uint8_t* __restrict__ in, uint64_t in_len, uint32_t fi
         const int npos = n - 2;                      // positions 0..n-3 are indexed (Fill :99)
         {
             uint32_t* cntw = reinterpret_cast<uint32_t*>(sm.cnt);     // two 16-bit counters per word (counts <= 4094)
-            for (int p = tid; p < npos; p += LZE_THREADS) {
-                const uint32_t h = lz_hash3(lz_load4(sm.in, p));
-                hashv[p] = (uint16_t)h;
-                atomicAdd(&cntw[h >> 1], 1u << (16 * (h & 1)));
+            // a warp's lanes hold 32 consecutive positions = one placement round: lanes with equal hashes find each other
+            // here, in parallel (leader lane | rank inside the group << 5 | group size - 1 << 10, parked in ord[])
+#pragma unroll 4
+            for (int m = 0; m < LZNT1_CHUNK / LZE_THREADS; ++m) {
+                const int p = tid + LZE_THREADS * m;
+                uint32_t h = 0xFFFFu;
+                if (p < npos) {
+                    h = lz_hash3(lz_load4(sm.in, p));
+                    hashv[p] = (uint16_t)h;
+                    atomicAdd(&cntw[h >> 1], 1u << (16 * (h & 1)));
+                }
+                const unsigned peers = __match_any_sync(FULL, h);
+                sm.ord[p] = (uint16_t)((uint32_t)(__ffs((int)peers) - 1) | ((uint32_t)__popc(peers & ((1u << lane) - 1)) << 5) | ((uint32_t)(__popc(peers) - 1) << 10));
             }
             __syncthreads();
             // exclusive scan of the 4096 counts (16 per thread + block scan of the 256 partial sums): cnt[h] = BEGIN of bucket h
@@ -124,34 +133,30 @@ lznt1_encode_kernel(const uint8_t* __restrict__ in, uint64_t in_len, uint32_t fi
             reinterpret_cast<uint4*>(sm.cnt)[2 * tid + 1] = make_uint4(wv[4], wv[5], wv[6], wv[7]);
         }
         __syncthreads();
-        // Placement in position order by one warp: a round takes 32 consecutive positions; lanes with equal hashes find
-        // each other with __match_any_sync, the first of them advances the bucket cursor by the size of the group with
-        // one shared-memory atomic and hands the old value to the others.  Rounds are ordered (__syncwarp between their
-        // cursor updates), lanes are ordered inside a round, so buckets come out ascending by
-        // position -- which the early exit and the tie rule of the search rely on.  Four rounds are in flight at a time
-        // (nothing but the cursors links them).  The other warps wait at the barrier; other blocks of the SM fill the
-        // issue slots meanwhile.
+        // Placement in position order by one warp, a round of 32 consecutive positions at a time: the first lane of every
+        // group of equal hashes advances the bucket cursor by the size of the group with one shared-memory atomic and hands
+        // the old value to the others.  Rounds are ordered (__syncwarp between their cursor updates), lanes are ordered
+        // inside a round, so buckets come out ascending by position -- which the early exit and the tie rule of the search
+        // rely on.  Four rounds are in flight at a time (nothing but the cursors links them).  The other warps wait at the
+        // barrier; other blocks of the SM fill the issue slots meanwhile.
         if (warp == 0) {
             uint32_t* cntw = reinterpret_cast<uint32_t*>(sm.cnt);
             const int rounds = (npos + 31) >> 5;
             for (int k = 0; k < rounds; k += 4) {
-                uint32_t h[4], got[4];
-                unsigned peers[4];
+                uint32_t h[4], inf[4], got[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) { const int p = 32 * (k + u) + lane; h[u] = p < npos ? (uint32_t)hashv[p] : 0xFFFFu; }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) peers[u] = __match_any_sync(FULL, h[u]);
+                for (int u = 0; u < 4; ++u) { const int p = min(32 * (k + u) + lane, LZNT1_CHUNK - 1); h[u] = hashv[p]; inf[u] = sm.ord[p]; }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     got[u] = 0;
-                    if (h[u] != 0xFFFFu && (peers[u] & ((1u << lane) - 1)) == 0)
-                        got[u] = atomicAdd(&cntw[h[u] >> 1], (uint32_t)__popc(peers[u]) << (16 * (h[u] & 1)));
+                    if (32 * (k + u) + lane < npos && (inf[u] & 0x3E0u) == 0)
+                        got[u] = atomicAdd(&cntw[h[u] >> 1], ((inf[u] >> 10) + 1u) << (16 * (h[u] & 1)));
                     __syncwarp();                                    // cursor updates of round u before those of round u+1
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const uint32_t base = (__shfl_sync(FULL, got[u], __ffs((int)peers[u]) - 1) >> (16 * (h[u] & 1))) & 0xFFFFu;
-                    if (h[u] != 0xFFFFu) sm.sorted[base + (uint32_t)__popc(peers[u] & ((1u << lane) - 1))] = (uint16_t)(32 * (k + u) + lane);
+                    const uint32_t base = (__shfl_sync(FULL, got[u], (int)(inf[u] & 31u)) >> (16 * (h[u] & 1))) & 0xFFFFu;
+                    if (32 * (k + u) + lane < npos) sm.sorted[base + ((inf[u] >> 5) & 31u)] = (uint16_t)(32 * (k + u) + lane);
                 }
             }
         }
