@@ -74,6 +74,18 @@ MSCOMPAPI MSCompStatus mscomp_gpu_lznt1_decompress(mscomp_gpu_ctx* ctx, const ui
                                                    uint32_t* d_chunk_size, int32_t* d_chunk_status,
                                                    mscomp_gpu_result* d_result);
 
+/* Chunk index of an unindexed LZNT1 stream, built on the GPU (the format stores none; the reference walks the headers
+ * serially: src/lznt1_decompress.cpp:254-273 with the header read of :127-135).  Synchronous.  d_chunk_off receives the
+ * offset of every chunk header in stream order (chunk_cap entries available).  h_result (host memory): number of chunks,
+ * bytes consumed by whole chunks, and how the chain ended: 0 clean end, 1 one stray zero byte, 2 one stray non-zero
+ * byte, 3 two-byte terminator at the very end, 4 terminator followed by data, 5 truncated chunk, 6 bad signature -- the
+ * conditions the reference's driver turns into MSCOMP_OK / BUF_ERROR / DATA_ERROR.  Returns MSCOMP_BUF_ERROR (with
+ * h_result filled) when the stream has more than chunk_cap chunks. */
+typedef struct mscomp_gpu_lznt1_index_result { uint64_t nchunks; uint64_t consumed; int32_t tail; int32_t reserved; } mscomp_gpu_lznt1_index_result;
+MSCOMPAPI MSCompStatus mscomp_gpu_lznt1_index(mscomp_gpu_ctx* ctx, const uint8_t* d_in, size_t in_len,
+                                              uint64_t* d_chunk_off, size_t chunk_cap,
+                                              mscomp_gpu_lznt1_index_result* h_result);
+
 /* ---- Xpress-Huffman and plain Xpress: batches of independent buffers ----------------------------------------- */
 /* Device paths behind xpress_huff_compress / _decompress (reference src/xpress_huff_compress.cpp:247-331,
  * src/xpress_huff_decompress.cpp:136-162) and xpress_compress / _decompress (src/xpress_compress.cpp:240-347,

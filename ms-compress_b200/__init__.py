@@ -82,6 +82,7 @@ def lib():
         L.mscomp_gpu_profile_report.restype, L.mscomp_gpu_profile_report.argtypes = sz, [vp, vp, sz]
         L.mscomp_gpu_lznt1_compress.restype, L.mscomp_gpu_lznt1_compress.argtypes = i32, [vp, vp, sz, vp, sz, vp, vp]
         L.mscomp_gpu_lznt1_decompress.restype, L.mscomp_gpu_lznt1_decompress.argtypes = i32, [vp, vp, sz, vp, u32, vp, vp, vp, vp]
+        L.mscomp_gpu_lznt1_index.restype, L.mscomp_gpu_lznt1_index.argtypes = i32, [vp, vp, sz, vp, sz, vp]
         for fmt in ("xpress_huff", "xpress"):
             for op in ("compress", "decompress"):
                 if not hasattr(L, "mscomp_gpu_%s_%s_batch" % (fmt, op)):
@@ -258,6 +259,22 @@ class GpuContext:
         if st < 0:
             raise MSCompError("mscomp_gpu_lznt1_decompress", st)
         return d_out, d_result
+
+    def lznt1_index(self, d_in, chunk_cap=None, in_len=None):
+        """Chunk index of an unindexed LZNT1 stream, built on the GPU.  Returns (offsets tensor, info dict with nchunks,
+        consumed, tail); tail: 0 clean, 1 stray zero byte, 2 stray byte, 3 terminator, 4 terminator + data, 5 truncated,
+        6 bad signature."""
+        n = d_in.numel() if in_len is None else in_len
+        if chunk_cap is None:
+            chunk_cap = n // 3 + 1
+        d_off = self.torch.empty(chunk_cap + 1, dtype=self.torch.int64, device=self.device)
+        res = (ctypes.c_uint64 * 3)()
+        st = lib().mscomp_gpu_lznt1_index(self.handle, d_in.data_ptr(), n, d_off.data_ptr(), chunk_cap, ctypes.addressof(res))
+        info = {"nchunks": int(res[0]), "consumed": int(res[1]), "tail": int(res[2] & 0xFFFFFFFF)}
+        if st < 0 and st != -5:
+            raise MSCompError("mscomp_gpu_lznt1_index", st)
+        info["status"] = st
+        return d_off, info
 
     # -- batches of independent buffers (Xpress-Huffman, Xpress) --
     def make_batch(self, in_off, in_len, out_off, out_cap):

@@ -15,8 +15,10 @@ struct mscomp_gpu_ctx {
     uint64_t launches = 0;
     void* scratch[SC_COUNT] = {};
     size_t scratch_cap[SC_COUNT] = {};
-    cudaStream_t copy_stream = nullptr;   // second stream of the host-pointer wrappers: uploads overlap with kernels
-    cudaEvent_t copy_ev[16] = {};
+    cudaStream_t copy_stream = nullptr;   // upload stream of the host-pointer wrappers: uploads overlap with kernels
+    cudaStream_t down_stream = nullptr;   // download stream: results leave while later slices are still being processed
+    cudaEvent_t copy_ev[16] = {};         // upload events (ring)
+    cudaEvent_t work_ev[16] = {};         // kernel-side events (ring)
     void* pinned = nullptr;          // small pinned mailbox for results
     size_t pinned_cap = 0;
 
@@ -25,7 +27,10 @@ struct mscomp_gpu_ctx {
     {
         if (copy_stream) return true;
         if (cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); copy_stream = nullptr; return false; }
-        for (int i = 0; i < 16; ++i) cudaEventCreateWithFlags(&copy_ev[i], cudaEventDisableTiming);
+        if (cudaStreamCreateWithFlags(&down_stream, cudaStreamNonBlocking) != cudaSuccess) {
+            cudaGetLastError(); cudaStreamDestroy(copy_stream); copy_stream = down_stream = nullptr; return false;
+        }
+        for (int i = 0; i < 16; ++i) { cudaEventCreateWithFlags(&copy_ev[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&work_ev[i], cudaEventDisableTiming); }
         return true;
     }
 

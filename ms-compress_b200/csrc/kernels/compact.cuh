@@ -11,13 +11,15 @@ namespace msc {
 constexpr int SCAN_THREADS = 1024;
 
 // offs[i] = base + sum_{j<i} sizes[j] for i in [0, n]; single block (n is a unit count: <= a few million).
+// base_ptr (may be null) adds a device-resident base: the end offset of the previous slice when a stream is compacted
+// slice by slice.
 __global__ void __launch_bounds__(SCAN_THREADS)
-scan_sizes_kernel(const uint32_t* __restrict__ sizes, uint32_t n, uint64_t base, uint64_t* __restrict__ offs)
+scan_sizes_kernel(const uint32_t* __restrict__ sizes, uint32_t n, uint64_t base, const uint64_t* base_ptr, uint64_t* __restrict__ offs)
 {
     __shared__ uint64_t wsum[32];
     __shared__ uint64_t carry;
     const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) carry = base;
+    if (tid == 0) carry = base + (base_ptr ? *base_ptr : 0);
     __syncthreads();
     for (uint32_t start = 0; start < n; start += SCAN_THREADS * 4) {
         uint32_t v[4];

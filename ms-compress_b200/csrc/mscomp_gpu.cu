@@ -4,6 +4,7 @@
 #include "kernels/lznt1_decode.cuh"
 #include "kernels/lznt1_encode.cuh"
 #include "kernels/lznt1_decode_lanes.cuh"
+#include "kernels/lznt1_index.cuh"
 #include <stdlib.h>
 #include <string.h>
 #include "kernels/compact.cuh"
@@ -18,16 +19,24 @@ using namespace msc;
 
 static_assert(sizeof(GpuResult) == sizeof(mscomp_gpu_result), "result layout");
 
-MSCompStatus msc_compact_slots(mscomp_gpu_ctx* ctx, const uint8_t* d_slots, uint64_t stride, const uint32_t* d_sizes,
-                               uint32_t n, uint64_t* d_offs, uint8_t* d_dst)
+// Units [first, first + n) of a slot array: offsets continue from d_offs[first] (written by the previous range; 0 when
+// first == 0), the bytes go to their final place in d_dst.  A whole array is the range (0, n).
+MSCompStatus msc_compact_slots_range(mscomp_gpu_ctx* ctx, const uint8_t* d_slots, uint64_t stride, const uint32_t* d_sizes,
+                                     uint32_t first, uint32_t n, uint64_t* d_offs, uint8_t* d_dst)
 {
-    MSC_LAUNCH(ctx, scan_sizes_kernel, 1, SCAN_THREADS, d_sizes, n, (uint64_t)0, d_offs);
+    MSC_LAUNCH(ctx, scan_sizes_kernel, 1, SCAN_THREADS, d_sizes + first, n, (uint64_t)0, first ? (const uint64_t*)(d_offs + first) : nullptr, d_offs + first);
     if (n) {
         const uint32_t gw = (n + 7) / 8;
         const uint32_t grid = gw < (uint32_t)ctx->sm_count * 8 ? gw : (uint32_t)ctx->sm_count * 8;
-        MSC_LAUNCH(ctx, gather_slots_kernel, grid, 256, d_slots, stride, d_sizes, d_offs, n, d_dst);
+        MSC_LAUNCH(ctx, gather_slots_kernel, grid, 256, d_slots + (uint64_t)first * stride, stride, d_sizes + first, (const uint64_t*)(d_offs + first), n, d_dst);
     }
     return msc_cuda_status(cudaGetLastError(), "compact_slots");
+}
+
+MSCompStatus msc_compact_slots(mscomp_gpu_ctx* ctx, const uint8_t* d_slots, uint64_t stride, const uint32_t* d_sizes,
+                               uint32_t n, uint64_t* d_offs, uint8_t* d_dst)
+{
+    return msc_compact_slots_range(ctx, d_slots, stride, d_sizes, 0, n, d_offs, d_dst);
 }
 
 // Encode chunks [first, first+count) of the stream d_in[0..in_len) into their slots (one 256-thread block per chunk).
@@ -80,7 +89,10 @@ void mscomp_gpu_destroy(mscomp_gpu_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < SC_COUNT; ++i) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
-    if (ctx->copy_stream) { for (int i = 0; i < 16; ++i) cudaEventDestroy(ctx->copy_ev[i]); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->copy_stream) {
+        for (int i = 0; i < 16; ++i) { cudaEventDestroy(ctx->copy_ev[i]); cudaEventDestroy(ctx->work_ev[i]); }
+        cudaStreamDestroy(ctx->copy_stream); cudaStreamDestroy(ctx->down_stream);
+    }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -146,6 +158,107 @@ MSCompStatus mscomp_gpu_lznt1_compress(mscomp_gpu_ctx* ctx, const uint8_t* d_in,
     return msc_cuda_status(cudaGetLastError(), "lznt1_compress");
 }
 
+// ---- LZNT1 chunk index (kernels/lznt1_index.cuh) -------------------------------------------------------------------
+static_assert(sizeof(Lznt1IndexState) == sizeof(msc_lznt1_index_state), "index state layout");
+
+// Steps 1-4 for segments [seg0, seg0 + nseg) of the stream: d_state is updated (chunks of the range, how the chain
+// ended).  The per-segment entries / chunk numbers stay in scratch slot `slot` (0 or 1) for the matching _write call.
+MSCompStatus msc_lznt1_index_count(mscomp_gpu_ctx* ctx, const uint8_t* d_in, size_t in_len, uint32_t seg0, uint32_t nseg,
+                                   int slot, msc_lznt1_index_state* d_state)
+{
+    const uint32_t S = LZI_SEG_BYTES, ng = (nseg + LZI_GROUP - 1) / LZI_GROUP;
+    const size_t t_bytes = ((size_t)nseg + ng) * LZI_STRIDE * sizeof(uint16_t);
+    const size_t e_bytes = (((size_t)nseg * 6 + (size_t)ng * 2) + 255) / 256 * 256;       // seg_base u32 | seg_entry u16 | grp_entry u16
+    uint16_t* T1 = (uint16_t*)ctx->get(SC_AUX0, t_bytes + 64);
+    uint8_t* e = (uint8_t*)ctx->get(SC_AUX1, 2 * e_bytes + 64);
+    if (!T1 || !e) return MSCOMP_MEM_ERROR;
+    uint16_t* T2 = T1 + (size_t)nseg * LZI_STRIDE;
+    e += (size_t)(slot & 1) * e_bytes;
+    uint32_t* seg_base = (uint32_t*)e;
+    uint16_t* seg_entry = (uint16_t*)(seg_base + nseg);
+    uint16_t* grp_entry = seg_entry + nseg;
+    const uint32_t grid = nseg < (uint32_t)ctx->sm_count * 12 ? nseg : (uint32_t)ctx->sm_count * 12;
+    MSC_OPT_IN_SMEM(lznt1_index_tables_kernel, S + 16);
+    MSC_LAUNCH_SMEM(ctx, lznt1_index_tables_kernel, grid, LZI_THREADS, S + 16, d_in, (uint64_t)in_len, seg0, nseg, S, T1);
+    MSC_LAUNCH(ctx, lznt1_index_compose_kernel, ng, LZI_THREADS, (const uint16_t*)T1, nseg, T2);
+    MSC_LAUNCH(ctx, lznt1_index_entries_kernel, 1, 256, (const uint16_t*)T1, (const uint16_t*)T2, nseg, (Lznt1IndexState*)d_state, seg_entry, grp_entry);
+    MSC_LAUNCH(ctx, lznt1_index_count_kernel, 1, LZI_THREADS, d_in, (uint64_t)in_len, seg0, nseg, S, (const uint16_t*)seg_entry, seg_base, (Lznt1IndexState*)d_state);
+    return msc_cuda_status(cudaGetLastError(), "lznt1_index");
+}
+
+// Step 5: chunk offsets of the range into d_offs[0 .. range_chunks) (the caller passes the position of the range's first chunk).
+MSCompStatus msc_lznt1_index_write(mscomp_gpu_ctx* ctx, const uint8_t* d_in, size_t in_len, uint32_t seg0, uint32_t nseg,
+                                   int slot, uint64_t* d_offs)
+{
+    const uint32_t S = LZI_SEG_BYTES, ng = (nseg + LZI_GROUP - 1) / LZI_GROUP;
+    const size_t e_bytes = (((size_t)nseg * 6 + (size_t)ng * 2) + 255) / 256 * 256;
+    uint8_t* e = (uint8_t*)ctx->scratch[SC_AUX1];
+    if (!e) return MSCOMP_ARG_ERROR;
+    e += (size_t)(slot & 1) * e_bytes;
+    const uint32_t* seg_base = (const uint32_t*)e;
+    const uint16_t* seg_entry = (const uint16_t*)(seg_base + nseg);
+    const uint32_t grid = (nseg + 255) / 256;
+    MSC_LAUNCH(ctx, lznt1_index_write_kernel, grid, 256, d_in, (uint64_t)in_len, seg0, nseg, S, seg_entry, seg_base, d_offs);
+    return msc_cuda_status(cudaGetLastError(), "lznt1_index");
+}
+
+MSCompStatus mscomp_gpu_lznt1_index(mscomp_gpu_ctx* ctx, const uint8_t* d_in, size_t in_len, uint64_t* d_chunk_off, size_t chunk_cap,
+                                    mscomp_gpu_lznt1_index_result* h_result)
+{
+    if (!ctx || (!d_in && in_len) || !h_result || (!d_chunk_off && chunk_cap)) return MSCOMP_ARG_ERROR;
+    cudaSetDevice(ctx->device);
+    const uint64_t nseg64 = in_len ? (in_len + LZI_SEG_BYTES - 1) / LZI_SEG_BYTES : 1;
+    if (nseg64 > 0x7fffffffu) return MSCOMP_ARG_ERROR;
+    msc_lznt1_index_state* d_st = (msc_lznt1_index_state*)ctx->get(SC_RESULT, 256);
+    msc_lznt1_index_state* h_st = (msc_lznt1_index_state*)ctx->get_pinned(256);
+    if (!d_st || !h_st) return MSCOMP_MEM_ERROR;
+    cudaMemsetAsync(d_st, 0, sizeof(*d_st), ctx->stream);
+    MSCompStatus st = msc_lznt1_index_count(ctx, d_in, in_len, 0, (uint32_t)nseg64, 0, d_st);
+    if (st != MSCOMP_OK) return st;
+    cudaMemcpyAsync(h_st, d_st, sizeof(*h_st), cudaMemcpyDeviceToHost, ctx->stream);
+    if ((st = msc_cuda_status(cudaStreamSynchronize(ctx->stream), "lznt1_index")) != MSCOMP_OK) return st;
+    h_result->nchunks = h_st->nchunks;
+    h_result->consumed = h_st->ip;
+    h_result->tail = (int32_t)h_st->tail;
+    h_result->reserved = 0;
+    if (h_st->nchunks > chunk_cap) return MSCOMP_BUF_ERROR;
+    if (h_st->nchunks) {
+        if ((st = msc_lznt1_index_write(ctx, d_in, in_len, 0, (uint32_t)nseg64, 0, d_chunk_off)) != MSCOMP_OK) return st;
+        st = msc_cuda_status(cudaStreamSynchronize(ctx->stream), "lznt1_index");
+    }
+    return st;
+}
+
+// Decode chunks whose headers sit at d_chunk_off[0 .. nchunks) of the stream; chunk i goes to d_out + 4096 * i.
+MSCompStatus msc_lznt1_decode_chunks(mscomp_gpu_ctx* ctx, const uint8_t* d_in, size_t in_len, const uint64_t* d_chunk_off, uint32_t nchunks,
+                                     uint8_t* d_out, uint32_t* sizes, int32_t* status)
+{
+    // Two mappings of the same decoder.  Default: a warp per chunk with the chunk staged in shared memory -- its DRAM
+    // traffic equals the algorithmic bytes (profiles/traffic.json).  MSCOMP_LZNT1_DECODE=lanes selects the
+    // lane-per-chunk variant: same speed on B200 but every lane's 4 KiB window lives in L2/HBM, and with ~300k
+    // chunks in flight the match reads miss L2 (20x read amplification measured), so it is not the default.
+    static const char* mode = getenv("MSCOMP_LZNT1_DECODE");
+    const bool lanes = mode && strcmp(mode, "lanes") == 0;
+    if (lanes) {
+        const uint32_t tpb = 32 * LZL_WARPS_PER_BLOCK;
+        const uint32_t blocks = (nchunks + tpb - 1) / tpb, cap = (uint32_t)ctx->sm_count * 16;
+        MSC_LAUNCH(ctx, lznt1_decode_lanes_kernel, blocks < cap ? blocks : cap, tpb,
+                   d_in, (uint64_t)in_len, d_chunk_off, nchunks, d_out, sizes, status);
+    } else {
+        const uint32_t blocks = (nchunks + LZNT1_WARPS_PER_BLOCK - 1) / LZNT1_WARPS_PER_BLOCK;
+        const uint32_t cap = (uint32_t)ctx->sm_count * 6 * 4;             // 6 resident blocks per SM, a few waves
+        MSC_LAUNCH(ctx, lznt1_decode_kernel, blocks < cap ? blocks : cap, LZNT1_WARPS_PER_BLOCK * 32,
+                   d_in, (uint64_t)in_len, d_chunk_off, nchunks, d_out, sizes, status);
+    }
+    return msc_cuda_status(cudaGetLastError(), "lznt1_decode");
+}
+
+MSCompStatus msc_summarize_units(mscomp_gpu_ctx* ctx, const uint32_t* d_sizes, const int32_t* d_status, uint32_t n, uint32_t full_unit, mscomp_gpu_result* d_res)
+{
+    MSC_LAUNCH(ctx, summarize_kernel, 1, SUM_THREADS, d_sizes, d_status, n, full_unit, (GpuResult*)d_res);
+    return msc_cuda_status(cudaGetLastError(), "summarize");
+}
+
 MSCompStatus mscomp_gpu_lznt1_decompress(mscomp_gpu_ctx* ctx, const uint8_t* d_in, size_t in_len, const uint64_t* d_chunk_off,
                                          uint32_t nchunks, uint8_t* d_out, uint32_t* d_chunk_size, int32_t* d_chunk_status,
                                          mscomp_gpu_result* d_result)
@@ -155,25 +268,7 @@ MSCompStatus mscomp_gpu_lznt1_decompress(mscomp_gpu_ctx* ctx, const uint8_t* d_i
     uint32_t* sizes = d_chunk_size ? d_chunk_size : (uint32_t*)ctx->get(SC_SIZES, ((size_t)nchunks + 1) * sizeof(uint32_t));
     int32_t* status = d_chunk_status ? d_chunk_status : (int32_t*)ctx->get(SC_STATUS, ((size_t)nchunks + 1) * sizeof(int32_t));
     if (!sizes || !status) return MSCOMP_MEM_ERROR;
-    if (nchunks) {
-        // Two mappings of the same decoder.  Default: a warp per chunk with the chunk staged in shared memory -- its DRAM
-        // traffic equals the algorithmic bytes (profiles/traffic.json).  MSCOMP_LZNT1_DECODE=lanes selects the
-        // lane-per-chunk variant: same speed on B200 but every lane's 4 KiB window lives in L2/HBM, and with ~300k
-        // chunks in flight the match reads miss L2 (20x read amplification measured), so it is not the default.
-        static const char* mode = getenv("MSCOMP_LZNT1_DECODE");
-        const bool lanes = mode && strcmp(mode, "lanes") == 0;
-        if (lanes) {
-            const uint32_t tpb = 32 * LZL_WARPS_PER_BLOCK;
-            const uint32_t blocks = (nchunks + tpb - 1) / tpb, cap = (uint32_t)ctx->sm_count * 16;
-            MSC_LAUNCH(ctx, lznt1_decode_lanes_kernel, blocks < cap ? blocks : cap, tpb,
-                       d_in, (uint64_t)in_len, d_chunk_off, nchunks, d_out, sizes, status);
-        } else {
-            const uint32_t blocks = (nchunks + LZNT1_WARPS_PER_BLOCK - 1) / LZNT1_WARPS_PER_BLOCK;
-            const uint32_t cap = (uint32_t)ctx->sm_count * 6 * 4;             // 6 resident blocks per SM, a few waves
-            MSC_LAUNCH(ctx, lznt1_decode_kernel, blocks < cap ? blocks : cap, LZNT1_WARPS_PER_BLOCK * 32,
-                       d_in, (uint64_t)in_len, d_chunk_off, nchunks, d_out, sizes, status);
-        }
-    }
+    if (nchunks) msc_lznt1_decode_chunks(ctx, d_in, in_len, d_chunk_off, nchunks, d_out, sizes, status);
     MSC_LAUNCH(ctx, summarize_kernel, 1, SUM_THREADS, sizes, status, nchunks, (uint32_t)LZNT1_CHUNK, (GpuResult*)d_result);
     return msc_cuda_status(cudaGetLastError(), "lznt1_decompress");
 }

@@ -12,6 +12,7 @@
 // header walk) and to reproducing the reference's status codes.  No codec work happens on the CPU.
 #include "ctx.cuh"
 #include "shim_common.h"
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -34,6 +35,23 @@ mscomp_gpu_ctx* msc_thread_ctx()
 
 static inline unsigned rd16(const uint8_t* p) { return (unsigned)p[0] | ((unsigned)p[1] << 8); }
 
+// Tuning / test hooks of the pipelined host wrappers (bytes): MSCOMP_PIPE_SLICE = upload/encode/download granularity of
+// lznt1_compress, MSCOMP_PIPE_MIN = smallest stream lznt1_decompress pipelines, MSCOMP_PIPE_RANGE = its range size.
+static size_t env_bytes(const char* name, size_t dflt)
+{
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    const unsigned long long x = strtoull(v, nullptr, 10);
+    return x ? (size_t)x : dflt;
+}
+
+namespace {
+struct StreamGuard {            // the user's buffers must not be in use by a DMA once we return
+    cudaStream_t s[3] = {nullptr, nullptr, nullptr};
+    ~StreamGuard() { for (cudaStream_t x : s) if (x) cudaStreamSynchronize(x); }
+};
+} // namespace
+
 // =================================================================================================================
 // LZNT1
 // =================================================================================================================
@@ -54,32 +72,59 @@ extern "C" MSCompStatus lznt1_compress(const_bytes in, size_t in_len, bytes out,
     mscomp_gpu_result* h_res = (mscomp_gpu_result*)ctx->get_pinned(256);
     if (!d_in || !d_out || !d_res || !h_res) return MSCOMP_MEM_ERROR;
     MSCompStatus st;
-    const size_t kSlice = (size_t)64 << 20;                 // upload / encode granularity (a multiple of the chunk size)
+    static const size_t kSliceEnv = env_bytes("MSCOMP_PIPE_SLICE", (size_t)64 << 20);
+    const size_t kSlice = (kSliceEnv + 4095) / 4096 * 4096;  // upload / encode / download granularity (a multiple of the chunk size)
     if (in_len > kSlice && ctx->copy_ready()) {
-        // chunks are independent: upload slice i+1 on the copy stream while slice i is being encoded
+        // Chunks are independent and the stream is their concatenation, so the call runs as a three-stage pipeline over
+        // slices: upload slice k+1 (copy stream) | encode + compact slice k (compute stream) | download the bytes of slice
+        // k-1 (download stream).  The device keeps the running end offset (scan_sizes_kernel continues from the previous
+        // slice); the host learns it from a pinned mailbox one slice behind, to address the download.
         uint8_t* d_slots = (uint8_t*)ctx->get(SC_SLOTS, nchunks * MSC_LZNT1_SLOT_BYTES + 16);
         uint32_t* d_sizes = (uint32_t*)ctx->get(SC_SIZES, (nchunks + 1) * sizeof(uint32_t));
         uint64_t* d_offs = (uint64_t*)ctx->get(SC_OFFS, (nchunks + 1) * sizeof(uint64_t));
-        if (!d_slots || !d_sizes || !d_offs) return MSCOMP_MEM_ERROR;
+        uint64_t* h_end = (uint64_t*)ctx->get_pinned(1024);
+        if (!d_slots || !d_sizes || !d_offs || !h_end) return MSCOMP_MEM_ERROR;
+        h_end += 32;                                                         // the first 256 bytes are the result mailbox
+        StreamGuard guard;
+        guard.s[0] = ctx->copy_stream; guard.s[1] = ctx->down_stream; guard.s[2] = ctx->stream;
         cudaEventRecord(ctx->copy_ev[15], ctx->stream);                      // earlier work on the scratch buffers
         cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[15], 0);
-        int k = 0;
-        for (size_t off = 0; off < in_len; off += kSlice, ++k) {
-            const size_t len = in_len - off < kSlice ? in_len - off : kSlice;
+        cudaStreamWaitEvent(ctx->down_stream, ctx->copy_ev[15], 0);
+        const size_t nslices = (in_len + kSlice - 1) / kSlice;
+        size_t sent = 0;                                                     // compressed bytes already on their way to `out`
+        bool overflow = false;
+        auto download = [&](size_t k) -> MSCompStatus {                      // slice k is encoded and compacted: ship its bytes
+            MSCompStatus s2 = msc_cuda_status(cudaEventSynchronize(ctx->work_ev[k % 15]), "lznt1_compress");
+            if (s2 != MSCOMP_OK) return s2;
+            const size_t end = (size_t)h_end[k % 15];
+            if (end > cap) { overflow = true; return MSCOMP_OK; }
+            if (end > sent && !overflow) cudaMemcpyAsync(out + sent, d_out + sent, end - sent, cudaMemcpyDeviceToHost, ctx->down_stream);
+            sent = end;
+            return MSCOMP_OK;
+        };
+        for (size_t k = 0; k < nslices; ++k) {
+            const size_t off = k * kSlice, len = in_len - off < kSlice ? in_len - off : kSlice;
+            const uint32_t first = (uint32_t)(off / 4096), cnt = (uint32_t)((len + 4095) / 4096);
             cudaEvent_t ev = ctx->copy_ev[k % 15];
-            if (k >= 15) cudaEventSynchronize(ev);                            // (ring reuse: that slice was consumed long ago)
             cudaMemcpyAsync(d_in + off, in + off, len, cudaMemcpyHostToDevice, ctx->copy_stream);
             cudaEventRecord(ev, ctx->copy_stream);
             cudaStreamWaitEvent(ctx->stream, ev, 0);
-            if ((st = msc_lznt1_encode_chunks(ctx, d_in, in_len, (uint32_t)(off / 4096), (uint32_t)((len + 4095) / 4096), d_slots, d_sizes)) != MSCOMP_OK) return st;
+            if ((st = msc_lznt1_encode_chunks(ctx, d_in, in_len, first, cnt, d_slots, d_sizes)) != MSCOMP_OK) return st;
+            if ((st = msc_compact_slots_range(ctx, d_slots, MSC_LZNT1_SLOT_BYTES, d_sizes, first, cnt, d_offs, d_out)) != MSCOMP_OK) return st;
+            cudaMemcpyAsync(&h_end[k % 15], d_offs + first + cnt, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+            cudaEventRecord(ctx->work_ev[k % 15], ctx->stream);
+            if (k >= 1 && (st = download(k - 1)) != MSCOMP_OK) return st;   // one slice behind: the GPU always has slice k queued
         }
-        if ((st = msc_compact_slots(ctx, d_slots, MSC_LZNT1_SLOT_BYTES, d_sizes, (uint32_t)nchunks, d_offs, d_out)) != MSCOMP_OK) return st;
-        cudaMemsetAsync(d_res, 0, sizeof(*d_res), ctx->stream);
-        cudaMemcpyAsync(&d_res->bytes, d_offs + nchunks, sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream);
-    } else {
-        if (in_len) cudaMemcpyAsync(d_in, in, in_len, cudaMemcpyHostToDevice, ctx->stream);
-        if ((st = mscomp_gpu_lznt1_compress(ctx, d_in, in_len, d_out, dcap, nullptr, d_res)) != MSCOMP_OK) return st;
+        if ((st = download(nslices - 1)) != MSCOMP_OK) return st;
+        if ((st = msc_cuda_status(cudaStreamSynchronize(ctx->down_stream), "lznt1_compress")) != MSCOMP_OK) return st;
+        if (overflow) return MSCOMP_BUF_ERROR;                               // same outcome as the chunk-by-chunk checks upstream (:239-259)
+        const size_t total = sent;
+        if (cap - total >= 2) out[total] = out[total + 1] = 0;               // end-of-buffer terminator, not counted (:268-271)
+        *out_len = total;
+        return MSCOMP_OK;
     }
+    if (in_len) cudaMemcpyAsync(d_in, in, in_len, cudaMemcpyHostToDevice, ctx->stream);
+    if ((st = mscomp_gpu_lznt1_compress(ctx, d_in, in_len, d_out, dcap, nullptr, d_res)) != MSCOMP_OK) return st;
     cudaMemcpyAsync(h_res, d_res, sizeof(*h_res), cudaMemcpyDeviceToHost, ctx->stream);
     if ((st = msc_cuda_status(cudaStreamSynchronize(ctx->stream), "lznt1_compress")) != MSCOMP_OK) return st;
     const size_t total = (size_t)h_res->bytes;
@@ -122,14 +167,141 @@ MSCompStatus lznt1_replay(size_t nchunks, size_t cap, Lznt1Tail tail, FS size_of
 }
 } // namespace
 
+namespace {
+constexpr MSCompStatus MSC_FALLBACK = (MSCompStatus)1000;    // internal: "take the simple path"
+
+// lznt1_decompress for large streams, as a pipeline over ranges of the compressed stream:
+//   upload range k+1 (copy stream) | index + decode range k (compute stream) | download the output of range k-1.
+// The chunk index is built on the GPU (kernels/lznt1_index.cuh) range by range, so nothing waits for a host-side walk
+// over the headers (one cache miss per chunk).  This path handles the normal case only -- every chunk decodes, every
+// chunk but the last is 4096 bytes, the output fits; anything else drains the pipeline and returns MSC_FALLBACK, and
+// the caller runs the simple path, which reproduces the reference's status codes chunk by chunk.
+MSCompStatus lznt1_decompress_pipelined(mscomp_gpu_ctx* ctx, const_bytes in, size_t in_len, bytes out, size_t* out_len, size_t range_bytes)
+{
+    const size_t cap = *out_len;
+    const size_t S = MSC_LZNT1_INDEX_SEG;
+    const size_t R = (range_bytes + S - 1) / S * S;
+    const size_t nranges = (in_len + R - 1) / R;
+    const size_t kOverlap = 8192;                                // a chunk that starts inside a range ends < 4098 bytes past it
+    size_t ncap = cap / 4096 + 2;                                // more chunks than this cannot fit the output anyway
+    if (ncap > in_len / 3 + 1) ncap = in_len / 3 + 1;
+    if (ncap > 0x7fffffffu) return MSC_FALLBACK;
+    uint8_t* d_in = (uint8_t*)ctx->get(SC_IN, in_len + kOverlap + 64);
+    uint8_t* d_out = (uint8_t*)ctx->get(SC_OUT, ncap * 4096 + 64);
+    uint64_t* d_offs = (uint64_t*)ctx->get(SC_OFFS, (ncap + 1) * sizeof(uint64_t));
+    uint32_t* d_sizes = (uint32_t*)ctx->get(SC_SIZES, (ncap + 1) * sizeof(uint32_t));
+    int32_t* d_status = (int32_t*)ctx->get(SC_STATUS, (ncap + 1) * sizeof(int32_t));
+    uint8_t* d_box = (uint8_t*)ctx->get(SC_RESULT, 1024);        // index state at +0, per-range summaries at +256
+    uint8_t* h_box = (uint8_t*)ctx->get_pinned(4096);            // per-range copies of the state at +256, of the summaries at +2048
+    if (!d_in || !d_out || !d_offs || !d_sizes || !d_status || !d_box || !h_box) return MSCOMP_MEM_ERROR;
+    msc_lznt1_index_state* d_state = (msc_lznt1_index_state*)d_box;
+    mscomp_gpu_result* d_sum = (mscomp_gpu_result*)(d_box + 256);
+    auto h_state = [&](size_t k) { return (msc_lznt1_index_state*)(h_box + 256 + 64 * (k % 8)); };
+    auto h_sum = [&](size_t k) { return (mscomp_gpu_result*)(h_box + 2048 + 64 * (k % 8)); };
+
+    StreamGuard guard;
+    guard.s[0] = ctx->copy_stream; guard.s[1] = ctx->down_stream; guard.s[2] = ctx->stream;
+    cudaEventRecord(ctx->copy_ev[15], ctx->stream);              // earlier work on the scratch buffers
+    cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[15], 0);
+    cudaStreamWaitEvent(ctx->down_stream, ctx->copy_ev[15], 0);
+    cudaMemsetAsync(d_state, 0, sizeof(*d_state), ctx->stream);
+
+    MSCompStatus st = MSCOMP_OK;
+    auto stage_in = [&](size_t k) -> MSCompStatus {              // upload range k, then count its chunks
+        const size_t off = k * R;
+        size_t len = in_len - off < R + kOverlap ? in_len - off : R + kOverlap;
+        cudaMemcpyAsync(d_in + off, in + off, len, cudaMemcpyHostToDevice, ctx->copy_stream);
+        cudaEventRecord(ctx->copy_ev[k % 15], ctx->copy_stream);
+        cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[k % 15], 0);
+        const size_t bytes = in_len - off < R ? in_len - off : R;
+        MSCompStatus s2 = msc_lznt1_index_count(ctx, d_in, in_len, (uint32_t)(off / S), (uint32_t)((bytes + S - 1) / S), (int)(k & 1), d_state);
+        if (s2 != MSCOMP_OK) return s2;
+        cudaMemcpyAsync(h_state(k), d_state, sizeof(msc_lznt1_index_state), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaEventRecord(ctx->work_ev[(2 * k) % 16], ctx->stream);
+        return MSCOMP_OK;
+    };
+    struct Range { size_t c0 = 0, n = 0; bool last = false; };
+    std::vector<Range> rg(nranges);
+    bool seen_end = false;
+    auto stage_decode = [&](size_t k) -> MSCompStatus {          // chunk offsets, decode, summary of range k
+        MSCompStatus s2 = msc_cuda_status(cudaEventSynchronize(ctx->work_ev[(2 * k) % 16]), "lznt1_decompress");
+        if (s2 != MSCOMP_OK) return s2;
+        const msc_lznt1_index_state hs = *h_state(k);
+        if (hs.nchunks > ncap) return MSC_FALLBACK;
+        rg[k].n = (size_t)hs.range_chunks;
+        rg[k].c0 = (size_t)(hs.nchunks - hs.range_chunks);
+        rg[k].last = hs.done && !seen_end;                       // the chain ends in this range: its last chunk may be short
+        if (hs.done) seen_end = true;
+        if (rg[k].n) {
+            const size_t off = k * R, bytes = in_len - off < R ? in_len - off : R;
+            if ((s2 = msc_lznt1_index_write(ctx, d_in, in_len, (uint32_t)(off / S), (uint32_t)((bytes + S - 1) / S), (int)(k & 1), d_offs + rg[k].c0)) != MSCOMP_OK) return s2;
+            if ((s2 = msc_lznt1_decode_chunks(ctx, d_in, in_len, d_offs + rg[k].c0, (uint32_t)rg[k].n, d_out + rg[k].c0 * 4096,
+                                              d_sizes + rg[k].c0, d_status + rg[k].c0)) != MSCOMP_OK) return s2;
+            if ((s2 = msc_summarize_units(ctx, d_sizes + rg[k].c0, d_status + rg[k].c0, (uint32_t)rg[k].n, 4096, d_sum + (k % 8))) != MSCOMP_OK) return s2;
+            cudaMemcpyAsync(h_sum(k), d_sum + (k % 8), sizeof(mscomp_gpu_result), cudaMemcpyDeviceToHost, ctx->stream);
+        }
+        cudaEventRecord(ctx->work_ev[(2 * k + 1) % 16], ctx->stream);
+        return MSCOMP_OK;
+    };
+    size_t total = 0, last_size = 4096;
+    auto stage_out = [&](size_t k) -> MSCompStatus {             // range k is decoded: check it, ship its bytes
+        MSCompStatus s2 = msc_cuda_status(cudaEventSynchronize(ctx->work_ev[(2 * k + 1) % 16]), "lznt1_decompress");
+        if (s2 != MSCOMP_OK || !rg[k].n) return s2;
+        const mscomp_gpu_result r = *h_sum(k);
+        if (r.status != 0 || r.short_units != 0) return MSC_FALLBACK;
+        const size_t last = (size_t)r.bytes - (rg[k].n - 1) * 4096;
+        if (!rg[k].last && last != 4096) return MSC_FALLBACK;   // a short chunk in mid-stream
+        if (rg[k].c0 * 4096 != total || (size_t)r.bytes > cap - total) return MSC_FALLBACK;
+        cudaMemcpyAsync(out + total, d_out + total, (size_t)r.bytes, cudaMemcpyDeviceToHost, ctx->down_stream);
+        total += (size_t)r.bytes;
+        last_size = last;
+        return MSCOMP_OK;
+    };
+
+    if ((st = stage_in(0)) != MSCOMP_OK) return st;
+    for (size_t k = 0; k < nranges && st == MSCOMP_OK; ++k) {
+        if (k + 1 < nranges) st = stage_in(k + 1);               // keep the GPU one range ahead of the host
+        if (st == MSCOMP_OK) st = stage_decode(k);
+        if (st == MSCOMP_OK && k >= 1) st = stage_out(k - 1);
+    }
+    if (st == MSCOMP_OK) st = stage_out(nranges - 1);
+    if (st != MSCOMP_OK) return st;                              // (the guard drains the streams)
+    if ((st = msc_cuda_status(cudaStreamSynchronize(ctx->down_stream), "lznt1_decompress")) != MSCOMP_OK) return st;
+    const msc_lznt1_index_state fin = *h_state(nranges - 1);
+    if (!fin.done || fin.nchunks == 0) return MSC_FALLBACK;
+    const size_t nchunks = (size_t)fin.nchunks;
+    size_t replayed = 0;
+    st = lznt1_replay(nchunks, cap, (Lznt1Tail)fin.tail, [&](size_t c) { return c + 1 < nchunks ? (size_t)4096 : last_size; },
+                      [](size_t) { return 0; }, &replayed);
+    if (st == MSCOMP_OK) *out_len = replayed;
+    return st;
+}
+} // namespace
+
 extern "C" MSCompStatus lznt1_decompress(const_bytes in, size_t in_len, bytes out, size_t* out_len)
 {
     if (!out_len || (!in && in_len) || (!out && *out_len)) return MSCOMP_ARG_ERROR;
     const size_t cap = *out_len;
 
-    // The upload of the stream starts first, on the copy stream, so that it overlaps with the header walk below.
     mscomp_gpu_ctx* ctx = in_len >= 2 ? msc_thread_ctx() : nullptr;
     if (in_len >= 2 && !ctx) return MSCOMP_MEM_ERROR;
+
+    // Large streams: pipelined, chunk index built on the GPU.  Whatever that path does not cover comes back as
+    // MSC_FALLBACK and takes the simple path below.
+    static const size_t kPipeMin = env_bytes("MSCOMP_PIPE_MIN", (size_t)4 << 20), kPipeRange = env_bytes("MSCOMP_PIPE_RANGE", 0);
+    if (in_len >= kPipeMin && cap && ctx->copy_ready()) {
+        size_t range = kPipeRange;
+        if (!range) {                                            // about 8 ranges per call, 4..32 MiB each
+            range = in_len / 8;
+            if (range < ((size_t)4 << 20)) range = (size_t)4 << 20;
+            if (range > ((size_t)32 << 20)) range = (size_t)32 << 20;
+        }
+        const MSCompStatus pst = lznt1_decompress_pipelined(ctx, in, in_len, out, out_len, range);
+        if (pst != MSC_FALLBACK) return pst;
+        *out_len = cap;
+    }
+
+    // Simple path.  The upload of the stream starts first, on the copy stream, so that it overlaps with the header walk below.
     uint8_t* d_in = ctx ? (uint8_t*)ctx->get(SC_IN, in_len + 64) : nullptr;
     if (ctx && !d_in) return MSCOMP_MEM_ERROR;
     struct CopyGuard {          // the user's buffer must not be in use by a DMA once we return

@@ -13,10 +13,25 @@ mscomp_gpu_ctx* msc_thread_ctx();
 MSCompStatus msc_compact_slots(mscomp_gpu_ctx* ctx, const uint8_t* d_slots, uint64_t stride, const uint32_t* d_sizes,
                                uint32_t n, uint64_t* d_offs, uint8_t* d_dst);
 
+MSCompStatus msc_compact_slots_range(mscomp_gpu_ctx* ctx, const uint8_t* d_slots, uint64_t stride, const uint32_t* d_sizes,
+                                     uint32_t first, uint32_t n, uint64_t* d_offs, uint8_t* d_dst);
+
 // LZNT1 encoder over a slice of chunks (lets the host wrapper overlap uploads with encoding)
 MSCompStatus msc_lznt1_encode_chunks(mscomp_gpu_ctx* ctx, const uint8_t* d_in, size_t in_len, uint32_t first, uint32_t count,
                                      uint8_t* d_slots, uint32_t* d_sizes);
 constexpr size_t MSC_LZNT1_SLOT_BYTES = 4112;
+
+// LZNT1 chunk index built on the GPU (kernels/lznt1_index.cuh), range by range; layout == msc::Lznt1IndexState
+struct msc_lznt1_index_state { uint32_t entry, done, tail, next_entry; uint64_t ip, nchunks, range_chunks; };
+constexpr size_t MSC_LZNT1_INDEX_SEG = 65536;          // segment size of the index builder (ranges are multiples of it)
+extern "C" MSCompStatus msc_lznt1_index_count(mscomp_gpu_ctx* ctx, const uint8_t* d_in, size_t in_len, uint32_t seg0, uint32_t nseg,
+                                   int slot, msc_lznt1_index_state* d_state);
+extern "C" MSCompStatus msc_lznt1_index_write(mscomp_gpu_ctx* ctx, const uint8_t* d_in, size_t in_len, uint32_t seg0, uint32_t nseg,
+                                   int slot, uint64_t* d_offs);
+
+extern "C" MSCompStatus msc_lznt1_decode_chunks(mscomp_gpu_ctx* ctx, const uint8_t* d_in, size_t in_len, const uint64_t* d_chunk_off, uint32_t nchunks,
+                                                uint8_t* d_out, uint32_t* sizes, int32_t* status);
+extern "C" MSCompStatus msc_summarize_units(mscomp_gpu_ctx* ctx, const uint32_t* d_sizes, const int32_t* d_status, uint32_t n, uint32_t full_unit, mscomp_gpu_result* d_res);
 
 // reduce per-unit sizes / statuses into one mscomp_gpu_result (device)
 MSCompStatus msc_summarize(mscomp_gpu_ctx* ctx, const uint32_t* d_sizes, const int32_t* d_status, uint32_t n, mscomp_gpu_result* d_res);

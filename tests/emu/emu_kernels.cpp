@@ -3,6 +3,7 @@
 #include "simt_emu.h"
 #include "../../ms-compress_b200/csrc/kernels/lznt1_decode.cuh"
 #include "../../ms-compress_b200/csrc/kernels/lznt1_encode.cuh"
+#include "../../ms-compress_b200/csrc/kernels/lznt1_index.cuh"
 #include "../../ms-compress_b200/csrc/kernels/lznt1_decode_lanes.cuh"
 #include "../../ms-compress_b200/csrc/kernels/compact.cuh"
 #include "../../ms-compress_b200/csrc/kernels/xhuff_decode.cuh"
@@ -34,7 +35,7 @@ void emu_lznt1_encode(const uint8_t* in, uint64_t in_len, uint32_t nchunks, uint
                       uint64_t* offs, uint8_t* out, uint32_t grid, uint32_t heavy_work)
 {
     emu::launch(msc::lznt1_encode_kernel, dim3e(grid), dim3e(msc::LZE_THREADS), in, in_len, 0u, nchunks, slots, slot_size, heavy_work);
-    emu::launch(msc::scan_sizes_kernel, dim3e(1), dim3e(msc::SCAN_THREADS), (const uint32_t*)slot_size, nchunks, (uint64_t)0, offs);
+    emu::launch(msc::scan_sizes_kernel, dim3e(1), dim3e(msc::SCAN_THREADS), (const uint32_t*)slot_size, nchunks, (uint64_t)0, (const uint64_t*)nullptr, offs);
     emu::launch(msc::gather_slots_kernel, dim3e(grid), dim3e(256), (const uint8_t*)slots, (uint64_t)msc::LZNT1_SLOT,
                 (const uint32_t*)slot_size, (const uint64_t*)offs, nchunks, out);
 }
@@ -87,6 +88,31 @@ void emu_xpress_decode2(const uint8_t* in, uint8_t* out, uint32_t count, const u
     std::vector<uint32_t> tok(emu_extent(count, out_off, out_cap) + 16), ntok(count + 1);
     emu::launch(msc::xpress_parse_kernel, dim3e(grid), dim3e(32 * msc::XPD_WARPS_PER_BLOCK), in, tok.data(), count, in_off, in_len, out_off, out_cap, out_len, status, ntok.data());
     emu::launch(msc::lz_apply_kernel, dim3e(grid), dim3e(32 * msc::LZA_WARPS_PER_BLOCK), (const uint32_t*)tok.data(), (const uint32_t*)ntok.data(), out_off, (const int32_t*)status, count, out);
+}
+
+// Chunk index of an LZNT1 stream, built range by range (range_segs segments at a time) like the pipelined host wrapper does.
+// state_out = {done, tail, ip, nchunks}; returns 0, or 1 when more than cap chunks were found.
+int emu_lznt1_index(const uint8_t* in, uint64_t in_len, uint32_t S, uint32_t range_segs, uint64_t* offs, uint64_t cap, uint64_t* state_out)
+{
+    using namespace msc;
+    const uint64_t ns64 = in_len ? (in_len + S - 1) / S : 1;
+    const uint32_t NS = (uint32_t)ns64;
+    Lznt1IndexState st;
+    memset(&st, 0, sizeof(st));
+    for (uint32_t seg0 = 0; seg0 < NS; seg0 += range_segs) {
+        const uint32_t nseg = std::min(range_segs, NS - seg0), ng = (nseg + LZI_GROUP - 1) / LZI_GROUP;
+        std::vector<uint16_t> T1((size_t)nseg * LZI_STRIDE), T2((size_t)ng * LZI_STRIDE), seg_entry(nseg), grp_entry(ng);
+        std::vector<uint32_t> seg_base(nseg);
+        emu::launch(lznt1_index_tables_kernel, dim3e(std::min(nseg, 3u)), dim3e(LZI_THREADS), in, in_len, seg0, nseg, S, T1.data());
+        emu::launch(lznt1_index_compose_kernel, dim3e(ng), dim3e(LZI_THREADS), (const uint16_t*)T1.data(), nseg, T2.data());
+        emu::launch(lznt1_index_entries_kernel, dim3e(1), dim3e(256), (const uint16_t*)T1.data(), (const uint16_t*)T2.data(), nseg, &st, seg_entry.data(), grp_entry.data());
+        emu::launch(lznt1_index_count_kernel, dim3e(1), dim3e(LZI_THREADS), in, in_len, seg0, nseg, S, (const uint16_t*)seg_entry.data(), seg_base.data(), &st);
+        if (st.nchunks > cap) return 1;
+        emu::launch(lznt1_index_write_kernel, dim3e(2), dim3e(256), in, in_len, seg0, nseg, S, (const uint16_t*)seg_entry.data(), (const uint32_t*)seg_base.data(),
+                    offs + (st.nchunks - st.range_chunks));
+    }
+    state_out[0] = st.done; state_out[1] = st.tail; state_out[2] = st.ip; state_out[3] = st.nchunks;
+    return 0;
 }
 
 }
