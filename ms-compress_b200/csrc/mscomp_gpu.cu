@@ -163,12 +163,20 @@ static_assert(sizeof(Lznt1IndexState) == sizeof(msc_lznt1_index_state), "index s
 
 // Steps 1-4 for segments [seg0, seg0 + nseg) of the stream: d_state is updated (chunks of the range, how the chain
 // ended).  The per-segment entries / chunk numbers stay in scratch slot `slot` (0 or 1) for the matching _write call.
-MSCompStatus msc_lznt1_index_count(mscomp_gpu_ctx* ctx, const uint8_t* d_in, size_t in_len, uint32_t seg0, uint32_t nseg,
+// Bytes of one scratch slot (seg_base u32 | seg_entry u16 | grp_entry u16) for ranges of up to nseg_cap segments.
+static size_t lzi_slot_bytes(uint32_t nseg_cap)
+{
+    const size_t ng = (nseg_cap + LZI_GROUP - 1) / LZI_GROUP;
+    return (((size_t)nseg_cap * 6 + ng * 2) + 255) / 256 * 256;
+}
+
+MSCompStatus msc_lznt1_index_count(mscomp_gpu_ctx* ctx, const uint8_t* d_in, size_t in_len, uint32_t seg0, uint32_t nseg, uint32_t nseg_cap,
                                    int slot, msc_lznt1_index_state* d_state)
 {
+    if (nseg > nseg_cap) return MSCOMP_ARG_ERROR;
     const uint32_t S = LZI_SEG_BYTES, ng = (nseg + LZI_GROUP - 1) / LZI_GROUP;
     const size_t t_bytes = ((size_t)nseg + ng) * LZI_STRIDE * sizeof(uint16_t);
-    const size_t e_bytes = (((size_t)nseg * 6 + (size_t)ng * 2) + 255) / 256 * 256;       // seg_base u32 | seg_entry u16 | grp_entry u16
+    const size_t e_bytes = lzi_slot_bytes(nseg_cap);                                       // the slot layout must not depend on this range's size
     uint16_t* T1 = (uint16_t*)ctx->get(SC_AUX0, t_bytes + 64);
     uint8_t* e = (uint8_t*)ctx->get(SC_AUX1, 2 * e_bytes + 64);
     if (!T1 || !e) return MSCOMP_MEM_ERROR;
@@ -187,11 +195,11 @@ MSCompStatus msc_lznt1_index_count(mscomp_gpu_ctx* ctx, const uint8_t* d_in, siz
 }
 
 // Step 5: chunk offsets of the range into d_offs[0 .. range_chunks) (the caller passes the position of the range's first chunk).
-MSCompStatus msc_lznt1_index_write(mscomp_gpu_ctx* ctx, const uint8_t* d_in, size_t in_len, uint32_t seg0, uint32_t nseg,
+MSCompStatus msc_lznt1_index_write(mscomp_gpu_ctx* ctx, const uint8_t* d_in, size_t in_len, uint32_t seg0, uint32_t nseg, uint32_t nseg_cap,
                                    int slot, uint64_t* d_offs)
 {
-    const uint32_t S = LZI_SEG_BYTES, ng = (nseg + LZI_GROUP - 1) / LZI_GROUP;
-    const size_t e_bytes = (((size_t)nseg * 6 + (size_t)ng * 2) + 255) / 256 * 256;
+    const uint32_t S = LZI_SEG_BYTES;
+    const size_t e_bytes = lzi_slot_bytes(nseg_cap);
     uint8_t* e = (uint8_t*)ctx->scratch[SC_AUX1];
     if (!e) return MSCOMP_ARG_ERROR;
     e += (size_t)(slot & 1) * e_bytes;
@@ -213,7 +221,7 @@ MSCompStatus mscomp_gpu_lznt1_index(mscomp_gpu_ctx* ctx, const uint8_t* d_in, si
     msc_lznt1_index_state* h_st = (msc_lznt1_index_state*)ctx->get_pinned(256);
     if (!d_st || !h_st) return MSCOMP_MEM_ERROR;
     cudaMemsetAsync(d_st, 0, sizeof(*d_st), ctx->stream);
-    MSCompStatus st = msc_lznt1_index_count(ctx, d_in, in_len, 0, (uint32_t)nseg64, 0, d_st);
+    MSCompStatus st = msc_lznt1_index_count(ctx, d_in, in_len, 0, (uint32_t)nseg64, (uint32_t)nseg64, 0, d_st);
     if (st != MSCOMP_OK) return st;
     cudaMemcpyAsync(h_st, d_st, sizeof(*h_st), cudaMemcpyDeviceToHost, ctx->stream);
     if ((st = msc_cuda_status(cudaStreamSynchronize(ctx->stream), "lznt1_index")) != MSCOMP_OK) return st;
@@ -223,7 +231,7 @@ MSCompStatus mscomp_gpu_lznt1_index(mscomp_gpu_ctx* ctx, const uint8_t* d_in, si
     h_result->reserved = 0;
     if (h_st->nchunks > chunk_cap) return MSCOMP_BUF_ERROR;
     if (h_st->nchunks) {
-        if ((st = msc_lznt1_index_write(ctx, d_in, in_len, 0, (uint32_t)nseg64, 0, d_chunk_off)) != MSCOMP_OK) return st;
+        if ((st = msc_lznt1_index_write(ctx, d_in, in_len, 0, (uint32_t)nseg64, (uint32_t)nseg64, 0, d_chunk_off)) != MSCOMP_OK) return st;
         st = msc_cuda_status(cudaStreamSynchronize(ctx->stream), "lznt1_index");
     }
     return st;

@@ -14,6 +14,7 @@
 #include "shim_common.h"
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <vector>
 
 // ---- per-thread default context -------------------------------------------------------------------------------
@@ -167,6 +168,10 @@ MSCompStatus lznt1_replay(size_t nchunks, size_t cap, Lznt1Tail tail, FS size_of
 }
 } // namespace
 
+static unsigned long long g_pipeline_fallbacks = 0;
+// Diagnostic (not part of the reference ABI): how often the pipelined lznt1_decompress handed a stream to the simple path.
+extern "C" MSCOMPAPI unsigned long long msc_pipeline_fallbacks(void) { return g_pipeline_fallbacks; }
+
 namespace {
 constexpr MSCompStatus MSC_FALLBACK = (MSCompStatus)1000;    // internal: "take the simple path"
 
@@ -206,15 +211,25 @@ MSCompStatus lznt1_decompress_pipelined(mscomp_gpu_ctx* ctx, const_bytes in, siz
     cudaStreamWaitEvent(ctx->down_stream, ctx->copy_ev[15], 0);
     cudaMemsetAsync(d_state, 0, sizeof(*d_state), ctx->stream);
 
+    static const bool trace = getenv("MSCOMP_TRACE") != nullptr;  // host-side timeline of the pipeline on stderr
+    struct timespec ts0;
+    clock_gettime(CLOCK_MONOTONIC, &ts0);
+    auto tr = [&](const char* what, size_t k) {
+        if (!trace) return;
+        struct timespec t;
+        clock_gettime(CLOCK_MONOTONIC, &t);
+        fprintf(stderr, "[lznt1_decompress] %8.1f us  %s %zu\n", (t.tv_sec - ts0.tv_sec) * 1e6 + (t.tv_nsec - ts0.tv_nsec) * 1e-3, what, k);
+    };
     MSCompStatus st = MSCOMP_OK;
     auto stage_in = [&](size_t k) -> MSCompStatus {              // upload range k, then count its chunks
+        tr("in", k);
         const size_t off = k * R;
         size_t len = in_len - off < R + kOverlap ? in_len - off : R + kOverlap;
         cudaMemcpyAsync(d_in + off, in + off, len, cudaMemcpyHostToDevice, ctx->copy_stream);
         cudaEventRecord(ctx->copy_ev[k % 15], ctx->copy_stream);
         cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[k % 15], 0);
         const size_t bytes = in_len - off < R ? in_len - off : R;
-        MSCompStatus s2 = msc_lznt1_index_count(ctx, d_in, in_len, (uint32_t)(off / S), (uint32_t)((bytes + S - 1) / S), (int)(k & 1), d_state);
+        MSCompStatus s2 = msc_lznt1_index_count(ctx, d_in, in_len, (uint32_t)(off / S), (uint32_t)((bytes + S - 1) / S), (uint32_t)(R / S), (int)(k & 1), d_state);
         if (s2 != MSCOMP_OK) return s2;
         cudaMemcpyAsync(h_state(k), d_state, sizeof(msc_lznt1_index_state), cudaMemcpyDeviceToHost, ctx->stream);
         cudaEventRecord(ctx->work_ev[(2 * k) % 16], ctx->stream);
@@ -224,8 +239,10 @@ MSCompStatus lznt1_decompress_pipelined(mscomp_gpu_ctx* ctx, const_bytes in, siz
     std::vector<Range> rg(nranges);
     bool seen_end = false;
     auto stage_decode = [&](size_t k) -> MSCompStatus {          // chunk offsets, decode, summary of range k
+        tr("wait-count", k);
         MSCompStatus s2 = msc_cuda_status(cudaEventSynchronize(ctx->work_ev[(2 * k) % 16]), "lznt1_decompress");
         if (s2 != MSCOMP_OK) return s2;
+        tr("counted", k);
         const msc_lznt1_index_state hs = *h_state(k);
         if (hs.nchunks > ncap) return MSC_FALLBACK;
         rg[k].n = (size_t)hs.range_chunks;
@@ -234,7 +251,7 @@ MSCompStatus lznt1_decompress_pipelined(mscomp_gpu_ctx* ctx, const_bytes in, siz
         if (hs.done) seen_end = true;
         if (rg[k].n) {
             const size_t off = k * R, bytes = in_len - off < R ? in_len - off : R;
-            if ((s2 = msc_lznt1_index_write(ctx, d_in, in_len, (uint32_t)(off / S), (uint32_t)((bytes + S - 1) / S), (int)(k & 1), d_offs + rg[k].c0)) != MSCOMP_OK) return s2;
+            if ((s2 = msc_lznt1_index_write(ctx, d_in, in_len, (uint32_t)(off / S), (uint32_t)((bytes + S - 1) / S), (uint32_t)(R / S), (int)(k & 1), d_offs + rg[k].c0)) != MSCOMP_OK) return s2;
             if ((s2 = msc_lznt1_decode_chunks(ctx, d_in, in_len, d_offs + rg[k].c0, (uint32_t)rg[k].n, d_out + rg[k].c0 * 4096,
                                               d_sizes + rg[k].c0, d_status + rg[k].c0)) != MSCOMP_OK) return s2;
             if ((s2 = msc_summarize_units(ctx, d_sizes + rg[k].c0, d_status + rg[k].c0, (uint32_t)rg[k].n, 4096, d_sum + (k % 8))) != MSCOMP_OK) return s2;
@@ -245,7 +262,9 @@ MSCompStatus lznt1_decompress_pipelined(mscomp_gpu_ctx* ctx, const_bytes in, siz
     };
     size_t total = 0, last_size = 4096;
     auto stage_out = [&](size_t k) -> MSCompStatus {             // range k is decoded: check it, ship its bytes
+        tr("wait-decode", k);
         MSCompStatus s2 = msc_cuda_status(cudaEventSynchronize(ctx->work_ev[(2 * k + 1) % 16]), "lznt1_decompress");
+        tr("decoded", k);
         if (s2 != MSCOMP_OK || !rg[k].n) return s2;
         const mscomp_gpu_result r = *h_sum(k);
         if (r.status != 0 || r.short_units != 0) return MSC_FALLBACK;
@@ -266,7 +285,9 @@ MSCompStatus lznt1_decompress_pipelined(mscomp_gpu_ctx* ctx, const_bytes in, siz
     }
     if (st == MSCOMP_OK) st = stage_out(nranges - 1);
     if (st != MSCOMP_OK) return st;                              // (the guard drains the streams)
+    tr("wait-downloads", nranges);
     if ((st = msc_cuda_status(cudaStreamSynchronize(ctx->down_stream), "lznt1_decompress")) != MSCOMP_OK) return st;
+    tr("done", nranges);
     const msc_lznt1_index_state fin = *h_state(nranges - 1);
     if (!fin.done || fin.nchunks == 0) return MSC_FALLBACK;
     const size_t nchunks = (size_t)fin.nchunks;
@@ -298,6 +319,7 @@ extern "C" MSCompStatus lznt1_decompress(const_bytes in, size_t in_len, bytes ou
         }
         const MSCompStatus pst = lznt1_decompress_pipelined(ctx, in, in_len, out, out_len, range);
         if (pst != MSC_FALLBACK) return pst;
+        __atomic_fetch_add(&g_pipeline_fallbacks, 1ull, __ATOMIC_RELAXED);
         *out_len = cap;
     }
 

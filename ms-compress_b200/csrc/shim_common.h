@@ -24,10 +24,11 @@ constexpr size_t MSC_LZNT1_SLOT_BYTES = 4112;
 // LZNT1 chunk index built on the GPU (kernels/lznt1_index.cuh), range by range; layout == msc::Lznt1IndexState
 struct msc_lznt1_index_state { uint32_t entry, done, tail, next_entry; uint64_t ip, nchunks, range_chunks; };
 constexpr size_t MSC_LZNT1_INDEX_SEG = 65536;          // segment size of the index builder (ranges are multiples of it)
-extern "C" MSCompStatus msc_lznt1_index_count(mscomp_gpu_ctx* ctx, const uint8_t* d_in, size_t in_len, uint32_t seg0, uint32_t nseg,
-                                   int slot, msc_lznt1_index_state* d_state);
-extern "C" MSCompStatus msc_lznt1_index_write(mscomp_gpu_ctx* ctx, const uint8_t* d_in, size_t in_len, uint32_t seg0, uint32_t nseg,
-                                   int slot, uint64_t* d_offs);
+// nseg_cap = the largest range of the pipeline (fixes the layout of the two scratch slots)
+extern "C" MSCompStatus msc_lznt1_index_count(mscomp_gpu_ctx* ctx, const uint8_t* d_in, size_t in_len, uint32_t seg0, uint32_t nseg, uint32_t nseg_cap,
+                                              int slot, msc_lznt1_index_state* d_state);
+extern "C" MSCompStatus msc_lznt1_index_write(mscomp_gpu_ctx* ctx, const uint8_t* d_in, size_t in_len, uint32_t seg0, uint32_t nseg, uint32_t nseg_cap,
+                                              int slot, uint64_t* d_offs);
 
 extern "C" MSCompStatus msc_lznt1_decode_chunks(mscomp_gpu_ctx* ctx, const uint8_t* d_in, size_t in_len, const uint64_t* d_chunk_off, uint32_t nchunks,
                                                 uint8_t* d_out, uint32_t* sizes, int32_t* status);

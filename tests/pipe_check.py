@@ -18,6 +18,12 @@ rnd = random.Random(21)
 checked = 0
 
 
+import ctypes  # noqa: E402
+
+fallbacks = ms.lib().msc_pipeline_fallbacks
+fallbacks.restype = ctypes.c_ulonglong
+
+
 def same(src, cap):
     global checked
     got, want = ms.raw_call("lznt1_decompress", src, cap), oracle.decompress("lznt1", src, cap)
@@ -31,7 +37,11 @@ for kind, n in (("text", 3 << 20), ("random", (1 << 20) + 77), ("runs", 2 << 20)
     assert ms.raw_call("lznt1_compress", plain, MAXSZ["lznt1"](n)) == (0, comp), ("compress", kind, n)
     assert ms.raw_call("lznt1_compress", plain, len(comp)) == (0, comp)
     assert ms.raw_call("lznt1_compress", plain, len(comp) - 1)[0] == oracle.call("lznt1_compress", plain, len(comp) - 1)[0]
-    for cap in (n, n + 1, n + 5000, n - 1, n // 2, 4 * n):
+    f0 = fallbacks()
+    for cap in (n, n + 1, n + 5000, 4 * n):
+        same(comp, cap)
+    assert fallbacks() == f0, "a well-formed stream must stay on the pipelined path"
+    for cap in (n - 1, n // 2):
         same(comp, cap)
     for tail in (b"\0", b"\x55", b"\0\0", b"\0\0\x01", b"\0" * 9):
         same(comp + tail, n)
