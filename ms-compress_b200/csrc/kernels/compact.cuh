@@ -14,7 +14,8 @@ constexpr int SCAN_THREADS = 1024;
 // base_ptr (may be null) adds a device-resident base: the end offset of the previous slice when a stream is compacted
 // slice by slice.
 __global__ void __launch_bounds__(SCAN_THREADS)
-scan_sizes_kernel(const uint32_t* __restrict__ sizes, uint32_t n, uint64_t base, const uint64_t* base_ptr, uint64_t* __restrict__ offs)
+scan_sizes_kernel(const uint32_t* __restrict__ sizes, uint32_t n, uint64_t base, const uint64_t* base_ptr, uint64_t* __restrict__ offs,
+                  uint64_t* total_mirror)   // optional copy of offs[n] in mapped host memory
 {
     __shared__ uint64_t wsum[32];
     __shared__ uint64_t carry;
@@ -40,7 +41,7 @@ scan_sizes_kernel(const uint32_t* __restrict__ sizes, uint32_t n, uint64_t base,
         if (tid == SCAN_THREADS - 1) carry = run;
         __syncthreads();
     }
-    if (tid == 0) offs[n] = carry;
+    if (tid == 0) { offs[n] = carry; if (total_mirror) { *total_mirror = carry; __threadfence_system(); } }
 }
 
 // One warp per unit: dst[offs[u] .. +sizes[u]) = slots[u*stride .. +sizes[u])

@@ -156,8 +156,9 @@ __device__ __forceinline__ uint32_t lzi_walk_segment(const uint8_t* __restrict__
 // ---- 4: chunks per segment, first chunk number of every segment, end of the chain (single block) -----------------------------
 __global__ void __launch_bounds__(LZI_THREADS)
 lznt1_index_count_kernel(const uint8_t* __restrict__ in, uint64_t in_len, uint32_t seg0, uint32_t nseg, uint32_t S,
-                         const uint16_t* __restrict__ seg_entry, uint32_t* __restrict__ seg_base, Lznt1IndexState* __restrict__ st)
-{
+                         const uint16_t* __restrict__ seg_entry, uint32_t* __restrict__ seg_base, Lznt1IndexState* __restrict__ st,
+                         Lznt1IndexState* mirror)   // optional copy of the state in mapped host memory (saves a device-to-host memcpy
+{                                                   // that would queue behind the bulk downloads on the copy engine)
     __shared__ uint32_t wsum[32];
     __shared__ uint32_t carry;
     const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -185,6 +186,7 @@ lznt1_index_count_kernel(const uint8_t* __restrict__ in, uint64_t in_len, uint32
         st->range_chunks = carry;
         st->nchunks += carry;
         st->entry = st->next_entry;
+        if (mirror) { *mirror = *st; __threadfence_system(); }
     }
 }
 

@@ -22,9 +22,9 @@ static_assert(sizeof(GpuResult) == sizeof(mscomp_gpu_result), "result layout");
 // Units [first, first + n) of a slot array: offsets continue from d_offs[first] (written by the previous range; 0 when
 // first == 0), the bytes go to their final place in d_dst.  A whole array is the range (0, n).
 MSCompStatus msc_compact_slots_range(mscomp_gpu_ctx* ctx, const uint8_t* d_slots, uint64_t stride, const uint32_t* d_sizes,
-                                     uint32_t first, uint32_t n, uint64_t* d_offs, uint8_t* d_dst)
+                                     uint32_t first, uint32_t n, uint64_t* d_offs, uint8_t* d_dst, uint64_t* h_end)
 {
-    MSC_LAUNCH(ctx, scan_sizes_kernel, 1, SCAN_THREADS, d_sizes + first, n, (uint64_t)0, first ? (const uint64_t*)(d_offs + first) : nullptr, d_offs + first);
+    MSC_LAUNCH(ctx, scan_sizes_kernel, 1, SCAN_THREADS, d_sizes + first, n, (uint64_t)0, first ? (const uint64_t*)(d_offs + first) : nullptr, d_offs + first, h_end);
     if (n) {
         const uint32_t gw = (n + 7) / 8;
         const uint32_t grid = gw < (uint32_t)ctx->sm_count * 8 ? gw : (uint32_t)ctx->sm_count * 8;
@@ -36,7 +36,7 @@ MSCompStatus msc_compact_slots_range(mscomp_gpu_ctx* ctx, const uint8_t* d_slots
 MSCompStatus msc_compact_slots(mscomp_gpu_ctx* ctx, const uint8_t* d_slots, uint64_t stride, const uint32_t* d_sizes,
                                uint32_t n, uint64_t* d_offs, uint8_t* d_dst)
 {
-    return msc_compact_slots_range(ctx, d_slots, stride, d_sizes, 0, n, d_offs, d_dst);
+    return msc_compact_slots_range(ctx, d_slots, stride, d_sizes, 0, n, d_offs, d_dst, nullptr);
 }
 
 // Encode chunks [first, first+count) of the stream d_in[0..in_len) into their slots (one 256-thread block per chunk).
@@ -162,7 +162,9 @@ MSCompStatus mscomp_gpu_lznt1_compress(mscomp_gpu_ctx* ctx, const uint8_t* d_in,
 static_assert(sizeof(Lznt1IndexState) == sizeof(msc_lznt1_index_state), "index state layout");
 
 // Steps 1-4 for segments [seg0, seg0 + nseg) of the stream: d_state is updated (chunks of the range, how the chain
-// ended).  The per-segment entries / chunk numbers stay in scratch slot `slot` (0 or 1) for the matching _write call.
+// ended).  The per-segment entries / chunk numbers stay in scratch slot `slot` (0..7) for the matching _write call;
+// h_mirror (may be null): mapped host memory that receives a copy of the state.
+constexpr int LZI_SLOTS = 8;          // ranges whose count may be pending between _count and _write
 // Bytes of one scratch slot (seg_base u32 | seg_entry u16 | grp_entry u16) for ranges of up to nseg_cap segments.
 static size_t lzi_slot_bytes(uint32_t nseg_cap)
 {
@@ -171,17 +173,17 @@ static size_t lzi_slot_bytes(uint32_t nseg_cap)
 }
 
 MSCompStatus msc_lznt1_index_count(mscomp_gpu_ctx* ctx, const uint8_t* d_in, size_t in_len, uint32_t seg0, uint32_t nseg, uint32_t nseg_cap,
-                                   int slot, msc_lznt1_index_state* d_state)
+                                   int slot, msc_lznt1_index_state* d_state, msc_lznt1_index_state* h_mirror)
 {
     if (nseg > nseg_cap) return MSCOMP_ARG_ERROR;
     const uint32_t S = LZI_SEG_BYTES, ng = (nseg + LZI_GROUP - 1) / LZI_GROUP;
     const size_t t_bytes = ((size_t)nseg + ng) * LZI_STRIDE * sizeof(uint16_t);
     const size_t e_bytes = lzi_slot_bytes(nseg_cap);                                       // the slot layout must not depend on this range's size
     uint16_t* T1 = (uint16_t*)ctx->get(SC_AUX0, t_bytes + 64);
-    uint8_t* e = (uint8_t*)ctx->get(SC_AUX1, 2 * e_bytes + 64);
+    uint8_t* e = (uint8_t*)ctx->get(SC_AUX1, LZI_SLOTS * e_bytes + 64);
     if (!T1 || !e) return MSCOMP_MEM_ERROR;
     uint16_t* T2 = T1 + (size_t)nseg * LZI_STRIDE;
-    e += (size_t)(slot & 1) * e_bytes;
+    e += (size_t)(slot % LZI_SLOTS) * e_bytes;
     uint32_t* seg_base = (uint32_t*)e;
     uint16_t* seg_entry = (uint16_t*)(seg_base + nseg);
     uint16_t* grp_entry = seg_entry + nseg;
@@ -190,7 +192,7 @@ MSCompStatus msc_lznt1_index_count(mscomp_gpu_ctx* ctx, const uint8_t* d_in, siz
     MSC_LAUNCH_SMEM(ctx, lznt1_index_tables_kernel, grid, LZI_THREADS, S + 16, d_in, (uint64_t)in_len, seg0, nseg, S, T1);
     MSC_LAUNCH(ctx, lznt1_index_compose_kernel, ng, LZI_THREADS, (const uint16_t*)T1, nseg, T2);
     MSC_LAUNCH(ctx, lznt1_index_entries_kernel, 1, 256, (const uint16_t*)T1, (const uint16_t*)T2, nseg, (Lznt1IndexState*)d_state, seg_entry, grp_entry);
-    MSC_LAUNCH(ctx, lznt1_index_count_kernel, 1, LZI_THREADS, d_in, (uint64_t)in_len, seg0, nseg, S, (const uint16_t*)seg_entry, seg_base, (Lznt1IndexState*)d_state);
+    MSC_LAUNCH(ctx, lznt1_index_count_kernel, 1, LZI_THREADS, d_in, (uint64_t)in_len, seg0, nseg, S, (const uint16_t*)seg_entry, seg_base, (Lznt1IndexState*)d_state, (Lznt1IndexState*)h_mirror);
     return msc_cuda_status(cudaGetLastError(), "lznt1_index");
 }
 
@@ -202,7 +204,7 @@ MSCompStatus msc_lznt1_index_write(mscomp_gpu_ctx* ctx, const uint8_t* d_in, siz
     const size_t e_bytes = lzi_slot_bytes(nseg_cap);
     uint8_t* e = (uint8_t*)ctx->scratch[SC_AUX1];
     if (!e) return MSCOMP_ARG_ERROR;
-    e += (size_t)(slot & 1) * e_bytes;
+    e += (size_t)(slot % LZI_SLOTS) * e_bytes;
     const uint32_t* seg_base = (const uint32_t*)e;
     const uint16_t* seg_entry = (const uint16_t*)(seg_base + nseg);
     const uint32_t grid = (nseg + 255) / 256;
@@ -221,7 +223,7 @@ MSCompStatus mscomp_gpu_lznt1_index(mscomp_gpu_ctx* ctx, const uint8_t* d_in, si
     msc_lznt1_index_state* h_st = (msc_lznt1_index_state*)ctx->get_pinned(256);
     if (!d_st || !h_st) return MSCOMP_MEM_ERROR;
     cudaMemsetAsync(d_st, 0, sizeof(*d_st), ctx->stream);
-    MSCompStatus st = msc_lznt1_index_count(ctx, d_in, in_len, 0, (uint32_t)nseg64, (uint32_t)nseg64, 0, d_st);
+    MSCompStatus st = msc_lznt1_index_count(ctx, d_in, in_len, 0, (uint32_t)nseg64, (uint32_t)nseg64, 0, d_st, nullptr);
     if (st != MSCOMP_OK) return st;
     cudaMemcpyAsync(h_st, d_st, sizeof(*h_st), cudaMemcpyDeviceToHost, ctx->stream);
     if ((st = msc_cuda_status(cudaStreamSynchronize(ctx->stream), "lznt1_index")) != MSCOMP_OK) return st;

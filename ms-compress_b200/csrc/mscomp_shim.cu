@@ -111,8 +111,9 @@ extern "C" MSCompStatus lznt1_compress(const_bytes in, size_t in_len, bytes out,
             cudaEventRecord(ev, ctx->copy_stream);
             cudaStreamWaitEvent(ctx->stream, ev, 0);
             if ((st = msc_lznt1_encode_chunks(ctx, d_in, in_len, first, cnt, d_slots, d_sizes)) != MSCOMP_OK) return st;
-            if ((st = msc_compact_slots_range(ctx, d_slots, MSC_LZNT1_SLOT_BYTES, d_sizes, first, cnt, d_offs, d_out)) != MSCOMP_OK) return st;
-            cudaMemcpyAsync(&h_end[k % 15], d_offs + first + cnt, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+            // (the running end offset goes straight into the pinned mailbox: a small device-to-host memcpy here would
+            // queue behind the bulk downloads on the copy engine and stall this stream)
+            if ((st = msc_compact_slots_range(ctx, d_slots, MSC_LZNT1_SLOT_BYTES, d_sizes, first, cnt, d_offs, d_out, &h_end[k % 15])) != MSCOMP_OK) return st;
             cudaEventRecord(ctx->work_ev[k % 15], ctx->stream);
             if (k >= 1 && (st = download(k - 1)) != MSCOMP_OK) return st;   // one slice behind: the GPU always has slice k queued
         }
@@ -200,7 +201,6 @@ MSCompStatus lznt1_decompress_pipelined(mscomp_gpu_ctx* ctx, const_bytes in, siz
     uint8_t* h_box = (uint8_t*)ctx->get_pinned(4096);            // per-range copies of the state at +256, of the summaries at +2048
     if (!d_in || !d_out || !d_offs || !d_sizes || !d_status || !d_box || !h_box) return MSCOMP_MEM_ERROR;
     msc_lznt1_index_state* d_state = (msc_lznt1_index_state*)d_box;
-    mscomp_gpu_result* d_sum = (mscomp_gpu_result*)(d_box + 256);
     auto h_state = [&](size_t k) { return (msc_lznt1_index_state*)(h_box + 256 + 64 * (k % 8)); };
     auto h_sum = [&](size_t k) { return (mscomp_gpu_result*)(h_box + 2048 + 64 * (k % 8)); };
 
@@ -229,9 +229,9 @@ MSCompStatus lznt1_decompress_pipelined(mscomp_gpu_ctx* ctx, const_bytes in, siz
         cudaEventRecord(ctx->copy_ev[k % 15], ctx->copy_stream);
         cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[k % 15], 0);
         const size_t bytes = in_len - off < R ? in_len - off : R;
-        MSCompStatus s2 = msc_lznt1_index_count(ctx, d_in, in_len, (uint32_t)(off / S), (uint32_t)((bytes + S - 1) / S), (uint32_t)(R / S), (int)(k & 1), d_state);
-        if (s2 != MSCOMP_OK) return s2;
-        cudaMemcpyAsync(h_state(k), d_state, sizeof(msc_lznt1_index_state), cudaMemcpyDeviceToHost, ctx->stream);
+        MSCompStatus s2 = msc_lznt1_index_count(ctx, d_in, in_len, (uint32_t)(off / S), (uint32_t)((bytes + S - 1) / S), (uint32_t)(R / S), (int)(k % 8), d_state, h_state(k));
+        if (s2 != MSCOMP_OK) return s2;               // (state and summaries are written to the pinned mailbox by the kernels themselves:
+                                                      // small device-to-host memcpys would queue behind the bulk downloads on the copy engine)
         cudaEventRecord(ctx->work_ev[(2 * k) % 16], ctx->stream);
         return MSCOMP_OK;
     };
@@ -251,11 +251,10 @@ MSCompStatus lznt1_decompress_pipelined(mscomp_gpu_ctx* ctx, const_bytes in, siz
         if (hs.done) seen_end = true;
         if (rg[k].n) {
             const size_t off = k * R, bytes = in_len - off < R ? in_len - off : R;
-            if ((s2 = msc_lznt1_index_write(ctx, d_in, in_len, (uint32_t)(off / S), (uint32_t)((bytes + S - 1) / S), (uint32_t)(R / S), (int)(k & 1), d_offs + rg[k].c0)) != MSCOMP_OK) return s2;
+            if ((s2 = msc_lznt1_index_write(ctx, d_in, in_len, (uint32_t)(off / S), (uint32_t)((bytes + S - 1) / S), (uint32_t)(R / S), (int)(k % 8), d_offs + rg[k].c0)) != MSCOMP_OK) return s2;
             if ((s2 = msc_lznt1_decode_chunks(ctx, d_in, in_len, d_offs + rg[k].c0, (uint32_t)rg[k].n, d_out + rg[k].c0 * 4096,
                                               d_sizes + rg[k].c0, d_status + rg[k].c0)) != MSCOMP_OK) return s2;
-            if ((s2 = msc_summarize_units(ctx, d_sizes + rg[k].c0, d_status + rg[k].c0, (uint32_t)rg[k].n, 4096, d_sum + (k % 8))) != MSCOMP_OK) return s2;
-            cudaMemcpyAsync(h_sum(k), d_sum + (k % 8), sizeof(mscomp_gpu_result), cudaMemcpyDeviceToHost, ctx->stream);
+            if ((s2 = msc_summarize_units(ctx, d_sizes + rg[k].c0, d_status + rg[k].c0, (uint32_t)rg[k].n, 4096, h_sum(k))) != MSCOMP_OK) return s2;
         }
         cudaEventRecord(ctx->work_ev[(2 * k + 1) % 16], ctx->stream);
         return MSCOMP_OK;
@@ -277,9 +276,12 @@ MSCompStatus lznt1_decompress_pipelined(mscomp_gpu_ctx* ctx, const_bytes in, siz
         return MSCOMP_OK;
     };
 
-    if ((st = stage_in(0)) != MSCOMP_OK) return st;
+    // uploads and chunk counts run `ahead` ranges in front of the decoder, so the copy engine never waits for the host
+    static const size_t kAheadEnv = env_bytes("MSCOMP_PIPE_AHEAD", 1);
+    const size_t ahead = kAheadEnv < 1 ? 1 : (kAheadEnv > 6 ? 6 : kAheadEnv);
+    for (size_t k = 0; k < ahead && k < nranges && st == MSCOMP_OK; ++k) st = stage_in(k);
     for (size_t k = 0; k < nranges && st == MSCOMP_OK; ++k) {
-        if (k + 1 < nranges) st = stage_in(k + 1);               // keep the GPU one range ahead of the host
+        if (k + ahead < nranges) st = stage_in(k + ahead);
         if (st == MSCOMP_OK) st = stage_decode(k);
         if (st == MSCOMP_OK && k >= 1) st = stage_out(k - 1);
     }

@@ -14,7 +14,7 @@ MSCompStatus msc_compact_slots(mscomp_gpu_ctx* ctx, const uint8_t* d_slots, uint
                                uint32_t n, uint64_t* d_offs, uint8_t* d_dst);
 
 MSCompStatus msc_compact_slots_range(mscomp_gpu_ctx* ctx, const uint8_t* d_slots, uint64_t stride, const uint32_t* d_sizes,
-                                     uint32_t first, uint32_t n, uint64_t* d_offs, uint8_t* d_dst);
+                                     uint32_t first, uint32_t n, uint64_t* d_offs, uint8_t* d_dst, uint64_t* h_end);
 
 // LZNT1 encoder over a slice of chunks (lets the host wrapper overlap uploads with encoding)
 MSCompStatus msc_lznt1_encode_chunks(mscomp_gpu_ctx* ctx, const uint8_t* d_in, size_t in_len, uint32_t first, uint32_t count,
@@ -26,7 +26,7 @@ struct msc_lznt1_index_state { uint32_t entry, done, tail, next_entry; uint64_t 
 constexpr size_t MSC_LZNT1_INDEX_SEG = 65536;          // segment size of the index builder (ranges are multiples of it)
 // nseg_cap = the largest range of the pipeline (fixes the layout of the two scratch slots)
 extern "C" MSCompStatus msc_lznt1_index_count(mscomp_gpu_ctx* ctx, const uint8_t* d_in, size_t in_len, uint32_t seg0, uint32_t nseg, uint32_t nseg_cap,
-                                              int slot, msc_lznt1_index_state* d_state);
+                                              int slot, msc_lznt1_index_state* d_state, msc_lznt1_index_state* h_mirror);
 extern "C" MSCompStatus msc_lznt1_index_write(mscomp_gpu_ctx* ctx, const uint8_t* d_in, size_t in_len, uint32_t seg0, uint32_t nseg, uint32_t nseg_cap,
                                               int slot, uint64_t* d_offs);
 

@@ -35,7 +35,7 @@ void emu_lznt1_encode(const uint8_t* in, uint64_t in_len, uint32_t nchunks, uint
                       uint64_t* offs, uint8_t* out, uint32_t grid, uint32_t heavy_work)
 {
     emu::launch(msc::lznt1_encode_kernel, dim3e(grid), dim3e(msc::LZE_THREADS), in, in_len, 0u, nchunks, slots, slot_size, heavy_work);
-    emu::launch(msc::scan_sizes_kernel, dim3e(1), dim3e(msc::SCAN_THREADS), (const uint32_t*)slot_size, nchunks, (uint64_t)0, (const uint64_t*)nullptr, offs);
+    emu::launch(msc::scan_sizes_kernel, dim3e(1), dim3e(msc::SCAN_THREADS), (const uint32_t*)slot_size, nchunks, (uint64_t)0, (const uint64_t*)nullptr, offs, (uint64_t*)nullptr);
     emu::launch(msc::gather_slots_kernel, dim3e(grid), dim3e(256), (const uint8_t*)slots, (uint64_t)msc::LZNT1_SLOT,
                 (const uint32_t*)slot_size, (const uint64_t*)offs, nchunks, out);
 }
@@ -106,7 +106,7 @@ int emu_lznt1_index(const uint8_t* in, uint64_t in_len, uint32_t S, uint32_t ran
         emu::launch(lznt1_index_tables_kernel, dim3e(std::min(nseg, 3u)), dim3e(LZI_THREADS), in, in_len, seg0, nseg, S, T1.data());
         emu::launch(lznt1_index_compose_kernel, dim3e(ng), dim3e(LZI_THREADS), (const uint16_t*)T1.data(), nseg, T2.data());
         emu::launch(lznt1_index_entries_kernel, dim3e(1), dim3e(256), (const uint16_t*)T1.data(), (const uint16_t*)T2.data(), nseg, &st, seg_entry.data(), grp_entry.data());
-        emu::launch(lznt1_index_count_kernel, dim3e(1), dim3e(LZI_THREADS), in, in_len, seg0, nseg, S, (const uint16_t*)seg_entry.data(), seg_base.data(), &st);
+        emu::launch(lznt1_index_count_kernel, dim3e(1), dim3e(LZI_THREADS), in, in_len, seg0, nseg, S, (const uint16_t*)seg_entry.data(), seg_base.data(), &st, (Lznt1IndexState*)nullptr);
         if (st.nchunks > cap) return 1;
         emu::launch(lznt1_index_write_kernel, dim3e(2), dim3e(256), in, in_len, seg0, nseg, S, (const uint16_t*)seg_entry.data(), (const uint32_t*)seg_base.data(),
                     offs + (st.nchunks - st.range_chunks));

@@ -167,6 +167,7 @@ inline void __syncwarp(unsigned mask = 0xffffffffu) { EMU_FULL(mask); emu::warp_
 inline void __syncthreads() { emu::block_rendezvous(); }
 inline void __threadfence() {}
 inline void __threadfence_block() {}
+inline void __threadfence_system() {}
 
 template <class T> inline T __shfl_sync(unsigned mask, T v, int src, int width = 32)
 { EMU_FULL(mask); (void)width; int me = emu::cur()->lane; uint64_t* s = emu::exchange(emu::to_bits(v)); int l = src & 31; return emu::from_bits<T>(l < emu::warp_lanes() ? s[l] : s[me]); }
