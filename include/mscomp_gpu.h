@@ -99,5 +99,26 @@ MSCOMPAPI MSCompStatus mscomp_gpu_xpress_compress_batch(mscomp_gpu_ctx* ctx, con
 MSCOMPAPI MSCompStatus mscomp_gpu_xpress_decompress_batch(mscomp_gpu_ctx* ctx, const uint8_t* d_in, uint8_t* d_out,
                                                           const mscomp_gpu_batch* batch);
 
+/* Plain Xpress is one unbroken stream per buffer (flag words and shared length nibbles chain every item to the previous
+ * ones), so a reference-made stream decodes on one GPU lane.  Streams made HERE can carry a side-band restart index --
+ * never part of the stream, the stream stays byte-for-byte what the call above produces -- with one entry per seg_bytes
+ * (a multiple of 2048) of input: the decoder state at an item boundary.  With it the decoder parses every segment on its own
+ * lane.  d_index holds index_stride entries per buffer (entry 0 carries the number of entries actually used; buffers with
+ * more segments than index_stride get longer last segments). */
+typedef struct mscomp_gpu_xpress_seg {
+    uint32_t in_pos;      /* compressed offset of the next byte to read */
+    uint32_t out_pos;     /* uncompressed position of the next item */
+    uint32_t flag_pos;    /* compressed offset of the flag word in force (when flag_used != 0) */
+    uint32_t flag_used;   /* items of that flag word already consumed, 0..31 */
+    uint32_t half_pos;    /* compressed offset of the byte whose high length nibble is still unused, 0xFFFFFFFF = none */
+    uint32_t nseg;        /* entry 0 only: entries of this buffer */
+} mscomp_gpu_xpress_seg;
+MSCOMPAPI MSCompStatus mscomp_gpu_xpress_compress_batch_indexed(mscomp_gpu_ctx* ctx, const uint8_t* d_in, uint8_t* d_out,
+                                                                const mscomp_gpu_batch* batch, uint32_t seg_bytes,
+                                                                mscomp_gpu_xpress_seg* d_index, uint32_t index_stride);
+MSCOMPAPI MSCompStatus mscomp_gpu_xpress_decompress_batch_indexed(mscomp_gpu_ctx* ctx, const uint8_t* d_in, uint8_t* d_out,
+                                                                  const mscomp_gpu_batch* batch,
+                                                                  const mscomp_gpu_xpress_seg* d_index, uint32_t index_stride);
+
 EXTERN_C_END
 #endif

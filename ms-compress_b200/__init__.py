@@ -89,6 +89,10 @@ def lib():
                     continue
                 f = getattr(L, "mscomp_gpu_%s_%s_batch" % (fmt, op))
                 f.restype, f.argtypes = i32, [vp, vp, vp, vp]
+        L.mscomp_gpu_xpress_compress_batch_indexed.restype = i32
+        L.mscomp_gpu_xpress_compress_batch_indexed.argtypes = [vp, vp, vp, vp, u32, vp, u32]
+        L.mscomp_gpu_xpress_decompress_batch_indexed.restype = i32
+        L.mscomp_gpu_xpress_decompress_batch_indexed.argtypes = [vp, vp, vp, vp, vp, u32]
         _lib = L
     return _lib
 
@@ -296,6 +300,26 @@ class GpuContext:
         st = f(self.handle, d_in.data_ptr(), d_out.data_ptr(), ctypes.byref(batch))
         if st < 0:
             raise MSCompError(f.__name__, st)
+
+    XPRESS_SEG_WORDS = 6     # uint32 fields of mscomp_gpu_xpress_seg
+
+    def xpress_index_tensor(self, count, stride):
+        """Device storage for the restart index of `count` plain-Xpress buffers, `stride` entries each."""
+        return self.torch.zeros(count * stride * self.XPRESS_SEG_WORDS, dtype=self.torch.int32, device=self.device)
+
+    def xpress_compress_indexed(self, d_in, d_out, batch, seg_bytes, d_index, stride):
+        """Plain Xpress encode that also writes the side-band restart index (the streams equal those of run_batch)."""
+        st = lib().mscomp_gpu_xpress_compress_batch_indexed(self.handle, d_in.data_ptr(), d_out.data_ptr(), ctypes.byref(batch), seg_bytes,
+                                                            d_index.data_ptr(), stride)
+        if st < 0:
+            raise MSCompError("mscomp_gpu_xpress_compress_batch_indexed", st)
+
+    def xpress_decompress_indexed(self, d_in, d_out, batch, d_index, stride):
+        """Decode of streams made by xpress_compress_indexed: one lane per segment instead of one lane per buffer."""
+        st = lib().mscomp_gpu_xpress_decompress_batch_indexed(self.handle, d_in.data_ptr(), d_out.data_ptr(), ctypes.byref(batch),
+                                                              d_index.data_ptr(), stride)
+        if st < 0:
+            raise MSCompError("mscomp_gpu_xpress_decompress_batch_indexed", st)
 
 
 # ---- synthetic data (SURVEY.md 8d) ---------------------------------------------------------------------------------

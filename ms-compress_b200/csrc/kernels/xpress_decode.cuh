@@ -11,6 +11,7 @@
 #include "lz_exec.cuh"
 #include "lane_out.cuh"
 #include "lz_apply.cuh"
+#include "xpress_encode.cuh"   // XpressSeg
 
 namespace msc {
 
@@ -22,6 +23,7 @@ struct XpLane {
     uint32_t ip;
     uint32_t flags; bool flagged, have_flags;
     uint32_t half_val; bool has_half;        // value of the byte whose high nibble is still unused (:88-92)
+    uint32_t stop_ip;                        // indexed decode: this lane's segment ends when ip reaches it (else 0xFFFFFFFF)
     int status;                              // 0 running, 1 finished OK, < 0 error
 };
 
@@ -35,6 +37,7 @@ template <class Sink>
 __device__ __forceinline__ void xp_step(XpLane& L, Sink& O)
 {
     do {
+        if (L.ip >= L.stop_ip) { L.status = (L.ip == L.stop_ip) ? 1 : ST_DATA; break; }     // end of this lane's segment
         if (!L.have_flags) {                                            // start a fragment (:425-430)
             if (L.ip + 4 > L.in_len) { L.status = ST_DATA; break; }     // :461
             const uint32_t f = xp_rd32(L, L.ip);
@@ -103,7 +106,7 @@ __device__ __forceinline__ void xpress_decode_body(const uint8_t* __restrict__ i
         const uint32_t i = g * 32 + lane;
         XpLane L;
         L.in = in; L.in_len = 0; L.cap = 0; L.ip = 0; L.flags = 0; L.flagged = false; L.have_flags = false;
-        L.half_val = 0; L.has_half = false; L.status = 1;
+        L.half_val = 0; L.has_half = false; L.status = 1; L.stop_ip = 0xFFFFFFFFu;
         Sink O;
         if (i < count) {
             L.in = in + in_off[i]; L.in_len = in_len[i]; L.cap = out_cap[i];
@@ -140,6 +143,104 @@ xpress_parse_kernel(const uint8_t* __restrict__ in, uint32_t* __restrict__ tok, 
                     uint32_t* __restrict__ out_len, int32_t* __restrict__ status, uint32_t* __restrict__ ntok)
 {
     xpress_decode_body<LaneTok>(in, nullptr, tok, count, in_off, in_len, out_off, out_cap, out_len, status, ntok);
+}
+
+// Indexed parse: streams that come with a restart index (XpressSeg, made by xpress_encode_kernel) are parsed by one lane per
+// SEGMENT instead of one lane per stream.  Lane i handles segment i % stride of stream i / stride; tokens of a segment go to
+// tok + out_off + seg.out_pos (a token stands for at least one output byte, so segments cannot collide).
+__global__ void __launch_bounds__(32 * XPD_WARPS_PER_BLOCK)
+xpress_parse_indexed_kernel(const uint8_t* __restrict__ in, uint32_t* __restrict__ tok, uint32_t count,
+                            const uint64_t* __restrict__ in_off, const uint32_t* __restrict__ in_len,
+                            const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ out_cap,
+                            const XpressSeg* __restrict__ index, uint32_t stride,
+                            uint32_t* __restrict__ seg_ntok, int32_t* __restrict__ seg_status, uint32_t* __restrict__ seg_end)
+{
+    const int lane = lane_id();
+    const int wib = (int)(threadIdx.x >> 5);
+    const uint32_t warps_total = gridDim.x * XPD_WARPS_PER_BLOCK;
+    const uint64_t lanes = (uint64_t)count * stride;
+    for (uint64_t g = blockIdx.x * XPD_WARPS_PER_BLOCK + wib; g * 32 < lanes; g += warps_total) {
+        const uint64_t i = g * 32 + lane;
+        const uint32_t u = (uint32_t)(i / stride), sgm = (uint32_t)(i % stride);
+        XpLane L;
+        L.in = in; L.in_len = 0; L.cap = 0; L.ip = 0; L.flags = 0; L.flagged = false; L.have_flags = false;
+        L.half_val = 0; L.has_half = false; L.status = 1; L.stop_ip = 0xFFFFFFFFu;
+        LaneTok O;
+        O.init(tok);
+        bool mine = false;
+        if (i < lanes) {
+            const XpressSeg* ix = index + (uint64_t)u * stride;
+            const uint32_t nseg = ix[0].nseg;
+            if (sgm < nseg) {
+                mine = true;
+                const XpressSeg e = ix[sgm];
+                L.in = in + in_off[u]; L.in_len = in_len[u]; L.cap = out_cap[u];
+                L.status = 0;
+                O.init(tok + out_off[u] + e.out_pos);
+                O.opos = e.out_pos;
+                if (sgm + 1 < nseg) L.stop_ip = ix[sgm + 1].in_pos;
+                if (sgm == 0) {
+                    if (L.in_len < 5) {                                     // :414-418 (sic)
+                        uint32_t w = 0;
+                        if (L.in_len == 4) w = (uint32_t)L.in[0] | ((uint32_t)L.in[1] << 8) | ((uint32_t)L.in[2] << 16) | ((uint32_t)L.in[3] << 24);
+                        L.status = (L.in_len == 0 || (L.in_len == 4 && w != 0xFFFFFFFFu)) ? 1 : ST_DATA;
+                    }
+                } else if (e.in_pos > L.in_len || e.out_pos > L.cap || (e.flag_used && (e.flag_used > 31 || (uint64_t)e.flag_pos + 4 > L.in_len)) ||
+                           (e.half_pos != 0xFFFFFFFFu && e.half_pos >= L.in_len)) {
+                    L.status = ST_DATA;                                     // an index that does not belong to this stream
+                } else {
+                    L.ip = e.in_pos;
+                    if (e.flag_used) {
+                        const uint8_t* f = L.in + e.flag_pos;
+                        const uint32_t fw = (uint32_t)f[0] | ((uint32_t)f[1] << 8) | ((uint32_t)f[2] << 16) | ((uint32_t)f[3] << 24);
+                        L.flagged = ((fw >> (31 - e.flag_used)) & 1u) != 0;
+                        L.flags = (e.flag_used == 31 ? 0u : (fw << (e.flag_used + 1))) | (1u << e.flag_used);
+                        L.have_flags = true;
+                    }
+                    if (e.half_pos != 0xFFFFFFFFu) { L.half_val = L.in[e.half_pos]; L.has_half = true; }
+                }
+            }
+        }
+        L.win.init(L.in, L.in + L.in_len);
+        while (__any_sync(FULL, L.status == 0)) {
+            if (L.status == 0) xp_step(L, O);
+        }
+        if (mine) { seg_ntok[i] = O.ntok; seg_status[i] = L.status == 1 ? ST_OK : L.status; seg_end[i] = O.opos; }
+    }
+}
+
+// Second stage for indexed streams: one warp per STREAM executes the token runs of its segments in order (matches may reach
+// back into earlier segments), after checking that every segment parsed cleanly and ended where the next one starts.
+__global__ void __launch_bounds__(32 * LZA_WARPS_PER_BLOCK)
+xpress_apply_indexed_kernel(const uint32_t* __restrict__ tok_base, const uint32_t* __restrict__ seg_ntok, const int32_t* __restrict__ seg_status,
+                            const uint32_t* __restrict__ seg_end, const XpressSeg* __restrict__ index, uint32_t stride,
+                            const uint64_t* __restrict__ out_off, uint32_t count, uint8_t* __restrict__ out,
+                            uint32_t* __restrict__ out_len, int32_t* __restrict__ status)
+{
+    const int lane = lane_id();
+    const uint32_t warps_total = gridDim.x * LZA_WARPS_PER_BLOCK;
+    for (uint32_t u = blockIdx.x * LZA_WARPS_PER_BLOCK + (threadIdx.x >> 5); u < count; u += warps_total) {
+        const XpressSeg* ix = index + (uint64_t)u * stride;
+        const uint64_t i0 = (uint64_t)u * stride;
+        const uint32_t nseg = ix[0].nseg;
+        int bad = 0;                                                    // first failing segment's status
+        for (uint32_t s0 = 0; s0 < nseg && !bad; s0 += 32) {
+            const uint32_t sg = s0 + lane;
+            int st = 0;
+            if (sg < nseg) {
+                st = seg_status[i0 + sg];
+                if (st == 0 && sg + 1 < nseg && seg_end[i0 + sg] != ix[sg + 1].out_pos) st = ST_DATA;
+            }
+            const unsigned m = __ballot_sync(FULL, st < 0);
+            if (m) bad = __shfl_sync(FULL, st, __ffs((int)m) - 1);
+        }
+        if (nseg == 0) bad = ST_DATA;
+        if (bad) { if (lane == 0) { out_len[u] = 0; status[u] = bad; } continue; }
+        uint8_t* o = out + out_off[u];
+        for (uint32_t sg = 0; sg < nseg; ++sg)
+            lz_apply_run(tok_base + out_off[u] + ix[sg].out_pos, seg_ntok[i0 + sg], o, ix[sg].out_pos);
+        if (lane == 0) { out_len[u] = seg_end[i0 + nseg - 1]; status[u] = ST_OK; }
+    }
 }
 
 } // namespace msc

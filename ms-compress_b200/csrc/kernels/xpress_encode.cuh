@@ -20,6 +20,18 @@ namespace msc {
 constexpr int XPE_THREADS = LZF_THREADS;
 constexpr int XPE_PER_THREAD = LZF_TILE / XPE_THREADS;     // 8 consecutive positions per thread
 
+// Restart point of a plain-Xpress stream (side-band, never part of the stream): everything a decoder needs to resume at an item
+// boundary.  One entry per segment of seg_tiles * LZF_TILE input bytes; entry 0 (stream start) also carries the entry count.
+// Layout == mscomp_gpu_xpress_seg (include/mscomp_gpu.h).
+struct XpressSeg {
+    uint32_t in_pos;      // compressed offset of the next byte to read (the flag word itself when flag_used == 0)
+    uint32_t out_pos;     // uncompressed position of the next item
+    uint32_t flag_pos;    // compressed offset of the flag word in force (valid when flag_used != 0)
+    uint32_t flag_used;   // items of that flag word already consumed (0..31)
+    uint32_t half_pos;    // compressed offset of the byte whose high nibble is still unused, 0xFFFFFFFF = none
+    uint32_t nseg;        // entry 0: number of entries of this stream
+};
+
 struct XpEncSmem {
     LzFrontSmem lz;
     uint32_t flagw[LZF_TILE / 32 + 2];       // flag words touched by this tile (first one may be carried in)
@@ -45,7 +57,8 @@ __global__ void __launch_bounds__(XPE_THREADS)
 xpress_encode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint32_t count,
                      const uint64_t* __restrict__ in_off, const uint32_t* __restrict__ in_len,
                      const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ out_cap,
-                     uint32_t* __restrict__ out_len, int32_t* __restrict__ status)
+                     uint32_t* __restrict__ out_len, int32_t* __restrict__ status,
+                     uint32_t seg_tiles, XpressSeg* __restrict__ index, uint32_t index_stride)     // optional restart index
 {
     MSC_DYN_SMEM(smem_raw);
     XpEncSmem& sm = *reinterpret_cast<XpEncSmem*>(smem_raw);
@@ -63,7 +76,24 @@ xpress_encode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, 
         }
         __syncthreads();
 
+        XpressSeg* idx = index ? index + (uint64_t)u * index_stride : nullptr;
+        if (idx && tid == 0) {
+            const uint32_t segb = seg_tiles * LZF_TILE;
+            const uint32_t nseg = n ? (n + segb - 1) / segb : 1u;
+            idx[0] = XpressSeg{0u, 0u, 0u, 0u, 0xFFFFFFFFu, nseg < index_stride ? nseg : index_stride};
+        }
         for (uint32_t t0 = 0; t0 < n && sm.status == ST_OK; t0 += LZF_TILE) {
+            if (idx && tid == 0 && t0 && (t0 / LZF_TILE) % seg_tiles == 0 && t0 / (LZF_TILE * seg_tiles) < index_stride) {
+                const uint32_t k = sm.items, c = k & 31u;                    // next item; the state below is final for everything before it
+                XpressSeg e;
+                e.in_pos = c ? sm.bytes + 4 * ((k >> 5) + 1) : sm.cur_flagpos;
+                e.out_pos = sm.lz.next_p;
+                e.flag_pos = sm.cur_flagpos;
+                e.flag_used = c;
+                e.half_pos = (sm.nibs & 1u) ? sm.pend_half : 0xFFFFFFFFu;
+                e.nseg = 0;
+                idx[t0 / (LZF_TILE * seg_tiles)] = e;
+            }
             lzf_tile(sm.lz, src, n, t0, 8192u, 8192u);
             // ---- per-thread item statistics over 8 consecutive positions ----
             const uint32_t items0 = sm.items, bytes0 = sm.bytes, nibs0 = sm.nibs;

@@ -366,7 +366,24 @@ MSCompStatus mscomp_gpu_xpress_compress_batch(mscomp_gpu_ctx* ctx, const uint8_t
     MSC_OPT_IN_SMEM(xpress_encode_kernel, sizeof(XpEncSmem));
     const uint32_t cap = (uint32_t)ctx->sm_count * 4;
     MSC_LAUNCH_SMEM(ctx, xpress_encode_kernel, b->count < cap ? b->count : cap, XPE_THREADS, sizeof(XpEncSmem),
-                    d_in, d_out, b->count, b->d_in_off, b->d_in_len, b->d_out_off, b->d_out_cap, b->d_out_len, b->d_status);
+                    d_in, d_out, b->count, b->d_in_off, b->d_in_len, b->d_out_off, b->d_out_cap, b->d_out_len, b->d_status,
+                    0u, (XpressSeg*)nullptr, 0u);
+    return msc_cuda_status(cudaGetLastError(), "xpress_compress");
+}
+
+static_assert(sizeof(XpressSeg) == sizeof(mscomp_gpu_xpress_seg), "xpress index entry layout");
+
+MSCompStatus mscomp_gpu_xpress_compress_batch_indexed(mscomp_gpu_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, const mscomp_gpu_batch* b,
+                                                      uint32_t seg_bytes, mscomp_gpu_xpress_seg* d_index, uint32_t index_stride)
+{
+    if (!batch_ok(ctx, d_in, d_out, b) || !d_index || !index_stride || seg_bytes < LZF_TILE || seg_bytes % LZF_TILE) return MSCOMP_ARG_ERROR;
+    if (!b->count) return MSCOMP_OK;
+    cudaSetDevice(ctx->device);
+    MSC_OPT_IN_SMEM(xpress_encode_kernel, sizeof(XpEncSmem));
+    const uint32_t cap = (uint32_t)ctx->sm_count * 4;
+    MSC_LAUNCH_SMEM(ctx, xpress_encode_kernel, b->count < cap ? b->count : cap, XPE_THREADS, sizeof(XpEncSmem),
+                    d_in, d_out, b->count, b->d_in_off, b->d_in_len, b->d_out_off, b->d_out_cap, b->d_out_len, b->d_status,
+                    seg_bytes / LZF_TILE, (XpressSeg*)d_index, index_stride);
     return msc_cuda_status(cudaGetLastError(), "xpress_compress");
 }
 
@@ -387,6 +404,32 @@ MSCompStatus mscomp_gpu_xpress_decompress_batch(mscomp_gpu_ctx* ctx, const uint8
         MSC_LAUNCH(ctx, xpress_decode_kernel, groups < cap ? groups : cap, 32 * XPD_WARPS_PER_BLOCK,
                    d_in, d_out, b->count, b->d_in_off, b->d_in_len, b->d_out_off, b->d_out_cap, b->d_out_len, b->d_status);
     }
+    return msc_cuda_status(cudaGetLastError(), "xpress_decompress");
+}
+
+MSCompStatus mscomp_gpu_xpress_decompress_batch_indexed(mscomp_gpu_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, const mscomp_gpu_batch* b,
+                                                        const mscomp_gpu_xpress_seg* d_index, uint32_t index_stride)
+{
+    if (!batch_ok(ctx, d_in, d_out, b) || !d_index || !index_stride) return MSCOMP_ARG_ERROR;
+    if (!b->count) return MSCOMP_OK;
+    cudaSetDevice(ctx->device);
+    const uint64_t lanes = (uint64_t)b->count * index_stride;
+    uint32_t* tok = lanes < 0x7fffffffu ? token_scratch(ctx, b) : nullptr;
+    uint32_t* seg = tok ? (uint32_t*)ctx->get(SC_AUX1, (size_t)lanes * 3 * sizeof(uint32_t) + 64) : nullptr;
+    if (!tok || !seg) return mscomp_gpu_xpress_decompress_batch(ctx, d_in, d_out, b);     // no room for tokens: one lane per stream
+    uint32_t* seg_ntok = seg;
+    int32_t* seg_status = (int32_t*)(seg + lanes);
+    uint32_t* seg_end = seg + 2 * lanes;
+    const uint32_t per_block = 32 * XPD_WARPS_PER_BLOCK;
+    const uint64_t groups = (lanes + per_block - 1) / per_block;
+    const uint32_t cap = (uint32_t)ctx->sm_count * 16;
+    MSC_LAUNCH(ctx, xpress_parse_indexed_kernel, groups < cap ? (uint32_t)groups : cap, per_block,
+               d_in, tok, b->count, b->d_in_off, b->d_in_len, b->d_out_off, b->d_out_cap, (const XpressSeg*)d_index, index_stride,
+               seg_ntok, seg_status, seg_end);
+    const uint32_t ab = (b->count + LZA_WARPS_PER_BLOCK - 1) / LZA_WARPS_PER_BLOCK, acap = (uint32_t)ctx->sm_count * 16;
+    MSC_LAUNCH(ctx, xpress_apply_indexed_kernel, ab < acap ? ab : acap, 32 * LZA_WARPS_PER_BLOCK,
+               (const uint32_t*)tok, (const uint32_t*)seg_ntok, (const int32_t*)seg_status, (const uint32_t*)seg_end,
+               (const XpressSeg*)d_index, index_stride, b->d_out_off, b->count, d_out, b->d_out_len, b->d_status);
     return msc_cuda_status(cudaGetLastError(), "xpress_decompress");
 }
 

@@ -56,8 +56,9 @@ def emu_lznt1_encode(emu, data, grid=3, heavy_work=32768):
     return out[16:16 + int(offs[nch])].tobytes(), offs
 
 
-def emu_batch(emu, fn_name, bufs, caps, grid=2):
-    """Run a batch kernel (decode or encode) over independent buffers; returns (status, out_len, [outputs])."""
+def emu_batch(emu, fn_name, bufs, caps, grid=2, extra=()):
+    """Run a batch kernel (decode or encode) over independent buffers; returns (status, out_len, [outputs]).
+    extra: further ctypes arguments of the emulator entry point (e.g. the Xpress restart index)."""
     count = len(bufs)
     in_off, pos = [], 0
     for b in bufs:
@@ -79,6 +80,6 @@ def emu_batch(emu, fn_name, bufs, caps, grid=2):
     ol = np.zeros(count, dtype=np.uint32)
     st = np.zeros(count, dtype=np.int32)
     getattr(emu, fn_name)(ctypes.c_void_p(addr), ctypes.c_void_p(out.ctypes.data + PAD), ctypes.c_uint32(count), P(io), P(il), P(oo), P(oc),
-                          P(ol), P(st), ctypes.c_uint32(grid))
+                          P(ol), P(st), ctypes.c_uint32(grid), *extra)
     outs = [out[PAD + out_off[i]:PAD + out_off[i] + ol[i]].tobytes() for i in range(count)]
     return st, ol, outs

@@ -5,7 +5,10 @@ import random
 
 import pytest
 from conftest import MAXSZ
-from emu_util import emu_batch
+import ctypes
+
+import numpy as np
+from emu_util import P, emu_batch
 
 KERNELS = {"xpress_huff": ("emu_xhuff_decode", "emu_xhuff_encode"), "xpress": ("emu_xpress_decode", "emu_xpress_encode")}
 SIZES = [1, 2, 3, 4, 5, 31, 32, 33, 100, 5000, 65535, 65536, 65537, 140000]
@@ -73,3 +76,46 @@ def test_decode_status_equals_oracle_on_bad_input(emu, oracle, ms, fmt, variant)
         assert st[i] == rc, (i, st[i], rc)
         if rc == 0:
             assert outs[i] == exp
+
+
+@pytest.mark.parametrize("seg_bytes,stride", [(2048, 80), (4096, 8), (16384, 16)])
+def test_xpress_restart_index(emu, oracle, ms, seg_bytes, stride):
+    """The side-band restart index of plain Xpress: the stream itself is unchanged (same bytes as the plain call, decodes with
+    the oracle), and the one-lane-per-segment decoder reproduces the input from (stream, index)."""
+    rnd = random.Random(seg_bytes)
+    plains = [ms.generate(kind, n, 7 + n) for kind in ("text", "runs", "random") for n in (1, 2047, 2048, 2049, 10000, 70000, 140000)]
+    plains += [b"", b"abc" * 30000, bytes(50000), bytes(rnd.getrandbits(8) & 3 for _ in range(30000))]
+    caps = [MAXSZ["xpress"](len(p)) for p in plains]
+    index = np.zeros(len(plains) * stride * 6, dtype=np.uint32)
+    st, _, comps = emu_batch(emu, "emu_xpress_encode_indexed", plains, caps,
+                             extra=(ctypes.c_uint32(seg_bytes), P(index), ctypes.c_uint32(stride)))
+    assert not st.any()
+    st0, _, comps0 = emu_batch(emu, "emu_xpress_encode", plains, caps)
+    assert comps == comps0                                           # the index does not change the stream
+    for p, c in zip(plains, comps):
+        if p:                                                        # (the reference rejects its own encoding of the empty input)
+            assert oracle.decompress("xpress", c, len(p)) == (0, p)
+    ix = index.reshape(len(plains), stride, 6)
+    for i, p in enumerate(plains):
+        want = min(stride, max(1, -(-len(p) // seg_bytes)))
+        assert ix[i, 0, 5] == want, (len(p), ix[i, 0])
+        outs_pos = [int(x) for x in ix[i, :want, 1]]
+        assert outs_pos == sorted(outs_pos) and outs_pos[0] == 0
+    st, ol, outs = emu_batch(emu, "emu_xpress_decode_indexed", comps, [len(p) for p in plains], extra=(P(index), ctypes.c_uint32(stride)))
+    st_plain, _, outs_plain = emu_batch(emu, "emu_xpress_decode2", comps, [len(p) for p in plains])
+    assert list(st) == list(st_plain) and list(st) == [0 if p else -3 for p in plains]       # (FF FF FF FF is rejected, as upstream)
+    assert outs == outs_plain and all(o == p for o, p in zip(outs, plains) if p)
+    # exact / too small capacities and damaged streams: the status of the plain decoder (which equals the oracle's), no crash
+    for i in rnd.sample(range(len(plains)), 6):
+        if len(plains[i]) < 100:
+            continue
+        bad = bytearray(comps[i])
+        bad[rnd.randrange(len(bad))] ^= 1 << rnd.randrange(8)
+        one_ix = ix[i:i + 1].copy().reshape(-1)
+        for data, cap in ((bytes(bad), len(plains[i])), (comps[i], len(plains[i]) - 1), (comps[i], len(plains[i]) // 2)):
+            st1, _, out1 = emu_batch(emu, "emu_xpress_decode_indexed", [data], [cap], extra=(P(one_ix), ctypes.c_uint32(stride)))
+            ref = oracle.decompress("xpress", data, cap)
+            if data is comps[i]:
+                assert st1[0] == ref[0] and (ref[0] < 0 or out1[0] == ref[1])
+            else:                                                    # the index no longer belongs to the stream: an error, or the right bytes
+                assert st1[0] < 0 or (ref[0] == 0 and out1[0] == ref[1])

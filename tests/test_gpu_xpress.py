@@ -144,3 +144,49 @@ def test_device_batch_roundtrip(ms, oracle, fmt):
     for i in range(count):
         assert out_host[in_off[i]:in_off[i] + sizes[i]].tobytes() == plains[i], i
     ctx.close()
+
+
+def test_xpress_restart_index_on_gpu(ms, oracle):
+    """Side-band restart index of plain Xpress through the device API: streams equal the unindexed ones and decode with the
+    oracle; the per-segment decoder reproduces the inputs."""
+    import numpy as np
+    import torch
+    ctx = ms.GpuContext()
+    rnd = random.Random(4)
+    sizes = [1, 2047, 2048, 2049, 70000, 300000, 1 << 20, (1 << 20) + 5, 0]
+    plains = [ms.generate(("text", "runs", "random")[i % 3], n, 11 + i) for i, n in enumerate(sizes)]
+    plains.append(bytes(rnd.getrandbits(8) & 3 for _ in range(100000)))
+    count = len(plains)
+    caps = [MAXSZ["xpress"](len(p)) for p in plains]
+    in_off = np.cumsum([0] + [(len(p) + 63) // 64 * 64 for p in plains])[:-1]
+    c_off = np.cumsum([0] + [(c + 63) // 64 * 64 for c in caps])[:-1]
+    blob = np.zeros(int(in_off[-1]) + len(plains[-1]) + 64, dtype=np.uint8)
+    for p, o in zip(plains, in_off):
+        blob[o:o + len(p)] = np.frombuffer(p, dtype=np.uint8)
+    d_in = torch.from_numpy(blob).cuda()
+    d_comp = torch.zeros(int(c_off[-1]) + caps[-1] + 64, dtype=torch.uint8, device="cuda")
+    d_out = torch.zeros_like(d_in)
+    enc, c_len, st1, keep1 = ctx.make_batch(in_off.tolist(), [len(p) for p in plains], c_off.tolist(), caps)
+    for seg_bytes, stride in ((2048, 600), (16384, 65), (65536, 4)):
+        d_index = ctx.xpress_index_tensor(count, stride)
+        ctx.xpress_compress_indexed(d_in, d_comp, enc, seg_bytes, d_index, stride)
+        torch.cuda.synchronize()
+        assert int(st1.abs().sum().item()) == 0
+        comps = [bytes(d_comp[o:o + n].cpu().numpy()) for o, n in zip(c_off.tolist(), c_len.tolist())]
+        d_plain = torch.zeros_like(d_comp)
+        enc2, c_len2, st1b, keep1b = ctx.make_batch(in_off.tolist(), [len(p) for p in plains], c_off.tolist(), caps)
+        ctx.run_batch("xpress", "compress", d_in, d_plain, enc2)
+        torch.cuda.synchronize()
+        assert c_len2.tolist() == c_len.tolist()
+        for p, c, o in zip(plains, comps, c_off.tolist()):
+            assert bytes(d_plain[o:o + len(c)].cpu().numpy()) == c              # the index does not change the stream
+            if p:
+                assert oracle.decompress("xpress", c, len(p)) == (0, p)
+        dec, o_len, st2, keep2 = ctx.make_batch(c_off.tolist(), c_len.tolist(), in_off.tolist(), [len(p) for p in plains])
+        d_out.zero_()
+        ctx.xpress_decompress_indexed(d_comp, d_out, dec, d_index, stride)
+        torch.cuda.synchronize()
+        assert st2.tolist() == [0 if p else -3 for p in plains]                 # (FF FF FF FF is rejected, as upstream)
+        for p, o, n in zip(plains, in_off.tolist(), o_len.tolist()):
+            if p:
+                assert n == len(p) and bytes(d_out[o:o + n].cpu().numpy()) == p
