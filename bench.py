@@ -116,7 +116,7 @@ def run_reference(args):
         "cpu_baseline": {"value": v, "unit": "MB/s", "cores": meas["cores"], "kind": meas["kind"], "sample": meas["sample"]},
         "e2e": {"value": v, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -262,7 +262,6 @@ def run_gpu(args):
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("MSCOMP_NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
@@ -412,13 +411,31 @@ def run_gpu(args):
     if cpu:
         line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
         line["cpu_baseline_detail"] = {k: cpu[k] for k in ("compress_MBps_per_core", "decompress_MBps_per_core", "ratio")}
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The one JSON line of the contract, on the process's ORIGINAL stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # Libraries print on stdout too (NCCL's version banner at any NCCL_DEBUG level, torch warnings): send file descriptor 1
+    # to stderr for the whole run and keep the original for the JSON line, so stdout carries exactly one line.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
