@@ -35,11 +35,13 @@ constexpr size_t XHE_SCRATCH_BYTES = XHE_SCR_WPOS + (size_t)XHE_WORD_CAP * 4;
 struct XhEncSmem {
     LzFrontSmem lz;
     uint32_t hist[XHE_SYMS];
-    uint32_t key[XHE_SYMS];            // (count << 9 | symbol), sorted ascending; unused symbols sort first
-    uint32_t w[2 * XHE_SYMS];          // Huffman node weights (leaves then internal nodes)
-    uint16_t parent[2 * XHE_SYMS];
-    uint16_t code[XHE_SYMS];
-    uint8_t len[XHE_SYMS];
+    // Scratch of the code builder and the emitter.  It lives in the hash table of the LZ77 front end, which is dead once the
+    // chunk's tokens exist (and is cleared again before the next chunk): 9.5 KB less shared memory = one more block per SM.
+    __device__ __forceinline__ uint32_t* key() { return reinterpret_cast<uint32_t*>(lz.H); }                   // [XHE_SYMS] (count << 9 | symbol), sorted ascending
+    __device__ __forceinline__ uint32_t* w() { return reinterpret_cast<uint32_t*>(lz.H) + XHE_SYMS; }           // [2 * XHE_SYMS] node weights
+    __device__ __forceinline__ uint16_t* parent() { return reinterpret_cast<uint16_t*>(lz.H) + 6 * XHE_SYMS; }  // [2 * XHE_SYMS]
+    __device__ __forceinline__ uint16_t* code() { return reinterpret_cast<uint16_t*>(lz.H) + 8 * XHE_SYMS; }    // [XHE_SYMS]
+    __device__ __forceinline__ uint8_t* len() { return reinterpret_cast<uint8_t*>(lz.H) + 18 * XHE_SYMS; }      // [XHE_SYMS]
     uint32_t blc[16];                  // codes per length
     uint32_t nused, raw_total, bits_total, scan_tmp[8];
     unsigned long long bit_carry;      // running (bits << 32 | raw bytes) between token tiles
@@ -64,7 +66,7 @@ __device__ __forceinline__ uint32_t xhe_raw_of(uint32_t tok)
 __device__ __forceinline__ void xhe_build_codes(XhEncSmem& sm)
 {
     const int tid = (int)threadIdx.x;
-    for (int i = tid; i < XHE_SYMS; i += XHE_THREADS) { sm.key[i] = (sm.hist[i] << 9) | (uint32_t)i; sm.len[i] = 0; sm.code[i] = 0; }
+    for (int i = tid; i < XHE_SYMS; i += XHE_THREADS) { sm.key()[i] = (sm.hist[i] << 9) | (uint32_t)i; sm.len()[i] = 0; sm.code()[i] = 0; }
     if (tid < 16) sm.blc[tid] = 0;
     __syncthreads();
     // bitonic sort of 512 keys, ascending
@@ -73,9 +75,9 @@ __device__ __forceinline__ void xhe_build_codes(XhEncSmem& sm)
             for (int i = tid; i < XHE_SYMS; i += XHE_THREADS) {
                 const int ixj = i ^ j;
                 if (ixj > i) {
-                    const uint32_t a = sm.key[i], b = sm.key[ixj];
+                    const uint32_t a = sm.key()[i], b = sm.key()[ixj];
                     const bool up = (i & k) == 0;
-                    if ((a > b) == up) { sm.key[i] = b; sm.key[ixj] = a; }
+                    if ((a > b) == up) { sm.key()[i] = b; sm.key()[ixj] = a; }
                 }
             }
             __syncthreads();
@@ -83,19 +85,19 @@ __device__ __forceinline__ void xhe_build_codes(XhEncSmem& sm)
     }
     if (tid == 0) {
         int first = 0;
-        while (first < XHE_SYMS && (sm.key[first] >> 9) == 0) ++first;
+        while (first < XHE_SYMS && (sm.key()[first] >> 9) == 0) ++first;
         const int m = XHE_SYMS - first;                            // used symbols, ascending by (count, symbol)
         sm.nused = (uint32_t)m;
-        if (m == 1) { sm.parent[0] = 0; }
+        if (m == 1) { sm.parent()[0] = 0; }
         else if (m > 1) {                                          // two-queue Huffman: leaves 0..m-1, internal m..2m-2
-            for (int i = 0; i < m; ++i) sm.w[i] = sm.key[first + i] >> 9;
+            for (int i = 0; i < m; ++i) sm.w()[i] = sm.key()[first + i] >> 9;
             int i = 0, j = m, k = m;
             while (k < 2 * m - 1) {
                 int a, b;
-                if (i < m && (j >= k || sm.w[i] <= sm.w[j])) a = i++; else a = j++;
-                if (i < m && (j >= k || sm.w[i] <= sm.w[j])) b = i++; else b = j++;
-                sm.w[k] = sm.w[a] + sm.w[b];
-                sm.parent[a] = (uint16_t)k; sm.parent[b] = (uint16_t)k;
+                if (i < m && (j >= k || sm.w()[i] <= sm.w()[j])) a = i++; else a = j++;
+                if (i < m && (j >= k || sm.w()[i] <= sm.w()[j])) b = i++; else b = j++;
+                sm.w()[k] = sm.w()[a] + sm.w()[b];
+                sm.parent()[a] = (uint16_t)k; sm.parent()[b] = (uint16_t)k;
                 ++k;
             }
         }
@@ -106,7 +108,7 @@ __device__ __forceinline__ void xhe_build_codes(XhEncSmem& sm)
     for (int i = tid; i < m; i += XHE_THREADS) {
         int d = 0;
         if (m == 1) d = 1;
-        else for (int x = i; x != 2 * m - 2; x = sm.parent[x]) ++d;
+        else for (int x = i; x != 2 * m - 2; x = sm.parent()[x]) ++d;
         if (d > 15) d = 15;
         atomicAdd(&sm.blc[d], 1u);
     }
@@ -124,11 +126,11 @@ __device__ __forceinline__ void xhe_build_codes(XhEncSmem& sm)
         // lengths by rank: the least frequent symbols take the longest codes
         int idx = 0;
         for (int l = 15; l >= 1; --l)
-            for (uint32_t c = 0; c < sm.blc[l]; ++c) sm.len[sm.key[first + idx++] & 511] = (uint8_t)l;
+            for (uint32_t c = 0; c < sm.blc[l]; ++c) sm.len()[sm.key()[first + idx++] & 511] = (uint8_t)l;
         // canonical codes, ascending (length, symbol)  (HuffmanEncoder.h:115-123)
         uint32_t next[16], code = 0;
         for (int l = 1; l <= 15; ++l) { next[l] = code; code = (code + sm.blc[l]) << 1; }
-        for (int s = 0; s < XHE_SYMS; ++s) { const int l = sm.len[s]; if (l) sm.code[s] = (uint16_t)next[l]++; }
+        for (int s = 0; s < XHE_SYMS; ++s) { const int l = sm.len()[s]; if (l) sm.code()[s] = (uint16_t)next[l]++; }
     }
     __syncthreads();
 }
@@ -220,7 +222,7 @@ xhuff_encode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, u
                         const uint32_t h = sm.hist[s];
                         if (h) {
                             const uint32_t ob = s >= 256 ? (uint32_t)((s >> 4) & 15) : 0u;
-                            local += ((unsigned long long)(h * (sm.len[s] + ob))) << 32;
+                            local += ((unsigned long long)(h * (sm.len()[s] + ob))) << 32;
                         }
                     }
                     for (int d = 16; d; d >>= 1) local += __shfl_xor_sync(FULL, local, d);
@@ -253,7 +255,7 @@ xhuff_encode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, u
             if ((uint64_t)opos + 256 + comp_len > cap || nwords + 2 > XHE_WORD_CAP) { st = ST_BUF; break; }
             uint8_t* o = obase + opos + 256;
             // 256-byte table: symbol 2i in the low nibble of byte i (:284, :320)
-            for (int i = tid; i < 256; i += XHE_THREADS) obase[opos + i] = (uint8_t)(sm.len[2 * i] | (sm.len[2 * i + 1] << 4));
+            for (int i = tid; i < 256; i += XHE_THREADS) obase[opos + i] = (uint8_t)(sm.len()[2 * i] | (sm.len()[2 * i + 1] << 4));
             // ---- pass A: bit addresses, raw bytes, word addresses ----
             for (uint32_t i = tid; i < (nwords + 1) / 2 + 1; i += XHE_THREADS) bits32[i] = 0;
             if (tid == 0) { sm.bit_carry = 0; wpos[0] = 0; wpos[1] = 2; }
@@ -262,7 +264,7 @@ xhuff_encode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, u
                 const uint32_t k = k0 + tid;
                 uint32_t t = 0, sym = 0, cl = 0, ob = 0, raw = 0;
                 if (k < ntok) {
-                    t = tok[k]; sym = xhe_sym_of(t); cl = sm.len[sym];
+                    t = tok[k]; sym = xhe_sym_of(t); cl = sm.len()[sym];
                     if (t >> 31) { ob = (sym >> 4) & 15; raw = xhe_raw_of(t); }
                 }
                 unsigned long long v = ((unsigned long long)(cl + ob) << 32) | raw, incl = v;
@@ -275,7 +277,7 @@ xhuff_encode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, u
                 if (k < ntok) {
                     const uint32_t B0 = (uint32_t)(excl >> 32), R0 = (uint32_t)excl;
                     const uint32_t B1 = B0 + cl, B2 = B1 + ob;
-                    xhe_put_bits(bits32, B0, sm.code[sym], cl);
+                    xhe_put_bits(bits32, B0, sm.code()[sym], cl);
                     if (xhe_reserved(B1) > xhe_reserved(B0)) { const uint32_t j = xhe_reserved(B0); wpos[j] = 4 + 2 * (j - 2) + R0; }
                     if (t >> 31) {
                         const uint32_t off = t & 0xFFFFu, lm3 = ((t >> 16) & 0x7FFFu) + 1 - 3;
