@@ -320,7 +320,9 @@ MSCompStatus msc_xpress_huff_compress_units(mscomp_gpu_ctx* ctx, const uint8_t* 
     if (!b->count) return MSCOMP_OK;
     cudaSetDevice(ctx->device);
     MSC_OPT_IN_SMEM(xhuff_encode_kernel, sizeof(XhEncSmem));
-    const uint32_t cap = (uint32_t)ctx->sm_count * 4;
+    static int per_sm = 0;                                            // resident blocks per SM (the kernel keeps per-block scratch: grid = one wave)
+    if (!per_sm && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, xhuff_encode_kernel, XHE_THREADS, sizeof(XhEncSmem)) != cudaSuccess || per_sm < 1)) per_sm = 3;
+    const uint32_t cap = (uint32_t)ctx->sm_count * (uint32_t)per_sm;
     const uint32_t grid = b->count < cap ? b->count : cap;
     uint8_t* scratch = (uint8_t*)ctx->get(SC_AUX2, (size_t)grid * XHE_SCRATCH_BYTES + 64);
     if (!scratch) return MSCOMP_MEM_ERROR;
