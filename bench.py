@@ -247,6 +247,125 @@ def measure_batch_format(ms, ctx, torch, fmt, each, count, steps, dev, peak, ran
             "encode_decode_MBps": U / MB / ((enc_ms + dec_ms) / 1e3), "gpu_launches": ctx.launches() - l0, "kernels": kern}
 
 
+def measure_mixed(ms, ctx, torch, dist, dev, rank, world, count, each, steps):
+    """BASELINE.json configs[4]: `count` independent buffers of `each` bytes per GPU, buffer i (global index) in format
+    [LZNT1, Xpress, Xpress-Huffman][i % 3], generator text with seed 42 + i.  Buffers are sharded contiguously by rank; the only
+    cross-GPU traffic is one all_gather of the per-rank compressed sizes.  Encode and decode of all three groups are timed
+    together with CUDA events; every round trip is verified."""
+    import numpy as np
+    U = count * each
+    host = np.empty(U, dtype=np.uint8)
+    ms.generate_batch_into(host, each, count, 42 + rank * count, "text")
+    g = [[j for j in range(count) if (rank * count + j) % 3 == f] for f in range(3)]
+    d_all = torch.empty(U, dtype=torch.uint8, device=dev)
+    for o in range(0, U, 1 << 28):
+        d_all[o:o + (1 << 28)].copy_(torch.from_numpy(host[o:o + (1 << 28)]))
+    view = d_all.view(count, each)
+    # LZNT1 group: its buffers back to back are one stream of independent 4 KiB chunks (each is a multiple of 4096)
+    d_l = view[torch.tensor(g[0], device=dev)].contiguous().view(-1)
+    nl = d_l.numel()
+    # Xpress group: whole buffers with the restart index; Xpress-Huffman group: 64 KiB units (the format's chunk)
+    def batch_for(idx, unit):
+        per = each // unit
+        offs = torch.tensor([j * each + k * unit for j in idx for k in range(per)], dtype=torch.int64, device=dev)
+        n = offs.numel()
+        capf = (lambda m: m + 4 + 4 * (m // 32)) if unit == each else (lambda m: m + 34 + 258 + 258 * (m // 65536))
+        slot = (capf(unit) + 15) // 16 * 16
+        c_off = torch.arange(n, dtype=torch.int64, device=dev) * slot
+        lens = torch.full((n,), unit, dtype=torch.int32, device=dev)
+        caps = torch.full((n,), slot, dtype=torch.int32, device=dev)
+        c_len = torch.zeros(n, dtype=torch.int32, device=dev)
+        st1 = torch.zeros(n, dtype=torch.int32, device=dev)
+        o_len = torch.zeros(n, dtype=torch.int32, device=dev)
+        st2 = torch.zeros(n, dtype=torch.int32, device=dev)
+        d_comp = torch.empty(slot * n, dtype=torch.uint8, device=dev)
+        enc = ms.Batch(n, offs.data_ptr(), lens.data_ptr(), c_off.data_ptr(), caps.data_ptr(), c_len.data_ptr(), st1.data_ptr())
+        dec = ms.Batch(n, c_off.data_ptr(), c_len.data_ptr(), offs.data_ptr(), lens.data_ptr(), o_len.data_ptr(), st2.data_ptr())
+        return {"n": n, "enc": enc, "dec": dec, "comp": d_comp, "c_len": c_len, "st": (st1, st2), "keep": (offs, c_off, lens, caps, o_len)}
+    bx, bh = batch_for(g[1], each), batch_for(g[2], 65536)
+    seg_bytes, stride = 16384, (each + 16383) // 16384
+    d_index = ctx.xpress_index_tensor(bx["n"], stride)
+    d_out = torch.zeros(U, dtype=torch.uint8, device=dev)
+    state = {}
+
+    # The three groups are independent: each runs on its own stream (own context), so the latency-bound lane kernels of one
+    # format overlap with the kernels of the others.  Events on the main stream bracket all of them.
+    main = torch.cuda.current_stream()
+    side = [torch.cuda.Stream() for _ in range(3)]
+    cx = []
+    for st_ in side:
+        with torch.cuda.stream(st_):
+            cx.append(ms.GpuContext())
+    fork, join = torch.cuda.Event(), [torch.cuda.Event() for _ in range(3)]
+
+    def phase(fns):
+        fork.record(main)
+        for i, fn in enumerate(fns):
+            side[i].wait_event(fork)
+            with torch.cuda.stream(side[i]):
+                fn()
+                join[i].record(side[i])
+        for i in range(3):
+            main.wait_event(join[i])
+
+    def enc_l():
+        state["l"] = cx[0].lznt1_compress(d_l)
+
+    def dec_l():
+        d_lc, d_loff, _ = state["l"]
+        state["lo"] = cx[0].lznt1_decompress(d_lc, d_loff, nl // 4096)
+
+    def step(ev=None):
+        if ev:
+            ev[0].record()
+        phase([enc_l, lambda: cx[1].xpress_compress_indexed(d_all, bx["comp"], bx["enc"], seg_bytes, d_index, stride),
+               lambda: cx[2].run_batch("xpress_huff", "compress", d_all, bh["comp"], bh["enc"])])
+        if ev:
+            ev[1].record()
+        phase([dec_l, lambda: cx[1].xpress_decompress_indexed(bx["comp"], d_out, bx["dec"], d_index, stride),
+               lambda: cx[2].run_batch("xpress_huff", "decompress", bh["comp"], d_out, bh["dec"])])
+        if ev:
+            ev[2].record()
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    for b in (bx, bh):
+        assert int(b["st"][0].abs().sum().item()) == 0 and int(b["st"][1].abs().sum().item()) == 0, "mixed batch: kernel reported an error"
+    ov = d_out.view(count, each)
+    for f in (1, 2):
+        ix = torch.tensor(g[f], device=dev)
+        assert torch.equal(ov[ix], view[ix]), "mixed batch: round trip mismatch (format %d)" % f
+    assert torch.equal(state["lo"][0][:nl], d_l), "mixed batch: LZNT1 round trip mismatch"
+    C = [int(ms.parse_result(state["l"][2])["bytes"]), int(bx["c_len"].to(torch.int64).sum().item()), int(bh["c_len"].to(torch.int64).sum().item())]
+    l0 = sum(c.launches() for c in cx)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    for k in range(steps):
+        step(evs[k])
+        if dist is not None:                      # the one collective of the sharded job: everybody learns every rank's output sizes
+            sizes = torch.tensor(C, dtype=torch.int64, device=dev)
+            gathered = [torch.empty_like(sizes) for _ in range(world)]
+            dist.all_gather(gathered, sizes)
+    torch.cuda.synchronize()
+    t = torch.tensor([statistics.mean(e[0].elapsed_time(e[1]) for e in evs), statistics.mean(e[1].elapsed_time(e[2]) for e in evs)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    enc_ms, dec_ms = t.tolist()
+    launches = sum(c.launches() for c in cx) - l0
+    del d_all, d_l, d_out, bx, bh, state
+    torch.cuda.empty_cache()
+    return {"config": "BASELINE.json configs[4]: %d independent %d-byte buffers per GPU, format [LZNT1, Xpress, Xpress-Huffman][i %% 3], sharded contiguously over %d GPU(s); "
+                      "Xpress-Huffman buffers as 64 KiB units, Xpress buffers with the side-band restart index" % (count, each, world),
+            "uncompressed_bytes_per_gpu": U, "compressed_ratio": sum(C) / U, "encode_ms": enc_ms, "decode_ms": dec_ms,
+            "encode_decode_MBps": world * U / MB / ((enc_ms + dec_ms) / 1e3), "encode_MBps": world * U / MB / (enc_ms / 1e3),
+            "decode_MBps": world * U / MB / (dec_ms / 1e3), "gpu_launches": launches,
+            "collective": "all_gather of 3 x int64 per rank per step" if world > 1 else "none (N=1)",
+            "streams": "one CUDA stream per format group (3), bracketed by events on the main stream"}
+
+
 def run_gpu(args):
     import numpy as np
     import torch
@@ -365,6 +484,15 @@ def run_gpu(args):
             formats["xpress"] = measure_batch_format(ms, ctx, torch, "xpress", BLOCK, args.mib, 2, dev, peak, rank)
             formats["xpress"]["config"] = "BASELINE.json configs[2]: %d MiB synthetic text as %d independent 1 MiB buffers (one stream each)" % (args.mib, args.mib)
 
+    mixed = None
+    if args.formats != "none" and hasattr(ms.lib(), "mscomp_gpu_xpress_compress_batch_indexed"):
+        try:
+            del d_comp, d_out, h_comp, h_out
+        except NameError:
+            pass
+        torch.cuda.empty_cache()
+        mixed = measure_mixed(ms, ctx, torch, dist, dev, rank, world, 1024, BLOCK, 3)
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -408,6 +536,8 @@ def run_gpu(args):
         "clocks": clk.summary(),
         "formats": formats,
     }
+    if mixed:
+        line["mixed_batch"] = mixed
     if cpu:
         line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
         line["cpu_baseline_detail"] = {k: cpu[k] for k in ("compress_MBps_per_core", "decompress_MBps_per_core", "ratio")}
