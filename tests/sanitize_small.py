@@ -1,20 +1,61 @@
 """Small end-to-end exercise of every kernel, meant to be run under compute-sanitizer on the GPU box:
     compute-sanitizer --tool memcheck  python tests/sanitize_small.py
     compute-sanitizer --tool racecheck python tests/sanitize_small.py
-"""
+Covers the one-shot C ABI (incl. the pipelined LZNT1 wrappers with small MSCOMP_PIPE_* thresholds), the heavy-chunk path of
+the LZNT1 encoder, the GPU chunk index and the indexed plain-Xpress batch calls."""
 import os
+import random
 import sys
 
+os.environ.setdefault("MSCOMP_PIPE_MIN", "65536")
+os.environ.setdefault("MSCOMP_PIPE_RANGE", "131072")
+os.environ.setdefault("MSCOMP_PIPE_SLICE", "131072")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
 import mscompress_b200 as ms  # noqa: E402
 
 MAXSZ = {"lznt1": lambda n: n + 3 + 2 * ((n + 4095) // 4096), "xpress": lambda n: n + 4 + 4 * (n // 32),
          "xpress_huff": lambda n: n + 34 + 258 + 258 * (n // 65536)}
-for fmt in ("lznt1", "xpress_huff", "xpress"):
-    for kind, n in (("text", 70000), ("runs", 20000), ("random", 5000), ("text", 33)):
-        plain = ms.generate(kind, n, 7)
-        st, comp = ms.raw_call(fmt + "_compress", plain, MAXSZ[fmt](n))
-        assert st == 0, (fmt, kind, n, st)
-        st, back = ms.raw_call(fmt + "_decompress", comp, n)
-        assert st == 0 and back == plain, (fmt, kind, n, st)
+rnd = random.Random(1)
+extra = [("lznt1", bytes(rnd.choice(b"ACGT") for _ in range(3 * 4096 + 100))),                       # heavy chunks: lazy parse
+         ("lznt1", b"".join((b"\x00" * rnd.randint(3, 300)) + bytes([rnd.randint(1, 255)]) for _ in range(200))),
+         ("lznt1", ms.generate("text", 400000, 3))]                                                    # several slices / ranges
+cases = [(fmt, ms.generate(kind, n, 7)) for fmt in ("lznt1", "xpress_huff", "xpress")
+         for kind, n in (("text", 70000), ("runs", 20000), ("random", 5000), ("text", 33))] + extra
+for fmt, plain in cases:
+    n = len(plain)
+    st, comp = ms.raw_call(fmt + "_compress", plain, MAXSZ[fmt](n))
+    assert st == 0, (fmt, n, st)
+    st, back = ms.raw_call(fmt + "_decompress", comp, n)
+    assert st == 0 and back == plain, (fmt, n, st)
+
+ctx = ms.GpuContext()
+# GPU chunk index
+comp = ms.raw_call("lznt1_compress", ms.generate("text", 300000, 9), MAXSZ["lznt1"](300000))[1]
+d = torch.from_numpy(np.frombuffer(comp + b"\0" * 16, dtype=np.uint8).copy()).cuda()
+d_off, info = ctx.lznt1_index(d, in_len=len(comp))
+assert info["nchunks"] == (300000 + 4095) // 4096 and info["tail"] == 0 and info["consumed"] == len(comp), info
+# indexed plain Xpress
+plains = [ms.generate("text", 70000, 1), ms.generate("runs", 30000, 2), ms.generate("random", 9000, 3)]
+caps = [MAXSZ["xpress"](len(p)) for p in plains]
+in_off = np.cumsum([0] + [(len(p) + 63) // 64 * 64 for p in plains])[:-1]
+c_off = np.cumsum([0] + [(c + 63) // 64 * 64 for c in caps])[:-1]
+blob = np.zeros(int(in_off[-1]) + len(plains[-1]) + 64, dtype=np.uint8)
+for p, o in zip(plains, in_off):
+    blob[o:o + len(p)] = np.frombuffer(p, dtype=np.uint8)
+d_in = torch.from_numpy(blob).cuda()
+d_comp = torch.zeros(int(c_off[-1]) + caps[-1] + 64, dtype=torch.uint8, device="cuda")
+d_out = torch.zeros_like(d_in)
+enc, c_len, st1, k1 = ctx.make_batch(in_off.tolist(), [len(p) for p in plains], c_off.tolist(), caps)
+stride = 40
+d_index = ctx.xpress_index_tensor(len(plains), stride)
+ctx.xpress_compress_indexed(d_in, d_comp, enc, 2048, d_index, stride)
+torch.cuda.synchronize()
+dec, o_len, st2, k2 = ctx.make_batch(c_off.tolist(), c_len.tolist(), in_off.tolist(), [len(p) for p in plains])
+ctx.xpress_decompress_indexed(d_comp, d_out, dec, d_index, stride)
+torch.cuda.synchronize()
+assert st1.tolist() == [0, 0, 0] and st2.tolist() == [0, 0, 0]
+for p, o in zip(plains, in_off.tolist()):
+    assert bytes(d_out[o:o + len(p)].cpu().numpy()) == p
 print("sanitize_small ok")
