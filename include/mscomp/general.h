@@ -64,4 +64,26 @@ typedef enum _MSCompFlush {
     MSCOMP_FINISH   = 4
 } MSCompFlush;
 
+/* Stream object of the *_deflate / *_inflate calls; same layout as the reference's (include/mscomp/general.h:96-120, built with
+ * its default configuration: error and warning texts present).  The caller sets in / in_avail / out / out_avail between calls;
+ * the library advances them and keeps the totals. */
+typedef struct _mscomp_internal_state mscomp_internal_state;
+typedef struct _mscomp_stream {
+    MSCompFormat format;
+#ifdef __cplusplus
+    bool         compressing;
+#else
+    int          compressing;
+#endif
+    const_bytes  in;          /* next input byte */
+    size_t       in_avail;    /* bytes available at in */
+    size_t       in_total;    /* input bytes consumed so far */
+    bytes        out;         /* next output byte goes here */
+    size_t       out_avail;   /* free space at out */
+    size_t       out_total;   /* bytes produced so far */
+    char         error[256];
+    char         warning[256];
+    mscomp_internal_state* state;
+} mscomp_stream;
+
 #endif
