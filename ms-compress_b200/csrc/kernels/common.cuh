@@ -35,6 +35,29 @@ __device__ __forceinline__ void st_stream16(void* p, const uint4& v)
 #endif
 }
 
+// One byte of global memory that another warp of this block may have written a moment ago: bypass L1.
+__device__ __forceinline__ uint32_t ld_byte_cg(const uint8_t* p)
+{
+#ifndef MSC_EMU
+    uint32_t r;
+    asm volatile("ld.global.cg.u8 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+    return r;
+#else
+    return *p;
+#endif
+}
+// Shared-memory words other warps update while this one polls them.
+__device__ __forceinline__ uint32_t ld_shared_volatile(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+__device__ __forceinline__ void st_shared_volatile(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
+__device__ __forceinline__ void spin_pause()
+{
+#ifndef MSC_EMU
+    __nanosleep(40);
+#else
+    emu::yield();
+#endif
+}
+
 // Inclusive warp prefix sum.
 __device__ __forceinline__ int warp_incl_scan(int v)
 {

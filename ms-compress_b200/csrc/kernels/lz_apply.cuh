@@ -116,4 +116,119 @@ lz_apply_kernel(const uint32_t* __restrict__ tok_base, const uint32_t* __restric
     }
 }
 
+// ---- one BLOCK per stream ----------------------------------------------------------------------------------------------
+// With few streams (plain Xpress: 1,024 buffers of 1 MiB) a warp per stream leaves the GPU idle and every round waits for the
+// round before it.  Here the rounds of 32 tokens of ONE stream are pipelined over the LZB_WARPS warps of a block: warp w takes rounds
+// w, w+LZB_WARPS, ... of a window of up to 512 rounds.  Round start positions come from a parallel prefix sum of the rounds' byte
+// counts, literals are stored at once, and a match runs as soon as its source is final:
+//   * the source lies in rounds that are completely done (below the frontier p0[done_upto], which advances in order), or
+//   * the source lies in the match's own round and the watermark rule of that round allows it, or
+//   * every earlier round is done, and the watermark rule of the round allows it (then this is lz_apply_run).
+// The lowest unfinished round never waits for another round, so the pipeline cannot deadlock.
+constexpr int LZB_WARPS = 8;
+constexpr int LZB_ROUNDS = 512;
+constexpr int LZB_EPT = LZB_ROUNDS / (32 * LZB_WARPS);   // rounds per thread in the prefix sum
+static_assert(LZB_EPT * 32 * LZB_WARPS == LZB_ROUNDS, "window size");
+
+struct LzBlockSmem {
+    uint32_t p0[LZB_ROUNDS + 1];      // output position of the first byte of every round of the window (+ end)
+    uint32_t flag[LZB_ROUNDS];        // round finished
+    uint32_t done_upto;               // rounds [0, done_upto) of the window are finished
+    uint32_t wsum[LZB_WARPS];
+};
+
+__device__ __forceinline__ uint32_t lz_apply_block_run(LzBlockSmem& sm, const uint32_t* __restrict__ tk, uint32_t n, uint8_t* __restrict__ o, uint32_t pstart)
+{
+    const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (uint32_t w0 = 0; w0 < n; w0 += 32u * LZB_ROUNDS) {
+        const uint32_t nt = min(n - w0, 32u * LZB_ROUNDS), R = (nt + 31) / 32;
+        // bytes per round
+        for (uint32_t r = warp; r < R; r += LZB_WARPS) {
+            const uint32_t t = 32 * r + lane;
+            const uint32_t tok = t < nt ? tk[w0 + t] : 0;
+            const uint32_t len = t < nt ? ((tok >> 31) ? ((tok >> 16) & 0x7FFFu) + 1 : 1u) : 0u;
+            const uint32_t sum = __reduce_add_sync(FULL, len);
+            if (lane == 0) sm.p0[r] = sum;
+        }
+        __syncthreads();
+        {   // exclusive scan of the (at most LZB_ROUNDS) round totals, LZB_EPT consecutive ones per thread
+            uint32_t v[LZB_EPT], sum = 0;
+#pragma unroll
+            for (int i = 0; i < LZB_EPT; ++i) { const uint32_t r = (uint32_t)(LZB_EPT * tid + i); v[i] = r < R ? sm.p0[r] : 0u; sum += v[i]; }
+            const uint32_t incl = (uint32_t)warp_incl_scan((int)sum);
+            if (lane == 31) sm.wsum[warp] = incl;
+            __syncthreads();
+            uint32_t run = pstart + incl - sum;
+            for (int w = 0; w < warp; ++w) run += sm.wsum[w];
+#pragma unroll
+            for (int i = 0; i < LZB_EPT; ++i) {
+                const uint32_t r = (uint32_t)(LZB_EPT * tid + i);
+                if (r < R) { sm.p0[r] = run; run += v[i]; if (r + 1 == R) sm.p0[R] = run; }
+            }
+            for (uint32_t r = tid; r < R; r += 32 * LZB_WARPS) sm.flag[r] = 0;
+            if (tid == 0) sm.done_upto = 0;
+        }
+        __syncthreads();
+        for (uint32_t r = warp; r < R; r += LZB_WARPS) {
+            const uint32_t t = 32 * r + lane;
+            const uint32_t tok = t < nt ? tk[w0 + t] : 0;
+            const bool is_match = (tok >> 31) != 0;
+            const uint32_t len = t < nt ? (is_match ? ((tok >> 16) & 0x7FFFu) + 1 : 1u) : 0u;
+            const uint32_t off = tok & 0xFFFFu;
+            const uint32_t p0r = sm.p0[r];
+            const uint32_t pos = p0r + (uint32_t)warp_incl_scan((int)len) - len;
+            if (len && !is_match) o[pos] = (uint8_t)tok;
+            bool pending = is_match;
+            const uint32_t a = pos - off, be = min(a + len, pos);        // the bytes a match reads: [a, be)
+            for (;;) {
+                __syncwarp();
+                const unsigned W = __reduce_min_sync(FULL, pending ? pos : 0xffffffffu);
+                if (W == 0xffffffffu) break;
+                const uint32_t d = ld_shared_volatile(&sm.done_upto);
+                const bool prev_done = d >= r;
+                const uint32_t F = sm.p0[prev_done ? r : d];               // everything below F is final
+                const bool can = pending && (be <= F || ((a >= p0r || prev_done) && (pos == W || be <= W)));
+                if (!__any_sync(FULL, can)) { spin_pause(); continue; }    // all pending matches wait for earlier rounds
+                if (!prev_done) __threadfence_block();                     // bytes of the rounds counted in d are visible from here on
+                const uint32_t cl = can ? len : 0u;
+                const uint32_t cincl = (uint32_t)warp_incl_scan((int)cl);
+                const uint32_t total = __shfl_sync(FULL, cincl, 31);
+                for (uint32_t b0 = 0; b0 < total; b0 += 32) {
+                    const uint32_t bidx = b0 + lane;
+                    int tt = 0;
+#pragma unroll
+                    for (int step = 16; step; step >>= 1) {
+                        const uint32_t c = __shfl_sync(FULL, cincl, tt + step - 1);
+                        if (c <= bidx) tt += step;
+                    }
+                    const uint32_t t_incl = __shfl_sync(FULL, cincl, tt), t_len = __shfl_sync(FULL, cl, tt);
+                    const uint32_t t_pos = __shfl_sync(FULL, pos, tt), t_off = __shfl_sync(FULL, off, tt);
+                    if (bidx < total) {
+                        const uint32_t k = bidx - (t_incl - t_len);
+                        const uint32_t sk = (t_off < t_len) ? (k % t_off) : k;
+                        o[t_pos + k] = (uint8_t)ld_byte_cg(o + t_pos - t_off + sk);
+                    }
+                }
+                if (can) pending = false;
+            }
+            // publish: the round is finished; whoever sees the frontier stuck at a finished round moves it
+            __syncwarp();
+            __threadfence_block();
+            if (lane == 0) {
+                st_shared_volatile(&sm.flag[r], 1u);
+                __threadfence_block();
+                for (;;) {
+                    const uint32_t d = ld_shared_volatile(&sm.done_upto);
+                    if (d >= R || !ld_shared_volatile(&sm.flag[d])) break;
+                    atomicCAS(&sm.done_upto, d, d + 1);
+                }
+            }
+        }
+        __syncthreads();
+        pstart = sm.p0[R];
+        __syncthreads();
+    }
+    return pstart;
+}
+
 } // namespace msc

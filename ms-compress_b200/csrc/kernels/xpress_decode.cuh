@@ -243,4 +243,38 @@ xpress_apply_indexed_kernel(const uint32_t* __restrict__ tok_base, const uint32_
     }
 }
 
+// The same for few, large streams: one BLOCK per stream, the rounds of a segment pipelined over its warps (lz_apply.cuh).
+__global__ void __launch_bounds__(32 * LZB_WARPS)
+xpress_apply_indexed_block_kernel(const uint32_t* __restrict__ tok_base, const uint32_t* __restrict__ seg_ntok, const int32_t* __restrict__ seg_status,
+                                  const uint32_t* __restrict__ seg_end, const XpressSeg* __restrict__ index, uint32_t stride,
+                                  const uint64_t* __restrict__ out_off, uint32_t count, uint8_t* __restrict__ out,
+                                  uint32_t* __restrict__ out_len, int32_t* __restrict__ status)
+{
+    __shared__ LzBlockSmem sm;
+    __shared__ int s_bad;
+    const int tid = (int)threadIdx.x;
+    for (uint32_t u = blockIdx.x; u < count; u += gridDim.x) {
+        const XpressSeg* ix = index + (uint64_t)u * stride;
+        const uint64_t i0 = (uint64_t)u * stride;
+        const uint32_t nseg = ix[0].nseg;
+        if (tid == 0) s_bad = 0x7fffffff;                               // first failing segment
+        __syncthreads();
+        for (uint32_t sg = tid; sg < nseg; sg += blockDim.x) {
+            int st = seg_status[i0 + sg];
+            if (st == 0 && sg + 1 < nseg && seg_end[i0 + sg] != ix[sg + 1].out_pos) st = ST_DATA;
+            if (st < 0) atomicMin(&s_bad, (int)sg);
+        }
+        __syncthreads();
+        int bad = 0;
+        if (nseg == 0) bad = ST_DATA;
+        else if (s_bad != 0x7fffffff) { bad = seg_status[i0 + (uint32_t)s_bad]; if (bad == 0) bad = ST_DATA; }
+        if (bad) { if (tid == 0) { out_len[u] = 0; status[u] = bad; } __syncthreads(); continue; }
+        uint8_t* o = out + out_off[u];
+        for (uint32_t sg = 0; sg < nseg; ++sg)
+            lz_apply_block_run(sm, tok_base + out_off[u] + ix[sg].out_pos, seg_ntok[i0 + sg], o, ix[sg].out_pos);
+        if (tid == 0) { out_len[u] = seg_end[i0 + nseg - 1]; status[u] = ST_OK; }
+        __syncthreads();
+    }
+}
+
 } // namespace msc

@@ -428,10 +428,20 @@ MSCompStatus mscomp_gpu_xpress_decompress_batch_indexed(mscomp_gpu_ctx* ctx, con
     MSC_LAUNCH(ctx, xpress_parse_indexed_kernel, groups < cap ? (uint32_t)groups : cap, per_block,
                d_in, tok, b->count, b->d_in_off, b->d_in_len, b->d_out_off, b->d_out_cap, (const XpressSeg*)d_index, index_stride,
                seg_ntok, seg_status, seg_end);
-    const uint32_t ab = (b->count + LZA_WARPS_PER_BLOCK - 1) / LZA_WARPS_PER_BLOCK, acap = (uint32_t)ctx->sm_count * 16;
-    MSC_LAUNCH(ctx, xpress_apply_indexed_kernel, ab < acap ? ab : acap, 32 * LZA_WARPS_PER_BLOCK,
-               (const uint32_t*)tok, (const uint32_t*)seg_ntok, (const int32_t*)seg_status, (const uint32_t*)seg_end,
-               (const XpressSeg*)d_index, index_stride, b->d_out_off, b->count, d_out, b->d_out_len, b->d_status);
+    // few streams: a block per stream (rounds pipelined over its warps); many streams: a warp per stream fills the GPU by itself
+    static const char* amode = getenv("MSCOMP_LZ_APPLY");             // "warp" / "block" force one of them
+    const bool block_apply = amode ? strcmp(amode, "block") == 0 : b->count < (uint32_t)ctx->sm_count * 24;
+    if (block_apply) {
+        const uint32_t acap = (uint32_t)ctx->sm_count * 8;           // 8 blocks of 8 warps fill an SM
+        MSC_LAUNCH(ctx, xpress_apply_indexed_block_kernel, b->count < acap ? b->count : acap, 32 * LZB_WARPS,
+                   (const uint32_t*)tok, (const uint32_t*)seg_ntok, (const int32_t*)seg_status, (const uint32_t*)seg_end,
+                   (const XpressSeg*)d_index, index_stride, b->d_out_off, b->count, d_out, b->d_out_len, b->d_status);
+    } else {
+        const uint32_t ab = (b->count + LZA_WARPS_PER_BLOCK - 1) / LZA_WARPS_PER_BLOCK, acap = (uint32_t)ctx->sm_count * 16;
+        MSC_LAUNCH(ctx, xpress_apply_indexed_kernel, ab < acap ? ab : acap, 32 * LZA_WARPS_PER_BLOCK,
+                   (const uint32_t*)tok, (const uint32_t*)seg_ntok, (const int32_t*)seg_status, (const uint32_t*)seg_end,
+                   (const XpressSeg*)d_index, index_stride, b->d_out_off, b->count, d_out, b->d_out_len, b->d_status);
+    }
     return msc_cuda_status(cudaGetLastError(), "xpress_decompress");
 }
 

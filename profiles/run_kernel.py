@@ -50,9 +50,16 @@ else:
     enc = ms.Batch(count, in_off.data_ptr(), in_len.data_ptr(), c_off.data_ptr(), c_cap.data_ptr(), c_len.data_ptr(), st1.data_ptr())
     dec = ms.Batch(count, c_off.data_ptr(), c_len.data_ptr(), in_off.data_ptr(), in_len.data_ptr(), o_len.data_ptr(), st2.data_ptr())
     ctx.profile(True)
+    indexed = fmt == "xpress"                  # plain Xpress: with the side-band restart index (one entry per 16 KiB)
+    seg_bytes, stride = 16384, (each + 16383) // 16384
+    d_index = ctx.xpress_index_tensor(count, stride) if indexed else None
     for _ in range(reps):
-        ctx.run_batch(fmt, "compress", d_in, d_comp, enc)
-        ctx.run_batch(fmt, "decompress", d_comp, d_out, dec)
+        if indexed:
+            ctx.xpress_compress_indexed(d_in, d_comp, enc, seg_bytes, d_index, stride)
+            ctx.xpress_decompress_indexed(d_comp, d_out, dec, d_index, stride)
+        else:
+            ctx.run_batch(fmt, "compress", d_in, d_comp, enc)
+            ctx.run_batch(fmt, "decompress", d_comp, d_out, dec)
     torch.cuda.synchronize()
     assert int(st1.abs().sum()) == 0 and int(st2.abs().sum()) == 0 and torch.equal(d_out, d_in)
     C = int(c_len.to(torch.int64).sum())

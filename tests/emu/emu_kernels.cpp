@@ -102,15 +102,19 @@ void emu_xpress_encode_indexed(const uint8_t* in, uint8_t* out, uint32_t count, 
 
 void emu_xpress_decode_indexed(const uint8_t* in, uint8_t* out, uint32_t count, const uint64_t* in_off, const uint32_t* in_len,
                                const uint64_t* out_off, const uint32_t* out_cap, uint32_t* out_len, int32_t* status, uint32_t grid,
-                               const void* index, uint32_t stride)
+                               const void* index, uint32_t stride, uint32_t block_apply)
 {
     const size_t lanes = (size_t)count * stride;
     std::vector<uint32_t> tok(emu_extent(count, out_off, out_cap) + 16), seg_ntok(lanes + 1), seg_end(lanes + 1);
     std::vector<int32_t> seg_status(lanes + 1);
     emu::launch(msc::xpress_parse_indexed_kernel, dim3e(grid), dim3e(32 * msc::XPD_WARPS_PER_BLOCK), in, tok.data(), count, in_off, in_len, out_off, out_cap,
                 (const msc::XpressSeg*)index, stride, seg_ntok.data(), seg_status.data(), seg_end.data());
-    emu::launch(msc::xpress_apply_indexed_kernel, dim3e(grid), dim3e(32 * msc::LZA_WARPS_PER_BLOCK), (const uint32_t*)tok.data(), (const uint32_t*)seg_ntok.data(),
-                (const int32_t*)seg_status.data(), (const uint32_t*)seg_end.data(), (const msc::XpressSeg*)index, stride, out_off, count, out, out_len, status);
+    if (block_apply)
+        emu::launch(msc::xpress_apply_indexed_block_kernel, dim3e(grid), dim3e(32 * msc::LZB_WARPS), (const uint32_t*)tok.data(), (const uint32_t*)seg_ntok.data(),
+                    (const int32_t*)seg_status.data(), (const uint32_t*)seg_end.data(), (const msc::XpressSeg*)index, stride, out_off, count, out, out_len, status);
+    else
+        emu::launch(msc::xpress_apply_indexed_kernel, dim3e(grid), dim3e(32 * msc::LZA_WARPS_PER_BLOCK), (const uint32_t*)tok.data(), (const uint32_t*)seg_ntok.data(),
+                    (const int32_t*)seg_status.data(), (const uint32_t*)seg_end.data(), (const msc::XpressSeg*)index, stride, out_off, count, out, out_len, status);
 }
 
 // Chunk index of an LZNT1 stream, built range by range (range_segs segments at a time) like the pipelined host wrapper does.

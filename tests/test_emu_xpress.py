@@ -78,8 +78,9 @@ def test_decode_status_equals_oracle_on_bad_input(emu, oracle, ms, fmt, variant)
             assert outs[i] == exp
 
 
+@pytest.mark.parametrize("block_apply", [0, 1], ids=["warp-per-stream", "block-per-stream"])
 @pytest.mark.parametrize("seg_bytes,stride", [(2048, 80), (4096, 8), (16384, 16)])
-def test_xpress_restart_index(emu, oracle, ms, seg_bytes, stride):
+def test_xpress_restart_index(emu, oracle, ms, seg_bytes, stride, block_apply):
     """The side-band restart index of plain Xpress: the stream itself is unchanged (same bytes as the plain call, decodes with
     the oracle), and the one-lane-per-segment decoder reproduces the input from (stream, index)."""
     rnd = random.Random(seg_bytes)
@@ -101,7 +102,7 @@ def test_xpress_restart_index(emu, oracle, ms, seg_bytes, stride):
         assert ix[i, 0, 5] == want, (len(p), ix[i, 0])
         outs_pos = [int(x) for x in ix[i, :want, 1]]
         assert outs_pos == sorted(outs_pos) and outs_pos[0] == 0
-    st, ol, outs = emu_batch(emu, "emu_xpress_decode_indexed", comps, [len(p) for p in plains], extra=(P(index), ctypes.c_uint32(stride)))
+    st, ol, outs = emu_batch(emu, "emu_xpress_decode_indexed", comps, [len(p) for p in plains], extra=(P(index), ctypes.c_uint32(stride), ctypes.c_uint32(block_apply)))
     st_plain, _, outs_plain = emu_batch(emu, "emu_xpress_decode2", comps, [len(p) for p in plains])
     assert list(st) == list(st_plain) and list(st) == [0 if p else -3 for p in plains]       # (FF FF FF FF is rejected, as upstream)
     assert outs == outs_plain and all(o == p for o, p in zip(outs, plains) if p)
@@ -113,7 +114,7 @@ def test_xpress_restart_index(emu, oracle, ms, seg_bytes, stride):
         bad[rnd.randrange(len(bad))] ^= 1 << rnd.randrange(8)
         one_ix = ix[i:i + 1].copy().reshape(-1)
         for data, cap in ((bytes(bad), len(plains[i])), (comps[i], len(plains[i]) - 1), (comps[i], len(plains[i]) // 2)):
-            st1, _, out1 = emu_batch(emu, "emu_xpress_decode_indexed", [data], [cap], extra=(P(one_ix), ctypes.c_uint32(stride)))
+            st1, _, out1 = emu_batch(emu, "emu_xpress_decode_indexed", [data], [cap], extra=(P(one_ix), ctypes.c_uint32(stride), ctypes.c_uint32(block_apply)))
             ref = oracle.decompress("xpress", data, cap)
             if data is comps[i]:
                 assert st1[0] == ref[0] and (ref[0] < 0 or out1[0] == ref[1])
