@@ -199,7 +199,8 @@ MSCompStatus lznt1_decompress_pipelined(mscomp_gpu_ctx* ctx, const_bytes in, siz
     int32_t* d_status = (int32_t*)ctx->get(SC_STATUS, (ncap + 1) * sizeof(int32_t));
     uint8_t* d_box = (uint8_t*)ctx->get(SC_RESULT, 1024);        // index state at +0, per-range summaries at +256
     uint8_t* h_box = (uint8_t*)ctx->get_pinned(4096);            // per-range copies of the state at +256, of the summaries at +2048
-    if (!d_in || !d_out || !d_offs || !d_sizes || !d_status || !d_box || !h_box) return MSCOMP_MEM_ERROR;
+    if (!d_in || !d_out || !d_offs || !d_sizes || !d_status || !d_box || !h_box) return MSC_FALLBACK;   // (an oversized *out_len makes this
+                                                                         // path ask for far more than the stream needs; the simple path sizes exactly)
     msc_lznt1_index_state* d_state = (msc_lznt1_index_state*)d_box;
     auto h_state = [&](size_t k) { return (msc_lznt1_index_state*)(h_box + 256 + 64 * (k % 8)); };
     auto h_sum = [&](size_t k) { return (mscomp_gpu_result*)(h_box + 2048 + 64 * (k % 8)); };
