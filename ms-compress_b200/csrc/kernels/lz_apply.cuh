@@ -231,4 +231,16 @@ __device__ __forceinline__ uint32_t lz_apply_block_run(LzBlockSmem& sm, const ui
     return pstart;
 }
 
+// Stream i: tokens tok_base + 4 * out_off[i] (ntok[i] of them) -> out + out_off[i], one block per stream.
+__global__ void __launch_bounds__(32 * LZB_WARPS)
+lz_apply_block_kernel(const uint32_t* __restrict__ tok_base, const uint32_t* __restrict__ ntok, const uint64_t* __restrict__ out_off,
+                      const int32_t* __restrict__ status, uint32_t count, uint8_t* __restrict__ out)
+{
+    __shared__ LzBlockSmem sm;
+    for (uint32_t s = blockIdx.x; s < count; s += gridDim.x) {
+        if (status[s] < 0) continue;                                   // (block-uniform)
+        lz_apply_block_run(sm, tok_base + out_off[s], ntok[s], out + out_off[s], 0u);
+    }
+}
+
 } // namespace msc

@@ -145,6 +145,134 @@ xpress_parse_kernel(const uint8_t* __restrict__ in, uint32_t* __restrict__ tok, 
     xpress_decode_body<LaneTok>(in, nullptr, tok, count, in_off, in_len, out_off, out_cap, out_len, status, ntok);
 }
 
+// ---- one WARP per stream ------------------------------------------------------------------------------------------------
+// A stream without a restart index (any reference-made stream) is a serial chain, but not a byte-serial one: the 32 items
+// behind a flag word are 1 (literal) or 2 (match symbol) bytes each, plus the rare length extensions.  A warp parses a whole
+// flag group at a time: lane i takes item i, its offset is the prefix sum of the base sizes, and the extended matches of
+// the group (length field 7) are resolved in order -- the lowest unresolved one always has an exact offset, it reads its
+// extension bytes, and the lanes behind it shift.  ~150 warp instructions per 32 items instead of ~115 per item and lane:
+// the latency of ONE stream drops by the warp width, which is what the one-shot xpress_decompress of a single buffer and
+// batches of few, large reference-made streams need.  Same statuses as xp_step (the first failing item in order decides).
+__device__ __forceinline__ uint32_t xpw_rd(const uint8_t* __restrict__ in, uint32_t at, uint32_t nbytes)
+{
+    uint32_t v = 0;
+    for (uint32_t k = 0; k < nbytes; ++k) v |= (uint32_t)__ldg(in + at + k) << (8 * k);
+    return v;
+}
+
+__global__ void __launch_bounds__(32 * XPD_WARPS_PER_BLOCK)
+xpress_parse_warp_kernel(const uint8_t* __restrict__ in_base, uint32_t* __restrict__ tok_base, uint32_t count,
+                         const uint64_t* __restrict__ in_off, const uint32_t* __restrict__ in_len_a,
+                         const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ out_cap,
+                         uint32_t* __restrict__ out_len, int32_t* __restrict__ status, uint32_t* __restrict__ ntok_out)
+{
+    const int lane = lane_id();
+    const uint32_t warps_total = gridDim.x * XPD_WARPS_PER_BLOCK;
+    for (uint32_t u = blockIdx.x * XPD_WARPS_PER_BLOCK + (threadIdx.x >> 5); u < count; u += warps_total) {
+        const uint8_t* in = in_base + in_off[u];
+        const uint32_t n = in_len_a[u], cap = out_cap[u];
+        uint32_t* tok = tok_base + out_off[u];
+        uint32_t ip = 0, opos = 0, ntok = 0, half_val = 0;
+        bool has_half = false;
+        int st = 0;                                                        // 0 running, 1 finished OK, < 0 error (warp-uniform)
+        if (n < 5) {                                                       // :414-418 (sic)
+            uint32_t w = 0;
+            if (n == 4) w = xpw_rd(in, 0, 4);
+            st = (n == 0 || (n == 4 && w != 0xFFFFFFFFu)) ? 1 : ST_DATA;
+        }
+        while (st == 0) {
+            if (ip + 4 > n) { st = ST_DATA; break; }                       // :461
+            const uint32_t f = xpw_rd(in, ip, 4);
+            ip += 4;
+            const bool flagged = ((f >> (31 - lane)) & 1u) != 0;
+            const uint32_t bsz = flagged ? 2u : 1u;
+            uint32_t o = ip + (uint32_t)warp_incl_scan((int)bsz) - bsz;   // offset of my item, exact up to the first unresolved extension
+            uint32_t mlen = 0, xbytes = 0;                                 // resolved extended length / its extension bytes (mine)
+            unsigned resolved = 0;
+            int xerr = 0;                                                  // error found while reading my extension
+            uint32_t sym = 0;
+            for (;;) {
+                sym = (flagged && (uint64_t)o + 2 <= n) ? xpw_rd(in, o, 2) : 0u;
+                const unsigned cand = __ballot_sync(FULL, flagged && (uint64_t)o + 2 <= n && (sym & 7u) == 7u) & ~resolved;
+                if (!cand) break;
+                const int e = __ffs((int)cand) - 1;                        // lowest unresolved extended match: its offset is exact
+                uint32_t extra = 0, hv = half_val;
+                bool hh = has_half;
+                if (lane == e) {
+                    uint32_t p = o + 2, len;
+                    do {
+                        if (hh) { len = hv >> 4; hh = false; }
+                        else if (p >= n) { xerr = ST_DATA; len = 0; break; }
+                        else { hv = xpw_rd(in, p, 1); hh = true; len = hv & 0xFu; ++p; }
+                        if (len == 0xF) {
+                            if (p >= n) { xerr = ST_DATA; break; }
+                            len = xpw_rd(in, p, 1); ++p;
+                            if (len == 0xFF) {
+                                if ((uint64_t)p + 2 > n) { xerr = ST_DATA; break; }
+                                len = xpw_rd(in, p, 2); p += 2;
+                                if (len == 0) {
+                                    if ((uint64_t)p + 4 > n) { xerr = ST_DATA; break; }
+                                    len = xpw_rd(in, p, 4); p += 4;
+                                }
+                                if (len < 0xF + 0x7) { xerr = ST_DATA; break; }
+                                len -= 0xF + 0x7;
+                            }
+                            len += 0xF;
+                        }
+                        len += 0x7;
+                    } while (false);
+                    mlen = len + 3;
+                    extra = p - (o + 2);
+                    xbytes = extra;
+                }
+                extra = __shfl_sync(FULL, extra, e);
+                half_val = __shfl_sync(FULL, hv, e);
+                has_half = __shfl_sync(FULL, (int)hh, e) != 0;
+                const int ee = __shfl_sync(FULL, xerr, e);
+                if (lane > e) o += extra;
+                resolved |= 1u << e;
+                if (ee) break;                                             // nothing behind a broken item is looked at
+            }
+            // what every lane's item is: end of stream, broken, literal or match
+            const bool at_end = o == n;                                    // the stream ends where this item would start (:433-438)
+            const unsigned endm = __ballot_sync(FULL, at_end);
+            const int nitems = endm ? (__ffs((int)endm) - 1) : 32;
+            const bool mine = lane < nitems;
+            uint32_t len = 0, off = 0;
+            int err = 0;
+            if (mine) {
+                if (flagged) {
+                    if ((uint64_t)o + 2 > n) err = ST_DATA;
+                    else if (xerr) err = xerr;
+                    else { off = (sym >> 3) + 1; len = ((sym & 7u) == 7u) ? mlen : (sym & 7u) + 3; }
+                } else len = 1;
+            }
+            const uint32_t pos = opos + (uint32_t)warp_incl_scan((int)len) - len;
+            if (mine && !err) {
+                if (flagged) { if (off > pos) err = ST_DATA; else if ((uint64_t)pos + len > cap) err = ST_BUF; }   // :442-443
+                else if (pos == cap) err = ST_BUF;                                                                  // :455
+            }
+            int end_err = 0;
+            if (endm && lane == nitems) end_err = ((f & (0xFFFFFFFFu >> lane)) == (0xFFFFFFFFu >> lane)) ? 0 : ST_DATA;
+            const unsigned errm = __ballot_sync(FULL, err != 0 || end_err != 0);
+            if (errm) { const int l = __ffs((int)errm) - 1; st = __shfl_sync(FULL, err ? err : end_err, l); break; }
+            // tokens (a match longer than LZQ_MAXLEN takes several)
+            const uint32_t nt = mine ? (flagged ? (len + LZQ_MAXLEN - 1) / LZQ_MAXLEN : 1u) : 0u;
+            const uint32_t tincl = (uint32_t)warp_incl_scan((int)nt);
+            if (mine) {
+                uint32_t* t = tok + ntok + tincl - nt;
+                if (!flagged) *t = lzt_lit(xpw_rd(in, o, 1));
+                else { uint32_t l = len; while (l) { const uint32_t c = l > LZQ_MAXLEN ? LZQ_MAXLEN : l; *t++ = lzt_match(off, c); l -= c; } }
+            }
+            ntok += __shfl_sync(FULL, tincl, 31);
+            opos = __shfl_sync(FULL, pos + len, 31 < nitems ? 31 : (nitems ? nitems - 1 : 0));
+            if (endm) { st = 1; break; }
+            ip = __shfl_sync(FULL, o + bsz + xbytes, 31);                  // first byte behind the last item = next flag word
+        }
+        if (lane == 0) { out_len[u] = opos; status[u] = st == 1 ? ST_OK : st; ntok_out[u] = ntok; }
+    }
+}
+
 // Indexed parse: streams that come with a restart index (XpressSeg, made by xpress_encode_kernel) are parsed by one lane per
 // SEGMENT instead of one lane per stream.  Lane i handles segment i % stride of stream i / stride; tokens of a segment go to
 // tok + out_off + seg.out_pos (a token stands for at least one output byte, so segments cannot collide).

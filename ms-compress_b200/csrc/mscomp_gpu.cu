@@ -395,13 +395,30 @@ MSCompStatus mscomp_gpu_xpress_decompress_batch(mscomp_gpu_ctx* ctx, const uint8
     if (!b->count) return MSCOMP_OK;
     cudaSetDevice(ctx->device);
     const uint32_t groups = (b->count + 32 * XPD_WARPS_PER_BLOCK - 1) / (32 * XPD_WARPS_PER_BLOCK), cap = (uint32_t)ctx->sm_count * 8;
-    uint32_t* tok = b->count >= 64 ? token_scratch(ctx, b) : nullptr;
+    // Few streams (down to the single buffer of the one-shot call): a WARP parses a stream, 32 items at a time, and a BLOCK
+    // applies it; many streams: a lane parses a stream and a warp applies it -- the batch itself fills the GPU then.
+    static const char* pmode = getenv("MSCOMP_XPRESS_PARSE");         // "lane" / "warp" force one of the parsers
+    static const char* amode = getenv("MSCOMP_LZ_APPLY");             // "warp" / "block" force one of the apply kernels
+    const bool warp_parse = pmode ? strcmp(pmode, "warp") == 0 : b->count < (uint32_t)ctx->sm_count * 64;
+    const bool block_apply = amode ? strcmp(amode, "block") == 0 : b->count < (uint32_t)ctx->sm_count * 24;
+    uint32_t* tok = (warp_parse || b->count >= 64) ? token_scratch(ctx, b) : nullptr;
     uint32_t* ntok = tok ? (uint32_t*)ctx->get(SC_AUX1, ((size_t)b->count + 1) * sizeof(uint32_t)) : nullptr;
     if (tok && ntok) {
-        MSC_LAUNCH(ctx, xpress_parse_kernel, groups < cap ? groups : cap, 32 * XPD_WARPS_PER_BLOCK,
-                   d_in, tok, b->count, b->d_in_off, b->d_in_len, b->d_out_off, b->d_out_cap, b->d_out_len, b->d_status, ntok);
-        const uint32_t ab = (b->count + LZA_WARPS_PER_BLOCK - 1) / LZA_WARPS_PER_BLOCK, acap = (uint32_t)ctx->sm_count * 16;
-        MSC_LAUNCH(ctx, lz_apply_kernel, ab < acap ? ab : acap, 32 * LZA_WARPS_PER_BLOCK, tok, ntok, b->d_out_off, b->d_status, b->count, d_out);
+        if (warp_parse) {
+            const uint32_t wb = (b->count + XPD_WARPS_PER_BLOCK - 1) / XPD_WARPS_PER_BLOCK, wcap = (uint32_t)ctx->sm_count * 16;
+            MSC_LAUNCH(ctx, xpress_parse_warp_kernel, wb < wcap ? wb : wcap, 32 * XPD_WARPS_PER_BLOCK,
+                       d_in, tok, b->count, b->d_in_off, b->d_in_len, b->d_out_off, b->d_out_cap, b->d_out_len, b->d_status, ntok);
+        } else {
+            MSC_LAUNCH(ctx, xpress_parse_kernel, groups < cap ? groups : cap, 32 * XPD_WARPS_PER_BLOCK,
+                       d_in, tok, b->count, b->d_in_off, b->d_in_len, b->d_out_off, b->d_out_cap, b->d_out_len, b->d_status, ntok);
+        }
+        if (block_apply) {
+            const uint32_t acap = (uint32_t)ctx->sm_count * 8;
+            MSC_LAUNCH(ctx, lz_apply_block_kernel, b->count < acap ? b->count : acap, 32 * LZB_WARPS, tok, ntok, b->d_out_off, b->d_status, b->count, d_out);
+        } else {
+            const uint32_t ab = (b->count + LZA_WARPS_PER_BLOCK - 1) / LZA_WARPS_PER_BLOCK, acap = (uint32_t)ctx->sm_count * 16;
+            MSC_LAUNCH(ctx, lz_apply_kernel, ab < acap ? ab : acap, 32 * LZA_WARPS_PER_BLOCK, tok, ntok, b->d_out_off, b->d_status, b->count, d_out);
+        }
     } else {
         MSC_LAUNCH(ctx, xpress_decode_kernel, groups < cap ? groups : cap, 32 * XPD_WARPS_PER_BLOCK,
                    d_in, d_out, b->count, b->d_in_off, b->d_in_len, b->d_out_off, b->d_out_cap, b->d_out_len, b->d_status);

@@ -91,6 +91,15 @@ void emu_xpress_decode2(const uint8_t* in, uint8_t* out, uint32_t count, const u
     emu::launch(msc::lz_apply_kernel, dim3e(grid), dim3e(32 * msc::LZA_WARPS_PER_BLOCK), (const uint32_t*)tok.data(), (const uint32_t*)ntok.data(), out_off, (const int32_t*)status, count, out);
 }
 
+// few-stream variant: one warp parses a stream (a flag group of 32 items at a time), one block applies it
+void emu_xpress_decode_warp(const uint8_t* in, uint8_t* out, uint32_t count, const uint64_t* in_off, const uint32_t* in_len,
+                            const uint64_t* out_off, const uint32_t* out_cap, uint32_t* out_len, int32_t* status, uint32_t grid)
+{
+    std::vector<uint32_t> tok(emu_extent(count, out_off, out_cap) + 64), ntok(count + 1);
+    emu::launch(msc::xpress_parse_warp_kernel, dim3e(grid), dim3e(32 * msc::XPD_WARPS_PER_BLOCK), in, tok.data(), count, in_off, in_len, out_off, out_cap, out_len, status, ntok.data());
+    emu::launch(msc::lz_apply_block_kernel, dim3e(grid), dim3e(32 * msc::LZB_WARPS), (const uint32_t*)tok.data(), (const uint32_t*)ntok.data(), out_off, (const int32_t*)status, count, out);
+}
+
 // plain Xpress with the side-band restart index: encode writes it, decode parses one lane per segment
 void emu_xpress_encode_indexed(const uint8_t* in, uint8_t* out, uint32_t count, const uint64_t* in_off, const uint32_t* in_len,
                                const uint64_t* out_off, const uint32_t* out_cap, uint32_t* out_len, int32_t* status, uint32_t grid,

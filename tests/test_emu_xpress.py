@@ -22,10 +22,11 @@ def corpus(ms):
     return out
 
 
-DECODERS = {"xpress_huff": ["emu_xhuff_decode", "emu_xhuff_decode2"], "xpress": ["emu_xpress_decode", "emu_xpress_decode2"]}   # fused, parse+apply
+DECODERS = {"xpress_huff": ["emu_xhuff_decode", "emu_xhuff_decode2", "emu_xhuff_decode2"],           # fused, parse+apply
+            "xpress": ["emu_xpress_decode", "emu_xpress_decode2", "emu_xpress_decode_warp"]}         # fused, lane parse + warp apply, warp parse + block apply
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("fmt", ["xpress_huff", "xpress"])
 def test_decode_matches_oracle(emu, oracle, ms, fmt, variant):
     plains = corpus(ms)
@@ -53,7 +54,7 @@ def test_encode_roundtrips_through_oracle(emu, oracle, ms, fmt):
     assert len(ours) <= 1.15 * len(oracle.compress(fmt, p))
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("fmt", ["xpress_huff", "xpress"])
 def test_decode_status_equals_oracle_on_bad_input(emu, oracle, ms, fmt, variant):
     rnd = random.Random(5)
