@@ -25,4 +25,29 @@ for kern in ("emu_lznt1_decode","emu_lznt1_decode_lanes"):
         st,sz,ch=emu_util.emu_lznt1_decode(emu,c,kernel=kern); assert not st.any() and b''.join(ch)==p
         e,_=emu_util.emu_lznt1_encode(emu,p); assert e==c
     print(kern,'ok')
+# two-kernel decoders, warp parser + block apply, restart index, heavy LZNT1 chunks, GPU chunk index
+import numpy as np, random
+for fmt,dk in (("xpress_huff","emu_xhuff_decode2"),("xpress","emu_xpress_decode2"),("xpress","emu_xpress_decode_warp")):
+    comps=[ocall(fmt+'_compress',p,MAX[fmt](len(p))+16)[1] for p in plains]
+    st,ol,outs2=emu_util.emu_batch(emu,dk,comps,[len(p) for p in plains])
+    assert not st.any() and outs2==plains
+    print(dk,'ok')
+stride=12; index=np.zeros(len(plains)*stride*6,dtype=np.uint32)
+st,_,comps=emu_util.emu_batch(emu,"emu_xpress_encode_indexed",plains,[MAX["xpress"](len(p)) for p in plains],extra=(ctypes.c_uint32(16384),emu_util.P(index),ctypes.c_uint32(stride)))
+assert not st.any()
+for blk in (0,1):
+    st,_,outs2=emu_util.emu_batch(emu,"emu_xpress_decode_indexed",comps,[len(p) for p in plains],extra=(emu_util.P(index),ctypes.c_uint32(stride),ctypes.c_uint32(blk)))
+    assert not st.any() and outs2==plains
+print('xpress restart index ok')
+rnd=random.Random(3)
+heavy=bytes(rnd.choice(b"ACGT") for _ in range(2*4096+50))
+rc,c=ocall('lznt1_compress',heavy,len(heavy)+100)
+for hw in (32768,0):
+    e,_=emu_util.emu_lznt1_encode(emu,heavy,heavy_work=hw); assert e==c
+rc,c=ocall('lznt1_compress',plains[3],len(plains[3])+100)
+a,addr=emu_util.padded(c); offs=np.zeros(len(c)//3+3,dtype=np.uint64); stt=np.zeros(4,dtype=np.uint64)
+emu.emu_lznt1_index.restype=ctypes.c_int
+assert emu.emu_lznt1_index(ctypes.c_void_p(addr),ctypes.c_uint64(len(c)),ctypes.c_uint32(4112),ctypes.c_uint32(3),emu_util.P(offs),ctypes.c_uint64(len(c)//3+2),emu_util.P(stt))==0
+assert int(stt[0])==1 and int(stt[3])==(len(plains[3])+4095)//4096
+print('heavy chunks + chunk index ok')
 print('sanitized run ok')
