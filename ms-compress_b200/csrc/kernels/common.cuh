@@ -46,9 +46,10 @@ __device__ __forceinline__ uint32_t ld_byte_cg(const uint8_t* p)
     return *p;
 #endif
 }
-// Shared-memory words other warps update while this one polls them.
-__device__ __forceinline__ uint32_t ld_shared_volatile(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
-__device__ __forceinline__ void st_shared_volatile(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
+// Shared-memory words other warps update while this one polls them: atomics on both sides (a deliberate signal between
+// warps, and the form compute-sanitizer's racecheck understands as such).
+__device__ __forceinline__ uint32_t ld_shared_signal(uint32_t* p) { return atomicAdd(p, 0u); }
+__device__ __forceinline__ void st_shared_signal(uint32_t* p, uint32_t v) { atomicExch(p, v); }
 __device__ __forceinline__ void spin_pause()
 {
 #ifndef MSC_EMU

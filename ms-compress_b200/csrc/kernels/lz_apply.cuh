@@ -184,7 +184,9 @@ __device__ __forceinline__ uint32_t lz_apply_block_run(LzBlockSmem& sm, const ui
                 __syncwarp();
                 const unsigned W = __reduce_min_sync(FULL, pending ? pos : 0xffffffffu);
                 if (W == 0xffffffffu) break;
-                const uint32_t d = ld_shared_volatile(&sm.done_upto);
+                uint32_t d = 0;
+                if (lane == 0) d = ld_shared_signal(&sm.done_upto);
+                d = __shfl_sync(FULL, d, 0);
                 const bool prev_done = d >= r;
                 const uint32_t F = sm.p0[prev_done ? r : d];               // everything below F is final
                 const bool can = pending && (be <= F || ((a >= p0r || prev_done) && (pos == W || be <= W)));
@@ -215,11 +217,11 @@ __device__ __forceinline__ uint32_t lz_apply_block_run(LzBlockSmem& sm, const ui
             __syncwarp();
             __threadfence_block();
             if (lane == 0) {
-                st_shared_volatile(&sm.flag[r], 1u);
+                st_shared_signal(&sm.flag[r], 1u);
                 __threadfence_block();
                 for (;;) {
-                    const uint32_t d = ld_shared_volatile(&sm.done_upto);
-                    if (d >= R || !ld_shared_volatile(&sm.flag[d])) break;
+                    const uint32_t d = ld_shared_signal(&sm.done_upto);
+                    if (d >= R || !ld_shared_signal(&sm.flag[d])) break;
                     atomicCAS(&sm.done_upto, d, d + 1);
                 }
             }
