@@ -94,6 +94,21 @@ __device__ __forceinline__ uint32_t lzf_match_len(const uint8_t* __restrict__ sr
     return i;
 }
 
+// Indexes positions [from, to) of src[0..n) without searching them: the history a segment-wise encoder wants in the table
+// before it starts in the middle of a buffer.  Same insert order as lzf_tile.  Must be called by all LZF_THREADS threads.
+__device__ __forceinline__ void lzf_warm(LzFrontSmem& sm, const uint8_t* __restrict__ src, uint32_t n, uint32_t from, uint32_t to)
+{
+    const int tid = (int)threadIdx.x;
+    for (uint32_t s0 = from; s0 < to; s0 += LZF_THREADS * LZF_STEP) {
+#pragma unroll
+        for (int u = 0; u < LZF_STEP; ++u) {
+            const uint32_t p = s0 + (uint32_t)u * LZF_THREADS + tid;
+            if (p < to && p + 3 <= n) lzf_insert(&sm.H[lzf_hash3(lzf_ld4(src, p, n) & 0xFFFFFFu)], p + 1, s0 + 1);
+        }
+        __syncthreads();
+    }
+}
+
 // Match search + greedy parse for tile [t0, t0 + LZF_TILE) of the unit src[0..n).  `window` = largest usable
 // offset, `far3` = largest offset accepted for a 3-byte match.  On return sm.lenoff / sm.M / sm.V / sm.prefV
 // describe the tile and sm.next_p has advanced; the number of tokens starting in the tile is returned.

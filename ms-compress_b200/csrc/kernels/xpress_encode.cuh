@@ -53,12 +53,26 @@ __device__ __forceinline__ uint32_t xpe_match_bytes(uint32_t lm3, bool new_half)
     return b;
 }
 
-__global__ void __launch_bounds__(XPE_THREADS)
-xpress_encode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint32_t count,
+// Two-pass variant for large buffers: match finding is the expensive part and needs no stream state, so it runs per 64 KiB
+// segment on its own block (xpress_match_kernel: matches and parse never cross a segment, the results of every tile -- lenoff,
+// visited bitmap, carried-in position -- go to scratch); the emission, which IS sequential along the stream (flag words,
+// shared nibbles), then only replays tiles from scratch (PRE = true).  One buffer no longer costs one block its whole
+// match-finding time: few large buffers, down to the single buffer of the one-shot call, use the whole GPU for the expensive part.
+constexpr uint32_t XPE_SEG = 65536;                                  // match-finding segment (a multiple of LZF_TILE)
+constexpr uint32_t XPE_SEG_TILES = XPE_SEG / LZF_TILE;
+struct XpPre {                                                       // scratch of the two-pass variant, indexed by global tile number
+    const uint32_t* seg_first;                                       // [count + 1] first global segment of every buffer
+    uint32_t* lenoff;                                                // [tiles][LZF_TILE]
+    uint32_t* visited;                                               // [tiles][LZF_TILE / 32]
+    uint32_t* next_p;                                                // [tiles] position (relative to the segment) where the parse enters the tile
+};
+
+template <bool PRE>
+__device__ __forceinline__ void xpress_encode_body(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint32_t count,
                      const uint64_t* __restrict__ in_off, const uint32_t* __restrict__ in_len,
                      const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ out_cap,
                      uint32_t* __restrict__ out_len, int32_t* __restrict__ status,
-                     uint32_t seg_tiles, XpressSeg* __restrict__ index, uint32_t index_stride)     // optional restart index
+                     uint32_t seg_tiles, XpressSeg* __restrict__ index, uint32_t index_stride, const XpPre pre)
 {
     MSC_DYN_SMEM(smem_raw);
     XpEncSmem& sm = *reinterpret_cast<XpEncSmem*>(smem_raw);
@@ -68,7 +82,7 @@ xpress_encode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, 
         const uint8_t* src = in + in_off[u];
         const uint32_t n = in_len[u], cap = out_cap[u];
         uint8_t* o = out + out_off[u];
-        for (int i = tid; i < (1 << LZF_HBITS); i += XPE_THREADS) sm.lz.H[i] = 0;
+        if (!PRE) for (int i = tid; i < (1 << LZF_HBITS); i += XPE_THREADS) sm.lz.H[i] = 0;
         if (tid == 0) {
             sm.lz.next_p = 0; sm.lz.ntok = 0;
             sm.items = 0; sm.bytes = 0; sm.nibs = 0; sm.pend_half = 0; sm.cur_flags = 0; sm.cur_flagpos = 0;
@@ -83,6 +97,12 @@ xpress_encode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, 
             idx[0] = XpressSeg{0u, 0u, 0u, 0u, 0xFFFFFFFFu, nseg < index_stride ? nseg : index_stride};
         }
         for (uint32_t t0 = 0; t0 < n && sm.status == ST_OK; t0 += LZF_TILE) {
+            uint32_t tile = 0;
+            if (PRE) {                                                       // where the parse enters this tile (known from pass 1)
+                tile = (pre.seg_first[u] + t0 / XPE_SEG) * XPE_SEG_TILES + (t0 % XPE_SEG) / LZF_TILE;
+                if (tid == 0) sm.lz.next_p = (t0 / XPE_SEG) * XPE_SEG + pre.next_p[tile];
+                __syncthreads();
+            }
             if (idx && tid == 0 && t0 && (t0 / LZF_TILE) % seg_tiles == 0 && t0 / (LZF_TILE * seg_tiles) < index_stride) {
                 const uint32_t k = sm.items, c = k & 31u;                    // next item; the state below is final for everything before it
                 XpressSeg e;
@@ -94,7 +114,14 @@ xpress_encode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, 
                 e.nseg = 0;
                 idx[t0 / (LZF_TILE * seg_tiles)] = e;
             }
-            lzf_tile(sm.lz, src, n, t0, 8192u, 8192u);
+            if (PRE) {
+                const uint32_t* lo = pre.lenoff + (uint64_t)tile * LZF_TILE;
+                for (int r = tid; r < LZF_TILE; r += XPE_THREADS) sm.lz.lenoff[r] = lo[r];
+                if (tid < LZF_TILE / 32) sm.lz.V[tid] = pre.visited[(uint64_t)tile * (LZF_TILE / 32) + tid];
+                __syncthreads();
+            } else {
+                lzf_tile(sm.lz, src, n, t0, 8192u, 8192u);
+            }
             // ---- per-thread item statistics over 8 consecutive positions ----
             const uint32_t items0 = sm.items, bytes0 = sm.bytes, nibs0 = sm.nibs;
             uint32_t my_items = 0, my_bytes = 0, my_nibs = 0;
@@ -230,6 +257,100 @@ xpress_encode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, 
             status[u] = sm.status;
         }
         __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(XPE_THREADS)
+xpress_encode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint32_t count,
+                     const uint64_t* __restrict__ in_off, const uint32_t* __restrict__ in_len,
+                     const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ out_cap,
+                     uint32_t* __restrict__ out_len, int32_t* __restrict__ status,
+                     uint32_t seg_tiles, XpressSeg* __restrict__ index, uint32_t index_stride)     // optional restart index
+{
+    xpress_encode_body<false>(in, out, count, in_off, in_len, out_off, out_cap, out_len, status, seg_tiles, index, index_stride, XpPre{});
+}
+
+// Pass 2 of the two-pass variant: emission from the per-tile results of xpress_match_kernel.
+__global__ void __launch_bounds__(XPE_THREADS)
+xpress_emit_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint32_t count,
+                   const uint64_t* __restrict__ in_off, const uint32_t* __restrict__ in_len,
+                   const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ out_cap,
+                   uint32_t* __restrict__ out_len, int32_t* __restrict__ status,
+                   uint32_t seg_tiles, XpressSeg* __restrict__ index, uint32_t index_stride, XpPre pre)
+{
+    xpress_encode_body<true>(in, out, count, in_off, in_len, out_off, out_cap, out_len, status, seg_tiles, index, index_stride, pre);
+}
+
+// seg_first[u] = segments of the buffers before u, seg_first[count] = all of them; totals[0] = that, totals[1] = input bytes.
+// Single block; also clears the work counter of the match kernel.
+__global__ void __launch_bounds__(1024)
+xpress_segments_kernel(const uint32_t* __restrict__ in_len, uint32_t count, uint32_t* __restrict__ seg_first, unsigned long long* __restrict__ totals,
+                       uint32_t* __restrict__ work_counter)
+{
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t carry;
+    __shared__ unsigned long long bytes;
+    const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { carry = 0; bytes = 0; *work_counter = 0; }
+    __syncthreads();
+    unsigned long long my_bytes = 0;
+    for (uint32_t u0 = 0; u0 < count; u0 += 1024) {
+        const uint32_t u = u0 + (uint32_t)tid;
+        const uint32_t n = u < count ? in_len[u] : 0u;
+        const uint32_t v = u < count ? (n + XPE_SEG - 1) / XPE_SEG : 0u;      // (an empty buffer has no segment: the emitter handles it alone)
+        my_bytes += n;
+        const uint32_t incl = (uint32_t)warp_incl_scan((int)v);
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        uint32_t woff = carry;
+        for (int w = 0; w < warp; ++w) woff += wsum[w];
+        if (u < count) seg_first[u] = woff + incl - v;
+        __syncthreads();
+        if (tid == 1023) carry = woff + incl;
+        __syncthreads();
+    }
+    atomicAdd(&bytes, my_bytes);
+    __syncthreads();
+    if (tid == 0) { seg_first[count] = carry; totals[0] = carry; totals[1] = bytes; }
+}
+
+// Pass 1 of the two-pass variant: persistent blocks pull (buffer, segment) pairs from a work counter and run the LZ77 front end
+// over the segment as if it were a buffer of its own.
+__global__ void __launch_bounds__(XPE_THREADS)
+xpress_match_kernel(const uint8_t* __restrict__ in, uint32_t count, const uint64_t* __restrict__ in_off, const uint32_t* __restrict__ in_len,
+                    const uint32_t* __restrict__ seg_first, uint32_t* __restrict__ work_counter,
+                    uint32_t* __restrict__ lenoff, uint32_t* __restrict__ visited, uint32_t* __restrict__ next_p)
+{
+    MSC_DYN_SMEM(smem_raw);
+    LzFrontSmem& lz = *reinterpret_cast<LzFrontSmem*>(smem_raw);
+    __shared__ uint32_t s_work;
+    const int tid = (int)threadIdx.x;
+    const uint32_t total = seg_first[count];
+    for (;;) {
+        if (tid == 0) s_work = atomicAdd(work_counter, 1u);
+        __syncthreads();
+        const uint32_t w = s_work;
+        __syncthreads();
+        if (w >= total) break;
+        uint32_t lo = 0, hi = count;                                  // the buffer u with seg_first[u] <= w < seg_first[u + 1]
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) / 2; if (seg_first[mid] <= w) lo = mid; else hi = mid; }
+        const uint32_t u = lo, sg = w - seg_first[u];
+        const uint8_t* src = in + in_off[u];                          // positions are relative to the buffer: matches may reach back
+        const uint32_t seg_start = sg * XPE_SEG;                      // into the previous segment (that is earlier data of the same stream)
+        const uint32_t n = min(seg_start + XPE_SEG, in_len[u]);       // ... but neither a match nor the parse crosses the segment's end
+        for (int i = tid; i < (1 << LZF_HBITS); i += XPE_THREADS) lz.H[i] = 0;
+        __syncthreads();
+        if (sg) lzf_warm(lz, src, n, seg_start - 8192u, seg_start);   // the window's worth of history before the segment
+        if (tid == 0) { lz.next_p = seg_start; lz.ntok = 0; }
+        __syncthreads();
+        for (uint32_t t0 = seg_start; t0 < n; t0 += LZF_TILE) {
+            const uint64_t tile = (uint64_t)w * XPE_SEG_TILES + (t0 - seg_start) / LZF_TILE;
+            if (tid == 0) next_p[tile] = lz.next_p - seg_start;
+            lzf_tile(lz, src, n, t0, 8192u, 8192u);
+            for (int r = tid; r < LZF_TILE; r += XPE_THREADS) lenoff[tile * LZF_TILE + r] = lz.lenoff[r];
+            if (tid < LZF_TILE / 32) visited[tile * (LZF_TILE / 32) + tid] = lz.V[tid];
+            __syncthreads();
+        }
     }
 }
 

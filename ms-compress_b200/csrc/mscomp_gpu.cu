@@ -360,17 +360,71 @@ MSCompStatus mscomp_gpu_xpress_huff_decompress_batch(mscomp_gpu_ctx* ctx, const 
     return msc_cuda_status(cudaGetLastError(), "xpress_huff_decompress");
 }
 
+// Plain Xpress encode of a batch; seg_tiles / index / stride describe the optional restart index.  Large buffers take the two-pass
+// variant (match finding per 64 KiB segment on its own block, then emission per buffer); small ones the single-pass kernel.
+static MSCompStatus xpress_encode_launch(mscomp_gpu_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, const mscomp_gpu_batch* b,
+                                         uint32_t seg_tiles, XpressSeg* index, uint32_t index_stride)
+{
+    cudaSetDevice(ctx->device);
+    MSC_OPT_IN_SMEM(xpress_encode_kernel, sizeof(XpEncSmem));
+    const uint32_t cap = (uint32_t)ctx->sm_count * 4;
+    static const char* mode = getenv("MSCOMP_XPRESS_ENCODE");          // "one" / "two" force a variant
+    bool two_pass = false;
+    uint32_t* seg_first = nullptr;
+    uint32_t* work = nullptr;
+    unsigned long long total_segs = 0;
+    if (!(mode && strcmp(mode, "one") == 0)) {
+        seg_first = (uint32_t*)ctx->get(SC_AUX1, ((size_t)b->count + 2) * sizeof(uint32_t) + 64);
+        unsigned long long* d_tot = (unsigned long long*)ctx->get(SC_RESULT, 1024);
+        unsigned long long* h_tot = (unsigned long long*)ctx->get_pinned(1024);
+        if (seg_first && d_tot && h_tot) {
+            d_tot += 64; h_tot += 64;                                  // (clear of the result mailbox at the front)
+            work = (uint32_t*)(d_tot + 4);
+            MSC_LAUNCH(ctx, xpress_segments_kernel, 1, 1024, b->d_in_len, b->count, seg_first, d_tot, work);
+            cudaMemcpyAsync(h_tot, d_tot, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream);
+            if (cudaStreamSynchronize(ctx->stream) == cudaSuccess) {
+                total_segs = h_tot[0];
+                const unsigned long long total_in = h_tot[1];
+                two_pass = total_segs > 0 && total_segs < (1ull << 24) &&
+                           ((mode && strcmp(mode, "two") == 0) || total_in / b->count >= (128u << 10));
+            }
+        }
+    }
+    XpPre pre{};
+    if (two_pass) {
+        const size_t tiles = (size_t)total_segs * XPE_SEG_TILES;
+        const size_t lo_b = tiles * LZF_TILE * sizeof(uint32_t), v_b = tiles * (LZF_TILE / 32) * sizeof(uint32_t), n_b = tiles * sizeof(uint32_t);
+        uint8_t* sc = (uint8_t*)ctx->get(SC_AUX2, lo_b + v_b + n_b + 256);
+        if (!sc) two_pass = false;
+        else {
+            pre.seg_first = seg_first;
+            pre.lenoff = (uint32_t*)sc;
+            pre.visited = (uint32_t*)(sc + lo_b);
+            pre.next_p = (uint32_t*)(sc + lo_b + v_b);
+        }
+    }
+    if (two_pass) {
+        MSC_OPT_IN_SMEM(xpress_match_kernel, sizeof(LzFrontSmem));
+        MSC_OPT_IN_SMEM(xpress_emit_kernel, sizeof(XpEncSmem));
+        const uint32_t mg = total_segs < (unsigned long long)ctx->sm_count * 5 ? (uint32_t)total_segs : (uint32_t)ctx->sm_count * 5;
+        MSC_LAUNCH_SMEM(ctx, xpress_match_kernel, mg, XPE_THREADS, sizeof(LzFrontSmem), d_in, b->count, b->d_in_off, b->d_in_len,
+                        (const uint32_t*)seg_first, work, pre.lenoff, pre.visited, pre.next_p);
+        MSC_LAUNCH_SMEM(ctx, xpress_emit_kernel, b->count < cap ? b->count : cap, XPE_THREADS, sizeof(XpEncSmem),
+                        d_in, d_out, b->count, b->d_in_off, b->d_in_len, b->d_out_off, b->d_out_cap, b->d_out_len, b->d_status,
+                        seg_tiles, index, index_stride, pre);
+    } else {
+        MSC_LAUNCH_SMEM(ctx, xpress_encode_kernel, b->count < cap ? b->count : cap, XPE_THREADS, sizeof(XpEncSmem),
+                        d_in, d_out, b->count, b->d_in_off, b->d_in_len, b->d_out_off, b->d_out_cap, b->d_out_len, b->d_status,
+                        seg_tiles, index, index_stride);
+    }
+    return msc_cuda_status(cudaGetLastError(), "xpress_compress");
+}
+
 MSCompStatus mscomp_gpu_xpress_compress_batch(mscomp_gpu_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, const mscomp_gpu_batch* b)
 {
     if (!batch_ok(ctx, d_in, d_out, b)) return MSCOMP_ARG_ERROR;
     if (!b->count) return MSCOMP_OK;
-    cudaSetDevice(ctx->device);
-    MSC_OPT_IN_SMEM(xpress_encode_kernel, sizeof(XpEncSmem));
-    const uint32_t cap = (uint32_t)ctx->sm_count * 4;
-    MSC_LAUNCH_SMEM(ctx, xpress_encode_kernel, b->count < cap ? b->count : cap, XPE_THREADS, sizeof(XpEncSmem),
-                    d_in, d_out, b->count, b->d_in_off, b->d_in_len, b->d_out_off, b->d_out_cap, b->d_out_len, b->d_status,
-                    0u, (XpressSeg*)nullptr, 0u);
-    return msc_cuda_status(cudaGetLastError(), "xpress_compress");
+    return xpress_encode_launch(ctx, d_in, d_out, b, 0u, nullptr, 0u);
 }
 
 static_assert(sizeof(XpressSeg) == sizeof(mscomp_gpu_xpress_seg), "xpress index entry layout");
@@ -380,13 +434,7 @@ MSCompStatus mscomp_gpu_xpress_compress_batch_indexed(mscomp_gpu_ctx* ctx, const
 {
     if (!batch_ok(ctx, d_in, d_out, b) || !d_index || !index_stride || seg_bytes < LZF_TILE || seg_bytes % LZF_TILE) return MSCOMP_ARG_ERROR;
     if (!b->count) return MSCOMP_OK;
-    cudaSetDevice(ctx->device);
-    MSC_OPT_IN_SMEM(xpress_encode_kernel, sizeof(XpEncSmem));
-    const uint32_t cap = (uint32_t)ctx->sm_count * 4;
-    MSC_LAUNCH_SMEM(ctx, xpress_encode_kernel, b->count < cap ? b->count : cap, XPE_THREADS, sizeof(XpEncSmem),
-                    d_in, d_out, b->count, b->d_in_off, b->d_in_len, b->d_out_off, b->d_out_cap, b->d_out_len, b->d_status,
-                    seg_bytes / LZF_TILE, (XpressSeg*)d_index, index_stride);
-    return msc_cuda_status(cudaGetLastError(), "xpress_compress");
+    return xpress_encode_launch(ctx, d_in, d_out, b, seg_bytes / LZF_TILE, (XpressSeg*)d_index, index_stride);
 }
 
 MSCompStatus mscomp_gpu_xpress_decompress_batch(mscomp_gpu_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, const mscomp_gpu_batch* b)

@@ -91,6 +91,26 @@ void emu_xpress_decode2(const uint8_t* in, uint8_t* out, uint32_t count, const u
     emu::launch(msc::lz_apply_kernel, dim3e(grid), dim3e(32 * msc::LZA_WARPS_PER_BLOCK), (const uint32_t*)tok.data(), (const uint32_t*)ntok.data(), out_off, (const int32_t*)status, count, out);
 }
 
+// two-pass plain Xpress encoder: match finding per 64 KiB segment (persistent blocks), then emission per buffer
+void emu_xpress_encode2(const uint8_t* in, uint8_t* out, uint32_t count, const uint64_t* in_off, const uint32_t* in_len,
+                        const uint64_t* out_off, const uint32_t* out_cap, uint32_t* out_len, int32_t* status, uint32_t grid,
+                        uint32_t seg_bytes, void* index, uint32_t stride)
+{
+    using namespace msc;
+    std::vector<uint32_t> seg_first(count + 2);
+    unsigned long long totals[2] = {0, 0};
+    uint32_t work = 0;
+    emu::launch(xpress_segments_kernel, dim3e(1), dim3e(1024), in_len, count, seg_first.data(), totals, &work);
+    const size_t tiles = (size_t)totals[0] * XPE_SEG_TILES;
+    std::vector<uint32_t> lenoff(tiles * LZF_TILE + 1), visited(tiles * (LZF_TILE / 32) + 1), next_p(tiles + 1);
+    if (totals[0])
+        emu::launch(xpress_match_kernel, dim3e(grid), dim3e(XPE_THREADS), in, count, in_off, in_len, (const uint32_t*)seg_first.data(), &work,
+                    lenoff.data(), visited.data(), next_p.data());
+    XpPre pre{seg_first.data(), lenoff.data(), visited.data(), next_p.data()};
+    emu::launch(xpress_emit_kernel, dim3e(grid), dim3e(XPE_THREADS), in, out, count, in_off, in_len, out_off, out_cap, out_len, status,
+                index ? seg_bytes / (uint32_t)LZF_TILE : 0u, (XpressSeg*)index, stride, pre);
+}
+
 // few-stream variant: one warp parses a stream (a flag group of 32 items at a time), one block applies it
 void emu_xpress_decode_warp(const uint8_t* in, uint8_t* out, uint32_t count, const uint64_t* in_off, const uint32_t* in_len,
                             const uint64_t* out_off, const uint32_t* out_cap, uint32_t* out_len, int32_t* status, uint32_t grid)

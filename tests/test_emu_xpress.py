@@ -121,3 +121,37 @@ def test_xpress_restart_index(emu, oracle, ms, seg_bytes, stride, block_apply):
                 assert st1[0] == ref[0] and (ref[0] < 0 or out1[0] == ref[1])
             else:                                                    # the index no longer belongs to the stream: an error, or the right bytes
                 assert st1[0] < 0 or (ref[0] == 0 and out1[0] == ref[1])
+
+
+@pytest.mark.parametrize("with_index", [False, True])
+def test_xpress_two_pass_encoder(emu, oracle, ms, with_index):
+    """Two-pass plain Xpress encoder (match finding per 64 KiB segment, emission per buffer): every stream decodes with the
+    oracle, stays inside the reference's bound and close to the single-pass encoder's size; the restart index it writes works."""
+    rnd = random.Random(9)
+    plains = [ms.generate(kind, n, 3 + n) for kind in ("text", "runs", "random") for n in (1, 5, 2049, 65535, 65536, 65537, 140000, 300000)]
+    plains += [b"", b"abc" * 70000, bytes(200000), bytes(rnd.getrandbits(8) & 3 for _ in range(150000))]
+    caps = [MAXSZ["xpress"](len(p)) for p in plains]
+    seg_bytes, stride = 16384, 24
+    index = np.zeros(len(plains) * stride * 6, dtype=np.uint32)
+    extra = (ctypes.c_uint32(seg_bytes), P(index) if with_index else ctypes.c_void_p(0), ctypes.c_uint32(stride))
+    st, _, comps = emu_batch(emu, "emu_xpress_encode2", plains, caps, extra=extra)
+    assert not st.any()
+    st1, _, comps1 = emu_batch(emu, "emu_xpress_encode", plains, caps)
+    for p, c, c1 in zip(plains, comps, comps1):
+        assert len(c) <= MAXSZ["xpress"](len(p))
+        if p:
+            assert oracle.decompress("xpress", c, len(p)) == (0, p)
+            assert len(c) <= len(c1) * 1.02 + 16, (len(p), len(c), len(c1))       # segment boundaries cost next to nothing
+    # exact-capacity and too-small outputs (with an index array of their own)
+    index2 = np.zeros(len(plains) * stride * 6, dtype=np.uint32)
+    extra2 = (ctypes.c_uint32(seg_bytes), P(index2) if with_index else ctypes.c_void_p(0), ctypes.c_uint32(stride))
+    st2, _, _ = emu_batch(emu, "emu_xpress_encode2", plains, [len(c) for c in comps], extra=extra2)
+    assert not st2.any()
+    st3, _, _ = emu_batch(emu, "emu_xpress_encode2", [p for p in plains if len(p) > 100], [len(c) - 1 for p, c in zip(plains, comps) if len(p) > 100], extra=extra2)
+    assert (st3 == -5).all()
+    if with_index:
+        for blk in (0, 1):
+            st4, _, outs = emu_batch(emu, "emu_xpress_decode_indexed", comps, [len(p) for p in plains],
+                                     extra=(P(index), ctypes.c_uint32(stride), ctypes.c_uint32(blk)))
+            assert list(st4) == [0 if p else -3 for p in plains]
+            assert all(o == p for o, p in zip(outs, plains) if p)
