@@ -20,7 +20,8 @@ MAXSZ = {"lznt1": lambda n: n + 3 + 2 * ((n + 4095) // 4096), "xpress": lambda n
 rnd = random.Random(1)
 extra = [("lznt1", bytes(rnd.choice(b"ACGT") for _ in range(3 * 4096 + 100))),                       # heavy chunks: lazy parse
          ("lznt1", b"".join((b"\x00" * rnd.randint(3, 300)) + bytes([rnd.randint(1, 255)]) for _ in range(200))),
-         ("lznt1", ms.generate("text", 400000, 3))]                                                    # several slices / ranges
+         ("lznt1", ms.generate("text", 400000, 3)),                                                    # several slices / ranges
+         ("xpress", ms.generate("text", 300000, 4)), ("xpress", ms.generate("runs", 200000, 5))]       # two-pass encoder, warp parser, block apply
 cases = [(fmt, ms.generate(kind, n, 7)) for fmt in ("lznt1", "xpress_huff", "xpress")
          for kind, n in (("text", 70000), ("runs", 20000), ("random", 5000), ("text", 33))] + extra
 for fmt, plain in cases:
