@@ -19,11 +19,15 @@ def test_partition_covers_everything(ms):
             assert max(h - l for l, h in ranges) - min(h - l for l, h in ranges) <= 1
 
 
-def test_gather_sizes_world2_gloo(tmp_path):
+def free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
+    return port
+
+
+def test_gather_sizes_world2_gloo(tmp_path):
     script = tmp_path / "w.py"
     script.write_text(textwrap.dedent("""
         import os, sys
@@ -43,8 +47,13 @@ def test_gather_sizes_world2_gloo(tmp_path):
         dist.destroy_process_group()
         print("rank", rank, "ok")
     """ % ROOT))
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                        "--master-port", str(port), str(script)], capture_output=True, text=True, env=env, timeout=240)
-    assert r.returncode == 0, r.stdout + r.stderr
-    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
+    last = None
+    for attempt in range(3):                    # (the port is chosen before torchrun binds it: retry if somebody else took it meanwhile)
+        port = free_port()
+        env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        last = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                               "--master-port", str(port), str(script)], capture_output=True, text=True, env=env, timeout=240)
+        if last.returncode == 0:
+            break
+    assert last.returncode == 0, last.stdout + last.stderr
+    assert "rank 0 ok" in last.stdout and "rank 1 ok" in last.stdout
