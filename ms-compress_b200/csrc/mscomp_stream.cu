@@ -188,15 +188,17 @@ MSCompStatus read_one(mscomp_stream* s, DState* st, const uint8_t* in, size_t* i
         st->in_avail = *in_len;
         return MSCOMP_OK;
     case H_BADSIG: set_error(s, "LZNT1 Decompression Error: Invalid header signature"); return MSCOMP_DATA_ERROR;
-    case H_STORED: *in_len = in_size; emit_stored(s, st, in + 2, in_size - 2); return MSCOMP_OK;
-    case H_COMPRESSED: break;
+    case H_STORED: case H_COMPRESSED: break;
     }
+    const HeaderKind kind = classify(in, *in_len, s->in_avail + st->in_avail, &in_size);
     *in_len = in_size;
+    // (stored chunks go through the GPU decoder too -- it copies them -- so that no chunk payload is handled on the CPU)
     std::vector<uint64_t> offs(1, 0); std::vector<uint8_t> out; std::vector<uint32_t> sizes; std::vector<int32_t> status;
     const MSCompStatus r = gpu_decode(in, in_size, offs, out, sizes, status);
     if (r != MSCOMP_OK) { set_error(s, "LZNT1 Decompression Error: GPU chunk decoder failed"); return r; }
     if (status[0] < 0) { set_error(s, "LZNT1 Decompression Error: Invalid chunk"); return MSCOMP_DATA_ERROR; }
-    emit_decoded(s, st, out.data(), sizes[0]);
+    if (kind == H_STORED) emit_stored(s, st, out.data(), sizes[0]);
+    else emit_decoded(s, st, out.data(), sizes[0]);
     return MSCOMP_OK;
 }
 
@@ -362,7 +364,7 @@ extern "C" MSCompStatus lznt1_inflate(mscomp_stream* s)
         while (run.size() < room && s->in_avail - p >= 2) {
             Item it{p, 0, H_END, -1};
             it.kind = classify(s->in + p, s->in_avail - p, s->in_avail - p + st->in_avail, &it.in_size);
-            if (it.kind == H_COMPRESSED) { it.slot = (int)offs.size(); offs.push_back(p); }
+            if (it.kind == H_COMPRESSED || it.kind == H_STORED) { it.slot = (int)offs.size(); offs.push_back(p); }   // (stored chunks are copied by the GPU decoder)
             run.push_back(it);
             if (it.kind != H_COMPRESSED && it.kind != H_STORED) break;      // the replay stops here
             p += it.in_size;
@@ -372,6 +374,7 @@ extern "C" MSCompStatus lznt1_inflate(mscomp_stream* s)
         for (size_t i = 0; i < run.size() && s->out_avail && s->in_avail >= 2; ++i) {
             const Item& it = run[i];
             const uint8_t* in = s->in;                          // == start of the run + it.off (everything before was consumed)
+            (void)in;
             switch (it.kind) {
             case H_END: adv_in(s, 2); st->end_of_stream = true; return MSCOMP_STREAM_END;
             case H_END_BAD: set_error(s, "LZNT1 Decompression Warning: End-of-stream found with data left"); return MSCOMP_DATA_ERROR;
@@ -382,7 +385,11 @@ extern "C" MSCompStatus lznt1_inflate(mscomp_stream* s)
                 st->in_avail = s->in_avail;
                 adv_in(s, s->in_avail);
                 break;
-            case H_STORED: emit_stored(s, st, in + 2, it.in_size - 2); adv_in(s, it.in_size); break;
+            case H_STORED:
+                if (status[it.slot] < 0) { set_error(s, "LZNT1 Decompression Error: Invalid chunk"); return MSCOMP_DATA_ERROR; }
+                emit_stored(s, st, out.data() + (size_t)it.slot * CHUNK, sizes[it.slot]);
+                adv_in(s, it.in_size);
+                break;
             case H_COMPRESSED:
                 if (status[it.slot] < 0) { set_error(s, "LZNT1 Decompression Error: Invalid chunk"); return MSCOMP_DATA_ERROR; }
                 emit_decoded(s, st, out.data() + (size_t)it.slot * CHUNK, sizes[it.slot]);
