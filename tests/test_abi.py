@@ -49,3 +49,18 @@ def test_none_format_copies(ms):
     assert ms.lib().ms_compress(0, b"hello", 5, out, ctypes.byref(n)) == 0 and out.raw[:n.value] == b"hello"
     n = ctypes.c_size_t(2)
     assert ms.lib().ms_decompress(0, b"hello", 5, out, ctypes.byref(n)) == ms.MSCOMP_BUF_ERROR
+
+
+def test_public_headers_compile_as_c_and_cpp(tmp_path):
+    """include/*.h is what a C (or C++) program of the reference's users sees: plain C99, no CUDA or torch types."""
+    import shutil
+    import subprocess
+    inc = os.path.join(ROOT, "include")
+    for h in ("mscomp.h", "lznt1.h", "xpress.h", "xpress_huff.h", "mscomp_gpu.h"):
+        for cc, std, lang in (("gcc", "-std=c99", "c"), ("g++", "-std=c++11", "c++")):
+            if not shutil.which(cc):
+                continue
+            src = '#include "%s"\nint main(void) { mscomp_stream s; (void)s; return (int)sizeof(MSCompStatus) - (int)sizeof(MSCompStatus); }\n' % h
+            r = subprocess.run([cc, std, "-Wall", "-Wextra", "-Werror", "-pedantic", "-fsyntax-only", "-I", inc, "-x", lang, "-"],
+                               input=src, capture_output=True, text=True)
+            assert r.returncode == 0, (h, cc, r.stderr)
