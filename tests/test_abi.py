@@ -64,3 +64,15 @@ def test_public_headers_compile_as_c_and_cpp(tmp_path):
             r = subprocess.run([cc, std, "-Wall", "-Wextra", "-Werror", "-pedantic", "-fsyntax-only", "-I", inc, "-x", lang, "-"],
                                input=src, capture_output=True, text=True)
             assert r.returncode == 0, (h, cc, r.stderr)
+
+
+def test_codec_calls_fail_loudly_without_a_gpu(ms):
+    """No CPU implementation hides behind the C ABI: without a CUDA device every codec entry point returns MSCOMP_MEM_ERROR."""
+    import torch
+    if torch.cuda.is_available():
+        return                                            # (the GPU box runs the real thing)
+    data = bytes(5000)
+    for fmt in ("lznt1", "xpress", "xpress_huff"):
+        assert ms.raw_call(fmt + "_compress", data, 10000)[0] == -4
+        assert ms.raw_call(fmt + "_decompress", data, 10000)[0] in (-4, -3, -5)      # (argument / header checks may come first)
+    assert ms.raw_call("lznt1_decompress", b"\x00\xb0" + bytes(100), 4096)[0] == -4
