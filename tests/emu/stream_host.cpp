@@ -1,0 +1,63 @@
+// stream_host.cpp -- TEST INFRASTRUCTURE.  The product's LZNT1 stream state machine (ms-compress_b200/csrc/stream_logic.h)
+// instantiated with the ORACLE's chunk functions instead of the GPU batch codec, so that the `-m "not gpu"` suite can drive the
+// very same host logic against the compiled reference, call by call.  Never part of the product library.
+#include "../../ms-compress_b200/csrc/stream_logic.h"
+extern "C" {
+#include "../../oracle/oracle.h"
+}
+
+using namespace msc_stream;
+
+namespace {
+struct OracleCodec {
+    static MSCompStatus encode(const uint8_t* in, size_t n, std::vector<uint8_t>& comp, std::vector<uint64_t>& offs)
+    {
+        comp.clear(); offs.clear();
+        for (size_t p = 0; p < n; p += CHUNK) {
+            const size_t len = n - p < CHUNK ? n - p : CHUNK;
+            uint8_t buf[CHUNK + 64];
+            size_t sz = sizeof(buf);
+            if (orc_lznt1_compress(in + p, len, buf, &sz) != 0) return MSCOMP_MEM_ERROR;
+            offs.push_back(comp.size());
+            comp.insert(comp.end(), buf, buf + sz);
+        }
+        offs.push_back(comp.size());
+        return MSCOMP_OK;
+    }
+    static MSCompStatus decode(const uint8_t* in, size_t n, const std::vector<uint64_t>& offs, std::vector<uint8_t>& out,
+                               std::vector<uint32_t>& sizes, std::vector<int32_t>& status)
+    {
+        const size_t k = offs.size();
+        out.assign(k * CHUNK, 0); sizes.assign(k, 0); status.assign(k, 0);
+        for (size_t i = 0; i < k; ++i) {
+            const uint8_t* c = in + offs[i];
+            const unsigned h = (unsigned)c[0] | ((unsigned)c[1] << 8);
+            const size_t payload = (h & 0x0FFF) + 1;
+            if (offs[i] + 2 + payload > n) { status[i] = -5; continue; }
+            if (h & 0x8000) {
+                size_t osz = 0;
+                status[i] = orc_lznt1_decompress_chunk(c + 2, payload, out.data() + i * CHUNK, CHUNK, &osz);
+                if (status[i] == -5) status[i] = -3;                 // (the stream layer reports both as a data error)
+                sizes[i] = (uint32_t)osz;
+            } else {
+                memcpy(out.data() + i * CHUNK, c + 2, payload);
+                sizes[i] = (uint32_t)payload;
+            }
+        }
+        return MSCOMP_OK;
+    }
+};
+} // namespace
+
+extern "C" {
+MSCompStatus hs_lznt1_deflate_init(mscomp_stream* s) { return lznt1_deflate_init_impl(s); }
+MSCompStatus hs_lznt1_deflate(mscomp_stream* s, MSCompFlush flush) { return lznt1_deflate_impl<OracleCodec>(s, flush); }
+MSCompStatus hs_lznt1_deflate_end(mscomp_stream* s) { return lznt1_deflate_end_impl(s); }
+MSCompStatus hs_lznt1_inflate_init(mscomp_stream* s) { return lznt1_inflate_init_impl(s); }
+MSCompStatus hs_lznt1_inflate(mscomp_stream* s) { return lznt1_inflate_impl<OracleCodec>(s); }
+MSCompStatus hs_lznt1_inflate_end(mscomp_stream* s) { return lznt1_inflate_end_impl(s); }
+MSCompStatus hs_copy_init(mscomp_stream* s) { return copy_init(s); }
+MSCompStatus hs_copy_deflate(mscomp_stream* s, MSCompFlush flush) { return copy_deflate(s, flush); }
+MSCompStatus hs_copy_inflate(mscomp_stream* s) { return copy_inflate(s); }
+MSCompStatus hs_copy_end(mscomp_stream* s) { return copy_end(s); }
+}

@@ -8,77 +8,12 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-NO_FLUSH, FLUSH, FINISH = 0, 2, 4
-STREAM_END, POSSIBLE_END = 1, 2
-
-
-class Stream(ctypes.Structure):
-    _fields_ = [("format", ctypes.c_int), ("compressing", ctypes.c_bool), ("in_", ctypes.c_void_p), ("in_avail", ctypes.c_size_t),
-                ("in_total", ctypes.c_size_t), ("out", ctypes.c_void_p), ("out_avail", ctypes.c_size_t), ("out_total", ctypes.c_size_t),
-                ("error", ctypes.c_char * 256), ("warning", ctypes.c_char * 256), ("state", ctypes.c_void_p)]
-
-
-class Driver:
-    """One stream of one library; feed() gives it input pieces and output room and records what every call did."""
-
-    def __init__(self, lib, prefix, fmt, deflate):
-        self.lib, self.deflate = lib, deflate
-        self.s = Stream()
-        self.name = prefix + ("deflate" if deflate else "inflate")
-        init = getattr(lib, self.name + "_init")
-        init.restype = ctypes.c_int
-        self.rc_init = init(ctypes.c_int(fmt), ctypes.byref(self.s)) if prefix == "ms_" else init(ctypes.byref(self.s))
-        self.f = getattr(lib, self.name)
-        self.f.restype = ctypes.c_int
-        self.end = getattr(lib, self.name + "_end")
-        self.end.restype = ctypes.c_int
-        self.out = bytearray()
-        self.pending = b""
-
-    def call(self, piece, cap, flush):
-        data = self.pending + piece
-        ibuf = ctypes.create_string_buffer(data, max(len(data), 1))
-        obuf = ctypes.create_string_buffer(max(cap, 1) + 2)
-        self.s.in_ = ctypes.addressof(ibuf); self.s.in_avail = len(data)
-        self.s.out = ctypes.addressof(obuf); self.s.out_avail = cap
-        rc = self.f(ctypes.byref(self.s), ctypes.c_int(flush)) if self.deflate else self.f(ctypes.byref(self.s))
-        used, made = len(data) - self.s.in_avail, cap - self.s.out_avail
-        self.out += obuf.raw[:made]
-        self.pending = data[used:]
-        return rc, used, made
-
-    def finish(self):
-        self.s.in_ = None; self.s.in_avail = 0; self.s.out = None; self.s.out_avail = 0
-        return self.end(ctypes.byref(self.s))
-
-
-def both(ms, reflib, prefix, fmt, deflate):
-    return Driver(ms.lib(), prefix, fmt, deflate), Driver(reflib.lib, prefix, fmt, deflate)
+from stream_util import FINISH, FLUSH, NO_FLUSH, POSSIBLE_END, STREAM_END, Driver, Stream, drive_pair  # noqa: E402,F401
 
 
 def drive(ms, reflib, prefix, fmt, deflate, data, rnd, max_piece, max_cap, use_flush):
-    a, b = both(ms, reflib, prefix, fmt, deflate)
-    assert a.rc_init == b.rc_init == 0
-    pos, trace = 0, []
-    for step in range(60000):
-        last = pos >= len(data)
-        piece = data[pos:pos + rnd.randint(0, max_piece)]
-        pos += len(piece)
-        cap = rnd.choice((0, 1, 2, 3, rnd.randint(0, max_cap), max_cap))
-        flush = FINISH if (pos >= len(data)) else (FLUSH if (use_flush and rnd.random() < 0.1) else NO_FLUSH)
-        ra, rb = a.call(piece, cap, flush), b.call(piece, cap, flush)
-        trace.append((len(piece), cap, flush, ra, rb))
-        assert ra == rb, trace[-5:]
-        if ra[0] < 0 or ra[0] == STREAM_END:
-            break
-        if last and not piece and cap > 0 and ra[1] == 0 and ra[2] == 0:
-            break                                         # nothing more to give and no progress: the stream is as far as it gets
-    else:
-        raise AssertionError("stream did not finish")
-    assert bytes(a.out) == bytes(b.out)
-    assert (a.s.in_total, a.s.out_total) == (b.s.in_total, b.s.out_total)
-    assert a.finish() == b.finish()
-    return bytes(a.out), ra[0]
+    f = fmt if prefix == "ms_" else None
+    return drive_pair(Driver(ms.lib(), prefix, deflate, f), Driver(reflib.lib, prefix, deflate, f), deflate, data, rnd, max_piece, max_cap, use_flush)
 
 
 @pytest.mark.parametrize("prefix", ["lznt1_", "ms_"])

@@ -1,0 +1,82 @@
+"""The product's LZNT1 stream state machine (ms-compress_b200/csrc/stream_logic.h) on the CPU: instantiated with the oracle's chunk
+codec (tests/emu/stream_host.cpp) and driven against the compiled reference call by call -- same random schedule of input pieces,
+output capacities and flush flags, same status / bytes consumed / bytes produced in every call.  The GPU suite runs the same
+schedules through the product library itself (tests/test_gpu_streaming.py)."""
+import ctypes
+import os
+import random
+import subprocess
+
+import pytest
+from conftest import ROOT
+from stream_util import STREAM_END, Driver, Stream, drive_pair
+
+
+@pytest.fixture(scope="module")
+def host():
+    d = os.path.join(ROOT, "tests", "emu")
+    subprocess.run(["make", "-s", "-C", d, "streamhost"], check=True)
+    return ctypes.CDLL(os.path.join(d, "libstreamhost.so"))
+
+
+def drive(host, reflib, deflate, data, rnd, max_piece, max_cap, use_flush):
+    return drive_pair(Driver(host, "hs_lznt1_", deflate), Driver(reflib.lib, "lznt1_", deflate), deflate, data, rnd, max_piece, max_cap, use_flush)
+
+
+def test_deflate_state_machine(host, reflib, oracle, ms):
+    rnd = random.Random(5)
+    for kind, n in (("text", 120000), ("random", 30000), ("runs", 90000), ("text", 4096 * 5), ("text", 5), ("text", 0)):
+        plain = ms.generate(kind, n, 3 + n % 5)
+        for max_piece, max_cap, use_flush in ((70000, 90000, False), (5000, 3000, True), (300, 9000, True), (20000, 100, False), (7, 5000, True)):
+            comp, rc = drive(host, reflib, True, plain, rnd, max_piece, max_cap, use_flush)
+            assert rc == STREAM_END
+            if not use_flush:
+                assert comp == oracle.compress("lznt1", plain)
+            assert oracle.decompress("lznt1", comp, n) == (0, plain)
+
+
+def test_inflate_state_machine(host, reflib, oracle, ms):
+    rnd = random.Random(6)
+    a, b, c = ms.generate("text", 100, 1), ms.generate("text", 50, 2), ms.generate("text", 60000, 3)
+    flushed = b"".join(oracle.compress("lznt1", x) for x in (a, b, c))                  # short chunks in mid-stream
+    streams = [(oracle.compress("lznt1", ms.generate(kind, n, 9 + n % 7)), ms.generate(kind, n, 9 + n % 7))
+               for kind, n in (("text", 150000), ("random", 30000), ("runs", 100000), ("text", 4096), ("text", 3))]
+    streams.append((flushed, a + b + c))
+    for comp, plain in streams:
+        variants = [comp, comp + b"\0\0", comp + b"\0", comp[:-3], comp + b"\0\0\x01", comp + b"\x07"]
+        if len(comp) > 100:
+            bad = bytearray(comp); bad[len(bad) // 2] ^= 0x10
+            hdr = bytearray(comp); hdr[1] ^= 0x40
+            variants += [bytes(bad), bytes(hdr)]
+        for v in variants:
+            for max_piece, max_cap in ((70000, 90000), (5000, 3000), (300, 5000), (20000, 100), (1, 4096)):
+                if max_piece == 1 and len(v) > 6000:
+                    continue
+                out, rc = drive(host, reflib, False, v, rnd, max_piece, max_cap, False)
+                if v is comp:
+                    assert out == plain and rc >= 0
+
+
+def test_copy_streams(host, reflib, ms):
+    rnd = random.Random(7)
+    data = ms.generate("text", 30000, 1)
+    # the copy engine shares one init / end for both directions (src/mscomp.cpp:34-61): drive it through small wrappers
+    class Copy(Driver):
+        def __init__(self, lib, deflate, ours):
+            self.lib, self.deflate = lib, deflate
+            self.s = Stream()
+            if ours:
+                init, self.f, self.end = lib.hs_copy_init, (lib.hs_copy_deflate if deflate else lib.hs_copy_inflate), lib.hs_copy_end
+                self.rc_init = init(ctypes.byref(self.s))
+            else:
+                init = lib.ms_deflate_init if deflate else lib.ms_inflate_init
+                self.f = lib.ms_deflate if deflate else lib.ms_inflate
+                self.end = lib.ms_deflate_end if deflate else lib.ms_inflate_end
+                self.rc_init = init(ctypes.c_int(0), ctypes.byref(self.s))
+            for fn in (self.f, self.end):
+                fn.restype = ctypes.c_int
+            self.out = bytearray()
+            self.pending = b""
+    for deflate in (True, False):
+        out, rc = drive_pair(Copy(host, deflate, True), Copy(reflib.lib, deflate, False), deflate, data, rnd, 4000, 3000, False)
+        assert out == data
