@@ -12,6 +12,7 @@
 // header walk) and to reproducing the reference's status codes.  No codec work happens on the CPU.
 #include "ctx.cuh"
 #include "shim_common.h"
+#include "lznt1_host.h"
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
@@ -138,36 +139,7 @@ extern "C" MSCompStatus lznt1_compress(const_bytes in, size_t in_len, bytes out,
     return MSCOMP_OK;
 }
 
-namespace {
-enum Lznt1Tail { T_CLEAN, T_ZERO, T_GARBAGE, T_TERM_OK, T_TERM_BAD, T_TRUNC, T_BADSIG };
-
-// Replays the reference's sequential driver (src/lznt1_decompress.cpp:254-273 + internal.h:616-630) over the
-// per-chunk results to obtain its status code.  size_of / status_of give chunk c's decoded size and status.
-template <class FS, class FT>
-MSCompStatus lznt1_replay(size_t nchunks, size_t cap, Lznt1Tail tail, FS size_of, FT status_of, size_t* total)
-{
-    size_t op = 0;
-    for (size_t c = 0; c < nchunks; ++c) {
-        if (cap - op == 0) return MSCOMP_BUF_ERROR;        // output full while input remains
-        if (status_of(c) < 0) return MSCOMP_DATA_ERROR;
-        const size_t sz = size_of(c);
-        if (sz > cap - op) return MSCOMP_BUF_ERROR;        // decoded bytes left over in the bounce buffer
-        op += sz;
-    }
-    *total = op;
-    switch (tail) {
-    case T_CLEAN: case T_ZERO: return MSCOMP_OK;
-    case T_GARBAGE: return MSCOMP_BUF_ERROR;
-    default: break;
-    }
-    if (cap - op == 0) return MSCOMP_BUF_ERROR;            // the loop never looks at the next header (:254)
-    switch (tail) {
-    case T_TERM_OK: return MSCOMP_OK;
-    case T_TRUNC: return MSCOMP_BUF_ERROR;
-    default: return MSCOMP_DATA_ERROR;                     // T_TERM_BAD, T_BADSIG
-    }
-}
-} // namespace
+using namespace msc_host;
 
 static unsigned long long g_pipeline_fallbacks = 0;
 // Diagnostic (not part of the reference ABI): how often the pipelined lznt1_decompress handed a stream to the simple path.
@@ -347,19 +319,8 @@ extern "C" MSCompStatus lznt1_decompress(const_bytes in, size_t in_len, bytes ou
     // where the stream already is.
     std::vector<uint64_t> offs;
     offs.reserve(in_len / 2048 + 4);
-    Lznt1Tail tail = T_CLEAN;
     size_t ip = 0;
-    bool stopped = false;
-    while (in_len - ip >= 2) {
-        const unsigned h = rd16(in + ip);
-        if (h == 0) { tail = (in_len - ip == 2) ? T_TERM_OK : T_TERM_BAD; stopped = true; break; }
-        const size_t sz = (h & 0x0FFF) + 3;
-        if (sz > in_len - ip) { tail = T_TRUNC; stopped = true; break; }
-        if ((h & 0x7000) != 0x3000) { tail = T_BADSIG; stopped = true; break; }
-        offs.push_back(ip);
-        ip += sz;
-    }
-    if (!stopped) tail = (in_len - ip == 0) ? T_CLEAN : (in[ip] == 0 ? T_ZERO : T_GARBAGE);
+    const Lznt1Tail tail = lznt1_walk(in, in_len, offs, &ip);
     const size_t nchunks = offs.size();
     if (nchunks > 0x7fffffffu) return MSCOMP_ARG_ERROR;
 

@@ -2,6 +2,7 @@
 // instantiated with the ORACLE's chunk functions instead of the GPU batch codec, so that the `-m "not gpu"` suite can drive the
 // very same host logic against the compiled reference, call by call.  Never part of the product library.
 #include "../../ms-compress_b200/csrc/stream_logic.h"
+#include "../../ms-compress_b200/csrc/lznt1_host.h"
 extern "C" {
 #include "../../oracle/oracle.h"
 }
@@ -56,6 +57,25 @@ MSCompStatus hs_lznt1_deflate_end(mscomp_stream* s) { return lznt1_deflate_end_i
 MSCompStatus hs_lznt1_inflate_init(mscomp_stream* s) { return lznt1_inflate_init_impl(s); }
 MSCompStatus hs_lznt1_inflate(mscomp_stream* s) { return lznt1_inflate_impl<OracleCodec>(s); }
 MSCompStatus hs_lznt1_inflate_end(mscomp_stream* s) { return lznt1_inflate_end_impl(s); }
+// The simple path of the product's one-shot lznt1_decompress (mscomp_shim.cu) with the oracle as the chunk decoder: header walk,
+// per-chunk decode into 4096-byte slots, replay of the reference's driver for the status, compaction of the decoded bytes.
+MSCompStatus hs_lznt1_decompress(const uint8_t* in, size_t in_len, uint8_t* out, size_t* out_len)
+{
+    using namespace msc_host;
+    const size_t cap = *out_len;
+    std::vector<uint64_t> offs;
+    size_t ip = 0;
+    const Lznt1Tail tail = lznt1_walk(in, in_len, offs, &ip);
+    std::vector<uint8_t> slots; std::vector<uint32_t> sizes; std::vector<int32_t> status;
+    if (!offs.empty()) OracleCodec::decode(in, ip, offs, slots, sizes, status);
+    size_t total = 0;
+    const MSCompStatus st = lznt1_replay(offs.size(), cap, tail, [&](size_t c) { return (size_t)sizes[c]; }, [&](size_t c) { return status[c]; }, &total);
+    if (st != MSCOMP_OK) return st;
+    size_t op = 0;
+    for (size_t c = 0; c < offs.size(); ++c) { memcpy(out + op, slots.data() + c * CHUNK, sizes[c]); op += sizes[c]; }
+    *out_len = total;
+    return MSCOMP_OK;
+}
 MSCompStatus hs_copy_init(mscomp_stream* s) { return copy_init(s); }
 MSCompStatus hs_copy_deflate(mscomp_stream* s, MSCompFlush flush) { return copy_deflate(s, flush); }
 MSCompStatus hs_copy_inflate(mscomp_stream* s) { return copy_inflate(s); }

@@ -80,3 +80,37 @@ def test_copy_streams(host, reflib, ms):
     for deflate in (True, False):
         out, rc = drive_pair(Copy(host, deflate, True), Copy(reflib.lib, deflate, False), deflate, data, rnd, 4000, 3000, False)
         assert out == data
+
+
+def test_one_shot_decompress_host_logic(host, reflib, oracle, ms):
+    """Header walk + status replay of the one-shot lznt1_decompress (csrc/lznt1_host.h) over the oracle's chunk decoder: same status
+    and bytes as the compiled reference on valid, truncated, padded and damaged streams and on every kind of capacity."""
+    rnd = random.Random(8)
+    f = host.hs_lznt1_decompress
+    f.restype = ctypes.c_int
+
+    def ours(src, cap):
+        out = ctypes.create_string_buffer(max(cap, 1))
+        n = ctypes.c_size_t(cap)
+        rc = f(src, ctypes.c_size_t(len(src)), out, ctypes.byref(n))
+        return rc, (out.raw[:n.value] if rc == 0 else None)
+
+    a, b, c = ms.generate("text", 100, 1), ms.generate("text", 50, 2), ms.generate("text", 9000, 3)
+    flushed = b"".join(oracle.compress("lznt1", x) for x in (a, b, c))
+    checked = 0
+    for plain in [ms.generate(k, n, 5 + n) for k in ("text", "runs", "random") for n in (0, 1, 3, 4095, 4096, 4097, 30000)] + [a + b + c]:
+        comp = flushed if plain == a + b + c else oracle.compress("lznt1", plain)
+        n = len(plain)
+        cases = [(comp, cap) for cap in (n, n + 1, n + 100, max(0, n - 1), n // 2, 0, 4 * n + 7)]
+        cases += [(comp + t, n + d) for t in (b"\0", b"\x55", b"\0\0", b"\0\0\x01", b"\0" * 5) for d in (0, 10)]
+        cases += [(comp[:-t], n) for t in (1, 2, 3, max(1, len(comp) // 2)) if t <= len(comp)]
+        for _ in range(25):
+            d = bytearray(comp)
+            for _ in range(rnd.randint(1, 3)):
+                if d:
+                    d[rnd.randrange(len(d))] ^= 1 << rnd.randrange(8)
+            cases.append((bytes(d), n + rnd.choice((0, 64))))
+        for src, cap in cases:
+            assert ours(src, cap) == reflib.call("lznt1_decompress", src, cap), (len(src), cap)
+            checked += 1
+    assert checked > 500
