@@ -74,21 +74,21 @@ extern "C" MSCompStatus ms_deflate_init(MSCompFormat format, mscomp_stream* s)
     switch ((unsigned)format) {
     case MSCOMP_NONE: return copy_init(s);
     case MSCOMP_LZNT1: return lznt1_deflate_init(s);
-    default: set_error(s, "Error: Invalid format provided (streaming: MSCOMP_NONE and MSCOMP_LZNT1)"); return MSCOMP_ARG_ERROR;
+    default: set_error(s, "no streaming for this format here (MSCOMP_NONE and MSCOMP_LZNT1 only)"); return MSCOMP_ARG_ERROR;
     }
 }
 extern "C" MSCompStatus ms_deflate(mscomp_stream* s, MSCompFlush flush)
 {
     if (s && s->format == MSCOMP_NONE) return copy_deflate(s, flush);
     if (s && s->format == MSCOMP_LZNT1) return lznt1_deflate(s, flush);
-    set_error(s, "Error: Invalid stream provided");
+    set_error(s, "stream argument is null, of another format / direction, or has a null buffer with a non-zero size");
     return MSCOMP_ARG_ERROR;
 }
 extern "C" MSCompStatus ms_deflate_end(mscomp_stream* s)
 {
     if (s && s->format == MSCOMP_NONE) return copy_end(s);
     if (s && s->format == MSCOMP_LZNT1) return lznt1_deflate_end(s);
-    set_error(s, "Error: Invalid stream provided");
+    set_error(s, "stream argument is null, of another format / direction, or has a null buffer with a non-zero size");
     return MSCOMP_ARG_ERROR;
 }
 extern "C" MSCompStatus ms_inflate_init(MSCompFormat format, mscomp_stream* s)
@@ -96,20 +96,20 @@ extern "C" MSCompStatus ms_inflate_init(MSCompFormat format, mscomp_stream* s)
     switch ((unsigned)format) {
     case MSCOMP_NONE: return copy_init(s);
     case MSCOMP_LZNT1: return lznt1_inflate_init(s);
-    default: set_error(s, "Error: Invalid format provided (streaming: MSCOMP_NONE and MSCOMP_LZNT1)"); return MSCOMP_ARG_ERROR;
+    default: set_error(s, "no streaming for this format here (MSCOMP_NONE and MSCOMP_LZNT1 only)"); return MSCOMP_ARG_ERROR;
     }
 }
 extern "C" MSCompStatus ms_inflate(mscomp_stream* s)
 {
     if (s && s->format == MSCOMP_NONE) return copy_inflate(s);
     if (s && s->format == MSCOMP_LZNT1) return lznt1_inflate(s);
-    set_error(s, "Error: Invalid stream provided");
+    set_error(s, "stream argument is null, of another format / direction, or has a null buffer with a non-zero size");
     return MSCOMP_ARG_ERROR;
 }
 extern "C" MSCompStatus ms_inflate_end(mscomp_stream* s)
 {
     if (s && s->format == MSCOMP_NONE) return copy_end(s);
     if (s && s->format == MSCOMP_LZNT1) return lznt1_inflate_end(s);
-    set_error(s, "Error: Invalid stream provided");
+    set_error(s, "stream argument is null, of another format / direction, or has a null buffer with a non-zero size");
     return MSCOMP_ARG_ERROR;
 }

@@ -83,7 +83,7 @@ MSCompStatus write_one(mscomp_stream* s, CState* st, const uint8_t* in, size_t i
 {
     std::vector<uint8_t> comp; std::vector<uint64_t> offs;
     const MSCompStatus r = Codec::encode(in, in_len, comp, offs);
-    if (r != MSCOMP_OK) { set_error(s, "LZNT1 Compression Error: GPU chunk encoder failed"); return r; }
+    if (r != MSCOMP_OK) { set_error(s, "lznt1_deflate: the chunk encoder could not run"); return r; }
     emit_chunk(s, st, comp.data(), comp.size(), in_len);
     return MSCOMP_OK;
 }
@@ -139,13 +139,13 @@ MSCompStatus read_one(mscomp_stream* s, DState* st, const uint8_t* in, size_t* i
     size_t in_size = 0;
     switch (classify(in, *in_len, s->in_avail + st->in_avail, &in_size)) {
     case H_END: *in_len = 2; st->end_of_stream = true; return MSCOMP_OK;
-    case H_END_BAD: set_error(s, "LZNT1 Decompression Warning: End-of-stream found with data left"); return MSCOMP_DATA_ERROR;
+    case H_END_BAD: set_error(s, "lznt1_inflate: data after the end-of-stream terminator"); return MSCOMP_DATA_ERROR;
     case H_PARTIAL:
         memmove(st->in, in, *in_len);
         st->in_needed = in_size - *in_len;
         st->in_avail = *in_len;
         return MSCOMP_OK;
-    case H_BADSIG: set_error(s, "LZNT1 Decompression Error: Invalid header signature"); return MSCOMP_DATA_ERROR;
+    case H_BADSIG: set_error(s, "lznt1_inflate: chunk header without the 011 signature bits"); return MSCOMP_DATA_ERROR;
     case H_STORED: case H_COMPRESSED: break;
     }
     const HeaderKind kind = classify(in, *in_len, s->in_avail + st->in_avail, &in_size);
@@ -153,8 +153,8 @@ MSCompStatus read_one(mscomp_stream* s, DState* st, const uint8_t* in, size_t* i
     // (stored chunks go through the chunk decoder too -- on the GPU it copies them -- so that no chunk payload is handled on the CPU)
     std::vector<uint64_t> offs(1, 0); std::vector<uint8_t> out; std::vector<uint32_t> sizes; std::vector<int32_t> status;
     const MSCompStatus r = Codec::decode(in, in_size, offs, out, sizes, status);
-    if (r != MSCOMP_OK) { set_error(s, "LZNT1 Decompression Error: GPU chunk decoder failed"); return r; }
-    if (status[0] < 0) { set_error(s, "LZNT1 Decompression Error: Invalid chunk"); return MSCOMP_DATA_ERROR; }
+    if (r != MSCOMP_OK) { set_error(s, "lznt1_inflate: the chunk decoder could not run"); return r; }
+    if (status[0] < 0) { set_error(s, "lznt1_inflate: malformed chunk payload"); return MSCOMP_DATA_ERROR; }
     if (kind == H_STORED) emit_stored(s, st, out.data(), sizes[0]);
     else emit_decoded(s, st, out.data(), sizes[0]);
     return MSCOMP_OK;
@@ -176,18 +176,18 @@ inline MSCompStatus copy_move(mscomp_stream* s)
 }
 inline MSCompStatus copy_deflate(mscomp_stream* s, MSCompFlush flush)
 {
-    if (bad_stream(s, true, MSCOMP_NONE)) { set_error(s, "Error: Invalid stream provided"); return MSCOMP_ARG_ERROR; }
+    if (bad_stream(s, true, MSCOMP_NONE)) { set_error(s, "stream argument is null, of another format / direction, or has a null buffer with a non-zero size"); return MSCOMP_ARG_ERROR; }
     copy_move(s);
     return (flush == MSCOMP_FINISH && !s->in_avail) ? MSCOMP_STREAM_END : MSCOMP_OK;
 }
 inline MSCompStatus copy_inflate(mscomp_stream* s)
 {   // (the reference initialises copy streams as "compressing" in both directions, src/mscomp.cpp:34,:48)
-    if (bad_stream(s, true, MSCOMP_NONE)) { set_error(s, "Error: Invalid stream provided"); return MSCOMP_ARG_ERROR; }
+    if (bad_stream(s, true, MSCOMP_NONE)) { set_error(s, "stream argument is null, of another format / direction, or has a null buffer with a non-zero size"); return MSCOMP_ARG_ERROR; }
     return copy_move(s);
 }
 inline MSCompStatus copy_end(mscomp_stream* s)
 {
-    if (bad_stream(s, true, MSCOMP_NONE)) { set_error(s, "Error: Invalid stream provided"); return MSCOMP_ARG_ERROR; }
+    if (bad_stream(s, true, MSCOMP_NONE)) { set_error(s, "stream argument is null, of another format / direction, or has a null buffer with a non-zero size"); return MSCOMP_ARG_ERROR; }
     return MSCOMP_OK;
 }
 
@@ -197,7 +197,7 @@ inline MSCompStatus lznt1_deflate_init_impl(mscomp_stream* s)
     if (!s) return MSCOMP_ARG_ERROR;
     init_stream(s, true, MSCOMP_LZNT1);
     CState* st = (CState*)malloc(sizeof(CState));
-    if (!st) { set_error(s, "LZNT1 Compression Error: Unable to allocate buffer memory"); return MSCOMP_MEM_ERROR; }
+    if (!st) { set_error(s, "lznt1_deflate_init: out of memory for the stream state"); return MSCOMP_MEM_ERROR; }
     st->finished = false; st->in_needed = st->in_avail = 0; st->out_pos = st->out_avail = 0;
     s->state = (mscomp_internal_state*)st;
     return MSCOMP_OK;
@@ -205,10 +205,10 @@ inline MSCompStatus lznt1_deflate_init_impl(mscomp_stream* s)
 
 inline MSCompStatus lznt1_deflate_end_impl(mscomp_stream* s)
 {
-    if (bad_stream(s, true, MSCOMP_LZNT1) || !s->state) { set_error(s, "Error: Invalid stream provided"); return MSCOMP_ARG_ERROR; }
+    if (bad_stream(s, true, MSCOMP_LZNT1) || !s->state) { set_error(s, "stream argument is null, of another format / direction, or has a null buffer with a non-zero size"); return MSCOMP_ARG_ERROR; }
     CState* st = (CState*)s->state;
     MSCompStatus r = MSCOMP_OK;
-    if (!st->finished || s->in_avail || st->in_avail || st->out_avail) { set_error(s, "LZNT1 Compression Error: End prematurely called"); r = MSCOMP_DATA_ERROR; }
+    if (!st->finished || s->in_avail || st->in_avail || st->out_avail) { set_error(s, "lznt1_deflate_end: the stream was not finished (input or output still pending)"); r = MSCOMP_DATA_ERROR; }
     free(st);
     s->state = nullptr;
     return r;
@@ -219,7 +219,7 @@ inline MSCompStatus lznt1_inflate_init_impl(mscomp_stream* s)
     if (!s) return MSCOMP_ARG_ERROR;
     init_stream(s, false, MSCOMP_LZNT1);
     DState* st = (DState*)malloc(sizeof(DState));
-    if (!st) { set_error(s, "LZNT1 Decompression Error: Unable to allocate buffer memory"); return MSCOMP_MEM_ERROR; }
+    if (!st) { set_error(s, "lznt1_inflate_init: out of memory for the stream state"); return MSCOMP_MEM_ERROR; }
     st->end_of_stream = false; st->in_needed = st->in_avail = 0; st->out_pos = st->out_avail = 0;
     s->state = (mscomp_internal_state*)st;
     return MSCOMP_OK;
@@ -227,10 +227,10 @@ inline MSCompStatus lznt1_inflate_init_impl(mscomp_stream* s)
 
 inline MSCompStatus lznt1_inflate_end_impl(mscomp_stream* s)
 {
-    if (bad_stream(s, false, MSCOMP_LZNT1) || !s->state) { set_error(s, "Error: Invalid stream provided"); return MSCOMP_ARG_ERROR; }
+    if (bad_stream(s, false, MSCOMP_LZNT1) || !s->state) { set_error(s, "stream argument is null, of another format / direction, or has a null buffer with a non-zero size"); return MSCOMP_ARG_ERROR; }
     DState* st = (DState*)s->state;
     MSCompStatus r = MSCOMP_OK;
-    if (!possible_end(s, st)) { set_error(s, "LZNT1 Decompression Error: End prematurely called"); r = MSCOMP_DATA_ERROR; }
+    if (!possible_end(s, st)) { set_error(s, "lznt1_inflate_end: the stream is in the middle of a chunk"); r = MSCOMP_DATA_ERROR; }
     free(st);
     s->state = nullptr;
     return r;
@@ -240,7 +240,7 @@ template <class Codec>
 MSCompStatus lznt1_deflate_impl(mscomp_stream* s, MSCompFlush flush)
 {
     CState* st = s ? (CState*)s->state : nullptr;
-    if (bad_stream(s, true, MSCOMP_LZNT1) || !st || st->finished) { set_error(s, "Error: Invalid stream provided"); return MSCOMP_ARG_ERROR; }
+    if (bad_stream(s, true, MSCOMP_LZNT1) || !st || st->finished) { set_error(s, "stream argument is null, of another format / direction, or has a null buffer with a non-zero size"); return MSCOMP_ARG_ERROR; }
     MSCompStatus r;
     bool at_end = false;
 
@@ -268,7 +268,7 @@ MSCompStatus lznt1_deflate_impl(mscomp_stream* s, MSCompFlush flush)
             size_t want = s->out_avail / (CHUNK + 2) + 1;
             if (want > s->in_avail / CHUNK) want = s->in_avail / CHUNK;
             std::vector<uint8_t> comp; std::vector<uint64_t> offs;
-            if ((r = Codec::encode(s->in, want * CHUNK, comp, offs)) != MSCOMP_OK) { set_error(s, "LZNT1 Compression Error: GPU chunk encoder failed"); return r; }
+            if ((r = Codec::encode(s->in, want * CHUNK, comp, offs)) != MSCOMP_OK) { set_error(s, "lznt1_deflate: the chunk encoder could not run"); return r; }
             for (size_t c = 0; c < want && s->out_avail; ++c) {
                 emit_chunk(s, st, comp.data() + offs[c], (size_t)(offs[c + 1] - offs[c]), CHUNK);
                 adv_in(s, CHUNK);
@@ -297,13 +297,13 @@ MSCompStatus lznt1_deflate_impl(mscomp_stream* s, MSCompFlush flush)
 template <class Codec>
 MSCompStatus lznt1_inflate_impl(mscomp_stream* s)
 {
-    if (bad_stream(s, false, MSCOMP_LZNT1) || !s->state) { set_error(s, "Error: Invalid stream provided"); return MSCOMP_ARG_ERROR; }
+    if (bad_stream(s, false, MSCOMP_LZNT1) || !s->state) { set_error(s, "stream argument is null, of another format / direction, or has a null buffer with a non-zero size"); return MSCOMP_ARG_ERROR; }
     DState* st = (DState*)s->state;
     MSCompStatus r;
 
     if (drain(st, s)) return MSCOMP_OK;
     if (st->end_of_stream) {
-        if (s->in_avail || st->in_avail) { set_error(s, "LZNT1 Decompression Warning: End-of-stream found with data left"); return MSCOMP_DATA_ERROR; }
+        if (s->in_avail || st->in_avail) { set_error(s, "lznt1_inflate: data after the end-of-stream terminator"); return MSCOMP_DATA_ERROR; }
         return MSCOMP_STREAM_END;
     }
     if (st->in_avail) {                                        // the chunk being assembled in the state's buffer (:236-245)
@@ -313,7 +313,7 @@ MSCompStatus lznt1_inflate_impl(mscomp_stream* s)
             if (st->in_needed) return MSCOMP_OK;
             size_t in_len = st->in_avail;
             r = read_one<Codec>(s, st, st->in, &in_len);
-            if (in_len != st->in_avail) { set_error(s, "LZNT1 Decompression Error: Inconsistent stream state"); return MSCOMP_ARG_ERROR; }
+            if (in_len != st->in_avail) { set_error(s, "lznt1_inflate: buffered chunk does not match its header"); return MSCOMP_ARG_ERROR; }
             if (r != MSCOMP_OK) return r;
             if (st->end_of_stream) return MSCOMP_STREAM_END;
             if (st->in_needed) continue;                       // there was only enough for the header so far
@@ -339,15 +339,15 @@ MSCompStatus lznt1_inflate_impl(mscomp_stream* s)
             p += it.in_size;
         }
         std::vector<uint8_t> out; std::vector<uint32_t> sizes; std::vector<int32_t> status;
-        if (!offs.empty() && (r = Codec::decode(s->in, p, offs, out, sizes, status)) != MSCOMP_OK) { set_error(s, "LZNT1 Decompression Error: GPU chunk decoder failed"); return r; }
+        if (!offs.empty() && (r = Codec::decode(s->in, p, offs, out, sizes, status)) != MSCOMP_OK) { set_error(s, "lznt1_inflate: the chunk decoder could not run"); return r; }
         for (size_t i = 0; i < run.size() && s->out_avail && s->in_avail >= 2; ++i) {
             const Item& it = run[i];
             const uint8_t* in = s->in;                          // == start of the run + it.off (everything before was consumed)
             (void)in;
             switch (it.kind) {
             case H_END: adv_in(s, 2); st->end_of_stream = true; return MSCOMP_STREAM_END;
-            case H_END_BAD: set_error(s, "LZNT1 Decompression Warning: End-of-stream found with data left"); return MSCOMP_DATA_ERROR;
-            case H_BADSIG: set_error(s, "LZNT1 Decompression Error: Invalid header signature"); return MSCOMP_DATA_ERROR;
+            case H_END_BAD: set_error(s, "lznt1_inflate: data after the end-of-stream terminator"); return MSCOMP_DATA_ERROR;
+            case H_BADSIG: set_error(s, "lznt1_inflate: chunk header without the 011 signature bits"); return MSCOMP_DATA_ERROR;
             case H_PARTIAL:                                     // the rest of the input is the beginning of a chunk
                 memcpy(st->in, in, s->in_avail);
                 st->in_needed = it.in_size - s->in_avail;
@@ -355,12 +355,12 @@ MSCompStatus lznt1_inflate_impl(mscomp_stream* s)
                 adv_in(s, s->in_avail);
                 break;
             case H_STORED:
-                if (status[it.slot] < 0) { set_error(s, "LZNT1 Decompression Error: Invalid chunk"); return MSCOMP_DATA_ERROR; }
+                if (status[it.slot] < 0) { set_error(s, "lznt1_inflate: malformed chunk payload"); return MSCOMP_DATA_ERROR; }
                 emit_stored(s, st, out.data() + (size_t)it.slot * CHUNK, sizes[it.slot]);
                 adv_in(s, it.in_size);
                 break;
             case H_COMPRESSED:
-                if (status[it.slot] < 0) { set_error(s, "LZNT1 Decompression Error: Invalid chunk"); return MSCOMP_DATA_ERROR; }
+                if (status[it.slot] < 0) { set_error(s, "lznt1_inflate: malformed chunk payload"); return MSCOMP_DATA_ERROR; }
                 emit_decoded(s, st, out.data() + (size_t)it.slot * CHUNK, sizes[it.slot]);
                 adv_in(s, it.in_size);
                 break;
