@@ -66,14 +66,41 @@ struct mscomp_gpu_ctx {
         scratch_cap[id] = want;
         return scratch[id];
     }
+    // The result mailbox: one fixed pinned block that is allocated once and never moves, so pointers into it stay valid
+    // whatever else a call allocates (kernels write results straight into it through the mapped address).
+    static constexpr size_t kMailboxBytes = 8192;
     void* get_pinned(size_t bytes)
     {
-        if (bytes <= pinned_cap) return pinned;
-        if (pinned) cudaFreeHost(pinned);
-        pinned = nullptr; pinned_cap = 0;
-        if (cudaMallocHost(&pinned, bytes + 256) != cudaSuccess) { cudaGetLastError(); pinned = nullptr; return nullptr; }
-        pinned_cap = bytes + 256;
+        if (bytes > kMailboxBytes) return nullptr;
+        if (pinned) return pinned;
+        if (cudaMallocHost(&pinned, kMailboxBytes) != cudaSuccess) { cudaGetLastError(); pinned = nullptr; return nullptr; }
+        pinned_cap = kMailboxBytes;
         return pinned;
+    }
+    // Grow-only pinned staging for bulk host-side tables (unit descriptors); separate from the mailbox.
+    void* pinned_big = nullptr;
+    size_t pinned_big_cap = 0;
+    void* get_pinned_big(size_t bytes)
+    {
+        if (bytes <= pinned_big_cap) return pinned_big;
+        cudaStreamSynchronize(stream);              // an upload from the old block may still be in flight
+        if (pinned_big) cudaFreeHost(pinned_big);
+        pinned_big = nullptr; pinned_big_cap = 0;
+        const size_t want = bytes + bytes / 4 + 4096;
+        if (cudaMallocHost(&pinned_big, want) != cudaSuccess) { cudaGetLastError(); pinned_big = nullptr; return nullptr; }
+        pinned_big_cap = want;
+        return pinned_big;
+    }
+    // Kernels that need more than 48 KB of dynamic shared memory opt in once per context (the attribute is per device,
+    // and a context is bound to one device and used by one host thread at a time).
+    static constexpr int kOptInMax = 32;
+    const void* opted_in[kOptInMax] = {};
+    int opted_n = 0;
+    void opt_in_smem(const void* func, size_t bytes)
+    {
+        for (int i = 0; i < opted_n; ++i) if (opted_in[i] == func) return;
+        cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (opted_n < kOptInMax) opted_in[opted_n++] = func;
     }
 };
 
@@ -88,12 +115,8 @@ struct mscomp_gpu_ctx {
     } while (0)
 #define MSC_LAUNCH(ctx, kernel, grid, block, ...) MSC_LAUNCH_SMEM(ctx, kernel, grid, block, 0, __VA_ARGS__)
 
-// Kernels that need more than 48 KB of dynamic shared memory opt in once per process.
-#define MSC_OPT_IN_SMEM(kernel, bytes)                                                              \
-    do {                                                                                            \
-        static bool done_ = false;                                                                  \
-        if (!done_) { cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); done_ = true; } \
-    } while (0)
+// Kernels that need more than 48 KB of dynamic shared memory opt in once per context (= per device).
+#define MSC_OPT_IN_SMEM(kernel, bytes) (ctx)->opt_in_smem((const void*)(kernel), (bytes))
 
 static inline MSCompStatus msc_cuda_status(cudaError_t e, const char* what)
 {

@@ -298,7 +298,8 @@ xpress_parse_indexed_kernel(const uint8_t* __restrict__ in, uint32_t* __restrict
         bool mine = false;
         if (i < lanes) {
             const XpressSeg* ix = index + (uint64_t)u * stride;
-            const uint32_t nseg = ix[0].nseg;
+            uint32_t nseg = ix[0].nseg;
+            if (nseg > stride) nseg = 0;                                    // not an index of this layout: the apply stage reports it
             if (sgm < nseg) {
                 mine = true;
                 const XpressSeg e = ix[sgm];
@@ -307,7 +308,10 @@ xpress_parse_indexed_kernel(const uint8_t* __restrict__ in, uint32_t* __restrict
                 O.init(tok + out_off[u] + e.out_pos);
                 O.opos = e.out_pos;
                 if (sgm + 1 < nseg) L.stop_ip = ix[sgm + 1].in_pos;
-                if (sgm == 0) {
+                if (sgm == 0 && (e.in_pos != 0 || e.out_pos != 0 || e.flag_used != 0 || e.half_pos != 0xFFFFFFFFu)) {
+                    L.status = ST_DATA;                                     // segment 0 is the start of the stream, nothing else
+                    O.init(tok + out_off[u]); O.opos = 0;
+                } else if (sgm == 0) {
                     if (L.in_len < 5) {                                     // :414-418 (sic)
                         uint32_t w = 0;
                         if (L.in_len == 4) w = (uint32_t)L.in[0] | ((uint32_t)L.in[1] << 8) | ((uint32_t)L.in[2] << 16) | ((uint32_t)L.in[3] << 24);
@@ -350,7 +354,8 @@ xpress_apply_indexed_kernel(const uint32_t* __restrict__ tok_base, const uint32_
     for (uint32_t u = blockIdx.x * LZA_WARPS_PER_BLOCK + (threadIdx.x >> 5); u < count; u += warps_total) {
         const XpressSeg* ix = index + (uint64_t)u * stride;
         const uint64_t i0 = (uint64_t)u * stride;
-        const uint32_t nseg = ix[0].nseg;
+        uint32_t nseg = ix[0].nseg;
+        if (nseg > stride) nseg = 0;
         int bad = 0;                                                    // first failing segment's status
         for (uint32_t s0 = 0; s0 < nseg && !bad; s0 += 32) {
             const uint32_t sg = s0 + lane;
@@ -384,7 +389,8 @@ xpress_apply_indexed_block_kernel(const uint32_t* __restrict__ tok_base, const u
     for (uint32_t u = blockIdx.x; u < count; u += gridDim.x) {
         const XpressSeg* ix = index + (uint64_t)u * stride;
         const uint64_t i0 = (uint64_t)u * stride;
-        const uint32_t nseg = ix[0].nseg;
+        uint32_t nseg = ix[0].nseg;
+        if (nseg > stride) nseg = 0;
         if (tid == 0) s_bad = 0x7fffffff;                               // first failing segment
         __syncthreads();
         for (uint32_t sg = tid; sg < nseg; sg += blockDim.x) {

@@ -89,6 +89,7 @@ void mscomp_gpu_destroy(mscomp_gpu_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < SC_COUNT; ++i) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->pinned_big) cudaFreeHost(ctx->pinned_big);
     if (ctx->copy_stream) {
         for (int i = 0; i < 16; ++i) { cudaEventDestroy(ctx->copy_ev[i]); cudaEventDestroy(ctx->work_ev[i]); }
         cudaStreamDestroy(ctx->copy_stream); cudaStreamDestroy(ctx->down_stream);

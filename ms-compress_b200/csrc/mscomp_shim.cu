@@ -63,6 +63,7 @@ extern "C" MSCompStatus lznt1_compress(const_bytes in, size_t in_len, bytes out,
 {
     if (!out_len || (!in && in_len) || !out) return MSCOMP_ARG_ERROR;
     const size_t cap = *out_len;
+    if (in_len == 0) { *out_len = 0; return MSCOMP_OK; }   // no chunk, no terminator needed (src/lznt1_compress.cpp:239,:268-272)
     if (cap == 0) return MSCOMP_BUF_ERROR;                 // undefined upstream (src/lznt1_compress.cpp:239), rejected here
     mscomp_gpu_ctx* ctx = msc_thread_ctx();
     if (!ctx) return MSCOMP_MEM_ERROR;
@@ -364,7 +365,7 @@ extern "C" MSCompStatus lznt1_decompress(const_bytes in, size_t in_len, bytes ou
             uint8_t* d_packed = (uint8_t*)ctx->get(SC_AUX0, (size_t)r.bytes + 64);
             uint64_t* d_dst = (uint64_t*)ctx->get(SC_AUX1, (nchunks + 1) * sizeof(uint64_t));
             if (!d_packed || !d_dst) return MSCOMP_MEM_ERROR;
-            msc_compact_slots(ctx, d_out, 4096, d_sizes, (uint32_t)nchunks, d_dst, d_packed);
+            if ((st = msc_compact_slots(ctx, d_out, 4096, d_sizes, (uint32_t)nchunks, d_dst, d_packed)) != MSCOMP_OK) return st;
             d_final = d_packed;
         }
     }
@@ -393,9 +394,8 @@ bool upload_units(mscomp_gpu_ctx* ctx, const std::vector<uint64_t>& in_off, cons
     const size_t n = in_off.size();
     const size_t bytes = n * (8 + 8 + 4 + 4 + 4 + 4);
     uint8_t* d = (uint8_t*)ctx->get(SC_AUX3, bytes + 64);
-    uint8_t* h = (uint8_t*)ctx->get_pinned(bytes + 512);
+    uint8_t* h = (uint8_t*)ctx->get_pinned_big(bytes + 64);
     if (!d || !h) return false;
-    h += 256;                                         // the first 256 bytes of the mailbox are used for results
     memcpy(h, in_off.data(), n * 8);
     memcpy(h + n * 8, out_off.data(), n * 8);
     memcpy(h + n * 16, in_len.data(), n * 4);
@@ -418,9 +418,10 @@ typedef MSCompStatus (*batch_fn)(mscomp_gpu_ctx*, const uint8_t*, uint8_t*, cons
 MSCompStatus one_buffer(batch_fn fn, const char* what, const_bytes in, size_t in_len, bytes out, size_t* out_len, size_t dev_cap)
 {
     if (!out_len || (!in && in_len) || (!out && *out_len)) return MSCOMP_ARG_ERROR;
-    if (in_len > 0xFFFFFFFFull) return MSCOMP_ARG_ERROR;          // the device batch interface uses 32-bit lengths
+    if (in_len > 0xFFFFFF00ull) return MSCOMP_ARG_ERROR;          // the device batch interface uses 32-bit lengths (with headroom
+                                                                  // for the readers' rounding of end positions)
     const size_t cap = *out_len;
-    if (dev_cap > 0xFFFFFFFFull) dev_cap = 0xFFFFFFFFull;
+    if (dev_cap > 0xFFFFFF00ull) dev_cap = 0xFFFFFF00ull;
     mscomp_gpu_ctx* ctx = msc_thread_ctx();
     if (!ctx) return MSCOMP_MEM_ERROR;
     uint8_t* d_in = (uint8_t*)ctx->get(SC_IN, in_len + 64);
@@ -429,7 +430,6 @@ MSCompStatus one_buffer(batch_fn fn, const char* what, const_bytes in, size_t in
     if (!d_in || !d_out || !h_res) return MSCOMP_MEM_ERROR;
     UnitBatch ub;
     if (!upload_units(ctx, {0}, {(uint32_t)in_len}, {0}, {(uint32_t)dev_cap}, &ub)) return MSCOMP_MEM_ERROR;
-    h_res = (decltype(h_res))ctx->get_pinned(256);                // (the mailbox may have been reallocated)
     if (in_len) cudaMemcpyAsync(d_in, in, in_len, cudaMemcpyHostToDevice, ctx->stream);
     MSCompStatus st = fn(ctx, d_in, d_out, &ub.b);
     if (st != MSCOMP_OK) return st;
