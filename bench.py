@@ -500,7 +500,7 @@ def run_gpu(args):
 
     steps = args.steps
     kern = {}
-    alg = {"lznt1_encode_kernel": U + C, "lznt1_decode_kernel": C + U, "lznt1_decode_lanes_kernel": C + U, "gather_slots_kernel": 2 * C}
+    alg = {"lznt1_encode_kernel": U + C, "lznt1_decode_kernel": C + U, "gather_slots_kernel": 2 * C}
     traffic = {}
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
@@ -512,7 +512,7 @@ def run_gpu(args):
             e["achieved_GBps"] = alg[name] / 1e9 / (per / 1e3)
             e["frac"] = e["achieved_GBps"] / peak
         kern[name] = e
-    dec_name = "lznt1_decode_lanes_kernel" if "lznt1_decode_lanes_kernel" in kern else "lznt1_decode_kernel"
+    dec_name = "lznt1_decode_kernel"
     dom = max((k for k in kern if k in alg), key=lambda k: kern[k]["ms_per_launch"] * kern[k]["calls_per_step"])
     roofline = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["achieved_GBps"], "peak": peak, "unit": "GB/s", "frac": kern[dom]["frac"],
                 "traffic": traffic.get(dom), "peak_source": peak_src,

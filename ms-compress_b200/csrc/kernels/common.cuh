@@ -4,6 +4,8 @@
 #ifndef MSC_EMU
 #include <cuda_runtime.h>
 #include <stdint.h>
+#else
+#include <string.h>
 #endif
 
 namespace msc {
@@ -56,6 +58,77 @@ __device__ __forceinline__ void spin_pause()
     __nanosleep(40);
 #else
     emu::yield();
+#endif
+}
+
+// ---- bulk asynchronous copies (TMA, 1-D) + mbarrier ---------------------------------------------------------------
+// cp.async.bulk moves a 16-byte-aligned, 16-byte-multiple range between global and shared memory without passing
+// through registers; a load signals an mbarrier with the byte count, a store is tracked by a bulk group.
+// Under the CPU emulator the copies are plain memcpy and the barrier is a no-op.
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+#ifndef MSC_EMU
+    return (uint32_t)__cvta_generic_to_shared(p);
+#else
+    return (uint32_t)(uintptr_t)p;
+#endif
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+#ifndef MSC_EMU
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#else
+    *bar = 0; (void)count;
+#endif
+}
+// writes made through the generic proxy (ordinary stores) become visible to / ordered before later async-proxy accesses
+__device__ __forceinline__ void fence_async_smem()
+{
+#ifndef MSC_EMU
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+}
+// one thread: announce `bytes` on the barrier and start the global -> shared copy that will deliver them
+__device__ __forceinline__ void bulk_load_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
+{
+#ifndef MSC_EMU
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+#else
+    memcpy(dst_smem, src_gmem, bytes); (void)bar;
+#endif
+}
+// every thread that reads the data: wait for the phase with the given parity to complete
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+#ifndef MSC_EMU
+    const uint32_t a = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    } while (!done);
+#else
+    (void)bar; (void)parity;
+    __syncwarp();                       // emulator: the copy is a memcpy made by one lane; the waiters meet it here (warp-scope use only)
+#endif
+}
+// one thread: shared -> global copy as a bulk group; wait_read returns once the shared source may be overwritten
+__device__ __forceinline__ void bulk_store_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes)
+{
+#ifndef MSC_EMU
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+#else
+    memcpy(dst_gmem, src_smem, bytes);
+#endif
+}
+__device__ __forceinline__ void bulk_store_wait_read()
+{
+#ifndef MSC_EMU
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 #endif
 }
 

@@ -8,32 +8,46 @@
 // output position p splits as off = (tok >> shift) + 1, len = (tok & ((1 << shift) - 1)) + 3 with
 // shift = 12 while p <= 16 and one less each time p passes a power of two (reference :59-63).
 //
-// Parallel scheme (per warp, chunk staged in shared memory):
-//   1. "chase": the start of flag group g+1 is start(g) + 9 + popc(flags(g)) -- a serial chain that does not
-//      depend on token contents; all lanes walk it redundantly, lane i keeps group i (<= 32 groups per round).
-//   2. every lane sums the output length of its own group assuming the round's shift is the one in force at
-//      the round's first byte; a warp scan turns that into output positions; groups up to the first one that
-//      has a token starting beyond the current power-of-two limit are exact ("valid").
-//   3. valid lanes emit: literals as they walk their items; matches under a watermark rule -- a pending match
-//      may run when every byte it reads lies below the lowest pending match destination of the whole warp
-//      (everything below that is final), or when it is that lowest one itself.  Long matches are copied by
-//      the whole warp.
-//   4. the first invalid group (at most one per power of two, <= 9 per chunk) is decoded item by item with the
-//      exact shift ("careful" path), warp-uniform.
+// Data movement: the payload is brought into shared memory by ONE bulk asynchronous copy (cp.async.bulk + mbarrier)
+// and the decoded chunk leaves by one bulk store; nothing passes through registers.  Decoding is IN PLACE: the
+// payload sits right-aligned at the top of a 4096+512-byte buffer and the output grows from byte 0.  A group of n
+// input bytes yields at least n-1 output bytes, so in a chunk that ends within 4096 bytes the write position never
+// reaches the unread input (margin: 4096/9 < 512); a chunk where it would is one that overflows 4096 bytes, i.e. an
+// error in the reference as well (:67, :99) -- the round that would cross the line reports it.
+//
+// Parallel scheme, per round of up to 32 flag groups (lane i owns group i):
+//   1. chase: start(g+1) = start(g) + 9 + popc(flags(g)) does not depend on token contents; lane i simply takes i
+//      steps of that chain (predicated, no cross-lane traffic; bytes read past the payload are harmless slack).
+//   2. the 8 items of the group go to registers together with the group's output length under the shift in force
+//      at the round's first byte; one warp scan (length and token count packed in one word) gives every group its
+//      output position and its first slot in the round's match list.
+//   3. if a token of the round starts beyond the current power-of-two limit, lengths are re-evaluated with the
+//      shift each token has at its own (tentative) position and re-scanned until nothing moves: positions are
+//      exact from the left, every pass fixes everything up to and including the next boundary crossing.
+//   4. literals are stored; tokens are appended, in position order, to a per-warp list {token, position, shift}.
+//   5. the list is executed 32 entries at a time: entries whose source lies wholly below the first entry of the
+//      batch (everything there is final) and that are short and not self-overlapping are copied at once, one per
+//      lane; the few others (a source inside the batch, a run, a long match) follow in order, copied by the whole
+//      warp.
 #pragma once
 #include "common.cuh"
 
 namespace msc {
 
 constexpr int LZNT1_CHUNK = 4096;
-constexpr int LZNT1_IN_SMEM = 4096 + 32;          // payload (<= 4096) + alignment skew (<= 15) rounded up to 16
 constexpr int LZNT1_WARPS_PER_BLOCK = 4;
-constexpr int LZNT1_COOP_LEN = 24;                // matches at least this long are copied by the whole warp
+constexpr int LZD_BUF = LZNT1_CHUNK + 512;        // in-place buffer: output from 0, payload right-aligned below LZD_BUF
+constexpr int LZD_SLACK = 544;                    // readable bytes behind it: the chase may run 31 * 17 bytes past the payload
+constexpr int LZD_LIST = 256;                     // tokens per round: 32 groups x 8 items
+constexpr int LZD_BULK_LEN = 16;                  // matches up to this long are copied one per lane
 
 struct Lznt1WarpSmem {
-    __align__(16) uint8_t in[LZNT1_IN_SMEM];
-    __align__(16) uint8_t out[LZNT1_CHUNK];
+    __align__(16) uint8_t buf[LZD_BUF + LZD_SLACK];
+    uint32_t list[LZD_LIST];                      // token | position << 16 | (shift - 4) << 28
+    __align__(8) uint64_t bar;                    // mbarrier of the payload load
+    uint64_t pad_;
 };
+static_assert(sizeof(Lznt1WarpSmem) % 16 == 0, "per-warp shared memory must keep 16-byte alignment");
 
 // shift / limit in force for a token that starts at chunk output position p
 __device__ __forceinline__ void lznt1_shift_limit(int p, int& shift, int& limit)
@@ -42,174 +56,189 @@ __device__ __forceinline__ void lznt1_shift_limit(int p, int& shift, int& limit)
     shift = 16 - m;
     limit = 1 << m;
 }
+// the same for positions that may be garbage (a damaged stream): the shift never leaves [4, 12]
+__device__ __forceinline__ int lzd_token_shift(int p)
+{
+    int m = (p <= 16) ? 4 : (32 - __clz(p - 1));
+    if (m > 12) m = 12;
+    return 16 - m;
+}
 
-// whole-warp copy of a match inside the shared output buffer (handles overlap like a byte-serial copy)
-__device__ __forceinline__ void lznt1_warp_match_copy(uint8_t* out, int dst, int off, int len)
+// Whole-warp copy of one match inside the buffer with the semantics of a byte-serial copy (all arguments uniform).
+__device__ __forceinline__ void lzd_coop_copy(uint8_t* o, int pos, int off, int len)
 {
     const int lane = lane_id();
-    if (off >= 32) {
-        for (int i = 0; i < len; i += 32) {
-            if (i + lane < len) out[dst + i + lane] = out[dst - off + i + lane];
-            __syncwarp();
-        }
-    } else {
-        // period `off` pattern: every byte equals one of the `off` bytes just before dst (all final)
-        for (int i = lane; i < len; i += 32) out[dst + i] = out[dst - off + (i % off)];
+    int src = pos - off;
+    if (off < 32 && off < len) {
+        // A run: the output repeats the `off` bytes before pos.  The first stretch is indexed modulo the period; after
+        // that the copy distance can be any multiple of the period, so one of at least 32 is used and 32-byte batches
+        // never read what they write.
+        const int off2 = off * ((31 + off) / off);
+        const int head = len < off2 ? len : off2;
+        for (int i = lane; i < head; i += 32) o[pos + i] = o[src + i % off];
+        __syncwarp();
+        pos += head; len -= head;
+        src = pos - off2;
+    }
+    for (int i = 0; i < len; i += 32) {
+        if (i + lane < len) o[pos + i + lane] = o[src + i + lane];
         __syncwarp();
     }
 }
 
-// Decode one compressed payload s_in[0..n) into s_out; returns bytes produced or a negative status.
-__device__ __forceinline__ int lznt1_decode_payload(const uint8_t* __restrict__ s_in, int n, uint8_t* __restrict__ s_out)
+// Group length with the shift every token has at its own position, the group starting at gs (items in registers).
+template <bool ALL8>
+__device__ __forceinline__ int lzd_group_len(const uint32_t (&it)[8], unsigned f, int nit, int gs)
 {
-    const int lane = lane_id();
-    int q = 0;          // payload offset of the next flag byte (uniform)
-    int P = 0;          // output bytes produced so far (uniform)
-    int err = 0;        // uniform
-
-    while (q < n && !err) {
-        int S, lim;
-        lznt1_shift_limit(P, S, lim);
-        const int mask = (1 << S) - 1;
-        int R = ((lim - P) >> 3) + 2;              // no more groups than this can be valid in this round
-        if (R > 32) R = 32;
-
-        // ---- 1. chase the group starts -------------------------------------------------------------
-        int s = q, my = -1;
-        unsigned myf = 0;
-        for (int i = 0; i < R; ++i) {
-            if (s < n) {
-                const unsigned f = s_in[s];
-                if (lane == i) { my = s; myf = f; }
-                s += 9 + __popc(f);
-            }
-        }
-
-        // ---- 2. group lengths under the round's shift ----------------------------------------------
-        int glen = 0, last_tok = -1;
-        bool trunc = false;                         // token cut by the end of the payload
-        if (my >= 0) {
-            int o = my + 1;
+    int pos = gs;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (o < n) {
-                    if ((myf >> j) & 1) {
-                        if (o + 2 > n) { trunc = true; o = n; }
-                        else {
-                            const int t = s_in[o] | (s_in[o + 1] << 8);
-                            last_tok = glen;
-                            glen += (t & mask) + 3;
-                            o += 2;
-                        }
-                    } else { glen += 1; o += 1; }
-                }
-            }
-        }
-        const int incl = warp_incl_scan(glen);
-        const int gs = P + incl - glen;             // my group's first output position (exact while all earlier lanes valid)
-        const bool valid = (my >= 0) && (last_tok < 0 || gs + last_tok <= lim);
-        const unsigned act = __ballot_sync(FULL, my >= 0);
-        const unsigned inv = __ballot_sync(FULL, my >= 0 && !valid);
-        const int nact = __popc(act);
-        const int G = inv ? (__ffs((int)inv) - 1) : nact;      // number of leading valid groups
-        // position after the valid groups
-        const int Pend = (G > 0) ? (P + __shfl_sync(FULL, incl, G - 1)) : P;
-        if (Pend > LZNT1_CHUNK) { err = ST_DATA; break; }
-        if (__ballot_sync(FULL, trunc && lane < G)) { err = ST_DATA; break; }
-
-        // ---- 3. emit the valid groups -----------------------------------------------------------------
-        {
-            const bool mine = lane < G;
-            // 3a. literals: every lane walks its (at most 8) items once; positions follow from the group start
-            unsigned mb = 0;                                   // my match items still to execute
-            if (mine) {
-                int o = my + 1, run = gs;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (o < n) {
-                        if ((myf >> j) & 1) {
-                            const int t = s_in[o] | (s_in[o + 1] << 8);
-                            run += (t & mask) + 3;
-                            o += 2;
-                            mb |= 1u << j;
-                        } else { s_out[run++] = s_in[o++]; }
-                    }
-                }
-            }
-            // 3b. matches, in position order per lane, under the watermark rule.  The next match of a lane is found
-            //     with find-first-set; its input / output offsets follow from popcounts (tokens are 2 bytes, literals 1).
-            int acc = 0;                                       // output bytes of my matches executed so far
-            bool bad = false;
-            for (;;) {
-                int pos = 0, m_len = 0, m_off = 0;
-                const bool pending = mb != 0;
-                if (pending) {
-                    const int j = __ffs((int)mb) - 1;
-                    const int tb = __popc(myf & ((1u << j) - 1));          // tokens before item j
-                    const int o = my + 1 + j + tb;
-                    pos = gs + (j - tb) + acc;
-                    const int t = s_in[o] | (s_in[o + 1] << 8);
-                    m_len = (t & mask) + 3; m_off = (t >> S) + 1;
-                    if (m_off > pos) { bad = true; mb = 0; }
-                }
-                __syncwarp();
-                const bool live = pending && !bad;
-                const unsigned W = __reduce_min_sync(FULL, live ? (unsigned)pos : 0xffffffffu);
-                if (W == 0xffffffffu) break;
-                const bool can = live && ((unsigned)pos == W || (unsigned)(pos - m_off + m_len) <= W);
-                unsigned coop = __ballot_sync(FULL, can && m_len >= LZNT1_COOP_LEN);
-                if (can && m_len < LZNT1_COOP_LEN) {
-                    for (int i = 0; i < m_len; ++i) s_out[pos + i] = s_out[pos - m_off + i];
-                }
-                while (coop) {
-                    const int src = __ffs((int)coop) - 1;
-                    coop &= coop - 1;
-                    const int d = __shfl_sync(FULL, pos, src), l = __shfl_sync(FULL, m_len, src), f = __shfl_sync(FULL, m_off, src);
-                    lznt1_warp_match_copy(s_out, d, f, l);
-                }
-                if (can) { acc += m_len; mb &= mb - 1; }
-            }
-            if (__ballot_sync(FULL, bad)) { err = ST_DATA; break; }
-        }
-        P = Pend;
-
-        // ---- 4. careful path for the first invalid group ------------------------------------------------
-        if (G < nact) {
-            const int cs = __shfl_sync(FULL, my, G);
-            const unsigned cf = __shfl_sync(FULL, myf, G);
-            int o = cs + 1;
-            for (int j = 0; j < 8 && o < n; ++j) {
-                if ((cf >> j) & 1) {
-                    if (o + 2 > n) { err = ST_DATA; break; }
-                    int S2, lim2;
-                    lznt1_shift_limit(P, S2, lim2);
-                    const int t = s_in[o] | (s_in[o + 1] << 8);
-                    const int len = (t & ((1 << S2) - 1)) + 3, off = (t >> S2) + 1;
-                    o += 2;
-                    if (off > P || P + len > LZNT1_CHUNK) { err = ST_DATA; break; }
-                    __syncwarp();
-                    lznt1_warp_match_copy(s_out, P, off, len);
-                    P += len;
-                } else {
-                    if (P >= LZNT1_CHUNK) { err = ST_DATA; break; }
-                    if (lane == 0) s_out[P] = s_in[o];
-                    ++P; ++o;
-                }
-            }
-            __syncwarp();
-            // next round starts after the careful group
-            q = (G + 1 < nact) ? __shfl_sync(FULL, my, G + 1) : s;
-        } else {
-            q = s;
+    for (int j = 0; j < 8; ++j) {
+        if (ALL8 || j < nit) {
+            if ((f >> j) & 1) { const int Sj = lzd_token_shift(pos); pos += (int)(it[j] & ((1u << Sj) - 1)) + 3; }
+            else pos += 1;
         }
     }
+    const int g = pos - gs;
+    return g < LZNT1_CHUNK + 1 ? g : LZNT1_CHUNK + 1;
+}
+
+// Literals to the buffer, tokens to the match list; returns true if a token reaches back beyond the chunk start.
+template <bool ALL8, bool MIXED>
+__device__ __forceinline__ bool lzd_emit(const uint32_t (&it)[8], unsigned f, int nit, int gs, int S0, int li, uint8_t* buf, uint32_t* list)
+{
+    bool bad = false;
+    int pos = gs;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (ALL8 || j < nit) {
+            const uint32_t t = it[j];
+            if ((f >> j) & 1) {
+                const int Sj = MIXED ? lzd_token_shift(pos) : S0;
+                const int l = (int)(t & ((1u << Sj) - 1)) + 3, off = (int)(t >> Sj) + 1;
+                bad |= off > pos;                                            // :65 / :98
+                list[li++] = t | ((uint32_t)pos << 16) | ((uint32_t)(Sj - 4) << 28);
+                pos += l;
+            } else buf[pos++] = (uint8_t)t;
+        }
+    }
+    return bad;
+}
+
+// Decodes the compressed payload buf[in0 .. in0+n) into buf[0 ..); returns bytes produced or a negative status.
+__device__ __forceinline__ int lznt1_decode_payload(Lznt1WarpSmem& sm, const int in0, const int n)
+{
+    uint8_t* const buf = sm.buf;
+    const uint8_t* const pin = sm.buf + in0;
+    const int lane = lane_id();
+    int q = 0;          // payload offset of the round's first flag byte (uniform)
+    int P = 0;          // output bytes produced so far (uniform)
+
+    while (q < n) {
+        // ---- 1. chase: lane i walks i groups ahead of q ------------------------------------------------------
+        int s = q;
+#pragma unroll
+        for (int step = 0; step < 31; ++step)
+            if (step < lane) s += 9 + __popc((unsigned)pin[s]);
+        const bool act = s < n;
+        const unsigned f = act ? (unsigned)pin[s] : 0u;
+        const int qn = __shfl_sync(FULL, s + 9 + __popc(f), 31);            // first flag byte of the next round (>= n: none)
+
+        // ---- 2. items to registers, group length under the round's first shift -------------------------------
+        const int S0 = lzd_token_shift(P);
+        const int lim = 1 << (16 - S0);                                      // last position that still has shift S0
+        const unsigned mask0 = (1u << S0) - 1;
+        uint32_t it[8];
+        int nit = 0, A = 0, lastA = -1;                                      // items present, length, start of my last token (relative)
+        bool trunc = false;                                                  // a token cut by the end of the payload (:90)
+        const bool all8 = __all_sync(FULL, s + 17 <= n);                     // every group of the round lies wholly inside the payload
+        if (all8) {
+            int o = s + 1;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                uint32_t v = pin[o];
+                if ((f >> j) & 1) { v |= (uint32_t)pin[o + 1] << 8; lastA = A; A += (int)(v & mask0) + 3; o += 2; }
+                else { A += 1; o += 1; }
+                it[j] = v;
+            }
+            nit = 8;
+        } else {
+            int o = s + 1;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                uint32_t v = 0;
+                if (act && o < n) {                                          // (the stream may end after any item, :86)
+                    if ((f >> j) & 1) {
+                        if (o + 2 > n) { trunc = true; o = n; }
+                        else { v = (uint32_t)pin[o] | ((uint32_t)pin[o + 1] << 8); lastA = A; A += (int)(v & mask0) + 3; o += 2; nit = j + 1; }
+                    } else { v = pin[o]; A += 1; o += 1; nit = j + 1; }
+                }
+                it[j] = v;
+            }
+        }
+        const int ntk = __popc(f & ((1u << nit) - 1u));
+        __syncwarp();                                                        // all input of the round is in registers: output may overwrite it
+
+        // ---- 3. positions ---------------------------------------------------------------------------------------
+        int glen = A < LZNT1_CHUNK + 1 ? A : LZNT1_CHUNK + 1;
+        int incl = warp_incl_scan(glen | (ntk << 20));
+        int gs = P + (incl & 0xFFFFF) - glen;
+        bool mixed = false;
+        if (__any_sync(FULL, lastA >= 0 && gs + lastA > lim)) {
+            mixed = true;
+            for (int iter = 0; iter < 34; ++iter) {
+                const int g2 = all8 ? lzd_group_len<true>(it, f, nit, gs) : lzd_group_len<false>(it, f, nit, gs);
+                const bool moved = g2 != glen;
+                glen = g2;
+                incl = warp_incl_scan(glen | (ntk << 20));
+                gs = P + (incl & 0xFFFFF) - glen;
+                if (!__any_sync(FULL, moved)) break;                         // lengths agree with the positions they were taken at
+            }
+        }
+        const int total = __shfl_sync(FULL, incl, 31);
+        const int Pend = P + (total & 0xFFFFF);
+        const int nm = total >> 20;
+        const bool cut = __any_sync(FULL, trunc);
+        if (cut || Pend > LZNT1_CHUNK || (qn < n && Pend > in0 + qn)) return ST_DATA;   // :90, :67/:99 (see the header on the last one)
+
+        // ---- 4. literals out, tokens to the list -----------------------------------------------------------------
+        const int li = (incl >> 20) - ntk;
+        bool bad;
+        if (all8) bad = mixed ? lzd_emit<true, true>(it, f, nit, gs, S0, li, buf, sm.list) : lzd_emit<true, false>(it, f, nit, gs, S0, li, buf, sm.list);
+        else bad = mixed ? lzd_emit<false, true>(it, f, nit, gs, S0, li, buf, sm.list) : lzd_emit<false, false>(it, f, nit, gs, S0, li, buf, sm.list);
+        if (__any_sync(FULL, bad)) return ST_DATA;
+        __syncwarp();
+
+        // ---- 5. matches --------------------------------------------------------------------------------------------
+        for (int base = 0; base < nm; base += 32) {
+            const bool have = base + lane < nm;
+            const uint32_t e = have ? sm.list[base + lane] : 0u;
+            const int Sj = (int)(e >> 28) + 4, pos = (int)(e >> 16) & 0xFFF, t = (int)(e & 0xFFFFu);
+            const int len = (t & ((1 << Sj) - 1)) + 3, off = (t >> Sj) + 1, src = pos - off;
+            const int W0 = __shfl_sync(FULL, pos, 0);                        // everything below the batch's first match is final
+            const bool now = have && len <= LZD_BULK_LEN && off >= len && src + len <= W0;
+            if (now) {
+                buf[pos] = buf[src]; buf[pos + 1] = buf[src + 1]; buf[pos + 2] = buf[src + 2];
+                for (int i = 3; i < len; ++i) buf[pos + i] = buf[src + i];
+            }
+            __syncwarp();
+            unsigned rest = __ballot_sync(FULL, have && !now);
+            while (rest) {
+                const int o = __ffs((int)rest) - 1;
+                rest &= rest - 1;
+                lzd_coop_copy(buf, __shfl_sync(FULL, pos, o), __shfl_sync(FULL, off, o), __shfl_sync(FULL, len, o));
+            }
+        }
+        P = Pend;
+        q = qn;
+    }
     __syncwarp();
-    return err ? err : P;
+    return P;
 }
 
 // One warp per chunk.  chunk_off[c] = byte offset of chunk c's header inside `in`.
 // Chunk c is written to out + c*4096 (slot layout); out_size[c] = bytes produced, status[c] = 0 or < 0.
-__global__ void __launch_bounds__(LZNT1_WARPS_PER_BLOCK * 32)
+// `in` must be readable up to the next 16-byte boundary behind in_len (the bulk copy moves whole 16-byte granules).
+__global__ void __launch_bounds__(LZNT1_WARPS_PER_BLOCK * 32, 8)
 lznt1_decode_kernel(const uint8_t* __restrict__ in, uint64_t in_len, const uint64_t* __restrict__ chunk_off, uint32_t nchunks,
                     uint8_t* __restrict__ out, uint32_t* __restrict__ out_size, int32_t* __restrict__ status)
 {
@@ -218,6 +247,9 @@ lznt1_decode_kernel(const uint8_t* __restrict__ in, uint64_t in_len, const uint6
     const int wib = (int)(threadIdx.x >> 5);
     Lznt1WarpSmem& sm = smem[wib];
     const uint32_t warps_total = gridDim.x * LZNT1_WARPS_PER_BLOCK;
+    if (lane == 0) mbar_init(&sm.bar, 1);
+    __syncwarp();
+    uint32_t phase = 0;
 
     for (uint32_t c = blockIdx.x * LZNT1_WARPS_PER_BLOCK + wib; c < nchunks; c += warps_total) {
         const uint64_t start = chunk_off[c];
@@ -235,33 +267,36 @@ lznt1_decode_kernel(const uint8_t* __restrict__ in, uint64_t in_len, const uint6
                 warp_copy_bytes(dst, in + start + 2, n);
                 produced = n;
             } else {
-                // stage the payload: 16-byte granules covering [src, src+n)
+                // payload -> top of the buffer: the 16-byte granules covering [src, src+n), one bulk copy
                 const uint8_t* src = in + start + 2;
                 const uint32_t skew = (uint32_t)((uintptr_t)src & 15u);
-                const uint8_t* a0 = src - skew;
                 const uint32_t wbytes = (skew + n + 15u) & ~15u;
-                for (uint32_t i = lane * 16; i < wbytes; i += 512)
-                    *reinterpret_cast<uint4*>(sm.in + i) = ld_stream16(a0 + i);
-                __syncwarp();
-                const int r = lznt1_decode_payload(sm.in + skew, (int)n, sm.out);
+                if (lane == 0) {
+                    bulk_store_wait_read();                              // the previous chunk has left the buffer
+                    fence_async_smem();
+                    bulk_load_g2s(sm.buf + LZD_BUF - wbytes, src - skew, wbytes, &sm.bar);
+                }
+                mbar_wait(&sm.bar, phase);
+                phase ^= 1u;
+                const int r = lznt1_decode_payload(sm, (int)(LZD_BUF - wbytes + skew), (int)n);
                 if (r < 0) st = r;
                 else {
                     produced = (uint32_t)r;
-                    // shared -> global, 16-byte vectors (dst is 16-byte aligned when `out` is)
-                    const uint32_t nvec = produced >> 4;
+                    fence_async_smem();                                  // the bytes written above, as seen by the bulk store
+                    __syncwarp();
+                    uint32_t nb = 0;
                     if (((uintptr_t)dst & 15u) == 0) {
-                        for (uint32_t v = lane; v < nvec; v += 32)
-                            st_stream16(dst + 16 * v, *reinterpret_cast<const uint4*>(sm.out + 16 * v));
-                        for (uint32_t b = (nvec << 4) + lane; b < produced; b += 32) dst[b] = sm.out[b];
-                    } else {
-                        for (uint32_t b = lane; b < produced; b += 32) dst[b] = sm.out[b];
+                        nb = produced & ~15u;
+                        if (lane == 0 && nb) bulk_store_s2g(dst, sm.buf, nb);
                     }
+                    for (uint32_t b = nb + lane; b < produced; b += 32) dst[b] = sm.buf[b];
                 }
                 __syncwarp();
             }
         }
         if (lane == 0) { out_size[c] = produced; status[c] = st; }
     }
+    if (lane == 0) bulk_store_wait_read();
 }
 
 } // namespace msc

@@ -3,7 +3,6 @@
 #include "shim_common.h"
 #include "kernels/lznt1_decode.cuh"
 #include "kernels/lznt1_encode.cuh"
-#include "kernels/lznt1_decode_lanes.cuh"
 #include "kernels/lznt1_index.cuh"
 #include <stdlib.h>
 #include <string.h>
@@ -244,23 +243,17 @@ MSCompStatus mscomp_gpu_lznt1_index(mscomp_gpu_ctx* ctx, const uint8_t* d_in, si
 MSCompStatus msc_lznt1_decode_chunks(mscomp_gpu_ctx* ctx, const uint8_t* d_in, size_t in_len, const uint64_t* d_chunk_off, uint32_t nchunks,
                                      uint8_t* d_out, uint32_t* sizes, int32_t* status)
 {
-    // Two mappings of the same decoder.  Default: a warp per chunk with the chunk staged in shared memory -- its DRAM
-    // traffic equals the algorithmic bytes (profiles/traffic.json).  MSCOMP_LZNT1_DECODE=lanes selects the
-    // lane-per-chunk variant: same speed on B200 but every lane's 4 KiB window lives in L2/HBM, and with ~300k
-    // chunks in flight the match reads miss L2 (20x read amplification measured), so it is not the default.
-    static const char* mode = getenv("MSCOMP_LZNT1_DECODE");
-    const bool lanes = mode && strcmp(mode, "lanes") == 0;
-    if (lanes) {
-        const uint32_t tpb = 32 * LZL_WARPS_PER_BLOCK;
-        const uint32_t blocks = (nchunks + tpb - 1) / tpb, cap = (uint32_t)ctx->sm_count * 16;
-        MSC_LAUNCH(ctx, lznt1_decode_lanes_kernel, blocks < cap ? blocks : cap, tpb,
-                   d_in, (uint64_t)in_len, d_chunk_off, nchunks, d_out, sizes, status);
-    } else {
-        const uint32_t blocks = (nchunks + LZNT1_WARPS_PER_BLOCK - 1) / LZNT1_WARPS_PER_BLOCK;
-        const uint32_t cap = (uint32_t)ctx->sm_count * 6 * 4;             // 6 resident blocks per SM, a few waves
-        MSC_LAUNCH(ctx, lznt1_decode_kernel, blocks < cap ? blocks : cap, LZNT1_WARPS_PER_BLOCK * 32,
-                   d_in, (uint64_t)in_len, d_chunk_off, nchunks, d_out, sizes, status);
+    // A warp per chunk, the chunk decoded in place in shared memory (6 KB per warp): DRAM traffic equals the algorithmic
+    // bytes.  Persistent blocks: 8 per SM (32 warps, the register budget of the kernel), each warp strides over the chunks.
+    static int per_sm = 0;
+    if (!per_sm) {
+        cudaFuncSetAttribute(lznt1_decode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lznt1_decode_kernel, LZNT1_WARPS_PER_BLOCK * 32, 0) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 8; }
     }
+    const uint32_t blocks = (nchunks + LZNT1_WARPS_PER_BLOCK - 1) / LZNT1_WARPS_PER_BLOCK;
+    const uint32_t cap = (uint32_t)ctx->sm_count * (uint32_t)per_sm;
+    MSC_LAUNCH(ctx, lznt1_decode_kernel, blocks < cap ? blocks : cap, LZNT1_WARPS_PER_BLOCK * 32,
+               d_in, (uint64_t)in_len, d_chunk_off, nchunks, d_out, sizes, status);
     return msc_cuda_status(cudaGetLastError(), "lznt1_decode");
 }
 

@@ -4,7 +4,6 @@
 #include "../../ms-compress_b200/csrc/kernels/lznt1_decode.cuh"
 #include "../../ms-compress_b200/csrc/kernels/lznt1_encode.cuh"
 #include "../../ms-compress_b200/csrc/kernels/lznt1_index.cuh"
-#include "../../ms-compress_b200/csrc/kernels/lznt1_decode_lanes.cuh"
 #include "../../ms-compress_b200/csrc/kernels/compact.cuh"
 #include "../../ms-compress_b200/csrc/kernels/xhuff_decode.cuh"
 #include "../../ms-compress_b200/csrc/kernels/xpress_decode.cuh"
@@ -20,13 +19,6 @@ void emu_lznt1_decode(const uint8_t* in, uint64_t in_len, const uint64_t* chunk_
                       uint8_t* out, uint32_t* out_size, int32_t* status, uint32_t grid)
 {
     emu::launch(msc::lznt1_decode_kernel, dim3e(grid), dim3e(msc::LZNT1_WARPS_PER_BLOCK * 32),
-                in, in_len, chunk_off, nchunks, out, out_size, status);
-}
-
-void emu_lznt1_decode_lanes(const uint8_t* in, uint64_t in_len, const uint64_t* chunk_off, uint32_t nchunks,
-                            uint8_t* out, uint32_t* out_size, int32_t* status, uint32_t grid)
-{
-    emu::launch(msc::lznt1_decode_lanes_kernel, dim3e(grid), dim3e(msc::LZL_WARPS_PER_BLOCK * 32),
                 in, in_len, chunk_off, nchunks, out, out_size, status);
 }
 

@@ -19,7 +19,7 @@ for fmt,(dk,ek) in {"xpress_huff":("emu_xhuff_decode","emu_xhuff_encode"),"xpres
     st,ol,outs2=emu_util.emu_batch(emu,dk,outs,[len(p) for p in plains])
     assert not st.any() and outs2==plains
     print(fmt,'ok')
-for kern in ("emu_lznt1_decode","emu_lznt1_decode_lanes"):
+for kern in ("emu_lznt1_decode",):
     for p in plains:
         rc,c=ocall('lznt1_compress',p,len(p)+100)
         st,sz,ch=emu_util.emu_lznt1_decode(emu,c,kernel=kern); assert not st.any() and b''.join(ch)==p

@@ -9,7 +9,7 @@ from emu_util import emu_lznt1_decode, emu_lznt1_encode, lznt1_walk
 SIZES = [1, 2, 3, 4, 7, 8, 9, 16, 17, 31, 32, 33, 100, 4095, 4096, 4097, 8193, 65536, 150000]
 
 
-KERNELS = ["emu_lznt1_decode", "emu_lznt1_decode_lanes"]      # warp per chunk, lane per chunk
+KERNELS = ["emu_lznt1_decode"]      # warp per chunk
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
