@@ -132,6 +132,20 @@ __device__ __forceinline__ void bulk_store_wait_read()
 #endif
 }
 
+// One byte of shared memory by its 32-bit shared-window address `saddr` (base / base_saddr = generic pointer and shared
+// address of one reference byte: the emulator, where a 32-bit address is not enough, reads base[saddr - base_saddr]).
+__device__ __forceinline__ uint32_t lds_u8(const uint8_t* base, uint32_t base_saddr, uint32_t saddr)
+{
+#ifndef MSC_EMU
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
+    (void)base; (void)base_saddr;
+    return v;
+#else
+    return base[saddr - base_saddr];
+#endif
+}
+
 // Inclusive warp prefix sum.
 __device__ __forceinline__ int warp_incl_scan(int v)
 {

@@ -59,8 +59,11 @@ __device__ __forceinline__ void lznt1_shift_limit(int p, int& shift, int& limit)
 // the same for positions that may be garbage (a damaged stream): the shift never leaves [4, 12]
 __device__ __forceinline__ int lzd_token_shift(int p)
 {
-    int m = (p <= 16) ? 4 : (32 - __clz(p - 1));
-    if (m > 12) m = 12;
+    int x = p - 1;
+    x = x < 0 ? 0 : x;
+    int m = 32 - __clz(x);                           // p <= 1 gives 0
+    m = m < 4 ? 4 : m;
+    m = m > 12 ? 12 : m;
     return 16 - m;
 }
 
@@ -94,8 +97,9 @@ __device__ __forceinline__ int lzd_group_len(const uint32_t (&it)[8], unsigned f
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         if (ALL8 || j < nit) {
-            if ((f >> j) & 1) { const int Sj = lzd_token_shift(pos); pos += (int)(it[j] & ((1u << Sj) - 1)) + 3; }
-            else pos += 1;
+            const int Sj = lzd_token_shift(pos);
+            const int l = (int)(it[j] & ((1u << Sj) - 1)) + 3;
+            pos += ((f >> j) & 1) ? l : 1;
         }
     }
     const int g = pos - gs;
@@ -112,13 +116,14 @@ __device__ __forceinline__ bool lzd_emit(const uint32_t (&it)[8], unsigned f, in
     for (int j = 0; j < 8; ++j) {
         if (ALL8 || j < nit) {
             const uint32_t t = it[j];
-            if ((f >> j) & 1) {
-                const int Sj = MIXED ? lzd_token_shift(pos) : S0;
-                const int l = (int)(t & ((1u << Sj) - 1)) + 3, off = (int)(t >> Sj) + 1;
-                bad |= off > pos;                                            // :65 / :98
-                list[li++] = t | ((uint32_t)pos << 16) | ((uint32_t)(Sj - 4) << 28);
-                pos += l;
-            } else buf[pos++] = (uint8_t)t;
+            const bool tk = (f >> j) & 1;
+            const int Sj = MIXED ? lzd_token_shift(pos) : S0;
+            const int l = (int)(t & ((1u << Sj) - 1)) + 3, off = (int)(t >> Sj) + 1;
+            bad |= tk && off > pos;                                          // :65 / :98
+            if (tk) list[li] = t | ((uint32_t)pos << 16) | ((uint32_t)(Sj - 4) << 28);
+            else buf[pos] = (uint8_t)t;
+            li += tk ? 1 : 0;
+            pos += tk ? l : 1;
         }
     }
     return bad;
@@ -128,6 +133,7 @@ __device__ __forceinline__ bool lzd_emit(const uint32_t (&it)[8], unsigned f, in
 __device__ __forceinline__ int lznt1_decode_payload(Lznt1WarpSmem& sm, const int in0, const int n)
 {
     uint8_t* const buf = sm.buf;
+    const uint32_t buf_sa = smem_u32(sm.buf);
     const uint8_t* const pin = sm.buf + in0;
     const int lane = lane_id();
     int q = 0;          // payload offset of the round's first flag byte (uniform)
@@ -135,10 +141,11 @@ __device__ __forceinline__ int lznt1_decode_payload(Lznt1WarpSmem& sm, const int
 
     while (q < n) {
         // ---- 1. chase: lane i walks i groups ahead of q ------------------------------------------------------
-        int s = q;
+        uint32_t sa = buf_sa + (uint32_t)(in0 + q);                          // (shared address; 4 instructions per step: test, load, popc, add)
 #pragma unroll
         for (int step = 0; step < 31; ++step)
-            if (step < lane) s += 9 + __popc((unsigned)pin[s]);
+            if (step < lane) sa += 9u + (uint32_t)__popc(lds_u8(buf, buf_sa, sa));
+        const int s = (int)(sa - buf_sa) - in0;
         const bool act = s < n;
         const unsigned f = act ? (unsigned)pin[s] : 0u;
         const int qn = __shfl_sync(FULL, s + 9 + __popc(f), 31);            // first flag byte of the next round (>= n: none)
@@ -185,13 +192,16 @@ __device__ __forceinline__ int lznt1_decode_payload(Lznt1WarpSmem& sm, const int
         bool mixed = false;
         if (__any_sync(FULL, lastA >= 0 && gs + lastA > lim)) {
             mixed = true;
+            // Positions taken under S0 can only be too large.  If even they stay within the next power of two, every token
+            // behind the crossing has shift S0 - 1 at its tentative and at its true position alike: one pass settles the round.
+            const bool single = P + (__shfl_sync(FULL, incl, 31) & 0xFFFFF) <= 2 * lim;
             for (int iter = 0; iter < 34; ++iter) {
                 const int g2 = all8 ? lzd_group_len<true>(it, f, nit, gs) : lzd_group_len<false>(it, f, nit, gs);
                 const bool moved = g2 != glen;
                 glen = g2;
                 incl = warp_incl_scan(glen | (ntk << 20));
                 gs = P + (incl & 0xFFFFF) - glen;
-                if (!__any_sync(FULL, moved)) break;                         // lengths agree with the positions they were taken at
+                if (single || !__any_sync(FULL, moved)) break;               // lengths agree with the positions they were taken at
             }
         }
         const int total = __shfl_sync(FULL, incl, 31);
