@@ -99,6 +99,33 @@ MSCOMPAPI MSCompStatus mscomp_gpu_xpress_compress_batch(mscomp_gpu_ctx* ctx, con
 MSCOMPAPI MSCompStatus mscomp_gpu_xpress_decompress_batch(mscomp_gpu_ctx* ctx, const uint8_t* d_in, uint8_t* d_out,
                                                           const mscomp_gpu_batch* batch);
 
+/* An Xpress-Huffman stream is bit-serial (variable-length codes, raw length bytes at the reader's byte cursor, chunk ends stored
+ * nowhere: reference src/xpress_huff_decompress.cpp:39-162), so without further knowledge one GPU lane walks a stream.  A
+ * side-band RESTART INDEX -- never part of the stream -- records the reference reader's state (include/mscomp/Bitstream.h:34-44)
+ * at every 64th symbol; with it every 64-symbol segment decodes on its own lane (one warp per stream).
+ *   mscomp_gpu_xpress_huff_decompress_batch          builds the index in scratch memory (serial walk, one lane per stream), then decodes
+ *   mscomp_gpu_xpress_huff_index_batch               only the walk: fills out_len / status of the batch (no output bytes) and the index
+ *   mscomp_gpu_xpress_huff_decompress_batch_indexed  only the decode, from an index kept by the caller (e.g. made once after compressing)
+ * Stream i owns entries d_index[d_index_off[i] .. d_index_off[i+1]) (count+1 offsets, in entries); d_nseg[i] = entries in use.
+ * mscomp_gpu_xpress_huff_index_bound(out_cap) entries are always enough for a stream with out_cap bytes of output room.  The
+ * decoder follows an index only as far as it is consistent with the stream: every segment must end exactly in the next entry's
+ * state; streams where it does not are decoded without the index (same bytes, same status codes as the reference). */
+typedef struct mscomp_gpu_xhuff_seg {
+    uint32_t mask;        /* bit window of the reader, valid bits left-aligned */
+    uint32_t ip;          /* byte offset of the next unread byte of the stream */
+    uint32_t out_pos;     /* output bytes produced before the segment's first symbol */
+    uint32_t info;        /* bits 0-5: valid bits in mask; bit 7: first segment of a chunk (its 256-byte table is at ip - 260);
+                             bits 8-15: symbols in the segment (1..64) */
+} mscomp_gpu_xhuff_seg;
+MSCOMPAPI uint64_t     mscomp_gpu_xpress_huff_index_bound(uint64_t out_cap);
+MSCOMPAPI MSCompStatus mscomp_gpu_xpress_huff_index_batch(mscomp_gpu_ctx* ctx, const uint8_t* d_in, const mscomp_gpu_batch* batch,
+                                                          mscomp_gpu_xhuff_seg* d_index, const uint64_t* d_index_off, uint32_t* d_nseg);
+MSCOMPAPI MSCompStatus mscomp_gpu_xpress_huff_decompress_batch_indexed(mscomp_gpu_ctx* ctx, const uint8_t* d_in, uint8_t* d_out,
+                                                                       const mscomp_gpu_batch* batch, const mscomp_gpu_xhuff_seg* d_index,
+                                                                       const uint64_t* d_index_off, const uint32_t* d_nseg);
+/* Diagnostic: streams the indexed decoder handed to the index-free decoder since the context was created (synchronises). */
+MSCOMPAPI uint64_t     mscomp_gpu_xpress_huff_second_chances(mscomp_gpu_ctx* ctx);
+
 /* Plain Xpress is one unbroken stream per buffer (flag words and shared length nibbles chain every item to the previous
  * ones), so a reference-made stream decodes on one GPU lane.  Streams made HERE can carry a side-band restart index --
  * never part of the stream, the stream stays byte-for-byte what the call above produces -- with one entry per seg_bytes

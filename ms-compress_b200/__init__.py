@@ -89,6 +89,11 @@ def lib():
                     continue
                 f = getattr(L, "mscomp_gpu_%s_%s_batch" % (fmt, op))
                 f.restype, f.argtypes = i32, [vp, vp, vp, vp]
+        L.mscomp_gpu_xpress_huff_index_bound.restype, L.mscomp_gpu_xpress_huff_index_bound.argtypes = u64, [u64]
+        L.mscomp_gpu_xpress_huff_index_batch.restype, L.mscomp_gpu_xpress_huff_index_batch.argtypes = i32, [vp, vp, vp, vp, vp, vp]
+        L.mscomp_gpu_xpress_huff_decompress_batch_indexed.restype = i32
+        L.mscomp_gpu_xpress_huff_decompress_batch_indexed.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+        L.mscomp_gpu_xpress_huff_second_chances.restype, L.mscomp_gpu_xpress_huff_second_chances.argtypes = u64, [vp]
         L.mscomp_gpu_xpress_compress_batch_indexed.restype = i32
         L.mscomp_gpu_xpress_compress_batch_indexed.argtypes = [vp, vp, vp, vp, u32, vp, u32]
         L.mscomp_gpu_xpress_decompress_batch_indexed.restype = i32
@@ -300,6 +305,40 @@ class GpuContext:
         st = f(self.handle, d_in.data_ptr(), d_out.data_ptr(), ctypes.byref(batch))
         if st < 0:
             raise MSCompError(f.__name__, st)
+
+    # -- Xpress-Huffman restart index (mscomp_gpu_xhuff_seg: 4 x uint32 per entry) --
+    def xhuff_index_alloc(self, out_caps):
+        """(index tensor, offsets tensor [count+1], nseg tensor) with room for streams of the given output capacities."""
+        t = self.torch
+        bound = [int(lib().mscomp_gpu_xpress_huff_index_bound(int(c))) for c in out_caps] if len(out_caps) < 4096 else None
+        if bound is None:                           # large batches: the bound formula, vectorised (cap/64 + cap/65536 + 3)
+            caps = t.as_tensor(out_caps, dtype=t.int64)
+            b = caps // 64 + caps // 65536 + 3
+        else:
+            b = t.as_tensor(bound, dtype=t.int64)
+        off = t.zeros(len(out_caps) + 1, dtype=t.int64)
+        off[1:] = t.cumsum(b, 0)
+        total = int(off[-1])
+        return (t.zeros(max(total, 1) * 4, dtype=t.int32, device=self.device), off.to(self.device),
+                t.zeros(len(out_caps), dtype=t.int32, device=self.device))
+
+    def xhuff_index(self, d_in, batch, d_index, d_index_off, d_nseg):
+        """The serial walk only: fills the batch's out_len / status and the restart index (no output bytes)."""
+        st = lib().mscomp_gpu_xpress_huff_index_batch(self.handle, d_in.data_ptr(), ctypes.byref(batch), d_index.data_ptr(),
+                                                      d_index_off.data_ptr(), d_nseg.data_ptr())
+        if st < 0:
+            raise MSCompError("mscomp_gpu_xpress_huff_index_batch", st)
+
+    def xhuff_decompress_indexed(self, d_in, d_out, batch, d_index, d_index_off, d_nseg):
+        """Decode from a restart index kept by the caller: one warp per stream, one lane per 64-symbol segment."""
+        st = lib().mscomp_gpu_xpress_huff_decompress_batch_indexed(self.handle, d_in.data_ptr(), d_out.data_ptr(), ctypes.byref(batch),
+                                                                   d_index.data_ptr(), d_index_off.data_ptr(), d_nseg.data_ptr())
+        if st < 0:
+            raise MSCompError("mscomp_gpu_xpress_huff_decompress_batch_indexed", st)
+
+    def xhuff_second_chances(self):
+        """Streams the indexed Xpress-Huffman decoder handed to the index-free decoder so far (diagnostic)."""
+        return int(lib().mscomp_gpu_xpress_huff_second_chances(self.handle))
 
     XPRESS_SEG_WORDS = 6     # uint32 fields of mscomp_gpu_xpress_seg
 

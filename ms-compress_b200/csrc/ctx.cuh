@@ -91,6 +91,15 @@ struct mscomp_gpu_ctx {
         pinned_big_cap = want;
         return pinned_big;
     }
+    // A few zero-initialised device counters (diagnostics), allocated on first use.
+    unsigned long long* counters = nullptr;
+    unsigned long long* get_counters()
+    {
+        if (counters) return counters;
+        if (cudaMalloc((void**)&counters, 256) != cudaSuccess) { cudaGetLastError(); counters = nullptr; return nullptr; }
+        cudaMemsetAsync(counters, 0, 256, stream);
+        return counters;
+    }
     // Kernels that need more than 48 KB of dynamic shared memory opt in once per context (the attribute is per device,
     // and a context is bound to one device and used by one host thread at a time).
     static constexpr int kOptInMax = 32;

@@ -104,6 +104,8 @@ struct LaneOut {
     {
         if (is_match) copy_match(off, len); else put_byte(lit);
     }
+    __device__ __forceinline__ void new_chunk() {}
+    __device__ __forceinline__ void before_symbol(uint32_t, uint32_t, uint32_t) {}
     // write out the pending piece and the bytes of the unfinished word
     __device__ __forceinline__ void finish()
     {

@@ -45,6 +45,8 @@ struct LaneTok {
         opos += len;
     }
     __device__ __forceinline__ void finish() {}
+    __device__ __forceinline__ void new_chunk() {}
+    __device__ __forceinline__ void before_symbol(uint32_t, uint32_t, uint32_t) {}
 };
 
 // sink plumbing shared by the two parsers

@@ -177,6 +177,7 @@ __device__ __forceinline__ void xh_step(XhLane& L, XhWarpSmem& sm, int lane, Sin
         L.ip += 260;
         L.chunk_end = O.opos + XH_CHUNK;
         L.need_table = false;
+        O.new_chunk();
     }
     if (!(O.opos < L.chunk_end || !xh_mask_is_zero(L))) {       // end of chunk (:79, :127-133)
         XhLane T = L;                                            // trial decode of an end-of-stream symbol
@@ -185,6 +186,7 @@ __device__ __forceinline__ void xh_step(XhLane& L, XhWarpSmem& sm, int lane, Sin
         L.need_table = true;
         return;
     }
+    O.before_symbol(L.mask, (uint32_t)L.bits, L.ip);
     const uint32_t sym = xh_decode_symbol(L, sm, lane);
     if (sym == 0xFFFFu) { L.status = ST_DATA; return; }
     if (sym == (uint32_t)XH_EOS && L.in_len - L.ip == 0 && xh_mask_is_zero(L)) { L.status = 1; return; }   // :83
@@ -225,7 +227,8 @@ template <class Sink>
 __device__ __forceinline__ void xhuff_decode_body(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint32_t* __restrict__ tok, uint32_t count,
                                                   const uint64_t* __restrict__ in_off, const uint32_t* __restrict__ in_len,
                                                   const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ out_cap,
-                                                  uint32_t* __restrict__ out_len, int32_t* __restrict__ status, uint32_t* __restrict__ ntok)
+                                                  uint32_t* __restrict__ out_len, int32_t* __restrict__ status, uint32_t* __restrict__ ntok,
+                                                  int only_status = 0, unsigned long long* __restrict__ handled = nullptr)
 {
     MSC_DYN_SMEM(smem_raw);
     XhWarpSmem& sm = reinterpret_cast<XhWarpSmem*>(smem_raw)[threadIdx.x >> 5];
@@ -233,6 +236,10 @@ __device__ __forceinline__ void xhuff_decode_body(const uint8_t* __restrict__ in
     const uint32_t warps_total = gridDim.x * XHD_WARPS_PER_BLOCK;
     for (uint32_t g = blockIdx.x * XHD_WARPS_PER_BLOCK + (threadIdx.x >> 5); g * 32 < count; g += warps_total) {
         const uint32_t i = g * 32 + lane;
+        // only_status != 0: second-chance pass -- only the streams another decoder left marked with that status are decoded
+        const bool mine = i < count && (only_status == 0 || status[i] == only_status);
+        if (only_status != 0 && !__any_sync(FULL, mine)) continue;
+        if (mine && handled) atomicAdd(handled, 1ull);
         XhLane L;
         L.status = 1; L.in = in; L.in_len = 0; L.cap = 0; L.ip = 0; L.nused = 0;
         L.mask = 0; L.bits = 0; L.chunk_end = 0; L.need_table = true;
@@ -241,7 +248,7 @@ __device__ __forceinline__ void xhuff_decode_body(const uint8_t* __restrict__ in
 #pragma unroll
         for (int k = 0; k < 8; ++k) { L.baseP[k] = 0; L.litendP[k] = 0; }
         Sink O;
-        if (i < count) {
+        if (mine) {
             L.in = in + in_off[i]; L.in_len = in_len[i]; L.cap = out_cap[i];
             sink_init(O, out, tok, out_off[i]);
             L.status = 0;
@@ -251,7 +258,7 @@ __device__ __forceinline__ void xhuff_decode_body(const uint8_t* __restrict__ in
             if (L.status == 0) xh_step(L, sm, lane, O);
         }
         O.finish();
-        if (i < count) { out_len[i] = O.opos; status[i] = L.status == 1 ? ST_OK : L.status; sink_count(O, ntok, i); }
+        if (mine) { out_len[i] = O.opos; status[i] = L.status == 1 ? ST_OK : L.status; sink_count(O, ntok, i); }
     }
 }
 
@@ -262,6 +269,16 @@ xhuff_decode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, u
                     uint32_t* __restrict__ out_len, int32_t* __restrict__ status)
 {
     xhuff_decode_body<LaneOut>(in, out, nullptr, count, in_off, in_len, out_off, out_cap, out_len, status, nullptr);
+}
+
+// The same decoder as a second chance: only streams whose status equals only_status are decoded (and counted).
+__global__ void __launch_bounds__(32 * XHD_WARPS_PER_BLOCK)
+xhuff_decode_marked_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint32_t count,
+                           const uint64_t* __restrict__ in_off, const uint32_t* __restrict__ in_len,
+                           const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ out_cap,
+                           uint32_t* __restrict__ out_len, int32_t* __restrict__ status, int only_status, unsigned long long* __restrict__ handled)
+{
+    xhuff_decode_body<LaneOut>(in, out, nullptr, count, in_off, in_len, out_off, out_cap, out_len, status, nullptr, only_status, handled);
 }
 
 __global__ void __launch_bounds__(32 * XHD_WARPS_PER_BLOCK)

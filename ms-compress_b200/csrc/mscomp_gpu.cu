@@ -9,6 +9,8 @@
 #include "kernels/compact.cuh"
 #include "kernels/summary.cuh"
 #include "kernels/xhuff_decode.cuh"
+#include "kernels/xhuff_index.cuh"
+#include "kernels/xhuff_decode_indexed.cuh"
 #include "kernels/xpress_decode.cuh"
 #include "kernels/xhuff_encode.cuh"
 #include "kernels/xpress_encode.cuh"
@@ -89,6 +91,7 @@ void mscomp_gpu_destroy(mscomp_gpu_ctx* ctx)
     for (int i = 0; i < SC_COUNT; ++i) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->pinned_big) cudaFreeHost(ctx->pinned_big);
+    if (ctx->counters) cudaFree(ctx->counters);
     if (ctx->copy_stream) {
         for (int i = 0; i < 16; ++i) { cudaEventDestroy(ctx->copy_ev[i]); cudaEventDestroy(ctx->work_ev[i]); }
         cudaStreamDestroy(ctx->copy_stream); cudaStreamDestroy(ctx->down_stream);
@@ -330,27 +333,134 @@ MSCompStatus mscomp_gpu_xpress_huff_compress_batch(mscomp_gpu_ctx* ctx, const ui
     return msc_xpress_huff_compress_units(ctx, d_in, d_out, b, 0);
 }
 
+// ---- Xpress-Huffman decode: restart index + one lane per segment ---------------------------------------------------------
+static_assert(sizeof(XhSeg) == sizeof(mscomp_gpu_xhuff_seg), "index entry layout");
+
+namespace msc {
+// room (entries) the index of every stream can need: bounded by its output capacity and by its input bits
+__global__ void xhi_room_kernel(const uint32_t* __restrict__ in_len, const uint32_t* __restrict__ out_cap, uint32_t n, uint32_t* __restrict__ room)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t by_out = xhi_max_segments(out_cap[i]);
+    const uint64_t by_in = (uint64_t)in_len[i] / 8 + (uint64_t)in_len[i] / 260 + 3;      // >= 1 bit per symbol, >= 260 bytes per chunk
+    const uint64_t r = by_out < by_in ? by_out : by_in;
+    room[i] = r > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)r;
+}
+} // namespace msc
+
+uint64_t mscomp_gpu_xpress_huff_index_bound(uint64_t out_cap) { return xhi_max_segments(out_cap); }
+
+static uint32_t xhd_grid(const mscomp_gpu_ctx* ctx, uint32_t count)
+{
+    const uint32_t groups = (count + 32 * XHD_WARPS_PER_BLOCK - 1) / (32 * XHD_WARPS_PER_BLOCK), cap = (uint32_t)ctx->sm_count * 2;
+    return groups < cap ? groups : cap;
+}
+
+// Streams the indexed decoder could not follow (an index that does not describe the stream) are decoded by the lane-per-stream
+// decoder, which needs no index and reproduces the reference's status codes; it finds nothing to do otherwise.
+static void xhuff_second_chance(mscomp_gpu_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, const mscomp_gpu_batch* b)
+{
+    unsigned long long* d_cnt = ctx->get_counters();
+    MSC_OPT_IN_SMEM(xhuff_decode_marked_kernel, XHD_SMEM_BYTES);
+    MSC_LAUNCH_SMEM(ctx, xhuff_decode_marked_kernel, xhd_grid(ctx, b->count), 32 * XHD_WARPS_PER_BLOCK, XHD_SMEM_BYTES,
+                    d_in, d_out, b->count, b->d_in_off, b->d_in_len, b->d_out_off, b->d_out_cap, b->d_out_len, b->d_status, (int)ST_INDEX,
+                    d_cnt);
+}
+
+// Streams the indexed decoder handed to the lane-per-stream decoder since the context was created (diagnostic; synchronises).
+uint64_t mscomp_gpu_xpress_huff_second_chances(mscomp_gpu_ctx* ctx)
+{
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    unsigned long long* d_cnt = ctx->get_counters();
+    if (!d_cnt) return 0;
+    unsigned long long h = 0;
+    cudaMemcpyAsync(&h, d_cnt, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    return h;
+}
+
+static uint32_t xhx_grid(const mscomp_gpu_ctx* ctx, uint32_t count)
+{
+    static int per_sm = 0;
+    if (!per_sm) {
+        cudaFuncSetAttribute(xhuff_decode_indexed_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, xhuff_decode_indexed_kernel, XHX_WARPS_PER_BLOCK * 32, 0) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 8; }
+    }
+    const uint32_t blocks = (count + XHX_WARPS_PER_BLOCK - 1) / XHX_WARPS_PER_BLOCK, cap = (uint32_t)ctx->sm_count * (uint32_t)per_sm;
+    return blocks < cap ? blocks : cap;
+}
+
+MSCompStatus mscomp_gpu_xpress_huff_index_batch(mscomp_gpu_ctx* ctx, const uint8_t* d_in, const mscomp_gpu_batch* b,
+                                                mscomp_gpu_xhuff_seg* d_index, const uint64_t* d_index_off, uint32_t* d_nseg)
+{
+    if (!ctx || !b || (b->count && (!d_in || !b->d_in_off || !b->d_in_len || !b->d_out_cap || !b->d_out_len || !b->d_status || !d_index || !d_index_off || !d_nseg)))
+        return MSCOMP_ARG_ERROR;
+    if (!b->count) return MSCOMP_OK;
+    cudaSetDevice(ctx->device);
+    MSC_OPT_IN_SMEM(xhuff_index_kernel, XHD_SMEM_BYTES);
+    MSC_LAUNCH_SMEM(ctx, xhuff_index_kernel, xhd_grid(ctx, b->count), 32 * XHD_WARPS_PER_BLOCK, XHD_SMEM_BYTES,
+                    d_in, b->count, b->d_in_off, b->d_in_len, b->d_out_cap, (XhSeg*)d_index, d_index_off, d_nseg, b->d_out_len, b->d_status);
+    return msc_cuda_status(cudaGetLastError(), "xpress_huff_index");
+}
+
+MSCompStatus mscomp_gpu_xpress_huff_decompress_batch_indexed(mscomp_gpu_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, const mscomp_gpu_batch* b,
+                                                             const mscomp_gpu_xhuff_seg* d_index, const uint64_t* d_index_off, const uint32_t* d_nseg)
+{
+    if (!batch_ok(ctx, d_in, d_out, b) || (b->count && (!d_index || !d_index_off || !d_nseg))) return MSCOMP_ARG_ERROR;
+    if (!b->count) return MSCOMP_OK;
+    cudaSetDevice(ctx->device);
+    const uint32_t grid = xhx_grid(ctx, b->count);
+    uint32_t* d_tok = (uint32_t*)ctx->get(SC_SLOTS, (size_t)grid * XHX_WARPS_PER_BLOCK * XHX_TOKBUF_WORDS * sizeof(uint32_t) + 64);
+    if (!d_tok) return MSCOMP_MEM_ERROR;
+    MSC_LAUNCH(ctx, xhuff_decode_indexed_kernel, grid, 32 * XHX_WARPS_PER_BLOCK,
+               d_in, d_out, b->count, b->d_in_off, b->d_in_len, b->d_out_off, b->d_out_cap, (const XhSeg*)d_index, d_index_off, d_nseg,
+               b->d_out_len, b->d_status, 0, d_tok);
+    xhuff_second_chance(ctx, d_in, d_out, b);
+    return msc_cuda_status(cudaGetLastError(), "xpress_huff_decompress");
+}
+
 MSCompStatus mscomp_gpu_xpress_huff_decompress_batch(mscomp_gpu_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, const mscomp_gpu_batch* b)
 {
     if (!batch_ok(ctx, d_in, d_out, b)) return MSCOMP_ARG_ERROR;
     if (!b->count) return MSCOMP_OK;
     cudaSetDevice(ctx->device);
-    MSC_OPT_IN_SMEM(xhuff_parse_kernel, XHD_SMEM_BYTES);
-    MSC_OPT_IN_SMEM(xhuff_decode_kernel, XHD_SMEM_BYTES);
-    // 7 warps x 16 KB per block, two blocks per SM
-    const uint32_t groups = (b->count + 32 * XHD_WARPS_PER_BLOCK - 1) / (32 * XHD_WARPS_PER_BLOCK), cap = (uint32_t)ctx->sm_count * 2;
-    uint32_t* tok = b->count >= 64 ? token_scratch(ctx, b) : nullptr;
-    uint32_t* ntok = tok ? (uint32_t*)ctx->get(SC_AUX1, ((size_t)b->count + 1) * sizeof(uint32_t)) : nullptr;
-    if (tok && ntok) {
-        // two kernels: bit parsing by one lane per buffer (tokens only), LZ77 execution by one warp per buffer
-        MSC_LAUNCH_SMEM(ctx, xhuff_parse_kernel, groups < cap ? groups : cap, 32 * XHD_WARPS_PER_BLOCK, XHD_SMEM_BYTES,
-                        d_in, tok, b->count, b->d_in_off, b->d_in_len, b->d_out_off, b->d_out_cap, b->d_out_len, b->d_status, ntok);
-        const uint32_t ab = (b->count + LZA_WARPS_PER_BLOCK - 1) / LZA_WARPS_PER_BLOCK, acap = (uint32_t)ctx->sm_count * 16;
-        MSC_LAUNCH(ctx, lz_apply_kernel, ab < acap ? ab : acap, 32 * LZA_WARPS_PER_BLOCK, tok, ntok, b->d_out_off, b->d_status, b->count, d_out);
-    } else {
-        MSC_LAUNCH_SMEM(ctx, xhuff_decode_kernel, groups < cap ? groups : cap, 32 * XHD_WARPS_PER_BLOCK, XHD_SMEM_BYTES,
-                        d_in, d_out, b->count, b->d_in_off, b->d_in_len, b->d_out_off, b->d_out_cap, b->d_out_len, b->d_status);
+    static const char* mode = getenv("MSCOMP_LZ_DECODE");            // "fused": the lane-per-stream decoder only (no index, no scratch)
+    const bool fused = mode && strcmp(mode, "fused") == 0;
+    // 1. room for the restart index of every stream -> offsets (one small kernel + the size scan), total to the host
+    uint32_t* d_room = fused ? nullptr : (uint32_t*)ctx->get(SC_AUX1, ((size_t)b->count + 1) * sizeof(uint32_t) * 2);
+    uint64_t* d_ioff = fused ? nullptr : (uint64_t*)ctx->get(SC_AUX0, ((size_t)b->count + 2) * sizeof(uint64_t));
+    uint64_t* h_tot = (uint64_t*)ctx->get_pinned(256);
+    XhSeg* d_index = nullptr;
+    if (d_room && d_ioff && h_tot) {
+        uint32_t* d_nseg = d_room + b->count + 1;
+        MSC_LAUNCH(ctx, xhi_room_kernel, (b->count + 255) / 256, 256, b->d_in_len, b->d_out_cap, b->count, d_room);
+        MSC_LAUNCH(ctx, scan_sizes_kernel, 1, SCAN_THREADS, (const uint32_t*)d_room, b->count, (uint64_t)0, (const uint64_t*)nullptr, d_ioff, h_tot + 8);
+        if (cudaStreamSynchronize(ctx->stream) == cudaSuccess) {
+            const uint64_t total = h_tot[8];
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            const uint64_t need = total * sizeof(XhSeg) + 64;
+            if (need <= ctx->scratch_cap[SC_AUX2] || need <= (uint64_t)free_b / 2 + ctx->scratch_cap[SC_AUX2]) d_index = (XhSeg*)ctx->get(SC_AUX2, need);
+        }
+        const uint32_t grid = xhx_grid(ctx, b->count);
+        uint32_t* d_tok = d_index ? (uint32_t*)ctx->get(SC_SLOTS, (size_t)grid * XHX_WARPS_PER_BLOCK * XHX_TOKBUF_WORDS * sizeof(uint32_t) + 64) : nullptr;
+        if (d_index && d_tok) {
+            // 2. the serial walk, one lane per stream: statuses, lengths and the index; 3. the decode proper, one lane per segment
+            MSCompStatus st = mscomp_gpu_xpress_huff_index_batch(ctx, d_in, b, (mscomp_gpu_xhuff_seg*)d_index, d_ioff, d_nseg);
+            if (st != MSCOMP_OK) return st;
+            MSC_LAUNCH(ctx, xhuff_decode_indexed_kernel, grid, 32 * XHX_WARPS_PER_BLOCK,
+                       d_in, d_out, b->count, b->d_in_off, b->d_in_len, b->d_out_off, b->d_out_cap, (const XhSeg*)d_index, (const uint64_t*)d_ioff,
+                       (const uint32_t*)d_nseg, b->d_out_len, b->d_status, 1, d_tok);
+            xhuff_second_chance(ctx, d_in, d_out, b);
+            return msc_cuda_status(cudaGetLastError(), "xpress_huff_decompress");
+        }
     }
+    // no room for an index (or MSCOMP_LZ_DECODE=fused): every lane decodes its own stream and writes its own bytes
+    MSC_OPT_IN_SMEM(xhuff_decode_kernel, XHD_SMEM_BYTES);
+    MSC_LAUNCH_SMEM(ctx, xhuff_decode_kernel, xhd_grid(ctx, b->count), 32 * XHD_WARPS_PER_BLOCK, XHD_SMEM_BYTES,
+                    d_in, d_out, b->count, b->d_in_off, b->d_in_len, b->d_out_off, b->d_out_cap, b->d_out_len, b->d_status);
     return msc_cuda_status(cudaGetLastError(), "xpress_huff_decompress");
 }
 

@@ -53,6 +53,7 @@ else:
     indexed = fmt == "xpress"                  # plain Xpress: with the side-band restart index (one entry per 16 KiB)
     seg_bytes, stride = 16384, (each + 16383) // 16384
     d_index = ctx.xpress_index_tensor(count, stride) if indexed else None
+    xh = ctx.xhuff_index_alloc([each] * count) if fmt == "xpress_huff" else None
     for _ in range(reps):
         if indexed:
             ctx.xpress_compress_indexed(d_in, d_comp, enc, seg_bytes, d_index, stride)
@@ -60,9 +61,15 @@ else:
         else:
             ctx.run_batch(fmt, "compress", d_in, d_comp, enc)
             ctx.run_batch(fmt, "decompress", d_comp, d_out, dec)
+            if xh is not None:                     # the same decode from a kept index (walk once, decode again)
+                ctx.xhuff_index(d_comp, dec, *xh)
+                d_out.zero_()
+                ctx.xhuff_decompress_indexed(d_comp, d_out, dec, *xh)
     torch.cuda.synchronize()
     assert int(st1.abs().sum()) == 0 and int(st2.abs().sum()) == 0 and torch.equal(d_out, d_in)
     C = int(c_len.to(torch.int64).sum())
+if fmt == "xpress_huff":
+    print("second chances:", ctx.xhuff_second_chances())
 for name, (calls, ms_tot) in ctx.profile_report().items():
     per = ms_tot / calls
     print("%-24s %8.3f ms/launch  %8.1f GB/s (U+C)  %8.1f GB/s (U)" % (name, per, (U + C) / 1e9 / (per / 1e3), U / 1e9 / (per / 1e3)))

@@ -6,6 +6,8 @@
 #include "../../ms-compress_b200/csrc/kernels/lznt1_index.cuh"
 #include "../../ms-compress_b200/csrc/kernels/compact.cuh"
 #include "../../ms-compress_b200/csrc/kernels/xhuff_decode.cuh"
+#include "../../ms-compress_b200/csrc/kernels/xhuff_index.cuh"
+#include "../../ms-compress_b200/csrc/kernels/xhuff_decode_indexed.cuh"
 #include "../../ms-compress_b200/csrc/kernels/xpress_decode.cuh"
 #include "../../ms-compress_b200/csrc/kernels/xhuff_encode.cuh"
 #include "../../ms-compress_b200/csrc/kernels/xpress_encode.cuh"
@@ -81,6 +83,34 @@ void emu_xpress_decode2(const uint8_t* in, uint8_t* out, uint32_t count, const u
     std::vector<uint32_t> tok(emu_extent(count, out_off, out_cap) + 16), ntok(count + 1);
     emu::launch(msc::xpress_parse_kernel, dim3e(grid), dim3e(32 * msc::XPD_WARPS_PER_BLOCK), in, tok.data(), count, in_off, in_len, out_off, out_cap, out_len, status, ntok.data());
     emu::launch(msc::lz_apply_kernel, dim3e(grid), dim3e(32 * msc::LZA_WARPS_PER_BLOCK), (const uint32_t*)tok.data(), (const uint32_t*)ntok.data(), out_off, (const int32_t*)status, count, out);
+}
+
+// Xpress-Huffman through the restart index: serial walk (one lane per stream) -> index; decode (one lane per segment); then the
+// second-chance pass for streams the indexed decoder gave up on.  damage != 0: entry `damage-1` of every index gets its byte
+// cursor shifted before decoding (an index that does not belong to the stream).  Returns the number of second chances taken.
+static uint64_t g_xhuff_second = 0;
+uint64_t emu_xhuff_second_chances() { return g_xhuff_second; }
+void emu_xhuff_decode_indexed(const uint8_t* in, uint8_t* out, uint32_t count, const uint64_t* in_off, const uint32_t* in_len,
+                              const uint64_t* out_off, const uint32_t* out_cap, uint32_t* out_len, int32_t* status, uint32_t grid, uint32_t damage, uint32_t trusted)
+{
+    using namespace msc;
+    std::vector<uint64_t> ioff(count + 1, 0);
+    for (uint32_t i = 0; i < count; ++i) {
+        const uint64_t by_out = xhi_max_segments(out_cap[i]), by_in = (uint64_t)in_len[i] / 8 + in_len[i] / 260 + 3;
+        ioff[i + 1] = ioff[i] + std::min(by_out, by_in);
+    }
+    std::vector<XhSeg> index(ioff[count] + 1);
+    std::vector<uint32_t> nseg(count + 1);
+    emu::launch(xhuff_index_kernel, dim3e(grid), dim3e(32 * XHD_WARPS_PER_BLOCK), in, count, in_off, in_len, out_cap, index.data(), (const uint64_t*)ioff.data(),
+                nseg.data(), out_len, status);
+    if (damage) for (uint32_t i = 0; i < count; ++i) if (nseg[i] >= damage) index[ioff[i] + damage - 1].ip += 2;
+    std::vector<uint4> tokbuf((size_t)grid * XHX_WARPS_PER_BLOCK * XHX_TOKBUF_WORDS / 4 + 4);
+    emu::launch(xhuff_decode_indexed_kernel, dim3e(grid), dim3e(32 * XHX_WARPS_PER_BLOCK), in, out, count, in_off, in_len, out_off, out_cap,
+                (const XhSeg*)index.data(), (const uint64_t*)ioff.data(), (const uint32_t*)nseg.data(), out_len, status, trusted ? 0 : 1, (uint32_t*)tokbuf.data());
+    unsigned long long handled = 0;
+    emu::launch(xhuff_decode_marked_kernel, dim3e(grid), dim3e(32 * XHD_WARPS_PER_BLOCK), in, out, count, in_off, in_len, out_off, out_cap, out_len, status,
+                (int)ST_INDEX, &handled);
+    g_xhuff_second += handled;
 }
 
 // two-pass plain Xpress encoder: match finding per 64 KiB segment (persistent blocks), then emission per buffer

@@ -156,3 +156,57 @@ def test_xpress_two_pass_encoder(emu, oracle, ms, with_index):
                                      extra=(P(index), ctypes.c_uint32(stride), ctypes.c_uint32(blk)))
             assert list(st4) == [0 if p else -3 for p in plains]
             assert all(o == p for o, p in zip(outs, plains) if p)
+
+
+# ---- Xpress-Huffman through the restart index (xhuff_index.cuh + xhuff_decode_indexed.cuh) -----------------------------------
+
+def _second(emu):
+    emu.emu_xhuff_second_chances.restype = ctypes.c_uint64
+    return int(emu.emu_xhuff_second_chances())
+
+
+@pytest.mark.parametrize("trusted", [0, 1])
+def test_xhuff_indexed_decode_matches_oracle(emu, oracle, ms, trusted):
+    """Serial walk -> index -> one lane per segment.  trusted=1: the decoder takes lengths / statuses from the index alone (the public
+    indexed entry point); valid streams must never need the second-chance (index-free) decoder."""
+    plains = corpus(ms)
+    comps = [oracle.compress("xpress_huff", p) for p in plains]
+    before = _second(emu)
+    st, ol, outs = emu_batch(emu, "emu_xhuff_decode_indexed", comps + [b""], [len(p) for p in plains] + [0],
+                             extra=(ctypes.c_uint32(0), ctypes.c_uint32(trusted)))
+    assert not st.any()
+    assert outs[:-1] == plains and outs[-1] == b""
+    assert _second(emu) - before == 0
+
+
+@pytest.mark.parametrize("damage", [1, 2, 5])
+def test_xhuff_indexed_decode_survives_a_wrong_index(emu, oracle, ms, damage):
+    plains = [ms.generate("text", 70000, 3), ms.generate("runs", 40000, 4), b"abc" * 3000]
+    comps = [oracle.compress("xpress_huff", p) for p in plains]
+    before = _second(emu)
+    st, ol, outs = emu_batch(emu, "emu_xhuff_decode_indexed", comps, [len(p) for p in plains], extra=(ctypes.c_uint32(damage), ctypes.c_uint32(1)))
+    assert not st.any() and outs == plains
+    assert _second(emu) - before >= 1
+
+
+def test_xhuff_indexed_status_equals_oracle_on_bad_input(emu, oracle, ms):
+    rnd = random.Random(6)
+    cases = []
+    for kind in ("text", "runs"):
+        n = 20000
+        plain = ms.generate(kind, n, 9)
+        comp = oracle.compress("xpress_huff", plain)
+        cases += [(comp, cap) for cap in (n, n + 100, n - 1, n // 2, 0)]
+        cases += [(comp[:-t], n) for t in (1, 2, 3, len(comp) // 2)]
+        cases += [(comp + b"\0\0", n), (comp + b"\0\0", n + 10), (comp + b"\x55", n)]
+        for _ in range(40):
+            b = bytearray(comp)
+            for _ in range(rnd.randint(1, 3)):
+                b[rnd.randrange(len(b))] ^= 1 << rnd.randrange(8)
+            cases.append((bytes(b), n + rnd.choice((0, 64))))
+    st, ol, outs = emu_batch(emu, "emu_xhuff_decode_indexed", [c for c, _ in cases], [cap for _, cap in cases], extra=(ctypes.c_uint32(0), ctypes.c_uint32(0)))
+    for i, (src, cap) in enumerate(cases):
+        rc, exp = oracle.decompress("xpress_huff", src, cap)
+        assert st[i] == rc, (i, st[i], rc)
+        if rc == 0:
+            assert outs[i] == exp
