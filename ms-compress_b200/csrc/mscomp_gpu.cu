@@ -426,11 +426,31 @@ MSCompStatus mscomp_gpu_xpress_huff_decompress_batch(mscomp_gpu_ctx* ctx, const 
     if (!batch_ok(ctx, d_in, d_out, b)) return MSCOMP_ARG_ERROR;
     if (!b->count) return MSCOMP_OK;
     cudaSetDevice(ctx->device);
-    static const char* mode = getenv("MSCOMP_LZ_DECODE");            // "fused": the lane-per-stream decoder only (no index, no scratch)
+    // Three ways to decode a batch that comes without an index (MSCOMP_LZ_DECODE selects one; default "tokens"):
+    //   tokens  one lane per stream parses into 4-byte tokens (scratch: 4 bytes per output byte), one warp per stream executes them
+    //   index   one lane per stream walks the stream and leaves a restart index, then one lane per SEGMENT decodes (the path of
+    //           mscomp_gpu_xpress_huff_decompress_batch_indexed, which skips the walk when the caller kept the index)
+    //   fused   one lane per stream does everything (no scratch at all; also the fallback when scratch cannot be had)
+    // Measured on configs[3] (65,536 x 64 KiB): tokens 30.7 ms, index 15.7 + 18.5 ms, fused 40.7 ms -- the walk is the same serial
+    // work in all three, so the index only pays when it is kept (18.5 ms).
+    static const char* mode = getenv("MSCOMP_LZ_DECODE");
     const bool fused = mode && strcmp(mode, "fused") == 0;
+    const bool use_index = mode && strcmp(mode, "index") == 0;
+    if (!fused && !use_index) {
+        MSC_OPT_IN_SMEM(xhuff_parse_kernel, XHD_SMEM_BYTES);
+        uint32_t* tok = b->count >= 64 ? token_scratch(ctx, b) : nullptr;
+        uint32_t* ntok = tok ? (uint32_t*)ctx->get(SC_AUX1, ((size_t)b->count + 1) * sizeof(uint32_t)) : nullptr;
+        if (tok && ntok) {
+            MSC_LAUNCH_SMEM(ctx, xhuff_parse_kernel, xhd_grid(ctx, b->count), 32 * XHD_WARPS_PER_BLOCK, XHD_SMEM_BYTES,
+                            d_in, tok, b->count, b->d_in_off, b->d_in_len, b->d_out_off, b->d_out_cap, b->d_out_len, b->d_status, ntok);
+            const uint32_t ab = (b->count + LZA_WARPS_PER_BLOCK - 1) / LZA_WARPS_PER_BLOCK, acap = (uint32_t)ctx->sm_count * 16;
+            MSC_LAUNCH(ctx, lz_apply_kernel, ab < acap ? ab : acap, 32 * LZA_WARPS_PER_BLOCK, tok, ntok, b->d_out_off, b->d_status, b->count, d_out);
+            return msc_cuda_status(cudaGetLastError(), "xpress_huff_decompress");
+        }
+    }
     // 1. room for the restart index of every stream -> offsets (one small kernel + the size scan), total to the host
-    uint32_t* d_room = fused ? nullptr : (uint32_t*)ctx->get(SC_AUX1, ((size_t)b->count + 1) * sizeof(uint32_t) * 2);
-    uint64_t* d_ioff = fused ? nullptr : (uint64_t*)ctx->get(SC_AUX0, ((size_t)b->count + 2) * sizeof(uint64_t));
+    uint32_t* d_room = !use_index ? nullptr : (uint32_t*)ctx->get(SC_AUX1, ((size_t)b->count + 1) * sizeof(uint32_t) * 2);
+    uint64_t* d_ioff = !use_index ? nullptr : (uint64_t*)ctx->get(SC_AUX0, ((size_t)b->count + 2) * sizeof(uint64_t));
     uint64_t* h_tot = (uint64_t*)ctx->get_pinned(256);
     XhSeg* d_index = nullptr;
     if (d_room && d_ioff && h_tot) {

@@ -190,3 +190,68 @@ def test_xpress_restart_index_on_gpu(ms, oracle):
         for p, o, n in zip(plains, in_off.tolist(), o_len.tolist()):
             if p:
                 assert n == len(p) and bytes(d_out[o:o + n].cpu().numpy()) == p
+
+
+def test_xhuff_restart_index_on_gpu(ms, oracle):
+    """Xpress-Huffman through the restart index: the serial walk (statuses, lengths, index) followed by the one-lane-per-segment
+    decoder must give the oracle's bytes and statuses -- for reference-made streams (multi-chunk, cross-chunk matches), damaged
+    streams and a damaged index (which sends the stream to the index-free decoder instead of into wrong output)."""
+    import numpy as np
+    import torch
+    rnd = random.Random(21)
+    ctx = ms.GpuContext()
+    plains = [ms.generate(k, n, 5 + n % 7) for k in ("text", "runs", "random") for n in (1, 100, 5000, 65536, 70000, 200000)]
+    plains += [b"abc" * 30000, bytes(150000), b""]
+    comps = [oracle.compress("xpress_huff", p) for p in plains]
+    caps = [len(p) for p in plains]
+    # damaged streams: the walk is the authority on their status
+    base = oracle.compress("xpress_huff", ms.generate("text", 20000, 9))
+    for _ in range(40):
+        b = bytearray(base)
+        for _ in range(rnd.randint(1, 3)):
+            b[rnd.randrange(len(b))] ^= 1 << rnd.randrange(8)
+        comps.append(bytes(b)); caps.append(20000 + rnd.choice((0, 64)))
+    comps += [base[:-1], base[:len(base) // 2], base + b"\0\0"]; caps += [20000, 20000, 20000]
+    c_off = np.cumsum([0] + [(len(c) + 31) // 16 * 16 for c in comps])
+    o_off = np.cumsum([0] + [(c + 31) // 16 * 16 for c in caps])
+    blob = np.zeros(int(c_off[-1]) + 64, dtype=np.uint8)
+    for c, o in zip(comps, c_off):
+        blob[o:o + len(c)] = np.frombuffer(c, dtype=np.uint8)
+    d_c = torch.from_numpy(blob).to(ctx.device)
+    d_out = torch.zeros(int(o_off[-1]) + 64, dtype=torch.uint8, device=ctx.device)
+    dec, o_len, st, keep = ctx.make_batch(c_off[:-1].tolist(), [len(c) for c in comps], o_off[:-1].tolist(), caps)
+    d_index, d_ioff, d_nseg = ctx.xhuff_index_alloc(caps)
+    before = ctx.xhuff_second_chances()
+    ctx.xhuff_index(d_c, dec, d_index, d_ioff, d_nseg)
+    walk_st, walk_len = st.cpu().tolist(), o_len.cpu().tolist()
+    ctx.xhuff_decompress_indexed(d_c, d_out, dec, d_index, d_ioff, d_nseg)
+    ctx.synchronize()
+    out = d_out.cpu().numpy()
+    got_st, got_len = st.cpu().tolist(), o_len.cpu().tolist()
+    for i, (c, cap) in enumerate(zip(comps, caps)):
+        rc, exp = oracle.decompress("xpress_huff", c, cap)
+        assert walk_st[i] == rc and got_st[i] == rc, (i, walk_st[i], got_st[i], rc)
+        if rc == 0:
+            assert walk_len[i] == got_len[i] == len(exp)
+            assert out[o_off[i]:o_off[i] + got_len[i]].tobytes() == exp, i
+    # valid streams never need the index-free decoder (the damaged ones that the walk rejects reach it through the trusted entry point)
+    nvalid = len(plains)
+    assert ctx.xhuff_second_chances() - before <= len(comps) - nvalid
+    # a wrong index: shift the byte cursor of one entry of every stream that has at least 3
+    idx = d_index.cpu().numpy().reshape(-1, 4).copy()
+    ioff, nseg = d_ioff.cpu().numpy(), d_nseg.cpu().numpy()
+    hit = 0
+    for i in range(nvalid):
+        if nseg[i] >= 3:
+            idx[ioff[i] + 2, 1] += 2
+            hit += 1
+    d_bad = torch.from_numpy(idx.reshape(-1)).to(ctx.device)
+    d_out.zero_()
+    before = ctx.xhuff_second_chances()
+    ctx.xhuff_decompress_indexed(d_c, d_out, dec, d_bad, d_ioff, d_nseg)
+    ctx.synchronize()
+    out = d_out.cpu().numpy()
+    got_st, got_len = st.cpu().tolist(), o_len.cpu().tolist()
+    for i in range(nvalid):
+        assert got_st[i] == 0 and out[o_off[i]:o_off[i] + got_len[i]].tobytes() == plains[i], i
+    assert ctx.xhuff_second_chances() - before >= hit
