@@ -23,10 +23,10 @@ MSCOMPAPI MSCompStatus ms_decompress(MSCompFormat format, const_bytes in, size_t
 /* Upper bound of ms_compress output for in_len input bytes; (size_t)-1 for an invalid format. */
 MSCOMPAPI size_t ms_max_compressed_size(MSCompFormat format, size_t in_len);
 
-/* Streaming dispatch (reference include/mscomp.h:114-213, src/mscomp.cpp:134-223): MSCOMP_NONE (copy) and MSCOMP_LZNT1.
- * Plain Xpress: upstream never finished xpress_deflate (its release build returns MSCOMP_MEM_ERROR from xpress_deflate_init,
- * src/xpress_compress.cpp:49-73) and its xpress_inflate is a byte-serial state machine with no parallel unit; both directions
- * return MSCOMP_ARG_ERROR here -- use the one-shot / batch calls.  Xpress-Huffman has no streaming API upstream either. */
+/* Streaming dispatch (reference include/mscomp.h:114-213, src/mscomp.cpp:134-223): MSCOMP_NONE (copy), MSCOMP_LZNT1 and
+ * MSCOMP_XPRESS -- the latter exactly as far as upstream goes: ms_inflate* work (xpress.h), ms_deflate_init answers
+ * MSCOMP_MEM_ERROR because upstream never finished xpress_deflate (src/xpress_compress.cpp:49-73).  Xpress-Huffman has no
+ * streaming API upstream (MSCOMP_ARG_ERROR, as for any other format number). */
 MSCOMPAPI MSCompStatus ms_deflate_init(MSCompFormat format, mscomp_stream* stream);
 MSCOMPAPI MSCompStatus ms_deflate(mscomp_stream* stream, MSCompFlush flush);
 MSCOMPAPI MSCompStatus ms_deflate_end(mscomp_stream* stream);

@@ -376,4 +376,59 @@ MSCompStatus lznt1_inflate_impl(mscomp_stream* s)
     return possible_end(s, st) ? MSCOMP_POSSIBLE_STREAM_END : MSCOMP_OK;
 }
 
+
+// ---- plain Xpress: xpress_inflate (src/xpress_decompress.cpp:45-61, :247-403) ----------------------------------------------------
+// The decoder state and the step that advances it live where the codec runs (kernels/xpress_stream.cuh); `Backend` says where
+// that is: the GPU (mscomp_stream.cu) or, for the CPU test-suite, host memory (tests/emu/stream_host.cpp).
+//   Backend::create() -> state handle or nullptr      Backend::destroy(handle)
+//   Backend::step(handle, in, in_len, out, out_cap, &in_used, &out_made, &status) -> MSCompStatus of the transport
+//   Backend::tail(handle, &flags, &flagged, &kept)     what xpress_inflate_end looks at
+template <class Backend> MSCompStatus xpress_inflate_init_impl(mscomp_stream* s)
+{
+    if (!s) return MSCOMP_ARG_ERROR;
+    init_stream(s, false, MSCOMP_XPRESS);
+    void* h = Backend::create();
+    if (!h) { set_error(s, "xpress_inflate_init: no memory for the decoder state"); return MSCOMP_MEM_ERROR; }
+    s->state = (mscomp_internal_state*)h;
+    return MSCOMP_OK;
+}
+template <class Backend> MSCompStatus xpress_inflate_impl(mscomp_stream* s)
+{
+    if (bad_stream(s, false, MSCOMP_XPRESS) || !s->state) { set_error(s, "xpress_inflate: not an open Xpress decompression stream"); return MSCOMP_ARG_ERROR; }
+    for (;;) {
+        // one step handles up to 1 GiB on either side; a larger call is a sequence of steps with the same outcome
+        const size_t kMax = (size_t)1 << 30;
+        const uint32_t n_in = (uint32_t)(s->in_avail < kMax ? s->in_avail : kMax), n_out = (uint32_t)(s->out_avail < kMax ? s->out_avail : kMax);
+        uint32_t used = 0, made = 0; int st = 0;
+        const MSCompStatus t = Backend::step(s->state, s->in, n_in, s->out, n_out, &used, &made, &st);
+        if (t != MSCOMP_OK) { set_error(s, "xpress_inflate: the device did not complete the step"); return t; }
+        adv_in(s, used); adv_out(s, made);
+        if (st < 0) { set_error(s, "xpress_inflate: the data is not a valid Xpress stream"); return (MSCompStatus)st; }
+        const bool clipped = (n_in == kMax && s->in_avail) || (n_out == kMax && s->out_avail);
+        if (!clipped || (used == 0 && made == 0)) return (MSCompStatus)st;
+    }
+}
+template <class Backend> MSCompStatus xpress_inflate_end_impl(mscomp_stream* s)
+{
+    if (bad_stream(s, false, MSCOMP_XPRESS) || !s->state) { set_error(s, "xpress_inflate_end: not an open Xpress decompression stream"); return MSCOMP_ARG_ERROR; }
+    uint32_t flags = 0, flagged = 0, kept = 0;
+    Backend::tail(s->state, &flags, &flagged, &kept);
+    MSCompStatus st = MSCOMP_OK;
+    const uint32_t inv = ~flags;
+    const bool ones_on_top = ((inv + 1u) & inv) == 0;
+    if (s->in_avail || kept || !flagged || !ones_on_top) { set_error(s, "xpress_inflate_end: the stream has not reached a possible end"); st = MSCOMP_DATA_ERROR; }   // :394
+    Backend::destroy(s->state);
+    s->state = nullptr;
+    return st;
+}
+// xpress_deflate*: upstream never finished them -- the release build answers MSCOMP_MEM_ERROR from init, MSCOMP_ARG_ERROR from
+// deflate, and deflate_end only checks its argument (src/xpress_compress.cpp:50-74, :75-221, :223-236).  Same answers here.
+inline MSCompStatus xpress_deflate_init_impl(mscomp_stream*) { return MSCOMP_MEM_ERROR; }
+inline MSCompStatus xpress_deflate_impl(mscomp_stream*, MSCompFlush) { return MSCOMP_ARG_ERROR; }
+inline MSCompStatus xpress_deflate_end_impl(mscomp_stream* s)
+{
+    if (bad_stream(s, true, MSCOMP_XPRESS) || !s->state) { set_error(s, "xpress_deflate_end: not an open Xpress compression stream"); return MSCOMP_ARG_ERROR; }
+    return MSCOMP_OK;
+}
+
 } // namespace msc_stream

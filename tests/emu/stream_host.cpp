@@ -3,6 +3,9 @@
 // very same host logic against the compiled reference, call by call.  Never part of the product library.
 #include "../../ms-compress_b200/csrc/stream_logic.h"
 #include "../../ms-compress_b200/csrc/lznt1_host.h"
+#define MSC_HOST_ONLY 1
+#include "../../ms-compress_b200/csrc/kernels/xpress_stream.cuh"
+#include <new>
 extern "C" {
 #include "../../oracle/oracle.h"
 }
@@ -50,7 +53,39 @@ struct OracleCodec {
 };
 } // namespace
 
+namespace {
+// the product's xpress_inflate host logic over the same step function, running in host memory
+struct HostXpressStream {
+    static void* create() { msc::XpStreamState* s = new (std::nothrow) msc::XpStreamState; if (s) msc::xps_init(s); return s; }
+    static void destroy(void* h) { delete (msc::XpStreamState*)h; }
+    static MSCompStatus step(void* h, const uint8_t* in, uint32_t n_in, uint8_t* out, uint32_t n_out, uint32_t* used, uint32_t* made, int* status)
+    {
+        msc::XpStreamResult r{0, 0, 0, 0};
+        msc::xps_step((msc::XpStreamState*)h, in, n_in, out, n_out, &r);
+        *used = r.in_used; *made = r.out_made; *status = r.status;
+        return MSCOMP_OK;
+    }
+    static void tail(void* h, uint32_t* flags, uint32_t* flagged, uint32_t* kept)
+    { const msc::XpStreamState* s = (const msc::XpStreamState*)h; *flags = s->flags; *flagged = s->flagged; *kept = s->stash_n; }
+};
+} // namespace
+
 extern "C" {
+MSCompStatus hs_xpress_inflate_init(mscomp_stream* s) { return xpress_inflate_init_impl<HostXpressStream>(s); }
+// the same with the reference's bookkeeping slip reproduced (differential runs against the compiled reference)
+MSCompStatus hs_xpressq_inflate_init(mscomp_stream* s)
+{
+    const MSCompStatus st = xpress_inflate_init_impl<HostXpressStream>(s);
+    if (st == MSCOMP_OK) ((msc::XpStreamState*)s->state)->upstream_quirk = 1;
+    return st;
+}
+MSCompStatus hs_xpressq_inflate(mscomp_stream* s) { return xpress_inflate_impl<HostXpressStream>(s); }
+MSCompStatus hs_xpressq_inflate_end(mscomp_stream* s) { return xpress_inflate_end_impl<HostXpressStream>(s); }
+MSCompStatus hs_xpress_inflate(mscomp_stream* s) { return xpress_inflate_impl<HostXpressStream>(s); }
+MSCompStatus hs_xpress_inflate_end(mscomp_stream* s) { return xpress_inflate_end_impl<HostXpressStream>(s); }
+MSCompStatus hs_xpress_deflate_init(mscomp_stream* s) { return xpress_deflate_init_impl(s); }
+MSCompStatus hs_xpress_deflate(mscomp_stream* s, MSCompFlush f) { return xpress_deflate_impl(s, f); }
+MSCompStatus hs_xpress_deflate_end(mscomp_stream* s) { return xpress_deflate_end_impl(s); }
 MSCompStatus hs_lznt1_deflate_init(mscomp_stream* s) { return lznt1_deflate_init_impl(s); }
 MSCompStatus hs_lznt1_deflate(mscomp_stream* s, MSCompFlush flush) { return lznt1_deflate_impl<OracleCodec>(s, flush); }
 MSCompStatus hs_lznt1_deflate_end(mscomp_stream* s) { return lznt1_deflate_end_impl(s); }

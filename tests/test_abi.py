@@ -16,6 +16,38 @@ def declared_symbols():
     return names
 
 
+# The reference's exported C symbols (`nm -D` of the reference build): the drop-in boundary, 30 names.
+REFERENCE_SYMBOLS = (
+    ["ms_compress", "ms_decompress", "ms_max_compressed_size"]
+    + ["ms_%s%s" % (d, s) for d in ("deflate", "inflate") for s in ("_init", "", "_end")]
+    + ["lznt1_compress", "lznt1_decompress", "lznt1_max_compressed_size"]
+    + ["lznt1_%s%s" % (d, s) for d in ("deflate", "inflate") for s in ("_init", "", "_end")]
+    + ["xpress_compress", "xpress_decompress", "xpress_max_compressed_size"]
+    + ["xpress_%s%s" % (d, s) for d in ("deflate", "inflate") for s in ("_init", "", "_end")]
+    + ["xpress_huff_compress", "xpress_huff_decompress", "xpress_huff_max_compressed_size"]
+)
+
+
+def _exported(path):
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True, check=True).stdout
+    return {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
+
+
+def test_library_exports_the_reference_boundary(ms):
+    """`nm -D` of our library is a superset of the reference's 30 C symbols -- the list is fixed here, not derived from our headers."""
+    assert len(REFERENCE_SYMBOLS) == 30 and len(set(REFERENCE_SYMBOLS)) == 30
+    ours = _exported(ms.LIB_PATH)
+    missing = sorted(set(REFERENCE_SYMBOLS) - ours)
+    assert not missing, missing
+    assert set(REFERENCE_SYMBOLS) <= declared_symbols()             # and every one of them is declared in include/*.h
+    ref = os.path.join(ROOT, "oracle", "_ref", "libMSCompression.so")
+    if os.path.exists(ref):                                          # the compiled reference, where it was built
+        ref_c = {n for n in _exported(ref) if not n.startswith("_Z")}
+        assert ref_c == set(REFERENCE_SYMBOLS), sorted(ref_c ^ set(REFERENCE_SYMBOLS))
+        assert not (ref_c - ours)
+
+
 def test_library_exports_declared_symbols(ms):
     lib = ctypes.CDLL(ms.LIB_PATH)
     names = declared_symbols()

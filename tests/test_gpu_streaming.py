@@ -59,9 +59,66 @@ def test_copy_streams_and_unsupported_formats(ms, reflib):
     data = ms.generate("text", 30000, 1)
     for deflate in (True, False):
         out, rc = drive(ms, reflib, "ms_", 0, deflate, data, rnd, 4000, 3000, False) if deflate else (None, None)
-    # formats without a stream implementation here: an error from init, never a crash
-    s = Stream()
-    for fmt in (1, 3, 4, 5, 77):
-        f = ms.lib().ms_deflate_init; f.restype = ctypes.c_int
-        g = ms.lib().ms_inflate_init; g.restype = ctypes.c_int
-        assert f(ctypes.c_int(fmt), ctypes.byref(s)) < 0 and g(ctypes.c_int(fmt), ctypes.byref(s)) < 0
+    # formats without a stream implementation: the reference's answers (src/mscomp.cpp:134-223, src/xpress_compress.cpp:50-74)
+    for lib in (ms.lib(), reflib.lib):
+        for fmt in (1, 3, 4, 5, 77):
+            s = Stream()
+            f = lib.ms_deflate_init; f.restype = ctypes.c_int
+            g = lib.ms_inflate_init; g.restype = ctypes.c_int
+            assert f(ctypes.c_int(fmt), ctypes.byref(s)) == (-4 if fmt == 3 else -2)
+            rc = g(ctypes.c_int(fmt), ctypes.byref(s))
+            assert rc == (0 if fmt == 3 else -2)
+            if rc == 0:
+                e = lib.ms_inflate_end; e.restype = ctypes.c_int
+                assert e(ctypes.byref(s)) == 0
+
+
+@pytest.mark.parametrize("prefix", ["xpress_", "ms_"])
+def test_xpress_inflate_matches_reference_call_by_call(ms, reflib, oracle, prefix, monkeypatch):
+    """xpress_inflate on the GPU (one thread walks the stream; state in device memory) against the compiled reference.  The
+    reference mis-counts a match that is owed over three or more calls and can read a clobbered length nibble
+    (src/xpress_decompress.cpp:261-263, :398-402 with :88-92); MSCOMP_XPRESS_INFLATE_UPSTREAM_QUIRK makes the library reproduce both
+    slips so that every schedule can be compared call by call -- the default build keeps the right bytes (checked below)."""
+    import subprocess, sys, os, textwrap
+    rnd = random.Random(11)
+    streams = [(oracle.compress("xpress", ms.generate(kind, n, 9 + n % 7)), ms.generate(kind, n, 9 + n % 7))
+               for kind, n in (("text", 120000), ("random", 20000), ("text", 4096), ("text", 3))]
+    # right bytes without the hook, any schedule (this process)
+    for comp, plain in streams + [(oracle.compress("xpress", ms.generate("runs", 90000, 4)), ms.generate("runs", 90000, 4))]:
+        for max_piece, max_cap in ((70000, 90000), (5000, 3000), (300, 700)):
+            d = Driver(ms.lib(), prefix, False, 3 if prefix == "ms_" else None)
+            pos = 0
+            for _ in range(100000):
+                piece = comp[pos:pos + rnd.randint(0, max_piece)]; pos += len(piece)
+                r = d.call(piece, rnd.choice((0, 1, 2, 3, rnd.randint(0, max_cap), max_cap)), 0)
+                assert r[0] >= 0
+                if pos >= len(comp) and not d.pending and len(d.out) >= len(plain):
+                    break
+            assert bytes(d.out) == plain and d.finish() == 0
+    # call-by-call against the reference, hook on (a child process: the hook is read once per process)
+    child = textwrap.dedent("""
+        import sys, random
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        import mscompress_b200 as ms
+        import os
+        from conftest import CodecLib, ROOT
+        from stream_util import Driver, drive_pair
+        ref = CodecLib(os.path.join(ROOT, "oracle", "_ref", "libMSCompression.so"), "")
+        orc = CodecLib(os.path.join(ROOT, "oracle", "liboracle.so"), "orc_")
+        rnd = random.Random(12)
+        prefix = %r
+        fmt = 3 if prefix == "ms_" else None
+        for kind, n in (("text", 120000), ("random", 20000), ("text", 4096), ("text", 3)):
+            plain = ms.generate(kind, n, 9 + n %% 7)
+            comp = orc.compress("xpress", plain)
+            bad = bytearray(comp); bad[len(bad) // 2] ^= 0x08
+            for v in (comp, comp + b"\0\0", comp[:-3], comp[:len(comp) // 2], bytes(bad)):
+                for max_piece, max_cap in ((70000, 90000), (5000, 3000), (300, 5000), (20000, 100)):
+                    if len(v) > 20000 and max_piece < 1000:
+                        continue
+                    drive_pair(Driver(ms.lib(), prefix, False, fmt), Driver(ref.lib, prefix, False, fmt), False, v, rnd, max_piece, max_cap, False)
+        print("xpress inflate differential ok")
+    """ % (os.path.dirname(os.path.abspath(__file__)), os.path.dirname(os.path.dirname(os.path.abspath(__file__))), prefix))
+    env = dict(os.environ, MSCOMP_XPRESS_INFLATE_UPSTREAM_QUIRK="1")
+    r = subprocess.run([sys.executable, "-c", child], capture_output=True, text=True, env=env, timeout=1500)
+    assert r.returncode == 0 and "differential ok" in r.stdout, (r.stdout + r.stderr)[-3000:]

@@ -114,3 +114,63 @@ def test_one_shot_decompress_host_logic(host, reflib, oracle, ms):
             assert ours(src, cap) == reflib.call("lznt1_decompress", src, cap), (len(src), cap)
             checked += 1
     assert checked > 500
+
+
+def test_xpress_inflate_state_machine(host, reflib, oracle, ms):
+    """xpress_inflate (kernels/xpress_stream.cuh + the host logic of stream_logic.h) against the compiled reference, call by call:
+    whole streams, streams with trailing bytes, truncated and damaged streams; pieces down to one byte, output room down to zero."""
+    rnd = random.Random(8)
+    streams = [(oracle.compress("xpress", ms.generate(kind, n, 9 + n % 7)), ms.generate(kind, n, 9 + n % 7))
+               for kind, n in (("text", 150000), ("random", 20000), ("runs", 100000), ("text", 4096), ("text", 3), ("runs", 9000))]
+    streams.append((oracle.compress("xpress", b"ab" * 50000), b"ab" * 50000))           # long lengths: u16 extensions
+    streams.append((oracle.compress("xpress", bytes(700000)), bytes(700000)))           # u32 length extension
+    for si, (comp, plain) in enumerate(streams):
+        variants = [comp, comp + b"\0\0", comp[:-3], comp[:len(comp) // 2], comp + b"\xff\xff\xff\xff", comp + b"\x07"]
+        if len(comp) > 100:
+            for _ in range(3):
+                bad = bytearray(comp); bad[rnd.randrange(len(bad))] ^= 1 << rnd.randrange(8)
+                variants.append(bytes(bad))
+        short_matches = si in (0, 3, 4)             # text: with the slip reproduced, a match longer than every later output room never ends
+        for v in variants:
+            for max_piece, max_cap in ((70000, 90000), (5000, 3000), (300, 5000), (20000, 100), (7, 50), (1, 4096)):
+                if max_piece <= 7 and len(v) > 6000:
+                    continue
+                if not short_matches:
+                    # long matches: only calls with room for everything can be compared with the reference (see above)
+                    a, b = Driver(host, "hs_xpressq_", False), Driver(reflib.lib, "xpress_", False)
+                    pos = 0
+                    while True:
+                        piece = v[pos:pos + rnd.randint(0, max_piece)]; pos += len(piece)
+                        ra, rb = a.call(piece, len(plain) + 64, 0), b.call(piece, len(plain) + 64, 0)
+                        assert ra == rb
+                        if ra[0] < 0 or (pos >= len(v) and not piece):
+                            break
+                    assert bytes(a.out) == bytes(b.out) and a.finish() == b.finish()
+                    if max_cap < 2000:
+                        continue
+                    out, rc = bytes(a.out), ra[0]
+                else:
+                    out, rc = drive_pair(Driver(host, "hs_xpressq_", False), Driver(reflib.lib, "xpress_", False), False, v, rnd, max_piece, max_cap, False)
+                # (hs_xpressq_: with the reference's slip in the owed-match bookkeeping reproduced -- src/xpress_decompress.cpp:261-263 --
+                # so that schedules where a match is owed over three or more calls can be compared too; there the reference's
+                # OUTPUT is wrong, which the second run below, without the slip, shows by getting the right bytes)
+                if v is comp:
+                    assert rc >= 0
+                    d = Driver(host, "hs_xpress_", False)
+                    pos = 0
+                    for _ in range(200000):
+                        piece = v[pos:pos + rnd.randint(0, max_piece)]; pos += len(piece)
+                        r = d.call(piece, rnd.choice((0, 1, 2, 3, rnd.randint(0, max_cap), max_cap)), 0)
+                        assert r[0] >= 0
+                        if pos >= len(v) and not d.pending and len(d.out) >= len(plain):
+                            break
+                    assert bytes(d.out) == plain
+
+
+def test_xpress_deflate_is_as_unfinished_as_upstream(host, reflib):
+    for lib, stem in ((host, "hs_xpress_"), (reflib.lib, "xpress_")):
+        s = Stream()
+        f = getattr(lib, stem + "deflate_init"); f.restype = ctypes.c_int
+        g = getattr(lib, stem + "deflate"); g.restype = ctypes.c_int
+        h = getattr(lib, stem + "deflate_end"); h.restype = ctypes.c_int
+        assert f(ctypes.byref(s)) == -4 and g(ctypes.byref(s), ctypes.c_int(0)) == -2 and h(ctypes.byref(s)) == -2
