@@ -51,51 +51,100 @@ def _cpu_lib():
     return os.path.join(ROOT, "oracle", "liboracle.so"), "orc_", "port"
 
 
-def _cpu_worker(args):
-    path, prefix, fmt, seed0, nblocks, reps = args
+def host_cores():
+    """Host threads this process may really use: the scheduler affinity mask, clipped by the cgroup CPU quota if there is one."""
+    aff = len(os.sched_getaffinity(0))
+    quota = None
+    for path in ("/sys/fs/cgroup/cpu.max",):
+        try:
+            q, per = open(path).read().split()[:2]
+            if q != "max":
+                quota = float(q) / float(per)
+        except Exception:
+            pass
+    if quota is None:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            pass
+    usable = aff if quota is None else max(1, min(aff, int(quota + 0.5)))
+    return usable, aff, quota
+
+
+CPU_UNIT = {"lznt1": BLOCK, "xpress": BLOCK, "xpress_huff": 65536}       # bytes per call: what the GPU arm's batch unit is
+
+
+def _cpu_proc(path, prefix, fmt, seed0, nunits, reps, barrier, queue):
+    """One worker: generate its units, warm up, wait for everybody, then time compress+decompress of every unit."""
     import mscompress_b200 as ms
     lib = ctypes.CDLL(path)
     comp_f, dec_f = getattr(lib, prefix + fmt + "_compress"), getattr(lib, prefix + fmt + "_decompress")
-    blocks = [ms.generate("text", BLOCK, seed0 + i) for i in range(nblocks)]
-    cap = BLOCK + BLOCK // 8 + 4096
-    cbuf, dbuf = ctypes.create_string_buffer(cap), ctypes.create_string_buffer(BLOCK)
+    unit = CPU_UNIT[fmt]
+    blocks = [ms.generate("text", unit, seed0 + i) for i in range(nunits)]
+    cap = unit + unit // 8 + 4096
+    cbuf, dbuf = ctypes.create_string_buffer(cap), ctypes.create_string_buffer(unit)
+    n = ctypes.c_size_t(cap)
+    comp_f(blocks[0], ctypes.c_size_t(unit), cbuf, ctypes.byref(n))              # warm (code + buffers paged in)
     t_c = t_d = 0.0
     csize = 0
+    barrier.wait()
+    t_begin = time.perf_counter()                                                # CLOCK_MONOTONIC: comparable across processes
     for _ in range(reps):
         for b in blocks:
             n = ctypes.c_size_t(cap)
             t0 = time.perf_counter()
-            rc = comp_f(b, ctypes.c_size_t(BLOCK), cbuf, ctypes.byref(n))
+            rc = comp_f(b, ctypes.c_size_t(unit), cbuf, ctypes.byref(n))
             t1 = time.perf_counter()
-            m = ctypes.c_size_t(BLOCK)
+            m = ctypes.c_size_t(unit)
             rc2 = dec_f(cbuf, n, dbuf, ctypes.byref(m))
             t2 = time.perf_counter()
-            assert rc == 0 and rc2 == 0 and m.value == BLOCK
+            assert rc == 0 and rc2 == 0 and m.value == unit
             t_c += t1 - t0
             t_d += t2 - t1
             csize += n.value
-    return nblocks * reps * BLOCK, t_c, t_d, csize
+    queue.put((nunits * reps * unit, t_c, t_d, csize, t_begin, time.perf_counter()))
 
 
-def cpu_measure(fmt="lznt1", blocks_per_proc=8, reps=1, procs=None):
-    """Aggregate MB/s of compress+decompress of 1 MiB text blocks over `procs` worker processes."""
+def cpu_measure(fmt="lznt1", bytes_per_proc=8 * BLOCK, reps=1, procs=None):
+    """Aggregate MB/s of compress+decompress of text units (1 MiB; 64 KiB for Xpress-Huffman) over `procs` worker processes.
+    Data generation and warm-up happen before a barrier; the wall clock runs from the first worker's start to the last one's end."""
     import multiprocessing as mp
     path, prefix, kind = _cpu_lib()
-    procs = procs or (os.cpu_count() or 1)
+    usable, aff, quota = host_cores()
+    procs = procs or usable
+    nunits = max(1, bytes_per_proc // CPU_UNIT[fmt])
     ctx = mp.get_context("fork")
-    with ctx.Pool(procs) as pool:
-        pool.map(_cpu_worker, [(path, prefix, fmt, 7, 1, 1)] * procs)                 # warm the workers
-        t0 = time.perf_counter()
-        res = pool.map(_cpu_worker, [(path, prefix, fmt, 42 + p * blocks_per_proc, blocks_per_proc, reps) for p in range(procs)])
-        wall = time.perf_counter() - t0
+    barrier, queue = ctx.Barrier(procs), ctx.Queue()
+    ps = [ctx.Process(target=_cpu_proc, args=(path, prefix, fmt, 42 + p * nunits, nunits, reps, barrier, queue)) for p in range(procs)]
+    for p in ps:
+        p.start()
+    res = [queue.get(timeout=600) for _ in ps]
+    for p in ps:
+        p.join()
+    wall = max(r[5] for r in res) - min(r[4] for r in res)
     total = sum(r[0] for r in res)
     tc, td = sum(r[1] for r in res), sum(r[2] for r in res)
     return {
         "value": total / MB / wall, "unit": "MB/s", "cores": procs, "kind": kind,
-        "sample": "%d processes x %d x 1 MiB text blocks, %s compress+decompress via %s" % (procs, blocks_per_proc * reps, fmt, os.path.basename(path)),
-        "compress_MBps_per_core": total / MB / tc * 1.0, "decompress_MBps_per_core": total / MB / td * 1.0,
+        "sample": "%d processes x %d x %d KiB text units, %s compress+decompress via %s (generation and warm-up outside the timed wall)"
+                  % (procs, nunits * reps, CPU_UNIT[fmt] // 1024, fmt, os.path.basename(path)),
+        "compress_MBps_per_core": total / MB / tc, "decompress_MBps_per_core": total / MB / td,
         "ratio": sum(r[3] for r in res) / total, "wall_s": wall,
+        "host": {"affinity_cpus": aff, "cgroup_cpu_quota": quota, "os_cpu_count": os.cpu_count()},
     }
+
+
+def cpu_baseline_block(fmt, bytes_per_proc):
+    """All-core and one-core figures of one format, in the shape the JSON line carries."""
+    full = cpu_measure(fmt, bytes_per_proc)
+    one = cpu_measure(fmt, bytes_per_proc, procs=1)
+    return {"value": full["value"], "unit": "MB/s", "cores": full["cores"], "kind": full["kind"], "sample": full["sample"],
+            "compress_MBps_per_core_loaded": full["compress_MBps_per_core"], "decompress_MBps_per_core_loaded": full["decompress_MBps_per_core"],
+            "one_core": {"value": one["value"], "compress_MBps": one["compress_MBps_per_core"], "decompress_MBps": one["decompress_MBps_per_core"]},
+            "ratio": full["ratio"], "host": full["host"]}
 
 
 def run_reference(args):
@@ -105,14 +154,16 @@ def run_reference(args):
     vals = []
     meas = None
     for i in range(args.warmup + args.steps):
-        meas = cpu_measure("lznt1", blocks_per_proc=16, reps=1)
+        meas = cpu_measure("lznt1", bytes_per_proc=16 * BLOCK, reps=1)
         if i >= args.warmup:
             vals.append(meas["value"])
     v = statistics.mean(vals)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "MB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * meas["wall_s"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "LZNT1 encode+decode, 1 GiB synthetic text stream as 4 KiB chunks (BASELINE.json configs[1]); CPU arm: bounded sample per step"},
+        "config": {"workload": "LZNT1 encode+decode, 1 GiB synthetic text stream as 4 KiB chunks (BASELINE.json configs[1]); CPU arm: every step times a "
+                               "bounded SAMPLE of that stream (16 MiB per host thread, same generator and seeds, one lznt1_compress + lznt1_decompress call per MiB)",
+                   "host": meas["host"]},
         "cpu_baseline": {"value": v, "unit": "MB/s", "cores": meas["cores"], "kind": meas["kind"], "sample": meas["sample"]},
         "e2e": {"value": v, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -160,8 +211,44 @@ class Clocks:
 # ------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------------------
+AFFINITY0 = os.sched_getaffinity(0)
 
-def measure_batch_format(ms, ctx, torch, fmt, each, count, steps, dev, peak, rank):
+
+def _cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if part:
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(torch, index):
+    """Pin this rank (and so its pinned host buffers, by first touch) to the NUMA node the GPU hangs off.  The e2e path moves
+    3.4 GB per step per rank through host memory; with 8 ranks on a two-socket box unbound buffers cross the socket link."""
+    try:
+        bus = torch.cuda.get_device_properties(index).pci_bus_id
+        dom = torch.cuda.get_device_properties(index).pci_domain_id
+        dev = torch.cuda.get_device_properties(index).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev)
+        node = int(open(path).read())
+        if node < 0:
+            return {"node": None, "why": "numa_node = -1 (single node or virtualised)"}
+        cpus = _cpulist(open("/sys/devices/system/node/node%d/cpulist" % node).read()) & AFFINITY0
+        if not cpus:
+            return {"node": node, "why": "no allowed cpu on that node"}
+        os.sched_setaffinity(0, cpus)
+        try:                                                 # memory policy: prefer the node as well (libnuma, if the box has it)
+            numa = ctypes.CDLL("libnuma.so.1")
+            if numa.numa_available() >= 0:
+                numa.numa_set_preferred(node)
+        except OSError:
+            pass
+        return {"node": node, "cpus": len(cpus)}
+    except Exception as e:                                   # no sysfs entry: stay unbound
+        return {"node": None, "why": "%s: %s" % (type(e).__name__, e)}
+
+def measure_batch_format(ms, ctx, torch, fmt, each, count, steps, dev, peak, rank, dist=None, world=1):
     """Encode+decode of `count` independent buffers of `each` bytes (generator text, seeds 42+rank*count+i) through the
     device batch API; returns a dict with MB/s, kernel times and roofline fractions."""
     import numpy as np
@@ -226,12 +313,16 @@ def measure_batch_format(ms, ctx, torch, fmt, each, count, steps, dev, peak, ran
     ctx.profile(False)
     enc_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in evs)
     dec_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in evs)
-    kern = {}
-    for name, (calls, ms_tot) in prof.items():
-        per = ms_tot / max(calls, 1)
-        kern[name] = {"ms_per_launch": per, "achieved_GBps": (U + C) / 1e9 / (per / 1e3), "frac": (U + C) / 1e9 / (per / 1e3) / peak}
+    if dist is not None:                                      # sharded: every rank its own `count` buffers; time = max over ranks
+        t = torch.tensor([enc_ms, dec_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        enc_ms, dec_ms = t.tolist()
+    # one roofline figure per direction: algorithmic bytes of the whole batch (U + C) over the time of ALL kernels of that direction
+    kern = {name: {"calls_per_step": calls / steps, "ms_per_launch": ms_tot / max(calls, 1)} for name, (calls, ms_tot) in prof.items()}
+    roof = {d: {"ms": t_ms, "achieved_GBps": (U + C) / 1e9 / (t_ms / 1e3), "frac": (U + C) / 1e9 / (t_ms / 1e3) / peak, "algorithmic_bytes": U + C}
+            for d, t_ms in (("encode", enc_ms), ("decode", dec_ms))}
     extra = {}
-    if indexed:
+    if indexed and world == 1:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         d_out.zero_()
         e0.record()
@@ -242,9 +333,10 @@ def measure_batch_format(ms, ctx, torch, fmt, each, count, steps, dev, peak, ran
         extra = {"decode_ms_unindexed": e0.elapsed_time(e1), "index": "side-band restart index, one entry per %d input bytes (%d per buffer)" % (seg_bytes, stride)}
     del d_in, d_comp, d_out
     torch.cuda.empty_cache()
-    return {"workload": "%d independent buffers x %d bytes (text), device batch API" % (count, each), "uncompressed_bytes": U, "compressed_ratio": C / U,
-            **extra, "encode_ms": enc_ms, "decode_ms": dec_ms, "encode_MBps": U / MB / (enc_ms / 1e3), "decode_MBps": U / MB / (dec_ms / 1e3),
-            "encode_decode_MBps": U / MB / ((enc_ms + dec_ms) / 1e3), "gpu_launches": ctx.launches() - l0, "kernels": kern}
+    return {"workload": "%d independent buffers x %d bytes (text) per GPU, device batch API, %d GPU(s)" % (count, each, world),
+            "uncompressed_bytes_per_gpu": U, "compressed_ratio": C / U,
+            **extra, "encode_ms": enc_ms, "decode_ms": dec_ms, "encode_MBps": world * U / MB / (enc_ms / 1e3), "decode_MBps": world * U / MB / (dec_ms / 1e3),
+            "encode_decode_MBps": world * U / MB / ((enc_ms + dec_ms) / 1e3), "gpu_launches": ctx.launches() - l0, "roofline": roof, "kernels": kern}
 
 
 def measure_mixed(ms, ctx, torch, dist, dev, rank, world, count, each, steps):
@@ -377,6 +469,7 @@ def run_gpu(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- this framework has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(torch, local)              # before any pinned allocation: first touch lands on the GPU's node
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -450,7 +543,7 @@ def run_gpu(args):
     h_comp = torch.empty(U + 2 * nchunks + 64, dtype=torch.uint8).pin_memory()
     h_out = torch.empty(U, dtype=torch.uint8).pin_memory()
     L = ms.lib()
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(1, args.steps)
     e2e_t = []
     csz = 0
     for k in range(1 + e2e_steps):
@@ -474,15 +567,17 @@ def run_gpu(args):
 
     peak, peak_src = peaks()
     formats = {}
-    if args.formats != "none" and world == 1:
+    if args.formats != "none":
         del d_comp, d_out, h_comp, h_out
         torch.cuda.empty_cache()
-        if hasattr(ms.lib(), "mscomp_gpu_xpress_huff_compress_batch"):
-            gib = args.xhuff_gib
-            formats["xpress_huff"] = measure_batch_format(ms, ctx, torch, "xpress_huff", 65536, gib * 16384, 2, dev, peak, rank)
-            formats["xpress_huff"]["config"] = "BASELINE.json configs[3]: %d GiB synthetic text as independent 64 KiB buffers" % gib
-            formats["xpress"] = measure_batch_format(ms, ctx, torch, "xpress", BLOCK, args.mib, 2, dev, peak, rank)
-            formats["xpress"]["config"] = "BASELINE.json configs[2]: %d MiB synthetic text as %d independent 1 MiB buffers (one stream each)" % (args.mib, args.mib)
+        gib = args.xhuff_gib
+        fsteps = max(2, min(args.steps, 5))
+        formats["xpress_huff"] = measure_batch_format(ms, ctx, torch, "xpress_huff", 65536, gib * 16384, fsteps, dev, peak, rank, dist, world)
+        formats["xpress_huff"]["config"] = ("BASELINE.json configs[3]: %d GiB synthetic text per GPU as independent 64 KiB buffers, "
+                                            "chunk-sharded over %d GPU(s) (weak scaling)" % (gib, world))
+        formats["xpress"] = measure_batch_format(ms, ctx, torch, "xpress", BLOCK, args.mib, fsteps, dev, peak, rank, dist, world)
+        formats["xpress"]["config"] = ("BASELINE.json configs[2]: %d MiB synthetic text per GPU as %d independent 1 MiB buffers (one stream each), "
+                                       "%d GPU(s)" % (args.mib, args.mib, world))
 
     mixed = None
     if args.formats != "none" and hasattr(ms.lib(), "mscomp_gpu_xpress_compress_batch_indexed"):
@@ -517,7 +612,12 @@ def run_gpu(args):
     roofline = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["achieved_GBps"], "peak": peak, "unit": "GB/s", "frac": kern[dom]["frac"],
                 "traffic": traffic.get(dom), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg[dom], "note": "achieved = (uncompressed + compressed bytes) / CUDA-event kernel time (SURVEY.md 8d)"}
-    cpu = cpu_measure("lznt1", blocks_per_proc=8, reps=1) if world == 1 else None
+    cpu = cpu_fmt = None
+    if world == 1:
+        os.sched_setaffinity(0, AFFINITY0)                   # the CPU arm gets every host thread back (the GPU arm was bound to one NUMA node)
+        cpu = cpu_baseline_block("lznt1", 8 * BLOCK)
+        if formats:
+            cpu_fmt = {"xpress": cpu_baseline_block("xpress", 16 * BLOCK), "xpress_huff": cpu_baseline_block("xpress_huff", 8 * BLOCK)}
 
     line = {
         "metric": METRIC, "value": value, "unit": "MB/s", "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
@@ -532,7 +632,8 @@ def run_gpu(args):
         "decode_roofline": {"kernel": dec_name, "bound": "hbm", "achieved": kern.get(dec_name, {}).get("achieved_GBps"), "peak": peak, "unit": "GB/s",
                             "frac": kern.get(dec_name, {}).get("frac"), "target_frac": 0.40},
         "e2e": {"value": world * U / MB / e2e_s, "unit": "MB/s", "h2d_bytes_per_step": U + C, "d2h_bytes_per_step": C + U,
-                "api": "lznt1_compress + lznt1_decompress (C ABI, pinned host buffers)", "ms_per_step": 1e3 * e2e_s},
+                "api": "lznt1_compress + lznt1_decompress (C ABI, pinned host buffers)", "ms_per_step": 1e3 * e2e_s, "steps": e2e_steps,
+                "numa": numa},
         "clocks": clk.summary(),
         "formats": formats,
     }
@@ -540,7 +641,11 @@ def run_gpu(args):
         line["mixed_batch"] = mixed
     if cpu:
         line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        line["cpu_baseline_detail"] = {k: cpu[k] for k in ("compress_MBps_per_core", "decompress_MBps_per_core", "ratio")}
+        line["cpu_baseline_detail"] = {k: v for k, v in cpu.items() if k not in line["cpu_baseline"]}
+    if cpu_fmt:
+        for f, c in cpu_fmt.items():
+            line["formats"][f]["cpu_baseline"] = c
+            line["formats"][f]["vs_cpu_all_cores"] = line["formats"][f]["encode_decode_MBps"] / c["value"]
     emit(line)
     if dist is not None:
         dist.destroy_process_group()

@@ -112,7 +112,7 @@ def test_xpress_inflate_matches_reference_call_by_call(ms, reflib, oracle, prefi
             plain = ms.generate(kind, n, 9 + n %% 7)
             comp = orc.compress("xpress", plain)
             bad = bytearray(comp); bad[len(bad) // 2] ^= 0x08
-            for v in (comp, comp + b"\0\0", comp[:-3], comp[:len(comp) // 2], bytes(bad)):
+            for v in (comp, comp + bytes(2), comp[:-3], comp[:len(comp) // 2], bytes(bad)):
                 for max_piece, max_cap in ((70000, 90000), (5000, 3000), (300, 5000), (20000, 100)):
                     if len(v) > 20000 and max_piece < 1000:
                         continue
