@@ -118,14 +118,41 @@ def _as_cbuf(data):
     return ctypes.addressof(buf), mv.nbytes, buf
 
 
-class OpenSrc:
-    """One-shot codec object: same shape as the reference harness' `OpenSrc` (test/compressors.py:214-314)."""
+class MSCompStream(ctypes.Structure):
+    """mscomp_stream (include/mscomp/general.h; reference test/compressors.py:216-221)."""
+    _fields_ = [("format", ctypes.c_int), ("compressing", ctypes.c_bool),
+                ("in_", ctypes.c_void_p), ("in_avail", ctypes.c_size_t), ("in_total", ctypes.c_size_t),
+                ("out", ctypes.c_void_p), ("out_avail", ctypes.c_size_t), ("out_total", ctypes.c_size_t),
+                ("error", ctypes.c_char * 256), ("warning", ctypes.c_char * 256), ("state", ctypes.c_void_p)]
 
-    def __init__(self, format):
+
+class OpenSrc:
+    """Codec object of the same shape as the reference harness' `OpenSrc` (test/compressors.py:214-314): one-shot
+    `Compress` / `Decompress` / `MaxCompressedSize` and the streaming members `CompressStream` / `DecompressStream`
+    (a StreamableCompressor upstream, :224-229, :258-309).  `library` is a loaded libMSCompression (ctypes); the default is this
+    package's GPU library -- the acceptance harness (tests/acceptance/) passes the compiled reference to get a second engine."""
+
+    NO_FLUSH, FLUSH, FINISH = 0, 2, 4
+
+    def __init__(self, format, library=None):
         self.format = int(format)
+        self._library = library
+
+    def _L(self):
+        return self._library if self._library is not None else lib()
+
+    def _call(self, name, *args):
+        f = getattr(self._L(), name)
+        f.restype = ctypes.c_int
+        st = f(*args)
+        if st < 0:
+            raise MSCompError(name, st)
+        return st
 
     def MaxCompressedSize(self, input_len):
-        val = lib().ms_max_compressed_size(self.format, input_len)
+        f = self._L().ms_max_compressed_size
+        f.restype = ctypes.c_size_t
+        val = f(ctypes.c_int(self.format), ctypes.c_size_t(input_len))
         if val == 0xFFFFFFFFFFFFFFFF:
             raise ValueError("invalid format")
         return val
@@ -135,9 +162,7 @@ class OpenSrc:
         cap = self.MaxCompressedSize(n) + 16 if output_buf is None else len(output_buf)
         out = ctypes.create_string_buffer(max(cap, 1)) if output_buf is None else (ctypes.c_char * cap).from_buffer(output_buf)
         olen = ctypes.c_size_t(cap)
-        st = lib().ms_compress(self.format, addr, n, ctypes.addressof(out), ctypes.byref(olen))
-        if st < 0:
-            raise MSCompError("ms_compress", st)
+        self._call("ms_compress", ctypes.c_int(self.format), ctypes.c_void_p(addr), ctypes.c_size_t(n), ctypes.c_void_p(ctypes.addressof(out)), ctypes.byref(olen))
         return bytes(out[:olen.value])
 
     def Decompress(self, input, output_buf=None, out_size=None):
@@ -149,10 +174,55 @@ class OpenSrc:
             cap = len(output_buf)
             out = (ctypes.c_char * cap).from_buffer(output_buf)
         olen = ctypes.c_size_t(cap)
-        st = lib().ms_decompress(self.format, addr, n, ctypes.addressof(out), ctypes.byref(olen))
-        if st < 0:
-            raise MSCompError("ms_decompress", st)
+        self._call("ms_decompress", ctypes.c_int(self.format), ctypes.c_void_p(addr), ctypes.c_size_t(n), ctypes.c_void_p(ctypes.addressof(out)), ctypes.byref(olen))
         return bytes(out[:olen.value])
+
+    # ---- streaming (reference test/compressors.py:258-309: the same loops, Python 3) ----
+    def _pump(self, init, step, end, step_args, input, output, input_buf, output_buf):
+        input_buf = bytearray(input_buf) if isinstance(input_buf, int) else (input_buf or bytearray(10 * 1024 * 1024))
+        output_buf = bytearray(output_buf) if isinstance(output_buf, int) else (output_buf or bytearray(10 * 1024 * 1024))
+        in_c = (ctypes.c_char * len(input_buf)).from_buffer(input_buf)
+        out_c = (ctypes.c_char * len(output_buf)).from_buffer(output_buf)
+        out_ptr, out_len = ctypes.addressof(out_c), len(output_buf)
+        s = MSCompStream()
+        self._call(init, ctypes.c_int(self.format), ctypes.byref(s))
+        try:
+            done = False
+            s.in_avail = input.readinto(input_buf)
+            while s.in_avail != 0:
+                s.in_ = ctypes.addressof(in_c)
+                while s.in_avail != 0:
+                    s.out, s.out_avail = out_ptr, out_len
+                    before = s.in_avail
+                    done = self._call(step, ctypes.byref(s), *step_args(False)) >= 1
+                    output.write(output_buf[:out_len - s.out_avail])
+                    if s.in_avail == before and s.out_avail == out_len:
+                        raise MSCompError(step, MSCOMP_BUF_ERROR)          # no progress with room on both sides: not a stream of this format
+                s.in_avail = input.readinto(input_buf)
+            for _ in range(1 << 20):
+                if done:
+                    break
+                s.out, s.out_avail = out_ptr, out_len
+                done = self._call(step, ctypes.byref(s), *step_args(True)) >= 1
+                output.write(output_buf[:out_len - s.out_avail])
+                if s.out_avail == out_len and not done:
+                    break                                                 # nothing more comes out (a decoder that cannot tell the end)
+        finally:
+            self._call(end, ctypes.byref(s))
+
+    def CompressStream(self, input, output, input_buf=None, output_buf=None):
+        self._pump("ms_deflate_init", "ms_deflate", "ms_deflate_end",
+                   lambda finishing: (ctypes.c_int(self.FINISH if finishing else self.NO_FLUSH),), input, output, input_buf, output_buf)
+
+    def DecompressStream(self, input, output, input_buf=None, output_buf=None):
+        self._pump("ms_inflate_init", "ms_inflate", "ms_inflate_end", lambda finishing: (), input, output, input_buf, output_buf)
+
+    @property
+    def streamable(self):
+        """(compress, decompress): which streaming directions the library implements for this format (upstream: both for
+        NoCompression and LZNT1, decompress only for Xpress, none for Xpress-Huffman; src/mscomp.cpp:134-223)."""
+        return {CompressionFormat.NoCompression: (True, True), CompressionFormat.LZNT1: (True, True),
+                CompressionFormat.Xpress: (False, True)}.get(self.format, (False, False))
 
 
 OpenSrc.NoCompression = OpenSrc(CompressionFormat.NoCompression)
