@@ -276,24 +276,30 @@ def measure_batch_format(ms, ctx, torch, fmt, each, count, steps, dev, peak, ran
 
     # plain Xpress: our encoder also writes the side-band restart index (one entry per 16 KiB of input), which lets the
     # decoder parse every segment on its own lane; without it a stream is one lane (reported as decode_ms_unindexed)
-    indexed = fmt == "xpress"
+    # Both formats: our encoder also leaves a side-band restart index (never part of the stream: the streams are byte for byte those
+    # of the plain call and decode with the reference), which lets the decoder start inside a stream -- one lane per segment.
+    # Without it a stream is one lane (reported as decode_ms_unindexed: the path a reference-made stream takes).
+    indexed = True
     seg_bytes = 16384
     stride = (each + seg_bytes - 1) // seg_bytes
-    d_index = ctx.xpress_index_tensor(count, stride) if indexed else None
+    if fmt == "xpress":
+        d_index = ctx.xpress_index_tensor(count, stride)
+    else:
+        d_index, d_ioff, d_nseg = ctx.xhuff_index_alloc(torch.full((count,), each, dtype=torch.int64))
 
     def step(ev=None):
         if ev:
             ev[0].record()
-        if indexed:
+        if fmt == "xpress":
             ctx.xpress_compress_indexed(d_in, d_comp, enc, seg_bytes, d_index, stride)
         else:
-            ctx.run_batch(fmt, "compress", d_in, d_comp, enc)
+            ctx.xhuff_compress_indexed(d_in, d_comp, enc, d_index, d_ioff, d_nseg)
         if ev:
             ev[1].record()
-        if indexed:
+        if fmt == "xpress":
             ctx.xpress_decompress_indexed(d_comp, d_out, dec, d_index, stride)
         else:
-            ctx.run_batch(fmt, "decompress", d_comp, d_out, dec)
+            ctx.xhuff_decompress_indexed(d_comp, d_out, dec, d_index, d_ioff, d_nseg)
         if ev:
             ev[2].record()
 
@@ -330,7 +336,9 @@ def measure_batch_format(ms, ctx, torch, fmt, each, count, steps, dev, peak, ran
         e1.record()
         torch.cuda.synchronize()
         assert torch.equal(d_out, d_in)
-        extra = {"decode_ms_unindexed": e0.elapsed_time(e1), "index": "side-band restart index, one entry per %d input bytes (%d per buffer)" % (seg_bytes, stride)}
+        extra = {"decode_ms_unindexed": e0.elapsed_time(e1),
+                 "index": ("side-band restart index written by the encoder, one entry per %d input bytes (%d per buffer)" % (seg_bytes, stride)) if fmt == "xpress"
+                          else "side-band restart index written by the encoder, one entry (16 bytes) per 64 symbols"}
     del d_in, d_comp, d_out
     torch.cuda.empty_cache()
     return {"workload": "%d independent buffers x %d bytes (text) per GPU, device batch API, %d GPU(s)" % (count, each, world),
@@ -377,6 +385,7 @@ def measure_mixed(ms, ctx, torch, dist, dev, rank, world, count, each, steps):
     bx, bh = batch_for(g[1], each), batch_for(g[2], 65536)
     seg_bytes, stride = 16384, (each + 16383) // 16384
     d_index = ctx.xpress_index_tensor(bx["n"], stride)
+    h_index, h_ioff, h_nseg = ctx.xhuff_index_alloc(torch.full((bh["n"],), 65536, dtype=torch.int64))
     d_out = torch.zeros(U, dtype=torch.uint8, device=dev)
     state = {}
 
@@ -411,11 +420,11 @@ def measure_mixed(ms, ctx, torch, dist, dev, rank, world, count, each, steps):
         if ev:
             ev[0].record()
         phase([enc_l, lambda: cx[1].xpress_compress_indexed(d_all, bx["comp"], bx["enc"], seg_bytes, d_index, stride),
-               lambda: cx[2].run_batch("xpress_huff", "compress", d_all, bh["comp"], bh["enc"])])
+               lambda: cx[2].xhuff_compress_indexed(d_all, bh["comp"], bh["enc"], h_index, h_ioff, h_nseg)])
         if ev:
             ev[1].record()
         phase([dec_l, lambda: cx[1].xpress_decompress_indexed(bx["comp"], d_out, bx["dec"], d_index, stride),
-               lambda: cx[2].run_batch("xpress_huff", "decompress", bh["comp"], d_out, bh["dec"])])
+               lambda: cx[2].xhuff_decompress_indexed(bh["comp"], d_out, bh["dec"], h_index, h_ioff, h_nseg)])
         if ev:
             ev[2].record()
 
@@ -450,7 +459,7 @@ def measure_mixed(ms, ctx, torch, dist, dev, rank, world, count, each, steps):
     del d_all, d_l, d_out, bx, bh, state
     torch.cuda.empty_cache()
     return {"config": "BASELINE.json configs[4]: %d independent %d-byte buffers per GPU, format [LZNT1, Xpress, Xpress-Huffman][i %% 3], sharded contiguously over %d GPU(s); "
-                      "Xpress-Huffman buffers as 64 KiB units, Xpress buffers with the side-band restart index" % (count, each, world),
+                      "Xpress-Huffman buffers as 64 KiB units, Xpress and Xpress-Huffman with the side-band restart index their encoders write" % (count, each, world),
             "uncompressed_bytes_per_gpu": U, "compressed_ratio": sum(C) / U, "encode_ms": enc_ms, "decode_ms": dec_ms,
             "encode_decode_MBps": world * U / MB / ((enc_ms + dec_ms) / 1e3), "encode_MBps": world * U / MB / (enc_ms / 1e3),
             "decode_MBps": world * U / MB / (dec_ms / 1e3), "gpu_launches": launches,

@@ -123,6 +123,11 @@ MSCOMPAPI MSCompStatus mscomp_gpu_xpress_huff_index_batch(mscomp_gpu_ctx* ctx, c
 MSCOMPAPI MSCompStatus mscomp_gpu_xpress_huff_decompress_batch_indexed(mscomp_gpu_ctx* ctx, const uint8_t* d_in, uint8_t* d_out,
                                                                        const mscomp_gpu_batch* batch, const mscomp_gpu_xhuff_seg* d_index,
                                                                        const uint64_t* d_index_off, const uint32_t* d_nseg);
+/* Compress AND leave the restart index of every stream (room: mscomp_gpu_xpress_huff_index_bound(in_len[i]) entries for stream i):
+ * the streams are byte for byte those of mscomp_gpu_xpress_huff_compress_batch; the index is what the walk would find. */
+MSCOMPAPI MSCompStatus mscomp_gpu_xpress_huff_compress_batch_indexed(mscomp_gpu_ctx* ctx, const uint8_t* d_in, uint8_t* d_out,
+                                                                     const mscomp_gpu_batch* batch, mscomp_gpu_xhuff_seg* d_index,
+                                                                     const uint64_t* d_index_off, uint32_t* d_nseg);
 /* Diagnostic: streams the indexed decoder handed to the index-free decoder since the context was created (synchronises). */
 MSCOMPAPI uint64_t     mscomp_gpu_xpress_huff_second_chances(mscomp_gpu_ctx* ctx);
 

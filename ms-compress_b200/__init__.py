@@ -93,6 +93,8 @@ def lib():
         L.mscomp_gpu_xpress_huff_index_batch.restype, L.mscomp_gpu_xpress_huff_index_batch.argtypes = i32, [vp, vp, vp, vp, vp, vp]
         L.mscomp_gpu_xpress_huff_decompress_batch_indexed.restype = i32
         L.mscomp_gpu_xpress_huff_decompress_batch_indexed.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+        L.mscomp_gpu_xpress_huff_compress_batch_indexed.restype = i32
+        L.mscomp_gpu_xpress_huff_compress_batch_indexed.argtypes = [vp, vp, vp, vp, vp, vp, vp]
         L.mscomp_gpu_xpress_huff_second_chances.restype, L.mscomp_gpu_xpress_huff_second_chances.argtypes = u64, [vp]
         L.mscomp_gpu_xpress_compress_batch_indexed.restype = i32
         L.mscomp_gpu_xpress_compress_batch_indexed.argtypes = [vp, vp, vp, vp, u32, vp, u32]
@@ -405,6 +407,13 @@ class GpuContext:
                                                                    d_index.data_ptr(), d_index_off.data_ptr(), d_nseg.data_ptr())
         if st < 0:
             raise MSCompError("mscomp_gpu_xpress_huff_decompress_batch_indexed", st)
+
+    def xhuff_compress_indexed(self, d_in, d_out, batch, d_index, d_index_off, d_nseg):
+        """Xpress-Huffman encode that also leaves the side-band restart index of every stream (the streams equal those of run_batch)."""
+        st = lib().mscomp_gpu_xpress_huff_compress_batch_indexed(self.handle, d_in.data_ptr(), d_out.data_ptr(), ctypes.byref(batch),
+                                                                 d_index.data_ptr(), d_index_off.data_ptr(), d_nseg.data_ptr())
+        if st < 0:
+            raise MSCompError("mscomp_gpu_xpress_huff_compress_batch_indexed", st)
 
     def xhuff_second_chances(self):
         """Streams the indexed Xpress-Huffman decoder handed to the index-free decoder so far (diagnostic)."""

@@ -15,9 +15,16 @@
 //      byte and every 16-bit word its final byte address (placement model of SURVEY.md A.3, which mirrors
 //      OutputBitstream: two words are always reserved ahead, raw bytes go to the write cursor)
 //   -> pass B: the assembled 16-bit words are scattered to their addresses.
+//
+// Restart index (optional, side-band; xhuff_index.cuh): pass A knows, for every token, how many bits and raw bytes precede it,
+// and that is all the reference's reader state at that symbol depends on -- words fetched F = 2 at the start, else
+// 1 + ceil(bits / 16) (Bitstream.h:59-70: a refill whenever fewer than 16 bits are left), valid bits = 16 F - bits, byte cursor
+// = 2 F + raw bytes.  So the encoder writes the entry of every 64th symbol itself, identical to what the serial walk
+// (xhuff_index_kernel) finds, and the decoder can start with one lane per segment without any walk.
 #pragma once
 #include "common.cuh"
 #include "lz_front.cuh"
+#include "xhuff_index.cuh"
 
 namespace msc {
 
@@ -30,7 +37,8 @@ constexpr uint32_t XHE_WORD_CAP = 36864;                         // 16-bit words
 constexpr size_t XHE_SCR_TOK = 0;
 constexpr size_t XHE_SCR_BITS = XHE_SCR_TOK + (size_t)XHE_TOK_CAP * 4;
 constexpr size_t XHE_SCR_WPOS = XHE_SCR_BITS + (size_t)XHE_WORD_CAP * 2;
-constexpr size_t XHE_SCRATCH_BYTES = XHE_SCR_WPOS + (size_t)XHE_WORD_CAP * 4;
+constexpr size_t XHE_SCR_SEGPOS = XHE_SCR_WPOS + (size_t)XHE_WORD_CAP * 4;      // input position of every 64th token (restart index)
+constexpr size_t XHE_SCRATCH_BYTES = XHE_SCR_SEGPOS + ((size_t)XHE_TOK_CAP / XHI_SEG_SYMS + 2) * 4;
 
 struct XhEncSmem {
     LzFrontSmem lz;
@@ -155,7 +163,8 @@ __global__ void __launch_bounds__(XHE_THREADS)
 xhuff_encode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint32_t count,
                     const uint64_t* __restrict__ in_off, const uint32_t* __restrict__ in_len,
                     const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ out_cap,
-                    uint32_t* __restrict__ out_len, int32_t* __restrict__ status, uint8_t* __restrict__ scratch, int eos_mode)
+                    uint32_t* __restrict__ out_len, int32_t* __restrict__ status, uint8_t* __restrict__ scratch, int eos_mode,
+                    XhSeg* __restrict__ index, const uint64_t* __restrict__ index_off, uint32_t* __restrict__ nseg)
 {
     MSC_DYN_SMEM(smem_raw);
     XhEncSmem& sm = *reinterpret_cast<XhEncSmem*>(smem_raw);
@@ -165,6 +174,7 @@ xhuff_encode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, u
     uint32_t* bits32 = reinterpret_cast<uint32_t*>(scr + XHE_SCR_BITS);
     uint16_t* bits16 = reinterpret_cast<uint16_t*>(scr + XHE_SCR_BITS);
     uint32_t* wpos = reinterpret_cast<uint32_t*>(scr + XHE_SCR_WPOS);
+    uint32_t* segpos = reinterpret_cast<uint32_t*>(scr + XHE_SCR_SEGPOS);
 
     for (uint32_t u = blockIdx.x; u < count; u += gridDim.x) {
         const uint8_t* ubase = in + in_off[u];
@@ -173,6 +183,9 @@ xhuff_encode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, u
         uint32_t opos = 0;
         int st = ST_OK;
         const bool stream_end_here = (eos_mode == 0) || (u + 1 == count);
+        XhSeg* ix = index ? index + index_off[u] : nullptr;              // this stream's restart index (eos_mode 0 only)
+        const uint64_t ix_room = index ? index_off[u + 1] - index_off[u] : 0;
+        uint32_t nent = 0;                                               // entries of the chunks before this one
 
         for (uint32_t c0 = 0; c0 < ulen && st == ST_OK; c0 += XHE_CHUNK) {
             const uint8_t* src = ubase + c0;
@@ -197,6 +210,7 @@ xhuff_encode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, u
                                 const uint32_t lo = sm.lz.lenoff[r];
                                 const uint32_t t = lo ? (0x80000000u | lo) : (uint32_t)src[t0 + r];
                                 tok[k] = t;
+                                if ((k & (XHI_SEG_SYMS - 1)) == 0) segpos[k / XHI_SEG_SYMS] = t0 + (uint32_t)r;
                                 atomicAdd(&sm.hist[xhe_sym_of(t)], 1u);
                             }
                         }
@@ -208,6 +222,7 @@ xhuff_encode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, u
                     for (int i = tid; i < XHE_SYMS; i += XHE_THREADS) sm.hist[i] = 0;
                     __syncthreads();
                     for (uint32_t i = tid; i < n; i += XHE_THREADS) { const uint32_t b = src[i]; tok[i] = b; atomicAdd(&sm.hist[b], 1u); }
+                    for (uint32_t i = tid; i * XHI_SEG_SYMS < n; i += XHE_THREADS) segpos[i] = i * XHI_SEG_SYMS;
                     if (tid == 0) sm.lz.ntok = n;
                     __syncthreads();
                 }
@@ -249,6 +264,7 @@ xhuff_encode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, u
             }
 
             const uint32_t ntok = sm.lz.ntok;
+            const uint32_t nsym = ntok - (last ? 1u : 0u);                // symbols that produce output (the index does not count the end-of-stream code)
             const uint32_t Btot = sm.bits_total;
             const uint32_t nwords = xhe_reserved(Btot);
             const uint32_t comp_len = 2 * nwords + sm.raw_total;
@@ -277,6 +293,13 @@ xhuff_encode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, u
                 if (k < ntok) {
                     const uint32_t B0 = (uint32_t)(excl >> 32), R0 = (uint32_t)excl;
                     const uint32_t B1 = B0 + cl, B2 = B1 + ob;
+                    if (ix && (k & (XHI_SEG_SYMS - 1)) == 0 && k < nsym) {   // the reader's state before symbol k (mask: see below)
+                        const uint32_t F = xhe_reserved(B0), e = nent + k / XHI_SEG_SYMS;
+                        const uint32_t left = nsym - k;
+                        if (e < ix_room)
+                            ix[e] = XhSeg{B0, opos + 256u + 2u * F + R0, c0 + segpos[k / XHI_SEG_SYMS],
+                                          (16u * F - B0) | (k == 0 ? XHI_NEWCHUNK : 0u) | ((left < XHI_SEG_SYMS ? left : XHI_SEG_SYMS) << 8)};
+                    }
                     xhe_put_bits(bits32, B0, sm.code()[sym], cl);
                     if (xhe_reserved(B1) > xhe_reserved(B0)) { const uint32_t j = xhe_reserved(B0); wpos[j] = 4 + 2 * (j - 2) + R0; }
                     if (t >> 31) {
@@ -299,10 +322,24 @@ xhuff_encode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, u
                 const uint32_t wv = bits16[j], p = wpos[j];
                 o[p] = (uint8_t)wv; o[p + 1] = (uint8_t)(wv >> 8);
             }
+            // index entries of this chunk: the bit window = the next `valid` bits of the bit string from the symbol's bit address on
+            if (ix) {
+                const uint32_t ne = (nsym + XHI_SEG_SYMS - 1) / XHI_SEG_SYMS;
+                for (uint32_t s2 = tid; s2 < ne; s2 += XHE_THREADS) {
+                    const uint32_t e = nent + s2;
+                    if (e < ix_room) {
+                        const uint32_t B0 = ix[e].mask, valid = ix[e].info & 63u;
+                        const uint32_t j = B0 >> 4, r = B0 & 15u;
+                        const uint32_t w0 = j < nwords ? bits16[j] : 0u, w1 = j + 1 < nwords ? bits16[j + 1] : 0u;
+                        ix[e].mask = (((w0 << 16) | w1) << r) & (valid >= 32u ? 0xFFFFFFFFu : ~(0xFFFFFFFFu >> valid));
+                    }
+                }
+                nent += ne;
+            }
             __syncthreads();
             opos += 256 + comp_len;
         }
-        if (tid == 0) { out_len[u] = (st == ST_OK) ? opos : 0; status[u] = st; }
+        if (tid == 0) { out_len[u] = (st == ST_OK) ? opos : 0; status[u] = st; if (nseg) nseg[u] = (st == ST_OK) ? nent : 0; }
         __syncthreads();
     }
 }

@@ -311,7 +311,8 @@ static bool batch_ok(const mscomp_gpu_ctx* ctx, const uint8_t* d_in, const uint8
     return ctx && b && (b->count == 0 || (d_in && d_out && b->d_in_off && b->d_in_len && b->d_out_off && b->d_out_cap && b->d_out_len && b->d_status));
 }
 
-MSCompStatus msc_xpress_huff_compress_units(mscomp_gpu_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, const mscomp_gpu_batch* b, int eos_mode)
+static MSCompStatus xhuff_encode_launch(mscomp_gpu_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, const mscomp_gpu_batch* b, int eos_mode,
+                                        XhSeg* d_index, const uint64_t* d_index_off, uint32_t* d_nseg)
 {
     if (!batch_ok(ctx, d_in, d_out, b)) return MSCOMP_ARG_ERROR;
     if (!b->count) return MSCOMP_OK;
@@ -324,13 +325,27 @@ MSCompStatus msc_xpress_huff_compress_units(mscomp_gpu_ctx* ctx, const uint8_t* 
     uint8_t* scratch = (uint8_t*)ctx->get(SC_AUX2, (size_t)grid * XHE_SCRATCH_BYTES + 64);
     if (!scratch) return MSCOMP_MEM_ERROR;
     MSC_LAUNCH_SMEM(ctx, xhuff_encode_kernel, grid, XHE_THREADS, sizeof(XhEncSmem), d_in, d_out, b->count, b->d_in_off, b->d_in_len, b->d_out_off,
-                    b->d_out_cap, b->d_out_len, b->d_status, scratch, eos_mode);
+                    b->d_out_cap, b->d_out_len, b->d_status, scratch, eos_mode, d_index, d_index_off, d_nseg);
     return msc_cuda_status(cudaGetLastError(), "xpress_huff_compress");
+}
+
+MSCompStatus msc_xpress_huff_compress_units(mscomp_gpu_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, const mscomp_gpu_batch* b, int eos_mode)
+{
+    return xhuff_encode_launch(ctx, d_in, d_out, b, eos_mode, nullptr, nullptr, nullptr);
 }
 
 MSCompStatus mscomp_gpu_xpress_huff_compress_batch(mscomp_gpu_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, const mscomp_gpu_batch* b)
 {
-    return msc_xpress_huff_compress_units(ctx, d_in, d_out, b, 0);
+    return xhuff_encode_launch(ctx, d_in, d_out, b, 0, nullptr, nullptr, nullptr);
+}
+
+// The same streams, byte for byte, plus the side-band restart index of each (the encoder knows every symbol's bit address, so the
+// index costs it nothing; what the serial walk of mscomp_gpu_xpress_huff_index_batch would find, entry for entry).
+MSCompStatus mscomp_gpu_xpress_huff_compress_batch_indexed(mscomp_gpu_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, const mscomp_gpu_batch* b,
+                                                           mscomp_gpu_xhuff_seg* d_index, const uint64_t* d_index_off, uint32_t* d_nseg)
+{
+    if (b && b->count && (!d_index || !d_index_off || !d_nseg)) return MSCOMP_ARG_ERROR;
+    return xhuff_encode_launch(ctx, d_in, d_out, b, 0, (XhSeg*)d_index, d_index_off, d_nseg);
 }
 
 // ---- Xpress-Huffman decode: restart index + one lane per segment ---------------------------------------------------------

@@ -54,7 +54,34 @@ void emu_xhuff_encode(const uint8_t* in, uint8_t* out, uint32_t count, const uin
 {
     std::vector<uint8_t> scratch((size_t)grid * msc::XHE_SCRATCH_BYTES + 64);
     emu::launch(msc::xhuff_encode_kernel, dim3e(grid), dim3e(msc::XHE_THREADS), in, out, count, in_off, in_len, out_off, out_cap, out_len, status,
-                scratch.data(), 0);
+                scratch.data(), 0, (msc::XhSeg*)nullptr, (const uint64_t*)nullptr, (uint32_t*)nullptr);
+}
+// the encoder's own restart index next to the one the serial walk finds for the streams it wrote: returns the number of streams
+// whose two indices differ (entry count or any entry)
+uint32_t emu_xhuff_encode_index_check(const uint8_t* in, uint8_t* out, uint32_t count, const uint64_t* in_off, const uint32_t* in_len,
+                                      const uint64_t* out_off, const uint32_t* out_cap, uint32_t* out_len, int32_t* status, uint32_t grid)
+{
+    using namespace msc;
+    std::vector<uint8_t> scratch((size_t)grid * XHE_SCRATCH_BYTES + 64);
+    std::vector<uint64_t> ioff(count + 1, 0);
+    for (uint32_t i = 0; i < count; ++i) ioff[i + 1] = ioff[i] + xhi_max_segments(in_len[i]);
+    std::vector<XhSeg> mine(ioff[count] + 1), walk(ioff[count] + 1);
+    std::vector<uint32_t> n_mine(count + 1), n_walk(count + 1), wl(count + 1);
+    std::vector<int32_t> ws(count + 1);
+    emu::launch(xhuff_encode_kernel, dim3e(grid), dim3e(XHE_THREADS), in, out, count, in_off, in_len, out_off, out_cap, out_len, status,
+                scratch.data(), 0, mine.data(), (const uint64_t*)ioff.data(), n_mine.data());
+    emu::launch(xhuff_index_kernel, dim3e(grid), dim3e(32 * XHD_WARPS_PER_BLOCK), (const uint8_t*)out, count, out_off, (const uint32_t*)out_len, in_len,
+                walk.data(), (const uint64_t*)ioff.data(), n_walk.data(), wl.data(), ws.data());
+    uint32_t bad = 0;
+    for (uint32_t i = 0; i < count; ++i) {
+        bool same = status[i] == 0 && ws[i] == 0 && wl[i] == in_len[i] && n_mine[i] == n_walk[i];
+        for (uint32_t e = 0; same && e < n_mine[i]; ++e) {
+            const XhSeg &a = mine[ioff[i] + e], &b = walk[ioff[i] + e];
+            same = a.mask == b.mask && a.ip == b.ip && a.out_pos == b.out_pos && a.info == b.info;
+        }
+        bad += same ? 0 : 1;
+    }
+    return bad;
 }
 
 

@@ -79,7 +79,9 @@ def emu_batch(emu, fn_name, bufs, caps, grid=2, extra=()):
     oc = np.array(caps, dtype=np.uint32)
     ol = np.zeros(count, dtype=np.uint32)
     st = np.zeros(count, dtype=np.int32)
-    getattr(emu, fn_name)(ctypes.c_void_p(addr), ctypes.c_void_p(out.ctypes.data + PAD), ctypes.c_uint32(count), P(io), P(il), P(oo), P(oc),
-                          P(ol), P(st), ctypes.c_uint32(grid), *extra)
+    fn = getattr(emu, fn_name)
+    fn.restype = ctypes.c_uint32
+    emu_batch.last_return = fn(ctypes.c_void_p(addr), ctypes.c_void_p(out.ctypes.data + PAD), ctypes.c_uint32(count), P(io), P(il), P(oo), P(oc),
+                               P(ol), P(st), ctypes.c_uint32(grid), *extra)
     outs = [out[PAD + out_off[i]:PAD + out_off[i] + ol[i]].tobytes() for i in range(count)]
     return st, ol, outs

@@ -210,3 +210,18 @@ def test_xhuff_indexed_status_equals_oracle_on_bad_input(emu, oracle, ms):
         assert st[i] == rc, (i, st[i], rc)
         if rc == 0:
             assert outs[i] == exp
+
+
+def test_xhuff_encoder_writes_the_index_the_walk_finds(emu, oracle, ms):
+    """mscomp_gpu_xpress_huff_compress_batch_indexed: the encoder's own restart index equals, entry for entry, the one the serial
+    walk finds in the stream it wrote (multi-chunk buffers, the literal-only fallback, long matches with raw length bytes, tiny
+    buffers), and the streams are the ones the plain call writes."""
+    plains = corpus(ms) + [ms.generate("text", 200000, 5), ms.generate("random", 70000, 6), ms.generate("runs", 140000, 7), b"a", b"ab" * 40000]
+    caps = [len(p) + 34 + 258 + 258 * (len(p) // 65536) + 16 for p in plains]
+    st, ol, outs = emu_batch(emu, "emu_xhuff_encode_index_check", plains, caps)
+    assert not st.any() and emu_batch.last_return == 0
+    st2, ol2, outs2 = emu_batch(emu, "emu_xhuff_encode", plains, caps)
+    assert outs == outs2
+    for p, c in zip(plains, outs):
+        rc, back = oracle.decompress("xpress_huff", c, len(p))
+        assert rc == 0 and back == p

@@ -255,3 +255,56 @@ def test_xhuff_restart_index_on_gpu(ms, oracle):
     for i in range(nvalid):
         assert got_st[i] == 0 and out[o_off[i]:o_off[i] + got_len[i]].tobytes() == plains[i], i
     assert ctx.xhuff_second_chances() - before >= hit
+
+
+@pytest.mark.gpu
+def test_xhuff_encoder_index_on_gpu(ms, oracle):
+    """mscomp_gpu_xpress_huff_compress_batch_indexed: same streams as the plain call (the oracle decodes them), and an index that
+    equals the serial walk's entry for entry; the indexed decoder gives the plain bytes back without a single second chance."""
+    import numpy as np
+    import torch
+    ctx = ms.GpuContext()
+    plains = [ms.generate(k, n, 3 + n % 5) for k in ("text", "runs", "random") for n in (1, 63, 4096, 65536, 65537, 200000)] + [b"ab" * 70000, bytes(100000)]
+    caps = [len(p) + 34 + 258 + 258 * (len(p) // 65536) + 16 for p in plains]
+    i_off = np.cumsum([0] + [(len(p) + 31) // 16 * 16 for p in plains])
+    c_off = np.cumsum([0] + [(c + 31) // 16 * 16 for c in caps])
+    blob = np.zeros(int(i_off[-1]) + 64, dtype=np.uint8)
+    for p, o in zip(plains, i_off):
+        blob[o:o + len(p)] = np.frombuffer(p, dtype=np.uint8)
+    d_in = torch.from_numpy(blob).to(ctx.device)
+    d_c = torch.zeros(int(c_off[-1]) + 64, dtype=torch.uint8, device=ctx.device)
+    d_c2 = torch.zeros_like(d_c)
+    enc, c_len, st, keep = ctx.make_batch(i_off[:-1].tolist(), [len(p) for p in plains], c_off[:-1].tolist(), caps)
+    d_index, d_ioff, d_nseg = ctx.xhuff_index_alloc([len(p) for p in plains])
+    ctx.xhuff_compress_indexed(d_in, d_c, enc, d_index, d_ioff, d_nseg)
+    ctx.synchronize()
+    assert not st.cpu().numpy().any()
+    lens = c_len.cpu().tolist()
+    mine, n_mine = d_index.cpu().numpy().reshape(-1, 4).copy(), d_nseg.cpu().numpy().copy()
+    ctx.run_batch("xpress_huff", "compress", d_in, d_c2, enc)
+    ctx.synchronize()
+    assert c_len.cpu().tolist() == lens and torch.equal(d_c, d_c2)
+    comp = d_c.cpu().numpy()
+    for i, p in enumerate(plains):
+        rc, back = oracle.decompress("xpress_huff", comp[c_off[i]:c_off[i] + lens[i]].tobytes(), len(p))
+        assert rc == 0 and back == p, i
+    # the walk over the same streams
+    dec, o_len, st2, keep2 = ctx.make_batch(c_off[:-1].tolist(), lens, i_off[:-1].tolist(), [len(p) for p in plains])
+    d_index2, d_ioff2, d_nseg2 = ctx.xhuff_index_alloc([len(p) for p in plains])
+    ctx.xhuff_index(d_c, dec, d_index2, d_ioff2, d_nseg2)
+    ctx.synchronize()
+    walk, n_walk = d_index2.cpu().numpy().reshape(-1, 4), d_nseg2.cpu().numpy()
+    ioff = d_ioff.cpu().numpy()
+    assert (n_mine == n_walk).all()
+    for i in range(len(plains)):
+        assert (mine[ioff[i]:ioff[i] + n_mine[i]] == walk[ioff[i]:ioff[i] + n_walk[i]]).all(), i
+    # decode from the encoder's index
+    d_out = torch.zeros(int(i_off[-1]) + 64, dtype=torch.uint8, device=ctx.device)
+    before = ctx.xhuff_second_chances()
+    ctx.xhuff_decompress_indexed(d_c, d_out, dec, d_index, d_ioff, d_nseg)
+    ctx.synchronize()
+    assert not st2.cpu().numpy().any() and o_len.cpu().tolist() == [len(p) for p in plains]
+    out = d_out.cpu().numpy()
+    for i, p in enumerate(plains):
+        assert out[i_off[i]:i_off[i] + len(p)].tobytes() == p, i
+    assert ctx.xhuff_second_chances() == before
