@@ -330,6 +330,7 @@ def measure_batch_format(ms, ctx, torch, fmt, each, count, steps, dev, peak, ran
     extra = {}
     if indexed and world == 1:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ctx.run_batch(fmt, "decompress", d_comp, d_out, dec)          # warm: the first call sizes the token scratch
         d_out.zero_()
         e0.record()
         ctx.run_batch(fmt, "decompress", d_comp, d_out, dec)

@@ -35,6 +35,7 @@ constexpr int LZNT1_SLOT = 4112;                 // 2-byte header + <= 4096 payl
 // (as the reference does for every position, src/lznt1_compress.cpp:62-70), by a whole warp per visited position.
 constexpr uint32_t LZE_HEAVY_WORK = 32768;
 constexpr int LZE_LAZY_RANK = 16;
+constexpr int LZE_ITEM_CAP = LZNT1_CHUNK / 2;    // work items of the pair search (they live in ord[], 4 bytes each)
 
 struct Lznt1EncSmem {
     __align__(16) uint8_t in[LZNT1_CHUNK + 16];  // zero padded
@@ -53,7 +54,7 @@ struct Lznt1EncSmem {
     uint16_t prefV[128], prefVM[128];
     uint16_t goff[LZNT1_CHUNK / 8 + 8];          // byte offset of each group's flag byte
     uint16_t chain[LZNT1_CHUNK / 12 + 8];        // every 4th visited match of the greedy parse
-    uint32_t nchain, scan_tmp[8], work_tmp[8];
+    uint32_t nchain, scan_tmp[8], work_tmp[8], in_tmp[8], cross_tmp[8];
 };
 
 __device__ __forceinline__ uint32_t lz_load4(const uint8_t* s, int idx)
@@ -62,6 +63,44 @@ __device__ __forceinline__ uint32_t lz_load4(const uint8_t* s, int idx)
     return __funnelshift_r(w[0], w[1], 8 * (idx & 3));
 }
 __device__ __forceinline__ uint32_t lz_hash3(uint32_t x) { return ((x & 0xFFFFFFu) * 0x9E3779B1u) >> 20; }
+
+// One position of a bucket in registers: its 16 bytes, the longest match the format can express there, the best key so far.
+struct LzeEnt { int p, ml; uint32_t k0, k1, k2, k3, best; };
+__device__ __forceinline__ void lze_load(LzeEnt& e, const Lznt1EncSmem& sm, int idx, int n)
+{
+    e.p = sm.sorted[idx];
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(sm.in) + (e.p >> 2);
+    const uint32_t sh = 8u * ((uint32_t)e.p & 3u);
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];     // (in[] is zero padded by 16 bytes)
+    e.k0 = __funnelshift_r(w0, w1, sh); e.k1 = __funnelshift_r(w1, w2, sh); e.k2 = __funnelshift_r(w2, w3, sh); e.k3 = __funnelshift_r(w3, w4, sh);
+    int S, lim;
+    lznt1_shift_limit(e.p, S, lim);
+    e.ml = min(n - e.p, (1 << S) + 2);                                        // mask3 (src/lznt1_compress.cpp:51,:66)
+    e.best = 0;
+}
+// Common prefix of two positions of a bucket (16 bytes without a branch, the rare rest from shared memory), credited to the later one.
+__device__ __forceinline__ void lze_pair(LzeEnt& x, LzeEnt& y, const Lznt1EncSmem& sm)
+{
+    uint32_t w = x.k0 ^ y.k0;
+    int l = 0;
+    if (!w) { w = x.k1 ^ y.k1; l = 4; }
+    if (!w) { w = x.k2 ^ y.k2; l = 8; }
+    if (!w) { w = x.k3 ^ y.k3; l = 12; }
+    l = w ? l + ((__ffs((int)w) - 1) >> 3) : 16;
+    const bool x_later = x.p > y.p;
+    const int ml = x_later ? x.ml : y.ml;
+    if (l == 16 && ml > 16) {
+        while (l < ml) {
+            const uint32_t d = lz_load4(sm.in, x.p + l) ^ lz_load4(sm.in, y.p + l);
+            if (d) { l += (__ffs((int)d) - 1) >> 3; break; }
+            l += 4;
+        }
+    }
+    l = min(l, ml);
+    const uint32_t key = l >= 3 ? ((uint32_t)l << 12) | (uint32_t)(4095 - (x_later ? y.p : x.p)) : 0u;
+    x.best = max(x.best, x_later ? key : 0u);
+    y.best = max(y.best, x_later ? 0u : key);
+}
 
 __global__ void __launch_bounds__(LZE_THREADS, 4)
 lznt1_encode_kernel(const uint8_t* __restrict__ in, uint64_t in_len, uint32_t first, uint32_t nchunks,
@@ -92,13 +131,12 @@ lznt1_encode_kernel(const uint8_t* __restrict__ in, uint64_t in_len, uint32_t fi
         sm.rankcnt[tid] = 0;
         __syncthreads();
 
-        // ---- B: counting sort by hash ------------------------------------------------------------------
+        // ---- B: hash of every position + histogram ------------------------------------------------------
         const int npos = n - 2;                      // positions 0..n-3 are indexed (Fill :99)
+        uint32_t hh[8];                              // my 16 hashes, two per register (0xFFFF: no position)
         {
             uint32_t* cntw = reinterpret_cast<uint32_t*>(sm.cnt);     // two 16-bit counters per word (counts <= 4094)
-            // a warp's lanes hold 32 consecutive positions = one placement round: lanes with equal hashes find each other
-            // here, in parallel (leader lane | rank inside the group << 5 | group size - 1 << 10, parked in ord[])
-#pragma unroll 4
+#pragma unroll
             for (int m = 0; m < LZNT1_CHUNK / LZE_THREADS; ++m) {
                 const int p = tid + LZE_THREADS * m;
                 uint32_t h = 0xFFFFu;
@@ -107,151 +145,255 @@ lznt1_encode_kernel(const uint8_t* __restrict__ in, uint64_t in_len, uint32_t fi
                     hashv[p] = (uint16_t)h;
                     atomicAdd(&cntw[h >> 1], 1u << (16 * (h & 1)));
                 }
-                const unsigned peers = __match_any_sync(FULL, h);
-                sm.ord[p] = (uint16_t)((uint32_t)(__ffs((int)peers) - 1) | ((uint32_t)__popc(peers & ((1u << lane) - 1)) << 5) | ((uint32_t)(__popc(peers) - 1) << 10));
+                if (m & 1) hh[m >> 1] |= h << 16; else hh[m >> 1] = h;
             }
-            __syncthreads();
-            // exclusive scan of the 4096 counts (16 per thread + block scan of the 256 partial sums): cnt[h] = BEGIN of bucket h
+        }
+        __syncthreads();
+        // Exclusive scan of the 4096 counts (16 per thread + block scan of the 256 partial sums): cnt[h] = BEGIN of bucket h.
+        // The same pass sizes the search: a bucket of c positions is cut into tiles of 4; every pair of positions of a bucket is
+        // compared exactly once, inside a tile ("in-tile" item, tiles of >= 2) or between two tiles ("cross" item).
+        bool fast;                                   // block-uniform: the pair search below; else the ordered-bucket path (heavy chunks)
+        uint32_t n_in = 0, n_cross = 0;              // items of the two kinds in the whole chunk
+        {
             uint4 q0 = reinterpret_cast<const uint4*>(sm.cnt)[2 * tid], q1 = reinterpret_cast<const uint4*>(sm.cnt)[2 * tid + 1];
             uint32_t wv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-            uint32_t sum = 0;
+            uint32_t sum = 0, my_pairs = 0, my_in = 0, my_cross = 0;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) sum += (wv[i] & 0xFFFFu) + (wv[i] >> 16);
-            const int incl = warp_incl_scan((int)sum);
-            if (lane == 31) sm.scan_tmp[warp] = (uint32_t)incl;
+            for (int i = 0; i < 16; ++i) {
+                const uint32_t c = (wv[i >> 1] >> (16 * (i & 1))) & 0xFFFFu, T = (c + 3) >> 2;
+                sum += c;
+                my_pairs += (c * (c - 1)) >> 1;
+                my_cross += (T * (T - 1)) >> 1;
+                my_in += c >= 2 ? T - ((c & 3u) == 1u ? 1u : 0u) : 0u;
+            }
+            const int incl = warp_incl_scan((int)sum), incl_in = warp_incl_scan((int)my_in), incl_cross = warp_incl_scan((int)my_cross);
+            const uint32_t wp = __reduce_add_sync(FULL, my_pairs);
+            if (lane == 31) { sm.scan_tmp[warp] = (uint32_t)incl; sm.work_tmp[warp] = wp; sm.in_tmp[warp] = (uint32_t)incl_in; sm.cross_tmp[warp] = (uint32_t)incl_cross; }
             __syncthreads();
-            uint32_t woff = 0;
-            for (int w = 0; w < warp; ++w) woff += sm.scan_tmp[w];
+            uint32_t woff = 0, in_off = 0, cross_off = 0, pairs = 0;
+            for (int w = 0; w < LZE_THREADS / 32; ++w) {
+                if (w < warp) { woff += sm.scan_tmp[w]; in_off += sm.in_tmp[w]; cross_off += sm.cross_tmp[w]; }
+                pairs += sm.work_tmp[w]; n_in += sm.in_tmp[w]; n_cross += sm.cross_tmp[w];
+            }
+            fast = pairs <= heavy_work && n_in + n_cross <= (uint32_t)LZE_ITEM_CAP;
+            in_off += (uint32_t)incl_in - my_in;
+            cross_off += n_in + (uint32_t)incl_cross - my_cross;
             uint32_t run = woff + (uint32_t)incl - sum;
+            uint32_t* items = reinterpret_cast<uint32_t*>(sm.ord);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const uint32_t lo = run; run += wv[i] & 0xFFFFu;
-                const uint32_t hi = run; run += wv[i] >> 16;
-                wv[i] = lo | (hi << 16);
+            for (int i = 0; i < 16; ++i) {
+                const uint32_t c = (wv[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
+                const uint32_t b = run;
+                run += c;
+                if (i & 1) wv[i >> 1] = (wv[i >> 1] & 0xFFFFu) | (b << 16); else wv[i >> 1] = (wv[i >> 1] & 0xFFFF0000u) | b;
+                if (fast && c >= 2) {                 // items of this bucket: tile a = entries [b + 4a, b + 4a + sa)
+                    const uint32_t T = (c + 3) >> 2;
+                    for (uint32_t a = 0; a < T; ++a) {
+                        const uint32_t sa = min(4u, c - 4 * a), A = (b + 4 * a) | ((sa - 1) << 12);
+                        if (sa >= 2) items[in_off++] = A;
+                        for (uint32_t bb = 0; bb < a; ++bb) items[cross_off++] = A | ((b + 4 * bb) << 14) | (1u << 28);   // (earlier tiles are full)
+                    }
+                }
             }
             reinterpret_cast<uint4*>(sm.cnt)[2 * tid] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
             reinterpret_cast<uint4*>(sm.cnt)[2 * tid + 1] = make_uint4(wv[4], wv[5], wv[6], wv[7]);
         }
         __syncthreads();
-        // Placement in position order by one warp, a round of 32 consecutive positions at a time: the first lane of every
-        // group of equal hashes advances the bucket cursor by the size of the group with one shared-memory atomic and hands
-        // the old value to the others.  Rounds are ordered (__syncwarp between their cursor updates), lanes are ordered
-        // inside a round, so buckets come out ascending by position -- which the early exit and the tie rule of the search
-        // rely on.  Four rounds are in flight at a time (nothing but the cursors links them).  The other warps wait at the
-        // barrier; other blocks of the SM fill the issue slots meanwhile.
-        if (warp == 0) {
-            uint32_t* cntw = reinterpret_cast<uint32_t*>(sm.cnt);
-            const int rounds = (npos + 31) >> 5;
-            for (int k = 0; k < rounds; k += 4) {
-                uint32_t h[4], inf[4], got[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) { const int p = min(32 * (k + u) + lane, LZNT1_CHUNK - 1); h[u] = hashv[p]; inf[u] = sm.ord[p]; }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    got[u] = 0;
-                    if (32 * (k + u) + lane < npos && (inf[u] & 0x3E0u) == 0)
-                        got[u] = atomicAdd(&cntw[h[u] >> 1], ((inf[u] >> 10) + 1u) << (16 * (h[u] & 1)));
-                    __syncwarp();                                    // cursor updates of round u before those of round u+1
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const uint32_t base = (__shfl_sync(FULL, got[u], (int)(inf[u] & 31u)) >> (16 * (h[u] & 1))) & 0xFFFFu;
-                    if (32 * (k + u) + lane < npos) sm.sorted[base + ((inf[u] >> 5) & 31u)] = (uint16_t)(32 * (k + u) + lane);
-                }
-            }
-        }
-        __syncthreads();
-        // cnt[h] = end offset of bucket h; begin = cnt[h-1] (0 for h == 0)
 
-        // ---- C: match search for every position ------------------------------------------------------
-        // The k-th entry of a bucket has k candidates (the earlier entries).  Threads take the entries grouped by that
-        // rank, so the lanes of a warp run the candidate loop the same number of times.
-        bool heavy;                                                  // block-uniform
-        {
-            uint32_t rr[4] = {0, 0, 0, 0};                           // ranks of my 16 entries, one byte each
-            heavy = false;
+        bool heavy = false;                          // block-uniform: deferred (lazy) search during the parse
+        if (fast) {
+            // ---- C (pair search): Find(p) = the longest common prefix with an EARLIER position of p's bucket, the earliest one on
+            // ties, capped at max_len(p) -- as a maximum over pairs it needs no order inside the buckets: every pair is compared
+            // once and credited to its later position, key (length << 12 | 4095 - earlier position), by a shared-memory atomicMax.
+            {   // unordered scatter into the buckets (cursors: cnt[h] ends up at the END of bucket h); lenoff is cleared meanwhile
+                uint32_t* cntw = reinterpret_cast<uint32_t*>(sm.cnt);
 #pragma unroll
-            for (int m = 0; m < 16; ++m) {
-                const int idx = tid + LZE_THREADS * m;
-                if (idx < npos) {
-                    const uint32_t h = hashv[sm.sorted[idx]];
-                    int r = idx - (int)(h ? sm.cnt[h - 1] : 0);
-                    r = r < 255 ? r : 255;
-                    rr[m >> 2] |= (uint32_t)r << (8 * (m & 3));
-                    atomicAdd(&sm.rankcnt[r], 1u);
-                }
-            }
-            __syncthreads();
-            {   // exclusive scan of the 256 rank counts (one per thread); sum of rank * count = candidate evaluations
-                const uint32_t v = sm.rankcnt[tid];
-                const int incl = warp_incl_scan((int)v);
-                const uint32_t wk = __reduce_add_sync(FULL, v * (uint32_t)tid);
-                if (lane == 31) { sm.scan_tmp[warp] = (uint32_t)incl; sm.work_tmp[warp] = wk; }
-                __syncthreads();
-                uint32_t woff = 0, work = 0;
-                for (int w = 0; w < warp; ++w) woff += sm.scan_tmp[w];
-                for (int w = 0; w < LZE_THREADS / 32; ++w) work += sm.work_tmp[w];
-                heavy = work > heavy_work;
-                sm.rankcnt[tid] = woff + (uint32_t)incl - v;
-            }
-            __syncthreads();
-#pragma unroll
-            for (int m = 0; m < 16; ++m) {
-                const int idx = tid + LZE_THREADS * m;
-                if (idx < npos) sm.ord[atomicAdd(&sm.rankcnt[(rr[m >> 2] >> (8 * (m & 3))) & 0xFFu], 1u)] = (uint16_t)idx;
-            }
-        }
-        __syncthreads();                                             // hashes are dead from here: lenoff takes their place
-#pragma unroll
-        for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(sm.lenoff)[tid + LZE_THREADS * i] = make_uint4(0, 0, 0, 0);
-        const int rank0_end = (int)sm.rankcnt[0];                    // entries of rank 0 have no candidate: no match
-        const int defer_start = heavy ? (int)sm.rankcnt[LZE_LAZY_RANK - 1] : npos;   // rankcnt[r] = end of rank r by now
-        __syncthreads();
-        for (int i = defer_start + tid; i < npos; i += LZE_THREADS) { const int p = sm.sorted[sm.ord[i]]; atomicOr(&sm.U[p >> 5], 1u << (p & 31)); }
-        for (int i = rank0_end + tid; i < defer_start; i += LZE_THREADS) {
-            const int idx = sm.ord[i];
-            const int p = sm.sorted[idx];
-            int S, lim;
-            lznt1_shift_limit(p, S, lim);
-            const int max_len = min(n - p, (1 << S) + 2);           // mask3 (src/lznt1_compress.cpp:51,:66)
-            const uint32_t key = lz_load4(sm.in, p), key2 = lz_load4(sm.in, p + 4);
-            const uint32_t h = lz_hash3(key);
-            int k = (h == 0) ? 0 : (int)sm.cnt[h - 1];
-            int best = 0, bj = 0;
-            int j = sm.sorted[k];
-            uint32_t dj = lz_load4(sm.in, j);
-            for (;;) {                                              // earlier entries of my bucket = earlier positions
-                const int kn = k + 1;
-                int jn = 0;
-                uint32_t djn = 0;
-                if (kn < idx) { jn = sm.sorted[kn]; djn = lz_load4(sm.in, jn); }   // next candidate: loads in flight during the compare
-                // common prefix of p and j, 4 bytes at a time; a hash collision simply ends with i < 3
-                int i2 = 0;
-                uint32_t d = dj ^ key;
-                if (!d) {
-                    i2 = 4;
-                    d = lz_load4(sm.in, j + 4) ^ key2;
-                    while (!d) {
-                        i2 += 4;
-                        if (i2 >= max_len) break;
-                        d = lz_load4(sm.in, p + i2) ^ lz_load4(sm.in, j + i2);
+                for (int m = 0; m < LZNT1_CHUNK / LZE_THREADS; ++m) {
+                    const uint32_t h = (hh[m >> 1] >> (16 * (m & 1))) & 0xFFFFu;
+                    if (h != 0xFFFFu) {
+                        const uint32_t old = atomicAdd(&cntw[h >> 1], 1u << (16 * (h & 1)));
+                        sm.sorted[(old >> (16 * (h & 1))) & 0xFFFFu] = (uint16_t)(tid + LZE_THREADS * m);
                     }
                 }
-                if (d) i2 += (__ffs((int)d) - 1) >> 3;
-                if (i2 > max_len) i2 = max_len;
-                if (i2 > best) { best = i2; bj = j; if (best == max_len) break; }
-                if (kn >= idx) break;
-                k = kn; j = jn; dj = djn;
             }
-            if (best >= 3) sm.lenoff[p] = (uint32_t)best | ((uint32_t)(p - bj) << 16);
+            __syncthreads();                                             // (the hashes in lenoff's first half are dead only now)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(sm.lenoff)[tid + LZE_THREADS * i] = make_uint4(0, 0, 0, 0);
+            __syncthreads();
+            {
+                const uint32_t* items = reinterpret_cast<const uint32_t*>(sm.ord);
+                const uint32_t n_items = n_in + n_cross;
+                for (uint32_t it = tid; it < n_items; it += LZE_THREADS) {
+                    const uint32_t item = items[it];
+                    const int ia = (int)(item & 0xFFFu), sa = (int)((item >> 12) & 3u) + 1;
+                    LzeEnt e0, e1, e2, e3;
+                    lze_load(e0, sm, ia, n);
+                    lze_load(e1, sm, ia + (sa > 1 ? 1 : 0), n);
+                    lze_load(e2, sm, ia + (sa > 2 ? 2 : 0), n);
+                    lze_load(e3, sm, ia + (sa > 3 ? 3 : 0), n);
+                    if (!(item >> 28)) {
+                        lze_pair(e0, e1, sm);
+                        if (sa > 2) { lze_pair(e0, e2, sm); lze_pair(e1, e2, sm); }
+                        if (sa > 3) { lze_pair(e0, e3, sm); lze_pair(e1, e3, sm); lze_pair(e2, e3, sm); }
+                    } else {
+                        const int ib = (int)((item >> 14) & 0xFFFu);
+                        for (int u = 0; u < 4; ++u) {
+                            LzeEnt f;
+                            lze_load(f, sm, ib + u, n);
+                            lze_pair(e0, f, sm);
+                            if (sa > 1) lze_pair(e1, f, sm);
+                            if (sa > 2) lze_pair(e2, f, sm);
+                            if (sa > 3) lze_pair(e3, f, sm);
+                            if (f.best) atomicMax(&sm.lenoff[f.p], f.best);
+                        }
+                    }
+                    if (e0.best) atomicMax(&sm.lenoff[e0.p], e0.best);
+                    if (sa > 1 && e1.best) atomicMax(&sm.lenoff[e1.p], e1.best);
+                    if (sa > 2 && e2.best) atomicMax(&sm.lenoff[e2.p], e2.best);
+                    if (sa > 3 && e3.best) atomicMax(&sm.lenoff[e3.p], e3.best);
+                }
+            }
+            __syncthreads();
+            // keys -> len | dist << 16 (what the parse and the emitter read), and the match bitmap
+            for (int p = tid; p < LZNT1_CHUNK; p += LZE_THREADS) {
+                const uint32_t v = sm.lenoff[p];
+                if (v) sm.lenoff[p] = (v >> 12) | ((uint32_t)(p - (4095 - (int)(v & 0xFFFu))) << 16);
+                const unsigned mm = __ballot_sync(FULL, v != 0);
+                if (lane == 0) sm.M[p >> 5] = mm;
+            }
+            if (tid == 0) sm.M[128] = 0;
+            __syncthreads();
+        } else {
+            // ---- ordered buckets (heavy chunks: the lazy search needs the candidates in position order) ----------------------
+            // a warp's lanes hold 32 consecutive positions = one placement round: lanes with equal hashes find each other
+            // here, in parallel (leader lane | rank inside the group << 5 | group size - 1 << 10, parked in ord[])
+#pragma unroll 4
+            for (int m = 0; m < LZNT1_CHUNK / LZE_THREADS; ++m) {
+                const int p = tid + LZE_THREADS * m;
+                const uint32_t h = (p < npos) ? (uint32_t)hashv[p] : 0xFFFFu;
+                const unsigned peers = __match_any_sync(FULL, h);
+                sm.ord[p] = (uint16_t)((uint32_t)(__ffs((int)peers) - 1) | ((uint32_t)__popc(peers & ((1u << lane) - 1)) << 5) | ((uint32_t)(__popc(peers) - 1) << 10));
+            }
+            __syncthreads();
+            // Placement in position order by one warp, a round of 32 consecutive positions at a time: the first lane of every
+            // group of equal hashes advances the bucket cursor by the size of the group with one shared-memory atomic and hands
+            // the old value to the others.  Rounds are ordered (__syncwarp between their cursor updates), lanes are ordered
+            // inside a round, so buckets come out ascending by position -- which the early exit and the tie rule of the search
+            // rely on.  Four rounds are in flight at a time (nothing but the cursors links them).  The other warps wait at the
+            // barrier; other blocks of the SM fill the issue slots meanwhile.
+            if (warp == 0) {
+                uint32_t* cntw = reinterpret_cast<uint32_t*>(sm.cnt);
+                const int rounds = (npos + 31) >> 5;
+                for (int k = 0; k < rounds; k += 4) {
+                    uint32_t h[4], inf[4], got[4];
+    #pragma unroll
+                    for (int u = 0; u < 4; ++u) { const int p = min(32 * (k + u) + lane, LZNT1_CHUNK - 1); h[u] = hashv[p]; inf[u] = sm.ord[p]; }
+    #pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        got[u] = 0;
+                        if (32 * (k + u) + lane < npos && (inf[u] & 0x3E0u) == 0)
+                            got[u] = atomicAdd(&cntw[h[u] >> 1], ((inf[u] >> 10) + 1u) << (16 * (h[u] & 1)));
+                        __syncwarp();                                    // cursor updates of round u before those of round u+1
+                    }
+    #pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint32_t base = (__shfl_sync(FULL, got[u], (int)(inf[u] & 31u)) >> (16 * (h[u] & 1))) & 0xFFFFu;
+                        if (32 * (k + u) + lane < npos) sm.sorted[base + ((inf[u] >> 5) & 31u)] = (uint16_t)(32 * (k + u) + lane);
+                    }
+                }
+            }
+            __syncthreads();
+            // cnt[h] = end offset of bucket h; begin = cnt[h-1] (0 for h == 0)
+
+            // ---- C: match search for every position ------------------------------------------------------
+            // The k-th entry of a bucket has k candidates (the earlier entries).  Threads take the entries grouped by that
+            // rank, so the lanes of a warp run the candidate loop the same number of times.
+            {
+                uint32_t rr[4] = {0, 0, 0, 0};                           // ranks of my 16 entries, one byte each
+                heavy = false;
+    #pragma unroll
+                for (int m = 0; m < 16; ++m) {
+                    const int idx = tid + LZE_THREADS * m;
+                    if (idx < npos) {
+                        const uint32_t h = hashv[sm.sorted[idx]];
+                        int r = idx - (int)(h ? sm.cnt[h - 1] : 0);
+                        r = r < 255 ? r : 255;
+                        rr[m >> 2] |= (uint32_t)r << (8 * (m & 3));
+                        atomicAdd(&sm.rankcnt[r], 1u);
+                    }
+                }
+                __syncthreads();
+                {   // exclusive scan of the 256 rank counts (one per thread); sum of rank * count = candidate evaluations
+                    const uint32_t v = sm.rankcnt[tid];
+                    const int incl = warp_incl_scan((int)v);
+                    const uint32_t wk = __reduce_add_sync(FULL, v * (uint32_t)tid);
+                    if (lane == 31) { sm.scan_tmp[warp] = (uint32_t)incl; sm.work_tmp[warp] = wk; }
+                    __syncthreads();
+                    uint32_t woff = 0, work = 0;
+                    for (int w = 0; w < warp; ++w) woff += sm.scan_tmp[w];
+                    for (int w = 0; w < LZE_THREADS / 32; ++w) work += sm.work_tmp[w];
+                    heavy = work > heavy_work;
+                    sm.rankcnt[tid] = woff + (uint32_t)incl - v;
+                }
+                __syncthreads();
+    #pragma unroll
+                for (int m = 0; m < 16; ++m) {
+                    const int idx = tid + LZE_THREADS * m;
+                    if (idx < npos) sm.ord[atomicAdd(&sm.rankcnt[(rr[m >> 2] >> (8 * (m & 3))) & 0xFFu], 1u)] = (uint16_t)idx;
+                }
+            }
+            __syncthreads();                                             // hashes are dead from here: lenoff takes their place
+    #pragma unroll
+            for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(sm.lenoff)[tid + LZE_THREADS * i] = make_uint4(0, 0, 0, 0);
+            const int rank0_end = (int)sm.rankcnt[0];                    // entries of rank 0 have no candidate: no match
+            const int defer_start = heavy ? (int)sm.rankcnt[LZE_LAZY_RANK - 1] : npos;   // rankcnt[r] = end of rank r by now
+            __syncthreads();
+            for (int i = defer_start + tid; i < npos; i += LZE_THREADS) { const int p = sm.sorted[sm.ord[i]]; atomicOr(&sm.U[p >> 5], 1u << (p & 31)); }
+            for (int i = rank0_end + tid; i < defer_start; i += LZE_THREADS) {
+                const int idx = sm.ord[i];
+                const int p = sm.sorted[idx];
+                int S, lim;
+                lznt1_shift_limit(p, S, lim);
+                const int max_len = min(n - p, (1 << S) + 2);           // mask3 (src/lznt1_compress.cpp:51,:66)
+                const uint32_t key = lz_load4(sm.in, p), key2 = lz_load4(sm.in, p + 4);
+                const uint32_t h = lz_hash3(key);
+                int k = (h == 0) ? 0 : (int)sm.cnt[h - 1];
+                int best = 0, bj = 0;
+                int j = sm.sorted[k];
+                uint32_t dj = lz_load4(sm.in, j);
+                for (;;) {                                              // earlier entries of my bucket = earlier positions
+                    const int kn = k + 1;
+                    int jn = 0;
+                    uint32_t djn = 0;
+                    if (kn < idx) { jn = sm.sorted[kn]; djn = lz_load4(sm.in, jn); }   // next candidate: loads in flight during the compare
+                    // common prefix of p and j, 4 bytes at a time; a hash collision simply ends with i < 3
+                    int i2 = 0;
+                    uint32_t d = dj ^ key;
+                    if (!d) {
+                        i2 = 4;
+                        d = lz_load4(sm.in, j + 4) ^ key2;
+                        while (!d) {
+                            i2 += 4;
+                            if (i2 >= max_len) break;
+                            d = lz_load4(sm.in, p + i2) ^ lz_load4(sm.in, j + i2);
+                        }
+                    }
+                    if (d) i2 += (__ffs((int)d) - 1) >> 3;
+                    if (i2 > max_len) i2 = max_len;
+                    if (i2 > best) { best = i2; bj = j; if (best == max_len) break; }
+                    if (kn >= idx) break;
+                    k = kn; j = jn; dj = djn;
+                }
+                if (best >= 3) sm.lenoff[p] = (uint32_t)best | ((uint32_t)(p - bj) << 16);
+            }
+            __syncthreads();
+            for (int p = tid; p < LZNT1_CHUNK; p += LZE_THREADS) {
+                const unsigned mm = __ballot_sync(FULL, sm.lenoff[p] != 0);
+                if (lane == 0) sm.M[p >> 5] = mm;
+            }
+            if (tid == 0) sm.M[128] = 0;
+            __syncthreads();
         }
-        __syncthreads();
-        for (int p = tid; p < LZNT1_CHUNK; p += LZE_THREADS) {
-            const unsigned mm = __ballot_sync(FULL, sm.lenoff[p] != 0);
-            if (lane == 0) sm.M[p >> 5] = mm;
-        }
-        if (tid == 0) sm.M[128] = 0;
-        __syncthreads();
 
         // ---- D: greedy parse p += max(1, len[p]) ------------------------------------------
         // For a match position q the parse continues at nxt(q) = first match position >= q + len[q] (everything in
