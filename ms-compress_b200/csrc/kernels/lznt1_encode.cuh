@@ -54,7 +54,8 @@ struct Lznt1EncSmem {
     uint16_t prefV[128], prefVM[128];
     uint16_t goff[LZNT1_CHUNK / 8 + 8];          // byte offset of each group's flag byte
     uint16_t chain[LZNT1_CHUNK / 12 + 8];        // every 4th visited match of the greedy parse
-    uint32_t nchain, scan_tmp[8], work_tmp[8], in_tmp[8], cross_tmp[8];
+    uint32_t nchain, scan_tmp[8], work_tmp[8], cross_tmp[8], nbig, big_fill[4];
+    unsigned long long tot_tmp[8], small_tmp[8];
 };
 
 __device__ __forceinline__ uint32_t lz_load4(const uint8_t* s, int idx)
@@ -150,34 +151,55 @@ lznt1_encode_kernel(const uint8_t* __restrict__ in, uint64_t in_len, uint32_t fi
         }
         __syncthreads();
         // Exclusive scan of the 4096 counts (16 per thread + block scan of the 256 partial sums): cnt[h] = BEGIN of bucket h.
-        // The same pass sizes the search: a bucket of c positions is cut into tiles of 4; every pair of positions of a bucket is
-        // compared exactly once, inside a tile ("in-tile" item, tiles of >= 2) or between two tiles ("cross" item).
+        // The same pass lists the work of the search.  A bucket of c positions is cut into tiles of 4; every pair of positions of a
+        // bucket is compared exactly once, inside a tile ("in-tile" item; lists by tile size 2, 3, 4 so that a warp's lanes do the
+        // same work) or between two tiles ("cross" item).  Buckets of up to 4 are one tile, listed right here; the few larger ones
+        // go to a side list and are expanded below.  Item lists live in ord[]: [size 2 | size 3 | size 4 | cross].
         bool fast;                                   // block-uniform: the pair search below; else the ordered-bucket path (heavy chunks)
-        uint32_t n_in = 0, n_cross = 0;              // items of the two kinds in the whole chunk
+        uint32_t base3 = 0, base4 = 0, basex = 0, n_items = 0;
         {
             uint4 q0 = reinterpret_cast<const uint4*>(sm.cnt)[2 * tid], q1 = reinterpret_cast<const uint4*>(sm.cnt)[2 * tid + 1];
             uint32_t wv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-            uint32_t sum = 0, my_pairs = 0, my_in = 0, my_cross = 0;
+            uint32_t sum = 0, my_pairs = 0, my_big = 0;
+            unsigned long long small = 0;            // single-tile buckets of size 2 | 3 << 16 | 4 << 32
+            unsigned long long tot = 0;              // tiles of size 2 | 3 << 16 | 4 << 32 | cross items << 48, large buckets only
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-                const uint32_t c = (wv[i >> 1] >> (16 * (i & 1))) & 0xFFFFu, T = (c + 3) >> 2;
+                const uint32_t c = (wv[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
                 sum += c;
                 my_pairs += (c * (c - 1)) >> 1;
-                my_cross += (T * (T - 1)) >> 1;
-                my_in += c >= 2 ? T - ((c & 3u) == 1u ? 1u : 0u) : 0u;
+                if (c >= 2 && c <= 4) small += 1ull << (16 * (c - 2));
+                if (c > 4) {
+                    const uint32_t T = (c + 3) >> 2, sl = c - 4 * (T - 1);
+                    ++my_big;
+                    tot += ((unsigned long long)(T - 1) << 32) + ((unsigned long long)((T * (T - 1)) >> 1) << 48) + (sl >= 2 ? 1ull << (16 * (sl - 2)) : 0ull);
+                }
             }
-            const int incl = warp_incl_scan((int)sum), incl_in = warp_incl_scan((int)my_in), incl_cross = warp_incl_scan((int)my_cross);
-            const uint32_t wp = __reduce_add_sync(FULL, my_pairs);
-            if (lane == 31) { sm.scan_tmp[warp] = (uint32_t)incl; sm.work_tmp[warp] = wp; sm.in_tmp[warp] = (uint32_t)incl_in; sm.cross_tmp[warp] = (uint32_t)incl_cross; }
+            const int incl = warp_incl_scan((int)sum);
+            unsigned long long incl_small = small;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const unsigned long long t = __shfl_up_sync(FULL, incl_small, d); if (lane >= d) incl_small += t; }
+            const uint32_t wp = __reduce_add_sync(FULL, my_pairs), wb = __reduce_add_sync(FULL, my_big);
+            unsigned long long wt = tot;
+#pragma unroll
+            for (int d = 16; d; d >>= 1) wt += __shfl_xor_sync(FULL, wt, d);
+            if (lane == 31) { sm.scan_tmp[warp] = (uint32_t)incl; sm.work_tmp[warp] = wp; sm.small_tmp[warp] = incl_small; sm.cross_tmp[warp] = wb; sm.tot_tmp[warp] = wt; }
+            if (tid == 0) { sm.nbig = 0; sm.big_fill[0] = 0; sm.big_fill[1] = 0; sm.big_fill[2] = 0; sm.big_fill[3] = 0; }
             __syncthreads();
-            uint32_t woff = 0, in_off = 0, cross_off = 0, pairs = 0;
+            uint32_t woff = 0, pairs = 0, nbig = 0;
+            unsigned long long big_tot = 0, soff = 0, nsmall = 0;
             for (int w = 0; w < LZE_THREADS / 32; ++w) {
-                if (w < warp) { woff += sm.scan_tmp[w]; in_off += sm.in_tmp[w]; cross_off += sm.cross_tmp[w]; }
-                pairs += sm.work_tmp[w]; n_in += sm.in_tmp[w]; n_cross += sm.cross_tmp[w];
+                if (w < warp) { woff += sm.scan_tmp[w]; soff += sm.small_tmp[w]; }
+                pairs += sm.work_tmp[w]; nsmall += sm.small_tmp[w]; nbig += sm.cross_tmp[w]; big_tot += sm.tot_tmp[w];
             }
-            fast = pairs <= heavy_work && n_in + n_cross <= (uint32_t)LZE_ITEM_CAP;
-            in_off += (uint32_t)incl_in - my_in;
-            cross_off += n_in + (uint32_t)incl_cross - my_cross;
+            const uint32_t n2s = (uint32_t)(nsmall & 0xFFFFu), n3s = (uint32_t)((nsmall >> 16) & 0xFFFFu), n4s = (uint32_t)(nsmall >> 32);
+            const uint32_t n2 = n2s + (uint32_t)(big_tot & 0xFFFFu), n3 = n3s + (uint32_t)((big_tot >> 16) & 0xFFFFu), n4 = n4s + (uint32_t)((big_tot >> 32) & 0xFFFFu);
+            const uint32_t nx = (uint32_t)(big_tot >> 48);
+            base3 = n2; base4 = n2 + n3; basex = n2 + n3 + n4; n_items = basex + nx;
+            // (16-bit fields: a chunk whose counts would overflow them has far more pairs than heavy_work)
+            fast = pairs <= heavy_work && n_items <= (uint32_t)LZE_ITEM_CAP && nbig <= 256u;
+            soff += incl_small - small;
+            uint32_t o2 = (uint32_t)(soff & 0xFFFFu), o3 = base3 + (uint32_t)((soff >> 16) & 0xFFFFu), o4 = base4 + (uint32_t)(soff >> 32);
             uint32_t run = woff + (uint32_t)incl - sum;
             uint32_t* items = reinterpret_cast<uint32_t*>(sm.ord);
 #pragma unroll
@@ -186,17 +208,31 @@ lznt1_encode_kernel(const uint8_t* __restrict__ in, uint64_t in_len, uint32_t fi
                 const uint32_t b = run;
                 run += c;
                 if (i & 1) wv[i >> 1] = (wv[i >> 1] & 0xFFFFu) | (b << 16); else wv[i >> 1] = (wv[i >> 1] & 0xFFFF0000u) | b;
-                if (fast && c >= 2) {                 // items of this bucket: tile a = entries [b + 4a, b + 4a + sa)
-                    const uint32_t T = (c + 3) >> 2;
-                    for (uint32_t a = 0; a < T; ++a) {
-                        const uint32_t sa = min(4u, c - 4 * a), A = (b + 4 * a) | ((sa - 1) << 12);
-                        if (sa >= 2) items[in_off++] = A;
-                        for (uint32_t bb = 0; bb < a; ++bb) items[cross_off++] = A | ((b + 4 * bb) << 14) | (1u << 28);   // (earlier tiles are full)
-                    }
+                if (fast) {
+                    if (c == 2) items[o2++] = b;
+                    if (c == 3) items[o3++] = b;
+                    if (c == 4) items[o4++] = b;
+                    if (c > 4) sm.rankcnt[atomicAdd(&sm.nbig, 1u)] = b | (c << 12);      // (rankcnt[] is free on this path)
                 }
             }
             reinterpret_cast<uint4*>(sm.cnt)[2 * tid] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
             reinterpret_cast<uint4*>(sm.cnt)[2 * tid + 1] = make_uint4(wv[4], wv[5], wv[6], wv[7]);
+            __syncthreads();
+            if (fast && (uint32_t)tid < nbig) {       // a large bucket: its tiles and tile pairs (places by atomics: the order inside a list is free)
+                const uint32_t e = sm.rankcnt[tid], b = e & 0xFFFu, c = e >> 12;
+                const uint32_t T = (c + 3) >> 2, sl = c - 4 * (T - 1);
+                uint32_t at = base4 + n4s + atomicAdd(&sm.big_fill[2], T - 1);
+                for (uint32_t a = 0; a + 1 < T; ++a) items[at++] = b + 4 * a;
+                if (sl >= 2) {
+                    const uint32_t cls = sl - 2, basec = cls == 0 ? n2s : (cls == 1 ? base3 + n3s : base4 + n4s);
+                    items[basec + atomicAdd(&sm.big_fill[cls], 1u)] = b + 4 * (T - 1);
+                }
+                at = basex + atomicAdd(&sm.big_fill[3], (T * (T - 1)) >> 1);
+                for (uint32_t a = 1; a < T; ++a) {
+                    const uint32_t A = (b + 4 * a) | (((a + 1 < T ? 4u : sl) - 1) << 12);
+                    for (uint32_t bb = 0; bb < a; ++bb) items[at++] = A | ((b + 4 * bb) << 14);          // (earlier tiles are full)
+                }
+            }
         }
         __syncthreads();
 
@@ -222,30 +258,45 @@ lznt1_encode_kernel(const uint8_t* __restrict__ in, uint64_t in_len, uint32_t fi
             __syncthreads();
             {
                 const uint32_t* items = reinterpret_cast<const uint32_t*>(sm.ord);
-                const uint32_t n_items = n_in + n_cross;
-                for (uint32_t it = tid; it < n_items; it += LZE_THREADS) {
+                // in-tile items, one list per tile size (a warp straddling two lists runs both bodies once)
+                for (uint32_t it = tid; it < basex; it += LZE_THREADS) {
+                    const int ia = (int)items[it];
+                    LzeEnt e0, e1;
+                    lze_load(e0, sm, ia, n);
+                    lze_load(e1, sm, ia + 1, n);
+                    lze_pair(e0, e1, sm);
+                    if (it >= base3) {
+                        LzeEnt e2;
+                        lze_load(e2, sm, ia + 2, n);
+                        lze_pair(e0, e2, sm); lze_pair(e1, e2, sm);
+                        if (it >= base4) {
+                            LzeEnt e3;
+                            lze_load(e3, sm, ia + 3, n);
+                            lze_pair(e0, e3, sm); lze_pair(e1, e3, sm); lze_pair(e2, e3, sm);
+                            if (e3.best) atomicMax(&sm.lenoff[e3.p], e3.best);
+                        }
+                        if (e2.best) atomicMax(&sm.lenoff[e2.p], e2.best);
+                    }
+                    if (e0.best) atomicMax(&sm.lenoff[e0.p], e0.best);
+                    if (e1.best) atomicMax(&sm.lenoff[e1.p], e1.best);
+                }
+                // cross items: tile A (1..4 positions) in registers, the 4 positions of tile B streamed past it
+                for (uint32_t it = basex + tid; it < n_items; it += LZE_THREADS) {
                     const uint32_t item = items[it];
-                    const int ia = (int)(item & 0xFFFu), sa = (int)((item >> 12) & 3u) + 1;
+                    const int ia = (int)(item & 0xFFFu), sa = (int)((item >> 12) & 3u) + 1, ib = (int)((item >> 14) & 0xFFFu);
                     LzeEnt e0, e1, e2, e3;
                     lze_load(e0, sm, ia, n);
                     lze_load(e1, sm, ia + (sa > 1 ? 1 : 0), n);
                     lze_load(e2, sm, ia + (sa > 2 ? 2 : 0), n);
                     lze_load(e3, sm, ia + (sa > 3 ? 3 : 0), n);
-                    if (!(item >> 28)) {
-                        lze_pair(e0, e1, sm);
-                        if (sa > 2) { lze_pair(e0, e2, sm); lze_pair(e1, e2, sm); }
-                        if (sa > 3) { lze_pair(e0, e3, sm); lze_pair(e1, e3, sm); lze_pair(e2, e3, sm); }
-                    } else {
-                        const int ib = (int)((item >> 14) & 0xFFFu);
-                        for (int u = 0; u < 4; ++u) {
-                            LzeEnt f;
-                            lze_load(f, sm, ib + u, n);
-                            lze_pair(e0, f, sm);
-                            if (sa > 1) lze_pair(e1, f, sm);
-                            if (sa > 2) lze_pair(e2, f, sm);
-                            if (sa > 3) lze_pair(e3, f, sm);
-                            if (f.best) atomicMax(&sm.lenoff[f.p], f.best);
-                        }
+                    for (int u = 0; u < 4; ++u) {
+                        LzeEnt f;
+                        lze_load(f, sm, ib + u, n);
+                        lze_pair(e0, f, sm);
+                        if (sa > 1) lze_pair(e1, f, sm);
+                        if (sa > 2) lze_pair(e2, f, sm);
+                        if (sa > 3) lze_pair(e3, f, sm);
+                        if (f.best) atomicMax(&sm.lenoff[f.p], f.best);
                     }
                     if (e0.best) atomicMax(&sm.lenoff[e0.p], e0.best);
                     if (sa > 1 && e1.best) atomicMax(&sm.lenoff[e1.p], e1.best);
