@@ -276,6 +276,7 @@ def measure_batch_format(ms, ctx, torch, fmt, each, count, steps, dev, peak, ran
 
     # plain Xpress: our encoder also writes the side-band restart index (one entry per 16 KiB of input), which lets the
     # decoder parse every segment on its own lane; without it a stream is one lane (reported as decode_ms_unindexed)
+    sizes_all = torch.zeros(world, dtype=torch.int64, device=dev)
     # Both formats: our encoder also leaves a side-band restart index (never part of the stream: the streams are byte for byte those
     # of the plain call and decode with the reference), which lets the decoder start inside a stream -- one lane per segment.
     # Without it a stream is one lane (reported as decode_ms_unindexed: the path a reference-made stream takes).
@@ -294,6 +295,8 @@ def measure_batch_format(ms, ctx, torch, fmt, each, count, steps, dev, peak, ran
             ctx.xpress_compress_indexed(d_in, d_comp, enc, seg_bytes, d_index, stride)
         else:
             ctx.xhuff_compress_indexed(d_in, d_comp, enc, d_index, d_ioff, d_nseg)
+        if dist is not None:                      # the sharded job's one exchange: every rank learns every rank's compressed size
+            ctx.sizes_allgather(c_len.sum(dtype=torch.int64).reshape(1), sizes_all)
         if ev:
             ev[1].record()
         if fmt == "xpress":
@@ -493,6 +496,11 @@ def run_gpu(args):
     ms.generate_batch_into(host.numpy(), BLOCK, nblocks, 42 + rank * nblocks, "text")
     d_in = host.to(dev, non_blocking=True)
     ctx = ms.GpuContext(local)
+    if dist is not None:
+        # the data-path exchange goes through the LIBRARY's multi-GPU entry (C ABI: mscomp_gpu_lznt1_compress_sharded = single-GPU
+        # pipeline + ncclAllGather on the compute stream, its own communicator); torch.distributed only carries the NCCL id and the timers
+        from importlib import import_module
+        ctx.comm_init(rank, world, import_module("mscompress_b200.sharding").torch_broadcaster(dist, dev))
     nchunks = U // 4096
     d_comp = torch.empty(U + 2 * nchunks + 64, dtype=torch.uint8, device=dev)
     d_off = torch.empty(nchunks + 1, dtype=torch.int64, device=dev)
@@ -504,15 +512,16 @@ def run_gpu(args):
     def step(events=None):
         if events:
             events[0].record()
-        ctx.lznt1_compress(d_in, d_comp, d_off, d_res_c)
+        if dist is not None:   # the single collective -- all-gather of the per-rank compressed sizes, inside the library call
+            ctx.lznt1_compress_sharded(d_in, d_comp, d_off, d_res_c, sizes_all)
+        else:
+            ctx.lznt1_compress(d_in, d_comp, d_off, d_res_c)
         if events:
             events[1].record()
         # the compressed stream stays resident; its length lives in d_off[nchunks] / d_res_c (the decoder takes the buffer bound)
         ctx.lznt1_decompress(d_comp, d_off, nchunks, d_out, d_res_d)
         if events:
             events[2].record()
-        if dist is not None:   # the single collective -- all-gather of the per-rank compressed sizes
-            dist.all_gather_into_tensor(sizes_all, d_off[nchunks:nchunks + 1])
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -634,7 +643,8 @@ def run_gpu(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": "LZNT1 encode+decode, %d MiB synthetic text stream as 4 KiB chunks per GPU (BASELINE.json configs[1])" % nblocks,
                    "chunks_per_gpu": nchunks, "compressed_ratio": C / U, "l2": "inputs larger than L2 (1 GiB in, %.2f GiB compressed, 126 MB L2); no flush needed" % (C / 2**30),
-                   "collective": "all_gather of per-rank compressed size (8 B/rank) per step" if world > 1 else "none (N=1)"},
+                   "collective": ("ncclAllGather of the per-rank compressed size (8 B/rank) per step, issued by mscomp_gpu_lznt1_compress_sharded on the "
+                                  "compute stream (%d collectives, communicator of %d ranks)" % (ctx.collectives(), ctx.comm_size())) if world > 1 else "none (N=1)"},
         "gpu_launches": launches,
         "encode_MBps": world * U / MB / (enc_ms / 1e3), "decode_MBps": world * U / MB / (dec_ms / 1e3),
         "encode_ms": enc_ms, "decode_ms": dec_ms,

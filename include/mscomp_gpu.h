@@ -152,5 +152,31 @@ MSCOMPAPI MSCompStatus mscomp_gpu_xpress_decompress_batch_indexed(mscomp_gpu_ctx
                                                                   const mscomp_gpu_batch* batch,
                                                                   const mscomp_gpu_xpress_seg* d_index, uint32_t index_stride);
 
+/* ---- several GPUs: one process (or thread) and one context per GPU ------------------------------------------------------- */
+/* The units of all three formats are independent, so a job over N GPUs is N single-GPU jobs on contiguous unit ranges plus ONE
+ * exchange -- every rank learns every rank's output sizes (an ncclAllGather on the context's stream, nothing else crosses
+ * NVLink).  NCCL is bound at run time (libnccl.so.2); single-GPU users need none.
+ *   mscomp_gpu_shard_range      the unit range of a rank: [floor(rank * units / nranks), floor((rank + 1) * units / nranks))
+ *   mscomp_gpu_comm_unique_id   rank 0 makes the 128-byte id and hands it to the other ranks by its own means (MPI, a file, a socket)
+ *   mscomp_gpu_comm_init        collective: every rank, with that id (ncclCommInitRank); the communicator belongs to the context
+ *   mscomp_gpu_comm_attach      instead: use an ncclComm_t the caller made (passed as void*); it is not destroyed with the context
+ *   mscomp_gpu_sizes_allgather  d_all[r * n_values + k] = rank r's d_mine[k] (device uint64 arrays; d_all holds nranks * n_values)
+ *   mscomp_gpu_lznt1_compress_sharded / mscomp_gpu_compress_batch_sharded: this rank's shard through the single-GPU path, then
+ *       d_sizes_all[r] = compressed bytes of rank r -- the global stream / batch is the ranks' parts in rank order. */
+#define MSCOMP_GPU_COMM_ID_BYTES 128
+MSCOMPAPI void         mscomp_gpu_shard_range(uint64_t units, uint32_t rank, uint32_t nranks, uint64_t* first, uint64_t* count);
+MSCOMPAPI MSCompStatus mscomp_gpu_comm_unique_id(void* id128);
+MSCOMPAPI MSCompStatus mscomp_gpu_comm_init(mscomp_gpu_ctx* ctx, const void* id128, uint32_t rank, uint32_t nranks);
+MSCOMPAPI MSCompStatus mscomp_gpu_comm_attach(mscomp_gpu_ctx* ctx, void* nccl_comm, uint32_t rank, uint32_t nranks);
+MSCOMPAPI void         mscomp_gpu_comm_release(mscomp_gpu_ctx* ctx);
+MSCOMPAPI uint32_t     mscomp_gpu_comm_rank(const mscomp_gpu_ctx* ctx);
+MSCOMPAPI uint32_t     mscomp_gpu_comm_size(const mscomp_gpu_ctx* ctx);
+MSCOMPAPI MSCompStatus mscomp_gpu_sizes_allgather(mscomp_gpu_ctx* ctx, const uint64_t* d_mine, uint32_t n_values, uint64_t* d_all);
+MSCOMPAPI uint64_t     mscomp_gpu_collectives(const mscomp_gpu_ctx* ctx);     /* NCCL collectives issued through this context */
+MSCOMPAPI MSCompStatus mscomp_gpu_lznt1_compress_sharded(mscomp_gpu_ctx* ctx, const uint8_t* d_in, size_t in_len, uint8_t* d_out, size_t out_cap,
+                                                         uint64_t* d_chunk_off, mscomp_gpu_result* d_result, uint64_t* d_sizes_all);
+MSCOMPAPI MSCompStatus mscomp_gpu_compress_batch_sharded(mscomp_gpu_ctx* ctx, int format, const uint8_t* d_in, uint8_t* d_out,
+                                                         const mscomp_gpu_batch* batch, uint64_t* d_my_total, uint64_t* d_sizes_all);
+
 EXTERN_C_END
 #endif

@@ -93,6 +93,17 @@ def lib():
         L.mscomp_gpu_xpress_huff_index_batch.restype, L.mscomp_gpu_xpress_huff_index_batch.argtypes = i32, [vp, vp, vp, vp, vp, vp]
         L.mscomp_gpu_xpress_huff_decompress_batch_indexed.restype = i32
         L.mscomp_gpu_xpress_huff_decompress_batch_indexed.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+        L.mscomp_gpu_shard_range.restype, L.mscomp_gpu_shard_range.argtypes = None, [u64, u32, u32, vp, vp]
+        L.mscomp_gpu_comm_unique_id.restype, L.mscomp_gpu_comm_unique_id.argtypes = i32, [vp]
+        L.mscomp_gpu_comm_init.restype, L.mscomp_gpu_comm_init.argtypes = i32, [vp, vp, u32, u32]
+        L.mscomp_gpu_comm_release.restype, L.mscomp_gpu_comm_release.argtypes = None, [vp]
+        L.mscomp_gpu_comm_size.restype, L.mscomp_gpu_comm_size.argtypes = u32, [vp]
+        L.mscomp_gpu_comm_rank.restype, L.mscomp_gpu_comm_rank.argtypes = u32, [vp]
+        L.mscomp_gpu_sizes_allgather.restype, L.mscomp_gpu_sizes_allgather.argtypes = i32, [vp, vp, u32, vp]
+        L.mscomp_gpu_collectives.restype, L.mscomp_gpu_collectives.argtypes = u64, [vp]
+        L.mscomp_gpu_lznt1_compress_sharded.restype = i32
+        L.mscomp_gpu_lznt1_compress_sharded.argtypes = [vp, vp, ctypes.c_size_t, vp, ctypes.c_size_t, vp, vp, vp]
+        L.mscomp_gpu_compress_batch_sharded.restype, L.mscomp_gpu_compress_batch_sharded.argtypes = i32, [vp, i32, vp, vp, vp, vp, vp]
         L.mscomp_gpu_xpress_huff_compress_batch_indexed.restype = i32
         L.mscomp_gpu_xpress_huff_compress_batch_indexed.argtypes = [vp, vp, vp, vp, vp, vp, vp]
         L.mscomp_gpu_xpress_huff_second_chances.restype, L.mscomp_gpu_xpress_huff_second_chances.argtypes = u64, [vp]
@@ -289,6 +300,40 @@ class GpuContext:
 
     def launches(self):
         return int(lib().mscomp_gpu_kernel_launches(self.handle))
+
+    # ---- several GPUs (include/mscomp_gpu.h "several GPUs"): the library's own NCCL communicator ----
+    def comm_init(self, rank, world, broadcast):
+        """Collective.  Rank 0 makes the 128-byte NCCL id; `broadcast(bytes_or_None) -> bytes` hands it to every rank (any
+        transport: torch.distributed, MPI, a file); then ncclCommInitRank inside the library."""
+        idbuf = ctypes.create_string_buffer(128)
+        if rank == 0:
+            st = lib().mscomp_gpu_comm_unique_id(ctypes.addressof(idbuf))
+            if st < 0:
+                raise MSCompError("mscomp_gpu_comm_unique_id", st)
+        got = broadcast(bytes(idbuf.raw) if rank == 0 else None)
+        idbuf = ctypes.create_string_buffer(bytes(got), 128)
+        st = lib().mscomp_gpu_comm_init(self.handle, ctypes.addressof(idbuf), rank, world)
+        if st < 0:
+            raise MSCompError("mscomp_gpu_comm_init", st)
+
+    def comm_size(self):
+        return int(lib().mscomp_gpu_comm_size(self.handle))
+
+    def collectives(self):
+        return int(lib().mscomp_gpu_collectives(self.handle))
+
+    def sizes_allgather(self, d_mine, d_all):
+        """d_all[r * n + k] = rank r's d_mine[k] (int64 / uint64 device tensors), one ncclAllGather on this context's stream."""
+        st = lib().mscomp_gpu_sizes_allgather(self.handle, d_mine.data_ptr(), d_mine.numel(), d_all.data_ptr())
+        if st < 0:
+            raise MSCompError("mscomp_gpu_sizes_allgather", st)
+
+    def lznt1_compress_sharded(self, d_in, d_out, d_chunk_off, d_result, d_sizes_all):
+        """This rank's shard of an LZNT1 stream through the single-GPU path + the all-gather of the per-rank compressed sizes."""
+        st = lib().mscomp_gpu_lznt1_compress_sharded(self.handle, d_in.data_ptr(), d_in.numel(), d_out.data_ptr(), d_out.numel(),
+                                                     d_chunk_off.data_ptr(), d_result.data_ptr(), d_sizes_all.data_ptr())
+        if st < 0:
+            raise MSCompError("mscomp_gpu_lznt1_compress_sharded", st)
 
     def profile(self, on=True):
         lib().mscomp_gpu_profile_enable(self.handle, 1 if on else 0)

@@ -18,7 +18,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared",
 ]
-CU_SOURCES = ["mscomp_gpu.cu", "mscomp_shim.cu", "mscomp_stream.cu"]
+CU_SOURCES = ["mscomp_gpu.cu", "mscomp_shim.cu", "mscomp_stream.cu", "mscomp_multi.cu"]
 
 
 def _newer(target, sources):

@@ -19,6 +19,10 @@ struct mscomp_gpu_ctx {
     cudaStream_t down_stream = nullptr;   // download stream: results leave while later slices are still being processed
     cudaEvent_t copy_ev[16] = {};         // upload events (ring)
     cudaEvent_t work_ev[16] = {};         // kernel-side events (ring)
+    void* comm = nullptr;            // ncclComm_t of the multi-GPU calls (mscomp_multi.cu); null = one GPU
+    bool comm_owned = false;
+    uint32_t comm_rank = 0, comm_size = 1;
+    uint64_t collectives = 0;        // NCCL collectives issued through this context
     void* pinned = nullptr;          // small pinned mailbox for results
     size_t pinned_cap = 0;
 

@@ -88,6 +88,7 @@ void mscomp_gpu_destroy(mscomp_gpu_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    mscomp_gpu_comm_release(ctx);
     for (int i = 0; i < SC_COUNT; ++i) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->pinned_big) cudaFreeHost(ctx->pinned_big);

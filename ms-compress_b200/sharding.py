@@ -26,3 +26,16 @@ def gather_sizes(local_total, device=None, group=None):
     dist.all_gather_into_tensor(sizes, local_total, group=group)
     host = sizes.cpu()
     return sizes, int(host[:rank].sum().item()), int(host.sum().item())
+
+
+def torch_broadcaster(dist, device):
+    """`broadcast` argument of GpuContext.comm_init over an initialised torch.distributed group (rank 0 is the source)."""
+    import torch
+
+    def broadcast(payload):
+        t = torch.zeros(128, dtype=torch.uint8, device=device)
+        if payload is not None:
+            t.copy_(torch.frombuffer(bytearray(payload), dtype=torch.uint8))
+        dist.broadcast(t, src=0)
+        return bytes(t.cpu().numpy().tobytes())
+    return broadcast

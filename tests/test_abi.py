@@ -108,3 +108,28 @@ def test_codec_calls_fail_loudly_without_a_gpu(ms):
         assert ms.raw_call(fmt + "_compress", data, 10000)[0] == -4
         assert ms.raw_call(fmt + "_decompress", data, 10000)[0] in (-4, -3, -5)      # (argument / header checks may come first)
     assert ms.raw_call("lznt1_decompress", b"\x00\xb0" + bytes(100), 4096)[0] == -4
+
+
+def test_shard_range_is_the_python_partition(ms):
+    """mscomp_gpu_shard_range (C ABI, no GPU needed) = mscompress_b200.sharding.partition: contiguous, covering, balanced."""
+    from importlib import import_module
+    sh = import_module("mscompress_b200.sharding")
+    L = ms.lib()
+    for units in (0, 1, 7, 8, 262144, 65536 * 3 + 5, 2 ** 40 + 123):
+        for world in (1, 2, 3, 4, 8):
+            total = 0
+            for rank in range(world):
+                first, count = ctypes.c_uint64(), ctypes.c_uint64()
+                L.mscomp_gpu_shard_range(ctypes.c_uint64(units), rank, world, ctypes.byref(first), ctypes.byref(count))
+                lo, hi = sh.partition(units, world, rank)
+                assert (first.value, first.value + count.value) == (lo, hi)
+                total += count.value
+            assert total == units
+
+
+def test_multi_gpu_calls_fail_cleanly_without_a_context(ms):
+    L = ms.lib()
+    buf = ctypes.create_string_buffer(128)
+    assert L.mscomp_gpu_comm_init(None, ctypes.addressof(buf), 0, 1) == ms.MSCOMP_ARG_ERROR
+    assert L.mscomp_gpu_sizes_allgather(None, None, 1, None) == ms.MSCOMP_ARG_ERROR
+    assert L.mscomp_gpu_comm_size(None) == 1 and L.mscomp_gpu_collectives(None) == 0
