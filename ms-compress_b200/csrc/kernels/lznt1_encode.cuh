@@ -50,6 +50,7 @@ struct Lznt1EncSmem {
     uint32_t rankcnt[256];                       // entries per rank (ranks >= 255 share the last bin)
     uint32_t M[132], V[128], F[128], K[128];     // match bitmap (+ zero sentinel), visited bitmap, flag bits (by item), visited matches
     uint32_t U[128];                             // heavy chunks: positions whose search is deferred to the parse
+    uint32_t C[128];                             // positions inside (not at the start of) a match the parse takes
     uint16_t nmw[132], pmw[128];                 // next non-zero word of M at or after w; previous non-zero word of K before w
     uint16_t prefV[128], prefVM[128];
     uint16_t goff[LZNT1_CHUNK / 8 + 8];          // byte offset of each group's flag byte
@@ -64,6 +65,16 @@ __device__ __forceinline__ uint32_t lz_load4(const uint8_t* s, int idx)
     return __funnelshift_r(w[0], w[1], 8 * (idx & 3));
 }
 __device__ __forceinline__ uint32_t lz_hash3(uint32_t x) { return ((x & 0xFFFFFFu) * 0x9E3779B1u) >> 20; }
+
+// A match the greedy parse takes at q covers positions q+1 .. q+len-1: they start no item.
+__device__ __forceinline__ void lze_cover(uint32_t* C, int q, int len)
+{
+    const int s = q + 1, e = q + len - 1;                                     // (len >= 3)
+    const int w0 = s >> 5, w1 = e >> 5;
+    const uint32_t m0 = 0xffffffffu << (s & 31), m1 = 0xffffffffu >> (31 - (e & 31));
+    if (w0 == w1) atomicOr(&C[w0], m0 & m1);
+    else { atomicOr(&C[w0], m0); for (int w = w0 + 1; w < w1; ++w) atomicOr(&C[w], 0xffffffffu); atomicOr(&C[w1], m1); }
+}
 
 // One position of a bucket in registers: its 16 bytes, the longest match the format can express there, the best key so far.
 struct LzeEnt { int p, ml; uint32_t k0, k1, k2, k3, best; };
@@ -128,7 +139,7 @@ lznt1_encode_kernel(const uint8_t* __restrict__ in, uint64_t in_len, uint32_t fi
         if (tid < 16) sm.in[LZNT1_CHUNK + tid] = 0;
         reinterpret_cast<uint4*>(sm.cnt)[tid] = make_uint4(0, 0, 0, 0);
         reinterpret_cast<uint4*>(sm.cnt)[tid + LZE_THREADS] = make_uint4(0, 0, 0, 0);
-        if (tid < 128) { sm.F[tid] = 0; sm.K[tid] = 0; sm.U[tid] = 0; }
+        if (tid < 128) { sm.F[tid] = 0; sm.C[tid] = 0; sm.U[tid] = 0; }
         sm.rankcnt[tid] = 0;
         __syncthreads();
 
@@ -160,21 +171,23 @@ lznt1_encode_kernel(const uint8_t* __restrict__ in, uint64_t in_len, uint32_t fi
         {
             uint4 q0 = reinterpret_cast<const uint4*>(sm.cnt)[2 * tid], q1 = reinterpret_cast<const uint4*>(sm.cnt)[2 * tid + 1];
             uint32_t wv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-            uint32_t sum = 0, my_pairs = 0, my_big = 0;
-            unsigned long long small = 0;            // single-tile buckets of size 2 | 3 << 16 | 4 << 32
+            uint32_t sum = 0, my_pairs = 0, my_big = 0, bigmask = 0, s2 = 0, s3 = 0, s4 = 0;
             unsigned long long tot = 0;              // tiles of size 2 | 3 << 16 | 4 << 32 | cross items << 48, large buckets only
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const uint32_t c = (wv[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
                 sum += c;
                 my_pairs += (c * (c - 1)) >> 1;
-                if (c >= 2 && c <= 4) small += 1ull << (16 * (c - 2));
-                if (c > 4) {
-                    const uint32_t T = (c + 3) >> 2, sl = c - 4 * (T - 1);
-                    ++my_big;
-                    tot += ((unsigned long long)(T - 1) << 32) + ((unsigned long long)((T * (T - 1)) >> 1) << 48) + (sl >= 2 ? 1ull << (16 * (sl - 2)) : 0ull);
-                }
+                s2 += c == 2 ? 1u : 0u; s3 += c == 3 ? 1u : 0u; s4 += c == 4 ? 1u : 0u;
+                bigmask |= c > 4 ? 1u << i : 0u;
             }
+            for (uint32_t bm = bigmask; bm; bm &= bm - 1) {                  // the few large buckets (counts still in cnt[])
+                const uint32_t c = sm.cnt[16 * tid + (__ffs((int)bm) - 1)];
+                const uint32_t T = (c + 3) >> 2, sl = c - 4 * (T - 1);
+                ++my_big;
+                tot += ((unsigned long long)(T - 1) << 32) + ((unsigned long long)((T * (T - 1)) >> 1) << 48) + (sl >= 2 ? 1ull << (16 * (sl - 2)) : 0ull);
+            }
+            const unsigned long long small = (unsigned long long)s2 | ((unsigned long long)s3 << 16) | ((unsigned long long)s4 << 32);   // single-tile buckets by size
             const int incl = warp_incl_scan((int)sum);
             unsigned long long incl_small = small;
 #pragma unroll
@@ -212,11 +225,18 @@ lznt1_encode_kernel(const uint8_t* __restrict__ in, uint64_t in_len, uint32_t fi
                     if (c == 2) items[o2++] = b;
                     if (c == 3) items[o3++] = b;
                     if (c == 4) items[o4++] = b;
-                    if (c > 4) sm.rankcnt[atomicAdd(&sm.nbig, 1u)] = b | (c << 12);      // (rankcnt[] is free on this path)
                 }
             }
+            const uint32_t run_end = run;
             reinterpret_cast<uint4*>(sm.cnt)[2 * tid] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
             reinterpret_cast<uint4*>(sm.cnt)[2 * tid + 1] = make_uint4(wv[4], wv[5], wv[6], wv[7]);
+            if (fast) {
+                for (uint32_t bm = bigmask; bm; bm &= bm - 1) {              // (my own stores to cnt[] above: begin offsets by now)
+                    const int i = __ffs((int)bm) - 1;
+                    const uint32_t b = sm.cnt[16 * tid + i], e = i < 15 ? (uint32_t)sm.cnt[16 * tid + i + 1] : run_end;
+                    sm.rankcnt[atomicAdd(&sm.nbig, 1u)] = b | ((e - b) << 12);    // (rankcnt[] is free on this path)
+                }
+            }
             __syncthreads();
             if (fast && (uint32_t)tid < nbig) {       // a large bucket: its tiles and tile pairs (places by atomics: the order inside a list is free)
                 const uint32_t e = sm.rankcnt[tid], b = e & 0xFFFu, c = e >> 12;
@@ -490,12 +510,14 @@ lznt1_encode_kernel(const uint8_t* __restrict__ in, uint64_t in_len, uint32_t fi
                 }
                 __syncthreads();
                 for (uint32_t k = tid; k < sm.nchain; k += LZE_THREADS) {                         // the three in between, in parallel
-                    int q = sm.chain[k];
-                    atomicOr(&sm.K[q >> 5], 1u << (q & 31));
-                    const int q2 = nxt2[q];
-                    q = cur[q];
-                    if (q < LZNT1_CHUNK) atomicOr(&sm.K[q >> 5], 1u << (q & 31));
-                    if (q2 < LZNT1_CHUNK) { atomicOr(&sm.K[q2 >> 5], 1u << (q2 & 31)); const int q3 = cur[q2]; if (q3 < LZNT1_CHUNK) atomicOr(&sm.K[q3 >> 5], 1u << (q3 & 31)); }
+                    const int q = sm.chain[k], q1 = cur[q], q2 = nxt2[q];
+                    lze_cover(sm.C, q, (int)(sm.lenoff[q] & 0xFFFF));
+                    if (q1 < LZNT1_CHUNK) lze_cover(sm.C, q1, (int)(sm.lenoff[q1] & 0xFFFF));
+                    if (q2 < LZNT1_CHUNK) {
+                        lze_cover(sm.C, q2, (int)(sm.lenoff[q2] & 0xFFFF));
+                        const int q3 = cur[q2];
+                        if (q3 < LZNT1_CHUNK) lze_cover(sm.C, q3, (int)(sm.lenoff[q3] & 0xFFFF));
+                    }
                 }
             } else if (warp == 0) {
                 // Heavy chunk: one warp walks the parse; a deferred position is searched when (and only if) it is reached.
@@ -554,37 +576,16 @@ lznt1_encode_kernel(const uint8_t* __restrict__ in, uint64_t in_len, uint32_t fi
                         }
                         __syncwarp();
                     }
-                    if (lo) { if (lane == 0) sm.K[q >> 5] |= 1u << (q & 31); p = q + (int)(lo & 0xFFFF); }
+                    if (lo) { if (lane == 0) lze_cover(sm.C, q, (int)(lo & 0xFFFF)); p = q + (int)(lo & 0xFFFF); }
                     else p = q + 1;
                 }
             }
             __syncthreads();
-            if (warp == 0) {   // pmw[w] = last word < w of K that is not zero (0xFFFF = none)
-                int pz[4], carry = -1;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { const int w = lane * 4 + i; pz[i] = carry; carry = sm.K[w] ? w : carry; }
-                int v = carry;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULL, v, d); if (lane >= d) v = max(v, t); }
-                int before = __shfl_up_sync(FULL, v, 1);
-                if (lane == 0) before = -1;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) sm.pmw[lane * 4 + i] = (uint16_t)max(pz[i], before);
-            }
-            __syncthreads();
-            // visited bitmap: a position is visited iff it is a visited match, or it is not covered by the last visited
-            // match at or before it (then it is a literal: there is no match between the end of a visited match and the
-            // next visited match).  A warp handles one bitmap word per iteration, so V needs no atomics.
-            for (int p = tid; p < LZNT1_CHUNK; p += LZE_THREADS) {
-                const int w = p >> 5;
-                const uint32_t below = sm.K[w] & (0xffffffffu >> (31 - lane));
-                int q = -1;
-                if (below) q = w * 32 + 31 - __clz((int)below);
-                else { const int w2 = (int)(int16_t)sm.pmw[w]; if (w2 >= 0) q = w2 * 32 + 31 - __clz((int)sm.K[w2]); }
-                bool vis = p < n;
-                if (q >= 0) vis = vis && (p == q || p >= q + (int)(sm.lenoff[q] & 0xFFFF));
-                const unsigned vv = __ballot_sync(FULL, vis);
-                if (lane == 0) sm.V[w] = vv;
+            // visited bitmap: every position of the chunk that is not inside a taken match starts an item
+            if (tid < 128) {
+                const int lo = 32 * tid;
+                const uint32_t inside = n >= lo + 32 ? 0xffffffffu : (n > lo ? (0xffffffffu >> (32 - (n - lo))) : 0u);
+                sm.V[tid] = ~sm.C[tid] & inside;
             }
         }
         __syncthreads();
