@@ -45,20 +45,16 @@ struct LzFrontSmem {
     uint32_t ntok;                     // tokens emitted so far in the unit
 };
 
-// 4 bytes at src[p] (little endian), bytes at or beyond n read as 0; src need not be aligned.
+// 4 bytes at src[p] (little endian); src need not be aligned.  Only bytes below n are meaningful: every caller either masks the
+// rest off (3-byte keys with p + 3 <= n) or stays below n (4-byte compare steps with i + 4 <= maxlen <= n - p).  Two aligned words
+// and a funnel shift, no branch; the second word is clamped to the last word that holds a byte of the unit, so nothing beyond the
+// unit's 4-byte granules is ever read.
 __device__ __forceinline__ uint32_t lzf_ld4(const uint8_t* __restrict__ src, uint32_t p, uint32_t n)
 {
-    if (p + 4 <= n) {
-        const uint8_t* a = src + p;
-        const uint32_t sh = (uint32_t)((uintptr_t)a & 3u);
-        const uint32_t* w = reinterpret_cast<const uint32_t*>(a - sh);
-        if (sh == 0) return __ldg(w);
-        // the second word holds at least one byte of [p, p+4): it exists
-        return __funnelshift_r(__ldg(w), __ldg(w + 1), 8 * sh);
-    }
-    uint32_t v = 0;
-    for (uint32_t i = 0; i < 4 && p + i < n; ++i) v |= (uint32_t)src[p + i] << (8 * i);
-    return v;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(src) + p;
+    const uintptr_t last = (reinterpret_cast<uintptr_t>(src) + n - 1) & ~static_cast<uintptr_t>(3);      // (loop invariant)
+    const uintptr_t w0 = a & ~static_cast<uintptr_t>(3), w1 = w0 + 4 <= last ? w0 + 4 : last;
+    return __funnelshift_r(__ldg(reinterpret_cast<const uint32_t*>(w0)), __ldg(reinterpret_cast<const uint32_t*>(w1)), 8 * (uint32_t)(a & 3));
 }
 __device__ __forceinline__ uint32_t lzf_hash3(uint32_t x) { return ((x & 0xFFFFFFu) * 0x9E3779B1u) >> (32 - LZF_HBITS); }
 

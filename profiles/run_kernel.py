@@ -58,13 +58,12 @@ else:
         if indexed:
             ctx.xpress_compress_indexed(d_in, d_comp, enc, seg_bytes, d_index, stride)
             ctx.xpress_decompress_indexed(d_comp, d_out, dec, d_index, stride)
-        else:
-            ctx.run_batch(fmt, "compress", d_in, d_comp, enc)
-            ctx.run_batch(fmt, "decompress", d_comp, d_out, dec)
-            if xh is not None:                     # the same decode from a kept index (walk once, decode again)
-                ctx.xhuff_index(d_comp, dec, *xh)
-                d_out.zero_()
-                ctx.xhuff_decompress_indexed(d_comp, d_out, dec, *xh)
+        else:                                      # Xpress-Huffman: the encoder writes the restart index, the decoder starts from it
+            ctx.xhuff_compress_indexed(d_in, d_comp, enc, *xh)
+            d_out.zero_()
+            ctx.xhuff_decompress_indexed(d_comp, d_out, dec, *xh)
+            if os.environ.get("RUN_UNINDEXED"):    # the index-free path (what a reference-made stream takes)
+                ctx.run_batch(fmt, "decompress", d_comp, d_out, dec)
     torch.cuda.synchronize()
     assert int(st1.abs().sum()) == 0 and int(st2.abs().sum()) == 0 and torch.equal(d_out, d_in)
     C = int(c_len.to(torch.int64).sum())
