@@ -159,7 +159,7 @@ __device__ __forceinline__ uint32_t xhe_reserved(uint32_t B) { return B ? 1 + ((
 
 // One block per buffer.  eos_mode 0: every buffer is its own stream (ends with the end-of-stream symbol);
 // eos_mode 1: the buffers are consecutive chunks of ONE stream -- only the last buffer of the batch carries it.
-__global__ void __launch_bounds__(XHE_THREADS)
+__global__ void __launch_bounds__(XHE_THREADS, 4)
 xhuff_encode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint32_t count,
                     const uint64_t* __restrict__ in_off, const uint32_t* __restrict__ in_len,
                     const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ out_cap,
