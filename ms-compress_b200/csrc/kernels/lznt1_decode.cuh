@@ -90,14 +90,15 @@ __device__ __forceinline__ void lzd_coop_copy(uint8_t* o, int pos, int off, int 
 }
 
 // Group length with the shift every token has at its own position, the group starting at gs (items in registers).
-template <bool ALL8>
-__device__ __forceinline__ int lzd_group_len(const uint32_t (&it)[8], unsigned f, int nit, int gs)
+// ONE: the round crosses at most one power of two (positions stay <= 2 * lim): the shift is S0 up to lim and S1 = S0 - 1 behind it.
+template <bool ALL8, bool ONE>
+__device__ __forceinline__ int lzd_group_len(const uint32_t (&it)[8], unsigned f, int nit, int gs, int S0, int S1, int lim)
 {
     int pos = gs;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         if (ALL8 || j < nit) {
-            const int Sj = lzd_token_shift(pos);
+            const int Sj = ONE ? (pos > lim ? S1 : S0) : lzd_token_shift(pos);
             const int l = (int)(it[j] & ((1u << Sj) - 1)) + 3;
             pos += ((f >> j) & 1) ? l : 1;
         }
@@ -107,8 +108,9 @@ __device__ __forceinline__ int lzd_group_len(const uint32_t (&it)[8], unsigned f
 }
 
 // Literals to the buffer, tokens to the match list; returns true if a token reaches back beyond the chunk start.
-template <bool ALL8, bool MIXED>
-__device__ __forceinline__ bool lzd_emit(const uint32_t (&it)[8], unsigned f, int nit, int gs, int S0, int li, uint8_t* buf, uint32_t* list)
+// MIXED: 0 = every token of the round has shift S0; 1 = one power of two is crossed (S0 up to lim, S1 behind it); 2 = any.
+template <bool ALL8, int MIXED>
+__device__ __forceinline__ bool lzd_emit(const uint32_t (&it)[8], unsigned f, int nit, int gs, int S0, int S1, int lim, int li, uint8_t* buf, uint32_t* list)
 {
     bool bad = false;
     int pos = gs;
@@ -117,7 +119,7 @@ __device__ __forceinline__ bool lzd_emit(const uint32_t (&it)[8], unsigned f, in
         if (ALL8 || j < nit) {
             const uint32_t t = it[j];
             const bool tk = (f >> j) & 1;
-            const int Sj = MIXED ? lzd_token_shift(pos) : S0;
+            const int Sj = MIXED == 2 ? lzd_token_shift(pos) : (MIXED == 1 ? (pos > lim ? S1 : S0) : S0);
             const int l = (int)(t & ((1u << Sj) - 1)) + 3, off = (int)(t >> Sj) + 1;
             bad |= tk && off > pos;                                          // :65 / :98
             if (tk) list[li] = t | ((uint32_t)pos << 16) | ((uint32_t)(Sj - 4) << 28);
@@ -189,14 +191,16 @@ __device__ __forceinline__ int lznt1_decode_payload(Lznt1WarpSmem& sm, const int
         int glen = A < LZNT1_CHUNK + 1 ? A : LZNT1_CHUNK + 1;
         int incl = warp_incl_scan(glen | (ntk << 20));
         int gs = P + (incl & 0xFFFFF) - glen;
-        bool mixed = false;
+        int mixed = 0;
+        const int S1 = S0 > 4 ? S0 - 1 : 4;
         if (__any_sync(FULL, lastA >= 0 && gs + lastA > lim)) {
-            mixed = true;
             // Positions taken under S0 can only be too large.  If even they stay within the next power of two, every token
             // behind the crossing has shift S0 - 1 at its tentative and at its true position alike: one pass settles the round.
             const bool single = P + (__shfl_sync(FULL, incl, 31) & 0xFFFFF) <= 2 * lim;
+            mixed = single ? 1 : 2;
             for (int iter = 0; iter < 34; ++iter) {
-                const int g2 = all8 ? lzd_group_len<true>(it, f, nit, gs) : lzd_group_len<false>(it, f, nit, gs);
+                const int g2 = single ? (all8 ? lzd_group_len<true, true>(it, f, nit, gs, S0, S1, lim) : lzd_group_len<false, true>(it, f, nit, gs, S0, S1, lim))
+                                      : (all8 ? lzd_group_len<true, false>(it, f, nit, gs, S0, S1, lim) : lzd_group_len<false, false>(it, f, nit, gs, S0, S1, lim));
                 const bool moved = g2 != glen;
                 glen = g2;
                 incl = warp_incl_scan(glen | (ntk << 20));
@@ -213,8 +217,10 @@ __device__ __forceinline__ int lznt1_decode_payload(Lznt1WarpSmem& sm, const int
         // ---- 4. literals out, tokens to the list -----------------------------------------------------------------
         const int li = (incl >> 20) - ntk;
         bool bad;
-        if (all8) bad = mixed ? lzd_emit<true, true>(it, f, nit, gs, S0, li, buf, sm.list) : lzd_emit<true, false>(it, f, nit, gs, S0, li, buf, sm.list);
-        else bad = mixed ? lzd_emit<false, true>(it, f, nit, gs, S0, li, buf, sm.list) : lzd_emit<false, false>(it, f, nit, gs, S0, li, buf, sm.list);
+        if (all8) bad = mixed == 0 ? lzd_emit<true, 0>(it, f, nit, gs, S0, S1, lim, li, buf, sm.list)
+                      : (mixed == 1 ? lzd_emit<true, 1>(it, f, nit, gs, S0, S1, lim, li, buf, sm.list) : lzd_emit<true, 2>(it, f, nit, gs, S0, S1, lim, li, buf, sm.list));
+        else bad = mixed == 0 ? lzd_emit<false, 0>(it, f, nit, gs, S0, S1, lim, li, buf, sm.list)
+                 : (mixed == 1 ? lzd_emit<false, 1>(it, f, nit, gs, S0, S1, lim, li, buf, sm.list) : lzd_emit<false, 2>(it, f, nit, gs, S0, S1, lim, li, buf, sm.list));
         if (__any_sync(FULL, bad)) return ST_DATA;
         __syncwarp();
 
