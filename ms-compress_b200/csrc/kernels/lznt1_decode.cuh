@@ -225,36 +225,23 @@ __device__ __forceinline__ int lznt1_decode_payload(Lznt1WarpSmem& sm, const int
         __syncwarp();
 
         // ---- 5. matches --------------------------------------------------------------------------------------------
-        // The list is in position order.  A pending match may run when its whole source lies below the LOWEST pending match
-        // (everything below that is final: literals are in, earlier matches are done) -- in waves: each wave runs every such
-        // match, one per lane, and the lowest pending one always qualifies unless it is a run or long, which the whole warp copies.
         for (int base = 0; base < nm; base += 32) {
             const bool have = base + lane < nm;
             const uint32_t e = have ? sm.list[base + lane] : 0u;
             const int Sj = (int)(e >> 28) + 4, pos = (int)(e >> 16) & 0xFFF, t = (int)(e & 0xFFFFu);
             const int len = (t & ((1 << Sj) - 1)) + 3, off = (t >> Sj) + 1, src = pos - off;
-            const bool small = have && len <= LZD_BULK_LEN && off >= len;
-            unsigned pending = __ballot_sync(FULL, have);
-            while (pending) {
-                const int lo = __ffs((int)pending) - 1;
-                const int W = __shfl_sync(FULL, pos, lo);
-                const bool now = small && ((pending >> lane) & 1u) && src + len <= W;
-                if (now) {
-                    const uint32_t b0 = buf[src], b1 = buf[src + 1], b2 = buf[src + 2];
-                    buf[pos] = (uint8_t)b0; buf[pos + 1] = (uint8_t)b1; buf[pos + 2] = (uint8_t)b2;
-                    for (int i = 3; i < len; i += 2) {
-                        const uint32_t c0 = buf[src + i], c1 = i + 1 < len ? buf[src + i + 1] : 0u;
-                        buf[pos + i] = (uint8_t)c0;
-                        if (i + 1 < len) buf[pos + i + 1] = (uint8_t)c1;
-                    }
-                }
-                unsigned done = __ballot_sync(FULL, now);
-                if (!((done >> lo) & 1u)) {                                  // a run or a long match: by the whole warp, in order
-                    lzd_coop_copy(buf, W, __shfl_sync(FULL, off, lo), __shfl_sync(FULL, len, lo));
-                    done |= 1u << lo;
-                }
-                __syncwarp();
-                pending &= ~done;
+            const int W0 = __shfl_sync(FULL, pos, 0);                        // everything below the batch's first match is final
+            const bool now = have && len <= LZD_BULK_LEN && off >= len && src + len <= W0;
+            if (now) {
+                buf[pos] = buf[src]; buf[pos + 1] = buf[src + 1]; buf[pos + 2] = buf[src + 2];
+                for (int i = 3; i < len; ++i) buf[pos + i] = buf[src + i];
+            }
+            __syncwarp();
+            unsigned rest = __ballot_sync(FULL, have && !now);
+            while (rest) {
+                const int o = __ffs((int)rest) - 1;
+                rest &= rest - 1;
+                lzd_coop_copy(buf, __shfl_sync(FULL, pos, o), __shfl_sync(FULL, off, o), __shfl_sync(FULL, len, o));
             }
         }
         P = Pend;
