@@ -54,7 +54,7 @@ def test_decode_parity_and_encode_roundtrip(ms, oracle, fmt, kind):
         if len(comp) > 1:
             assert ms.raw_call(fmt + "_compress", plain, len(comp) - 1)[0] == ms.MSCOMP_BUF_ERROR
         if kind == "text" and n >= 65536:
-            assert len(comp) <= 1.20 * len(ref_comp), (kind, n, len(comp), len(ref_comp))
+            assert len(comp) <= 1.12 * len(ref_comp), (kind, n, len(comp), len(ref_comp))
 
 
 @pytest.mark.parametrize("fmt", FMTS)
