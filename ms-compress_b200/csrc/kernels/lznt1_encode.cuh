@@ -77,7 +77,7 @@ __device__ __forceinline__ void lze_cover(uint32_t* C, int q, int len)
 }
 
 // One position of a bucket in registers: its 16 bytes, the longest match the format can express there, the best key so far.
-struct LzeEnt { int p, ml; uint32_t k0, k1, k2, k3, best; };
+struct LzeEnt { int p, room; uint32_t k0, k1, k2, k3, best; };          // room = bytes from p to the end of the chunk
 __device__ __forceinline__ void lze_load(LzeEnt& e, const Lznt1EncSmem& sm, int idx, int n)
 {
     e.p = sm.sorted[idx];
@@ -85,9 +85,7 @@ __device__ __forceinline__ void lze_load(LzeEnt& e, const Lznt1EncSmem& sm, int 
     const uint32_t sh = 8u * ((uint32_t)e.p & 3u);
     const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];     // (in[] is zero padded by 16 bytes)
     e.k0 = __funnelshift_r(w0, w1, sh); e.k1 = __funnelshift_r(w1, w2, sh); e.k2 = __funnelshift_r(w2, w3, sh); e.k3 = __funnelshift_r(w3, w4, sh);
-    int S, lim;
-    lznt1_shift_limit(e.p, S, lim);
-    e.ml = min(n - e.p, (1 << S) + 2);                                        // mask3 (src/lznt1_compress.cpp:51,:66)
+    e.room = n - e.p;
     e.best = 0;
 }
 // Common prefix of two positions of a bucket (16 bytes without a branch, the rare rest from shared memory), credited to the later one.
@@ -100,15 +98,21 @@ __device__ __forceinline__ void lze_pair(LzeEnt& x, LzeEnt& y, const Lznt1EncSme
     if (!w) { w = x.k3 ^ y.k3; l = 12; }
     l = w ? l + ((__ffs((int)w) - 1) >> 3) : 16;
     const bool x_later = x.p > y.p;
-    const int ml = x_later ? x.ml : y.ml;
-    if (l == 16 && ml > 16) {
+    const int room = x_later ? x.room : y.room;
+    // max_len(p) = min(room, (1 << S(p)) + 2) (mask3, src/lznt1_compress.cpp:51,:66) is at least min(room, 18): the format's
+    // cap only matters once 16 bytes have matched
+    if (l == 16 && room > 16) {
+        int S, lim;
+        lznt1_shift_limit(x_later ? x.p : y.p, S, lim);
+        const int ml = min(room, (1 << S) + 2);
         while (l < ml) {
             const uint32_t d = lz_load4(sm.in, x.p + l) ^ lz_load4(sm.in, y.p + l);
             if (d) { l += (__ffs((int)d) - 1) >> 3; break; }
             l += 4;
         }
+        l = min(l, ml);
     }
-    l = min(l, ml);
+    l = min(l, room);
     const uint32_t key = l >= 3 ? ((uint32_t)l << 12) | (uint32_t)(4095 - (x_later ? y.p : x.p)) : 0u;
     x.best = max(x.best, x_later ? key : 0u);
     y.best = max(y.best, x_later ? 0u : key);
