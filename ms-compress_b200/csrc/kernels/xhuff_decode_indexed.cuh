@@ -428,11 +428,16 @@ xhuff_decode_indexed_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict_
                         if (fa + len > 16u) w2 = ldcg_u64(w + 2);
                     }
                     if (len && !off && !wide) O.ring[rp] = (uint8_t)hi;
-                    uint8_t* d = O.ring + rp;
-                    if (now && !far) {
-                        // sources inside the window: four bytes per step, loads before stores (source and destination never overlap here);
-                        // the far lanes' global loads are in flight meanwhile
-                        const uint8_t* q = O.ring + rs;
+                    const uint8_t* q = O.ring + rs;
+                    if (now && far) {
+                        unsigned long long* f = reinterpret_cast<unsigned long long*>(sm.slot + 48 * lane);
+                        f[0] = w0; f[1] = w1; f[2] = w2;
+                        q = sm.slot + 48 * lane + fa;
+                    }
+                    if (now) {
+                        // four bytes per step, loads before stores (source and destination never overlap here): the steps' shared-memory
+                        // round trips overlap instead of queueing up behind one another
+                        uint8_t* d = O.ring + rp;
                         for (uint32_t i = 0; i < len; i += 4) {
                             const uint32_t b0 = q[i], b1 = i + 1 < len ? q[i + 1] : 0u, b2 = i + 2 < len ? q[i + 2] : 0u, b3 = i + 3 < len ? q[i + 3] : 0u;
                             d[i] = (uint8_t)b0;
@@ -440,15 +445,6 @@ xhuff_decode_indexed_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict_
                             if (i + 2 < len) d[i + 2] = (uint8_t)b2;
                             if (i + 3 < len) d[i + 3] = (uint8_t)b3;
                         }
-                    }
-                    if (now && far) {
-                        // far sources: the wanted bytes [fa, fa + len) straight out of the three words (no staging in shared memory)
-                        const uint32_t sh = 8u * fa;
-                        const unsigned long long v0 = sh ? (w0 >> sh) | (w1 << (64u - sh)) : w0;
-                        const unsigned long long v1 = sh ? (w1 >> sh) | (w2 << (64u - sh)) : w1;
-#pragma unroll
-                        for (uint32_t i = 0; i < (uint32_t)XHX_BULK_LEN; ++i)
-                            if (i < len) d[i] = (uint8_t)((i < 8u ? v0 : v1) >> (8u * (i & 7u)));
                     }
                     __syncwarp();
                     unsigned rest = __ballot_sync(FULL, (match && !now) || (wide && len != 0));
