@@ -53,8 +53,11 @@ struct XhLane {
     uint32_t nused;                      // symbols with a code (ranks >= nused are invalid)
     // progress
     uint32_t chunk_end;
-    int status;                          // 0 running, 1 finished OK, <0 error
+    int status;                          // 0 running, 1 finished OK, 2 (speculative mode) this chunk is complete, <0 error
     bool need_table;
+    // speculative single-chunk mode (xhuff_chunks.cuh): the lane starts at a candidate chunk start with its output position at 0
+    bool spec;
+    uint32_t reach;                      // how far the chunk's matches reach back before its own first byte (0: self-contained)
 };
 
 __device__ __forceinline__ uint32_t xh_rd16(XhLane& L, uint32_t at) { return L.win.get32(at) & 0xFFFFu; }
@@ -183,6 +186,7 @@ __device__ __forceinline__ void xh_step(XhLane& L, XhWarpSmem& sm, int lane, Sin
         XhLane T = L;                                            // trial decode of an end-of-stream symbol
         const uint32_t s2 = xh_decode_symbol(T, sm, lane);
         if (s2 == (uint32_t)XH_EOS && T.in_len - T.ip == 0 && xh_mask_is_zero(T)) { L.status = 1; return; }
+        if (L.spec) { L.status = 2; return; }                    // the next chunk (table at L.ip) is another lane's
         L.need_table = true;
         return;
     }
@@ -214,7 +218,10 @@ __device__ __forceinline__ void xh_step(XhLane& L, XhWarpSmem& sm, int lane, Sin
     if (off_bits > L.bits) { L.status = ST_DATA; return; }
     const uint32_t off = xh_peek(L, off_bits) + (1u << off_bits);
     if (off_bits) xh_skip(L, off_bits);
-    if (is_match && O.opos < off) { L.status = ST_DATA; return; }        // :113
+    if (is_match && O.opos < off) {                                      // :113
+        if (!L.spec) { L.status = ST_DATA; return; }
+        L.reach = max(L.reach, off - O.opos);                            // (whether that much output precedes the chunk is the stitcher's call)
+    }
     if (L.cap - O.opos < len) { L.status = ST_BUF; return; }             // :114 (and :87 for a literal)
     O.emit(is_match, sym, off, len);
 }
@@ -228,7 +235,8 @@ __device__ __forceinline__ void xhuff_decode_body(const uint8_t* __restrict__ in
                                                   const uint64_t* __restrict__ in_off, const uint32_t* __restrict__ in_len,
                                                   const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ out_cap,
                                                   uint32_t* __restrict__ out_len, int32_t* __restrict__ status, uint32_t* __restrict__ ntok,
-                                                  int only_status = 0, unsigned long long* __restrict__ handled = nullptr)
+                                                  int only_status = 0, unsigned long long* __restrict__ handled = nullptr,
+                                                  uint32_t* __restrict__ end_ip = nullptr, uint32_t* __restrict__ reach = nullptr)
 {
     MSC_DYN_SMEM(smem_raw);
     XhWarpSmem& sm = reinterpret_cast<XhWarpSmem*>(smem_raw)[threadIdx.x >> 5];
@@ -243,6 +251,7 @@ __device__ __forceinline__ void xhuff_decode_body(const uint8_t* __restrict__ in
         XhLane L;
         L.status = 1; L.in = in; L.in_len = 0; L.cap = 0; L.ip = 0; L.nused = 0;
         L.mask = 0; L.bits = 0; L.chunk_end = 0; L.need_table = true;
+        L.spec = end_ip != nullptr; L.reach = 0;
 #pragma unroll
         for (int k = 0; k < 15; ++k) L.lims[k] = 0x8000u;
 #pragma unroll
@@ -258,7 +267,11 @@ __device__ __forceinline__ void xhuff_decode_body(const uint8_t* __restrict__ in
             if (L.status == 0) xh_step(L, sm, lane, O);
         }
         O.finish();
-        if (mine) { out_len[i] = O.opos; status[i] = L.status == 1 ? ST_OK : L.status; sink_count(O, ntok, i); }
+        if (mine) {
+            out_len[i] = O.opos; sink_count(O, ntok, i);
+            if (end_ip) { status[i] = L.status == 1 ? 0 : (L.status == 2 ? 1 : L.status); end_ip[i] = L.ip; reach[i] = L.reach; }   // 0 stream ends here, 1 chunk complete
+            else status[i] = L.status == 1 ? ST_OK : L.status;
+        }
     }
 }
 
@@ -288,6 +301,19 @@ xhuff_parse_kernel(const uint8_t* __restrict__ in, uint32_t* __restrict__ tok, u
                    uint32_t* __restrict__ out_len, int32_t* __restrict__ status, uint32_t* __restrict__ ntok)
 {
     xhuff_decode_body<LaneTok>(in, nullptr, tok, count, in_off, in_len, out_off, out_cap, out_len, status, ntok);
+}
+
+// Speculative mode: buffer i starts at a candidate chunk start; the lane parses ONE chunk into tokens (xhuff_chunks.cuh).
+// status[i]: 0 the stream ends inside / right after this chunk, 1 the chunk is complete and another table follows at end_ip[i]
+// (relative to the buffer), < 0 not a decodable chunk.
+__global__ void __launch_bounds__(32 * XHD_WARPS_PER_BLOCK)
+xhuff_parse_chunks_kernel(const uint8_t* __restrict__ in, uint32_t* __restrict__ tok, uint32_t count,
+                          const uint64_t* __restrict__ in_off, const uint32_t* __restrict__ in_len,
+                          const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ out_cap,
+                          uint32_t* __restrict__ out_len, int32_t* __restrict__ status, uint32_t* __restrict__ ntok,
+                          uint32_t* __restrict__ end_ip, uint32_t* __restrict__ reach)
+{
+    xhuff_decode_body<LaneTok>(in, nullptr, tok, count, in_off, in_len, out_off, out_cap, out_len, status, ntok, 0, nullptr, end_ip, reach);
 }
 
 } // namespace msc

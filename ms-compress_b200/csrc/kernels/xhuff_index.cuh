@@ -80,7 +80,7 @@ xhuff_index_kernel(const uint8_t* __restrict__ in, uint32_t count, const uint64_
         const uint32_t i = g * 32 + lane;
         XhLane L;
         L.status = 1; L.in = in; L.in_len = 0; L.cap = 0; L.ip = 0; L.nused = 0;
-        L.mask = 0; L.bits = 0; L.chunk_end = 0; L.need_table = true;
+        L.mask = 0; L.bits = 0; L.chunk_end = 0; L.need_table = true; L.spec = false; L.reach = 0;
 #pragma unroll
         for (int k = 0; k < 15; ++k) L.lims[k] = 0x8000u;
 #pragma unroll

@@ -11,10 +11,13 @@
 #include "kernels/xhuff_decode.cuh"
 #include "kernels/xhuff_index.cuh"
 #include "kernels/xhuff_decode_indexed.cuh"
+#include "kernels/xhuff_chunks.cuh"
 #include "kernels/xpress_decode.cuh"
 #include "kernels/xhuff_encode.cuh"
 #include "kernels/xpress_encode.cuh"
 #include <new>
+#include <algorithm>
+#include <vector>
 
 using namespace msc;
 
@@ -498,6 +501,123 @@ MSCompStatus mscomp_gpu_xpress_huff_decompress_batch(mscomp_gpu_ctx* ctx, const 
     MSC_LAUNCH_SMEM(ctx, xhuff_decode_kernel, xhd_grid(ctx, b->count), 32 * XHD_WARPS_PER_BLOCK, XHD_SMEM_BYTES,
                     d_in, d_out, b->count, b->d_in_off, b->d_in_len, b->d_out_off, b->d_out_cap, b->d_out_len, b->d_status);
     return msc_cuda_status(cudaGetLastError(), "xpress_huff_decompress");
+}
+
+// ---- one multi-chunk Xpress-Huffman stream: chunk-parallel parse (kernels/xhuff_chunks.cuh) --------------------------------
+// d_in[0..in_len) is the stream, d_out has room for `cap` bytes.  *handled = true: the stream was decoded, *total bytes produced,
+// status OK.  *handled = false: this path does not apply (one chunk, an incomplete code, a damaged stream, too little room or
+// memory ...) and nothing is promised about d_out -- the caller runs the serial decoder, which owns the status codes.
+MSCompStatus msc_xhuff_stream_decode(mscomp_gpu_ctx* ctx, const uint8_t* d_in, uint32_t in_len, uint8_t* d_out, uint64_t cap, uint64_t* total, bool* handled)
+{
+    *handled = false;
+    if (!ctx || in_len < 2 * (uint32_t)XH_MIN_DATA) return MSCOMP_OK;
+    cudaSetDevice(ctx->device);
+    // 1. candidate chunk starts
+    const uint32_t capc = in_len / (uint32_t)XH_MIN_DATA + 2;
+    uint32_t* d_cand = (uint32_t*)ctx->get(SC_AUX0, ((size_t)capc + 2) * sizeof(uint32_t));
+    uint32_t* h_small = (uint32_t*)ctx->get_pinned(256);
+    if (!d_cand || !h_small) return MSCOMP_OK;
+    cudaMemsetAsync(d_cand + capc, 0, sizeof(uint32_t), ctx->stream);
+    const uint32_t cblocks = (in_len + XHS_POS_PER_BLOCK - 1) / XHS_POS_PER_BLOCK, cmax = (uint32_t)ctx->sm_count * 8;
+    MSC_LAUNCH(ctx, xhs_candidates_kernel, cblocks < cmax ? cblocks : cmax, XHS_THREADS, d_in, in_len, d_cand, d_cand + capc, capc);
+    cudaMemcpyAsync(h_small + 32, d_cand + capc, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cudaGetLastError(); return MSCOMP_OK; }
+    const uint32_t ncand = h_small[32];
+    if (ncand < 2 || ncand > capc) return MSCOMP_OK;
+    std::vector<uint32_t> cand(ncand);
+    cudaMemcpyAsync(cand.data(), d_cand, (size_t)ncand * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cudaGetLastError(); return MSCOMP_OK; }
+    std::sort(cand.begin(), cand.end());
+    if (cand[0] != 0) return MSCOMP_OK;
+    // 2. one lane per candidate parses one chunk into tokens.  A lone lane is latency-bound, so the candidates are spread over as
+    //    many warps as the GPU holds (stride - 1 empty streams between two of them) instead of being packed 32 to a warp.
+    const uint32_t warps_avail = (uint32_t)ctx->sm_count * 2 * XHD_WARPS_PER_BLOCK;
+    uint32_t per_warp = (ncand + warps_avail - 1) / warps_avail;
+    uint32_t stride = 32;
+    while (stride > 1 && 32 / stride < per_warp) stride >>= 1;
+    const uint64_t count64 = (uint64_t)ncand * stride;
+    const uint64_t tok_bytes = (uint64_t)ncand * XH_CHUNK * sizeof(uint32_t);
+    if (count64 > 0x7FFFFFFFull) return MSCOMP_OK;
+    {
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        if (tok_bytes + 64 > ctx->scratch_cap[SC_AUX2] && tok_bytes > (uint64_t)free_b / 2 + ctx->scratch_cap[SC_AUX2]) return MSCOMP_OK;
+    }
+    const uint32_t count = (uint32_t)count64;
+    // descriptor block: in_off[count] out_off[count] (u64) | in_len out_cap out_len status ntok end_ip reach [count] (u32)
+    const size_t desc_bytes = (size_t)count * (8 + 8 + 7 * 4);
+    uint8_t* d_desc = (uint8_t*)ctx->get(SC_AUX1, desc_bytes + 64);
+    uint8_t* h_desc = (uint8_t*)ctx->get_pinned_big(desc_bytes + 64);
+    uint32_t* d_tok = (uint32_t*)ctx->get(SC_AUX2, tok_bytes + 64);
+    if (!d_desc || !h_desc || !d_tok) return MSCOMP_OK;
+    uint64_t* h_in_off = (uint64_t*)h_desc; uint64_t* h_out_off = h_in_off + count;
+    uint32_t* h_u32 = (uint32_t*)(h_out_off + count);
+    uint32_t *h_in_len = h_u32, *h_out_cap = h_u32 + count, *h_out_len = h_u32 + 2 * (size_t)count, *h_ntok = h_u32 + 4 * (size_t)count,
+             *h_end = h_u32 + 5 * (size_t)count, *h_reach = h_u32 + 6 * (size_t)count;
+    int32_t* h_status = (int32_t*)(h_u32 + 3 * (size_t)count);
+    memset(h_desc, 0, desc_bytes);
+    for (uint32_t k = 0; k < ncand; ++k) {
+        const size_t i = (size_t)k * stride;
+        h_in_off[i] = cand[k]; h_in_len[i] = in_len - cand[k]; h_out_off[i] = (uint64_t)k * XH_CHUNK; h_out_cap[i] = XH_CHUNK;
+    }
+    cudaMemcpyAsync(d_desc, h_desc, desc_bytes, cudaMemcpyHostToDevice, ctx->stream);
+    const uint64_t* d_in_off = (const uint64_t*)d_desc; const uint64_t* d_out_off = d_in_off + count;
+    uint32_t* d_u32 = (uint32_t*)(d_out_off + count);
+    MSC_OPT_IN_SMEM(xhuff_parse_chunks_kernel, XHD_SMEM_BYTES);
+    MSC_LAUNCH_SMEM(ctx, xhuff_parse_chunks_kernel, xhd_grid(ctx, count), 32 * XHD_WARPS_PER_BLOCK, XHD_SMEM_BYTES,
+                    d_in, d_tok, count, d_in_off, (const uint32_t*)d_u32, d_out_off, (const uint32_t*)(d_u32 + count),
+                    d_u32 + 2 * (size_t)count, (int32_t*)(d_u32 + 3 * (size_t)count), d_u32 + 4 * (size_t)count, d_u32 + 5 * (size_t)count,
+                    d_u32 + 6 * (size_t)count);
+    cudaMemcpyAsync(h_out_len, d_u32 + 2 * (size_t)count, (size_t)count * 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cudaGetLastError(); return MSCOMP_OK; }
+    // 3. stitch the chain from offset 0
+    std::vector<uint32_t> chain;                     // candidate numbers in stream order
+    std::vector<uint32_t> pos;                       // output position of each chunk
+    uint64_t produced = 0;
+    uint32_t at = 0;                                 // stream offset of the chunk being linked
+    bool ok = false, independent = true;
+    for (;;) {
+        const auto it = std::lower_bound(cand.begin(), cand.end(), at);
+        if (it == cand.end() || *it != at) break;
+        const uint32_t k = (uint32_t)(it - cand.begin());
+        const size_t i = (size_t)k * stride;
+        if (h_status[i] < 0 || (uint64_t)h_reach[i] > produced || produced > 0xFFFFFFFFull - XH_CHUNK) break;
+        if (h_reach[i]) independent = false;
+        chain.push_back(k); pos.push_back((uint32_t)produced);
+        produced += h_out_len[i];
+        if (h_status[i] == 0) { ok = true; break; }                              // the stream ended inside this chunk (:83)
+        const uint64_t next = (uint64_t)at + h_end[i];
+        if (next == in_len) { ok = true; break; }                                // a finished chunk at the end of the input (:145-149)
+        if (next > in_len || in_len - next < (uint64_t)XH_MIN_DATA || h_out_len[i] == 0) break;
+        at = (uint32_t)next;
+    }
+    if (!ok || produced > cap) return MSCOMP_OK;
+    // 4. execute the tokens
+    const size_t nch = chain.size();
+    {
+        const size_t cb = nch * (8 + 4 + 4);
+        uint8_t* d_ch = (uint8_t*)ctx->get(SC_OFFS, cb + 64);
+        if (!d_ch) return MSCOMP_OK;
+        std::vector<uint32_t> nt(nch);
+        for (size_t j = 0; j < nch; ++j) nt[j] = h_ntok[(size_t)chain[j] * stride];
+        uint64_t* h_slot = (uint64_t*)h_desc;                                     // (the descriptors are not needed any more)
+        uint32_t* h_nt = (uint32_t*)(h_slot + nch); uint32_t* h_pos = h_nt + nch;
+        for (size_t j = 0; j < nch; ++j) { h_slot[j] = (uint64_t)chain[j] * XH_CHUNK; h_nt[j] = nt[j]; h_pos[j] = pos[j]; }
+        cudaMemcpyAsync(d_ch, h_desc, cb, cudaMemcpyHostToDevice, ctx->stream);
+        if (independent) {                                                        // every chunk on its own warp
+            const uint32_t ab = ((uint32_t)nch + LZA_WARPS_PER_BLOCK - 1) / LZA_WARPS_PER_BLOCK, acap = (uint32_t)ctx->sm_count * 16;
+            MSC_LAUNCH(ctx, xhs_apply_chunks_kernel, ab < acap ? ab : acap, 32 * LZA_WARPS_PER_BLOCK, (const uint32_t*)d_tok, (const uint64_t*)d_ch,
+                       (const uint32_t*)(d_ch + nch * 8), (const uint32_t*)(d_ch + nch * 12), (uint32_t)nch, d_out);
+        } else {                                                                  // matches reach across chunk starts: in stream order, one block
+            MSC_LAUNCH(ctx, xhs_apply_chain_kernel, 1, 32 * LZB_WARPS, (const uint32_t*)d_tok, (const uint64_t*)d_ch, (const uint32_t*)(d_ch + nch * 8),
+                       (const uint32_t*)(d_ch + nch * 12), (uint32_t)nch, d_out);
+        }
+    }
+    const MSCompStatus st = msc_cuda_status(cudaGetLastError(), "xpress_huff_decompress");
+    if (st != MSCOMP_OK) return st;
+    *total = produced;
+    *handled = true;
+    return MSCOMP_OK;
 }
 
 // Plain Xpress encode of a batch; seg_tiles / index / stride describe the optional restart index.  Large buffers take the two-pass

@@ -458,7 +458,32 @@ extern "C" MSCompStatus xpress_decompress(const_bytes in, size_t in_len, bytes o
     return one_buffer(mscomp_gpu_xpress_decompress_batch, "xpress_decompress", in, in_len, out, out_len, out_len ? *out_len : 0);
 }
 extern "C" MSCompStatus xpress_huff_decompress(const_bytes in, size_t in_len, bytes out, size_t* out_len)
-{   // a multi-chunk stream is a serial chain (chunk lengths are implicit, matches cross chunks): one lane walks it
+{
+    if (!out_len || (!in && in_len) || (!out && *out_len)) return MSCOMP_ARG_ERROR;
+    // A multi-chunk stream is a serial chain for one lane (chunk lengths are implicit).  Streams of some size first try the
+    // chunk-parallel path: candidate chunk starts are recognised by their complete code-length tables and parsed side by side
+    // (kernels/xhuff_chunks.cuh); whatever it cannot vouch for goes to the serial decoder below, which owns the status codes.
+    static const bool no_spec = getenv("MSCOMP_XHUFF_ONESHOT") && strcmp(getenv("MSCOMP_XHUFF_ONESHOT"), "serial") == 0;
+    if (!no_spec && in_len >= 32768 && in_len <= 0xFFFFFF00ull) {
+        mscomp_gpu_ctx* ctx = msc_thread_ctx();
+        if (!ctx) return MSCOMP_MEM_ERROR;
+        const size_t cap = *out_len > 0xFFFFFF00ull ? (size_t)0xFFFFFF00ull : *out_len;
+        uint8_t* d_in = (uint8_t*)ctx->get(SC_IN, in_len + 64);
+        uint8_t* d_out = (uint8_t*)ctx->get(SC_OUT, cap + 64);
+        if (d_in && d_out) {
+            cudaMemcpyAsync(d_in, in, in_len, cudaMemcpyHostToDevice, ctx->stream);
+            uint64_t total = 0;
+            bool handled = false;
+            MSCompStatus st = msc_xhuff_stream_decode(ctx, d_in, (uint32_t)in_len, d_out, cap, &total, &handled);
+            if (st != MSCOMP_OK) return st;
+            if (handled) {
+                if (total) cudaMemcpyAsync(out, d_out, total, cudaMemcpyDeviceToHost, ctx->stream);
+                if ((st = msc_cuda_status(cudaStreamSynchronize(ctx->stream), "xpress_huff_decompress")) != MSCOMP_OK) return st;
+                *out_len = total;
+                return MSCOMP_OK;
+            }
+        }
+    }
     return one_buffer(mscomp_gpu_xpress_huff_decompress_batch, "xpress_huff_decompress", in, in_len, out, out_len, out_len ? *out_len : 0);
 }
 

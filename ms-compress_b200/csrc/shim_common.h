@@ -40,6 +40,10 @@ MSCompStatus msc_summarize(mscomp_gpu_ctx* ctx, const uint32_t* d_sizes, const i
 // Xpress-Huffman encoder over explicit units; eos_mode 1 = the units are consecutive chunks of one stream.
 extern "C" MSCompStatus msc_xpress_huff_compress_units(mscomp_gpu_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, const mscomp_gpu_batch* b, int eos_mode);
 
+// One multi-chunk Xpress-Huffman stream on the device: chunk-parallel parse + token execution (kernels/xhuff_chunks.cuh);
+// *handled = false leaves the stream to the serial decoder.
+extern "C" MSCompStatus msc_xhuff_stream_decode(mscomp_gpu_ctx* ctx, const uint8_t* d_in, uint32_t in_len, uint8_t* d_out, uint64_t cap, uint64_t* total, bool* handled);
+
 #ifdef MSC_NO_XPRESS   // bring-up only
 #define MSC_XPRESS_COMPRESS nullptr
 #define MSC_XPRESS_DECOMPRESS nullptr

@@ -8,10 +8,12 @@
 #include "../../ms-compress_b200/csrc/kernels/xhuff_decode.cuh"
 #include "../../ms-compress_b200/csrc/kernels/xhuff_index.cuh"
 #include "../../ms-compress_b200/csrc/kernels/xhuff_decode_indexed.cuh"
+#include "../../ms-compress_b200/csrc/kernels/xhuff_chunks.cuh"
 #include "../../ms-compress_b200/csrc/kernels/xpress_decode.cuh"
 #include "../../ms-compress_b200/csrc/kernels/xhuff_encode.cuh"
 #include "../../ms-compress_b200/csrc/kernels/xpress_encode.cuh"
 #include <vector>
+#include <algorithm>
 
 using emu::dim3e;
 
@@ -138,6 +140,69 @@ void emu_xhuff_decode_indexed(const uint8_t* in, uint8_t* out, uint32_t count, c
     emu::launch(xhuff_decode_marked_kernel, dim3e(grid), dim3e(32 * XHD_WARPS_PER_BLOCK), in, out, count, in_off, in_len, out_off, out_cap, out_len, status,
                 (int)ST_INDEX, &handled);
     g_xhuff_second += handled;
+}
+
+// One multi-chunk Xpress-Huffman stream through the chunk-parallel path (kernels/xhuff_chunks.cuh): candidates -> one lane per
+// candidate parses one chunk -> chain from offset 0 -> token execution (all chunks at once when none reaches back, else in order).
+// The stitching mirrors msc_xhuff_stream_decode (csrc/mscomp_gpu.cu).  Returns 1 when the stream was decoded this way (*total
+// bytes in out), 0 when the path declines; *info = candidates | chunks << 16 | (1 << 31 if the chunks ran independently).
+uint32_t emu_xhuff_stream_decode(const uint8_t* in, uint32_t n, uint8_t* out, uint64_t cap, uint64_t* total, uint32_t* info)
+{
+    using namespace msc;
+    *total = 0; *info = 0;
+    if (n < 2u * XH_MIN_DATA) return 0;
+    const uint32_t capc = n / XH_MIN_DATA + 2;
+    std::vector<uint32_t> cand(capc + 2, 0);
+    uint32_t ncand = 0;
+    emu::launch(xhs_candidates_kernel, dim3e(3), dim3e(XHS_THREADS), in, n, cand.data(), &ncand, capc);
+    if (ncand < 2 || ncand > capc) return 0;
+    cand.resize(ncand);
+    std::sort(cand.begin(), cand.end());
+    *info = ncand;
+    if (cand[0] != 0) return 0;
+    const uint32_t count = ncand;
+    std::vector<uint64_t> in_off(count), out_off(count);
+    std::vector<uint32_t> in_len(count), out_cap(count, XH_CHUNK), out_len(count), ntok(count + 1), end_ip(count), reach(count);
+    std::vector<int32_t> status(count);
+    for (uint32_t k = 0; k < count; ++k) { in_off[k] = cand[k]; in_len[k] = n - cand[k]; out_off[k] = (uint64_t)k * XH_CHUNK; }
+    std::vector<uint32_t> tok((size_t)count * XH_CHUNK + 16);
+    emu::launch(xhuff_parse_chunks_kernel, dim3e(2), dim3e(32 * XHD_WARPS_PER_BLOCK), in, tok.data(), count, (const uint64_t*)in_off.data(),
+                (const uint32_t*)in_len.data(), (const uint64_t*)out_off.data(), (const uint32_t*)out_cap.data(), out_len.data(), status.data(),
+                ntok.data(), end_ip.data(), reach.data());
+    std::vector<uint32_t> chain, pos;
+    uint64_t produced = 0;
+    uint32_t at = 0;
+    bool ok = false, independent = true;
+    for (;;) {
+        const auto it = std::lower_bound(cand.begin(), cand.end(), at);
+        if (it == cand.end() || *it != at) break;
+        const uint32_t k = (uint32_t)(it - cand.begin());
+        if (status[k] < 0 || reach[k] > produced) break;
+        if (reach[k]) independent = false;
+        chain.push_back(k); pos.push_back((uint32_t)produced);
+        produced += out_len[k];
+        if (status[k] == 0) { ok = true; break; }
+        const uint64_t next = (uint64_t)at + end_ip[k];
+        if (next == n) { ok = true; break; }
+        if (next > n || n - next < (uint64_t)XH_MIN_DATA || out_len[k] == 0) break;
+        at = (uint32_t)next;
+    }
+    if (!ok || produced > cap) return 0;
+    {
+        std::vector<uint64_t> slot(chain.size());
+        std::vector<uint32_t> nt(chain.size());
+        for (size_t j = 0; j < chain.size(); ++j) { slot[j] = (uint64_t)chain[j] * XH_CHUNK; nt[j] = ntok[chain[j]]; }
+        if (independent)
+            emu::launch(xhs_apply_chunks_kernel, dim3e(2), dim3e(32 * LZA_WARPS_PER_BLOCK), (const uint32_t*)tok.data(), (const uint64_t*)slot.data(),
+                        (const uint32_t*)nt.data(), (const uint32_t*)pos.data(), (uint32_t)chain.size(), out);
+        else
+            emu::launch(xhs_apply_chain_kernel, dim3e(1), dim3e(32 * LZB_WARPS), (const uint32_t*)tok.data(), (const uint64_t*)slot.data(),
+                        (const uint32_t*)nt.data(), (const uint32_t*)pos.data(), (uint32_t)chain.size(), out);
+    }
+    const bool packed = independent;
+    *total = produced;
+    *info = ncand | ((uint32_t)chain.size() << 16) | (packed ? 0x80000000u : 0u);
+    return 1;
 }
 
 // two-pass plain Xpress encoder: match finding per 64 KiB segment (persistent blocks), then emission per buffer

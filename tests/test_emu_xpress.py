@@ -8,7 +8,7 @@ from conftest import MAXSZ
 import ctypes
 
 import numpy as np
-from emu_util import P, emu_batch
+from emu_util import P, PAD, emu_batch, padded
 
 KERNELS = {"xpress_huff": ("emu_xhuff_decode", "emu_xhuff_encode"), "xpress": ("emu_xpress_decode", "emu_xpress_encode")}
 SIZES = [1, 2, 3, 4, 5, 31, 32, 33, 100, 5000, 65535, 65536, 65537, 140000]
@@ -225,3 +225,39 @@ def test_xhuff_encoder_writes_the_index_the_walk_finds(emu, oracle, ms):
     for p, c in zip(plains, outs):
         rc, back = oracle.decompress("xpress_huff", c, len(p))
         assert rc == 0 and back == p
+
+
+def _emu_stream_decode(emu, comp, cap):
+    import numpy as np
+    a, addr = padded(comp)
+    out = np.zeros(cap + 2 * PAD, dtype=np.uint8)
+    total, info = ctypes.c_uint64(0), ctypes.c_uint32(0)
+    emu.emu_xhuff_stream_decode.restype = ctypes.c_uint32
+    handled = emu.emu_xhuff_stream_decode(ctypes.c_void_p(addr), ctypes.c_uint32(len(comp)), ctypes.c_void_p(out.ctypes.data + PAD),
+                                          ctypes.c_uint64(cap), ctypes.byref(total), ctypes.byref(info))
+    return handled, out[PAD:PAD + total.value].tobytes(), info.value
+
+
+def test_xhuff_chunk_parallel_stream_decode(emu, oracle, ms):
+    """One multi-chunk stream: chunk starts recognised by their complete code-length tables, one lane per chunk, chain stitched from
+    offset 0.  Reference-made streams have matches that reach into the previous chunk (executed in order); streams made by our
+    encoder do not (all chunks at once).  Streams the path cannot vouch for must be declined, never decoded wrongly."""
+    for kind, n in (("text", 200000), ("text", 65536 * 3), ("runs", 150000), ("random", 140000), ("text", 65537)):
+        plain = ms.generate(kind, n, 7 + n % 5)
+        comp = oracle.compress("xpress_huff", plain)
+        handled, got, info = _emu_stream_decode(emu, comp, n)
+        assert handled == 1 and got == plain, (kind, n, handled, info)
+        assert (info >> 16) & 0x7FFF == (n + 65535) // 65536
+        # our own encoder: window reset per chunk -> independent chunks
+        st, ol, outs = emu_batch(emu, "emu_xhuff_encode", [plain], [len(plain) + 34 + 258 + 258 * (len(plain) // 65536) + 16])
+        assert not st.any()
+        handled, got, info = _emu_stream_decode(emu, outs[0], n)
+        assert handled == 1 and got == plain and (info >> 31) == 1, (kind, n, info)
+        # too little room, a damaged table, a truncated stream: declined (the serial decoder reports those)
+        assert _emu_stream_decode(emu, comp, n - 1)[0] == 0
+        bad = bytearray(comp); bad[3] ^= 0x10
+        assert _emu_stream_decode(emu, bytes(bad), n)[0] == 0
+        h, g, _ = _emu_stream_decode(emu, comp[:len(comp) - 5], n)
+        assert h == 0 or g == oracle.decompress("xpress_huff", comp[:len(comp) - 5], n)[1]
+    # a single chunk is not this path's business
+    assert _emu_stream_decode(emu, oracle.compress("xpress_huff", ms.generate("text", 50000, 1)), 50000)[0] == 0

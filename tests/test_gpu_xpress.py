@@ -308,3 +308,31 @@ def test_xhuff_encoder_index_on_gpu(ms, oracle):
     for i, p in enumerate(plains):
         assert out[i_off[i]:i_off[i] + len(p)].tobytes() == p, i
     assert ctx.xhuff_second_chances() == before
+
+
+@pytest.mark.gpu
+def test_xhuff_one_shot_multichunk_streams(ms, oracle):
+    """xpress_huff_decompress on ONE multi-chunk stream takes the chunk-parallel path (kernels/xhuff_chunks.cuh): reference-made
+    streams (matches reach into the previous chunk), streams made here (independent chunks), and everything that path must leave to
+    the serial decoder -- too little room, damaged tables and payloads, truncation, trailing bytes -- with the oracle's status."""
+    rnd = random.Random(5)
+    for kind, n in (("text", 1 << 23), ("text", 300001), ("runs", 1 << 20), ("random", 200000), ("text", 65536 * 2)):
+        plain = ms.generate(kind, n, 3 + n % 7)
+        ref = oracle.compress("xpress_huff", plain)
+        assert ms.raw_call("xpress_huff_decompress", ref, n) == (0, plain), (kind, n)
+        assert ms.raw_call("xpress_huff_decompress", ref, n + 1000) == (0, plain), (kind, n)
+        st, mine = ms.raw_call("xpress_huff_compress", plain, MAXSZ["xpress_huff"](n))
+        assert st == 0 and ms.raw_call("xpress_huff_decompress", mine, n) == (0, plain), (kind, n)
+        assert oracle.decompress("xpress_huff", mine, n) == (0, plain)
+        if n > 400000:
+            continue
+        cases = [(ref, n - 1), (ref, n // 2), (ref, 0), (ref[:-1], n), (ref[:-2], n), (ref[:len(ref) // 2], n), (ref + bytes(2), n + 10), (ref + b"U", n + 10)]
+        for _ in range(25):
+            b = bytearray(ref)
+            for _ in range(rnd.randint(1, 3)):
+                b[rnd.randrange(len(b))] ^= 1 << rnd.randrange(8)
+            cases.append((bytes(b), n + rnd.choice((0, 64))))
+        for comp, cap in cases:
+            exp = oracle.decompress("xpress_huff", comp, cap)
+            got = ms.raw_call("xpress_huff_decompress", comp, cap)
+            assert got[0] == exp[0] and (exp[0] != 0 or got[1] == exp[1]), (kind, n, cap, got[0], exp[0])
