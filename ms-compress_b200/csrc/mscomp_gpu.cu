@@ -591,6 +591,15 @@ MSCompStatus msc_xhuff_stream_decode(mscomp_gpu_ctx* ctx, const uint8_t* d_in, u
         if (next > in_len || in_len - next < (uint64_t)XH_MIN_DATA || h_out_len[i] == 0) break;
         at = (uint32_t)next;
     }
+    {
+        static const bool trace = getenv("MSCOMP_TRACE") != nullptr;
+        if (trace) {
+            uint32_t nreach = 0, maxreach = 0, first = 0xFFFFFFFFu;
+            for (size_t j = 0; j < chain.size(); ++j) { const uint32_t r = h_reach[(size_t)chain[j] * stride]; if (r) { ++nreach; if (first == 0xFFFFFFFFu) first = (uint32_t)j; } if (r > maxreach) maxreach = r; }
+            fprintf(stderr, "[mscomp] xhuff stream: %u candidates, %zu chunks linked, ok=%d, produced=%llu, chunks reaching back: %u (first %u, max %u bytes)\n",
+                    ncand, chain.size(), (int)ok, (unsigned long long)produced, nreach, first, maxreach);
+        }
+    }
     if (!ok || produced > cap) return MSCOMP_OK;
     // 4. execute the tokens
     const size_t nch = chain.size();
