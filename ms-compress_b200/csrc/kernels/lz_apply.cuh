@@ -139,19 +139,9 @@ struct LzBlockSmem {
     uint32_t wsum[LZB_WARPS];
 };
 
-// DEP: the unit (a chunk, a segment) is one of a CHAIN of units of the same stream that other blocks execute at the same time.
-//   ext_front  the predecessor's frontier (null for the first unit): every output byte below *ext_front is final.  A match whose
-//              source starts before this unit's first byte waits until the frontier has passed the part of its source that lies there.
-//   my_front   this unit's frontier, published as its rounds finish -- but only once the predecessor is complete, so that "every
-//              byte below the frontier is final" holds for the whole stream, not just for this unit's own bytes.
-// Units of a chain must be started in chain order by blocks that are all resident (a block never waits for a later unit).
-template <bool DEP>
-__device__ __forceinline__ uint32_t lz_apply_block_run_t(LzBlockSmem& sm, const uint32_t* __restrict__ tk, uint32_t n, uint8_t* __restrict__ o, uint32_t pstart,
-                                                         uint32_t* ext_front, uint32_t* my_front)
+__device__ __forceinline__ uint32_t lz_apply_block_run(LzBlockSmem& sm, const uint32_t* __restrict__ tk, uint32_t n, uint8_t* __restrict__ o, uint32_t pstart)
 {
     const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t base_lo = pstart;                         // first byte of the unit
-    uint32_t G = (DEP && ext_front) ? 0u : 0xFFFFFFFFu;      // last value seen of the predecessor's frontier (per warp, monotone)
     for (uint32_t w0 = 0; w0 < n; w0 += 32u * LZB_ROUNDS) {
         const uint32_t nt = min(n - w0, 32u * LZB_ROUNDS), R = (nt + 31) / 32;
         // bytes per round
@@ -192,8 +182,6 @@ __device__ __forceinline__ uint32_t lz_apply_block_run_t(LzBlockSmem& sm, const 
             if (len && !is_match) o[pos] = (uint8_t)tok;
             bool pending = is_match;
             const uint32_t a = pos - off, be = min(a + len, pos);        // the bytes a match reads: [a, be)
-            const bool ext = DEP && is_match && a < base_lo;             // part of the source belongs to the predecessor
-            const uint32_t be_x = min(be, base_lo);
             for (;;) {
                 __syncwarp();
                 const unsigned W = __reduce_min_sync(FULL, pending ? pos : 0xffffffffu);
@@ -203,15 +191,9 @@ __device__ __forceinline__ uint32_t lz_apply_block_run_t(LzBlockSmem& sm, const 
                 d = __shfl_sync(FULL, d, 0);
                 const bool prev_done = d >= r;
                 const uint32_t F = sm.p0[prev_done ? r : d];               // everything below F is final
-                if (DEP && __any_sync(FULL, pending && ext && be_x > G)) {  // look at the predecessor's frontier again
-                    uint32_t g = 0;
-                    if (lane == 0) g = atomicAdd(ext_front, 0u);
-                    G = __shfl_sync(FULL, g, 0);
-                }
-                const bool can = pending && (!ext || be_x <= G) && (be <= F || ((a >= p0r || prev_done) && (pos == W || be <= W)));
-                if (!__any_sync(FULL, can)) { spin_pause(); continue; }    // all pending matches wait for earlier rounds / units
-                if (DEP) __threadfence();                                  // (the other unit's bytes, seen through its frontier)
-                else if (!prev_done) __threadfence_block();                // bytes of the rounds counted in d are visible from here on
+                const bool can = pending && (be <= F || ((a >= p0r || prev_done) && (pos == W || be <= W)));
+                if (!__any_sync(FULL, can)) { spin_pause(); continue; }    // all pending matches wait for earlier rounds
+                if (!prev_done) __threadfence_block();                     // bytes of the rounds counted in d are visible from here on
                 const uint32_t cl = can ? len : 0u;
                 const uint32_t cincl = (uint32_t)warp_incl_scan((int)cl);
                 const uint32_t total = __shfl_sync(FULL, cincl, 31);
@@ -235,7 +217,7 @@ __device__ __forceinline__ uint32_t lz_apply_block_run_t(LzBlockSmem& sm, const 
             }
             // publish: the round is finished; whoever sees the frontier stuck at a finished round moves it
             __syncwarp();
-            if (DEP) __threadfence(); else __threadfence_block();
+            __threadfence_block();
             if (lane == 0) {
                 st_shared_signal(&sm.flag[r], 1u);
                 __threadfence_block();
@@ -244,33 +226,13 @@ __device__ __forceinline__ uint32_t lz_apply_block_run_t(LzBlockSmem& sm, const 
                     if (d >= R || !ld_shared_signal(&sm.flag[d])) break;
                     atomicCAS(&sm.done_upto, d, d + 1);
                 }
-                if (DEP && my_front) {
-                    // publish the frontier -- once the predecessor is complete (its frontier has reached this unit's first byte)
-                    if (G < base_lo && ext_front) G = atomicAdd(ext_front, 0u);
-                    if (G >= base_lo) {
-                        const uint32_t d = ld_shared_signal(&sm.done_upto);
-                        __threadfence();
-                        atomicMax(my_front, sm.p0[d < R ? d : R]);
-                    }
-                }
             }
-            if (DEP) G = __shfl_sync(FULL, G, 0);
         }
         __syncthreads();
         pstart = sm.p0[R];
         __syncthreads();
     }
-    if (DEP && my_front && tid == 0) {                       // the unit is complete: its end becomes the frontier as soon as the predecessor's has arrived
-        if (ext_front) while (atomicAdd(ext_front, 0u) < base_lo) spin_pause();
-        __threadfence();
-        atomicMax(my_front, pstart);
-    }
     return pstart;
-}
-
-__device__ __forceinline__ uint32_t lz_apply_block_run(LzBlockSmem& sm, const uint32_t* __restrict__ tk, uint32_t n, uint8_t* __restrict__ o, uint32_t pstart)
-{
-    return lz_apply_block_run_t<false>(sm, tk, n, o, pstart, nullptr, nullptr);
 }
 
 // Stream i: tokens tok_base + 4 * out_off[i] (ntok[i] of them) -> out + out_off[i], one block per stream.

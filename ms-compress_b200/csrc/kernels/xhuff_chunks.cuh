@@ -66,17 +66,13 @@ xhs_candidates_kernel(const uint8_t* __restrict__ in, uint32_t n, uint32_t* __re
     }
 }
 
-// The chunks of one stream whose matches reach back across chunk starts: chunk j = tokens tok + slot[j] (ntok[j] of them), first
-// output byte at pos[j] of `out`.  One block per chunk at a time, all chunks in flight together: a match waits for the frontier of
-// the chunk before it only when its source lies there (lz_apply_block_run_t<true>); front[] (nchain words, zeroed) carries the
-// frontiers.  Blocks take chunks b, b + gridDim.x, ... in rising order and the grid is resident, so nobody waits for a later chunk.
+// The chunks of one stream in order: chunk j = tokens tok + slot[j] (ntok[j] of them), first output byte at pos[j] of `out`.
 __global__ void __launch_bounds__(32 * LZB_WARPS)
 xhs_apply_chain_kernel(const uint32_t* __restrict__ tok, const uint64_t* __restrict__ slot, const uint32_t* __restrict__ ntok,
-                       const uint32_t* __restrict__ pos, uint32_t nchain, uint8_t* __restrict__ out, uint32_t* __restrict__ front)
+                       const uint32_t* __restrict__ pos, uint32_t nchain, uint8_t* __restrict__ out)
 {
     __shared__ LzBlockSmem sm;
-    for (uint32_t j = blockIdx.x; j < nchain; j += gridDim.x)
-        lz_apply_block_run_t<true>(sm, tok + slot[j], ntok[j], out, pos[j], j ? front + (j - 1) : nullptr, front + j);
+    for (uint32_t j = 0; j < nchain; ++j) lz_apply_block_run(sm, tok + slot[j], ntok[j], out, pos[j]);
 }
 
 // The same when no chunk reaches back before its own first byte: every chunk on its own warp.

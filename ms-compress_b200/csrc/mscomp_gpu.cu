@@ -617,15 +617,9 @@ MSCompStatus msc_xhuff_stream_decode(mscomp_gpu_ctx* ctx, const uint8_t* d_in, u
             const uint32_t ab = ((uint32_t)nch + LZA_WARPS_PER_BLOCK - 1) / LZA_WARPS_PER_BLOCK, acap = (uint32_t)ctx->sm_count * 16;
             MSC_LAUNCH(ctx, xhs_apply_chunks_kernel, ab < acap ? ab : acap, 32 * LZA_WARPS_PER_BLOCK, (const uint32_t*)d_tok, (const uint64_t*)d_ch,
                        (const uint32_t*)(d_ch + nch * 8), (const uint32_t*)(d_ch + nch * 12), (uint32_t)nch, d_out);
-        } else {                                                                  // matches reach across chunk starts: a block per chunk, chained by frontiers
-            uint32_t* d_front = (uint32_t*)ctx->get(SC_SIZES, nch * sizeof(uint32_t) + 64);
-            if (!d_front) return MSCOMP_OK;
-            cudaMemsetAsync(d_front, 0, nch * sizeof(uint32_t), ctx->stream);
-            static int per_sm = 0;                                               // the grid must be resident: blocks wait for their predecessors
-            if (!per_sm && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, xhs_apply_chain_kernel, 32 * LZB_WARPS, 0) != cudaSuccess || per_sm < 1)) { cudaGetLastError(); per_sm = 1; }
-            const uint32_t gcap = (uint32_t)ctx->sm_count * (uint32_t)per_sm;
-            MSC_LAUNCH(ctx, xhs_apply_chain_kernel, (uint32_t)nch < gcap ? (uint32_t)nch : gcap, 32 * LZB_WARPS, (const uint32_t*)d_tok, (const uint64_t*)d_ch,
-                       (const uint32_t*)(d_ch + nch * 8), (const uint32_t*)(d_ch + nch * 12), (uint32_t)nch, d_out, d_front);
+        } else {                                                                  // matches reach across chunk starts: in stream order, one block
+            MSC_LAUNCH(ctx, xhs_apply_chain_kernel, 1, 32 * LZB_WARPS, (const uint32_t*)d_tok, (const uint64_t*)d_ch, (const uint32_t*)(d_ch + nch * 8),
+                       (const uint32_t*)(d_ch + nch * 12), (uint32_t)nch, d_out);
         }
     }
     const MSCompStatus st = msc_cuda_status(cudaGetLastError(), "xpress_huff_decompress");

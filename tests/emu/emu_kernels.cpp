@@ -195,11 +195,9 @@ uint32_t emu_xhuff_stream_decode(const uint8_t* in, uint32_t n, uint8_t* out, ui
         if (independent)
             emu::launch(xhs_apply_chunks_kernel, dim3e(2), dim3e(32 * LZA_WARPS_PER_BLOCK), (const uint32_t*)tok.data(), (const uint64_t*)slot.data(),
                         (const uint32_t*)nt.data(), (const uint32_t*)pos.data(), (uint32_t)chain.size(), out);
-        else {   // (the emulator runs one block at a time, in order: one chunk per block, so every predecessor is complete)
-            std::vector<uint32_t> front(chain.size() + 1, 0);
-            emu::launch(xhs_apply_chain_kernel, dim3e((uint32_t)chain.size()), dim3e(32 * LZB_WARPS), (const uint32_t*)tok.data(), (const uint64_t*)slot.data(),
-                        (const uint32_t*)nt.data(), (const uint32_t*)pos.data(), (uint32_t)chain.size(), out, front.data());
-        }
+        else
+            emu::launch(xhs_apply_chain_kernel, dim3e(1), dim3e(32 * LZB_WARPS), (const uint32_t*)tok.data(), (const uint64_t*)slot.data(),
+                        (const uint32_t*)nt.data(), (const uint32_t*)pos.data(), (uint32_t)chain.size(), out);
     }
     const bool packed = independent;
     *total = produced;
