@@ -235,6 +235,130 @@ __device__ __forceinline__ uint32_t lz_apply_block_run(LzBlockSmem& sm, const ui
     return pstart;
 }
 
+// The same pipeline for ONE stream that has the GPU to itself (the one-shot calls): the most recent LZR_RING bytes of the output
+// also live in a shared-memory ring (byte x at ring[x & (LZR_RING - 1)]), and every match source is read from there -- a
+// shared-memory round trip per copy step instead of one through L2, which is what a lone block waits for.  Offsets reach back at
+// most 65,535 bytes, so the rounds in flight may span at most LZR_SPAN bytes: a window is cut where its rounds exceed that, and a
+// single round that is longer by itself (very long matches) runs its tokens strictly in order, which keeps the writes monotone.
+// Successive calls continue the same stream (pstart = where the previous call ended); the ring is carried over.
+constexpr uint32_t LZR_RING = 128u << 10;
+constexpr uint32_t LZR_SPAN = LZR_RING - 65536u - 4096u;
+__device__ __forceinline__ uint32_t lz_apply_ring_run(LzBlockSmem& sm, uint8_t* __restrict__ ring, const uint32_t* __restrict__ tk, uint32_t n,
+                                                      uint8_t* __restrict__ o, uint32_t pstart)
+{
+    const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr uint32_t RM = LZR_RING - 1u;
+    for (uint32_t w0 = 0; w0 < n; ) {
+        const uint32_t nt_all = min(n - w0, 32u * LZB_ROUNDS);
+        uint32_t nt = nt_all, R = (nt + 31) / 32;
+        // bytes per round
+        for (uint32_t r = warp; r < R; r += LZB_WARPS) {
+            const uint32_t t = 32 * r + lane;
+            const uint32_t tok = t < nt ? tk[w0 + t] : 0;
+            const uint32_t len = t < nt ? ((tok >> 31) ? ((tok >> 16) & 0x7FFFu) + 1 : 1u) : 0u;
+            const uint32_t sum = __reduce_add_sync(FULL, len);
+            if (lane == 0) sm.p0[r] = sum;
+        }
+        __syncthreads();
+        {   // exclusive scan of the (at most LZB_ROUNDS) round totals, LZB_EPT consecutive ones per thread
+            uint32_t v[LZB_EPT], sum = 0;
+#pragma unroll
+            for (int i = 0; i < LZB_EPT; ++i) { const uint32_t r = (uint32_t)(LZB_EPT * tid + i); v[i] = r < R ? sm.p0[r] : 0u; sum += v[i]; }
+            const uint32_t incl = (uint32_t)warp_incl_scan((int)sum);
+            if (lane == 31) sm.wsum[warp] = incl;
+            __syncthreads();
+            uint32_t run = pstart + incl - sum;
+            for (int w = 0; w < warp; ++w) run += sm.wsum[w];
+#pragma unroll
+            for (int i = 0; i < LZB_EPT; ++i) {
+                const uint32_t r = (uint32_t)(LZB_EPT * tid + i);
+                if (r < R) { sm.p0[r] = run; run += v[i]; if (r + 1 == R) sm.p0[R] = run; }
+            }
+            for (uint32_t r = tid; r < R; r += 32 * LZB_WARPS) sm.flag[r] = 0;
+            if (tid == 0) sm.done_upto = 0;
+        }
+        __syncthreads();
+        // cut the window where the rounds in flight would span more than the ring can hold behind a 64 KiB offset
+        bool serial = false;
+        {
+            int fit = 0;
+            for (uint32_t r = tid; r < R; r += 32 * LZB_WARPS) fit += (sm.p0[r + 1] - pstart <= LZR_SPAN) ? 1 : 0;
+            fit = __reduce_add_sync(FULL, fit);
+            if (lane == 0) sm.wsum[warp] = (uint32_t)fit;
+            __syncthreads();
+            uint32_t total_fit = 0;
+            for (int w = 0; w < LZB_WARPS; ++w) total_fit += sm.wsum[w];
+            __syncthreads();
+            if (total_fit == 0) { serial = true; total_fit = 1; }
+            if (total_fit < R) { R = total_fit; nt = 32u * R; }
+        }
+        for (uint32_t r = warp; r < R; r += LZB_WARPS) {
+            const uint32_t t = 32 * r + lane;
+            const uint32_t tok = t < nt ? tk[w0 + t] : 0;
+            const bool is_match = (tok >> 31) != 0;
+            const uint32_t len = t < nt ? (is_match ? ((tok >> 16) & 0x7FFFu) + 1 : 1u) : 0u;
+            const uint32_t off = tok & 0xFFFFu;
+            const uint32_t p0r = sm.p0[r];
+            const uint32_t pos = p0r + (uint32_t)warp_incl_scan((int)len) - len;
+            if (len && !is_match) { o[pos] = (uint8_t)tok; ring[pos & RM] = (uint8_t)tok; }
+            bool pending = is_match;
+            const uint32_t a = pos - off, be = min(a + len, pos);        // the bytes a match reads: [a, be)
+            for (;;) {
+                __syncwarp();
+                const unsigned W = __reduce_min_sync(FULL, pending ? pos : 0xffffffffu);
+                if (W == 0xffffffffu) break;
+                uint32_t d = 0;
+                if (lane == 0) d = ld_shared_signal(&sm.done_upto);
+                d = __shfl_sync(FULL, d, 0);
+                const bool prev_done = d >= r;
+                const uint32_t F = sm.p0[prev_done ? r : d];               // everything below F is final
+                const bool can = pending && (serial ? (prev_done && pos == W) : (be <= F || ((a >= p0r || prev_done) && (pos == W || be <= W))));
+                if (!__any_sync(FULL, can)) { spin_pause(); continue; }    // all pending matches wait for earlier rounds
+                if (!prev_done) __threadfence_block();                     // bytes of the rounds counted in d are visible from here on
+                const uint32_t cl = can ? len : 0u;
+                const uint32_t cincl = (uint32_t)warp_incl_scan((int)cl);
+                const uint32_t total = __shfl_sync(FULL, cincl, 31);
+                for (uint32_t b0 = 0; b0 < total; b0 += 32) {
+                    const uint32_t bidx = b0 + lane;
+                    int tt = 0;
+#pragma unroll
+                    for (int step = 16; step; step >>= 1) {
+                        const uint32_t c = __shfl_sync(FULL, cincl, tt + step - 1);
+                        if (c <= bidx) tt += step;
+                    }
+                    const uint32_t t_incl = __shfl_sync(FULL, cincl, tt), t_len = __shfl_sync(FULL, cl, tt);
+                    const uint32_t t_pos = __shfl_sync(FULL, pos, tt), t_off = __shfl_sync(FULL, off, tt);
+                    if (bidx < total) {
+                        const uint32_t k = bidx - (t_incl - t_len);
+                        const uint32_t sk = (t_off < t_len) ? (k % t_off) : k;
+                        const uint8_t v = ring[(t_pos - t_off + sk) & RM];
+                        ring[(t_pos + k) & RM] = v;
+                        o[t_pos + k] = v;
+                    }
+                }
+                if (can) pending = false;
+            }
+            // publish: the round is finished; whoever sees the frontier stuck at a finished round moves it
+            __syncwarp();
+            __threadfence_block();
+            if (lane == 0) {
+                st_shared_signal(&sm.flag[r], 1u);
+                __threadfence_block();
+                for (;;) {
+                    const uint32_t d = ld_shared_signal(&sm.done_upto);
+                    if (d >= R || !ld_shared_signal(&sm.flag[d])) break;
+                    atomicCAS(&sm.done_upto, d, d + 1);
+                }
+            }
+        }
+        __syncthreads();
+        pstart = sm.p0[R];
+        __syncthreads();
+        w0 += nt;
+    }
+    return pstart;
+}
+
 // Stream i: tokens tok_base + 4 * out_off[i] (ntok[i] of them) -> out + out_off[i], one block per stream.
 __global__ void __launch_bounds__(32 * LZB_WARPS)
 lz_apply_block_kernel(const uint32_t* __restrict__ tok_base, const uint32_t* __restrict__ ntok, const uint64_t* __restrict__ out_off,

@@ -66,13 +66,19 @@ xhs_candidates_kernel(const uint8_t* __restrict__ in, uint32_t n, uint32_t* __re
     }
 }
 
-// The chunks of one stream in order: chunk j = tokens tok + slot[j] (ntok[j] of them), first output byte at pos[j] of `out`.
+// The chunks of one stream in order (matches reach back across chunk starts, so the bytes must be produced in stream order): chunk j =
+// tokens tok + slot[j] (ntok[j] of them), first output byte at pos[j] of `out`; the chunks are contiguous in the output.  One block
+// with the last 128 KiB of output in a shared-memory ring (lz_apply_ring_run): a lone block would otherwise wait an L2 round trip
+// per copy step.  Dynamic shared memory: LZR_RING bytes.
 __global__ void __launch_bounds__(32 * LZB_WARPS)
 xhs_apply_chain_kernel(const uint32_t* __restrict__ tok, const uint64_t* __restrict__ slot, const uint32_t* __restrict__ ntok,
                        const uint32_t* __restrict__ pos, uint32_t nchain, uint8_t* __restrict__ out)
 {
+    MSC_DYN_SMEM(ring_raw);
     __shared__ LzBlockSmem sm;
-    for (uint32_t j = 0; j < nchain; ++j) lz_apply_block_run(sm, tok + slot[j], ntok[j], out, pos[j]);
+    uint8_t* ring = reinterpret_cast<uint8_t*>(ring_raw);
+    uint32_t p = nchain ? pos[0] : 0u;
+    for (uint32_t j = 0; j < nchain; ++j) p = lz_apply_ring_run(sm, ring, tok + slot[j], ntok[j], out, p);
 }
 
 // The same when no chunk reaches back before its own first byte: every chunk on its own warp.

@@ -618,8 +618,9 @@ MSCompStatus msc_xhuff_stream_decode(mscomp_gpu_ctx* ctx, const uint8_t* d_in, u
             MSC_LAUNCH(ctx, xhs_apply_chunks_kernel, ab < acap ? ab : acap, 32 * LZA_WARPS_PER_BLOCK, (const uint32_t*)d_tok, (const uint64_t*)d_ch,
                        (const uint32_t*)(d_ch + nch * 8), (const uint32_t*)(d_ch + nch * 12), (uint32_t)nch, d_out);
         } else {                                                                  // matches reach across chunk starts: in stream order, one block
-            MSC_LAUNCH(ctx, xhs_apply_chain_kernel, 1, 32 * LZB_WARPS, (const uint32_t*)d_tok, (const uint64_t*)d_ch, (const uint32_t*)(d_ch + nch * 8),
-                       (const uint32_t*)(d_ch + nch * 12), (uint32_t)nch, d_out);
+            MSC_OPT_IN_SMEM(xhs_apply_chain_kernel, LZR_RING);
+            MSC_LAUNCH_SMEM(ctx, xhs_apply_chain_kernel, 1, 32 * LZB_WARPS, LZR_RING, (const uint32_t*)d_tok, (const uint64_t*)d_ch, (const uint32_t*)(d_ch + nch * 8),
+                            (const uint32_t*)(d_ch + nch * 12), (uint32_t)nch, d_out);
         }
     }
     const MSCompStatus st = msc_cuda_status(cudaGetLastError(), "xpress_huff_decompress");

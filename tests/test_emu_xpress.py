@@ -259,5 +259,13 @@ def test_xhuff_chunk_parallel_stream_decode(emu, oracle, ms):
         assert _emu_stream_decode(emu, bytes(bad), n)[0] == 0
         h, g, _ = _emu_stream_decode(emu, comp[:len(comp) - 5], n)
         assert h == 0 or g == oracle.decompress("xpress_huff", comp[:len(comp) - 5], n)[1]
+    # very long matches across chunk starts (rounds longer than the ring's span run their tokens in order)
+    taken = 0
+    for plain in (bytes(200000), b"ab" * 100000, ms.generate("text", 3000, 2) * 70, bytes(range(256)) * 1000, ms.generate("runs", 400000, 3)):
+        comp = oracle.compress("xpress_huff", plain)
+        handled, got, info = _emu_stream_decode(emu, comp, len(plain))
+        assert handled == 0 or got == plain, (len(plain), info)      # (a chunk that uses ONE symbol has an incomplete code: declined)
+        taken += handled
+    assert taken >= 2
     # a single chunk is not this path's business
     assert _emu_stream_decode(emu, oracle.compress("xpress_huff", ms.generate("text", 50000, 1)), 50000)[0] == 0
