@@ -194,22 +194,7 @@ __device__ __forceinline__ uint32_t lz_apply_block_run(LzBlockSmem& sm, const ui
                 const bool can = pending && (be <= F || ((a >= p0r || prev_done) && (pos == W || be <= W)));
                 if (!__any_sync(FULL, can)) { spin_pause(); continue; }    // all pending matches wait for earlier rounds
                 if (!prev_done) __threadfence_block();                     // bytes of the rounds counted in d are visible from here on
-                // short matches that do not overlap their source: one per lane, four bytes per step (all loads of a step in flight
-                // together); the rest -- long ones, runs -- byte-parallel across the warp
-                const bool simple = can && len <= 16u && off >= len;
-                if (simple) {
-                    const uint8_t* q = o + a;
-                    uint8_t* dd = o + pos;
-                    for (uint32_t i = 0; i < len; i += 4) {
-                        const uint32_t b0 = ld_byte_cg(q + i), b1 = i + 1 < len ? ld_byte_cg(q + i + 1) : 0u, b2 = i + 2 < len ? ld_byte_cg(q + i + 2) : 0u,
-                                       b3 = i + 3 < len ? ld_byte_cg(q + i + 3) : 0u;
-                        dd[i] = (uint8_t)b0;
-                        if (i + 1 < len) dd[i + 1] = (uint8_t)b1;
-                        if (i + 2 < len) dd[i + 2] = (uint8_t)b2;
-                        if (i + 3 < len) dd[i + 3] = (uint8_t)b3;
-                    }
-                }
-                const uint32_t cl = (can && !simple) ? len : 0u;
+                const uint32_t cl = can ? len : 0u;
                 const uint32_t cincl = (uint32_t)warp_incl_scan((int)cl);
                 const uint32_t total = __shfl_sync(FULL, cincl, 31);
                 for (uint32_t b0 = 0; b0 < total; b0 += 32) {
@@ -330,18 +315,7 @@ __device__ __forceinline__ uint32_t lz_apply_ring_run(LzBlockSmem& sm, uint8_t* 
                 const bool can = pending && (serial ? (prev_done && pos == W) : (be <= F || ((a >= p0r || prev_done) && (pos == W || be <= W))));
                 if (!__any_sync(FULL, can)) { spin_pause(); continue; }    // all pending matches wait for earlier rounds
                 if (!prev_done) __threadfence_block();                     // bytes of the rounds counted in d are visible from here on
-                const bool simple = can && len <= 16u && off >= len;
-                if (simple) {
-                    for (uint32_t i = 0; i < len; i += 4) {
-                        const uint32_t b0 = ring[(a + i) & RM], b1 = i + 1 < len ? ring[(a + i + 1) & RM] : 0u, b2 = i + 2 < len ? ring[(a + i + 2) & RM] : 0u,
-                                       b3 = i + 3 < len ? ring[(a + i + 3) & RM] : 0u;
-                        ring[(pos + i) & RM] = (uint8_t)b0; o[pos + i] = (uint8_t)b0;
-                        if (i + 1 < len) { ring[(pos + i + 1) & RM] = (uint8_t)b1; o[pos + i + 1] = (uint8_t)b1; }
-                        if (i + 2 < len) { ring[(pos + i + 2) & RM] = (uint8_t)b2; o[pos + i + 2] = (uint8_t)b2; }
-                        if (i + 3 < len) { ring[(pos + i + 3) & RM] = (uint8_t)b3; o[pos + i + 3] = (uint8_t)b3; }
-                    }
-                }
-                const uint32_t cl = (can && !simple) ? len : 0u;
+                const uint32_t cl = can ? len : 0u;
                 const uint32_t cincl = (uint32_t)warp_incl_scan((int)cl);
                 const uint32_t total = __shfl_sync(FULL, cincl, 31);
                 for (uint32_t b0 = 0; b0 < total; b0 += 32) {
