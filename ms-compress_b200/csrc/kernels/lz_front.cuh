@@ -45,16 +45,26 @@ struct LzFrontSmem {
     uint32_t ntok;                     // tokens emitted so far in the unit
 };
 
-// 4 bytes at src[p] (little endian); src need not be aligned.  Only bytes below n are meaningful: every caller either masks the
-// rest off (3-byte keys with p + 3 <= n) or stays below n (4-byte compare steps with i + 4 <= maxlen <= n - p).  Two aligned words
-// and a funnel shift, no branch; the second word is clamped to the last word that holds a byte of the unit, so nothing beyond the
-// unit's 4-byte granules is ever read.
-__device__ __forceinline__ uint32_t lzf_ld4(const uint8_t* __restrict__ src, uint32_t p, uint32_t n)
+// Word view of a unit for unaligned 4-byte reads: 32-bit index arithmetic on an aligned base instead of 64-bit pointer arithmetic
+// per access.  last = index of the last word that holds a byte of the unit.
+struct LzfSrc {
+    const uint32_t* base;
+    uint32_t skew, last;
+    __device__ __forceinline__ LzfSrc(const uint8_t* src, uint32_t n)
+    {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(src);
+        base = reinterpret_cast<const uint32_t*>(a & ~static_cast<uintptr_t>(3));
+        skew = (uint32_t)(a & 3);
+        last = n ? (skew + n - 1) >> 2 : 0u;
+    }
+};
+// 4 bytes at unit offset p (little endian).  Only bytes below n are meaningful: every caller either masks the rest off (3-byte keys
+// with p + 3 <= n) or stays below n (4-byte compare steps with i + 4 <= maxlen <= n - p).  Two aligned words and a funnel shift, no
+// branch; the second word is clamped to the last word of the unit, so nothing beyond the unit's 4-byte granules is ever read.
+__device__ __forceinline__ uint32_t lzf_ld4(const LzfSrc& S, uint32_t p)
 {
-    const uintptr_t a = reinterpret_cast<uintptr_t>(src) + p;
-    const uintptr_t last = (reinterpret_cast<uintptr_t>(src) + n - 1) & ~static_cast<uintptr_t>(3);      // (loop invariant)
-    const uintptr_t w0 = a & ~static_cast<uintptr_t>(3), w1 = w0 + 4 <= last ? w0 + 4 : last;
-    return __funnelshift_r(__ldg(reinterpret_cast<const uint32_t*>(w0)), __ldg(reinterpret_cast<const uint32_t*>(w1)), 8 * (uint32_t)(a & 3));
+    const uint32_t q = S.skew + p, i0 = q >> 2, i1 = min(i0 + 1u, S.last);
+    return __funnelshift_r(__ldg(S.base + i0), __ldg(S.base + i1), 8u * (q & 3u));
 }
 __device__ __forceinline__ uint32_t lzf_hash3(uint32_t x) { return ((x & 0xFFFFFFu) * 0x9E3779B1u) >> (32 - LZF_HBITS); }
 
@@ -78,11 +88,11 @@ __device__ __forceinline__ void lzf_insert(uint16_t* slot, uint32_t v, uint32_t 
 }
 
 // common prefix length of src[p..] and src[c..] (c < p), at most maxlen
-__device__ __forceinline__ uint32_t lzf_match_len(const uint8_t* __restrict__ src, uint32_t p, uint32_t c, uint32_t maxlen, uint32_t n)
+__device__ __forceinline__ uint32_t lzf_match_len(const LzfSrc& S, const uint8_t* __restrict__ src, uint32_t p, uint32_t c, uint32_t maxlen)
 {
     uint32_t i = 0;
     while (i + 4 <= maxlen) {
-        const uint32_t d = lzf_ld4(src, p + i, n) ^ lzf_ld4(src, c + i, n);
+        const uint32_t d = lzf_ld4(S, p + i) ^ lzf_ld4(S, c + i);
         if (d) return i + ((uint32_t)(__ffs((int)d) - 1) >> 3);
         i += 4;
     }
@@ -95,11 +105,12 @@ __device__ __forceinline__ uint32_t lzf_match_len(const uint8_t* __restrict__ sr
 __device__ __forceinline__ void lzf_warm(LzFrontSmem& sm, const uint8_t* __restrict__ src, uint32_t n, uint32_t from, uint32_t to)
 {
     const int tid = (int)threadIdx.x;
+    const LzfSrc S(src, n);
     for (uint32_t s0 = from; s0 < to; s0 += LZF_THREADS * LZF_STEP) {
 #pragma unroll
         for (int u = 0; u < LZF_STEP; ++u) {
             const uint32_t p = s0 + (uint32_t)u * LZF_THREADS + tid;
-            if (p < to && p + 3 <= n) lzf_insert(&sm.H[lzf_hash3(lzf_ld4(src, p, n) & 0xFFFFFFu)], p + 1, s0 + 1);
+            if (p < to && p + 3 <= n) lzf_insert(&sm.H[lzf_hash3(lzf_ld4(S, p) & 0xFFFFFFu)], p + 1, s0 + 1);
         }
         __syncthreads();
     }
@@ -113,6 +124,7 @@ __device__ __forceinline__ uint32_t lzf_tile(LzFrontSmem& sm, const uint8_t* __r
                                              uint32_t window, uint32_t far3)
 {
     const int tid = (int)threadIdx.x, lane = tid & 31;
+    const LzfSrc S(src, n);
     // LZF_STEP positions per thread and step: their lookups are independent, so every thread has that many chains of loads
     // in flight, and the two barriers of a step are paid once per LZF_STEP * 256 positions.
     for (uint32_t s0 = t0; s0 < t0 + LZF_TILE; s0 += LZF_THREADS * LZF_STEP) {
@@ -123,7 +135,7 @@ __device__ __forceinline__ uint32_t lzf_tile(LzFrontSmem& sm, const uint8_t* __r
             uint32_t res = 0, h = 0xFFFFFFFFu;
             const bool on = p + 3 <= n;
             uint32_t key = 0;
-            if (on) { key = lzf_ld4(src, p, n) & 0xFFFFFFu; h = lzf_hash3(key); }
+            if (on) { key = lzf_ld4(S, p) & 0xFFFFFFu; h = lzf_hash3(key); }
             hh[u] = h;
             const unsigned peers = __match_any_sync(FULL, on ? h : (0x80000000u | (uint32_t)lane));
             if (on) {
@@ -132,15 +144,15 @@ __device__ __forceinline__ uint32_t lzf_tile(LzFrontSmem& sm, const uint8_t* __r
                 const unsigned below = peers & ((1u << lane) - 1);
                 if (below) {                                            // candidate B: nearest earlier lane, same hash
                     const uint32_t d = (uint32_t)(lane - (31 - __clz((int)below)));
-                    if (d <= window && (lzf_ld4(src, p - d, n) & 0xFFFFFFu) == key) { best = lzf_match_len(src, p, p - d, maxlen, n); boff = d; }
+                    if (d <= window && (lzf_ld4(S, p - d) & 0xFFFFFFu) == key) { best = lzf_match_len(S, src, p, p - d, maxlen); boff = d; }
                 }
                 const uint32_t a = sm.H[h];
                 if (a) {                                                // candidate A: most recent position of earlier steps
                     // the table keeps 16 bits of the position: the distance is exact while it is below 65536; an older
                     // (aliased) entry yields some other earlier position, which the key compare accepts or rejects on its merits
                     const uint32_t d = (p + 1 - a) & 0xFFFFu, c = p - d;
-                    if (d != 0 && d <= p && d <= window && d != boff && best < maxlen && (lzf_ld4(src, c, n) & 0xFFFFFFu) == key) {
-                        const uint32_t l = lzf_match_len(src, p, c, maxlen, n);
+                    if (d != 0 && d <= p && d <= window && d != boff && best < maxlen && (lzf_ld4(S, c) & 0xFFFFFFu) == key) {
+                        const uint32_t l = lzf_match_len(S, src, p, c, maxlen);
                         if (l > best) { best = l; boff = d; }
                     }
                 }
