@@ -38,7 +38,8 @@ constexpr int LZE_LAZY_RANK = 16;
 constexpr int LZE_ITEM_CAP = LZNT1_CHUNK / 2;    // work items of the pair search (they live in ord[], 4 bytes each)
 
 struct Lznt1EncSmem {
-    __align__(16) uint8_t in[LZNT1_CHUNK + 16];  // zero padded
+    __align__(16) uint8_t in[LZNT1_CHUNK + 16];  // zero padded; a full, aligned chunk arrives by one bulk async copy (cp.async.bulk + mbarrier)
+    __align__(8) uint64_t bar;                   // its mbarrier
     union {
         __align__(16) uint16_t cnt[LZE_BUCKETS]; // B,C: bucket cursors: begin offsets -> (after placement) end offsets
         uint16_t nxt4[LZNT1_CHUNK];              // D: successor link doubled twice
@@ -127,6 +128,9 @@ lznt1_encode_kernel(const uint8_t* __restrict__ in, uint64_t in_len, uint32_t fi
     const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint16_t* hashv = reinterpret_cast<uint16_t*>(sm.lenoff);           // live in B and in the rank pass of C only
 
+    if (tid == 0) mbar_init(&sm.bar, 1);
+    __syncthreads();
+    uint32_t phase = 0;
     // chunks [first, first + nchunks) of the stream `in` (a slice, so that uploads can overlap with encoding)
     for (uint32_t c = first + blockIdx.x; c < first + nchunks; c += gridDim.x) {
         const uint64_t base = (uint64_t)c * LZNT1_CHUNK;
@@ -135,8 +139,9 @@ lznt1_encode_kernel(const uint8_t* __restrict__ in, uint64_t in_len, uint32_t fi
         uint8_t* slot = slots + (uint64_t)c * LZNT1_SLOT;
 
         // ---- A: stage ------------------------------------------------------------------------------------
-        if ((((uintptr_t)src) & 15u) == 0 && n == LZNT1_CHUNK) {
-            reinterpret_cast<uint4*>(sm.in)[tid] = ld_stream16(src + 16 * tid);
+        const bool bulk = (((uintptr_t)src) & 15u) == 0 && n == LZNT1_CHUNK;      // (block-uniform)
+        if (bulk) {
+            if (tid == 0) { fence_async_smem(); bulk_load_g2s(sm.in, src, LZNT1_CHUNK, &sm.bar); }   // the chunk: one bulk copy, global -> shared
         } else {
             for (int i = tid; i < LZNT1_CHUNK; i += LZE_THREADS) sm.in[i] = (i < n) ? src[i] : 0;
         }
@@ -145,6 +150,7 @@ lznt1_encode_kernel(const uint8_t* __restrict__ in, uint64_t in_len, uint32_t fi
         reinterpret_cast<uint4*>(sm.cnt)[tid + LZE_THREADS] = make_uint4(0, 0, 0, 0);
         if (tid < 128) { sm.F[tid] = 0; sm.C[tid] = 0; sm.U[tid] = 0; }
         sm.rankcnt[tid] = 0;
+        if (bulk) { mbar_wait(&sm.bar, phase); phase ^= 1u; }
         __syncthreads();
 
         // ---- B: hash of every position + histogram ------------------------------------------------------
