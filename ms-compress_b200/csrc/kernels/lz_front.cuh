@@ -116,58 +116,12 @@ __device__ __forceinline__ void lzf_warm(LzFrontSmem& sm, const uint8_t* __restr
     }
 }
 
-// Match search + greedy parse for tile [t0, t0 + LZF_TILE) of the unit src[0..n).  `window` = largest usable
-// offset, `far3` = largest offset accepted for a 3-byte match.  On return sm.lenoff / sm.M / sm.V / sm.prefV
-// describe the tile and sm.next_p has advanced; the number of tokens starting in the tile is returned.
-// Must be called by all LZF_THREADS threads.
-__device__ __forceinline__ uint32_t lzf_tile(LzFrontSmem& sm, const uint8_t* __restrict__ src, uint32_t n, uint32_t t0,
-                                             uint32_t window, uint32_t far3)
+// Greedy parse of tile [t0, t0 + LZF_TILE) of a unit of n bytes from sm.lenoff / sm.M (one entry / bit per position of the tile),
+// entered at sm.next_p.  On return sm.V / sm.prefV describe the token starts and sm.next_p has advanced; the number of tokens
+// starting in the tile is returned.  Must be called by all LZF_THREADS threads.
+__device__ __forceinline__ uint32_t lzf_parse_tile(LzFrontSmem& sm, uint32_t n, uint32_t t0)
 {
     const int tid = (int)threadIdx.x, lane = tid & 31;
-    const LzfSrc S(src, n);
-    // LZF_STEP positions per thread and step: their lookups are independent, so every thread has that many chains of loads
-    // in flight, and the two barriers of a step are paid once per LZF_STEP * 256 positions.
-    for (uint32_t s0 = t0; s0 < t0 + LZF_TILE; s0 += LZF_THREADS * LZF_STEP) {
-        uint32_t hh[LZF_STEP];
-#pragma unroll
-        for (int u = 0; u < LZF_STEP; ++u) {
-            const uint32_t p = s0 + (uint32_t)u * LZF_THREADS + tid;
-            uint32_t res = 0, h = 0xFFFFFFFFu;
-            const bool on = p + 3 <= n;
-            uint32_t key = 0;
-            if (on) { key = lzf_ld4(S, p) & 0xFFFFFFu; h = lzf_hash3(key); }
-            hh[u] = h;
-            const unsigned peers = __match_any_sync(FULL, on ? h : (0x80000000u | (uint32_t)lane));
-            if (on) {
-                const uint32_t maxlen = min(n - p, LZQ_MAXLEN);
-                uint32_t best = 0, boff = 0;
-                const unsigned below = peers & ((1u << lane) - 1);
-                if (below) {                                            // candidate B: nearest earlier lane, same hash
-                    const uint32_t d = (uint32_t)(lane - (31 - __clz((int)below)));
-                    if (d <= window && (lzf_ld4(S, p - d) & 0xFFFFFFu) == key) { best = lzf_match_len(S, src, p, p - d, maxlen); boff = d; }
-                }
-                const uint32_t a = sm.H[h];
-                if (a) {                                                // candidate A: most recent position of earlier steps
-                    // the table keeps 16 bits of the position: the distance is exact while it is below 65536; an older
-                    // (aliased) entry yields some other earlier position, which the key compare accepts or rejects on its merits
-                    const uint32_t d = (p + 1 - a) & 0xFFFFu, c = p - d;
-                    if (d != 0 && d <= p && d <= window && d != boff && best < maxlen && (lzf_ld4(S, c) & 0xFFFFFFu) == key) {
-                        const uint32_t l = lzf_match_len(S, src, p, c, maxlen);
-                        if (l > best) { best = l; boff = d; }
-                    }
-                }
-                if (best >= 3 && !(best == 3 && boff > far3)) res = ((best - 1) << 16) | boff;
-            }
-            sm.lenoff[p - t0] = res;
-            const unsigned mm = __ballot_sync(FULL, res != 0);
-            if (lane == 0) sm.M[(p - t0) >> 5] = mm;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int u = 0; u < LZF_STEP; ++u)
-            if (hh[u] != 0xFFFFFFFFu) lzf_insert(&sm.H[hh[u]], s0 + (uint32_t)u * LZF_THREADS + tid + 1, s0 + 1);
-        __syncthreads();
-    }
     // Greedy parse of the tile, p += max(1, len[p]): for a match position q the parse continues at
     // nxt(q) = first match position >= q + len[q] (computed for all match positions in parallel); the visited matches
     // are the chain from the first match at or after the carried-in position -- one shared-memory load per link.
@@ -272,6 +226,62 @@ __device__ __forceinline__ uint32_t lzf_tile(LzFrontSmem& sm, const uint8_t* __r
     __syncthreads();
     // every thread needs the tile's token count: recompute from the last prefix entry
     return sm.prefV[LZF_TILE / 32 - 1] + (uint32_t)__popc(sm.V[LZF_TILE / 32 - 1]);
+}
+
+
+// Match search + greedy parse for tile [t0, t0 + LZF_TILE) of the unit src[0..n).  `window` = largest usable
+// offset, `far3` = largest offset accepted for a 3-byte match.  On return sm.lenoff / sm.M / sm.V / sm.prefV
+// describe the tile and sm.next_p has advanced; the number of tokens starting in the tile is returned.
+// Must be called by all LZF_THREADS threads.
+__device__ __forceinline__ uint32_t lzf_tile(LzFrontSmem& sm, const uint8_t* __restrict__ src, uint32_t n, uint32_t t0,
+                                             uint32_t window, uint32_t far3)
+{
+    const int tid = (int)threadIdx.x, lane = tid & 31;
+    const LzfSrc S(src, n);
+    // LZF_STEP positions per thread and step: their lookups are independent, so every thread has that many chains of loads
+    // in flight, and the two barriers of a step are paid once per LZF_STEP * 256 positions.
+    for (uint32_t s0 = t0; s0 < t0 + LZF_TILE; s0 += LZF_THREADS * LZF_STEP) {
+        uint32_t hh[LZF_STEP];
+#pragma unroll
+        for (int u = 0; u < LZF_STEP; ++u) {
+            const uint32_t p = s0 + (uint32_t)u * LZF_THREADS + tid;
+            uint32_t res = 0, h = 0xFFFFFFFFu;
+            const bool on = p + 3 <= n;
+            uint32_t key = 0;
+            if (on) { key = lzf_ld4(S, p) & 0xFFFFFFu; h = lzf_hash3(key); }
+            hh[u] = h;
+            const unsigned peers = __match_any_sync(FULL, on ? h : (0x80000000u | (uint32_t)lane));
+            if (on) {
+                const uint32_t maxlen = min(n - p, LZQ_MAXLEN);
+                uint32_t best = 0, boff = 0;
+                const unsigned below = peers & ((1u << lane) - 1);
+                if (below) {                                            // candidate B: nearest earlier lane, same hash
+                    const uint32_t d = (uint32_t)(lane - (31 - __clz((int)below)));
+                    if (d <= window && (lzf_ld4(S, p - d) & 0xFFFFFFu) == key) { best = lzf_match_len(S, src, p, p - d, maxlen); boff = d; }
+                }
+                const uint32_t a = sm.H[h];
+                if (a) {                                                // candidate A: most recent position of earlier steps
+                    // the table keeps 16 bits of the position: the distance is exact while it is below 65536; an older
+                    // (aliased) entry yields some other earlier position, which the key compare accepts or rejects on its merits
+                    const uint32_t d = (p + 1 - a) & 0xFFFFu, c = p - d;
+                    if (d != 0 && d <= p && d <= window && d != boff && best < maxlen && (lzf_ld4(S, c) & 0xFFFFFFu) == key) {
+                        const uint32_t l = lzf_match_len(S, src, p, c, maxlen);
+                        if (l > best) { best = l; boff = d; }
+                    }
+                }
+                if (best >= 3 && !(best == 3 && boff > far3)) res = ((best - 1) << 16) | boff;
+            }
+            sm.lenoff[p - t0] = res;
+            const unsigned mm = __ballot_sync(FULL, res != 0);
+            if (lane == 0) sm.M[(p - t0) >> 5] = mm;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < LZF_STEP; ++u)
+            if (hh[u] != 0xFFFFFFFFu) lzf_insert(&sm.H[hh[u]], s0 + (uint32_t)u * LZF_THREADS + tid + 1, s0 + 1);
+        __syncthreads();
+    }
+    return lzf_parse_tile(sm, n, t0);
 }
 
 } // namespace msc

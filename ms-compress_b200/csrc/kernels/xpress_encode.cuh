@@ -14,6 +14,7 @@
 #pragma once
 #include "common.cuh"
 #include "lz_front.cuh"
+#include "lz_exact.cuh"
 
 namespace msc {
 
@@ -43,13 +44,17 @@ struct XpEncSmem {
     uint32_t pend_half;                      // position of the half byte waiting for its high nibble (nibs odd)
     uint32_t cur_flags, cur_flagpos;         // the partially filled flag word
     int status;
+    // reference-parse variant (MODE 2)
+    uint32_t forced_end;                     // positions below it are literals whatever was found there (lzx_forced_literals)
+    uint32_t big_pos, big_len;               // the tile's visited match of LZX_CAP or more bytes (relative position, LZF_TILE = none), its true length
+    uint32_t red;
 };
 
 // bytes of a match item, given whether it has to allocate the shared half byte
 __device__ __forceinline__ uint32_t xpe_match_bytes(uint32_t lm3, bool new_half)
 {
     uint32_t b = 2;
-    if (lm3 >= 7) { b += new_half ? 1u : 0u; if (lm3 - 7 >= 15) { b += 1; if (lm3 - 22 >= 255) b += 2; } }
+    if (lm3 >= 7) { b += new_half ? 1u : 0u; if (lm3 - 7 >= 15) { b += 1; if (lm3 - 22 >= 255) b += lm3 <= 0xFFFFu ? 2u : 6u; } }
     return b;
 }
 
@@ -67,7 +72,10 @@ struct XpPre {                                                       // scratch 
     uint32_t* next_p;                                                // [tiles] position (relative to the segment) where the parse enters the tile
 };
 
-template <bool PRE>
+// MODE 0: matching and emission in one kernel; 1: emission from the tiles of xpress_match_kernel; 2: the reference's parse -- emission
+// from the answers of lz_find_kernel (lz_exact.cuh), the greedy parse runs here, along the whole buffer: byte-identical to the
+// reference's xpress_compress.
+template <int MODE>
 __device__ __forceinline__ void xpress_encode_body(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint32_t count,
                      const uint64_t* __restrict__ in_off, const uint32_t* __restrict__ in_len,
                      const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ out_cap,
@@ -77,13 +85,15 @@ __device__ __forceinline__ void xpress_encode_body(const uint8_t* __restrict__ i
     MSC_DYN_SMEM(smem_raw);
     XpEncSmem& sm = *reinterpret_cast<XpEncSmem*>(smem_raw);
     const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr bool PRE = MODE == 1, EXACT = MODE == 2;
 
     for (uint32_t u = blockIdx.x; u < count; u += gridDim.x) {
         const uint8_t* src = in + in_off[u];
         const uint32_t n = in_len[u], cap = out_cap[u];
         uint8_t* o = out + out_off[u];
-        if (!PRE) for (int i = tid; i < (1 << LZF_HBITS); i += XPE_THREADS) sm.lz.H[i] = 0;
+        if (MODE == 0) for (int i = tid; i < (1 << LZF_HBITS); i += XPE_THREADS) sm.lz.H[i] = 0;
         if (tid == 0) {
+            sm.forced_end = 0; sm.big_pos = LZF_TILE; sm.big_len = 0;
             sm.lz.next_p = 0; sm.lz.ntok = 0;
             sm.items = 0; sm.bytes = 0; sm.nibs = 0; sm.pend_half = 0; sm.cur_flags = 0; sm.cur_flagpos = 0;
             sm.status = (cap < 4) ? ST_BUF : ST_OK;
@@ -119,9 +129,35 @@ __device__ __forceinline__ void xpress_encode_body(const uint8_t* __restrict__ i
                 for (int r = tid; r < LZF_TILE; r += XPE_THREADS) sm.lz.lenoff[r] = lo[r];
                 if (tid < LZF_TILE / 32) sm.lz.V[tid] = pre.visited[(uint64_t)tile * (LZF_TILE / 32) + tid];
                 __syncthreads();
+            } else if (EXACT) {
+                const uint32_t* lo = pre.lenoff + (uint64_t)pre.seg_first[u] * XPE_SEG + t0;
+                const uint32_t fe = sm.forced_end;
+                for (int r = tid; r < LZF_TILE; r += XPE_THREADS) {
+                    const uint32_t p = t0 + (uint32_t)r;
+                    const uint32_t v = (p < n && p >= fe) ? lo[r] : 0u;
+                    sm.lz.lenoff[r] = v;
+                    const unsigned mm = __ballot_sync(FULL, v != 0);
+                    if (lane == 0) sm.lz.M[r >> 5] = mm;
+                }
+                if (tid == 0) sm.big_pos = LZF_TILE;
+                __syncthreads();
+                lzf_parse_tile(sm.lz, n, t0);
+                // a visited match of LZX_CAP bytes or more leaves the tile, so there is at most one: measure it
+                for (int r = tid; r < LZF_TILE; r += XPE_THREADS)
+                    if (((sm.lz.V[r >> 5] >> (r & 31)) & 1) && (sm.lz.lenoff[r] >> 16) == LZX_CAP - 1u) sm.big_pos = (uint32_t)r;
+                __syncthreads();
+                const uint32_t bp = sm.big_pos;
+                if (bp < (uint32_t)LZF_TILE) {
+                    const uint32_t p = t0 + bp;
+                    const uint32_t len = lzx_extend(src, p, sm.lz.lenoff[bp] & 0xFFFFu, n - p - 1u, &sm.red);
+                    if (tid == 0) { sm.big_len = len; sm.lz.next_p = p + len; sm.forced_end = p + len + lzx_forced_literals(p, len, n); }
+                    __syncthreads();
+                }
             } else {
                 lzf_tile(sm.lz, src, n, t0, 8192u, 8192u);
             }
+            const uint32_t big_pos = EXACT ? sm.big_pos : (uint32_t)LZF_TILE, big_len = EXACT ? sm.big_len : 0u;
+            auto len_of = [&](int r, uint32_t lo) -> uint32_t { return (EXACT && (uint32_t)r == big_pos) ? big_len : (lo >> 16) + 1u; };
             // ---- per-thread item statistics over 8 consecutive positions ----
             const uint32_t items0 = sm.items, bytes0 = sm.bytes, nibs0 = sm.nibs;
             uint32_t my_items = 0, my_bytes = 0, my_nibs = 0;
@@ -131,7 +167,7 @@ __device__ __forceinline__ void xpress_encode_body(const uint8_t* __restrict__ i
                 if ((sm.lz.V[r >> 5] >> (r & 31)) & 1) {
                     const uint32_t lo = sm.lz.lenoff[r];
                     ++my_items;
-                    if (lo && (lo >> 16) + 1 - 3 >= 7) ++my_nibs;
+                    if (lo && len_of(r, lo) - 3 >= 7) ++my_nibs;
                 }
             }
             // The half-byte allocation depends on the GLOBAL parity of the nibble-user rank: scan the nibble users first,
@@ -151,7 +187,7 @@ __device__ __forceinline__ void xpress_encode_body(const uint8_t* __restrict__ i
                     if ((sm.lz.V[r >> 5] >> (r & 31)) & 1) {
                         const uint32_t lo = sm.lz.lenoff[r];
                         if (lo) {
-                            const uint32_t lm3 = (lo >> 16) + 1 - 3;
+                            const uint32_t lm3 = len_of(r, lo) - 3;
                             const bool nib = lm3 >= 7;
                             my_bytes += xpe_match_bytes(lm3, nib && ((q & 1) == 0));
                             if (nib) ++q;
@@ -186,7 +222,7 @@ __device__ __forceinline__ void xpress_encode_body(const uint8_t* __restrict__ i
                         uint32_t pos = b + 4 * ((k >> 5) + 1);
                         if ((k & 31) == 0) sm.flagpos[(k >> 5) - w_first] = pos - 4;
                         if (lo) {
-                            const uint32_t lm3 = (lo >> 16) + 1 - 3, off = lo & 0xFFFFu;
+                            const uint32_t lm3 = len_of(r, lo) - 3, off = lo & 0xFFFFu;
                             const uint32_t sym = ((off - 1) << 3) | min(lm3, 7u);
                             atomicOr(&sm.flagw[(k >> 5) - w_first], 0x80000000u >> (k & 31));
                             o[pos] = (uint8_t)sym; o[pos + 1] = (uint8_t)(sym >> 8);
@@ -198,7 +234,13 @@ __device__ __forceinline__ void xpress_encode_body(const uint8_t* __restrict__ i
                                 ++q;
                                 if (lm3 - 7 >= 15) {
                                     o[e++] = (uint8_t)min(lm3 - 22, 255u); ++sz;
-                                    if (lm3 - 22 >= 255) { o[e] = (uint8_t)lm3; o[e + 1] = (uint8_t)(lm3 >> 8); sz += 2; }
+                                    if (lm3 - 22 >= 255) {
+                                        if (lm3 <= 0xFFFFu) { o[e] = (uint8_t)lm3; o[e + 1] = (uint8_t)(lm3 >> 8); sz += 2; }
+                                        else {                                   // src/xpress_compress.cpp:307-312
+                                            o[e] = 0; o[e + 1] = 0; o[e + 2] = (uint8_t)lm3; o[e + 3] = (uint8_t)(lm3 >> 8);
+                                            o[e + 4] = (uint8_t)(lm3 >> 16); o[e + 5] = (uint8_t)(lm3 >> 24); sz += 6;
+                                        }
+                                    }
                                 }
                             }
                             b += sz;
@@ -267,7 +309,7 @@ xpress_encode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, 
                      uint32_t* __restrict__ out_len, int32_t* __restrict__ status,
                      uint32_t seg_tiles, XpressSeg* __restrict__ index, uint32_t index_stride)     // optional restart index
 {
-    xpress_encode_body<false>(in, out, count, in_off, in_len, out_off, out_cap, out_len, status, seg_tiles, index, index_stride, XpPre{});
+    xpress_encode_body<0>(in, out, count, in_off, in_len, out_off, out_cap, out_len, status, seg_tiles, index, index_stride, XpPre{});
 }
 
 // Pass 2 of the two-pass variant: emission from the per-tile results of xpress_match_kernel.
@@ -278,11 +320,22 @@ xpress_emit_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, ui
                    uint32_t* __restrict__ out_len, int32_t* __restrict__ status,
                    uint32_t seg_tiles, XpressSeg* __restrict__ index, uint32_t index_stride, XpPre pre)
 {
-    xpress_encode_body<true>(in, out, count, in_off, in_len, out_off, out_cap, out_len, status, seg_tiles, index, index_stride, pre);
+    xpress_encode_body<1>(in, out, count, in_off, in_len, out_off, out_cap, out_len, status, seg_tiles, index, index_stride, pre);
+}
+
+// Emission of the reference's parse: pre.lenoff = the answers of lz_find_kernel (indexed seg_first[u] * XPE_SEG + position).
+__global__ void __launch_bounds__(XPE_THREADS)
+xpress_emit_exact_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint32_t count,
+                         const uint64_t* __restrict__ in_off, const uint32_t* __restrict__ in_len,
+                         const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ out_cap,
+                         uint32_t* __restrict__ out_len, int32_t* __restrict__ status,
+                         uint32_t seg_tiles, XpressSeg* __restrict__ index, uint32_t index_stride, XpPre pre)
+{
+    xpress_encode_body<2>(in, out, count, in_off, in_len, out_off, out_cap, out_len, status, seg_tiles, index, index_stride, pre);
 }
 
 // seg_first[u] = segments of the buffers before u, seg_first[count] = all of them; totals[0] = that, totals[1] = input bytes.
-// Single block; also clears the work counter of the match kernel.
+// Single block; also clears the four work counters of the kernels that follow.
 __global__ void __launch_bounds__(1024)
 xpress_segments_kernel(const uint32_t* __restrict__ in_len, uint32_t count, uint32_t* __restrict__ seg_first, unsigned long long* __restrict__ totals,
                        uint32_t* __restrict__ work_counter)
@@ -291,7 +344,8 @@ xpress_segments_kernel(const uint32_t* __restrict__ in_len, uint32_t count, uint
     __shared__ uint32_t carry;
     __shared__ unsigned long long bytes;
     const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { carry = 0; bytes = 0; *work_counter = 0; }
+    if (tid == 0) { carry = 0; bytes = 0; }
+    if (tid < 4) work_counter[tid] = 0;                                  // one counter per persistent kernel of the pipeline
     __syncthreads();
     unsigned long long my_bytes = 0;
     for (uint32_t u0 = 0; u0 < count; u0 += 1024) {

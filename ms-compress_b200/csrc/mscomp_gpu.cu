@@ -638,12 +638,15 @@ static MSCompStatus xpress_encode_launch(mscomp_gpu_ctx* ctx, const uint8_t* d_i
     cudaSetDevice(ctx->device);
     MSC_OPT_IN_SMEM(xpress_encode_kernel, sizeof(XpEncSmem));
     const uint32_t cap = (uint32_t)ctx->sm_count * 4;
-    static const char* mode = getenv("MSCOMP_XPRESS_ENCODE");          // "one" / "two" force a variant
-    bool two_pass = false;
+    // Default: the reference's parse (lz_exact.cuh), byte-identical to its xpress_compress.  "one" / "two" select the earlier
+    // bulk-synchronous matcher (1 table candidate + 1 lane peer; valid streams, other bytes), fused or per 64 KiB segment.
+    static const char* mode = getenv("MSCOMP_XPRESS_ENCODE");
+    const bool fast_one = mode && strcmp(mode, "one") == 0, fast_two = mode && strcmp(mode, "two") == 0;
+    bool two_pass = false, exact = false;
     uint32_t* seg_first = nullptr;
     uint32_t* work = nullptr;
     unsigned long long total_segs = 0;
-    if (!(mode && strcmp(mode, "one") == 0)) {
+    if (!fast_one) {
         seg_first = (uint32_t*)ctx->get(SC_AUX1, ((size_t)b->count + 2) * sizeof(uint32_t) + 64);
         unsigned long long* d_tot = (unsigned long long*)ctx->get(SC_RESULT, 1024);
         unsigned long long* h_tot = (unsigned long long*)ctx->get_pinned(1024);
@@ -654,13 +657,34 @@ static MSCompStatus xpress_encode_launch(mscomp_gpu_ctx* ctx, const uint8_t* d_i
             cudaMemcpyAsync(h_tot, d_tot, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream);
             if (cudaStreamSynchronize(ctx->stream) == cudaSuccess) {
                 total_segs = h_tot[0];
-                const unsigned long long total_in = h_tot[1];
-                two_pass = total_segs > 0 && total_segs < (1ull << 24) &&
-                           ((mode && strcmp(mode, "two") == 0) || total_in / b->count >= (128u << 10));
+                if (total_segs < (1ull << 24)) { two_pass = fast_two && total_segs > 0; exact = !fast_two; }
             }
         }
     }
     XpPre pre{};
+    if (exact) {
+        const size_t npos = (size_t)total_segs * LZX_SEG;
+        uint8_t* sc = (uint8_t*)ctx->get(SC_AUX2, npos * 6 + 256);
+        if (!sc) return MSCOMP_MEM_ERROR;
+        pre.seg_first = seg_first;
+        pre.lenoff = (uint32_t*)sc;
+        uint16_t* dist = (uint16_t*)(sc + npos * 4);
+        MSC_OPT_IN_SMEM(xpress_emit_exact_kernel, sizeof(XpEncSmem));
+        if (total_segs) {
+            MSC_OPT_IN_SMEM(lz_prev_kernel<uint16_t>, 65536);
+            const unsigned long long pieces = total_segs * (LZX_SEG / LZX_PIECE);
+            const uint32_t pg = pieces < (unsigned long long)ctx->sm_count * 3 ? (uint32_t)pieces : (uint32_t)ctx->sm_count * 3;
+            MSC_LAUNCH_SMEM(ctx, lz_prev_kernel<uint16_t>, pg, 32, 65536, d_in, b->count, b->d_in_off, b->d_in_len, (const uint32_t*)seg_first, work,
+                            dist, 8192u, LZX_PIECE);
+            const uint32_t fg = total_segs < (unsigned long long)ctx->sm_count * 8 ? (uint32_t)total_segs : (uint32_t)ctx->sm_count * 8;
+            MSC_LAUNCH(ctx, lz_find_kernel, fg, LZX_FIND_THREADS, d_in, b->count, b->d_in_off, b->d_in_len, (const uint32_t*)seg_first, work + 1,
+                       (const uint16_t*)dist, pre.lenoff, 8192u, 0u);
+        }
+        MSC_LAUNCH_SMEM(ctx, xpress_emit_exact_kernel, b->count < cap ? b->count : cap, XPE_THREADS, sizeof(XpEncSmem),
+                        d_in, d_out, b->count, b->d_in_off, b->d_in_len, b->d_out_off, b->d_out_cap, b->d_out_len, b->d_status,
+                        seg_tiles, index, index_stride, pre);
+        return msc_cuda_status(cudaGetLastError(), "xpress_compress");
+    }
     if (two_pass) {
         const size_t tiles = (size_t)total_segs * XPE_SEG_TILES;
         const size_t lo_b = tiles * LZF_TILE * sizeof(uint32_t), v_b = tiles * (LZF_TILE / 32) * sizeof(uint32_t), n_b = tiles * sizeof(uint32_t);

@@ -213,15 +213,39 @@ void emu_xpress_encode2(const uint8_t* in, uint8_t* out, uint32_t count, const u
     using namespace msc;
     std::vector<uint32_t> seg_first(count + 2);
     unsigned long long totals[2] = {0, 0};
-    uint32_t work = 0;
-    emu::launch(xpress_segments_kernel, dim3e(1), dim3e(1024), in_len, count, seg_first.data(), totals, &work);
+    uint32_t work[4] = {0, 0, 0, 0};
+    emu::launch(xpress_segments_kernel, dim3e(1), dim3e(1024), in_len, count, seg_first.data(), totals, work);
     const size_t tiles = (size_t)totals[0] * XPE_SEG_TILES;
     std::vector<uint32_t> lenoff(tiles * LZF_TILE + 1), visited(tiles * (LZF_TILE / 32) + 1), next_p(tiles + 1);
     if (totals[0])
-        emu::launch(xpress_match_kernel, dim3e(grid), dim3e(XPE_THREADS), in, count, in_off, in_len, (const uint32_t*)seg_first.data(), &work,
+        emu::launch(xpress_match_kernel, dim3e(grid), dim3e(XPE_THREADS), in, count, in_off, in_len, (const uint32_t*)seg_first.data(), work,
                     lenoff.data(), visited.data(), next_p.data());
     XpPre pre{seg_first.data(), lenoff.data(), visited.data(), next_p.data()};
     emu::launch(xpress_emit_kernel, dim3e(grid), dim3e(XPE_THREADS), in, out, count, in_off, in_len, out_off, out_cap, out_len, status,
+                index ? seg_bytes / (uint32_t)LZF_TILE : 0u, (XpressSeg*)index, stride, pre);
+}
+
+// the reference's parse: hash-chain links (one warp per 32 KiB piece), Find at every position, greedy parse + emission per buffer
+void emu_xpress_encode_exact(const uint8_t* in, uint8_t* out, uint32_t count, const uint64_t* in_off, const uint32_t* in_len,
+                             const uint64_t* out_off, const uint32_t* out_cap, uint32_t* out_len, int32_t* status, uint32_t grid,
+                             uint32_t seg_bytes, void* index, uint32_t stride)
+{
+    using namespace msc;
+    std::vector<uint32_t> seg_first(count + 2);
+    unsigned long long totals[2] = {0, 0};
+    uint32_t work[4] = {0, 0, 0, 0};
+    emu::launch(xpress_segments_kernel, dim3e(1), dim3e(1024), in_len, count, seg_first.data(), totals, work);
+    const size_t npos = (size_t)totals[0] * LZX_SEG;
+    std::vector<uint16_t> dist(npos + 1, 0xDEAD);
+    std::vector<uint32_t> lenoff(npos + 1, 0xDEADBEEFu);
+    if (totals[0]) {
+        emu::launch(lz_prev_kernel<uint16_t>, dim3e(grid), dim3e(32), in, count, in_off, in_len, (const uint32_t*)seg_first.data(), work,
+                    dist.data(), 8192u, LZX_PIECE);
+        emu::launch(lz_find_kernel, dim3e(grid), dim3e(LZX_FIND_THREADS), in, count, in_off, in_len, (const uint32_t*)seg_first.data(), work + 1,
+                    (const uint16_t*)dist.data(), lenoff.data(), 8192u, 0u);
+    }
+    XpPre pre{seg_first.data(), lenoff.data(), nullptr, nullptr};
+    emu::launch(xpress_emit_exact_kernel, dim3e(grid), dim3e(XPE_THREADS), in, out, count, in_off, in_len, out_off, out_cap, out_len, status,
                 index ? seg_bytes / (uint32_t)LZF_TILE : 0u, (XpressSeg*)index, stride, pre);
 }
 

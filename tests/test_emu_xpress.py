@@ -158,6 +158,40 @@ def test_xpress_two_pass_encoder(emu, oracle, ms, with_index):
             assert all(o == p for o, p in zip(outs, plains) if p)
 
 
+def test_xpress_reference_parse_is_byte_identical(emu, oracle, ms):
+    """The default plain-Xpress encoder (lz_exact.cuh: hash-chain links, Find at every position, greedy parse + emission) writes the
+    very bytes of the reference's xpress_compress: edge sizes, the end-of-input length quirk, hash collisions (4-symbol data), matches
+    longer than LZX_CAP that the parse extends, and the literals the reference is forced into after a match that outruns its 8 KiB
+    dictionary fills (src/xpress_compress.cpp:269)."""
+    rnd = random.Random(5)
+    plains = [ms.generate(kind, n, 3 + n) for kind in ("text", "runs", "random") for n in (1, 2, 3, 4, 5, 31, 32, 33, 100, 4096, 70000)]
+    plains += [b"", b"abc" * 50000, bytes(140000), bytes(rnd.getrandbits(8) & 3 for _ in range(70000)),
+               bytes(9000) + ms.generate("text", 30000, 1), bytes(30000) + b"x" + bytes(30000) + ms.generate("text", 1000, 2),
+               bytes(300000) + ms.generate("text", 3000, 2) + bytes(70000) + b"q" + bytes(70000),
+               ms.generate("text", 20000, 7) * 3, ms.generate("text", 140001, 9)]
+    caps = [MAXSZ["xpress"](len(p)) for p in plains]
+    seg_bytes, stride = 16384, 24
+    index = np.zeros(len(plains) * stride * 6, dtype=np.uint32)
+    st, _, comps = emu_batch(emu, "emu_xpress_encode_exact", plains, caps, grid=3, extra=(ctypes.c_uint32(seg_bytes), P(index), ctypes.c_uint32(stride)))
+    assert not st.any()
+    for p, c in zip(plains, comps):
+        assert c == oracle.compress("xpress", p), len(p)
+    # exact capacity passes, one byte less is a buffer error
+    big = [(p, c) for p, c in zip(plains, comps) if len(p) > 100]
+    st2, _, _ = emu_batch(emu, "emu_xpress_encode_exact", [p for p, _ in big], [len(c) for _, c in big],
+                          extra=(ctypes.c_uint32(seg_bytes), ctypes.c_void_p(0), ctypes.c_uint32(0)))
+    assert not st2.any()
+    st3, _, _ = emu_batch(emu, "emu_xpress_encode_exact", [p for p, _ in big], [len(c) - 1 for _, c in big],
+                          extra=(ctypes.c_uint32(seg_bytes), ctypes.c_void_p(0), ctypes.c_uint32(0)))
+    assert (st3 == -5).all()
+    # the restart index written along the way works
+    for blk in (0, 1):
+        st4, _, outs = emu_batch(emu, "emu_xpress_decode_indexed", comps, [len(p) for p in plains],
+                                 extra=(P(index), ctypes.c_uint32(stride), ctypes.c_uint32(blk)))
+        assert list(st4) == [0 if p else -3 for p in plains]
+        assert all(o == p for o, p in zip(outs, plains) if p)
+
+
 # ---- Xpress-Huffman through the restart index (xhuff_index.cuh + xhuff_decode_indexed.cuh) -----------------------------------
 
 def _second(emu):

@@ -1,6 +1,9 @@
 """Xpress and Xpress-Huffman parity on the B200 through the C ABI and the device batch API.
-Decode: bit-exact against the oracle, same status codes.  Encode: round-trips through the oracle's decoder (a restatement
-of the reference's), stays within max_compressed_size and near the reference's ratio."""
+Decode: bit-exact against the oracle, same status codes.  Encode, plain Xpress: the very bytes of the reference's encoder
+(oracle == compiled reference, tests/test_oracle.py; reference-made digests in tests/golden/digests.json).  Encode, Xpress-Huffman:
+round-trips through the oracle's decoder (a restatement of the reference's), stays within max_compressed_size and near the
+reference's ratio."""
+import hashlib
 import glob
 import json
 import os
@@ -48,6 +51,8 @@ def test_decode_parity_and_encode_roundtrip(ms, oracle, fmt, kind):
         if fmt == "xpress" and n == 0:
             assert comp == ref_comp == b"\xff\xff\xff\xff"
             continue
+        if fmt == "xpress":
+            assert comp == ref_comp, (kind, n)                                # byte-identical to the reference's encoder
         assert oracle.decompress(fmt, comp, n) == (0, plain), (kind, n)       # the reference's decoder accepts our stream
         assert ms.raw_call(fmt + "_decompress", comp, n) == (0, plain), (kind, n)
         assert ms.raw_call(fmt + "_compress", plain, len(comp)) == (0, comp)      # exact capacity
@@ -84,7 +89,32 @@ def test_degenerate_inputs(ms, oracle, fmt):
         assert st == 0
         assert oracle.decompress(fmt, comp, len(plain)) == (0, plain)
         ref_comp = oracle.compress(fmt, plain)
+        if fmt == "xpress":
+            assert comp == ref_comp, len(plain)
         assert ms.raw_call(fmt + "_decompress", ref_comp, len(plain)) == (0, plain)
+
+
+def test_xpress_generator_digests(ms):
+    """md5 of our plain-Xpress streams == md5 of the compiled reference's (made in the build container by make_golden.py)."""
+    dig = json.load(open(golden_path("digests.json")))
+    for key, d in dig.items():
+        kind, n = key.rsplit("_", 1)
+        plain = ms.generate(kind, int(n), 42)
+        assert hashlib.md5(plain).hexdigest() == d["input_md5"]
+        st, comp = ms.raw_call("xpress_compress", plain, MAXSZ["xpress"](len(plain)))
+        assert st == 0 and len(comp) == d["xpress"]["size"] and hashlib.md5(comp).hexdigest() == d["xpress"]["md5"], key
+
+
+def test_xpress_long_matches_and_forced_literals(ms, oracle):
+    """Matches longer than the finder's cap are measured by the parse; after a match that outruns the reference's 8 KiB dictionary
+    fills the reference emits literals where it would otherwise match (src/xpress_compress.cpp:269) -- same bytes here."""
+    rnd = random.Random(5)
+    cases = [bytes(9000) + ms.generate("text", 30000, 1), bytes(30000) + b"x" + bytes(30000) + ms.generate("text", 1000, 2),
+             bytes(300000) + ms.generate("text", 3000, 2) + bytes(70000) + b"q" + bytes(70000), ms.generate("text", 20000, 7) * 3,
+             bytes(rnd.getrandbits(8) & 3 for _ in range(70000)), ms.generate("text", 5000, 3) * 300, bytes(3 << 20)]
+    for plain in cases:
+        st, comp = ms.raw_call("xpress_compress", plain, MAXSZ["xpress"](len(plain)))
+        assert st == 0 and comp == oracle.compress("xpress", plain), len(plain)
 
 
 @pytest.mark.parametrize("fmt", FMTS)
