@@ -40,6 +40,10 @@ __device__ __forceinline__ uint32_t lzx_hash(uint32_t key3) { return (((key3 & 0
 // 32 positions per round: the nearest earlier lane with the same hash (__match_any_sync) wins, else the table; the highest lane of
 // every hash group updates the table.  dist[] (one entry per position, indexed like the units' segments: seg_first[u] * LZX_SEG + p)
 // receives p - prev(p), or 0 when there is none within the window.
+// The rounds form one dependent chain through the table, so nothing else may wait inside a round: the input comes through a
+// shared-memory stage of LZX_STAGE bytes that is refilled from registers loaded one stage ahead (aligned 16-byte loads, the
+// whole warp), and every round reads its 3-byte keys from there.
+constexpr uint32_t LZX_STAGE = 2048;           // positions per stage (a multiple of 512); the stage holds 16 bytes more for the keys at its end
 template <typename TE>
 __global__ void __launch_bounds__(32)
 lz_prev_kernel(const uint8_t* __restrict__ in, uint32_t count, const uint64_t* __restrict__ in_off, const uint32_t* __restrict__ in_len,
@@ -48,9 +52,11 @@ lz_prev_kernel(const uint8_t* __restrict__ in, uint32_t count, const uint64_t* _
 {
     MSC_DYN_SMEM(smem_raw);
     TE* T = reinterpret_cast<TE*>(smem_raw);
+    uint32_t* stage = reinterpret_cast<uint32_t*>(smem_raw + 32768u * sizeof(TE));         // LZX_STAGE + 16 bytes (+ slack for the look-ahead)
     const int lane = (int)threadIdx.x;
     const uint32_t per_seg = LZX_SEG / piece;
     const uint32_t total = seg_first[count] * per_seg;
+    constexpr int VPL = LZX_STAGE / 512;                               // 16-byte vectors per lane and stage
     for (;;) {
         uint32_t w = 0;
         if (lane == 0) w = atomicAdd(work_counter, 1u);
@@ -64,36 +70,79 @@ lz_prev_kernel(const uint8_t* __restrict__ in, uint32_t count, const uint64_t* _
         if (s0 >= n) continue;
         const uint32_t s1 = min(s0 + piece, n);
         const uint32_t w0 = s0 > window ? s0 - window : 0u;
-        const LzfSrc S(in + in_off[u], n);
+        // the unit as aligned 16-byte vectors: vector v holds bytes [16 v - skew, 16 v - skew + 16) of the unit
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(in + in_off[u]);
+        const uint4* vbase = reinterpret_cast<const uint4*>(addr & ~static_cast<uintptr_t>(15));
+        const uint32_t skew = (uint32_t)(addr & 15), vlast = (skew + n - 1u) >> 4;      // last vector holding a byte of the unit
         uint16_t* dst = dist + (uint64_t)seg_first[u] * LZX_SEG;
         for (uint32_t i = (uint32_t)lane; i < 32768u * sizeof(TE) / 16u; i += 32) reinterpret_cast<uint4*>(T)[i] = make_uint4(0, 0, 0, 0);
+        // stage k covers unit bytes [b0 + k * LZX_STAGE, ... + LZX_STAGE + 16), b0 = the 16-byte granule of w0
+        const uint32_t v0 = (skew + w0) >> 4;                          // first vector of stage 0
+        uint4 nx[VPL + 1];
+        auto fetch = [&](uint32_t vfirst) {
+#pragma unroll
+            for (int j = 0; j < VPL; ++j) { const uint32_t v = vfirst + (uint32_t)(j * 32 + lane); nx[j] = v <= vlast ? __ldg(vbase + v) : make_uint4(0, 0, 0, 0); }
+            const uint32_t v = vfirst + (uint32_t)(VPL * 32);
+            nx[VPL] = (lane == 0 && v <= vlast) ? __ldg(vbase + v) : make_uint4(0, 0, 0, 0);
+        };
+        fetch(v0);
         __syncwarp();
-        for (uint32_t p0 = w0; p0 < s1; p0 += 32) {
-            const uint32_t p = p0 + (uint32_t)lane;
-            const bool on = p + 3 <= n;
-            const uint32_t h = on ? lzx_hash(lzf_ld4(S, p)) : (0x8000u | (uint32_t)lane);
-            const unsigned peers = __match_any_sync(FULL, h);
-            const unsigned below = peers & ((1u << lane) - 1u);
-            uint32_t d = 0;
-            if (on) {
-                if (below) d = (uint32_t)(lane - (31 - __clz((int)below)));
-                else { const uint32_t t = T[h]; if (t) d = (p - w0 + 1u) - t; }
+        for (uint32_t sb = 0;; ++sb) {                                 // stages
+            const uint32_t vfirst = v0 + sb * (LZX_STAGE / 16);
+            const uint32_t pb = vfirst * 16u - skew;                   // unit position of stage byte 0 (may be "negative" for the first stage: wraps, unused)
+#pragma unroll
+            for (int j = 0; j < VPL; ++j) reinterpret_cast<uint4*>(stage)[j * 32 + lane] = nx[j];
+            if (lane == 0) reinterpret_cast<uint4*>(stage)[VPL * 32] = nx[VPL];
+            __syncwarp();
+            const uint32_t pend = pb + LZX_STAGE;                      // positions of this stage: [max(pb, w0), min(pend, s1))
+            if (pend < s1) fetch(vfirst + LZX_STAGE / 16);              // the next stage is on its way while this one is processed
+            const uint32_t first = (sb == 0) ? w0 : pb;
+            // the hash of a round is computed one round ahead: it does not depend on the table, the chain through the table does not wait for it
+            auto hash_at = [&](uint32_t q) -> uint32_t { const uint32_t o = q - pb; return lzx_hash(__funnelshift_r(stage[o >> 2], stage[(o >> 2) + 1], 8u * (o & 3u))); };
+            uint32_t h_next = hash_at(first + (uint32_t)lane);
+            for (uint32_t p0 = first; p0 < min(pend, s1); p0 += 32) {
+                const uint32_t p = p0 + (uint32_t)lane;
+                const bool on = p + 3 <= n && p < pend;
+                const uint32_t h = h_next;
+                h_next = hash_at(p + 32u);                             // (beyond the stage on its last round: read from the slack, never used)
+                const uint32_t mine = p - w0 + 1u;
+                // Fast path, no two lanes with the same hash: everybody reads the table, writes itself, and reads itself back.
+                // (__match_any_sync costs one pass per distinct value -- 32 of them on ordinary data -- so it is kept for the
+                // rounds where some lane lost the write.)
+                const uint32_t told = on ? (uint32_t)T[h] : 0u;
+                __syncwarp();
+                if (on) T[h] = (TE)mine;
+                __syncwarp();
+                const bool lost = on && (uint32_t)T[h] != mine;
+                uint32_t d = (on && told) ? mine - told : 0u;
+                if (__any_sync(FULL, lost)) {
+                    const unsigned peers = __match_any_sync(FULL, on ? h : (0x8000u | (uint32_t)lane));
+                    const unsigned below = peers & ((1u << lane) - 1u);
+                    if (on && below) d = (uint32_t)(lane - (31 - __clz((int)below)));
+                    __syncwarp();
+                    if (on && (peers >> lane) == 1u) T[h] = (TE)mine;       // the highest lane of every hash group is the latest position
+                    __syncwarp();
+                }
                 if (d > window) d = 0;
+                if (p >= s0 && p < s1 && p < pend) dst[p] = (uint16_t)d;
             }
             __syncwarp();
-            if (on && (peers >> lane) == 1u) T[h] = (TE)(p - w0 + 1u);
-            __syncwarp();
-            if (p >= s0 && p < s1) dst[p] = (uint16_t)d;
+            if (pend >= s1) break;
         }
-        __syncwarp();
     }
 }
 
-// find(p) for every position of the units, one thread per position (persistent blocks pull 64 KiB segments).
-// lenoff[] (indexed like dist[]) receives (len - 1) << 16 | offset, or 0 when Find would return less than 3.
-// chunk = 0: the match may run to the end of the unit (plain Xpress); otherwise it is also clipped at the end of the chunk it
-// starts in and needs 3 bytes of chunk left (Xpress-Huffman: src/xpress_huff_compress.cpp:90-93).
-__global__ void __launch_bounds__(LZX_FIND_THREADS)
+// find(p) for every position of the units: lenoff[] (indexed like dist[]) receives (len - 1) << 16 | offset, or 0 when Find would
+// return less than 3.  dist = the links (lz_prev_kernel).  chunk = 0: a match may run to the end of the unit (plain Xpress);
+// otherwise the caller clips it at the end of the chunk it starts in and does not ask at all with fewer than 3 bytes of chunk
+// left (Xpress-Huffman: src/xpress_huff_compress.cpp:90-93).
+// Persistent blocks pull 64 KiB segments; a thread owns every LZX_FIND_THREADS-th position of the segment and runs ONE flat loop
+// over the links of all of them -- a lane whose chain ends early (a rare trigram) moves on to its next position instead of idling
+// until the longest chain of the warp (a common trigram, 11 links) is done.
+// A candidate can only beat the current length `len` if it agrees on byte `len`: one probe word per link decides (the three
+// bytes of the key while len is still 2, afterwards the four bytes ending at index len); a full compare only follows a hit.
+template <int MINB>
+__global__ void __launch_bounds__(LZX_FIND_THREADS, MINB)
 lz_find_kernel(const uint8_t* __restrict__ in, uint32_t count, const uint64_t* __restrict__ in_off, const uint32_t* __restrict__ in_len,
                const uint32_t* __restrict__ seg_first, uint32_t* __restrict__ work_counter, const uint16_t* __restrict__ dist,
                uint32_t* __restrict__ lenoff, uint32_t window, uint32_t chunk)
@@ -115,36 +164,157 @@ lz_find_kernel(const uint8_t* __restrict__ in, uint32_t count, const uint64_t* _
         const LzfSrc S(src, n);
         const uint16_t* dd = dist + (uint64_t)seg_first[u] * LZX_SEG;
         uint32_t* out = lenoff + (uint64_t)seg_first[u] * LZX_SEG;
-        for (uint32_t p = s0 + (uint32_t)tid; p < s1; p += LZX_FIND_THREADS) {
-            uint32_t res = 0;
-            if (p + 3 <= n) {
-                const uint32_t lim = n - p - 1u;                                 // GetMatchLength never reaches the last byte
-                const uint32_t rem = chunk ? chunk - (p % chunk) : 0xFFFFFFFFu;  // Find itself does not know about chunks ...
-                const uint32_t maxlen = min(lim, LZX_CAP);
-                if (maxlen >= 3u && rem >= 3u) {
-                    const uint32_t key = lzf_ld4(S, p);
-                    uint32_t len = 2, off = 0, x = p;
-                    for (uint32_t c = 0; c < LZX_CHAIN; ++c) {
-                        const uint32_t d = dd[x];
-                        if (!d || p - (x - d) > window) break;
-                        x -= d;
-                        const uint32_t cw = lzf_ld4(S, x);
-                        if ((cw ^ key) & 0xFFFFu) continue;                     // a hash collision: uses up a link, nothing else
-                        // a longer match must also agree on the four bytes ending at index len (bytes 0 and 1 are known to agree)
-                        if (len >= 3u && lzf_ld4(S, x + len - 3u) != lzf_ld4(S, p + len - 3u)) continue;
-                        const uint32_t l = lzf_match_len(S, src, p, x, maxlen);
-                        if (l > len) {
-                            len = l; off = p - x;
-                            if (len >= LZX_NICE || len == maxlen) break;        // (nothing is longer than maxlen: the walk could only waste links)
-                        }
+
+        // A lane is in one of three states: ST_HOP (follow a link, probe), ST_CMP (the probe hit: measure the candidate), ST_NEW (its
+        // position is answered: store, take the next one).  Every round the WARP runs the code of one state only -- the one most of
+        // its lanes are in -- so the rare, long pieces (compare, new position) run for many lanes at once instead of once per link
+        // round with a handful of lanes each.
+        enum { ST_HOP = 0, ST_CMP = 1, ST_NEW = 2, ST_END = 3 };
+        uint32_t p = s0 + (uint32_t)tid;
+        uint32_t x = 0, len = 0, off = 0, po = 0, mask = 0, pk = 0, links = 0, maxlen = 0, rem = 0;
+        uint32_t st = ST_NEW, res = 0;
+        bool fresh = true;                                             // ST_NEW without an answer to store (the lane's first position)
+        if (p >= s1) { st = ST_END; }
+        for (;;) {
+            const unsigned b_hop = __ballot_sync(FULL, st == ST_HOP), b_cmp = __ballot_sync(FULL, st == ST_CMP), b_new = __ballot_sync(FULL, st == ST_NEW);
+            if (!(b_hop | b_cmp | b_new)) break;
+            const int c_hop = __popc(b_hop), c_cmp = __popc(b_cmp), c_new = __popc(b_new);
+            if (c_hop >= c_cmp && c_hop >= c_new) {
+                if (st == ST_HOP) {
+                    const uint32_t d = dd[x];
+                    if (!d || p - x + d > window || links == 0u) { res = len >= 3u ? ((min(len, rem) - 1u) << 16) | off : 0u; st = ST_NEW; }
+                    else {
+                        x -= d; --links;
+                        if ((lzf_ld4(S, x + po) & mask) == pk) st = ST_CMP;        // (hash collisions and shorter matches only use up a link)
                     }
-                    len = min(len, rem);                                        // ... the caller clips what it found (:93)
-                    if (len >= 3u) res = ((len - 1u) << 16) | off;
+                }
+            } else if (c_cmp >= c_new) {
+                if (st == ST_CMP) {
+                    const uint32_t l = lzf_match_len(S, src, p, x, maxlen);
+                    st = ST_HOP;
+                    if (l > len) {
+                        len = l; off = p - x;
+                        if (len >= LZX_NICE || len == maxlen) {        // (nothing is longer than maxlen: the walk could only waste links)
+                            res = ((min(len, rem) - 1u) << 16) | off;  // the caller clips what Find found (:93); rem >= 3
+                            st = ST_NEW;
+                        } else { po = len - 3u; mask = 0xFFFFFFFFu; pk = lzf_ld4(S, p + po); }
+                    }
+                }
+            } else {
+                if (st == ST_NEW) {
+                    if (!fresh) { out[p] = res; p += LZX_FIND_THREADS; }
+                    fresh = false;
+                    for (;;) {                                         // positions where Find is not even asked answer 0 on the spot
+                        if (p >= s1) { st = ST_END; break; }
+                        bool ask = p + 3u <= n;
+                        if (ask) {
+                            rem = chunk ? chunk - (p % chunk) : 0xFFFFFFFFu;          // Find itself does not know about chunks ...
+                            maxlen = min(n - p - 1u, LZX_CAP);                         // GetMatchLength never reaches the last byte (:74-93)
+                            ask = maxlen >= 3u && rem >= 3u;
+                        }
+                        if (ask) { x = p; len = 2; off = 0; po = 0; mask = 0xFFFFFFu; pk = lzf_ld4(S, p) & mask; links = LZX_CHAIN; st = ST_HOP; break; }
+                        out[p] = 0; p += LZX_FIND_THREADS;
+                    }
                 }
             }
-            out[p] = res;
         }
     }
+}
+
+// The greedy parse of every tile of LZF_TILE positions AS IF a token started at the tile's first position, from the answers of
+// lz_find_kernel.  Per tile (global tile number seg_first[u] * (LZX_SEG / LZF_TILE) + position / LZF_TILE): the token-start bitmap
+// visited0[LZF_TILE / 32] of that parse and exit0 = the unit position where it leaves the tile.  Greedy parses that meet stay
+// together, so the true parse of a tile -- entered wherever the previous tile's last match ends -- follows its own steps only until
+// it lands on a token start of this one (lzx_merge_parse): the serial pass along the unit no longer parses, it merges.
+__global__ void __launch_bounds__(LZF_THREADS)
+lz_parse0_kernel(uint32_t count, const uint32_t* __restrict__ in_len, const uint32_t* __restrict__ seg_first, uint32_t* __restrict__ work_counter,
+                 const uint32_t* __restrict__ lenoff, uint32_t* __restrict__ visited0, uint32_t* __restrict__ exit0)
+{
+    MSC_DYN_SMEM(smem_raw);
+    LzFrontSmem& lz = *reinterpret_cast<LzFrontSmem*>(smem_raw);
+    __shared__ uint32_t s_work;
+    const int tid = (int)threadIdx.x, lane = tid & 31;
+    const uint32_t total = seg_first[count];
+    for (;;) {
+        if (tid == 0) s_work = atomicAdd(work_counter, 1u);
+        __syncthreads();
+        const uint32_t w = s_work;
+        __syncthreads();
+        if (w >= total) break;
+        uint32_t lo = 0, hi = count;
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) / 2; if (seg_first[mid] <= w) lo = mid; else hi = mid; }
+        const uint32_t u = lo, n = in_len[u];
+        const uint32_t s0 = (w - seg_first[u]) * LZX_SEG, s1 = min(s0 + LZX_SEG, n);
+        const uint32_t* src = lenoff + (uint64_t)seg_first[u] * LZX_SEG;
+        for (uint32_t t0 = s0; t0 < s1; t0 += LZF_TILE) {
+            for (int r = tid; r < LZF_TILE; r += LZF_THREADS) {
+                const uint32_t p = t0 + (uint32_t)r;
+                const uint32_t res = p < s1 ? src[p] : 0u;
+                lz.lenoff[r] = res;
+                const unsigned mm = __ballot_sync(FULL, res != 0);
+                if (lane == 0) lz.M[r >> 5] = mm;
+            }
+            if (tid == 0) lz.next_p = t0;
+            __syncthreads();
+            lzf_parse_tile(lz, n, t0);
+            const uint64_t tile = (uint64_t)seg_first[u] * (LZX_SEG / LZF_TILE) + t0 / LZF_TILE;
+            if (tid < LZF_TILE / 32) visited0[tile * (LZF_TILE / 32) + tid] = lz.V[tid];
+            if (tid == 0) exit0[tile] = lz.next_p;
+            __syncthreads();
+        }
+    }
+}
+
+// The true parse of a tile from the parse that assumed a token at the tile's first position (lz_find_kernel).  In: sm.lenoff (with
+// the forced literals already zeroed), sm.V = visited0 of the tile, sm.next_p = where the parse enters (unit position), exit0 of the
+// tile; fe = unit position below which every position is a literal.  One thread steps from the entry until it stands on a token
+// start of the assumed parse that lies at or beyond fe (from there on the two agree) or leaves the tile.  Out: sm.V, sm.prefV,
+// sm.next_p as lzf_parse_tile leaves them.  Must be called by all LZF_THREADS threads.
+__device__ __forceinline__ void lzx_merge_parse(LzFrontSmem& sm, uint32_t n, uint32_t t0, uint32_t exit0, uint32_t fe)
+{
+    const int tid = (int)threadIdx.x, lane = tid & 31;
+    const uint32_t tend_r = min(t0 + LZF_TILE, n) - t0;
+    if (tid < 32) {
+        const uint32_t start_r = sm.next_p > t0 ? sm.next_p - t0 : 0u;
+        const uint32_t fe_r = fe > t0 ? fe - t0 : 0u;
+        // lane 0 walks; the words it passes are rebuilt from its steps, the words beyond the meeting point keep the assumed parse
+        uint32_t p = start_r, m = LZF_TILE;                           // m = meeting point (LZF_TILE: none inside the tile)
+        uint32_t w_cur = 0xFFFFFFFFu, bits = 0;
+        if (lane == 0 && start_r < tend_r) {
+            w_cur = start_r >> 5;
+            while (p < tend_r) {
+                if (p >= fe_r && ((sm.V[p >> 5] >> (p & 31)) & 1)) { m = p; break; }
+                if ((p >> 5) != w_cur) { sm.K[w_cur] = bits; bits = 0; for (uint32_t w2 = w_cur + 1; w2 < (p >> 5); ++w2) sm.K[w2] = 0; w_cur = p >> 5; }
+                bits |= 1u << (p & 31);
+                const uint32_t lo = sm.lenoff[p];
+                p += lo ? (lo >> 16) + 1u : 1u;
+            }
+            sm.K[w_cur] = bits;
+        }
+        m = __shfl_sync(FULL, m, 0);
+        p = __shfl_sync(FULL, p, 0);
+        const uint32_t wc = __shfl_sync(FULL, w_cur, 0);              // last word the walk wrote; later words were not stepped on
+        __syncwarp();
+        const uint32_t w_first = start_r >> 5, w_meet = m >> 5;       // m == LZF_TILE: w_meet = LZF_TILE / 32, beyond the last word
+#pragma unroll
+        for (int k = 0; k < LZF_TILE / 1024; ++k) {
+            const uint32_t w = (uint32_t)(k * 32 + lane);
+            const uint32_t kv = (start_r < tend_r && w >= w_first && w <= wc) ? sm.K[w] : 0u;
+            uint32_t v;
+            if (start_r >= tend_r) v = 0;                              // a long match skips the tile
+            else if (w < w_meet) v = kv;
+            else if (w == w_meet) v = kv | (sm.V[w] & (0xFFFFFFFFu << (m & 31)));
+            else v = sm.V[w];
+            sm.V[w] = v;
+        }
+        if (lane == 0 && start_r < tend_r) sm.next_p = (m < (uint32_t)LZF_TILE) ? exit0 : t0 + max(p, tend_r);
+        __syncwarp();
+        const uint32_t a = (uint32_t)__popc(sm.V[2 * lane]), b = (uint32_t)__popc(sm.V[2 * lane + 1]);
+        const uint32_t incl = (uint32_t)warp_incl_scan((int)(a + b));
+        sm.prefV[2 * lane] = incl - a - b;
+        sm.prefV[2 * lane + 1] = incl - b;
+    }
+    __syncthreads();
 }
 
 // Number of positions after a match (start q, length len) of plain Xpress on which the reference's Find comes back empty-handed

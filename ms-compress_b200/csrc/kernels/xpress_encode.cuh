@@ -139,9 +139,11 @@ __device__ __forceinline__ void xpress_encode_body(const uint8_t* __restrict__ i
                     const unsigned mm = __ballot_sync(FULL, v != 0);
                     if (lane == 0) sm.lz.M[r >> 5] = mm;
                 }
+                const uint64_t gt = (uint64_t)pre.seg_first[u] * XPE_SEG_TILES + t0 / LZF_TILE;
+                if (tid < LZF_TILE / 32) sm.lz.V[tid] = pre.visited[gt * (LZF_TILE / 32) + tid];
                 if (tid == 0) sm.big_pos = LZF_TILE;
                 __syncthreads();
-                lzf_parse_tile(sm.lz, n, t0);
+                lzx_merge_parse(sm.lz, n, t0, pre.next_p[gt], fe);
                 // a visited match of LZX_CAP bytes or more leaves the tile, so there is at most one: measure it
                 for (int r = tid; r < LZF_TILE; r += XPE_THREADS)
                     if (((sm.lz.V[r >> 5] >> (r & 31)) & 1) && (sm.lz.lenoff[r] >> 16) == LZX_CAP - 1u) sm.big_pos = (uint32_t)r;
@@ -323,7 +325,8 @@ xpress_emit_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, ui
     xpress_encode_body<1>(in, out, count, in_off, in_len, out_off, out_cap, out_len, status, seg_tiles, index, index_stride, pre);
 }
 
-// Emission of the reference's parse: pre.lenoff = the answers of lz_find_kernel (indexed seg_first[u] * XPE_SEG + position).
+// Emission of the reference's parse: pre.lenoff = the answers of lz_find_kernel (indexed seg_first[u] * XPE_SEG + position),
+// pre.visited / pre.next_p = its per-tile parse from the tile's first position (visited0 / exit0).
 __global__ void __launch_bounds__(XPE_THREADS)
 xpress_emit_exact_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint32_t count,
                          const uint64_t* __restrict__ in_off, const uint32_t* __restrict__ in_len,

@@ -663,22 +663,35 @@ static MSCompStatus xpress_encode_launch(mscomp_gpu_ctx* ctx, const uint8_t* d_i
     }
     XpPre pre{};
     if (exact) {
-        const size_t npos = (size_t)total_segs * LZX_SEG;
-        uint8_t* sc = (uint8_t*)ctx->get(SC_AUX2, npos * 6 + 256);
+        const size_t npos = (size_t)total_segs * LZX_SEG, tiles = npos / LZF_TILE;
+        const size_t lo_b = npos * 4, v_b = npos / 8, x_b = tiles * 4;             // answers of Find, assumed parse per tile, its exit
+        uint8_t* sc = (uint8_t*)ctx->get(SC_AUX2, lo_b + v_b + x_b + npos * 2 + 256);
         if (!sc) return MSCOMP_MEM_ERROR;
         pre.seg_first = seg_first;
         pre.lenoff = (uint32_t*)sc;
-        uint16_t* dist = (uint16_t*)(sc + npos * 4);
+        pre.visited = (uint32_t*)(sc + lo_b);
+        pre.next_p = (uint32_t*)(sc + lo_b + v_b);
+        uint16_t* dist = (uint16_t*)(sc + lo_b + v_b + x_b);
         MSC_OPT_IN_SMEM(xpress_emit_exact_kernel, sizeof(XpEncSmem));
         if (total_segs) {
-            MSC_OPT_IN_SMEM(lz_prev_kernel<uint16_t>, 65536);
+            const size_t prev_smem = 32768 * sizeof(uint16_t) + LZX_STAGE + 128;
+            MSC_OPT_IN_SMEM(lz_prev_kernel<uint16_t>, prev_smem);
+            MSC_OPT_IN_SMEM(lz_parse0_kernel, sizeof(LzFrontSmem));
             const unsigned long long pieces = total_segs * (LZX_SEG / LZX_PIECE);
             const uint32_t pg = pieces < (unsigned long long)ctx->sm_count * 3 ? (uint32_t)pieces : (uint32_t)ctx->sm_count * 3;
-            MSC_LAUNCH_SMEM(ctx, lz_prev_kernel<uint16_t>, pg, 32, 65536, d_in, b->count, b->d_in_off, b->d_in_len, (const uint32_t*)seg_first, work,
+            MSC_LAUNCH_SMEM(ctx, lz_prev_kernel<uint16_t>, pg, 32, prev_smem, d_in, b->count, b->d_in_off, b->d_in_len, (const uint32_t*)seg_first, work,
                             dist, 8192u, LZX_PIECE);
             const uint32_t fg = total_segs < (unsigned long long)ctx->sm_count * 8 ? (uint32_t)total_segs : (uint32_t)ctx->sm_count * 8;
-            MSC_LAUNCH(ctx, lz_find_kernel, fg, LZX_FIND_THREADS, d_in, b->count, b->d_in_off, b->d_in_len, (const uint32_t*)seg_first, work + 1,
-                       (const uint16_t*)dist, pre.lenoff, 8192u, 0u);
+            static const char* occ = getenv("MSCOMP_FIND_OCC");
+            if (occ && occ[0] == '8')
+                MSC_LAUNCH(ctx, lz_find_kernel<8>, fg, LZX_FIND_THREADS, d_in, b->count, b->d_in_off, b->d_in_len, (const uint32_t*)seg_first,
+                           work + 1, (const uint16_t*)dist, pre.lenoff, 8192u, 0u);
+            else
+                MSC_LAUNCH(ctx, lz_find_kernel<6>, fg, LZX_FIND_THREADS, d_in, b->count, b->d_in_off, b->d_in_len, (const uint32_t*)seg_first,
+                           work + 1, (const uint16_t*)dist, pre.lenoff, 8192u, 0u);
+            const uint32_t qg = total_segs < (unsigned long long)ctx->sm_count * 5 ? (uint32_t)total_segs : (uint32_t)ctx->sm_count * 5;
+            MSC_LAUNCH_SMEM(ctx, lz_parse0_kernel, qg, LZF_THREADS, sizeof(LzFrontSmem), b->count, b->d_in_len, (const uint32_t*)seg_first,
+                            work + 2, (const uint32_t*)pre.lenoff, pre.visited, pre.next_p);
         }
         MSC_LAUNCH_SMEM(ctx, xpress_emit_exact_kernel, b->count < cap ? b->count : cap, XPE_THREADS, sizeof(XpEncSmem),
                         d_in, d_out, b->count, b->d_in_off, b->d_in_len, b->d_out_off, b->d_out_cap, b->d_out_len, b->d_status,

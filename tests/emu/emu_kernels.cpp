@@ -237,14 +237,16 @@ void emu_xpress_encode_exact(const uint8_t* in, uint8_t* out, uint32_t count, co
     emu::launch(xpress_segments_kernel, dim3e(1), dim3e(1024), in_len, count, seg_first.data(), totals, work);
     const size_t npos = (size_t)totals[0] * LZX_SEG;
     std::vector<uint16_t> dist(npos + 1, 0xDEAD);
-    std::vector<uint32_t> lenoff(npos + 1, 0xDEADBEEFu);
+    std::vector<uint32_t> lenoff(npos + 1, 0xDEADBEEFu), visited0(npos / 32 + 1, 0xDEADBEEFu), exit0(npos / LZF_TILE + 1, 0xDEADBEEFu);
     if (totals[0]) {
         emu::launch(lz_prev_kernel<uint16_t>, dim3e(grid), dim3e(32), in, count, in_off, in_len, (const uint32_t*)seg_first.data(), work,
                     dist.data(), 8192u, LZX_PIECE);
-        emu::launch(lz_find_kernel, dim3e(grid), dim3e(LZX_FIND_THREADS), in, count, in_off, in_len, (const uint32_t*)seg_first.data(), work + 1,
+        emu::launch(lz_find_kernel<6>, dim3e(grid), dim3e(LZX_FIND_THREADS), in, count, in_off, in_len, (const uint32_t*)seg_first.data(), work + 1,
                     (const uint16_t*)dist.data(), lenoff.data(), 8192u, 0u);
+        emu::launch(lz_parse0_kernel, dim3e(grid), dim3e(LZF_THREADS), count, in_len, (const uint32_t*)seg_first.data(), work + 2,
+                    (const uint32_t*)lenoff.data(), visited0.data(), exit0.data());
     }
-    XpPre pre{seg_first.data(), lenoff.data(), nullptr, nullptr};
+    XpPre pre{seg_first.data(), lenoff.data(), visited0.data(), exit0.data()};
     emu::launch(xpress_emit_exact_kernel, dim3e(grid), dim3e(XPE_THREADS), in, out, count, in_off, in_len, out_off, out_cap, out_len, status,
                 index ? seg_bytes / (uint32_t)LZF_TILE : 0u, (XpressSeg*)index, stride, pre);
 }
