@@ -5,7 +5,7 @@
 #include <stdio.h>
 #include "../../include/mscomp_gpu.h"
 
-enum ScratchId { SC_SLOTS = 0, SC_SIZES, SC_STATUS, SC_OFFS, SC_RESULT, SC_IN, SC_OUT, SC_AUX0, SC_AUX1, SC_AUX2, SC_AUX3, SC_COUNT };
+enum ScratchId { SC_SLOTS = 0, SC_SIZES, SC_STATUS, SC_OFFS, SC_RESULT, SC_IN, SC_OUT, SC_AUX0, SC_AUX1, SC_AUX2, SC_AUX3, SC_AUX4, SC_COUNT };
 
 struct mscomp_gpu_ctx {
     int device = 0;

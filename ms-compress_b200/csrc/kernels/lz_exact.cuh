@@ -180,6 +180,8 @@ lz_find_kernel(const uint8_t* __restrict__ in, uint32_t count, const uint64_t* _
             if (!(b_hop | b_cmp | b_new)) break;
             const int c_hop = __popc(b_hop), c_cmp = __popc(b_cmp), c_new = __popc(b_new);
             if (c_hop >= c_cmp && c_hop >= c_new) {
+#pragma unroll
+                for (int rep = 0; rep < 2; ++rep)                      // two links per round: half the votes per link
                 if (st == ST_HOP) {
                     const uint32_t d = dd[x];
                     if (!d || p - x + d > window || links == 0u) { res = len >= 3u ? ((min(len, rem) - 1u) << 16) | off : 0u; st = ST_NEW; }

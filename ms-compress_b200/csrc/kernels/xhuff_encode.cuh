@@ -24,6 +24,7 @@
 #pragma once
 #include "common.cuh"
 #include "lz_front.cuh"
+#include "lz_exact.cuh"
 #include "xhuff_index.cuh"
 
 namespace msc {
@@ -54,19 +55,24 @@ struct XhEncSmem {
     uint32_t nused, raw_total, bits_total, scan_tmp[8];
     unsigned long long bit_carry;      // running (bits << 32 | raw bytes) between token tiles
     unsigned long long wsum[XHE_THREADS / 32];   // per-warp partial sums of the block scans
+    uint32_t big_pos, red;             // reference-parse variant: the tile's visited match of LZX_CAP or more bytes (LZF_TILE = none)
 };
 
+// Token word of this encoder: a match is (len - 1) << 16 | offset (len 3..65536, offset 1..65535, so the high half is at least 2);
+// a literal is its byte value; the end-of-stream symbol is XHE_TOK_EOS (high half 1: neither of the two).
+constexpr uint32_t XHE_TOK_EOS = 0x00010000u;
+__device__ __forceinline__ bool xhe_is_match(uint32_t tok) { return (tok >> 16) >= 2u; }
 __device__ __forceinline__ uint32_t xhe_sym_of(uint32_t tok)
 {
-    if (!(tok >> 31)) return (tok & LZF_TOK_EOS) ? 256u : (tok & 0xFFu);
-    const uint32_t off = tok & 0xFFFFu, lm3 = ((tok >> 16) & 0x7FFFu) + 1 - 3;
+    if (!xhe_is_match(tok)) return (tok == XHE_TOK_EOS) ? 256u : (tok & 0xFFu);
+    const uint32_t off = tok & 0xFFFFu, lm3 = (tok >> 16) + 1 - 3;
     const uint32_t ob = 31u - (uint32_t)__clz((int)off);
     return 256u + ((ob << 4) | min(lm3, 15u));
 }
 __device__ __forceinline__ uint32_t xhe_raw_of(uint32_t tok)
-{   // raw length bytes after the code: 0, 1 or 3 (lengths are capped at 32768, the u32 form never occurs)
-    if (!(tok >> 31)) return 0;
-    const uint32_t lm3 = ((tok >> 16) & 0x7FFFu) + 1 - 3;
+{   // raw length bytes after the code: 0, 1 or 3 (a match ends with its 64 KiB chunk, the u32 form never occurs)
+    if (!xhe_is_match(tok)) return 0;
+    const uint32_t lm3 = (tok >> 16) + 1 - 3;
     return lm3 < 15 ? 0u : (lm3 < 15 + 255 ? 1u : 3u);
 }
 
@@ -157,14 +163,27 @@ __device__ __forceinline__ void xhe_put_bits(uint32_t* bits32, uint32_t b, uint3
 }
 __device__ __forceinline__ uint32_t xhe_reserved(uint32_t B) { return B ? 1 + ((B + 15) >> 4) : 2; }   // words reserved at B bits
 
+// The reference's LZ77 for this encoder (EXACT): the answers of lz_find_kernel (window 65535, clipped at the 64 KiB chunk), the assumed
+// parse per tile of lz_parse0_kernel, indexed by find coordinates = position in the STREAM (eos_mode 1: the units are its chunks, unit u
+// starts at u * 65536, seg_first unused) or in the unit (eos_mode 0, segment base seg_first[u]).
+struct XhPre {
+    const uint32_t* seg_first;
+    const uint32_t* lenoff;
+    const uint32_t* visited0;
+    const uint32_t* exit0;
+    const uint32_t* stream_len;                // eos_mode 1: length of the whole stream (device word)
+};
+
 // One block per buffer.  eos_mode 0: every buffer is its own stream (ends with the end-of-stream symbol);
 // eos_mode 1: the buffers are consecutive chunks of ONE stream -- only the last buffer of the batch carries it.
-__global__ void __launch_bounds__(XHE_THREADS, 4)
-xhuff_encode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint32_t count,
+// EXACT = false: lz_front.cuh's bulk-synchronous matcher, window reset at every chunk (valid streams, not the reference's tokens);
+// EXACT = true: the reference's tokens (xh_compress_lz77, src/xpress_huff_compress.cpp:52-153) from lz_exact.cuh.
+template <bool EXACT>
+__device__ __forceinline__ void xhuff_encode_body(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint32_t count,
                     const uint64_t* __restrict__ in_off, const uint32_t* __restrict__ in_len,
                     const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ out_cap,
                     uint32_t* __restrict__ out_len, int32_t* __restrict__ status, uint8_t* __restrict__ scratch, int eos_mode,
-                    XhSeg* __restrict__ index, const uint64_t* __restrict__ index_off, uint32_t* __restrict__ nseg)
+                    XhSeg* __restrict__ index, const uint64_t* __restrict__ index_off, uint32_t* __restrict__ nseg, const XhPre pre)
 {
     MSC_DYN_SMEM(smem_raw);
     XhEncSmem& sm = *reinterpret_cast<XhEncSmem*>(smem_raw);
@@ -186,6 +205,11 @@ xhuff_encode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, u
         XhSeg* ix = index ? index + index_off[u] : nullptr;              // this stream's restart index (eos_mode 0 only)
         const uint64_t ix_room = index ? index_off[u + 1] - index_off[u] : 0;
         uint32_t nent = 0;                                               // entries of the chunks before this one
+        // find coordinates of this unit (EXACT): source, length and first position of the thing lz_find_kernel saw
+        const uint8_t* fsrc = (eos_mode == 1) ? in + in_off[0] : ubase;
+        const uint32_t fn = (EXACT && eos_mode == 1) ? *pre.stream_len : ulen;
+        const uint32_t fpos0 = (eos_mode == 1) ? u * XHE_CHUNK : 0u;
+        const uint64_t fbase = (uint64_t)((EXACT && eos_mode != 1) ? pre.seg_first[u] : u) * XHE_CHUNK;      // index of the unit's position 0 in lenoff[]
 
         for (uint32_t c0 = 0; c0 < ulen && st == ST_OK; c0 += XHE_CHUNK) {
             const uint8_t* src = ubase + c0;
@@ -193,7 +217,7 @@ xhuff_encode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, u
             const bool last = (c0 + n == ulen) && stream_end_here;
 
             // ---- LZ77 -> tokens + histogram ----
-            for (int i = tid; i < (1 << LZF_HBITS); i += XHE_THREADS) sm.lz.H[i] = 0;
+            if (!EXACT) for (int i = tid; i < (1 << LZF_HBITS); i += XHE_THREADS) sm.lz.H[i] = 0;
             for (int i = tid; i < XHE_SYMS; i += XHE_THREADS) sm.hist[i] = 0;
             if (tid == 0) { sm.lz.next_p = 0; sm.lz.ntok = 0; }
             __syncthreads();
@@ -201,14 +225,35 @@ xhuff_encode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, u
             for (int attempt = 0; attempt < 2; ++attempt) {
                 if (!literal_only) {
                     for (uint32_t t0 = 0; t0 < n; t0 += LZF_TILE) {
-                        const uint32_t cnt = lzf_tile(sm.lz, src, n, t0, 65535u, 4096u);
+                        uint32_t cnt;
+                        if (EXACT) {
+                            const uint32_t* lo = pre.lenoff + fbase + c0 + t0;
+                            const uint64_t gt = (fbase + c0 + t0) / LZF_TILE;
+                            for (int r = tid; r < LZF_TILE; r += XHE_THREADS) sm.lz.lenoff[r] = (t0 + (uint32_t)r < n) ? lo[r] : 0u;
+                            if (tid < LZF_TILE / 32) sm.lz.V[tid] = pre.visited0[gt * (LZF_TILE / 32) + tid];
+                            if (tid == 0) sm.big_pos = LZF_TILE;
+                            __syncthreads();
+                            lzx_merge_parse(sm.lz, n, t0, pre.exit0[gt] - (fpos0 + c0), 0u);
+                            // a visited match of LZX_CAP bytes or more leaves the tile, so there is at most one: measure it
+                            for (int r = tid; r < LZF_TILE; r += XHE_THREADS)
+                                if (((sm.lz.V[r >> 5] >> (r & 31)) & 1) && (sm.lz.lenoff[r] >> 16) == LZX_CAP - 1u) sm.big_pos = (uint32_t)r;
+                            __syncthreads();
+                            const uint32_t bp = sm.big_pos;
+                            if (bp < (uint32_t)LZF_TILE) {
+                                const uint32_t P = fpos0 + c0 + t0 + bp, off = sm.lz.lenoff[bp] & 0xFFFFu;
+                                const uint32_t len = lzx_extend(fsrc, P, off, min(fn - P - 1u, XHE_CHUNK - (P % XHE_CHUNK)), &sm.red);
+                                if (tid == 0) { sm.lz.lenoff[bp] = ((len - 1u) << 16) | off; sm.lz.next_p = t0 + bp + len; }
+                                __syncthreads();
+                            }
+                            cnt = sm.lz.prefV[LZF_TILE / 32 - 1] + (uint32_t)__popc(sm.lz.V[LZF_TILE / 32 - 1]);
+                        } else cnt = lzf_tile(sm.lz, src, n, t0, 65535u, 4096u);
                         const uint32_t tb = sm.lz.ntok;
                         for (int r = tid; r < LZF_TILE; r += XHE_THREADS) {
                             const uint32_t v = sm.lz.V[r >> 5];
                             if ((v >> (r & 31)) & 1) {
                                 const uint32_t k = tb + sm.lz.prefV[r >> 5] + (uint32_t)__popc(v & ((1u << (r & 31)) - 1));
                                 const uint32_t lo = sm.lz.lenoff[r];
-                                const uint32_t t = lo ? (0x80000000u | lo) : (uint32_t)src[t0 + r];
+                                const uint32_t t = lo ? lo : (uint32_t)src[t0 + r];
                                 tok[k] = t;
                                 if ((k & (XHI_SEG_SYMS - 1)) == 0) segpos[k / XHI_SEG_SYMS] = t0 + (uint32_t)r;
                                 atomicAdd(&sm.hist[xhe_sym_of(t)], 1u);
@@ -226,7 +271,7 @@ xhuff_encode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, u
                     if (tid == 0) sm.lz.ntok = n;
                     __syncthreads();
                 }
-                if (tid == 0 && last) { tok[sm.lz.ntok] = LZF_TOK_EOS; sm.lz.ntok += 1; sm.hist[256] += 1; }
+                if (tid == 0 && last) { tok[sm.lz.ntok] = XHE_TOK_EOS; sm.lz.ntok += 1; sm.hist[256] += 1; }
                 __syncthreads();
 
                 // ---- codes + exact size (xh_calc_compressed_len :181-188) ----
@@ -281,7 +326,7 @@ xhuff_encode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, u
                 uint32_t t = 0, sym = 0, cl = 0, ob = 0, raw = 0;
                 if (k < ntok) {
                     t = tok[k]; sym = xhe_sym_of(t); cl = sm.len()[sym];
-                    if (t >> 31) { ob = (sym >> 4) & 15; raw = xhe_raw_of(t); }
+                    if (xhe_is_match(t)) { ob = (sym >> 4) & 15; raw = xhe_raw_of(t); }
                 }
                 unsigned long long v = ((unsigned long long)(cl + ob) << 32) | raw, incl = v;
                 for (int d = 1; d < 32; d <<= 1) { const unsigned long long x = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += x; }
@@ -302,8 +347,8 @@ xhuff_encode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, u
                     }
                     xhe_put_bits(bits32, B0, sm.code()[sym], cl);
                     if (xhe_reserved(B1) > xhe_reserved(B0)) { const uint32_t j = xhe_reserved(B0); wpos[j] = 4 + 2 * (j - 2) + R0; }
-                    if (t >> 31) {
-                        const uint32_t off = t & 0xFFFFu, lm3 = ((t >> 16) & 0x7FFFu) + 1 - 3;
+                    if (xhe_is_match(t)) {
+                        const uint32_t off = t & 0xFFFFu, lm3 = (t >> 16) + 1 - 3;
                         if (raw) {
                             uint8_t* rp = o + 4 + 2 * (B1 ? ((B1 + 15) >> 4) - 1 : 0) + R0;
                             if (raw == 1) rp[0] = (uint8_t)(lm3 - 15);
@@ -342,6 +387,41 @@ xhuff_encode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, u
         if (tid == 0) { out_len[u] = (st == ST_OK) ? opos : 0; status[u] = st; if (nseg) nseg[u] = (st == ST_OK) ? nent : 0; }
         __syncthreads();
     }
+}
+
+__global__ void __launch_bounds__(XHE_THREADS, 4)
+xhuff_encode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint32_t count,
+                    const uint64_t* __restrict__ in_off, const uint32_t* __restrict__ in_len,
+                    const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ out_cap,
+                    uint32_t* __restrict__ out_len, int32_t* __restrict__ status, uint8_t* __restrict__ scratch, int eos_mode,
+                    XhSeg* __restrict__ index, const uint64_t* __restrict__ index_off, uint32_t* __restrict__ nseg)
+{
+    xhuff_encode_body<false>(in, out, count, in_off, in_len, out_off, out_cap, out_len, status, scratch, eos_mode, index, index_off, nseg, XhPre{});
+}
+
+__global__ void __launch_bounds__(XHE_THREADS, 4)
+xhuff_encode_exact_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint32_t count,
+                          const uint64_t* __restrict__ in_off, const uint32_t* __restrict__ in_len,
+                          const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ out_cap,
+                          uint32_t* __restrict__ out_len, int32_t* __restrict__ status, uint8_t* __restrict__ scratch, int eos_mode,
+                          XhSeg* __restrict__ index, const uint64_t* __restrict__ index_off, uint32_t* __restrict__ nseg, XhPre pre)
+{
+    xhuff_encode_body<true>(in, out, count, in_off, in_len, out_off, out_cap, out_len, status, scratch, eos_mode, index, index_off, nseg, pre);
+}
+
+// The one-unit description of a stream whose chunks are the units of a batch (eos_mode 1), for lz_prev_kernel / lz_find_kernel:
+// desc_off[0] = in_off[0], desc_len[0] = bytes from there to the end of the last unit, seg_first = {0, chunks}; clears the work counters.
+__global__ void xhuff_stream_desc_kernel(uint32_t count, const uint64_t* __restrict__ in_off, const uint32_t* __restrict__ in_len,
+                                         uint64_t* __restrict__ desc_off, uint32_t* __restrict__ desc_len, uint32_t* __restrict__ seg_first,
+                                         uint32_t* __restrict__ work_counter)
+{
+    if (threadIdx.x == 0) {
+        const uint64_t total = in_off[count - 1] + in_len[count - 1] - in_off[0];
+        desc_off[0] = in_off[0];
+        desc_len[0] = (uint32_t)total;
+        seg_first[0] = 0; seg_first[1] = (uint32_t)((total + XHE_CHUNK - 1) / XHE_CHUNK);
+    }
+    if (threadIdx.x < 4) work_counter[threadIdx.x] = 0;
 }
 
 } // namespace msc

@@ -337,7 +337,8 @@ xpress_emit_exact_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ o
     xpress_encode_body<2>(in, out, count, in_off, in_len, out_off, out_cap, out_len, status, seg_tiles, index, index_stride, pre);
 }
 
-// seg_first[u] = segments of the buffers before u, seg_first[count] = all of them; totals[0] = that, totals[1] = input bytes.
+// seg_first[u] = segments of the buffers before u, seg_first[count] = all of them; totals[0] = that, totals[1] = input bytes,
+// totals[2] = the longest buffer.
 // Single block; also clears the four work counters of the kernels that follow.
 __global__ void __launch_bounds__(1024)
 xpress_segments_kernel(const uint32_t* __restrict__ in_len, uint32_t count, uint32_t* __restrict__ seg_first, unsigned long long* __restrict__ totals,
@@ -346,16 +347,19 @@ xpress_segments_kernel(const uint32_t* __restrict__ in_len, uint32_t count, uint
     __shared__ uint32_t wsum[32];
     __shared__ uint32_t carry;
     __shared__ unsigned long long bytes;
+    __shared__ uint32_t longest;
     const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { carry = 0; bytes = 0; }
+    if (tid == 0) { carry = 0; bytes = 0; longest = 0; }
     if (tid < 4) work_counter[tid] = 0;                                  // one counter per persistent kernel of the pipeline
     __syncthreads();
     unsigned long long my_bytes = 0;
+    uint32_t my_longest = 0;
     for (uint32_t u0 = 0; u0 < count; u0 += 1024) {
         const uint32_t u = u0 + (uint32_t)tid;
         const uint32_t n = u < count ? in_len[u] : 0u;
         const uint32_t v = u < count ? (n + XPE_SEG - 1) / XPE_SEG : 0u;      // (an empty buffer has no segment: the emitter handles it alone)
         my_bytes += n;
+        my_longest = max(my_longest, n);
         const uint32_t incl = (uint32_t)warp_incl_scan((int)v);
         if (lane == 31) wsum[warp] = incl;
         __syncthreads();
@@ -367,8 +371,9 @@ xpress_segments_kernel(const uint32_t* __restrict__ in_len, uint32_t count, uint
         __syncthreads();
     }
     atomicAdd(&bytes, my_bytes);
+    atomicMax(&longest, my_longest);
     __syncthreads();
-    if (tid == 0) { seg_first[count] = carry; totals[0] = carry; totals[1] = bytes; }
+    if (tid == 0) { seg_first[count] = carry; totals[0] = carry; totals[1] = bytes; totals[2] = longest; }
 }
 
 // Pass 1 of the two-pass variant: persistent blocks pull (buffer, segment) pairs from a work counter and run the LZ77 front end

@@ -321,15 +321,82 @@ static MSCompStatus xhuff_encode_launch(mscomp_gpu_ctx* ctx, const uint8_t* d_in
     if (!batch_ok(ctx, d_in, d_out, b)) return MSCOMP_ARG_ERROR;
     if (!b->count) return MSCOMP_OK;
     cudaSetDevice(ctx->device);
+    // Default: the reference's LZ77 tokens (lz_exact.cuh: hash-chain links, Find at every position, window 65535 across the chunks of a
+    // stream).  MSCOMP_XHUFF_ENCODE=fast selects the earlier bulk-synchronous matcher (window reset per chunk; valid streams, other tokens).
+    static const char* mode = getenv("MSCOMP_XHUFF_ENCODE");
+    const bool exact = !(mode && strcmp(mode, "fast") == 0);
+    XhPre pre{};
+    if (exact) {
+        uint32_t* seg_first = (uint32_t*)ctx->get(SC_AUX1, ((size_t)b->count + 2) * sizeof(uint32_t) + 128);
+        unsigned long long* d_tot = (unsigned long long*)ctx->get(SC_RESULT, 1024);
+        unsigned long long* h_tot = (unsigned long long*)ctx->get_pinned(1024);
+        if (!seg_first || !d_tot || !h_tot) return MSCOMP_MEM_ERROR;
+        d_tot += 64; h_tot += 64;                                      // (clear of the result mailbox at the front)
+        uint32_t* work = (uint32_t*)(d_tot + 4);
+        unsigned long long total_segs = 0;
+        bool big = false;                                              // units of more than one chunk: links reach back across chunks
+        uint32_t fcount = b->count;
+        const uint64_t* f_off = b->d_in_off;
+        const uint32_t* f_len = b->d_in_len;
+        if (eos_mode == 1) {                                           // the units are the chunks of ONE stream: Find sees the stream
+            uint64_t* desc_off = (uint64_t*)(d_tot + 8);
+            uint32_t* desc_len = (uint32_t*)(d_tot + 9);
+            MSC_LAUNCH(ctx, xhuff_stream_desc_kernel, 1, 32, b->count, b->d_in_off, b->d_in_len, desc_off, desc_len, seg_first, work);
+            total_segs = b->count; big = b->count > 1; fcount = 1; f_off = desc_off; f_len = desc_len;
+            pre.stream_len = desc_len;
+        } else {
+            MSC_LAUNCH(ctx, xpress_segments_kernel, 1, 1024, b->d_in_len, b->count, seg_first, d_tot, work);
+            cudaMemcpyAsync(h_tot, d_tot, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream);
+            if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return msc_cuda_status(cudaGetLastError(), "xpress_huff_compress");
+            total_segs = h_tot[0]; big = h_tot[2] > XHE_CHUNK;
+        }
+        if (total_segs >= (1ull << 24)) return MSCOMP_ARG_ERROR;
+        const size_t npos = (size_t)total_segs * LZX_SEG, tiles = npos / LZF_TILE;
+        const size_t lo_b = npos * 4, v_b = npos / 8, x_b = tiles * 4;
+        uint8_t* sc = (uint8_t*)ctx->get(SC_AUX4, lo_b + v_b + x_b + npos * 2 + 256);
+        if (!sc) return MSCOMP_MEM_ERROR;
+        uint32_t* lenoff = (uint32_t*)sc;
+        uint32_t* visited0 = (uint32_t*)(sc + lo_b);
+        uint32_t* exit0 = (uint32_t*)(sc + lo_b + v_b);
+        uint16_t* dist = (uint16_t*)(sc + lo_b + v_b + x_b);
+        pre.seg_first = seg_first; pre.lenoff = lenoff; pre.visited0 = visited0; pre.exit0 = exit0;
+        if (total_segs) {
+            if (big) {
+                const size_t prev_smem = 32768 * sizeof(uint32_t) + LZX_STAGE + 128;
+                MSC_OPT_IN_SMEM(lz_prev_kernel<uint32_t>, prev_smem);
+                const uint32_t pg = total_segs < (unsigned long long)ctx->sm_count ? (uint32_t)total_segs : (uint32_t)ctx->sm_count;
+                MSC_LAUNCH_SMEM(ctx, lz_prev_kernel<uint32_t>, pg, 32, prev_smem, d_in, fcount, f_off, f_len, (const uint32_t*)seg_first, work,
+                                dist, 65535u, LZX_SEG);
+            } else {
+                const size_t prev_smem = 32768 * sizeof(uint16_t) + LZX_STAGE + 128;
+                MSC_OPT_IN_SMEM(lz_prev_kernel<uint16_t>, prev_smem);
+                const uint32_t pg = total_segs < (unsigned long long)ctx->sm_count * 3 ? (uint32_t)total_segs : (uint32_t)ctx->sm_count * 3;
+                MSC_LAUNCH_SMEM(ctx, lz_prev_kernel<uint16_t>, pg, 32, prev_smem, d_in, fcount, f_off, f_len, (const uint32_t*)seg_first, work,
+                                dist, 65535u, LZX_SEG);
+            }
+            const uint32_t fg = total_segs < (unsigned long long)ctx->sm_count * 8 ? (uint32_t)total_segs : (uint32_t)ctx->sm_count * 8;
+            MSC_LAUNCH(ctx, lz_find_kernel<6>, fg, LZX_FIND_THREADS, d_in, fcount, f_off, f_len, (const uint32_t*)seg_first,
+                       work + 1, (const uint16_t*)dist, lenoff, 65535u, XHE_CHUNK);
+            MSC_OPT_IN_SMEM(lz_parse0_kernel, sizeof(LzFrontSmem));
+            const uint32_t qg = total_segs < (unsigned long long)ctx->sm_count * 5 ? (uint32_t)total_segs : (uint32_t)ctx->sm_count * 5;
+            MSC_LAUNCH_SMEM(ctx, lz_parse0_kernel, qg, LZF_THREADS, sizeof(LzFrontSmem), fcount, f_len, (const uint32_t*)seg_first,
+                            work + 2, (const uint32_t*)lenoff, visited0, exit0);
+        }
+    }
     MSC_OPT_IN_SMEM(xhuff_encode_kernel, sizeof(XhEncSmem));
+    MSC_OPT_IN_SMEM(xhuff_encode_exact_kernel, sizeof(XhEncSmem));
     static int per_sm = 0;                                            // resident blocks per SM (the kernel keeps per-block scratch: grid = one wave)
-    if (!per_sm && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, xhuff_encode_kernel, XHE_THREADS, sizeof(XhEncSmem)) != cudaSuccess || per_sm < 1)) per_sm = 3;
+    if (!per_sm && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, xhuff_encode_exact_kernel, XHE_THREADS, sizeof(XhEncSmem)) != cudaSuccess || per_sm < 1)) per_sm = 3;
     const uint32_t cap = (uint32_t)ctx->sm_count * (uint32_t)per_sm;
     const uint32_t grid = b->count < cap ? b->count : cap;
     uint8_t* scratch = (uint8_t*)ctx->get(SC_AUX2, (size_t)grid * XHE_SCRATCH_BYTES + 64);
     if (!scratch) return MSCOMP_MEM_ERROR;
-    MSC_LAUNCH_SMEM(ctx, xhuff_encode_kernel, grid, XHE_THREADS, sizeof(XhEncSmem), d_in, d_out, b->count, b->d_in_off, b->d_in_len, b->d_out_off,
-                    b->d_out_cap, b->d_out_len, b->d_status, scratch, eos_mode, d_index, d_index_off, d_nseg);
+    if (exact)
+        MSC_LAUNCH_SMEM(ctx, xhuff_encode_exact_kernel, grid, XHE_THREADS, sizeof(XhEncSmem), d_in, d_out, b->count, b->d_in_off, b->d_in_len, b->d_out_off,
+                        b->d_out_cap, b->d_out_len, b->d_status, scratch, eos_mode, d_index, d_index_off, d_nseg, pre);
+    else
+        MSC_LAUNCH_SMEM(ctx, xhuff_encode_kernel, grid, XHE_THREADS, sizeof(XhEncSmem), d_in, d_out, b->count, b->d_in_off, b->d_in_len, b->d_out_off,
+                        b->d_out_cap, b->d_out_len, b->d_status, scratch, eos_mode, d_index, d_index_off, d_nseg);
     return msc_cuda_status(cudaGetLastError(), "xpress_huff_compress");
 }
 

@@ -58,6 +58,52 @@ void emu_xhuff_encode(const uint8_t* in, uint8_t* out, uint32_t count, const uin
     emu::launch(msc::xhuff_encode_kernel, dim3e(grid), dim3e(msc::XHE_THREADS), in, out, count, in_off, in_len, out_off, out_cap, out_len, status,
                 scratch.data(), 0, (msc::XhSeg*)nullptr, (const uint64_t*)nullptr, (uint32_t*)nullptr);
 }
+// the reference's LZ77 tokens: links, Find, assumed parse per tile, then the encoder.  eos_mode 1: the buffers are the consecutive 64 KiB
+// chunks of ONE stream (Find sees the stream); eos_mode 0: independent buffers (of any length).  With `index` the encoder also writes
+// its restart index (eos_mode 0), laid out like emu_xhuff_encode_index_check's.
+static void emu_xhuff_exact_front(const uint8_t* in, uint32_t count, const uint64_t* in_off, const uint32_t* in_len, uint32_t grid, int eos_mode,
+                                  std::vector<uint32_t>& seg_first, std::vector<uint32_t>& lenoff, std::vector<uint32_t>& visited0,
+                                  std::vector<uint32_t>& exit0, std::vector<uint32_t>& desc_len)
+{
+    using namespace msc;
+    unsigned long long totals[3] = {0, 0, 0};
+    uint32_t work[4] = {0, 0, 0, 0};
+    std::vector<uint64_t> desc_off(1);
+    seg_first.assign(count + 2, 0);
+    desc_len.assign(1, 0);
+    uint32_t fcount = count;
+    const uint64_t* f_off = in_off;
+    const uint32_t* f_len = in_len;
+    bool big;
+    if (eos_mode == 1) {
+        emu::launch(xhuff_stream_desc_kernel, dim3e(1), dim3e(32), count, in_off, in_len, desc_off.data(), desc_len.data(), seg_first.data(), work);
+        totals[0] = count; big = count > 1; fcount = 1; f_off = desc_off.data(); f_len = desc_len.data();
+    } else {
+        emu::launch(xpress_segments_kernel, dim3e(1), dim3e(1024), in_len, count, seg_first.data(), totals, work);
+        big = totals[2] > XHE_CHUNK;
+    }
+    const size_t npos = (size_t)totals[0] * LZX_SEG;
+    std::vector<uint16_t> dist(npos + 1, 0xDEAD);
+    lenoff.assign(npos + 1, 0xDEADBEEFu); visited0.assign(npos / 32 + 1, 0xDEADBEEFu); exit0.assign(npos / LZF_TILE + 1, 0xDEADBEEFu);
+    if (!totals[0]) return;
+    if (big) emu::launch(lz_prev_kernel<uint32_t>, dim3e(grid), dim3e(32), in, fcount, f_off, f_len, (const uint32_t*)seg_first.data(), work, dist.data(), 65535u, LZX_SEG);
+    else emu::launch(lz_prev_kernel<uint16_t>, dim3e(grid), dim3e(32), in, fcount, f_off, f_len, (const uint32_t*)seg_first.data(), work, dist.data(), 65535u, LZX_SEG);
+    emu::launch(lz_find_kernel<6>, dim3e(grid), dim3e(LZX_FIND_THREADS), in, fcount, f_off, f_len, (const uint32_t*)seg_first.data(), work + 1,
+                (const uint16_t*)dist.data(), lenoff.data(), 65535u, XHE_CHUNK);
+    emu::launch(lz_parse0_kernel, dim3e(grid), dim3e(LZF_THREADS), fcount, f_len, (const uint32_t*)seg_first.data(), work + 2,
+                (const uint32_t*)lenoff.data(), visited0.data(), exit0.data());
+}
+void emu_xhuff_encode_exact(const uint8_t* in, uint8_t* out, uint32_t count, const uint64_t* in_off, const uint32_t* in_len,
+                            const uint64_t* out_off, const uint32_t* out_cap, uint32_t* out_len, int32_t* status, uint32_t grid, uint32_t eos_mode)
+{
+    using namespace msc;
+    std::vector<uint32_t> seg_first, lenoff, visited0, exit0, desc_len;
+    emu_xhuff_exact_front(in, count, in_off, in_len, grid, (int)eos_mode, seg_first, lenoff, visited0, exit0, desc_len);
+    std::vector<uint8_t> scratch((size_t)grid * XHE_SCRATCH_BYTES + 64);
+    XhPre pre{seg_first.data(), lenoff.data(), visited0.data(), exit0.data(), desc_len.data()};
+    emu::launch(xhuff_encode_exact_kernel, dim3e(grid), dim3e(XHE_THREADS), in, out, count, in_off, in_len, out_off, out_cap, out_len, status,
+                scratch.data(), (int)eos_mode, (XhSeg*)nullptr, (const uint64_t*)nullptr, (uint32_t*)nullptr, pre);
+}
 // the encoder's own restart index next to the one the serial walk finds for the streams it wrote: returns the number of streams
 // whose two indices differ (entry count or any entry)
 uint32_t emu_xhuff_encode_index_check(const uint8_t* in, uint8_t* out, uint32_t count, const uint64_t* in_off, const uint32_t* in_len,
@@ -212,7 +258,7 @@ void emu_xpress_encode2(const uint8_t* in, uint8_t* out, uint32_t count, const u
 {
     using namespace msc;
     std::vector<uint32_t> seg_first(count + 2);
-    unsigned long long totals[2] = {0, 0};
+    unsigned long long totals[3] = {0, 0, 0};
     uint32_t work[4] = {0, 0, 0, 0};
     emu::launch(xpress_segments_kernel, dim3e(1), dim3e(1024), in_len, count, seg_first.data(), totals, work);
     const size_t tiles = (size_t)totals[0] * XPE_SEG_TILES;
@@ -232,7 +278,7 @@ void emu_xpress_encode_exact(const uint8_t* in, uint8_t* out, uint32_t count, co
 {
     using namespace msc;
     std::vector<uint32_t> seg_first(count + 2);
-    unsigned long long totals[2] = {0, 0};
+    unsigned long long totals[3] = {0, 0, 0};
     uint32_t work[4] = {0, 0, 0, 0};
     emu::launch(xpress_segments_kernel, dim3e(1), dim3e(1024), in_len, count, seg_first.data(), totals, work);
     const size_t npos = (size_t)totals[0] * LZX_SEG;
