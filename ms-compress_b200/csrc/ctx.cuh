@@ -61,6 +61,7 @@ struct mscomp_gpu_ctx {
     // grow-only device scratch; returns nullptr on allocation failure
     void* get(ScratchId id, size_t bytes)
     {
+        if (id == SC_RESULT && bytes < 4096) bytes = 4096;   // the device result mailbox never moves: callers keep pointers into it across launches
         if (bytes <= scratch_cap[id]) return scratch[id];
         cudaStreamSynchronize(stream);              // the old block may still be in use
         if (scratch[id]) cudaFree(scratch[id]);

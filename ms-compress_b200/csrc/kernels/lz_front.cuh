@@ -36,7 +36,7 @@ struct LzFrontSmem {
     uint32_t K[LZF_TILE / 32];         // visited matches (marks of the pointer-jumping parse)
     uint16_t nmw[LZF_TILE / 32 + 2];   // next non-zero word of M at or after w
     uint16_t pmw[LZF_TILE / 32];       // previous non-zero word of K before w (0xFFFF = none)
-    uint16_t nxt[LZF_TILE];            // nxt(q) = first match position >= q + len[q] (relative; LZF_TILE = leaves the tile)
+    __align__(16) uint16_t nxt[LZF_TILE];   // nxt(q) = first match position >= q + len[q] (relative; LZF_TILE = leaves the tile)
     uint16_t nxt2[LZF_TILE], nxt4[LZF_TILE];   // nxt o nxt and its square
     uint16_t chain[LZF_TILE / 12 + 8]; // every 4th visited match of the tile
     uint32_t nchain;

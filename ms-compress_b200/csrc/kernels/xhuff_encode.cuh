@@ -149,6 +149,93 @@ __device__ __forceinline__ void xhe_build_codes(XhEncSmem& sm)
     __syncthreads();
 }
 
+// The reference's code lengths, tie for tie: HuffmanEncoder::CreateCodes (include/mscomp/HuffmanEncoder.h:58-127) is bzip2's
+// heap-driven Huffman construction over ALL 512 symbols (an unused symbol weighs 1, so every symbol gets a code), weights carry the
+// subtree depth in their low byte, and while some code is longer than 15 bits all weights are halved (+1) and the tree is rebuilt.
+// Which of several equally heavy nodes is merged first -- and with it which of two equally frequent symbols gets the longer code --
+// is decided by the order the binary heap happens to hold them in, so the heap is replayed operation for operation: one thread,
+// heap entries that carry their weight (one shared-memory load per comparison).  The depths are then read off by all threads.
+// Scratch: the parse arrays of the LZ77 front end (dead while codes are built).
+__device__ __forceinline__ void xhe_build_codes_reference(XhEncSmem& sm)
+{
+    const int tid = (int)threadIdx.x;
+    unsigned long long* heap = reinterpret_cast<unsigned long long*>(sm.lz.nxt);                  // [514]  weight << 32 | node
+    uint32_t* w = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(sm.lz.nxt) + 4128);     // [1024] node weights (count << 8 | depth)
+    uint16_t* parent = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(sm.lz.nxt) + 8224); // [1024]
+    static_assert(8224 + 2048 <= 3 * LZF_TILE * sizeof(uint16_t), "scratch of the code builder fits the parse arrays");
+    for (int i = tid; i < XHE_SYMS; i += XHE_THREADS) { const uint32_t c = sm.hist[i]; w[i + 1] = (c ? c : 1u) << 8; }
+    if (tid == 0) w[0] = 0;
+    __syncthreads();
+    for (;;) {
+        for (int i = tid; i < 2 * XHE_SYMS; i += XHE_THREADS) parent[i] = 0;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t hl = 0;
+            heap[0] = 0;                                                      // node 0, weight 0: the sentinel above the root
+            auto push = [&](uint32_t x, uint32_t wx) {
+                uint32_t j = ++hl;
+                for (;;) { const unsigned long long up = heap[j >> 1]; if (!(wx < (uint32_t)(up >> 32))) break; heap[j] = up; j >>= 1; }
+                heap[j] = ((unsigned long long)wx << 32) | x;
+            };
+            auto pop = [&]() {
+                const unsigned long long t = heap[hl--];
+                const uint32_t wt = (uint32_t)(t >> 32);
+                uint32_t i = 1;
+                for (;;) {
+                    uint32_t j = i << 1;
+                    if (j > hl) break;
+                    unsigned long long c = heap[j];
+                    if (j < hl) { const unsigned long long c2 = heap[j + 1]; if ((uint32_t)(c2 >> 32) < (uint32_t)(c >> 32)) { c = c2; ++j; } }
+                    if (wt < (uint32_t)(c >> 32)) break;
+                    heap[i] = c; i = j;
+                }
+                heap[i] = t;
+            };
+            for (uint32_t i = 1; i <= (uint32_t)XHE_SYMS; ++i) push(i, w[i]);
+            uint32_t nn = XHE_SYMS;
+            while (hl > 1) {
+                const unsigned long long e1 = heap[1]; pop();
+                const unsigned long long e2 = heap[1]; pop();
+                const uint32_t n1 = (uint32_t)e1, n2 = (uint32_t)e2, w1 = (uint32_t)(e1 >> 32), w2 = (uint32_t)(e2 >> 32);
+                ++nn;
+                parent[n1] = (uint16_t)nn; parent[n2] = (uint16_t)nn;
+                const uint32_t wn = ((w1 & 0xffffff00u) + (w2 & 0xffffff00u)) | (1u + max(w1 & 0xffu, w2 & 0xffu));
+                w[nn] = wn;
+                push(nn, wn);
+            }
+        }
+        __syncthreads();
+        int too_long = 0;
+        for (int i = tid; i < XHE_SYMS; i += XHE_THREADS) {
+            uint32_t d = 0;
+            for (uint32_t k = (uint32_t)i + 1; parent[k]; k = parent[k]) ++d;
+            sm.len()[i] = (uint8_t)min(d, 255u);
+            if (d > 15) too_long = 1;
+        }
+        if (tid == 0) sm.scan_tmp[0] = 0;
+        __syncthreads();
+        if (too_long) sm.scan_tmp[0] = 1;
+        __syncthreads();
+        const bool again = sm.scan_tmp[0] != 0;
+        __syncthreads();
+        if (!again) break;
+        for (int i = tid; i < XHE_SYMS; i += XHE_THREADS) w[i + 1] = (1u + (w[i + 1] >> 9)) << 8;
+        __syncthreads();
+    }
+    // canonical codes, ascending (length, symbol) (:104-116); every symbol has a length here
+    if (tid < 16) sm.blc[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < XHE_SYMS; i += XHE_THREADS) atomicAdd(&sm.blc[sm.len()[i]], 1u);
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t next[16], code = 0;
+        for (int l = 1; l <= 15; ++l) { next[l] = code; code = (code + sm.blc[l]) << 1; }
+        for (int s2 = 0; s2 < XHE_SYMS; ++s2) { const int l = sm.len()[s2]; sm.code()[s2] = (uint16_t)next[l]++; }
+        sm.nused = XHE_SYMS;
+    }
+    __syncthreads();
+}
+
 __device__ __forceinline__ void xhe_or16(uint32_t* bits32, uint32_t j, uint32_t v)
 {   // OR a 16-bit value into word j of the little-endian 16-bit word array
     atomicOr(&bits32[j >> 1], (v & 0xFFFFu) << (16 * (j & 1)));
@@ -275,7 +362,7 @@ __device__ __forceinline__ void xhuff_encode_body(const uint8_t* __restrict__ in
                 __syncthreads();
 
                 // ---- codes + exact size (xh_calc_compressed_len :181-188) ----
-                xhe_build_codes(sm);
+                if (EXACT && !literal_only) xhe_build_codes_reference(sm); else xhe_build_codes(sm);
                 {
                     unsigned long long local = 0;      // bits << 32 | raw bytes
                     for (int s = tid; s < XHE_SYMS; s += XHE_THREADS) {

@@ -85,3 +85,23 @@ def emu_batch(emu, fn_name, bufs, caps, grid=2, extra=()):
                                P(ol), P(st), ctypes.c_uint32(grid), *extra)
     outs = [out[PAD + out_off[i]:PAD + out_off[i] + ol[i]].tobytes() for i in range(count)]
     return st, ol, outs
+
+
+def emu_xhuff_stream_exact(emu, data, grid=2):
+    """The one-shot layout of xpress_huff_compress: ONE stream, its 64 KiB chunks are the units of the batch (contiguous input, eos_mode 1);
+    returns (status per chunk, packed stream)."""
+    n = len(data)
+    count = (n + 65535) // 65536
+    a, addr = padded(data)
+    stride = 65536 + 256 + 64
+    out = np.zeros(count * stride + 2 * PAD, dtype=np.uint8)
+    io = np.arange(count, dtype=np.uint64) * np.uint64(65536)
+    il = np.array([min(65536, n - i * 65536) for i in range(count)], dtype=np.uint32)
+    oo = np.arange(count, dtype=np.uint64) * np.uint64(stride)
+    oc = np.full(count, stride, dtype=np.uint32)
+    ol = np.zeros(count, dtype=np.uint32)
+    st = np.zeros(count, dtype=np.int32)
+    emu.emu_xhuff_encode_exact(ctypes.c_void_p(addr), ctypes.c_void_p(out.ctypes.data + PAD), ctypes.c_uint32(count), P(io), P(il), P(oo), P(oc), P(ol), P(st),
+                               ctypes.c_uint32(grid), ctypes.c_uint32(1))
+    packed = b"".join(out[PAD + i * stride:PAD + i * stride + int(ol[i])].tobytes() for i in range(count))
+    return st, packed

@@ -8,7 +8,7 @@ from conftest import MAXSZ
 import ctypes
 
 import numpy as np
-from emu_util import P, PAD, emu_batch, padded
+from emu_util import emu_xhuff_stream_exact, P, PAD, emu_batch, padded
 
 KERNELS = {"xpress_huff": ("emu_xhuff_decode", "emu_xhuff_encode"), "xpress": ("emu_xpress_decode", "emu_xpress_encode")}
 SIZES = [1, 2, 3, 4, 5, 31, 32, 33, 100, 5000, 65535, 65536, 65537, 140000]
@@ -190,6 +190,27 @@ def test_xpress_reference_parse_is_byte_identical(emu, oracle, ms):
                                  extra=(P(index), ctypes.c_uint32(stride), ctypes.c_uint32(blk)))
         assert list(st4) == [0 if p else -3 for p in plains]
         assert all(o == p for o, p in zip(outs, plains) if p)
+
+
+def test_xhuff_reference_encoder_is_byte_identical(emu, oracle, ms):
+    """The default Xpress-Huffman encoder writes the very bytes of the reference's xpress_huff_compress: its LZ77 tokens (lz_exact.cuh,
+    window 65535 across chunks, clipped at the chunk), the code lengths of its heap-driven CreateCodes replayed tie for tie, and the
+    literal-only fallback on chunks that would expand.  Independent buffers (one or several chunks each) and the one-shot layout (the
+    chunks of ONE stream as the units of the batch, matches reaching into the previous chunk)."""
+    rnd = random.Random(7)
+    plains = [ms.generate(kind, n, 3 + n) for kind in ("text", "runs", "random") for n in (1, 2, 3, 5, 100, 4096, 65535, 65536, 70000)]
+    plains += [b"abc" * 30000, bytes(140000), bytes(rnd.getrandbits(8) & 3 for _ in range(70000)), ms.generate("text", 20000, 7) * 8,
+               ms.generate("text", 200001, 9), ms.generate("text", 65536, 1) * 2 + b"xyz",
+               bytes(min(255, int(rnd.expovariate(1 / 40.0))) for _ in range(100000)),
+               bytes(rnd.getrandbits(8) for _ in range(40000)) + ms.generate("text", 60000, 5)]
+    st, _, comps = emu_batch(emu, "emu_xhuff_encode_exact", plains, [MAXSZ["xpress_huff"](len(p)) for p in plains], grid=3, extra=(ctypes.c_uint32(0),))
+    assert not st.any()
+    for p, c in zip(plains, comps):
+        assert c == oracle.compress("xpress_huff", p), len(p)
+    for p in plains:
+        if len(p) > 65536:
+            st1, c1 = emu_xhuff_stream_exact(emu, p)
+            assert not st1.any() and c1 == oracle.compress("xpress_huff", p), len(p)
 
 
 # ---- Xpress-Huffman through the restart index (xhuff_index.cuh + xhuff_decode_indexed.cuh) -----------------------------------
