@@ -55,6 +55,16 @@ MSCOMPAPI uint64_t        mscomp_gpu_kernel_launches(const mscomp_gpu_ctx* ctx);
  * reports).  mscomp_gpu_profile_report synchronises and writes one "kernel_name calls total_ms" line per kernel. */
 MSCOMPAPI void            mscomp_gpu_profile_enable(mscomp_gpu_ctx* ctx, int on);
 MSCOMPAPI size_t          mscomp_gpu_profile_report(mscomp_gpu_ctx* ctx, char* buf, size_t cap);
+/* Xpress / Xpress-Huffman encoders of this context.  MSCOMP_GPU_ENCODER_REFERENCE (the default): the reference's own parse --
+ * hash chains of 11 links, nice length 48 (include/mscomp/XpressDictionary.h:28-36, level 3) and, for Xpress-Huffman, its
+ * heap-built code lengths: the streams are byte-identical to xpress_compress / xpress_huff_compress of the reference.
+ * MSCOMP_GPU_ENCODER_FAST: a bulk-synchronous matcher with two candidates per position (and a window reset per 64 KiB chunk for
+ * Xpress-Huffman): valid streams for the reference's decoders, 2-3x the encode speed, 5-9 % larger on text.
+ * The initial mode of a context is REFERENCE unless the environment has MSCOMP_GPU_ENCODER=fast.  LZNT1 has one encoder. */
+#define MSCOMP_GPU_ENCODER_REFERENCE 0
+#define MSCOMP_GPU_ENCODER_FAST      1
+MSCOMPAPI void            mscomp_gpu_set_encoder(mscomp_gpu_ctx* ctx, int mode);
+MSCOMPAPI int             mscomp_gpu_get_encoder(const mscomp_gpu_ctx* ctx);
 
 /* ---- LZNT1: one logical stream of 4 KiB chunks ------------------------------------------------------------ */
 /* Device path behind lznt1_compress (reference src/lznt1_compress.cpp:233-273).  out_cap must be at least

@@ -79,6 +79,8 @@ def lib():
         L.mscomp_gpu_synchronize.restype, L.mscomp_gpu_synchronize.argtypes = i32, [vp]
         L.mscomp_gpu_kernel_launches.restype, L.mscomp_gpu_kernel_launches.argtypes = u64, [vp]
         L.mscomp_gpu_profile_enable.restype, L.mscomp_gpu_profile_enable.argtypes = None, [vp, i32]
+        L.mscomp_gpu_set_encoder.restype, L.mscomp_gpu_set_encoder.argtypes = None, [vp, i32]
+        L.mscomp_gpu_get_encoder.restype, L.mscomp_gpu_get_encoder.argtypes = i32, [vp]
         L.mscomp_gpu_profile_report.restype, L.mscomp_gpu_profile_report.argtypes = sz, [vp, vp, sz]
         L.mscomp_gpu_lznt1_compress.restype, L.mscomp_gpu_lznt1_compress.argtypes = i32, [vp, vp, sz, vp, sz, vp, vp]
         L.mscomp_gpu_lznt1_decompress.restype, L.mscomp_gpu_lznt1_decompress.argtypes = i32, [vp, vp, sz, vp, u32, vp, vp, vp, vp]
@@ -337,6 +339,13 @@ class GpuContext:
 
     def profile(self, on=True):
         lib().mscomp_gpu_profile_enable(self.handle, 1 if on else 0)
+
+    def set_encoder(self, mode):
+        """"reference" (default: byte-identical to the reference's Xpress / Xpress-Huffman encoders) or "fast"."""
+        lib().mscomp_gpu_set_encoder(self.handle, {"reference": 0, "fast": 1}[mode])
+
+    def encoder(self):
+        return ("reference", "fast")[lib().mscomp_gpu_get_encoder(self.handle)]
 
     def profile_report(self):
         """{kernel_name: (calls, total_ms)} since profiling was enabled / last reported (synchronises)."""

@@ -13,6 +13,7 @@ struct mscomp_gpu_ctx {
     bool own_stream = false;
     int sm_count = 148;
     uint64_t launches = 0;
+    int encoder = 0;                 // MSCOMP_GPU_ENCODER_*: Xpress / Xpress-Huffman encoders (mscomp_gpu_set_encoder)
     void* scratch[SC_COUNT] = {};
     size_t scratch_cap[SC_COUNT] = {};
     cudaStream_t copy_stream = nullptr;   // upload stream of the host-pointer wrappers: uploads overlap with kernels

@@ -80,6 +80,8 @@ static mscomp_gpu_ctx* create_ctx(int device, void* cuda_stream, bool use_given)
     }
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (ctx->sm_count <= 0) ctx->sm_count = 148;
+    const char* enc = getenv("MSCOMP_GPU_ENCODER");
+    ctx->encoder = (enc && strcmp(enc, "fast") == 0) ? MSCOMP_GPU_ENCODER_FAST : MSCOMP_GPU_ENCODER_REFERENCE;
     return ctx;
 }
 
@@ -111,6 +113,9 @@ MSCompStatus mscomp_gpu_synchronize(mscomp_gpu_ctx* ctx)
 }
 
 uint64_t mscomp_gpu_kernel_launches(const mscomp_gpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+void mscomp_gpu_set_encoder(mscomp_gpu_ctx* ctx, int mode) { if (ctx) ctx->encoder = mode == MSCOMP_GPU_ENCODER_FAST ? MSCOMP_GPU_ENCODER_FAST : MSCOMP_GPU_ENCODER_REFERENCE; }
+int mscomp_gpu_get_encoder(const mscomp_gpu_ctx* ctx) { return ctx ? ctx->encoder : 0; }
 
 void mscomp_gpu_profile_enable(mscomp_gpu_ctx* ctx, int on)
 {
@@ -321,10 +326,9 @@ static MSCompStatus xhuff_encode_launch(mscomp_gpu_ctx* ctx, const uint8_t* d_in
     if (!batch_ok(ctx, d_in, d_out, b)) return MSCOMP_ARG_ERROR;
     if (!b->count) return MSCOMP_OK;
     cudaSetDevice(ctx->device);
-    // Default: the reference's LZ77 tokens (lz_exact.cuh: hash-chain links, Find at every position, window 65535 across the chunks of a
-    // stream).  MSCOMP_XHUFF_ENCODE=fast selects the earlier bulk-synchronous matcher (window reset per chunk; valid streams, other tokens).
-    static const char* mode = getenv("MSCOMP_XHUFF_ENCODE");
-    const bool exact = !(mode && strcmp(mode, "fast") == 0);
+    // Default: the reference's LZ77 tokens (lz_exact.cuh: hash-chain links, Find, window 65535 across the chunks of a stream) and code
+    // lengths.  MSCOMP_GPU_ENCODER_FAST selects the earlier bulk-synchronous matcher (window reset per chunk; valid streams, other bytes).
+    const bool exact = ctx->encoder != MSCOMP_GPU_ENCODER_FAST;
     XhPre pre{};
     if (exact) {
         uint32_t* seg_first = (uint32_t*)ctx->get(SC_AUX1, ((size_t)b->count + 2) * sizeof(uint32_t) + 128);
@@ -705,10 +709,13 @@ static MSCompStatus xpress_encode_launch(mscomp_gpu_ctx* ctx, const uint8_t* d_i
     cudaSetDevice(ctx->device);
     MSC_OPT_IN_SMEM(xpress_encode_kernel, sizeof(XpEncSmem));
     const uint32_t cap = (uint32_t)ctx->sm_count * 4;
-    // Default: the reference's parse (lz_exact.cuh), byte-identical to its xpress_compress.  "one" / "two" select the earlier
-    // bulk-synchronous matcher (1 table candidate + 1 lane peer; valid streams, other bytes), fused or per 64 KiB segment.
+    // Default: the reference's parse (lz_exact.cuh), byte-identical to its xpress_compress.  MSCOMP_GPU_ENCODER_FAST selects the earlier
+    // bulk-synchronous matcher (1 table candidate + 1 lane peer; valid streams, other bytes): fused ("one") for small buffers, per
+    // 64 KiB segment ("two") for large ones; MSCOMP_XPRESS_ENCODE=one/two forces a variant of it.
     static const char* mode = getenv("MSCOMP_XPRESS_ENCODE");
-    const bool fast_one = mode && strcmp(mode, "one") == 0, fast_two = mode && strcmp(mode, "two") == 0;
+    const bool fast = ctx->encoder == MSCOMP_GPU_ENCODER_FAST;
+    const bool fast_one = fast && mode && strcmp(mode, "one") == 0;
+    bool fast_two = fast && mode && strcmp(mode, "two") == 0;
     bool two_pass = false, exact = false;
     uint32_t* seg_first = nullptr;
     uint32_t* work = nullptr;
@@ -724,11 +731,13 @@ static MSCompStatus xpress_encode_launch(mscomp_gpu_ctx* ctx, const uint8_t* d_i
             cudaMemcpyAsync(h_tot, d_tot, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream);
             if (cudaStreamSynchronize(ctx->stream) == cudaSuccess) {
                 total_segs = h_tot[0];
-                if (total_segs < (1ull << 24)) { two_pass = fast_two && total_segs > 0; exact = !fast_two; }
+                if (fast && !fast_two && total_segs && h_tot[1] / b->count >= (128u << 10)) fast_two = true;
+                if (total_segs < (1ull << 24)) { two_pass = fast_two && total_segs > 0; exact = !fast; }
             }
         }
     }
     XpPre pre{};
+    if (!fast && !exact) return MSCOMP_MEM_ERROR;                      // the reference parse never falls back to the other matcher
     if (exact) {
         const size_t npos = (size_t)total_segs * LZX_SEG, tiles = npos / LZF_TILE;
         const size_t lo_b = npos * 4, v_b = npos / 8, x_b = tiles * 4;             // answers of Find, assumed parse per tile, its exit
