@@ -343,9 +343,26 @@ def measure_batch_format(ms, ctx, torch, fmt, each, count, steps, dev, peak, ran
         extra = {"decode_ms_unindexed": e0.elapsed_time(e1),
                  "index": ("side-band restart index written by the encoder, one entry per %d input bytes (%d per buffer)" % (seg_bytes, stride)) if fmt == "xpress"
                           else "side-band restart index written by the encoder, one entry (16 bytes) per 64 symbols"}
+    if world == 1:
+        # the other encoder of the library (mscomp_gpu_set_encoder FAST: bulk-synchronous matcher, valid streams, not the reference's bytes)
+        ctx.set_encoder("fast")
+        step()
+        torch.cuda.synchronize()
+        assert int(st1.abs().sum().item()) == 0 and int(st2.abs().sum().item()) == 0 and torch.equal(d_out, d_in), "%s fast encoder round trip" % fmt
+        Cf = int(c_len.to(torch.int64).sum().item())
+        fe = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(min(steps, 3))]
+        for e in fe:
+            step(e)
+        torch.cuda.synchronize()
+        ctx.set_encoder("reference")
+        f_enc, f_dec = statistics.mean(e[0].elapsed_time(e[1]) for e in fe), statistics.mean(e[1].elapsed_time(e[2]) for e in fe)
+        extra["fast_encoder"] = {"what": "mscomp_gpu_set_encoder(MSCOMP_GPU_ENCODER_FAST): valid streams, not byte-identical to the reference",
+                                 "encode_ms": f_enc, "decode_ms": f_dec, "compressed_ratio": Cf / U,
+                                 "encode_decode_MBps": U / MB / ((f_enc + f_dec) / 1e3)}
     del d_in, d_comp, d_out
     torch.cuda.empty_cache()
     return {"workload": "%d independent buffers x %d bytes (text) per GPU, device batch API, %d GPU(s)" % (count, each, world),
+            "encoder": "reference parse (default): streams byte-identical to the reference's %s_compress" % fmt,
             "uncompressed_bytes_per_gpu": U, "compressed_ratio": C / U,
             **extra, "encode_ms": enc_ms, "decode_ms": dec_ms, "encode_MBps": world * U / MB / (enc_ms / 1e3), "decode_MBps": world * U / MB / (dec_ms / 1e3),
             "encode_decode_MBps": world * U / MB / ((enc_ms + dec_ms) / 1e3), "gpu_launches": ctx.launches() - l0, "roofline": roof, "kernels": kern}

@@ -132,20 +132,63 @@ lz_prev_kernel(const uint8_t* __restrict__ in, uint32_t count, const uint64_t* _
     }
 }
 
-// find(p) for every position of the units: lenoff[] (indexed like dist[]) receives (len - 1) << 16 | offset, or 0 when Find would
-// return less than 3.  dist = the links (lz_prev_kernel).  chunk = 0: a match may run to the end of the unit (plain Xpress);
-// otherwise the caller clips it at the end of the chunk it starts in and does not ask at all with fewer than 3 bytes of chunk
-// left (Xpress-Huffman: src/xpress_huff_compress.cpp:90-93).
-// Persistent blocks pull 64 KiB segments; a thread owns every LZX_FIND_THREADS-th position of the segment and runs ONE flat loop
-// over the links of all of them -- a lane whose chain ends early (a rare trigram) moves on to its next position instead of idling
-// until the longest chain of the warp (a common trigram, 11 links) is done.
-// A candidate can only beat the current length `len` if it agrees on byte `len`: one probe word per link decides (the three
-// bytes of the key while len is still 2, afterwards the four bytes ending at index len); a full compare only follows a hit.
+// What Find needs to know about a unit.
+struct LzxUnit {
+    LzfSrc S;                       // the unit's bytes as aligned words
+    const uint8_t* src;
+    const uint16_t* dd;             // its links (lz_prev_kernel)
+    uint32_t n, window, chunk;      // chunk = 0: a match may run to the end of the unit (plain Xpress); otherwise the caller clips it at
+                                    // the end of the chunk it starts in and does not ask at all with fewer than 3 bytes of chunk left
+                                    // (Xpress-Huffman: src/xpress_huff_compress.cpp:90-93)
+    __device__ __forceinline__ LzxUnit(const uint8_t* s, uint32_t n_, const uint16_t* d, uint32_t w, uint32_t c) : S(s, n_), src(s), dd(d), n(n_), window(w), chunk(c) {}
+};
+constexpr uint32_t LZX_UNKNOWN = 0xFFFFFFFFu;  // lenoff[] entry of a position nobody has asked about
+
+// find(p), one thread: (len - 1) << 16 | offset, or 0 when Find would return less than 3 (or is not asked).  A candidate can only
+// beat the current length `len` if it agrees on byte `len`: one probe word per link decides (the three bytes of the key while
+// len is still 2, afterwards the four bytes ending at index len); a full compare only follows a hit.
+__device__ __forceinline__ uint32_t lzx_find_one(const LzxUnit& U, uint32_t p)
+{
+    if (p + 3 > U.n) return 0;
+    const uint32_t rem = U.chunk ? U.chunk - (p % U.chunk) : 0xFFFFFFFFu;    // Find itself does not know about chunks ...
+    const uint32_t maxlen = min(U.n - p - 1u, LZX_CAP);                      // GetMatchLength never reaches the last byte (:74-93)
+    if (maxlen < 3u || rem < 3u) return 0;
+    uint32_t len = 2, off = 0, x = p;
+    uint32_t po = 0, mask = 0xFFFFFFu, pk = lzf_ld4(U.S, p) & mask;
+    for (uint32_t c = 0; c < LZX_CHAIN; ++c) {
+        const uint32_t d = U.dd[x];
+        if (!d || p - x + d > U.window) break;
+        x -= d;
+        if ((lzf_ld4(U.S, x + po) & mask) != pk) continue;                   // hash collisions and shorter matches only use up a link
+        const uint32_t l = lzf_match_len(U.S, U.src, p, x, maxlen);
+        if (l > len) {
+            len = l; off = p - x;
+            if (len >= LZX_NICE || len == maxlen) break;                     // (nothing is longer than maxlen: the walk could only waste links)
+            po = len - 3u; mask = 0xFFFFFFFFu; pk = lzf_ld4(U.S, p + po);
+        }
+    }
+    len = min(len, rem);                                                     // ... the caller clips what it found (:93)
+    return len >= 3u ? ((len - 1u) << 16) | off : 0u;
+}
+
+// Find only where a greedy parse goes.  The input is cut into sub-tiles of LZX_SUB positions; a lane owns a sub-tile and runs the
+// greedy parse p += max(1, len(find(p))) from the sub-tile's FIRST position -- an assumption: the true parse enters wherever the
+// match before ends -- asking Find only at the positions it steps on (a quarter of all positions on text).  Greedy parses that
+// meet stay together, so the true parse, entering elsewhere, follows steps of its own only until it stands on a token start of
+// the assumed one; those few extra questions are asked when the sub-tiles are stitched (lz_stitch_kernel, lzx_merge_parse).
+// Out: lenoff[] (indexed like dist[]; pre-set to LZX_UNKNOWN) at the visited positions; per sub-tile the bitmap of token starts
+// (two words, laid out so that the LZX_SUB / 32 words of consecutive sub-tiles form the per-tile bitmap) and the unit position
+// where the assumed parse leaves the sub-tile.
+// Persistent blocks pull 64 KiB segments; the 32 lanes of a warp own 32 consecutive sub-tiles (= one tile).  A lane is in one of
+// three states: ST_HOP (follow a link, probe), ST_CMP (the probe hit: measure the candidate), ST_NEW (a position is answered:
+// store, step, start the next).  Every round the WARP runs the code of one state only -- the one most of its lanes are in -- so the
+// rare, long pieces (compare, next position) run for many lanes at once instead of once per link round with a handful of lanes.
+constexpr uint32_t LZX_SUB = 64;
 template <int MINB>
 __global__ void __launch_bounds__(LZX_FIND_THREADS, MINB)
 lz_find_kernel(const uint8_t* __restrict__ in, uint32_t count, const uint64_t* __restrict__ in_off, const uint32_t* __restrict__ in_len,
                const uint32_t* __restrict__ seg_first, uint32_t* __restrict__ work_counter, const uint16_t* __restrict__ dist,
-               uint32_t* __restrict__ lenoff, uint32_t window, uint32_t chunk)
+               uint32_t* __restrict__ lenoff, uint32_t* __restrict__ visited_sub, uint32_t* __restrict__ exit_sub, uint32_t window, uint32_t chunk)
 {
     __shared__ uint32_t s_work;
     const int tid = (int)threadIdx.x;
@@ -162,19 +205,18 @@ lz_find_kernel(const uint8_t* __restrict__ in, uint32_t count, const uint64_t* _
         const uint32_t s0 = (w - seg_first[u]) * LZX_SEG, s1 = min(s0 + LZX_SEG, n);
         const uint8_t* src = in + in_off[u];
         const LzfSrc S(src, n);
-        const uint16_t* dd = dist + (uint64_t)seg_first[u] * LZX_SEG;
-        uint32_t* out = lenoff + (uint64_t)seg_first[u] * LZX_SEG;
+        const uint64_t ubase = (uint64_t)seg_first[u] * LZX_SEG;
+        const uint16_t* dd = dist + ubase;
+        uint32_t* out = lenoff + ubase;
 
-        // A lane is in one of three states: ST_HOP (follow a link, probe), ST_CMP (the probe hit: measure the candidate), ST_NEW (its
-        // position is answered: store, take the next one).  Every round the WARP runs the code of one state only -- the one most of
-        // its lanes are in -- so the rare, long pieces (compare, new position) run for many lanes at once instead of once per link
-        // round with a handful of lanes each.
         enum { ST_HOP = 0, ST_CMP = 1, ST_NEW = 2, ST_END = 3 };
-        uint32_t p = s0 + (uint32_t)tid;
+        uint32_t b = s0 + (uint32_t)tid * LZX_SUB;                     // the sub-tile in hand: [b, e)
+        uint32_t e = min(b + LZX_SUB, s1);
+        uint32_t p = b, vlo = 0, vhi = 0;
         uint32_t x = 0, len = 0, off = 0, po = 0, mask = 0, pk = 0, links = 0, maxlen = 0, rem = 0;
         uint32_t st = ST_NEW, res = 0;
-        bool fresh = true;                                             // ST_NEW without an answer to store (the lane's first position)
-        if (p >= s1) { st = ST_END; }
+        bool fresh = true;                                             // ST_NEW without an answer to store (a sub-tile's first position)
+        if (b >= s1) st = ST_END;
         for (;;) {
             const unsigned b_hop = __ballot_sync(FULL, st == ST_HOP), b_cmp = __ballot_sync(FULL, st == ST_CMP), b_new = __ballot_sync(FULL, st == ST_NEW);
             if (!(b_hop | b_cmp | b_new)) break;
@@ -204,75 +246,95 @@ lz_find_kernel(const uint8_t* __restrict__ in, uint32_t count, const uint64_t* _
                 }
             } else {
                 if (st == ST_NEW) {
-                    if (!fresh) { out[p] = res; p += LZX_FIND_THREADS; }
-                    fresh = false;
-                    for (;;) {                                         // positions where Find is not even asked answer 0 on the spot
-                        if (p >= s1) { st = ST_END; break; }
+                    for (;;) {
+                        if (!fresh) {                                  // answer in hand: store it, mark the token start, step
+                            out[p] = res;
+                            const uint32_t k = p - b;
+                            if (k < 32u) vlo |= 1u << k; else vhi |= 1u << (k - 32u);
+                            p += res ? (res >> 16) + 1u : 1u;
+                        }
+                        fresh = false;
+                        if (p >= e) {                                  // the assumed parse leaves the sub-tile
+                            const uint64_t sub = (ubase + b) / LZX_SUB;
+                            visited_sub[2 * sub] = vlo; visited_sub[2 * sub + 1] = vhi; exit_sub[sub] = p;
+                            b += LZX_FIND_THREADS * LZX_SUB;
+                            if (b >= s1) { st = ST_END; break; }
+                            e = min(b + LZX_SUB, s1); p = b; vlo = vhi = 0;
+                        }
                         bool ask = p + 3u <= n;
                         if (ask) {
                             rem = chunk ? chunk - (p % chunk) : 0xFFFFFFFFu;          // Find itself does not know about chunks ...
                             maxlen = min(n - p - 1u, LZX_CAP);                         // GetMatchLength never reaches the last byte (:74-93)
                             ask = maxlen >= 3u && rem >= 3u;
                         }
-                        if (ask) { x = p; len = 2; off = 0; po = 0; mask = 0xFFFFFFu; pk = lzf_ld4(S, p) & mask; links = LZX_CHAIN; st = ST_HOP; break; }
-                        out[p] = 0; p += LZX_FIND_THREADS;
+                        if (ask) { x = p; len = 2; off = 0; po = 0; mask = 0xFFFFFFu; pk = lzf_ld4(S, p) & mask; links = LZX_CHAIN; st = ST_HOP; fresh = false; break; }
+                        res = 0;                                       // Find is not even asked here: a literal on the spot
                     }
+                    if (st == ST_HOP) fresh = false;
                 }
             }
         }
     }
 }
 
-// The greedy parse of every tile of LZF_TILE positions AS IF a token started at the tile's first position, from the answers of
-// lz_find_kernel.  Per tile (global tile number seg_first[u] * (LZX_SEG / LZF_TILE) + position / LZF_TILE): the token-start bitmap
-// visited0[LZF_TILE / 32] of that parse and exit0 = the unit position where it leaves the tile.  Greedy parses that meet stay
-// together, so the true parse of a tile -- entered wherever the previous tile's last match ends -- follows its own steps only until
-// it lands on a token start of this one (lzx_merge_parse): the serial pass along the unit no longer parses, it merges.
-__global__ void __launch_bounds__(LZF_THREADS)
-lz_parse0_kernel(uint32_t count, const uint32_t* __restrict__ in_len, const uint32_t* __restrict__ seg_first, uint32_t* __restrict__ work_counter,
-                 const uint32_t* __restrict__ lenoff, uint32_t* __restrict__ visited0, uint32_t* __restrict__ exit0)
+// Stitches the sub-tile parses of lz_find_kernel into the greedy parse of every tile of LZF_TILE positions AS IF a token started at
+// the tile's first position: one thread per tile walks its sub-tiles in order, entering each where the one before was left;
+// inside a sub-tile it steps (asking Find for positions nobody asked about, and recording the answer) until it stands on a token
+// start of the sub-tile's own parse, whose remainder and exit it then takes over.  Out, per tile (global tile number
+// seg_first[u] * (LZX_SEG / LZF_TILE) + position / LZF_TILE): the token-start bitmap visited0[LZF_TILE / 32] (in place: the
+// sub-tile words ARE the tile's words) and exit0 = the unit position where that parse leaves the tile.
+__global__ void __launch_bounds__(128)
+lz_stitch_kernel(const uint8_t* __restrict__ in, uint32_t count, const uint64_t* __restrict__ in_off, const uint32_t* __restrict__ in_len,
+                 const uint32_t* __restrict__ seg_first, const uint16_t* __restrict__ dist, uint32_t* __restrict__ lenoff,
+                 uint32_t* __restrict__ visited0, const uint32_t* __restrict__ exit_sub, uint32_t* __restrict__ exit0, uint32_t window, uint32_t chunk)
 {
-    MSC_DYN_SMEM(smem_raw);
-    LzFrontSmem& lz = *reinterpret_cast<LzFrontSmem*>(smem_raw);
-    __shared__ uint32_t s_work;
-    const int tid = (int)threadIdx.x, lane = tid & 31;
-    const uint32_t total = seg_first[count];
-    for (;;) {
-        if (tid == 0) s_work = atomicAdd(work_counter, 1u);
-        __syncthreads();
-        const uint32_t w = s_work;
-        __syncthreads();
-        if (w >= total) break;
+    constexpr uint32_t TPS = LZX_SEG / LZF_TILE, SPT = LZF_TILE / LZX_SUB;       // tiles per segment, sub-tiles per tile
+    const uint64_t ntiles = (uint64_t)seg_first[count] * TPS;
+    for (uint64_t gt = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; gt < ntiles; gt += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t sg = (uint32_t)(gt / TPS);
         uint32_t lo = 0, hi = count;
-        while (hi - lo > 1) { const uint32_t mid = (lo + hi) / 2; if (seg_first[mid] <= w) lo = mid; else hi = mid; }
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) / 2; if (seg_first[mid] <= sg) lo = mid; else hi = mid; }
         const uint32_t u = lo, n = in_len[u];
-        const uint32_t s0 = (w - seg_first[u]) * LZX_SEG, s1 = min(s0 + LZX_SEG, n);
-        const uint32_t* src = lenoff + (uint64_t)seg_first[u] * LZX_SEG;
-        for (uint32_t t0 = s0; t0 < s1; t0 += LZF_TILE) {
-            for (int r = tid; r < LZF_TILE; r += LZF_THREADS) {
-                const uint32_t p = t0 + (uint32_t)r;
-                const uint32_t res = p < s1 ? src[p] : 0u;
-                lz.lenoff[r] = res;
-                const unsigned mm = __ballot_sync(FULL, res != 0);
-                if (lane == 0) lz.M[r >> 5] = mm;
+        const uint64_t ubase = (uint64_t)seg_first[u] * LZX_SEG;
+        const uint32_t t0 = (uint32_t)(gt * LZF_TILE - ubase);
+        if (t0 >= n) { exit0[gt] = t0; continue; }
+        const uint32_t tend = min(t0 + LZF_TILE, n);
+        const LzxUnit U(in + in_off[u], n, dist + ubase, window, chunk);
+        uint32_t* lo_u = lenoff + ubase;
+        uint32_t e = t0;                                               // where the parse enters the next sub-tile
+        for (uint32_t k = 0; k < SPT; ++k) {
+            const uint32_t sb = t0 + k * LZX_SUB;
+            uint32_t* vw = visited0 + (gt * SPT + k) * 2;
+            if (sb >= tend) { vw[0] = 0; vw[1] = 0; continue; }
+            const uint32_t se = min(sb + LZX_SUB, tend);
+            if (e >= se) { vw[0] = 0; vw[1] = 0; continue; }           // a match jumps over the sub-tile
+            const unsigned long long v = (unsigned long long)vw[0] | ((unsigned long long)vw[1] << 32);
+            unsigned long long mine = 0;
+            uint32_t p = e;
+            bool met = false;
+            while (p < se) {
+                const uint32_t kbit = p - sb;
+                if ((v >> kbit) & 1ull) { met = true; mine |= v & (~0ull << kbit); break; }
+                uint32_t r = lo_u[p];
+                if (r == LZX_UNKNOWN) { r = lzx_find_one(U, p); lo_u[p] = r; }
+                mine |= 1ull << kbit;
+                p += r ? (r >> 16) + 1u : 1u;
             }
-            if (tid == 0) lz.next_p = t0;
-            __syncthreads();
-            lzf_parse_tile(lz, n, t0);
-            const uint64_t tile = (uint64_t)seg_first[u] * (LZX_SEG / LZF_TILE) + t0 / LZF_TILE;
-            if (tid < LZF_TILE / 32) visited0[tile * (LZF_TILE / 32) + tid] = lz.V[tid];
-            if (tid == 0) exit0[tile] = lz.next_p;
-            __syncthreads();
+            e = met ? exit_sub[(ubase + sb) / LZX_SUB] : p;
+            vw[0] = (uint32_t)mine; vw[1] = (uint32_t)(mine >> 32);
         }
+        exit0[gt] = e;
     }
 }
 
-// The true parse of a tile from the parse that assumed a token at the tile's first position (lz_find_kernel).  In: sm.lenoff (with
-// the forced literals already zeroed), sm.V = visited0 of the tile, sm.next_p = where the parse enters (unit position), exit0 of the
-// tile; fe = unit position below which every position is a literal.  One thread steps from the entry until it stands on a token
-// start of the assumed parse that lies at or beyond fe (from there on the two agree) or leaves the tile.  Out: sm.V, sm.prefV,
-// sm.next_p as lzf_parse_tile leaves them.  Must be called by all LZF_THREADS threads.
-__device__ __forceinline__ void lzx_merge_parse(LzFrontSmem& sm, uint32_t n, uint32_t t0, uint32_t exit0, uint32_t fe)
+// The true parse of a tile from the parse that assumed a token at the tile's first position (lz_stitch_kernel).  In: sm.lenoff = the
+// tile's lenoff[] entries (LZX_UNKNOWN where nobody asked; the forced literals already zeroed), sm.V = visited0 of the tile,
+// sm.next_p = where the parse enters (same coordinates as t0), exit0 of the tile in those coordinates; fe = position below which
+// every position is a literal; U + pos0 = the unit and the unit position of the tile's first position, for the questions nobody has
+// asked yet.  One thread steps from the entry until it stands on a token start of the assumed parse that lies at or beyond fe
+// (from there on the two agree) or leaves the tile.  Out: sm.V, sm.prefV, sm.next_p as lzf_parse_tile leaves them; sm.lenoff
+// holds an answer at every token start.  Must be called by all LZF_THREADS threads.
+__device__ __forceinline__ void lzx_merge_parse(LzFrontSmem& sm, uint32_t n, uint32_t t0, uint32_t exit0, uint32_t fe, const LzxUnit& U, uint32_t pos0)
 {
     const int tid = (int)threadIdx.x, lane = tid & 31;
     const uint32_t tend_r = min(t0 + LZF_TILE, n) - t0;
@@ -288,7 +350,8 @@ __device__ __forceinline__ void lzx_merge_parse(LzFrontSmem& sm, uint32_t n, uin
                 if (p >= fe_r && ((sm.V[p >> 5] >> (p & 31)) & 1)) { m = p; break; }
                 if ((p >> 5) != w_cur) { sm.K[w_cur] = bits; bits = 0; for (uint32_t w2 = w_cur + 1; w2 < (p >> 5); ++w2) sm.K[w2] = 0; w_cur = p >> 5; }
                 bits |= 1u << (p & 31);
-                const uint32_t lo = sm.lenoff[p];
+                uint32_t lo = sm.lenoff[p];
+                if (lo == LZX_UNKNOWN) { lo = lzx_find_one(U, pos0 + p); sm.lenoff[p] = lo; }
                 p += lo ? (lo >> 16) + 1u : 1u;
             }
             sm.K[w_cur] = bits;

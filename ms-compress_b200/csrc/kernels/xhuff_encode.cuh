@@ -258,6 +258,7 @@ struct XhPre {
     const uint32_t* lenoff;
     const uint32_t* visited0;
     const uint32_t* exit0;
+    const uint16_t* dist;                      // the links, for questions nobody has asked yet
     const uint32_t* stream_len;                // eos_mode 1: length of the whole stream (device word)
 };
 
@@ -320,7 +321,8 @@ __device__ __forceinline__ void xhuff_encode_body(const uint8_t* __restrict__ in
                             if (tid < LZF_TILE / 32) sm.lz.V[tid] = pre.visited0[gt * (LZF_TILE / 32) + tid];
                             if (tid == 0) sm.big_pos = LZF_TILE;
                             __syncthreads();
-                            lzx_merge_parse(sm.lz, n, t0, pre.exit0[gt] - (fpos0 + c0), 0u);
+                            lzx_merge_parse(sm.lz, n, t0, pre.exit0[gt] - (fpos0 + c0), 0u, LzxUnit(fsrc, fn, pre.dist + fbase - fpos0, 65535u, XHE_CHUNK),
+                                            fpos0 + c0 + t0);
                             // a visited match of LZX_CAP bytes or more leaves the tile, so there is at most one: measure it
                             for (int r = tid; r < LZF_TILE; r += XHE_THREADS)
                                 if (((sm.lz.V[r >> 5] >> (r & 31)) & 1) && (sm.lz.lenoff[r] >> 16) == LZX_CAP - 1u) sm.big_pos = (uint32_t)r;

@@ -70,6 +70,7 @@ struct XpPre {                                                       // scratch 
     uint32_t* lenoff;                                                // [tiles][LZF_TILE]
     uint32_t* visited;                                               // [tiles][LZF_TILE / 32]
     uint32_t* next_p;                                                // [tiles] position (relative to the segment) where the parse enters the tile
+    const uint16_t* dist;                                            // reference parse (MODE 2): the links, for questions nobody has asked yet
 };
 
 // MODE 0: matching and emission in one kernel; 1: emission from the tiles of xpress_match_kernel; 2: the reference's parse -- emission
@@ -130,20 +131,18 @@ __device__ __forceinline__ void xpress_encode_body(const uint8_t* __restrict__ i
                 if (tid < LZF_TILE / 32) sm.lz.V[tid] = pre.visited[(uint64_t)tile * (LZF_TILE / 32) + tid];
                 __syncthreads();
             } else if (EXACT) {
-                const uint32_t* lo = pre.lenoff + (uint64_t)pre.seg_first[u] * XPE_SEG + t0;
+                const uint64_t ubase = (uint64_t)pre.seg_first[u] * XPE_SEG;
+                const uint32_t* lo = pre.lenoff + ubase + t0;
                 const uint32_t fe = sm.forced_end;
                 for (int r = tid; r < LZF_TILE; r += XPE_THREADS) {
                     const uint32_t p = t0 + (uint32_t)r;
-                    const uint32_t v = (p < n && p >= fe) ? lo[r] : 0u;
-                    sm.lz.lenoff[r] = v;
-                    const unsigned mm = __ballot_sync(FULL, v != 0);
-                    if (lane == 0) sm.lz.M[r >> 5] = mm;
+                    sm.lz.lenoff[r] = (p < n && p >= fe) ? lo[r] : 0u;       // (LZX_UNKNOWN where nobody has asked)
                 }
-                const uint64_t gt = (uint64_t)pre.seg_first[u] * XPE_SEG_TILES + t0 / LZF_TILE;
+                const uint64_t gt = (ubase + t0) / LZF_TILE;
                 if (tid < LZF_TILE / 32) sm.lz.V[tid] = pre.visited[gt * (LZF_TILE / 32) + tid];
                 if (tid == 0) sm.big_pos = LZF_TILE;
                 __syncthreads();
-                lzx_merge_parse(sm.lz, n, t0, pre.next_p[gt], fe);
+                lzx_merge_parse(sm.lz, n, t0, pre.next_p[gt], fe, LzxUnit(src, n, pre.dist + ubase, 8192u, 0u), t0);
                 // a visited match of LZX_CAP bytes or more leaves the tile, so there is at most one: measure it
                 for (int r = tid; r < LZF_TILE; r += XPE_THREADS)
                     if (((sm.lz.V[r >> 5] >> (r & 31)) & 1) && (sm.lz.lenoff[r] >> 16) == LZX_CAP - 1u) sm.big_pos = (uint32_t)r;

@@ -356,7 +356,7 @@ static MSCompStatus xhuff_encode_launch(mscomp_gpu_ctx* ctx, const uint8_t* d_in
         }
         if (total_segs >= (1ull << 24)) return MSCOMP_ARG_ERROR;
         const size_t npos = (size_t)total_segs * LZX_SEG, tiles = npos / LZF_TILE;
-        const size_t lo_b = npos * 4, v_b = npos / 8, x_b = tiles * 4;
+        const size_t lo_b = npos * 4, v_b = npos / 8, x_b = tiles * 4 + (npos / LZX_SUB) * 4;    // answers, token starts, exits per tile + per sub-tile
         uint8_t* sc = (uint8_t*)ctx->get(SC_AUX4, lo_b + v_b + x_b + npos * 2 + 256);
         if (!sc) return MSCOMP_MEM_ERROR;
         uint32_t* lenoff = (uint32_t*)sc;
@@ -378,14 +378,16 @@ static MSCompStatus xhuff_encode_launch(mscomp_gpu_ctx* ctx, const uint8_t* d_in
                 MSC_LAUNCH_SMEM(ctx, lz_prev_kernel<uint16_t>, pg, 32, prev_smem, d_in, fcount, f_off, f_len, (const uint32_t*)seg_first, work,
                                 dist, 65535u, LZX_SEG);
             }
+            cudaMemsetAsync(lenoff, 0xFF, lo_b, ctx->stream);           // LZX_UNKNOWN: nobody has asked
             const uint32_t fg = total_segs < (unsigned long long)ctx->sm_count * 8 ? (uint32_t)total_segs : (uint32_t)ctx->sm_count * 8;
             MSC_LAUNCH(ctx, lz_find_kernel<6>, fg, LZX_FIND_THREADS, d_in, fcount, f_off, f_len, (const uint32_t*)seg_first,
-                       work + 1, (const uint16_t*)dist, lenoff, 65535u, XHE_CHUNK);
-            MSC_OPT_IN_SMEM(lz_parse0_kernel, sizeof(LzFrontSmem));
-            const uint32_t qg = total_segs < (unsigned long long)ctx->sm_count * 5 ? (uint32_t)total_segs : (uint32_t)ctx->sm_count * 5;
-            MSC_LAUNCH_SMEM(ctx, lz_parse0_kernel, qg, LZF_THREADS, sizeof(LzFrontSmem), fcount, f_len, (const uint32_t*)seg_first,
-                            work + 2, (const uint32_t*)lenoff, visited0, exit0);
+                       work + 1, (const uint16_t*)dist, lenoff, visited0, exit0 + tiles, 65535u, XHE_CHUNK);
+            const unsigned long long sb = (tiles + 127) / 128;
+            const uint32_t qg = sb < (unsigned long long)ctx->sm_count * 16 ? (uint32_t)sb : (uint32_t)ctx->sm_count * 16;
+            MSC_LAUNCH(ctx, lz_stitch_kernel, qg, 128, d_in, fcount, f_off, f_len, (const uint32_t*)seg_first, (const uint16_t*)dist, lenoff,
+                       visited0, (const uint32_t*)(exit0 + tiles), exit0, 65535u, XHE_CHUNK);
         }
+        pre.dist = dist;
     }
     MSC_OPT_IN_SMEM(xhuff_encode_kernel, sizeof(XhEncSmem));
     MSC_OPT_IN_SMEM(xhuff_encode_exact_kernel, sizeof(XhEncSmem));
@@ -740,7 +742,7 @@ static MSCompStatus xpress_encode_launch(mscomp_gpu_ctx* ctx, const uint8_t* d_i
     if (!fast && !exact) return MSCOMP_MEM_ERROR;                      // the reference parse never falls back to the other matcher
     if (exact) {
         const size_t npos = (size_t)total_segs * LZX_SEG, tiles = npos / LZF_TILE;
-        const size_t lo_b = npos * 4, v_b = npos / 8, x_b = tiles * 4;             // answers of Find, assumed parse per tile, its exit
+        const size_t lo_b = npos * 4, v_b = npos / 8, x_b = tiles * 4 + (npos / LZX_SUB) * 4;   // answers of Find, token starts, exits per tile + per sub-tile
         uint8_t* sc = (uint8_t*)ctx->get(SC_AUX2, lo_b + v_b + x_b + npos * 2 + 256);
         if (!sc) return MSCOMP_MEM_ERROR;
         pre.seg_first = seg_first;
@@ -752,23 +754,20 @@ static MSCompStatus xpress_encode_launch(mscomp_gpu_ctx* ctx, const uint8_t* d_i
         if (total_segs) {
             const size_t prev_smem = 32768 * sizeof(uint16_t) + LZX_STAGE + 128;
             MSC_OPT_IN_SMEM(lz_prev_kernel<uint16_t>, prev_smem);
-            MSC_OPT_IN_SMEM(lz_parse0_kernel, sizeof(LzFrontSmem));
             const unsigned long long pieces = total_segs * (LZX_SEG / LZX_PIECE);
             const uint32_t pg = pieces < (unsigned long long)ctx->sm_count * 3 ? (uint32_t)pieces : (uint32_t)ctx->sm_count * 3;
             MSC_LAUNCH_SMEM(ctx, lz_prev_kernel<uint16_t>, pg, 32, prev_smem, d_in, b->count, b->d_in_off, b->d_in_len, (const uint32_t*)seg_first, work,
                             dist, 8192u, LZX_PIECE);
             const uint32_t fg = total_segs < (unsigned long long)ctx->sm_count * 8 ? (uint32_t)total_segs : (uint32_t)ctx->sm_count * 8;
-            static const char* occ = getenv("MSCOMP_FIND_OCC");
-            if (occ && occ[0] == '8')
-                MSC_LAUNCH(ctx, lz_find_kernel<8>, fg, LZX_FIND_THREADS, d_in, b->count, b->d_in_off, b->d_in_len, (const uint32_t*)seg_first,
-                           work + 1, (const uint16_t*)dist, pre.lenoff, 8192u, 0u);
-            else
-                MSC_LAUNCH(ctx, lz_find_kernel<6>, fg, LZX_FIND_THREADS, d_in, b->count, b->d_in_off, b->d_in_len, (const uint32_t*)seg_first,
-                           work + 1, (const uint16_t*)dist, pre.lenoff, 8192u, 0u);
-            const uint32_t qg = total_segs < (unsigned long long)ctx->sm_count * 5 ? (uint32_t)total_segs : (uint32_t)ctx->sm_count * 5;
-            MSC_LAUNCH_SMEM(ctx, lz_parse0_kernel, qg, LZF_THREADS, sizeof(LzFrontSmem), b->count, b->d_in_len, (const uint32_t*)seg_first,
-                            work + 2, (const uint32_t*)pre.lenoff, pre.visited, pre.next_p);
+            cudaMemsetAsync(pre.lenoff, 0xFF, lo_b, ctx->stream);       // LZX_UNKNOWN: nobody has asked
+            MSC_LAUNCH(ctx, lz_find_kernel<6>, fg, LZX_FIND_THREADS, d_in, b->count, b->d_in_off, b->d_in_len, (const uint32_t*)seg_first,
+                       work + 1, (const uint16_t*)dist, pre.lenoff, pre.visited, pre.next_p + tiles, 8192u, 0u);
+            const unsigned long long sb = (tiles + 127) / 128;
+            const uint32_t qg = sb < (unsigned long long)ctx->sm_count * 16 ? (uint32_t)sb : (uint32_t)ctx->sm_count * 16;
+            MSC_LAUNCH(ctx, lz_stitch_kernel, qg, 128, d_in, b->count, b->d_in_off, b->d_in_len, (const uint32_t*)seg_first, (const uint16_t*)dist,
+                       pre.lenoff, pre.visited, (const uint32_t*)(pre.next_p + tiles), pre.next_p, 8192u, 0u);
         }
+        pre.dist = dist;
         MSC_LAUNCH_SMEM(ctx, xpress_emit_exact_kernel, b->count < cap ? b->count : cap, XPE_THREADS, sizeof(XpEncSmem),
                         d_in, d_out, b->count, b->d_in_off, b->d_in_len, b->d_out_off, b->d_out_cap, b->d_out_len, b->d_status,
                         seg_tiles, index, index_stride, pre);

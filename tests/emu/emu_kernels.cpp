@@ -63,7 +63,7 @@ void emu_xhuff_encode(const uint8_t* in, uint8_t* out, uint32_t count, const uin
 // its restart index (eos_mode 0), laid out like emu_xhuff_encode_index_check's.
 static void emu_xhuff_exact_front(const uint8_t* in, uint32_t count, const uint64_t* in_off, const uint32_t* in_len, uint32_t grid, int eos_mode,
                                   std::vector<uint32_t>& seg_first, std::vector<uint32_t>& lenoff, std::vector<uint32_t>& visited0,
-                                  std::vector<uint32_t>& exit0, std::vector<uint32_t>& desc_len)
+                                  std::vector<uint32_t>& exit0, std::vector<uint32_t>& desc_len, std::vector<uint16_t>& dist_out)
 {
     using namespace msc;
     unsigned long long totals[3] = {0, 0, 0};
@@ -83,24 +83,26 @@ static void emu_xhuff_exact_front(const uint8_t* in, uint32_t count, const uint6
         big = totals[2] > XHE_CHUNK;
     }
     const size_t npos = (size_t)totals[0] * LZX_SEG;
-    std::vector<uint16_t> dist(npos + 1, 0xDEAD);
-    lenoff.assign(npos + 1, 0xDEADBEEFu); visited0.assign(npos / 32 + 1, 0xDEADBEEFu); exit0.assign(npos / LZF_TILE + 1, 0xDEADBEEFu);
+    lenoff.assign(npos + 1, LZX_UNKNOWN); visited0.assign(npos / 32 + 1, 0xDEADBEEFu); exit0.assign(npos / LZF_TILE + 1, 0xDEADBEEFu);
+    std::vector<uint32_t> exit_sub(npos / LZX_SUB + 1, 0xDEADBEEFu);
+    dist_out.assign(npos + 1, 0xDEAD);
     if (!totals[0]) return;
-    if (big) emu::launch(lz_prev_kernel<uint32_t>, dim3e(grid), dim3e(32), in, fcount, f_off, f_len, (const uint32_t*)seg_first.data(), work, dist.data(), 65535u, LZX_SEG);
-    else emu::launch(lz_prev_kernel<uint16_t>, dim3e(grid), dim3e(32), in, fcount, f_off, f_len, (const uint32_t*)seg_first.data(), work, dist.data(), 65535u, LZX_SEG);
+    if (big) emu::launch(lz_prev_kernel<uint32_t>, dim3e(grid), dim3e(32), in, fcount, f_off, f_len, (const uint32_t*)seg_first.data(), work, dist_out.data(), 65535u, LZX_SEG);
+    else emu::launch(lz_prev_kernel<uint16_t>, dim3e(grid), dim3e(32), in, fcount, f_off, f_len, (const uint32_t*)seg_first.data(), work, dist_out.data(), 65535u, LZX_SEG);
     emu::launch(lz_find_kernel<6>, dim3e(grid), dim3e(LZX_FIND_THREADS), in, fcount, f_off, f_len, (const uint32_t*)seg_first.data(), work + 1,
-                (const uint16_t*)dist.data(), lenoff.data(), 65535u, XHE_CHUNK);
-    emu::launch(lz_parse0_kernel, dim3e(grid), dim3e(LZF_THREADS), fcount, f_len, (const uint32_t*)seg_first.data(), work + 2,
-                (const uint32_t*)lenoff.data(), visited0.data(), exit0.data());
+                (const uint16_t*)dist_out.data(), lenoff.data(), visited0.data(), exit_sub.data(), 65535u, XHE_CHUNK);
+    emu::launch(lz_stitch_kernel, dim3e(grid), dim3e(128), in, fcount, f_off, f_len, (const uint32_t*)seg_first.data(), (const uint16_t*)dist_out.data(),
+                lenoff.data(), visited0.data(), (const uint32_t*)exit_sub.data(), exit0.data(), 65535u, XHE_CHUNK);
 }
 void emu_xhuff_encode_exact(const uint8_t* in, uint8_t* out, uint32_t count, const uint64_t* in_off, const uint32_t* in_len,
                             const uint64_t* out_off, const uint32_t* out_cap, uint32_t* out_len, int32_t* status, uint32_t grid, uint32_t eos_mode)
 {
     using namespace msc;
     std::vector<uint32_t> seg_first, lenoff, visited0, exit0, desc_len;
-    emu_xhuff_exact_front(in, count, in_off, in_len, grid, (int)eos_mode, seg_first, lenoff, visited0, exit0, desc_len);
+    std::vector<uint16_t> dist;
+    emu_xhuff_exact_front(in, count, in_off, in_len, grid, (int)eos_mode, seg_first, lenoff, visited0, exit0, desc_len, dist);
     std::vector<uint8_t> scratch((size_t)grid * XHE_SCRATCH_BYTES + 64);
-    XhPre pre{seg_first.data(), lenoff.data(), visited0.data(), exit0.data(), desc_len.data()};
+    XhPre pre{seg_first.data(), lenoff.data(), visited0.data(), exit0.data(), dist.data(), desc_len.data()};
     emu::launch(xhuff_encode_exact_kernel, dim3e(grid), dim3e(XHE_THREADS), in, out, count, in_off, in_len, out_off, out_cap, out_len, status,
                 scratch.data(), (int)eos_mode, (XhSeg*)nullptr, (const uint64_t*)nullptr, (uint32_t*)nullptr, pre);
 }
@@ -283,16 +285,16 @@ void emu_xpress_encode_exact(const uint8_t* in, uint8_t* out, uint32_t count, co
     emu::launch(xpress_segments_kernel, dim3e(1), dim3e(1024), in_len, count, seg_first.data(), totals, work);
     const size_t npos = (size_t)totals[0] * LZX_SEG;
     std::vector<uint16_t> dist(npos + 1, 0xDEAD);
-    std::vector<uint32_t> lenoff(npos + 1, 0xDEADBEEFu), visited0(npos / 32 + 1, 0xDEADBEEFu), exit0(npos / LZF_TILE + 1, 0xDEADBEEFu);
+    std::vector<uint32_t> lenoff(npos + 1, LZX_UNKNOWN), visited0(npos / 32 + 1, 0xDEADBEEFu), exit0(npos / LZF_TILE + 1, 0xDEADBEEFu), exit_sub(npos / LZX_SUB + 1, 0xDEADBEEFu);
     if (totals[0]) {
         emu::launch(lz_prev_kernel<uint16_t>, dim3e(grid), dim3e(32), in, count, in_off, in_len, (const uint32_t*)seg_first.data(), work,
                     dist.data(), 8192u, LZX_PIECE);
         emu::launch(lz_find_kernel<6>, dim3e(grid), dim3e(LZX_FIND_THREADS), in, count, in_off, in_len, (const uint32_t*)seg_first.data(), work + 1,
-                    (const uint16_t*)dist.data(), lenoff.data(), 8192u, 0u);
-        emu::launch(lz_parse0_kernel, dim3e(grid), dim3e(LZF_THREADS), count, in_len, (const uint32_t*)seg_first.data(), work + 2,
-                    (const uint32_t*)lenoff.data(), visited0.data(), exit0.data());
+                    (const uint16_t*)dist.data(), lenoff.data(), visited0.data(), exit_sub.data(), 8192u, 0u);
+        emu::launch(lz_stitch_kernel, dim3e(grid), dim3e(128), in, count, in_off, in_len, (const uint32_t*)seg_first.data(), (const uint16_t*)dist.data(),
+                    lenoff.data(), visited0.data(), (const uint32_t*)exit_sub.data(), exit0.data(), 8192u, 0u);
     }
-    XpPre pre{seg_first.data(), lenoff.data(), visited0.data(), exit0.data()};
+    XpPre pre{seg_first.data(), lenoff.data(), visited0.data(), exit0.data(), dist.data()};
     emu::launch(xpress_emit_exact_kernel, dim3e(grid), dim3e(XPE_THREADS), in, out, count, in_off, in_len, out_off, out_cap, out_len, status,
                 index ? seg_bytes / (uint32_t)LZF_TILE : 0u, (XpressSeg*)index, stride, pre);
 }
