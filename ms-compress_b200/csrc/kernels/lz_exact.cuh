@@ -30,7 +30,9 @@ constexpr uint32_t LZX_PIECE = 32768;          // lz_prev_kernel, 16-bit table: 
 constexpr uint32_t LZX_CHAIN = 11, LZX_NICE = 48;
 constexpr uint32_t LZX_CAP = 4096;             // lz_find_kernel measures at most this many bytes; len == LZX_CAP means "at least": the
                                                // parse extends the (rare) visited ones (lzx_extend), nobody measures the others
-constexpr int LZX_FIND_THREADS = 256;
+constexpr int LZX_FIND_THREADS = 512;         // lz_find_kernel: 16 warps on one 64 KiB segment -- the fewer segments an SM has in flight, the more of their
+                                               // links and bytes stay in L1 / L2 (Xpress-Huffman chains roam the whole 64 KiB)
+constexpr int LZX_FIND_MINB = 3;
 
 // the reference's progressive hash after three updates (XpressDictionary.h:58-61 with HashBits = 15): the first byte's high bits fall off
 __device__ __forceinline__ uint32_t lzx_hash(uint32_t key3) { return (((key3 & 0xFFu) << 10) ^ ((key3 >> 3) & 0x1FE0u) ^ ((key3 >> 16) & 0xFFu)) & 0x7FFFu; }
@@ -190,13 +192,14 @@ lz_find_kernel(const uint8_t* __restrict__ in, uint32_t count, const uint64_t* _
                const uint32_t* __restrict__ seg_first, uint32_t* __restrict__ work_counter, const uint16_t* __restrict__ dist,
                uint32_t* __restrict__ lenoff, uint32_t* __restrict__ visited_sub, uint32_t* __restrict__ exit_sub, uint32_t window, uint32_t chunk)
 {
-    __shared__ uint32_t s_work;
+    __shared__ uint32_t s_work, s_next;
     const int tid = (int)threadIdx.x;
     const uint32_t total = seg_first[count];
     for (;;) {
         if (tid == 0) s_work = atomicAdd(work_counter, 1u);
-        __syncthreads();
+        __syncthreads();                                               // (everybody is done with the segment before)
         const uint32_t w = s_work;
+        if (tid == 0) s_next = LZX_FIND_THREADS;                       // sub-tiles beyond the first round are handed out on demand
         __syncthreads();
         if (w >= total) break;
         uint32_t lo = 0, hi = count;
@@ -257,7 +260,7 @@ lz_find_kernel(const uint8_t* __restrict__ in, uint32_t count, const uint64_t* _
                         if (p >= e) {                                  // the assumed parse leaves the sub-tile
                             const uint64_t sub = (ubase + b) / LZX_SUB;
                             visited_sub[2 * sub] = vlo; visited_sub[2 * sub + 1] = vhi; exit_sub[sub] = p;
-                            b += LZX_FIND_THREADS * LZX_SUB;
+                            b = s0 + atomicAdd(&s_next, 1u) * LZX_SUB;     // whoever is done first takes the next one
                             if (b >= s1) { st = ST_END; break; }
                             e = min(b + LZX_SUB, s1); p = b; vlo = vhi = 0;
                         }

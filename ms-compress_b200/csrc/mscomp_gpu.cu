@@ -379,8 +379,8 @@ static MSCompStatus xhuff_encode_launch(mscomp_gpu_ctx* ctx, const uint8_t* d_in
                                 dist, 65535u, LZX_SEG);
             }
             cudaMemsetAsync(lenoff, 0xFF, lo_b, ctx->stream);           // LZX_UNKNOWN: nobody has asked
-            const uint32_t fg = total_segs < (unsigned long long)ctx->sm_count * 8 ? (uint32_t)total_segs : (uint32_t)ctx->sm_count * 8;
-            MSC_LAUNCH(ctx, lz_find_kernel<6>, fg, LZX_FIND_THREADS, d_in, fcount, f_off, f_len, (const uint32_t*)seg_first,
+            const uint32_t fg = total_segs < (unsigned long long)ctx->sm_count * LZX_FIND_MINB ? (uint32_t)total_segs : (uint32_t)ctx->sm_count * LZX_FIND_MINB;
+            MSC_LAUNCH(ctx, lz_find_kernel<LZX_FIND_MINB>, fg, LZX_FIND_THREADS, d_in, fcount, f_off, f_len, (const uint32_t*)seg_first,
                        work + 1, (const uint16_t*)dist, lenoff, visited0, exit0 + tiles, 65535u, XHE_CHUNK);
             const unsigned long long sb = (tiles + 127) / 128;
             const uint32_t qg = sb < (unsigned long long)ctx->sm_count * 16 ? (uint32_t)sb : (uint32_t)ctx->sm_count * 16;
@@ -758,9 +758,9 @@ static MSCompStatus xpress_encode_launch(mscomp_gpu_ctx* ctx, const uint8_t* d_i
             const uint32_t pg = pieces < (unsigned long long)ctx->sm_count * 3 ? (uint32_t)pieces : (uint32_t)ctx->sm_count * 3;
             MSC_LAUNCH_SMEM(ctx, lz_prev_kernel<uint16_t>, pg, 32, prev_smem, d_in, b->count, b->d_in_off, b->d_in_len, (const uint32_t*)seg_first, work,
                             dist, 8192u, LZX_PIECE);
-            const uint32_t fg = total_segs < (unsigned long long)ctx->sm_count * 8 ? (uint32_t)total_segs : (uint32_t)ctx->sm_count * 8;
+            const uint32_t fg = total_segs < (unsigned long long)ctx->sm_count * LZX_FIND_MINB ? (uint32_t)total_segs : (uint32_t)ctx->sm_count * LZX_FIND_MINB;
             cudaMemsetAsync(pre.lenoff, 0xFF, lo_b, ctx->stream);       // LZX_UNKNOWN: nobody has asked
-            MSC_LAUNCH(ctx, lz_find_kernel<6>, fg, LZX_FIND_THREADS, d_in, b->count, b->d_in_off, b->d_in_len, (const uint32_t*)seg_first,
+            MSC_LAUNCH(ctx, lz_find_kernel<LZX_FIND_MINB>, fg, LZX_FIND_THREADS, d_in, b->count, b->d_in_off, b->d_in_len, (const uint32_t*)seg_first,
                        work + 1, (const uint16_t*)dist, pre.lenoff, pre.visited, pre.next_p + tiles, 8192u, 0u);
             const unsigned long long sb = (tiles + 127) / 128;
             const uint32_t qg = sb < (unsigned long long)ctx->sm_count * 16 ? (uint32_t)sb : (uint32_t)ctx->sm_count * 16;

@@ -89,7 +89,7 @@ static void emu_xhuff_exact_front(const uint8_t* in, uint32_t count, const uint6
     if (!totals[0]) return;
     if (big) emu::launch(lz_prev_kernel<uint32_t>, dim3e(grid), dim3e(32), in, fcount, f_off, f_len, (const uint32_t*)seg_first.data(), work, dist_out.data(), 65535u, LZX_SEG);
     else emu::launch(lz_prev_kernel<uint16_t>, dim3e(grid), dim3e(32), in, fcount, f_off, f_len, (const uint32_t*)seg_first.data(), work, dist_out.data(), 65535u, LZX_SEG);
-    emu::launch(lz_find_kernel<6>, dim3e(grid), dim3e(LZX_FIND_THREADS), in, fcount, f_off, f_len, (const uint32_t*)seg_first.data(), work + 1,
+    emu::launch(lz_find_kernel<LZX_FIND_MINB>, dim3e(grid), dim3e(LZX_FIND_THREADS), in, fcount, f_off, f_len, (const uint32_t*)seg_first.data(), work + 1,
                 (const uint16_t*)dist_out.data(), lenoff.data(), visited0.data(), exit_sub.data(), 65535u, XHE_CHUNK);
     emu::launch(lz_stitch_kernel, dim3e(grid), dim3e(128), in, fcount, f_off, f_len, (const uint32_t*)seg_first.data(), (const uint16_t*)dist_out.data(),
                 lenoff.data(), visited0.data(), (const uint32_t*)exit_sub.data(), exit0.data(), 65535u, XHE_CHUNK);
@@ -289,7 +289,7 @@ void emu_xpress_encode_exact(const uint8_t* in, uint8_t* out, uint32_t count, co
     if (totals[0]) {
         emu::launch(lz_prev_kernel<uint16_t>, dim3e(grid), dim3e(32), in, count, in_off, in_len, (const uint32_t*)seg_first.data(), work,
                     dist.data(), 8192u, LZX_PIECE);
-        emu::launch(lz_find_kernel<6>, dim3e(grid), dim3e(LZX_FIND_THREADS), in, count, in_off, in_len, (const uint32_t*)seg_first.data(), work + 1,
+        emu::launch(lz_find_kernel<LZX_FIND_MINB>, dim3e(grid), dim3e(LZX_FIND_THREADS), in, count, in_off, in_len, (const uint32_t*)seg_first.data(), work + 1,
                     (const uint16_t*)dist.data(), lenoff.data(), visited0.data(), exit_sub.data(), 8192u, 0u);
         emu::launch(lz_stitch_kernel, dim3e(grid), dim3e(128), in, count, in_off, in_len, (const uint32_t*)seg_first.data(), (const uint16_t*)dist.data(),
                     lenoff.data(), visited0.data(), (const uint32_t*)exit_sub.data(), exit0.data(), 8192u, 0u);
