@@ -172,22 +172,39 @@ __device__ __forceinline__ void xhe_build_codes_reference(XhEncSmem& sm)
         if (tid == 0) {
             uint32_t hl = 0;
             heap[0] = 0;                                                      // node 0, weight 0: the sentinel above the root
+            // The replay is one long chain of dependent shared-memory loads, so both primitives fetch everything a step can need in
+            // one go: a push all the ancestors of the new leaf (their indices are known up front), a pop both children AND the four
+            // grandchildren (the sift only rewrites ancestors, so what was fetched stays true) -- two levels per round trip.
             auto push = [&](uint32_t x, uint32_t wx) {
                 uint32_t j = ++hl;
-                for (;;) { const unsigned long long up = heap[j >> 1]; if (!(wx < (uint32_t)(up >> 32))) break; heap[j] = up; j >>= 1; }
+                unsigned long long up[10];
+#pragma unroll
+                for (int k = 0; k < 10; ++k) up[k] = heap[j >> (k + 1)];             // j <= 513: the 10th ancestor is the sentinel at 0
+#pragma unroll
+                for (int k = 0; k < 10; ++k) { if (!(wx < (uint32_t)(up[k] >> 32))) break; heap[j] = up[k]; j >>= 1; }
                 heap[j] = ((unsigned long long)wx << 32) | x;
             };
+            auto wof = [](unsigned long long e2) -> uint32_t { return (uint32_t)(e2 >> 32); };
             auto pop = [&]() {
                 const unsigned long long t = heap[hl--];
                 const uint32_t wt = (uint32_t)(t >> 32);
                 uint32_t i = 1;
                 for (;;) {
-                    uint32_t j = i << 1;
+                    const uint32_t j = i << 1;
                     if (j > hl) break;
-                    unsigned long long c = heap[j];
-                    if (j < hl) { const unsigned long long c2 = heap[j + 1]; if ((uint32_t)(c2 >> 32) < (uint32_t)(c >> 32)) { c = c2; ++j; } }
-                    if (wt < (uint32_t)(c >> 32)) break;
-                    heap[i] = c; i = j;
+                    const unsigned long long c0 = heap[j], c1 = heap[min(j + 1u, 513u)];
+                    const unsigned long long g0 = heap[min(2u * j, 513u)], g1 = heap[min(2u * j + 1u, 513u)], g2 = heap[min(2u * j + 2u, 513u)], g3 = heap[min(2u * j + 3u, 513u)];
+                    const bool right = j < hl && wof(c1) < wof(c0);
+                    const unsigned long long c = right ? c1 : c0;
+                    if (wt < wof(c)) break;
+                    heap[i] = c; i = right ? j + 1u : j;
+                    const uint32_t jj = i << 1;
+                    if (jj > hl) break;
+                    const unsigned long long ga = right ? g2 : g0, gb = right ? g3 : g1;
+                    const bool right2 = jj < hl && wof(gb) < wof(ga);
+                    const unsigned long long g = right2 ? gb : ga;
+                    if (wt < wof(g)) break;
+                    heap[i] = g; i = right2 ? jj + 1u : jj;
                 }
                 heap[i] = t;
             };

@@ -25,6 +25,18 @@ for kern in ("emu_lznt1_decode",):
         st,sz,ch=emu_util.emu_lznt1_decode(emu,c,kernel=kern); assert not st.any() and b''.join(ch)==p
         e,_=emu_util.emu_lznt1_encode(emu,p); assert e==c
     print(kern,'ok')
+# the reference-parse encoders (lz_exact.cuh): byte-identical to the oracle's compressors; independent buffers and the one-shot stream layout
+xp=plains+[bytes(9000)+plains[3], bytes(30000)+b"x"+bytes(30000)+plains[2], plains[3]*3]
+st,_,outs=emu_util.emu_batch(emu,"emu_xpress_encode_exact",xp,[MAX["xpress"](len(p)) for p in xp],grid=3,extra=(ctypes.c_uint32(16384),ctypes.c_void_p(0),ctypes.c_uint32(0)))
+assert not st.any()
+for p,c in zip(xp,outs): assert c==ocall('xpress_compress',p,MAX["xpress"](len(p))+16)[1]
+st,_,outs=emu_util.emu_batch(emu,"emu_xhuff_encode_exact",xp,[MAX["xpress_huff"](len(p)) for p in xp],grid=3,extra=(ctypes.c_uint32(0),))
+assert not st.any()
+for p,c in zip(xp,outs): assert c==ocall('xpress_huff_compress',p,MAX["xpress_huff"](len(p))+16)[1]
+for p in xp:
+    if len(p)>65536:
+        st,c=emu_util.emu_xhuff_stream_exact(emu,p); assert not st.any() and c==ocall('xpress_huff_compress',p,MAX["xpress_huff"](len(p))+16)[1]
+print('reference-parse encoders ok')
 # two-kernel decoders, warp parser + block apply, restart index, heavy LZNT1 chunks, GPU chunk index
 import numpy as np, random
 for fmt,dk in (("xpress_huff","emu_xhuff_decode2"),("xpress","emu_xpress_decode2"),("xpress","emu_xpress_decode_warp")):
