@@ -221,9 +221,10 @@ lz_find_kernel(const uint8_t* __restrict__ in, uint32_t count, const uint64_t* _
         bool fresh = true;                                             // ST_NEW without an answer to store (a sub-tile's first position)
         if (b >= s1) st = ST_END;
         for (;;) {
-            const unsigned b_hop = __ballot_sync(FULL, st == ST_HOP), b_cmp = __ballot_sync(FULL, st == ST_CMP), b_new = __ballot_sync(FULL, st == ST_NEW);
-            if (!(b_hop | b_cmp | b_new)) break;
-            const int c_hop = __popc(b_hop), c_cmp = __popc(b_cmp), c_new = __popc(b_new);
+            // the census of the three states in one warp reduction: 8 bits per state (ST_END contributes nothing)
+            const uint32_t census = __reduce_add_sync(FULL, st < ST_END ? 1u << (8u * st) : 0u);
+            if (!census) break;
+            const int c_hop = (int)(census & 0xFFu), c_cmp = (int)((census >> 8) & 0xFFu), c_new = (int)(census >> 16);
             if (c_hop >= c_cmp && c_hop >= c_new) {
 #pragma unroll
                 for (int rep = 0; rep < 2; ++rep)                      // two links per round: half the votes per link

@@ -505,7 +505,7 @@ xhuff_encode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, u
     xhuff_encode_body<false>(in, out, count, in_off, in_len, out_off, out_cap, out_len, status, scratch, eos_mode, index, index_off, nseg, XhPre{});
 }
 
-__global__ void __launch_bounds__(XHE_THREADS, 4)
+__global__ void __launch_bounds__(XHE_THREADS, 5)
 xhuff_encode_exact_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint32_t count,
                           const uint64_t* __restrict__ in_off, const uint32_t* __restrict__ in_len,
                           const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ out_cap,
