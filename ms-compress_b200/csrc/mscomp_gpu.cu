@@ -12,6 +12,7 @@
 #include "kernels/xhuff_index.cuh"
 #include "kernels/xhuff_decode_indexed.cuh"
 #include "kernels/xhuff_chunks.cuh"
+#include "kernels/lz_jump.cuh"
 #include "kernels/xpress_decode.cuh"
 #include "kernels/xhuff_encode.cuh"
 #include "kernels/xpress_encode.cuh"
@@ -576,6 +577,34 @@ MSCompStatus mscomp_gpu_xpress_huff_decompress_batch(mscomp_gpu_ctx* ctx, const 
     return msc_cuda_status(cudaGetLastError(), "xpress_huff_decompress");
 }
 
+// Token execution of one chain of chunks by pointer jumping (kernels/lz_jump.cuh): d_ch = slot[nch] (u64) | ntok[nch] | pos[nch] as
+// xhs_apply_chain_kernel takes them.  false: no room for the words (4 bytes per output byte) -- the caller executes in order.
+static bool produce_by_jumping(mscomp_gpu_ctx* ctx, const uint32_t* d_tok, const uint8_t* d_ch, size_t nch, uint32_t produced, uint8_t* d_out)
+{
+    static const bool off = getenv("MSCOMP_LZ_JUMP") && strcmp(getenv("MSCOMP_LZ_JUMP"), "0") == 0;
+    if (off || !produced) return false;
+    const size_t bytes = (size_t)produced * sizeof(uint32_t) + 256;
+    if (bytes > ctx->scratch_cap[SC_AUX0]) {
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        if (bytes > free_b / 2 + ctx->scratch_cap[SC_AUX0]) return false;
+    }
+    uint32_t* word = (uint32_t*)ctx->get(SC_AUX0, bytes);
+    unsigned long long* ctr = ctx->get_counters();
+    if (!word || !ctr) return false;
+    uint32_t* unknown = (uint32_t*)(ctr + 8);
+    const uint32_t cap = (uint32_t)ctx->sm_count * 8;
+    const uint32_t blocks = (produced + LZJ_THREADS - 1) / LZJ_THREADS;
+    MSC_LAUNCH(ctx, lzj_expand_kernel, (uint32_t)nch < cap ? (uint32_t)nch : cap, LZJ_THREADS, d_tok, (const uint64_t*)d_ch, (const uint32_t*)(d_ch + nch * 8),
+               (const uint32_t*)(d_ch + nch * 12), (uint32_t)nch, word);
+    uint32_t rounds = 1;
+    while ((1ull << rounds) < produced) ++rounds;                                 // the distance to a chain's literal at least halves per round
+    for (uint32_t r = 0; r < rounds; ++r) MSC_LAUNCH(ctx, lzj_round_kernel, blocks < cap * 2 ? blocks : cap * 2, LZJ_THREADS, word, produced);
+    cudaMemsetAsync(unknown, 0, sizeof(uint32_t), ctx->stream);
+    MSC_LAUNCH(ctx, lzj_store_kernel, blocks < cap * 2 ? blocks : cap * 2, LZJ_THREADS, (const uint32_t*)word, d_out, produced, unknown);
+    return true;
+}
+
 // ---- one multi-chunk Xpress-Huffman stream: chunk-parallel parse (kernels/xhuff_chunks.cuh) --------------------------------
 // d_in[0..in_len) is the stream, d_out has room for `cap` bytes.  *handled = true: the stream was decoded, *total bytes produced,
 // status OK.  *handled = false: this path does not apply (one chunk, an incomplete code, a damaged stream, too little room or
@@ -690,7 +719,9 @@ MSCompStatus msc_xhuff_stream_decode(mscomp_gpu_ctx* ctx, const uint8_t* d_in, u
             const uint32_t ab = ((uint32_t)nch + LZA_WARPS_PER_BLOCK - 1) / LZA_WARPS_PER_BLOCK, acap = (uint32_t)ctx->sm_count * 16;
             MSC_LAUNCH(ctx, xhs_apply_chunks_kernel, ab < acap ? ab : acap, 32 * LZA_WARPS_PER_BLOCK, (const uint32_t*)d_tok, (const uint64_t*)d_ch,
                        (const uint32_t*)(d_ch + nch * 8), (const uint32_t*)(d_ch + nch * 12), (uint32_t)nch, d_out);
-        } else {                                                                  // matches reach across chunk starts: in stream order, one block
+        } else if (produced <= 0x7FFFFFFFull && produce_by_jumping(ctx, (const uint32_t*)d_tok, d_ch, nch, (uint32_t)produced, d_out)) {
+            // matches reach across chunk starts: no order at all, pointer jumping over one word per output byte (lz_jump.cuh)
+        } else {                                                                  // ... or, without room for the words, in stream order by one block
             MSC_OPT_IN_SMEM(xhs_apply_chain_kernel, LZR_RING);
             MSC_LAUNCH_SMEM(ctx, xhs_apply_chain_kernel, 1, 32 * LZB_WARPS, LZR_RING, (const uint32_t*)d_tok, (const uint64_t*)d_ch, (const uint32_t*)(d_ch + nch * 8),
                             (const uint32_t*)(d_ch + nch * 12), (uint32_t)nch, d_out);

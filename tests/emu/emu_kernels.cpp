@@ -9,6 +9,7 @@
 #include "../../ms-compress_b200/csrc/kernels/xhuff_index.cuh"
 #include "../../ms-compress_b200/csrc/kernels/xhuff_decode_indexed.cuh"
 #include "../../ms-compress_b200/csrc/kernels/xhuff_chunks.cuh"
+#include "../../ms-compress_b200/csrc/kernels/lz_jump.cuh"
 #include "../../ms-compress_b200/csrc/kernels/xpress_decode.cuh"
 #include "../../ms-compress_b200/csrc/kernels/xhuff_encode.cuh"
 #include "../../ms-compress_b200/csrc/kernels/xpress_encode.cuh"
@@ -194,6 +195,8 @@ void emu_xhuff_decode_indexed(const uint8_t* in, uint8_t* out, uint32_t count, c
 // candidate parses one chunk -> chain from offset 0 -> token execution (all chunks at once when none reaches back, else in order).
 // The stitching mirrors msc_xhuff_stream_decode (csrc/mscomp_gpu.cu).  Returns 1 when the stream was decoded this way (*total
 // bytes in out), 0 when the path declines; *info = candidates | chunks << 16 | (1 << 31 if the chunks ran independently).
+static int g_chain_in_order = 0;
+void emu_xhuff_stream_in_order(int on) { g_chain_in_order = on; }
 uint32_t emu_xhuff_stream_decode(const uint8_t* in, uint32_t n, uint8_t* out, uint64_t cap, uint64_t* total, uint32_t* info)
 {
     using namespace msc;
@@ -243,9 +246,19 @@ uint32_t emu_xhuff_stream_decode(const uint8_t* in, uint32_t n, uint8_t* out, ui
         if (independent)
             emu::launch(xhs_apply_chunks_kernel, dim3e(2), dim3e(32 * LZA_WARPS_PER_BLOCK), (const uint32_t*)tok.data(), (const uint64_t*)slot.data(),
                         (const uint32_t*)nt.data(), (const uint32_t*)pos.data(), (uint32_t)chain.size(), out);
-        else
+        else if (g_chain_in_order)
             emu::launch(xhs_apply_chain_kernel, dim3e(1), dim3e(32 * LZB_WARPS), (const uint32_t*)tok.data(), (const uint64_t*)slot.data(),
                         (const uint32_t*)nt.data(), (const uint32_t*)pos.data(), (uint32_t)chain.size(), out);
+        else {                                                     // pointer jumping (lz_jump.cuh), as msc_xhuff_stream_decode does it
+            std::vector<uint32_t> word(produced + 1, 0xDEADBEEFu);
+            uint32_t unknown = 0, rounds = 1;
+            while ((1ull << rounds) < produced) ++rounds;
+            emu::launch(lzj_expand_kernel, dim3e(2), dim3e(LZJ_THREADS), (const uint32_t*)tok.data(), (const uint64_t*)slot.data(), (const uint32_t*)nt.data(),
+                        (const uint32_t*)pos.data(), (uint32_t)chain.size(), word.data());
+            for (uint32_t r = 0; r < rounds; ++r) emu::launch(lzj_round_kernel, dim3e(3), dim3e(LZJ_THREADS), word.data(), (uint32_t)produced);
+            emu::launch(lzj_store_kernel, dim3e(3), dim3e(LZJ_THREADS), (const uint32_t*)word.data(), out, (uint32_t)produced, &unknown);
+            if (unknown) return 0;
+        }
     }
     const bool packed = independent;
     *total = produced;

@@ -297,12 +297,14 @@ def test_xhuff_chunk_parallel_stream_decode(emu, oracle, ms):
     """One multi-chunk stream: chunk starts recognised by their complete code-length tables, one lane per chunk, chain stitched from
     offset 0.  Reference-made streams have matches that reach into the previous chunk (executed in order); streams made by our
     encoder do not (all chunks at once).  Streams the path cannot vouch for must be declined, never decoded wrongly."""
-    for kind, n in (("text", 200000), ("text", 65536 * 3), ("runs", 150000), ("random", 140000), ("text", 65537)):
+    for kind, n in (("text", 200000), ("text", 65536 * 3), ("runs", 150000), ("random", 140000), ("text", 65537), ("runs", 400000)):
         plain = ms.generate(kind, n, 7 + n % 5)
         comp = oracle.compress("xpress_huff", plain)
-        handled, got, info = _emu_stream_decode(emu, comp, n)
-        assert handled == 1 and got == plain, (kind, n, handled, info)
-        assert (info >> 16) & 0x7FFF == (n + 65535) // 65536
+        for in_order in (1, 0):                                      # the in-order block executor, then pointer jumping (lz_jump.cuh, the default)
+            emu.emu_xhuff_stream_in_order(in_order)
+            handled, got, info = _emu_stream_decode(emu, comp, n)
+            assert handled == 1 and got == plain, (kind, n, handled, info, in_order)
+            assert (info >> 16) & 0x7FFF == (n + 65535) // 65536
         # our own encoder: window reset per chunk -> independent chunks
         st, ol, outs = emu_batch(emu, "emu_xhuff_encode", [plain], [len(plain) + 34 + 258 + 258 * (len(plain) // 65536) + 16])
         assert not st.any()
