@@ -16,6 +16,7 @@
 #include "kernels/xpress_decode.cuh"
 #include "kernels/xhuff_encode.cuh"
 #include "kernels/xpress_encode.cuh"
+#include "kernels/xpress_spec.cuh"
 #include <new>
 #include <algorithm>
 #include <vector>
@@ -392,8 +393,13 @@ static MSCompStatus xhuff_encode_launch(mscomp_gpu_ctx* ctx, const uint8_t* d_in
     }
     MSC_OPT_IN_SMEM(xhuff_encode_kernel, sizeof(XhEncSmem));
     MSC_OPT_IN_SMEM(xhuff_encode_exact_kernel, sizeof(XhEncSmem));
-    static int per_sm = 0;                                            // resident blocks per SM (the kernel keeps per-block scratch: grid = one wave)
-    if (!per_sm && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, xhuff_encode_exact_kernel, XHE_THREADS, sizeof(XhEncSmem)) != cudaSuccess || per_sm < 1)) per_sm = 3;
+    static int per_sm_of[2] = {0, 0};                                 // resident blocks per SM of the kernel that runs (per-block scratch: grid = ONE wave;
+    int& per_sm = per_sm_of[exact ? 1 : 0];                           // the two kernels differ: 4 and 5 -- a grid sized for the other one leaves a tail wave)
+    if (!per_sm) {
+        const cudaError_t oe = exact ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, xhuff_encode_exact_kernel, XHE_THREADS, sizeof(XhEncSmem))
+                                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, xhuff_encode_kernel, XHE_THREADS, sizeof(XhEncSmem));
+        if (oe != cudaSuccess || per_sm < 1) per_sm = 3;
+    }
     const uint32_t cap = (uint32_t)ctx->sm_count * (uint32_t)per_sm;
     const uint32_t grid = b->count < cap ? b->count : cap;
     uint8_t* scratch = (uint8_t*)ctx->get(SC_AUX2, (size_t)grid * XHE_SCRATCH_BYTES + 64);
@@ -728,6 +734,100 @@ MSCompStatus msc_xhuff_stream_decode(mscomp_gpu_ctx* ctx, const uint8_t* d_in, u
         }
     }
     const MSCompStatus st = msc_cuda_status(cudaGetLastError(), "xpress_huff_decompress");
+    if (st != MSCOMP_OK) return st;
+    *total = produced;
+    *handled = true;
+    return MSCOMP_OK;
+}
+
+// ---- one plain Xpress stream: flag groups found by speculation (kernels/xpress_spec.cuh) ------------------------------------
+// d_in[0..in_len) is the stream, d_out has room for `cap` bytes (d_out == nullptr: the context's SC_OUT scratch, grown to what the stream
+// produces).  *handled = true: the stream was decoded, *total bytes produced,
+// status OK.  *handled = false: this path does not apply (a damaged stream, too little room or memory ...) and nothing is promised
+// about d_out -- the caller runs the serial decoder, which owns the status codes.
+MSCompStatus msc_xpress_stream_decode(mscomp_gpu_ctx* ctx, const uint8_t* d_in, uint32_t in_len, uint8_t* d_out, uint64_t cap, uint64_t* total, bool* handled)
+{
+    *handled = false;
+    if (!ctx || in_len < 64 || in_len > (1u << 30)) return MSCOMP_OK;
+    cudaSetDevice(ctx->device);
+    const uint32_t npos = in_len - 3;
+    const uint32_t nblk = (npos + XPS_BLK - 1) / XPS_BLK;
+    // layout of the small tables: table[nblk * XPS_NENT] entry[nblk] half[nblk] (u32) | count[nblk] base[nblk] (u64) | summary | result[2] | unit descriptors
+    const size_t t_words = (size_t)nblk * XPS_NENT + 2 * (size_t)nblk;
+    const size_t t_bytes = ((t_words * 4 + 15) & ~(size_t)15) + 2 * (size_t)nblk * 8 + 256;
+    unsigned long long* rec = (unsigned long long*)ctx->get(SC_AUX3, (size_t)npos * 3 * sizeof(unsigned long long) + 64);
+    uint8_t* tb = (uint8_t*)ctx->get(SC_AUX4, t_bytes);
+    uint8_t* h_box = (uint8_t*)ctx->get_pinned(1024);
+    if (!rec || !tb || !h_box) return MSCOMP_OK;
+    uint32_t* table = (uint32_t*)tb;
+    uint32_t* entry = table + (size_t)nblk * XPS_NENT;
+    uint32_t* entry_half = entry + nblk;
+    unsigned long long* count = (unsigned long long*)(tb + ((t_words * 4 + 15) & ~(size_t)15));
+    unsigned long long* base = count + nblk;
+    XpsSummary* d_sum = (XpsSummary*)(base + nblk);
+    uint32_t* d_result = (uint32_t*)(d_sum + 1);
+    uint8_t* d_unit = (uint8_t*)(d_result + 4);                                   // in_off out_off (u64) | in_len out_cap (u32)
+    XpsSummary* h_sum = (XpsSummary*)(h_box + 512);                               // (the first 256 bytes are the result mailbox of the wrappers)
+    uint32_t* h_result = (uint32_t*)(h_box + 512 + 64);
+    uint8_t* h_unit = h_box + 512 + 128;
+    const uint32_t wide = (uint32_t)ctx->sm_count * 8;
+    // 1. every group that could be, the blocks' transfer tables, the true entry states, the true groups counted
+    {
+        const uint64_t nstate = (uint64_t)npos * 3, gb = (nstate + 255) / 256;
+        MSC_LAUNCH(ctx, xps_groups_kernel, gb < wide * 4 ? (uint32_t)gb : wide * 4, 256, d_in, in_len, rec);
+        MSC_OPT_IN_SMEM(xps_blocks_kernel, XPS_NST * sizeof(uint32_t));
+        const uint32_t bcap = (uint32_t)ctx->sm_count * 2;
+        MSC_LAUNCH_SMEM(ctx, xps_blocks_kernel, nblk < bcap ? nblk : bcap, XPS_THREADS, XPS_NST * sizeof(uint32_t), (const unsigned long long*)rec, in_len, nblk, table);
+        MSC_LAUNCH(ctx, xps_entries_kernel, 1, 32, (const uint32_t*)table, nblk, entry, entry_half, d_sum);
+        MSC_LAUNCH(ctx, xps_walk_kernel<false>, nblk < wide * 4 ? nblk : wide * 4, 32, d_in, in_len, (const unsigned long long*)rec, (const uint32_t*)entry,
+                   (const uint32_t*)entry_half, (const XpsSummary*)d_sum, count, (const unsigned long long*)base, (XpressSeg*)nullptr);
+        MSC_LAUNCH(ctx, xps_scan_kernel, 1, 32, (const unsigned long long*)count, base, d_sum, (unsigned long long)cap);
+        cudaMemcpyAsync(h_sum, d_sum, sizeof(XpsSummary), cudaMemcpyDeviceToHost, ctx->stream);
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cudaGetLastError(); return MSCOMP_OK; }
+    }
+    {
+        static const bool trace = getenv("MSCOMP_TRACE") != nullptr;
+        if (trace) fprintf(stderr, "[mscomp] xpress stream: %u blocks, ok=%u, %u groups, %u restart entries, %llu bytes\n", nblk, h_sum->ok, h_sum->groups,
+                           h_sum->nseg, (unsigned long long)h_sum->bytes);
+    }
+    if (!h_sum->ok || !h_sum->nseg || h_sum->bytes > cap || h_sum->bytes > 0x7FFFFFFFull) return MSCOMP_OK;
+    const uint32_t nseg = h_sum->nseg, produced = (uint32_t)h_sum->bytes;
+    if (!produced) return MSCOMP_OK;
+    // 2. the restart index, the indexed parse (one lane per segment), the check that the segments join up
+    const size_t ix_bytes = ((size_t)nseg * sizeof(XpressSeg) + 15) & ~(size_t)15;
+    uint8_t* ixb = (uint8_t*)ctx->get(SC_AUX1, ix_bytes + (size_t)nseg * 3 * sizeof(uint32_t) + 64);
+    uint32_t* tok = (uint32_t*)ctx->get(SC_AUX2, ((size_t)produced + 64) * sizeof(uint32_t));
+    uint8_t* d_ch = (uint8_t*)ctx->get(SC_OFFS, (size_t)nseg * 16 + 64);
+    if (!ixb || !tok || !d_ch) return MSCOMP_OK;
+    XpressSeg* index = (XpressSeg*)ixb;
+    uint32_t* seg_ntok = (uint32_t*)(ixb + ix_bytes);
+    int32_t* seg_status = (int32_t*)(seg_ntok + nseg);
+    uint32_t* seg_end = seg_ntok + 2 * (size_t)nseg;
+    {
+        uint64_t* hu = (uint64_t*)h_unit; hu[0] = 0; hu[1] = 0;
+        uint32_t* hw = (uint32_t*)(hu + 2); hw[0] = in_len; hw[1] = produced;     // capacity = what the stream produces: a segment that disagrees fails
+        cudaMemcpyAsync(d_unit, h_unit, 24, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemsetAsync(d_result, 0, 16, ctx->stream);
+        MSC_LAUNCH(ctx, xps_walk_kernel<true>, nblk < wide * 4 ? nblk : wide * 4, 32, d_in, in_len, (const unsigned long long*)rec, (const uint32_t*)entry,
+                   (const uint32_t*)entry_half, (const XpsSummary*)d_sum, count, (const unsigned long long*)base, index);
+        const uint32_t per_block = 32 * XPD_WARPS_PER_BLOCK;
+        // a lone lane is latency-bound: one segment per warp would be ideal, but the kernel maps 32 consecutive segments to a warp
+        const uint32_t groups = (nseg + per_block - 1) / per_block;
+        MSC_LAUNCH(ctx, xpress_parse_indexed_kernel, groups < wide * 2 ? groups : wide * 2, per_block, d_in, tok, 1u, (const uint64_t*)d_unit,
+                   (const uint32_t*)(d_unit + 16), (const uint64_t*)(d_unit + 8), (const uint32_t*)(d_unit + 20), (const XpressSeg*)index, nseg,
+                   seg_ntok, seg_status, seg_end);
+        const uint32_t cb = (nseg + 255) / 256;
+        MSC_LAUNCH(ctx, xps_chain_kernel, cb < wide ? cb : wide, 256, (const XpressSeg*)index, nseg, (const uint32_t*)seg_ntok, (const int32_t*)seg_status,
+                   (const uint32_t*)seg_end, (unsigned long long*)d_ch, (uint32_t*)(d_ch + (size_t)nseg * 8), (uint32_t*)(d_ch + (size_t)nseg * 12), d_result);
+        cudaMemcpyAsync(h_result, d_result, 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cudaGetLastError(); return MSCOMP_OK; }
+    }
+    if (h_result[0] != 0 || h_result[1] != produced) return MSCOMP_OK;
+    // 3. the tokens, in no order at all (kernels/lz_jump.cuh)
+    if (!d_out) d_out = (uint8_t*)ctx->get(SC_OUT, (size_t)produced + 64);        // (the one-shot wrapper: room for what the stream really produces)
+    if (!d_out) return MSCOMP_OK;
+    if (!produce_by_jumping(ctx, (const uint32_t*)tok, d_ch, nseg, produced, d_out)) return MSCOMP_OK;
+    const MSCompStatus st = msc_cuda_status(cudaGetLastError(), "xpress_decompress");
     if (st != MSCOMP_OK) return st;
     *total = produced;
     *handled = true;

@@ -455,6 +455,33 @@ extern "C" MSCompStatus xpress_compress(const_bytes in, size_t in_len, bytes out
 }
 extern "C" MSCompStatus xpress_decompress(const_bytes in, size_t in_len, bytes out, size_t* out_len)
 {
+    if (!out_len || (!in && in_len) || (!out && *out_len)) return MSCOMP_ARG_ERROR;
+    // One stream is a serial chain for one warp (the format has no marker to start a second reader from).  Streams of some size first
+    // try the speculative path: the flag groups that could start at ANY offset are walked side by side, the true ones are linked up
+    // and become a restart index (kernels/xpress_spec.cuh); whatever it cannot vouch for goes to the serial decoder below, which owns
+    // the status codes.  MSCOMP_XPRESS_ONESHOT=serial forces that one.
+    static const bool no_spec = getenv("MSCOMP_XPRESS_ONESHOT") && strcmp(getenv("MSCOMP_XPRESS_ONESHOT"), "serial") == 0;
+    if (!no_spec && in_len >= 32768 && in_len <= (1u << 30) && *out_len) {
+        mscomp_gpu_ctx* ctx = msc_thread_ctx();
+        if (!ctx) return MSCOMP_MEM_ERROR;
+        const size_t cap = *out_len > 0x7FFFFFFFull ? (size_t)0x7FFFFFFFull : *out_len;
+        uint8_t* d_in = (uint8_t*)ctx->get(SC_IN, in_len + 64);
+        // (the room for the output is only taken once the stream's size is known: callers pass generous capacities)
+        if (d_in) {
+            cudaMemcpyAsync(d_in, in, in_len, cudaMemcpyHostToDevice, ctx->stream);
+            uint64_t total = 0;
+            bool handled = false;
+            MSCompStatus st = msc_xpress_stream_decode(ctx, d_in, (uint32_t)in_len, nullptr, cap, &total, &handled);
+            if (st != MSCOMP_OK) return st;
+            if (handled) {
+                uint8_t* d_out = (uint8_t*)ctx->scratch[SC_OUT];
+                if (total) cudaMemcpyAsync(out, d_out, total, cudaMemcpyDeviceToHost, ctx->stream);
+                if ((st = msc_cuda_status(cudaStreamSynchronize(ctx->stream), "xpress_decompress")) != MSCOMP_OK) return st;
+                *out_len = total;
+                return MSCOMP_OK;
+            }
+        }
+    }
     return one_buffer(mscomp_gpu_xpress_decompress_batch, "xpress_decompress", in, in_len, out, out_len, out_len ? *out_len : 0);
 }
 extern "C" MSCompStatus xpress_huff_decompress(const_bytes in, size_t in_len, bytes out, size_t* out_len)

@@ -43,6 +43,7 @@ extern "C" MSCompStatus msc_xpress_huff_compress_units(mscomp_gpu_ctx* ctx, cons
 // One multi-chunk Xpress-Huffman stream on the device: chunk-parallel parse + token execution (kernels/xhuff_chunks.cuh);
 // *handled = false leaves the stream to the serial decoder.
 extern "C" MSCompStatus msc_xhuff_stream_decode(mscomp_gpu_ctx* ctx, const uint8_t* d_in, uint32_t in_len, uint8_t* d_out, uint64_t cap, uint64_t* total, bool* handled);
+extern "C" MSCompStatus msc_xpress_stream_decode(mscomp_gpu_ctx* ctx, const uint8_t* d_in, uint32_t in_len, uint8_t* d_out, uint64_t cap, uint64_t* total, bool* handled);
 
 #ifdef MSC_NO_XPRESS   // bring-up only
 #define MSC_XPRESS_COMPRESS nullptr

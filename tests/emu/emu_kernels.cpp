@@ -13,6 +13,7 @@
 #include "../../ms-compress_b200/csrc/kernels/xpress_decode.cuh"
 #include "../../ms-compress_b200/csrc/kernels/xhuff_encode.cuh"
 #include "../../ms-compress_b200/csrc/kernels/xpress_encode.cuh"
+#include "../../ms-compress_b200/csrc/kernels/xpress_spec.cuh"
 #include <vector>
 #include <algorithm>
 
@@ -345,6 +346,53 @@ void emu_xpress_decode_indexed(const uint8_t* in, uint8_t* out, uint32_t count, 
     else
         emu::launch(msc::xpress_apply_indexed_kernel, dim3e(grid), dim3e(32 * msc::LZA_WARPS_PER_BLOCK), (const uint32_t*)tok.data(), (const uint32_t*)seg_ntok.data(),
                     (const int32_t*)seg_status.data(), (const uint32_t*)seg_end.data(), (const msc::XpressSeg*)index, stride, out_off, count, out, out_len, status);
+}
+
+// One plain Xpress stream, flag groups by speculation (kernels/xpress_spec.cuh), as msc_xpress_stream_decode does it.
+// returns 1 = decoded (*total bytes), 0 = left to the serial decoder; info = {blocks, groups, restart entries, stage that gave up}
+uint32_t emu_xpress_stream_decode(const uint8_t* in, uint32_t n, uint8_t* out, uint64_t cap, uint64_t* total, uint32_t* info)
+{
+    using namespace msc;
+    *total = 0; info[0] = info[1] = info[2] = info[3] = 0;
+    if (n < 64) return 0;
+    const uint32_t npos = n - 3, nblk = (npos + XPS_BLK - 1) / XPS_BLK;
+    info[0] = nblk;
+    std::vector<unsigned long long> rec((size_t)npos * 3 + 8), count(nblk + 1), base(nblk + 1);
+    std::vector<uint32_t> table((size_t)nblk * XPS_NENT + 8), entry(nblk + 1), entry_half(nblk + 1);
+    XpsSummary sum;
+    emu::launch(xps_groups_kernel, dim3e(3), dim3e(256), in, n, rec.data());
+    emu::launch(xps_blocks_kernel, dim3e(2), dim3e(XPS_THREADS), (const unsigned long long*)rec.data(), n, nblk, table.data());
+    emu::launch(xps_entries_kernel, dim3e(1), dim3e(32), (const uint32_t*)table.data(), nblk, entry.data(), entry_half.data(), &sum);
+    emu::launch(xps_walk_kernel<false>, dim3e(3), dim3e(32), in, n, (const unsigned long long*)rec.data(), (const uint32_t*)entry.data(),
+                (const uint32_t*)entry_half.data(), (const XpsSummary*)&sum, count.data(), (const unsigned long long*)base.data(), (XpressSeg*)nullptr);
+    emu::launch(xps_scan_kernel, dim3e(1), dim3e(32), (const unsigned long long*)count.data(), base.data(), &sum, (unsigned long long)cap);
+    info[1] = sum.groups; info[2] = sum.nseg;
+    if (!sum.ok || !sum.nseg || sum.bytes > cap || sum.bytes > 0x7FFFFFFFull || !sum.bytes) { info[3] = 1; return 0; }
+    const uint32_t nseg = sum.nseg, produced = (uint32_t)sum.bytes;
+    std::vector<XpressSeg> index(nseg + 1);
+    std::vector<uint32_t> tok((size_t)produced + 64), seg_ntok(nseg + 1), seg_end(nseg + 1), ntok(nseg + 1), pos(nseg + 1);
+    std::vector<int32_t> seg_status(nseg + 1);
+    std::vector<unsigned long long> slot(nseg + 1);
+    uint32_t result[4] = {0, 0, 0, 0};
+    const uint64_t in_off = 0, out_off = 0;
+    const uint32_t in_len = n, out_cap = produced;
+    emu::launch(xps_walk_kernel<true>, dim3e(3), dim3e(32), in, n, (const unsigned long long*)rec.data(), (const uint32_t*)entry.data(),
+                (const uint32_t*)entry_half.data(), (const XpsSummary*)&sum, count.data(), (const unsigned long long*)base.data(), index.data());
+    emu::launch(xpress_parse_indexed_kernel, dim3e(2), dim3e(32 * XPD_WARPS_PER_BLOCK), in, tok.data(), 1u, &in_off, &in_len, &out_off, &out_cap,
+                (const XpressSeg*)index.data(), nseg, seg_ntok.data(), seg_status.data(), seg_end.data());
+    emu::launch(xps_chain_kernel, dim3e(2), dim3e(256), (const XpressSeg*)index.data(), nseg, (const uint32_t*)seg_ntok.data(), (const int32_t*)seg_status.data(),
+                (const uint32_t*)seg_end.data(), slot.data(), ntok.data(), pos.data(), result);
+    if (result[0] != 0 || result[1] != produced) { info[3] = 2; return 0; }
+    std::vector<uint32_t> word((size_t)produced + 1, 0xDEADBEEFu);
+    uint32_t unknown = 0, rounds = 1;
+    while ((1ull << rounds) < produced) ++rounds;
+    emu::launch(lzj_expand_kernel, dim3e(2), dim3e(LZJ_THREADS), (const uint32_t*)tok.data(), (const uint64_t*)slot.data(), (const uint32_t*)ntok.data(),
+                (const uint32_t*)pos.data(), nseg, word.data());
+    for (uint32_t r = 0; r < rounds; ++r) emu::launch(lzj_round_kernel, dim3e(3), dim3e(LZJ_THREADS), word.data(), produced);
+    emu::launch(lzj_store_kernel, dim3e(3), dim3e(LZJ_THREADS), (const uint32_t*)word.data(), out, produced, &unknown);
+    if (unknown) { info[3] = 3; return 0; }
+    *total = produced;
+    return 1;
 }
 
 // Chunk index of an LZNT1 stream, built range by range (range_segs segments at a time) like the pipelined host wrapper does.

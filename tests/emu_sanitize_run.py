@@ -62,4 +62,14 @@ emu.emu_lznt1_index.restype=ctypes.c_int
 assert emu.emu_lznt1_index(ctypes.c_void_p(addr),ctypes.c_uint64(len(c)),ctypes.c_uint32(4112),ctypes.c_uint32(3),emu_util.P(offs),ctypes.c_uint64(len(c)//3+2),emu_util.P(stt))==0
 assert int(stt[0])==1 and int(stt[3])==(len(plains[3])+4095)//4096
 print('heavy chunks + chunk index ok')
+# one plain Xpress stream by speculation (xpress_spec.cuh): groups at every offset, block tables, true chain, restart index, indexed parse, pointer jumping
+emu.emu_xpress_stream_decode.restype=ctypes.c_uint32
+for p in (plains[3],plains[8],plains[13],plains[4]*2):
+    c=ocall('xpress_compress',p,MAX["xpress"](len(p))+16)[1]
+    for comp,cap in ((c,len(p)),(c[:-3],len(p)),(c,len(p)-1)):
+        a,addr=emu_util.padded(comp); out=np.zeros(cap+128,dtype=np.uint8); tot=ctypes.c_uint64(0); info=(ctypes.c_uint32*4)()
+        h=emu.emu_xpress_stream_decode(ctypes.c_void_p(addr),ctypes.c_uint32(len(comp)),ctypes.c_void_p(out.ctypes.data+64),ctypes.c_uint64(cap),ctypes.byref(tot),info)
+        if comp is c and cap==len(p): assert h==1 and out[64:64+tot.value].tobytes()==p
+        else: assert h==0 or (0,out[64:64+tot.value].tobytes())==ocall('xpress_decompress',comp,cap)
+print('xpress speculative stream decode ok')
 print('sanitized run ok')

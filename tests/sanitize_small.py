@@ -82,6 +82,11 @@ for plain in (ms.generate("text", 300000, 11), ms.generate("runs", 400000, 12)):
     st, comp = ms.raw_call("xpress_huff_compress", plain, MAXSZ["xpress_huff"](len(plain)))
     assert st == 0 and ms.raw_call("xpress_huff_decompress", comp, len(plain)) == (0, plain)
     assert ms.raw_call("xpress_huff_decompress", oracle_compress("xpress_huff", plain), len(plain)) == (0, plain)
+# one-shot plain Xpress, ONE stream: flag groups by speculation, restart index, indexed parse, pointer jumping (kernels/xpress_spec.cuh)
+for plain in (ms.generate("text", 300000, 13), ms.generate("runs", 400000, 14) + ms.generate("random", 40000, 15)):
+    comp = oracle_compress("xpress", plain)
+    assert ms.raw_call("xpress_decompress", comp, len(plain)) == (0, plain)
+    assert ms.raw_call("xpress_decompress", comp[:-3], len(plain))[0] != 0
 # Xpress-Huffman with the encoder's restart index
 plains = [ms.generate("text", 140000, 1), ms.generate("runs", 70000, 2), ms.generate("random", 9000, 3)]
 caps = [MAXSZ["xpress_huff"](len(p)) + 16 for p in plains]

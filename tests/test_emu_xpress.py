@@ -326,3 +326,55 @@ def test_xhuff_chunk_parallel_stream_decode(emu, oracle, ms):
     assert taken >= 2
     # a single chunk is not this path's business
     assert _emu_stream_decode(emu, oracle.compress("xpress_huff", ms.generate("text", 50000, 1)), 50000)[0] == 0
+
+
+def _emu_xpress_stream_decode(emu, comp, cap):
+    a, addr = padded(comp)
+    out = np.zeros(cap + 2 * PAD, dtype=np.uint8)
+    total = ctypes.c_uint64(0)
+    info = (ctypes.c_uint32 * 4)()
+    emu.emu_xpress_stream_decode.restype = ctypes.c_uint32
+    handled = emu.emu_xpress_stream_decode(ctypes.c_void_p(addr), ctypes.c_uint32(len(comp)), ctypes.c_void_p(out.ctypes.data + PAD),
+                                           ctypes.c_uint64(cap), ctypes.byref(total), info)
+    return handled, out[PAD:PAD + total.value].tobytes(), list(info)
+
+
+def test_xpress_speculative_stream_decode(emu, oracle, ms):
+    """One plain Xpress stream, flag groups found by speculation (kernels/xpress_spec.cuh): the group that would start at EVERY offset in
+    every half-byte state, the true chain linked up block by block, a restart index from it, the indexed parser and the order-free
+    token execution.  Reference-made streams of all kinds decode bit-exactly; streams the path cannot vouch for are declined
+    (the serial decoder reports those), never decoded wrongly."""
+    rnd = random.Random(11)
+    plains = [ms.generate(kind, n, 3 + n % 7) for kind, n in (("text", 200000), ("runs", 150000), ("random", 70000), ("text", 65537), ("runs", 400000),
+                                                              ("text", 9000), ("text", 300))]
+    plains += [bytes(200000), b"ab" * 100000, ms.generate("text", 3000, 2) * 70, bytes(range(256)) * 1000,
+               bytes(rnd.randrange(4) for _ in range(120000)),                     # many long matches: the shared length nibbles are busy
+               b"".join(bytes([rnd.randrange(256)]) * rnd.choice((1, 2, 9, 10, 11, 24, 25, 26, 300, 70000)) for _ in range(3000))]
+    for plain in plains:
+        n = len(plain)
+        comp = oracle.compress("xpress", plain)
+        handled, got, info = _emu_xpress_stream_decode(emu, comp, n)
+        if len(comp) < 64:
+            assert handled == 0
+            continue
+        assert handled == 1 and got == plain, (n, len(comp), handled, info)
+        assert info[2] == (info[1] + 15) // 16 and info[0] == (len(comp) - 3 + 8191) // 8192
+        assert _emu_xpress_stream_decode(emu, comp, n + 1000)[1] == plain         # more room than needed
+        assert _emu_xpress_stream_decode(emu, comp, n - 1)[0] == 0                 # too little: declined
+        # damaged streams: declined, or exactly what the oracle makes of them
+        for t in (1, 2, 5, len(comp) // 2):
+            cut = comp[:len(comp) - t]
+            h, g, _ = _emu_xpress_stream_decode(emu, cut, n)
+            assert h == 0 or (0, g) == oracle.decompress("xpress", cut, n), (n, t)
+        for _ in range(6):
+            b = bytearray(comp)
+            b[rnd.randrange(len(b))] ^= 1 << rnd.randrange(8)
+            h, g, _ = _emu_xpress_stream_decode(emu, bytes(b), n)
+            assert h == 0 or (0, g) == oracle.decompress("xpress", bytes(b), n), n
+    # streams of this library's own encoders decode the same way
+    for name, extra in (("emu_xpress_encode", ()), ("emu_xpress_encode_exact", (ctypes.c_uint32(16384), ctypes.c_void_p(0), ctypes.c_uint32(0)))):
+        plain = ms.generate("text", 150000, 5)
+        st, ol, outs = emu_batch(emu, name, [plain], [MAXSZ["xpress"](len(plain))], extra=extra)
+        assert not st.any()
+        handled, got, _ = _emu_xpress_stream_decode(emu, outs[0], len(plain))
+        assert handled == 1 and got == plain

@@ -382,3 +382,34 @@ def test_xhuff_one_shot_multichunk_streams(ms, oracle):
             exp = oracle.decompress("xpress_huff", comp, cap)
             got = ms.raw_call("xpress_huff_decompress", comp, cap)
             assert got[0] == exp[0] and (exp[0] != 0 or got[1] == exp[1]), (kind, n, cap, got[0], exp[0])
+
+
+@pytest.mark.gpu
+def test_xpress_one_shot_single_stream(ms, oracle):
+    """xpress_decompress on ONE stream of some size takes the speculative path (kernels/xpress_spec.cuh: the flag group that would
+    start at every offset, the true chain linked up, a restart index from it, indexed parse + order-free token execution):
+    reference-made streams of every kind, streams made here, and everything that path must leave to the serial decoder -- too little
+    room, damage, truncation, trailing bytes -- with the oracle's status."""
+    rnd = random.Random(7)
+    plains = [ms.generate(kind, n, 3 + n % 7) for kind, n in (("text", 1 << 23), ("text", 300001), ("runs", 1 << 22), ("random", 200000), ("text", 90000))]
+    plains += [bytes(rnd.randrange(4) for _ in range(300000)),                       # long matches everywhere: busy length nibbles
+               b"".join(bytes([rnd.randrange(256)]) * rnd.choice((1, 2, 9, 10, 11, 24, 25, 26, 300, 70000)) for _ in range(20000))]
+    for plain in plains:
+        n = len(plain)
+        ref = oracle.compress("xpress", plain)
+        assert ms.raw_call("xpress_decompress", ref, n) == (0, plain), n
+        assert ms.raw_call("xpress_decompress", ref, n + 1000) == (0, plain), n
+        st, mine = ms.raw_call("xpress_compress", plain, MAXSZ["xpress"](n))
+        assert st == 0 and mine == ref and ms.raw_call("xpress_decompress", mine, n) == (0, plain), n
+        if n > 400000 or len(ref) < 32768:
+            continue
+        cases = [(ref, n - 1), (ref, n // 2), (ref, 0), (ref[:-1], n), (ref[:-2], n), (ref[:len(ref) // 2], n), (ref + bytes(2), n + 10), (ref + b"U", n + 10)]
+        for _ in range(25):
+            b = bytearray(ref)
+            for _ in range(rnd.randint(1, 3)):
+                b[rnd.randrange(len(b))] ^= 1 << rnd.randrange(8)
+            cases.append((bytes(b), n + rnd.choice((0, 64))))
+        for comp, cap in cases:
+            exp = oracle.decompress("xpress", comp, cap)
+            got = ms.raw_call("xpress_decompress", comp, cap)
+            assert got[0] == exp[0] and (exp[0] != 0 or got[1] == exp[1]), (n, cap, got[0], exp[0])
