@@ -488,6 +488,40 @@ def measure_mixed(ms, ctx, torch, dist, dev, rank, world, count, each, steps):
             "streams": "one CUDA stream per format group (3), bracketed by events on the main stream"}
 
 
+def measure_oneshot(ms, mib=8, reps=3):
+    """The drop-in calls on ONE buffer in ordinary (pageable) host memory -- what a user of the reference's library hits first:
+    <fmt>_compress / <fmt>_decompress of one `mib` MiB text buffer, best of `reps`, only the C call inside the timer (buffers are
+    allocated and touched before).  The default encoders are byte-identical to the reference's, so the decoders are timed on
+    reference-made streams."""
+    import numpy as np
+    n = mib << 20
+    plain = np.frombuffer(ms.generate("text", n, 42), dtype=np.uint8).copy()
+    L = ms.lib()
+    out = {"what": "one %d MiB text buffer per call, pageable host memory, C ABI one-shot calls, best of %d; MB/s of uncompressed bytes" % (mib, reps)}
+    for fmt, cap in (("lznt1", n + 3 + 2 * ((n + 4095) // 4096)), ("xpress", n + 4 + 4 * (n // 32)), ("xpress_huff", n + 34 + 258 + 258 * (n // 65536))):
+        comp = np.zeros(cap + 64, dtype=np.uint8)
+        back = np.zeros(n + 64, dtype=np.uint8)
+        tc, td = [], []
+        clen = 0
+        for _ in range(reps):
+            m = ctypes.c_size_t(cap)
+            t0 = time.perf_counter()
+            st = getattr(L, fmt + "_compress")(ctypes.c_void_p(plain.ctypes.data), ctypes.c_size_t(n), ctypes.c_void_p(comp.ctypes.data), ctypes.byref(m))
+            t1 = time.perf_counter()
+            assert st == 0, (fmt, st)
+            clen = m.value
+            k = ctypes.c_size_t(n)
+            t2 = time.perf_counter()
+            st = getattr(L, fmt + "_decompress")(ctypes.c_void_p(comp.ctypes.data), ctypes.c_size_t(clen), ctypes.c_void_p(back.ctypes.data), ctypes.byref(k))
+            t3 = time.perf_counter()
+            assert st == 0 and k.value == n, (fmt, st, k.value)
+            tc.append(t1 - t0); td.append(t3 - t2)
+        assert bytes(back[:n]) == bytes(plain), fmt + " one-shot round trip"
+        out[fmt] = {"compress_ms": 1e3 * min(tc), "decompress_ms": 1e3 * min(td), "compress_MBps": n / MB / min(tc), "decompress_MBps": n / MB / min(td),
+                    "compressed_ratio": clen / n}
+    return out
+
+
 def run_gpu(args):
     import numpy as np
     import torch
@@ -683,6 +717,15 @@ def run_gpu(args):
         for f, c in cpu_fmt.items():
             line["formats"][f]["cpu_baseline"] = c
             line["formats"][f]["vs_cpu_all_cores"] = line["formats"][f]["encode_decode_MBps"] / c["value"]
+    if world == 1:
+        one = measure_oneshot(ms)
+        ref1 = {"lznt1": (cpu or {}).get("one_core")}
+        for f, c in (cpu_fmt or {}).items():
+            ref1[f] = c.get("one_core")
+        for f, r in ref1.items():
+            if r and f in one:
+                one[f]["reference_one_core"] = {"compress_MBps": r.get("compress_MBps"), "decompress_MBps": r.get("decompress_MBps")}
+        line["oneshot"] = one
     emit(line)
     if dist is not None:
         dist.destroy_process_group()

@@ -12,6 +12,7 @@
 #include "kernels/xhuff_index.cuh"
 #include "kernels/xhuff_decode_indexed.cuh"
 #include "kernels/xhuff_chunks.cuh"
+#include "kernels/xhuff_chunk_warp.cuh"
 #include "kernels/lz_jump.cuh"
 #include "kernels/xpress_decode.cuh"
 #include "kernels/xhuff_encode.cuh"
@@ -618,7 +619,7 @@ static bool produce_by_jumping(mscomp_gpu_ctx* ctx, const uint32_t* d_tok, const
 MSCompStatus msc_xhuff_stream_decode(mscomp_gpu_ctx* ctx, const uint8_t* d_in, uint32_t in_len, uint8_t* d_out, uint64_t cap, uint64_t* total, bool* handled)
 {
     *handled = false;
-    if (!ctx || in_len < 2 * (uint32_t)XH_MIN_DATA) return MSCOMP_OK;
+    if (!ctx || in_len < (uint32_t)XH_MIN_DATA + 2) return MSCOMP_OK;
     cudaSetDevice(ctx->device);
     // 1. candidate chunk starts
     const uint32_t capc = in_len / (uint32_t)XH_MIN_DATA + 2;
@@ -631,7 +632,7 @@ MSCompStatus msc_xhuff_stream_decode(mscomp_gpu_ctx* ctx, const uint8_t* d_in, u
     cudaMemcpyAsync(h_small + 32, d_cand + capc, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cudaGetLastError(); return MSCOMP_OK; }
     const uint32_t ncand = h_small[32];
-    if (ncand < 2 || ncand > capc) return MSCOMP_OK;
+    if (ncand < 1 || ncand > capc) return MSCOMP_OK;
     std::vector<uint32_t> cand(ncand);
     cudaMemcpyAsync(cand.data(), d_cand, (size_t)ncand * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cudaGetLastError(); return MSCOMP_OK; }
@@ -639,9 +640,12 @@ MSCompStatus msc_xhuff_stream_decode(mscomp_gpu_ctx* ctx, const uint8_t* d_in, u
     if (cand[0] != 0) return MSCOMP_OK;
     // 2. one lane per candidate parses one chunk into tokens.  A lone lane is latency-bound, so the candidates are spread over as
     //    many warps as the GPU holds (stride - 1 empty streams between two of them) instead of being packed 32 to a warp.
+    // MSCOMP_XHUFF_CHUNK_PARSE=lane: the batch parser in speculative mode, one lane per candidate; default: a warp per candidate
+    // (kernels/xhuff_chunk_warp.cuh: shared lookup table, lane 0 walks the symbols -- 5x fewer dependent instructions per symbol)
+    static const bool lane_parse = getenv("MSCOMP_XHUFF_CHUNK_PARSE") && strcmp(getenv("MSCOMP_XHUFF_CHUNK_PARSE"), "lane") == 0;
     const uint32_t warps_avail = (uint32_t)ctx->sm_count * 2 * XHD_WARPS_PER_BLOCK;
     uint32_t per_warp = (ncand + warps_avail - 1) / warps_avail;
-    uint32_t stride = 32;
+    uint32_t stride = lane_parse ? 32 : 1;
     while (stride > 1 && 32 / stride < per_warp) stride >>= 1;
     const uint64_t count64 = (uint64_t)ncand * stride;
     const uint64_t tok_bytes = (uint64_t)ncand * XH_CHUNK * sizeof(uint32_t);
@@ -671,11 +675,19 @@ MSCompStatus msc_xhuff_stream_decode(mscomp_gpu_ctx* ctx, const uint8_t* d_in, u
     cudaMemcpyAsync(d_desc, h_desc, desc_bytes, cudaMemcpyHostToDevice, ctx->stream);
     const uint64_t* d_in_off = (const uint64_t*)d_desc; const uint64_t* d_out_off = d_in_off + count;
     uint32_t* d_u32 = (uint32_t*)(d_out_off + count);
-    MSC_OPT_IN_SMEM(xhuff_parse_chunks_kernel, XHD_SMEM_BYTES);
-    MSC_LAUNCH_SMEM(ctx, xhuff_parse_chunks_kernel, xhd_grid(ctx, count), 32 * XHD_WARPS_PER_BLOCK, XHD_SMEM_BYTES,
-                    d_in, d_tok, count, d_in_off, (const uint32_t*)d_u32, d_out_off, (const uint32_t*)(d_u32 + count),
-                    d_u32 + 2 * (size_t)count, (int32_t*)(d_u32 + 3 * (size_t)count), d_u32 + 4 * (size_t)count, d_u32 + 5 * (size_t)count,
-                    d_u32 + 6 * (size_t)count);
+    if (lane_parse) {
+        MSC_OPT_IN_SMEM(xhuff_parse_chunks_kernel, XHD_SMEM_BYTES);
+        MSC_LAUNCH_SMEM(ctx, xhuff_parse_chunks_kernel, xhd_grid(ctx, count), 32 * XHD_WARPS_PER_BLOCK, XHD_SMEM_BYTES,
+                        d_in, d_tok, count, d_in_off, (const uint32_t*)d_u32, d_out_off, (const uint32_t*)(d_u32 + count),
+                        d_u32 + 2 * (size_t)count, (int32_t*)(d_u32 + 3 * (size_t)count), d_u32 + 4 * (size_t)count, d_u32 + 5 * (size_t)count,
+                        d_u32 + 6 * (size_t)count);
+    } else {
+        const uint32_t wb = (count + XHW_WARPS_PER_BLOCK - 1) / XHW_WARPS_PER_BLOCK, wcap = (uint32_t)ctx->sm_count * 16;
+        MSC_LAUNCH(ctx, xhuff_parse_chunks_warp_kernel, wb < wcap ? wb : wcap, 32 * XHW_WARPS_PER_BLOCK,
+                   d_in, d_tok, count, d_in_off, (const uint32_t*)d_u32, d_out_off, (const uint32_t*)(d_u32 + count),
+                   d_u32 + 2 * (size_t)count, (int32_t*)(d_u32 + 3 * (size_t)count), d_u32 + 4 * (size_t)count, d_u32 + 5 * (size_t)count,
+                   d_u32 + 6 * (size_t)count);
+    }
     cudaMemcpyAsync(h_out_len, d_u32 + 2 * (size_t)count, (size_t)count * 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cudaGetLastError(); return MSCOMP_OK; }
     // 3. stitch the chain from offset 0

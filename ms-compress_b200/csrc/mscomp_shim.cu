@@ -491,7 +491,7 @@ extern "C" MSCompStatus xpress_huff_decompress(const_bytes in, size_t in_len, by
     // chunk-parallel path: candidate chunk starts are recognised by their complete code-length tables and parsed side by side
     // (kernels/xhuff_chunks.cuh); whatever it cannot vouch for goes to the serial decoder below, which owns the status codes.
     static const bool no_spec = getenv("MSCOMP_XHUFF_ONESHOT") && strcmp(getenv("MSCOMP_XHUFF_ONESHOT"), "serial") == 0;
-    if (!no_spec && in_len >= 32768 && in_len <= 0xFFFFFF00ull) {
+    if (!no_spec && in_len >= 2048 && in_len <= 0xFFFFFF00ull) {             // (below that the serial decoder's one lane is as quick)
         mscomp_gpu_ctx* ctx = msc_thread_ctx();
         if (!ctx) return MSCOMP_MEM_ERROR;
         const size_t cap = *out_len > 0xFFFFFF00ull ? (size_t)0xFFFFFF00ull : *out_len;

@@ -9,6 +9,7 @@
 #include "../../ms-compress_b200/csrc/kernels/xhuff_index.cuh"
 #include "../../ms-compress_b200/csrc/kernels/xhuff_decode_indexed.cuh"
 #include "../../ms-compress_b200/csrc/kernels/xhuff_chunks.cuh"
+#include "../../ms-compress_b200/csrc/kernels/xhuff_chunk_warp.cuh"
 #include "../../ms-compress_b200/csrc/kernels/lz_jump.cuh"
 #include "../../ms-compress_b200/csrc/kernels/xpress_decode.cuh"
 #include "../../ms-compress_b200/csrc/kernels/xhuff_encode.cuh"
@@ -198,16 +199,18 @@ void emu_xhuff_decode_indexed(const uint8_t* in, uint8_t* out, uint32_t count, c
 // bytes in out), 0 when the path declines; *info = candidates | chunks << 16 | (1 << 31 if the chunks ran independently).
 static int g_chain_in_order = 0;
 void emu_xhuff_stream_in_order(int on) { g_chain_in_order = on; }
+static int g_chunk_lane_parse = 0;                                  // 1: the batch parser, one lane per candidate; 0: a warp per candidate (the default)
+void emu_xhuff_stream_lane_parse(int on) { g_chunk_lane_parse = on; }
 uint32_t emu_xhuff_stream_decode(const uint8_t* in, uint32_t n, uint8_t* out, uint64_t cap, uint64_t* total, uint32_t* info)
 {
     using namespace msc;
     *total = 0; *info = 0;
-    if (n < 2u * XH_MIN_DATA) return 0;
+    if (n < XH_MIN_DATA + 2u) return 0;
     const uint32_t capc = n / XH_MIN_DATA + 2;
     std::vector<uint32_t> cand(capc + 2, 0);
     uint32_t ncand = 0;
     emu::launch(xhs_candidates_kernel, dim3e(3), dim3e(XHS_THREADS), in, n, cand.data(), &ncand, capc);
-    if (ncand < 2 || ncand > capc) return 0;
+    if (ncand < 1 || ncand > capc) return 0;
     cand.resize(ncand);
     std::sort(cand.begin(), cand.end());
     *info = ncand;
@@ -218,9 +221,14 @@ uint32_t emu_xhuff_stream_decode(const uint8_t* in, uint32_t n, uint8_t* out, ui
     std::vector<int32_t> status(count);
     for (uint32_t k = 0; k < count; ++k) { in_off[k] = cand[k]; in_len[k] = n - cand[k]; out_off[k] = (uint64_t)k * XH_CHUNK; }
     std::vector<uint32_t> tok((size_t)count * XH_CHUNK + 16);
-    emu::launch(xhuff_parse_chunks_kernel, dim3e(2), dim3e(32 * XHD_WARPS_PER_BLOCK), in, tok.data(), count, (const uint64_t*)in_off.data(),
-                (const uint32_t*)in_len.data(), (const uint64_t*)out_off.data(), (const uint32_t*)out_cap.data(), out_len.data(), status.data(),
-                ntok.data(), end_ip.data(), reach.data());
+    if (g_chunk_lane_parse)
+        emu::launch(xhuff_parse_chunks_kernel, dim3e(2), dim3e(32 * XHD_WARPS_PER_BLOCK), in, tok.data(), count, (const uint64_t*)in_off.data(),
+                    (const uint32_t*)in_len.data(), (const uint64_t*)out_off.data(), (const uint32_t*)out_cap.data(), out_len.data(), status.data(),
+                    ntok.data(), end_ip.data(), reach.data());
+    else
+        emu::launch(xhuff_parse_chunks_warp_kernel, dim3e(2), dim3e(32 * XHW_WARPS_PER_BLOCK), in, tok.data(), count, (const uint64_t*)in_off.data(),
+                    (const uint32_t*)in_len.data(), (const uint64_t*)out_off.data(), (const uint32_t*)out_cap.data(), out_len.data(), status.data(),
+                    ntok.data(), end_ip.data(), reach.data());
     std::vector<uint32_t> chain, pos;
     uint64_t produced = 0;
     uint32_t at = 0;

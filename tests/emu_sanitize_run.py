@@ -72,4 +72,14 @@ for p in (plains[3],plains[8],plains[13],plains[4]*2):
         if comp is c and cap==len(p): assert h==1 and out[64:64+tot.value].tobytes()==p
         else: assert h==0 or (0,out[64:64+tot.value].tobytes())==ocall('xpress_decompress',comp,cap)
 print('xpress speculative stream decode ok')
+# one Xpress-Huffman stream: candidates, a warp per chunk (xhuff_chunk_warp.cuh), pointer jumping -- multi-chunk and single-chunk, whole and truncated
+emu.emu_xhuff_stream_decode.restype=ctypes.c_uint32
+for p in (plains[4],plains[3],plains[9],plains[12]):
+    c=ocall('xpress_huff_compress',p,MAX["xpress_huff"](len(p))+16)[1]
+    for comp,cap in ((c,len(p)),(c[:-3],len(p)),(c,len(p)-1)):
+        a,addr=emu_util.padded(comp); out=np.zeros(cap+128,dtype=np.uint8); tot=ctypes.c_uint64(0); info=ctypes.c_uint32(0)
+        h=emu.emu_xhuff_stream_decode(ctypes.c_void_p(addr),ctypes.c_uint32(len(comp)),ctypes.c_void_p(out.ctypes.data+64),ctypes.c_uint64(cap),ctypes.byref(tot),ctypes.byref(info))
+        if comp is c and cap==len(p): assert h==1 and out[64:64+tot.value].tobytes()==p
+        else: assert h==0 or (0,out[64:64+tot.value].tobytes())==ocall('xpress_huff_decompress',comp,cap)
+print('xpress-huffman chunk-parallel stream decode ok')
 print('sanitized run ok')

@@ -300,10 +300,11 @@ def test_xhuff_chunk_parallel_stream_decode(emu, oracle, ms):
     for kind, n in (("text", 200000), ("text", 65536 * 3), ("runs", 150000), ("random", 140000), ("text", 65537), ("runs", 400000)):
         plain = ms.generate(kind, n, 7 + n % 5)
         comp = oracle.compress("xpress_huff", plain)
-        for in_order in (1, 0):                                      # the in-order block executor, then pointer jumping (lz_jump.cuh, the default)
-            emu.emu_xhuff_stream_in_order(in_order)
+        for in_order, lane_parse in ((1, 1), (0, 1), (1, 0), (0, 0)):  # the in-order block executor / pointer jumping (lz_jump.cuh, the default);
+            emu.emu_xhuff_stream_in_order(in_order)                  # the batch parser one lane per chunk / a warp per chunk (xhuff_chunk_warp.cuh, the default)
+            emu.emu_xhuff_stream_lane_parse(lane_parse)
             handled, got, info = _emu_stream_decode(emu, comp, n)
-            assert handled == 1 and got == plain, (kind, n, handled, info, in_order)
+            assert handled == 1 and got == plain, (kind, n, handled, info, in_order, lane_parse)
             assert (info >> 16) & 0x7FFF == (n + 65535) // 65536
         # our own encoder: window reset per chunk -> independent chunks
         st, ol, outs = emu_batch(emu, "emu_xhuff_encode", [plain], [len(plain) + 34 + 258 + 258 * (len(plain) // 65536) + 16])
@@ -324,8 +325,16 @@ def test_xhuff_chunk_parallel_stream_decode(emu, oracle, ms):
         assert handled == 0 or got == plain, (len(plain), info)      # (a chunk that uses ONE symbol has an incomplete code: declined)
         taken += handled
     assert taken >= 2
-    # a single chunk is not this path's business
-    assert _emu_stream_decode(emu, oracle.compress("xpress_huff", ms.generate("text", 50000, 1)), 50000)[0] == 0
+    # a single chunk takes the same path (one warp walks it)
+    for kind, n in (("text", 50000), ("text", 65536), ("runs", 30000), ("random", 3000), ("text", 700)):
+        plain = ms.generate(kind, n, 1)
+        comp = oracle.compress("xpress_huff", plain)
+        handled, got, info = _emu_stream_decode(emu, comp, n)
+        assert handled == 1 and got == plain, (kind, n, info)
+        assert _emu_stream_decode(emu, comp, n - 1)[0] == 0
+        for t in (1, 2, 7):
+            h, g, _ = _emu_stream_decode(emu, comp[:len(comp) - t], n)
+            assert h == 0 or (0, g) == oracle.decompress("xpress_huff", comp[:len(comp) - t], n), (kind, n, t)
 
 
 def _emu_xpress_stream_decode(emu, comp, cap):
