@@ -760,7 +760,7 @@ MSCompStatus msc_xhuff_stream_decode(mscomp_gpu_ctx* ctx, const uint8_t* d_in, u
 MSCompStatus msc_xpress_stream_decode(mscomp_gpu_ctx* ctx, const uint8_t* d_in, uint32_t in_len, uint8_t* d_out, uint64_t cap, uint64_t* total, bool* handled)
 {
     *handled = false;
-    if (!ctx || in_len < 64 || in_len > (1u << 30)) return MSCOMP_OK;
+    if (!ctx || in_len < 64 || in_len > (1u << 28)) return MSCOMP_OK;              // (24 bytes of records per stream byte stay with the context)
     cudaSetDevice(ctx->device);
     const uint32_t npos = in_len - 3;
     const uint32_t nblk = (npos + XPS_BLK - 1) / XPS_BLK;

@@ -461,7 +461,7 @@ extern "C" MSCompStatus xpress_decompress(const_bytes in, size_t in_len, bytes o
     // and become a restart index (kernels/xpress_spec.cuh); whatever it cannot vouch for goes to the serial decoder below, which owns
     // the status codes.  MSCOMP_XPRESS_ONESHOT=serial forces that one.
     static const bool no_spec = getenv("MSCOMP_XPRESS_ONESHOT") && strcmp(getenv("MSCOMP_XPRESS_ONESHOT"), "serial") == 0;
-    if (!no_spec && in_len >= 32768 && in_len <= (1u << 30) && *out_len) {
+    if (!no_spec && in_len >= 32768 && in_len <= (1u << 28) && *out_len) {
         mscomp_gpu_ctx* ctx = msc_thread_ctx();
         if (!ctx) return MSCOMP_MEM_ERROR;
         const size_t cap = *out_len > 0x7FFFFFFFull ? (size_t)0x7FFFFFFFull : *out_len;
