@@ -643,6 +643,7 @@ MSCompStatus msc_xhuff_stream_decode(mscomp_gpu_ctx* ctx, const uint8_t* d_in, u
     // MSCOMP_XHUFF_CHUNK_PARSE=lane: the batch parser in speculative mode, one lane per candidate; default: a warp per candidate
     // (kernels/xhuff_chunk_warp.cuh: shared lookup table, lane 0 walks the symbols -- 5x fewer dependent instructions per symbol)
     static const bool lane_parse = getenv("MSCOMP_XHUFF_CHUNK_PARSE") && strcmp(getenv("MSCOMP_XHUFF_CHUNK_PARSE"), "lane") == 0;
+    static const bool serial_parse = getenv("MSCOMP_XHUFF_CHUNK_PARSE") && strcmp(getenv("MSCOMP_XHUFF_CHUNK_PARSE"), "serial") == 0;   // lane 0 of the warp walks every symbol
     const uint32_t warps_avail = (uint32_t)ctx->sm_count * 2 * XHD_WARPS_PER_BLOCK;
     uint32_t per_warp = (ncand + warps_avail - 1) / warps_avail;
     uint32_t stride = lane_parse ? 32 : 1;
@@ -683,10 +684,16 @@ MSCompStatus msc_xhuff_stream_decode(mscomp_gpu_ctx* ctx, const uint8_t* d_in, u
                         d_u32 + 6 * (size_t)count);
     } else {
         const uint32_t wb = (count + XHW_WARPS_PER_BLOCK - 1) / XHW_WARPS_PER_BLOCK, wcap = (uint32_t)ctx->sm_count * 16;
-        MSC_LAUNCH(ctx, xhuff_parse_chunks_warp_kernel, wb < wcap ? wb : wcap, 32 * XHW_WARPS_PER_BLOCK,
-                   d_in, d_tok, count, d_in_off, (const uint32_t*)d_u32, d_out_off, (const uint32_t*)(d_u32 + count),
-                   d_u32 + 2 * (size_t)count, (int32_t*)(d_u32 + 3 * (size_t)count), d_u32 + 4 * (size_t)count, d_u32 + 5 * (size_t)count,
-                   d_u32 + 6 * (size_t)count);
+        if (serial_parse)
+            MSC_LAUNCH(ctx, xhuff_parse_chunks_warp_serial_kernel, wb < wcap ? wb : wcap, 32 * XHW_WARPS_PER_BLOCK,
+                       d_in, d_tok, count, d_in_off, (const uint32_t*)d_u32, d_out_off, (const uint32_t*)(d_u32 + count),
+                       d_u32 + 2 * (size_t)count, (int32_t*)(d_u32 + 3 * (size_t)count), d_u32 + 4 * (size_t)count, d_u32 + 5 * (size_t)count,
+                       d_u32 + 6 * (size_t)count);
+        else
+            MSC_LAUNCH(ctx, xhuff_parse_chunks_warp_kernel, wb < wcap ? wb : wcap, 32 * XHW_WARPS_PER_BLOCK,
+                       d_in, d_tok, count, d_in_off, (const uint32_t*)d_u32, d_out_off, (const uint32_t*)(d_u32 + count),
+                       d_u32 + 2 * (size_t)count, (int32_t*)(d_u32 + 3 * (size_t)count), d_u32 + 4 * (size_t)count, d_u32 + 5 * (size_t)count,
+                       d_u32 + 6 * (size_t)count);
     }
     cudaMemcpyAsync(h_out_len, d_u32 + 2 * (size_t)count, (size_t)count * 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cudaGetLastError(); return MSCOMP_OK; }

@@ -199,8 +199,9 @@ void emu_xhuff_decode_indexed(const uint8_t* in, uint8_t* out, uint32_t count, c
 // bytes in out), 0 when the path declines; *info = candidates | chunks << 16 | (1 << 31 if the chunks ran independently).
 static int g_chain_in_order = 0;
 void emu_xhuff_stream_in_order(int on) { g_chain_in_order = on; }
-static int g_chunk_lane_parse = 0;                                  // 1: the batch parser, one lane per candidate; 0: a warp per candidate (the default)
+static int g_chunk_lane_parse = 0;                                  // 1: the batch parser, one lane per candidate; 2: a warp per candidate, lane 0 walks; 0: a warp per candidate, speculative rounds (the default)
 void emu_xhuff_stream_lane_parse(int on) { g_chunk_lane_parse = on; }
+void emu_xhuff_chunk_warp_counts(uint64_t* out) { out[0] = msc::g_xhw_round_syms; out[1] = msc::g_xhw_serial_syms; msc::g_xhw_round_syms = msc::g_xhw_serial_syms = 0; }
 uint32_t emu_xhuff_stream_decode(const uint8_t* in, uint32_t n, uint8_t* out, uint64_t cap, uint64_t* total, uint32_t* info)
 {
     using namespace msc;
@@ -221,7 +222,11 @@ uint32_t emu_xhuff_stream_decode(const uint8_t* in, uint32_t n, uint8_t* out, ui
     std::vector<int32_t> status(count);
     for (uint32_t k = 0; k < count; ++k) { in_off[k] = cand[k]; in_len[k] = n - cand[k]; out_off[k] = (uint64_t)k * XH_CHUNK; }
     std::vector<uint32_t> tok((size_t)count * XH_CHUNK + 16);
-    if (g_chunk_lane_parse)
+    if (g_chunk_lane_parse == 2)
+        emu::launch(xhuff_parse_chunks_warp_serial_kernel, dim3e(2), dim3e(32 * XHW_WARPS_PER_BLOCK), in, tok.data(), count, (const uint64_t*)in_off.data(),
+                    (const uint32_t*)in_len.data(), (const uint64_t*)out_off.data(), (const uint32_t*)out_cap.data(), out_len.data(), status.data(),
+                    ntok.data(), end_ip.data(), reach.data());
+    else if (g_chunk_lane_parse)
         emu::launch(xhuff_parse_chunks_kernel, dim3e(2), dim3e(32 * XHD_WARPS_PER_BLOCK), in, tok.data(), count, (const uint64_t*)in_off.data(),
                     (const uint32_t*)in_len.data(), (const uint64_t*)out_off.data(), (const uint32_t*)out_cap.data(), out_len.data(), status.data(),
                     ntok.data(), end_ip.data(), reach.data());

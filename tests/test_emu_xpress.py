@@ -300,8 +300,8 @@ def test_xhuff_chunk_parallel_stream_decode(emu, oracle, ms):
     for kind, n in (("text", 200000), ("text", 65536 * 3), ("runs", 150000), ("random", 140000), ("text", 65537), ("runs", 400000)):
         plain = ms.generate(kind, n, 7 + n % 5)
         comp = oracle.compress("xpress_huff", plain)
-        for in_order, lane_parse in ((1, 1), (0, 1), (1, 0), (0, 0)):  # the in-order block executor / pointer jumping (lz_jump.cuh, the default);
-            emu.emu_xhuff_stream_in_order(in_order)                  # the batch parser one lane per chunk / a warp per chunk (xhuff_chunk_warp.cuh, the default)
+        for in_order, lane_parse in ((1, 1), (0, 1), (0, 2), (1, 0), (0, 0)):  # the in-order block executor / pointer jumping (lz_jump.cuh, the default);
+            emu.emu_xhuff_stream_in_order(in_order)                  # the batch parser one lane per chunk (1) / a warp per chunk, lane 0 walks (2) / speculative rounds (0, the default)
             emu.emu_xhuff_stream_lane_parse(lane_parse)
             handled, got, info = _emu_stream_decode(emu, comp, n)
             assert handled == 1 and got == plain, (kind, n, handled, info, in_order, lane_parse)
@@ -325,6 +325,13 @@ def test_xhuff_chunk_parallel_stream_decode(emu, oracle, ms):
         assert handled == 0 or got == plain, (len(plain), info)      # (a chunk that uses ONE symbol has an incomplete code: declined)
         taken += handled
     assert taken >= 2
+    # the speculative rounds carry the load: on text nearly every symbol is taken by a round, the serial routine only sees length escapes and chunk ends
+    cnt = (ctypes.c_uint64 * 2)()
+    emu.emu_xhuff_chunk_warp_counts(cnt)
+    plain = ms.generate("text", 200000, 3)
+    assert _emu_stream_decode(emu, oracle.compress("xpress_huff", plain), len(plain))[1] == plain
+    emu.emu_xhuff_chunk_warp_counts(cnt)
+    assert cnt[0] > 20 * cnt[1] and cnt[0] > 30000, list(cnt)
     # a single chunk takes the same path (one warp walks it)
     for kind, n in (("text", 50000), ("text", 65536), ("runs", 30000), ("random", 3000), ("text", 700)):
         plain = ms.generate(kind, n, 1)
