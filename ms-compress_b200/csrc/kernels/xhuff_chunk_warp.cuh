@@ -11,8 +11,9 @@
 //   * PAR = true (the default): the warp decodes by speculation on the start bit.  The reader's state between two symbols is
 //     (window, valid bits, cursor) (Bitstream.h:34-44), and as long as no raw length byte is read the bits to come are simply the
 //     window followed by the 16-bit words at the cursor.  So lane j decodes the symbol that WOULD start j bits ahead (code, offset
-//     bits -- up to 30 bits from a 96-bit look-ahead every lane holds), the true chain 0 -> adv(0) -> ... is followed with one
-//     shuffle per symbol, its lanes write their tokens (positions by a warp scan), and the reader state after the last one follows
+//     bits -- up to 30 bits of the look-ahead every lane holds), the true chain 0 -> adv(0) -> ... is followed with one shuffle
+//     per symbol (which also carries the length: the output positions add up along the way), its lanes write their tokens, and
+//     the reader state after the last one follows
 //     from the number of bits consumed: a refill happens whenever fewer than 16 bits are left (Bitstream.h:59-70), so with b = valid
 //     bits - consumed, k = the refills that bring b back into [16, 31]: valid bits = b + 16 k, cursor += 2 k.  ≈ 4 symbols per round.
 //     Anything that is not plain -- a length escape (raw bytes move the cursor), an invalid code, the end of the chunk or of the
@@ -116,16 +117,19 @@ __device__ __forceinline__ void xhuff_parse_chunks_warp_body(const uint8_t* __re
                 }
                 uint32_t taken = 0;                                              // symbols of this round's chain
                 if (R.ip + 16u <= n && R.bits >= 16u && S.opos < XH_CHUNK) {
-                    // ---- a speculative round: 96 bits of look-ahead = the window + the four words at the cursor ----
+                    // ---- a speculative round.  The bits to come: the window's valid bits, then the four words at the cursor (P).
+                    // V0 = bits [0, 64) of that string, V1 = bits [32, 96): a lane needs at most 30 bits from an offset below 32,
+                    // the reader's next window at most 31 bits from an offset below 62. ----
                     const uint32_t d = R.ip - R.slot_ip;
-                    unsigned __int128 W = (unsigned __int128)R.mask << 96;
+                    unsigned long long P = 0;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint32_t w = (uint32_t)R.slot[d + 2 * k] | ((uint32_t)R.slot[d + 2 * k + 1] << 8);
-                        W |= (unsigned __int128)w << (112u - R.bits - 16u * (uint32_t)k);     // its first bit right behind the window's valid bits
-                    }
+                    for (int k = 0; k < 4; ++k)
+                        P |= (unsigned long long)((uint32_t)R.slot[d + 2 * k] | ((uint32_t)R.slot[d + 2 * k + 1] << 8)) << (48 - 16 * k);
+                    const unsigned long long V0 = ((unsigned long long)R.mask << 32) | (P >> R.bits);                 // (bits in 16..32)
+                    const unsigned long long V1 = (V0 << 32) | (unsigned long long)(uint32_t)((P << (64u - R.bits)) >> 32);
                     // lane j: the symbol that would start j bits ahead
-                    const uint32_t x = (uint32_t)(W >> (113u - (uint32_t)lane)) & 0x7FFFu;      // 15 bits from offset j
+                    const unsigned long long Vj = V0 << lane;
+                    const uint32_t x = (uint32_t)(Vj >> 49);                     // 15 bits
                     const uint32_t e = sm.lut[x >> (15 - XHX_LUT_BITS)];
                     uint32_t nb = (e >> 9) & 15u, sym = e & 511u;
                     bool stop = (e & 0x8000u) != 0;
@@ -138,30 +142,23 @@ __device__ __forceinline__ void xhuff_parse_chunks_warp_body(const uint8_t* __re
                     const bool is_match = sym >= 256u;
                     stop |= is_match && (sym & 15u) == 15u;                      // a length escape: raw bytes at the cursor, lane 0's business
                     const uint32_t ob = is_match ? (sym >> 4) & 15u : 0u;
-                    const uint32_t obits = (uint32_t)(W >> (128u - (uint32_t)lane - nb - ob)) & ((1u << ob) - 1u);
+                    const uint32_t obits = (uint32_t)((Vj << nb) >> 49) >> (15u - ob);              // the ob bits behind the code
                     const uint32_t off = is_match ? obits + (1u << ob) : 0u;
                     const uint32_t len = is_match ? (sym & 15u) + 3u : 1u;
-                    const uint32_t adv = nb + ob;
-                    // the true chain from bit 0
-                    uint32_t M = 0, cur = 0;
+                    // the true chain from bit 0, one shuffle per symbol: adv | len << 8 | stop << 16
+                    const uint32_t mine3 = (nb + ob) | (len << 8) | (stop ? 0x10000u : 0u);
+                    uint32_t M = 0, cur = 0, run = S.opos, before = 0;
                     while (cur < 32u) {
-                        const uint32_t a = __shfl_sync(FULL, adv, (int)cur);
-                        const bool sp = __shfl_sync(FULL, (int)stop, (int)cur) != 0;
-                        if (sp) break;
+                        const uint32_t v = __shfl_sync(FULL, mine3, (int)cur);
+                        const uint32_t l = (v >> 8) & 0xFFu;
+                        // an escape or an invalid code; the chunk's end; the room's end: the chain stops in front of it
+                        if ((v >> 16) || run >= XH_CHUNK || cap - run < l) break;
+                        if ((uint32_t)lane == cur) before = run;
                         M |= 1u << cur;
-                        cur += a;
+                        run += l;
+                        cur += v & 0xFFu;
                     }
-                    const bool mine = (M >> lane) & 1u;
-                    const uint32_t incl = (uint32_t)warp_incl_scan(mine ? (int)len : 0);
-                    const uint32_t before = S.opos + incl - (mine ? len : 0u);
-                    // the chunk ends, or the room: the chain stops in front of the first such symbol
-                    const unsigned late = __ballot_sync(FULL, mine && (before >= XH_CHUNK || cap - before < len));
-                    uint32_t used = cur;                                          // bits consumed
-                    if (late) {
-                        const int first = __ffs((int)late) - 1;
-                        M &= (1u << first) - 1u;
-                        used = (uint32_t)first;
-                    }
+                    const uint32_t used = cur;                                    // bits consumed
                     const bool on = (M >> lane) & 1u;
                     taken = (uint32_t)__popc(M);
                     if (taken) {
@@ -169,19 +166,19 @@ __device__ __forceinline__ void xhuff_parse_chunks_warp_body(const uint8_t* __re
                         if (on) t[S.nt + rank] = is_match ? lzt_match(off, len) : lzt_lit(sym);
                         const uint32_t r = (on && is_match && before < off) ? off - before : 0u;
                         S.rch = max(S.rch, __reduce_max_sync(FULL, r));
-                        const unsigned last = 31u - (uint32_t)__clz((int)M);
-                        S.opos = __shfl_sync(FULL, before + len, (int)last);
+                        S.opos = run;
                         S.nt += taken;
 #ifdef MSC_EMU
                         if (lane == 0) g_xhw_round_syms += taken;
 #endif
                         // the reader after `used` bits (Bitstream.h:59-70: a refill whenever fewer than 16 bits are left)
-                        int b = (int)R.bits - (int)used;
-                        uint32_t k = 0;
-                        while (b < 16) { b += 16; ++k; }
+                        const int b0 = (int)R.bits - (int)used;
+                        const uint32_t k = b0 >= 16 ? 0u : (uint32_t)(31 - b0) >> 4;
+                        const uint32_t b = (uint32_t)(b0 + 16 * (int)k);          // 16..31 (32 only for a round that consumed nothing)
                         R.ip += 2u * k;
-                        R.bits = (uint32_t)b;
-                        R.mask = (uint32_t)((W << used) >> 96) & (0xFFFFFFFFu << (32u - (uint32_t)b));
+                        R.bits = b;
+                        const unsigned long long Vn = used < 32u ? V0 << used : V1 << (used - 32u);
+                        R.mask = (uint32_t)(Vn >> 32) & (0xFFFFFFFFu << (32u - b));
                     }
                 }
                 if (!taken) {                                                    // one symbol the serial way
