@@ -740,7 +740,11 @@ MSCompStatus msc_xhuff_stream_decode(mscomp_gpu_ctx* ctx, const uint8_t* d_in, u
         uint32_t* h_nt = (uint32_t*)(h_slot + nch); uint32_t* h_pos = h_nt + nch;
         for (size_t j = 0; j < nch; ++j) { h_slot[j] = (uint64_t)chain[j] * XH_CHUNK; h_nt[j] = nt[j]; h_pos[j] = pos[j]; }
         cudaMemcpyAsync(d_ch, h_desc, cb, cudaMemcpyHostToDevice, ctx->stream);
-        if (independent) {                                                        // every chunk on its own warp
+        // Few chunks: pointer jumping even when no chunk reaches back -- a warp executing its chunk's ≈ 12,000 tokens in order takes
+        // as long as the parse, the order-free rounds use the whole GPU.  Many chunks fill the GPU by themselves with O(n) work.
+        const bool own_warps = independent && nch >= (size_t)ctx->sm_count * 8;
+        if (independent && !own_warps && produced <= 0x7FFFFFFFull && produce_by_jumping(ctx, (const uint32_t*)d_tok, d_ch, nch, (uint32_t)produced, d_out)) {
+        } else if (independent) {                                                 // every chunk on its own warp
             const uint32_t ab = ((uint32_t)nch + LZA_WARPS_PER_BLOCK - 1) / LZA_WARPS_PER_BLOCK, acap = (uint32_t)ctx->sm_count * 16;
             MSC_LAUNCH(ctx, xhs_apply_chunks_kernel, ab < acap ? ab : acap, 32 * LZA_WARPS_PER_BLOCK, (const uint32_t*)d_tok, (const uint64_t*)d_ch,
                        (const uint32_t*)(d_ch + nch * 8), (const uint32_t*)(d_ch + nch * 12), (uint32_t)nch, d_out);

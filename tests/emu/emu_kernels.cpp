@@ -257,7 +257,7 @@ uint32_t emu_xhuff_stream_decode(const uint8_t* in, uint32_t n, uint8_t* out, ui
         std::vector<uint64_t> slot(chain.size());
         std::vector<uint32_t> nt(chain.size());
         for (size_t j = 0; j < chain.size(); ++j) { slot[j] = (uint64_t)chain[j] * XH_CHUNK; nt[j] = ntok[chain[j]]; }
-        if (independent)
+        if (independent && g_chain_in_order)                       // (the product takes this branch for streams of many chunks; few chunks go by pointer jumping)
             emu::launch(xhs_apply_chunks_kernel, dim3e(2), dim3e(32 * LZA_WARPS_PER_BLOCK), (const uint32_t*)tok.data(), (const uint64_t*)slot.data(),
                         (const uint32_t*)nt.data(), (const uint32_t*)pos.data(), (uint32_t)chain.size(), out);
         else if (g_chain_in_order)

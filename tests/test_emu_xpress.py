@@ -309,8 +309,10 @@ def test_xhuff_chunk_parallel_stream_decode(emu, oracle, ms):
         # our own encoder: window reset per chunk -> independent chunks
         st, ol, outs = emu_batch(emu, "emu_xhuff_encode", [plain], [len(plain) + 34 + 258 + 258 * (len(plain) // 65536) + 16])
         assert not st.any()
-        handled, got, info = _emu_stream_decode(emu, outs[0], n)
-        assert handled == 1 and got == plain and (info >> 31) == 1, (kind, n, info)
+        for own_warps in (1, 0):                                     # every chunk on its own warp (many chunks) / pointer jumping (few chunks)
+            emu.emu_xhuff_stream_in_order(own_warps)
+            handled, got, info = _emu_stream_decode(emu, outs[0], n)
+            assert handled == 1 and got == plain and (info >> 31) == 1, (kind, n, info, own_warps)
         # too little room, a damaged table, a truncated stream: declined (the serial decoder reports those)
         assert _emu_stream_decode(emu, comp, n - 1)[0] == 0
         bad = bytearray(comp); bad[3] ^= 0x10
