@@ -45,7 +45,7 @@ def test_gather_sizes_world2_gloo(tmp_path):
         assert off == sum(100 + i for i in range(0, lo)), off
         assert sizes.tolist()[rank] == local
         dist.destroy_process_group()
-        print("rank", rank, "ok")
+        sys.stdout.write("rank " + str(rank) + " ok" + chr(10)); sys.stdout.flush()   # one write: the ranks share a pipe
     """ % ROOT))
     last = None
     for attempt in range(3):                    # (the port is chosen before torchrun binds it: retry if somebody else took it meanwhile)
