@@ -396,3 +396,40 @@ def test_xpress_speculative_stream_decode(emu, oracle, ms):
         assert not st.any()
         handled, got, _ = _emu_xpress_stream_decode(emu, outs[0], len(plain))
         assert handled == 1 and got == plain
+
+
+def test_xhuff_chunk_warp_parser_fuzz(emu, oracle, ms):
+    """The warp-per-chunk parser (xhuff_chunk_warp.cuh: speculation on the start bit, reader state from the bits consumed) against the oracle
+    on random inputs of several kinds and sizes, whole and damaged: a handled stream must be exactly what the oracle decodes."""
+    rnd = random.Random(2024)
+    emu.emu_xhuff_stream_in_order(0)
+    emu.emu_xhuff_stream_lane_parse(0)
+    taken = 0
+    for it in range(24):
+        kind = rnd.choice(["text", "runs", "random", "sym4", "mix", "rep"])
+        n = rnd.choice([700, 3000, 20000, 65536, 70000, 131072])
+        if kind in ("text", "runs", "random"):
+            plain = ms.generate(kind, n, rnd.randrange(1000))
+        elif kind == "sym4":
+            plain = bytes(rnd.randrange(4) for _ in range(n))
+        elif kind == "rep":
+            plain = (ms.generate("text", rnd.choice([5, 37, 300, 3000]), rnd.randrange(99)) * (n // 5 + 1))[:n]
+        else:
+            plain = b"".join(rnd.choice([ms.generate("text", 3000, rnd.randrange(99)), bytes(rnd.randrange(2000)),
+                                         bytes(rnd.getrandbits(8) for _ in range(500)), b"ab" * rnd.randrange(400)]) for _ in range(n // 2000 + 1))[:n]
+        n = len(plain)
+        comp = oracle.compress("xpress_huff", plain)
+        handled, got, info = _emu_stream_decode(emu, comp, n)
+        assert handled == 0 or got == plain, (kind, n, info)
+        taken += handled
+        for _ in range(2):
+            b = bytearray(comp)
+            if rnd.random() < 0.5:
+                b = b[:len(b) - rnd.randrange(1, 9)]
+            else:
+                for _ in range(rnd.randint(1, 3)):
+                    b[rnd.randrange(len(b))] ^= 1 << rnd.randrange(8)
+            cap = n + rnd.choice((0, 0, 64))
+            h2, g2, _ = _emu_stream_decode(emu, bytes(b), cap)
+            assert h2 == 0 or (0, g2) == oracle.decompress("xpress_huff", bytes(b), cap), (kind, n)
+    assert taken >= 18
