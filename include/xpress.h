@@ -2,8 +2,8 @@
  * xpress.h -- plain Xpress (LZ77, MS-XCA "LZ77" variant, format 3) one-shot API, B200-native.
  *
  * Replaces reference include/xpress.h:47-50 (implemented upstream in src/xpress_compress.cpp:240-347 and
- * src/xpress_decompress.cpp:405-462).  Our compressed bytes differ from the reference's where match choice
- * differs; they decode with the reference's xpress_decompress and vice versa.
+ * src/xpress_decompress.cpp:405-462).  xpress_compress writes the very bytes of the reference's encoder (its hash-chain
+ * parse is rebuilt position for position, csrc/kernels/lz_exact.cuh); streams of either library decode with the other.
  */
 #ifndef XPRESS_H
 #define XPRESS_H

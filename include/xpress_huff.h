@@ -2,9 +2,9 @@
  * xpress_huff.h -- Xpress-Huffman (MS-XCA "LZ77+Huffman", WIM, format 4) one-shot API, B200-native.
  *
  * Replaces reference include/xpress_huff.h:46-49 (implemented upstream in src/xpress_huff_compress.cpp:247-331
- * and src/xpress_huff_decompress.cpp:136-162).  Our compressed bytes differ from the reference's (different
- * match finder and code-length construction, per-64 KiB-chunk window); they decode with the reference's
- * xpress_huff_decompress and vice versa.
+ * and src/xpress_huff_decompress.cpp:136-162).  xpress_huff_compress writes the very bytes of the reference's encoder
+ * (its LZ77 tokens and the code lengths of HuffmanEncoder::CreateCodes, replayed tie for tie); streams of either library
+ * decode with the other.
  */
 #ifndef XPRESS_HUFF_H
 #define XPRESS_HUFF_H

@@ -522,8 +522,9 @@ extern "C" MSCompStatus xpress_huff_compress(const_bytes in, size_t in_len, byte
     const size_t cap = *out_len;
     mscomp_gpu_ctx* ctx = msc_thread_ctx();
     if (!ctx) return MSCOMP_MEM_ERROR;
-    // Every 64 KiB chunk is compressed on its own (window reset per chunk, valid for the reference's decoder:
-    // SURVEY.md 0.2) by its own thread block into a slot; the slots are then packed into one stream.
+    // Every 64 KiB chunk is encoded by its own thread block into a slot (eos_mode 1: the units are the chunks of ONE stream, so the
+    // reference-parse encoder sees the reference's tokens -- window 65,535 across chunk starts; the fast matcher resets the window per
+    // chunk, which the reference's decoder accepts as well: SURVEY.md 0.2); the slots are then packed into one stream.
     const size_t nunits = (in_len + 65535) / 65536;
     const size_t stride = 65536 + 256 + 64;
     uint8_t* d_in = (uint8_t*)ctx->get(SC_IN, in_len + 64);
